@@ -1,0 +1,230 @@
+/*
+ * sdmb200.h -- C ABI of libsdmb200.so, the B200-native (sm_100a) implementation of the
+ * Single-Decoupling / Alchemical-Transfer dual-state force path of
+ * rajatkrpal/openmm_sdm_plugin.
+ *
+ * Plain pointers and sizes only; no C++/torch/OpenMM types cross this boundary.  Every
+ * function returns SDM_OK (0) or a negative sdm_status; the message of the last failure on
+ * the calling thread is sdm_last_error().  Nothing throws across the boundary.  There is NO
+ * CPU fallback: without a CUDA device sdm_create() fails with SDM_ERR_NO_DEVICE.
+ *
+ * Two groups of entry points (citations are relative to the reference tree):
+ *
+ *  (A) the fused path -- replaces the whole force column of LangevinIntegratorSDM::step
+ *      (openmmapi/src/LangevinIntegratorSDM.cpp:156-182): the two
+ *      context->calcForcesAndEnergy(true,true,4) calls (:160,:168), SaveState1 / MakeState2 /
+ *      SaveState2 / RestoreState1 (:162-173, platforms/reference/src/ReferenceSDMKernels.cpp:
+ *      161-199) and the pre-integration half of execute() (:180,
+ *      ReferenceSDMKernels.cpp:202-318: soft-core, bias, PotEnergy/BindE, non-equilibrium
+ *      work, hybrid force).
+ *
+ *  (B) the literal kernel-interface operations -- one entry point per virtual of
+ *      SDMPlugin::IntegrateLangevinStepSDMKernel (openmmapi/include/SDMKernels.h:60-111) on
+ *      caller-owned DEVICE float4 buffers, for an OpenMM platform adapter that keeps using
+ *      OpenMM's own NonbondedForce (platforms/opencl/src/kernels/langevin.cl:72-87,147-206).
+ */
+#ifndef SDMB200_H_
+#define SDMB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDM_ABI_VERSION 1
+
+typedef enum {
+    SDM_OK = 0,
+    SDM_ERR_INVALID = -1,      /* bad argument (null pointer, index out of range, ...)      */
+    SDM_ERR_NO_DEVICE = -2,    /* no CUDA device / driver: there is no CPU fallback         */
+    SDM_ERR_CUDA = -3,         /* a CUDA runtime call failed; see sdm_last_error()          */
+    SDM_ERR_BOX = -4,          /* periodic box smaller than 2*cutoff (OpenMM throws there)  */
+    SDM_ERR_SOFTCORE = -5,     /* "Unknown soft core method" (LangevinIntegratorSDM.cpp:147)*/
+    SDM_ERR_STALE_LIST = -6,   /* an atom moved more than skin/2 since the list was built   */
+    SDM_ERR_CAPACITY = -7      /* internal list capacity exceeded (rebuilt larger on retry) */
+} sdm_status;
+
+/* NonbondedForce::NonbondedMethod as the reference's reader sets it
+ * (example/desmonddmsfile75.py:418-426). */
+#define SDM_NOCUTOFF 0
+#define SDM_CUTOFF_NONPERIODIC 1
+#define SDM_CUTOFF_PERIODIC 2
+
+/* LangevinIntegratorSDM.h:120-122 and :143-145 */
+#define SDM_BIAS_LINEAR 0
+#define SDM_BIAS_QUADRATIC 1
+#define SDM_BIAS_ILOGISTIC 2
+#define SDM_SOFTCORE_NONE 0
+#define SDM_SOFTCORE_TANH 1
+#define SDM_SOFTCORE_RATIONAL 2
+
+/* Which force array sdm_get_forces() returns. */
+#define SDM_FORCE_HYBRID 0     /* F  = F1 + sp*(F2-F1) + Fb  (ReferenceSDMKernels.cpp:309-318) */
+#define SDM_FORCE_STATE1 1     /* F1 = State1Forces                                            */
+#define SDM_FORCE_STATE2 2     /* F2 = State2Forces  (= F1 + dF)                               */
+#define SDM_FORCE_DELTA 3      /* dF = F2 - F1, accumulated over moved pairs only              */
+
+/* Pair-kernel selection (sdm_options.pair_mode). */
+#define SDM_PAIR_AUTO 0
+#define SDM_PAIR_ALLPAIRS 1    /* O(N^2) tile kernel, no list (small systems, cross-check)     */
+#define SDM_PAIR_CLUSTER 2     /* cell-sorted 8-atom clusters + cluster-pair list              */
+
+/* What reaches NonbondedForce in force group 2 (example/desmonddmsfile75.py:772-850) plus the
+ * displacement map (LangevinIntegratorSDM.h:467-472,508).  The map is SNAPSHOTTED here, like
+ * the reference does at initialize() (ReferenceSDMKernels.cpp:150-154); use
+ * sdm_set_displacement() to change it later (the reference needs Context::reinitialize). */
+typedef struct {
+    int32_t n_atoms;
+    int32_t method;                 /* SDM_NOCUTOFF / SDM_CUTOFF_NONPERIODIC / SDM_CUTOFF_PERIODIC */
+    double cutoff;                  /* nm */
+    double eps_rf;                  /* reaction-field dielectric, 78.3 is NonbondedForce's default */
+    double box[3];                  /* orthorhombic box edges (nm); ignored unless periodic */
+    int32_t use_dispersion_correction;
+    int32_t n_exclusions;           /* every addException pair, zero-parameter or not */
+    int32_t n_exceptions;           /* exceptions with chargeProd != 0 or epsilon != 0 (1-4) */
+    int32_t n_replicas;             /* lambda-replicas resident in this context (>= 1) */
+    const double* charge;           /* [n_atoms] e */
+    const double* sigma;            /* [n_atoms] nm */
+    const double* epsilon;          /* [n_atoms] kJ/mol */
+    const int32_t* exclusions;      /* [2*n_exclusions] System particle indices */
+    const int32_t* exceptions;      /* [2*n_exceptions] */
+    const double* exception_params; /* [3*n_exceptions] chargeProd (e^2), sigma (nm), epsilon (kJ/mol) */
+    const double* displacement;     /* [3*n_atoms] nm; NULL = all zero */
+} sdm_system;
+
+typedef struct {
+    int32_t device;                 /* CUDA device ordinal; -1 = current device */
+    int32_t pair_mode;              /* SDM_PAIR_* */
+    double skin;                    /* list buffer rlist - cutoff (nm); <0 = default 0.06 */
+    int32_t nstlist;                /* rebuild the cluster-pair list every nstlist evals; <=0 = default 20 */
+    int32_t exact_cutoff;           /* 1: re-test pairs within 1 ulp-band of the cutoff in FP64 so
+                                       the in-cutoff pair set is bit-identical to a double-precision
+                                       evaluation (default 1) */
+    int32_t reserved[8];
+} sdm_options;
+
+/* Scalar state of LangevinIntegratorSDM that execute() reads
+ * (ReferenceSDMKernels.cpp:205-258); field meaning and defaults as in the integrator's ctor
+ * (LangevinIntegratorSDM.cpp:48-85).  Units: kJ/mol, alpha in (kJ/mol)^-1, ps. */
+typedef struct {
+    int32_t bias_method;            /* SDM_BIAS_* */
+    int32_t softcore_method;        /* SDM_SOFTCORE_* */
+    double lambdac, gammac, wbcoeff, w0coeff;
+    double lambda1, lambda2, alpha, u0;
+    double umax, acore, ubcore;
+    int32_t nonequilibrium;         /* getNonEquilibrium() == 1 enables the lambda schedule */
+    int32_t pad_;
+    double noneq_tmax, work_value, time, step_size;
+    double m_lambda1, m_lambda2, m_u0, m_w0;   /* slopes     (set*Slope)     */
+    double b_lambda1, b_lambda2, b_u0, b_w0;   /* intercepts (set*intercept) */
+} sdm_alch;
+
+/* Everything execute() derives before it integrates. */
+typedef struct {
+    double E1, E2, Eb;              /* State1Energy, State2Energy (= E1 + u), RestraintEnergy */
+    double u;                       /* E2 - E1, accumulated over moved pairs only in FP64 */
+    double u_sc, fp;                /* SoftCoreF(u) and its derivative */
+    double ebias, bfp;              /* bias energy W(u_sc) and slope */
+    double sp;                      /* bfp*fp, the force-mixing coefficient */
+    double pot_energy;              /* E1 + ebias + Eb   -> integrator.setPotEnergy */
+    double bind_e;                  /* u_sc              -> integrator.setBindE     */
+    double E1_pair, E1_exc, E1_disp;/* decomposition of E1: pair sum, 1-4 exceptions, dispersion */
+    int64_t n_pairs1;               /* in-cutoff non-excluded pairs at state 1 */
+    int64_t n_moved1, n_moved2;     /* in-cutoff moved pairs (>=1 displaced atom, different
+                                       displacement) at state 1 / state 2 */
+    int32_t status;                 /* SDM_OK, SDM_ERR_SOFTCORE, SDM_ERR_STALE_LIST, ... */
+    int32_t list_age;               /* evals since the cluster-pair list was built */
+} sdm_scalars;
+
+typedef struct sdm_ctx sdm_ctx;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int sdm_abi_version(void);
+const char* sdm_last_error(void);
+int sdm_device_count(void);          /* 0 when there is no usable CUDA device */
+void sdm_default_options(sdm_options* opt);
+void sdm_default_alch(sdm_alch* alch);   /* LangevinIntegratorSDM ctor defaults */
+
+/* ---- (A) fused dual-state path ------------------------------------------------------------ */
+/* Replaces kernel.initialize(system, integrator) (ReferenceSDMKernels.cpp:144-159): copies all
+ * inputs (nothing is retained), uploads topology + displacement map, allocates per-replica
+ * state.  The handle is owned by the caller and freed with sdm_destroy(). */
+int sdm_create(const sdm_system* sys, const sdm_options* opt, sdm_ctx** out);
+void sdm_destroy(sdm_ctx* ctx);
+
+/* All work of a ctx is ordered on one CUDA stream (default: a stream the ctx owns).
+ * `cuda_stream` is a cudaStream_t / CUstream passed as void* (NULL = legacy default stream). */
+int sdm_set_stream(sdm_ctx* ctx, void* cuda_stream);
+int sdm_synchronize(sdm_ctx* ctx);
+
+/* Pinned host memory helpers for the end-to-end path (plain malloc'ed buffers also work,
+ * they are just slower to copy). */
+int sdm_host_alloc(void** ptr, uint64_t bytes);
+int sdm_host_free(void* ptr);
+
+/* Positions of one replica, [3*n_atoms] doubles in System particle order (Vec3 layout), nm.
+ * Host version copies asynchronously on the ctx stream; device version takes a device pointer. */
+int sdm_set_positions(sdm_ctx* ctx, int replica, const double* xyz);
+int sdm_set_positions_device(sdm_ctx* ctx, int replica, const double* d_xyz);
+/* Device address of the ctx-owned position buffer of a replica (for in-place integrators). */
+int sdm_positions_device_ptr(sdm_ctx* ctx, int replica, double** d_xyz);
+
+/* Result of the group-1 (bonded/restraint) evaluation the integrator does at :176: forces left
+ * in the force buffer and RestraintEnergy.  fb may be NULL (zero).  Host pointers. */
+int sdm_set_bonded_forces(sdm_ctx* ctx, int replica, const double* fb, double eb);
+
+int sdm_set_alchemical(sdm_ctx* ctx, int replica, const sdm_alch* alch);
+/* Reads back the state execute() writes into the integrator in non-equilibrium mode
+ * (lambda, lambda1, lambda2, u0, w0, work value, time).  Synchronises. */
+int sdm_get_alchemical(sdm_ctx* ctx, int replica, sdm_alch* alch);
+
+/* Replace the displacement map ([3*n_atoms], nm) -- what Context::reinitialize() would do. */
+int sdm_set_displacement(sdm_ctx* ctx, const double* displacement);
+
+/* One dual-state evaluation for every resident replica: E1, u, u_sc, W, sp, PotEnergy and the
+ * hybrid force, enqueued on the ctx stream; returns without synchronising. */
+int sdm_eval(sdm_ctx* ctx);
+/* Force a rebuild of the cluster-pair list at the next sdm_eval(). */
+int sdm_invalidate_list(sdm_ctx* ctx);
+
+int sdm_get_scalars(sdm_ctx* ctx, int replica, sdm_scalars* out);       /* synchronises */
+int sdm_get_forces(sdm_ctx* ctx, int replica, int which, double* out);  /* [3*n_atoms], synchronises */
+int sdm_forces_device_ptr(sdm_ctx* ctx, int replica, double** d_f);     /* hybrid force, device */
+/* Debug / parity: the sorted in-cutoff non-excluded (i<j) pair list the pair kernel evaluated at
+ * state 1, System particle indices.  pairs may be NULL to query *n only.  Synchronises. */
+int sdm_get_pairs(sdm_ctx* ctx, int replica, int32_t* pairs, int64_t max_pairs, int64_t* n);
+
+/* Launch statistics since creation (own kernels only) and device time of the last eval. */
+int sdm_get_launch_count(sdm_ctx* ctx, int64_t* n_launches);
+/* Device time (ms) spent in the pair kernel during the last sdm_eval() that had timing
+ * enabled; enable with sdm_set_timing(ctx, 1) (adds two cudaEventRecord per eval). */
+int sdm_set_timing(sdm_ctx* ctx, int enabled);
+int sdm_get_last_timing(sdm_ctx* ctx, float* pair_ms, float* total_ms);
+/* Algorithmic work of the last eval, summed over replicas: in-cutoff pairs evaluated. */
+int sdm_get_info(sdm_ctx* ctx, const char* key, double* value);
+
+/* ---- (B) literal kernel-interface operations on DEVICE float4 buffers --------------------- */
+/* MakeState2: posq[i] += displ[i]                   (langevin.cl:198-206) */
+int sdm_k_make_state2(void* cuda_stream, int n, void* posq, const void* displ);
+/* SaveState1: save_f = force, save_x = posq         (langevin.cl:161-178) */
+int sdm_k_save_state1(void* cuda_stream, int n, const void* posq, const void* force,
+                      void* save_f, void* save_x);
+/* SaveState2: save_f = force                        (langevin.cl:183-192) */
+int sdm_k_save_state2(void* cuda_stream, int n, const void* force, void* save_f);
+/* RestoreState1: posq = saved                       (langevin.cl:147-155) */
+int sdm_k_restore_state1(void* cuda_stream, int n, void* posq, const void* saved);
+/* sdmForce: force = (1-sp)*f1 + sp*f2 + force, all four lanes, sp as float
+ * (langevin.cl:72-87, OpenCLSDMKernels.cpp:273-275) */
+int sdm_k_hybrid_force(void* cuda_stream, int n, const void* f1, const void* f2, void* force,
+                       float sp);
+/* Scalar half of execute() (ReferenceSDMKernels.cpp:205-302): from E1, E2, Eb and the
+ * integrator state compute u_sc, fp, ebias, bfp, sp, PotEnergy, BindE and update the
+ * non-equilibrium state in *alch.  O(1) host arithmetic, exactly as the reference does it on
+ * the host for both of its platforms. */
+int sdm_execute_scalars(sdm_alch* alch, double E1, double E2, double Eb, sdm_scalars* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDMB200_H_ */

@@ -1,0 +1,201 @@
+"""SDMContext -- thin Python owner of an `sdm_ctx` handle (include/sdmb200.h).
+
+All arithmetic happens in libsdmb200.so on the GPU; this class only marshals numpy buffers
+through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import asdict
+
+import numpy as np
+
+from . import _lib
+from .system import AlchemicalState, NonbondedSystem
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def alch_to_c(a: AlchemicalState) -> _lib.SdmAlch:
+    c = _lib.SdmAlch()
+    for k, v in asdict(a).items():
+        setattr(c, k, v)
+    return c
+
+
+def alch_from_c(c: _lib.SdmAlch, a: AlchemicalState) -> AlchemicalState:
+    for k in asdict(a):
+        setattr(a, k, getattr(c, k))
+    return a
+
+
+class PinnedArray:
+    """A numpy view of cudaMallocHost memory (for the end-to-end path)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _lib.check(_lib.lib().sdm_host_alloc(C.byref(p), self.nbytes))
+        self._p = p
+        buf = (C.c_char * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            _lib.lib().sdm_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SDMContext:
+    def __init__(self, system: NonbondedSystem, displacement=None, n_replicas: int = 1,
+                 pair_mode: int = _lib.PAIR_AUTO, device: int = -1, skin: float = -1.0,
+                 nstlist: int = 0, exact_cutoff: bool = True):
+        L = _lib.lib()
+        self._L = L
+        self.system = system
+        self.n = system.n_atoms
+        self.R = int(n_replicas)
+        keep = [np.ascontiguousarray(system.charge, np.float64),
+                np.ascontiguousarray(system.sigma, np.float64),
+                np.ascontiguousarray(system.epsilon, np.float64),
+                np.ascontiguousarray(system.exclusions, np.int32),
+                np.ascontiguousarray(system.exception_pairs, np.int32),
+                np.ascontiguousarray(system.exception_params, np.float64),
+                None if displacement is None else np.ascontiguousarray(displacement, np.float64)]
+        if keep[6] is not None and keep[6].shape != (self.n, 3):
+            raise ValueError("displacement map must be [n_atoms, 3]")
+        s = _lib.SdmSystem()
+        s.n_atoms = self.n
+        s.method = int(system.method)
+        s.cutoff = float(system.cutoff)
+        s.eps_rf = float(system.eps_rf)
+        for d in range(3):
+            s.box[d] = float(system.box[d])
+        s.use_dispersion_correction = int(bool(system.use_dispersion_correction))
+        s.n_exclusions = len(keep[3])
+        s.n_exceptions = len(keep[4])
+        s.n_replicas = self.R
+        (s.charge, s.sigma, s.epsilon, s.exclusions, s.exceptions, s.exception_params,
+         s.displacement) = [_ptr(a) for a in keep]
+        o = _lib.SdmOptions()
+        L.sdm_default_options(C.byref(o))
+        o.device = device
+        o.pair_mode = pair_mode
+        o.skin = skin
+        o.nstlist = nstlist
+        o.exact_cutoff = int(exact_cutoff)
+        h = C.c_void_p()
+        _lib.check(L.sdm_create(C.byref(s), C.byref(o), C.byref(h)))
+        self._h = h
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.sdm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- inputs ---------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        _lib.check(self._L.sdm_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_positions(self, replica: int, xyz: np.ndarray):
+        a = np.ascontiguousarray(xyz, np.float64)
+        if a.size != 3 * self.n:
+            raise ValueError("positions must be [n_atoms, 3]")
+        _lib.check(self._L.sdm_set_positions(self._h, replica, _ptr(a)))
+        self._keep_pos = a  # async copy source must outlive the call
+
+    def set_positions_ptr(self, replica: int, host_ptr: int):
+        _lib.check(self._L.sdm_set_positions(self._h, replica, C.c_void_p(host_ptr)))
+
+    def set_bonded_forces(self, replica: int, fb, eb: float = 0.0):
+        a = None if fb is None else np.ascontiguousarray(fb, np.float64)
+        _lib.check(self._L.sdm_set_bonded_forces(self._h, replica, _ptr(a), float(eb)))
+        self._keep_fb = a
+
+    def set_alchemical(self, replica: int, alch: AlchemicalState):
+        c = alch_to_c(alch)
+        _lib.check(self._L.sdm_set_alchemical(self._h, replica, C.byref(c)))
+
+    def get_alchemical(self, replica: int, into: AlchemicalState | None = None) -> AlchemicalState:
+        c = _lib.SdmAlch()
+        _lib.check(self._L.sdm_get_alchemical(self._h, replica, C.byref(c)))
+        return alch_from_c(c, into if into is not None else AlchemicalState())
+
+    def set_displacement(self, displacement):
+        a = np.ascontiguousarray(displacement, np.float64)
+        if a.shape != (self.n, 3):
+            raise ValueError("displacement map must be [n_atoms, 3]")
+        _lib.check(self._L.sdm_set_displacement(self._h, _ptr(a)))
+
+    # -- evaluation -----------------------------------------------------------------------
+    def eval(self):
+        _lib.check(self._L.sdm_eval(self._h))
+
+    def synchronize(self):
+        _lib.check(self._L.sdm_synchronize(self._h))
+
+    def invalidate_list(self):
+        _lib.check(self._L.sdm_invalidate_list(self._h))
+
+    def scalars(self, replica: int = 0) -> dict:
+        sc = _lib.SdmScalars()
+        _lib.check(self._L.sdm_get_scalars(self._h, replica, C.byref(sc)))
+        return {k: getattr(sc, k) for k, _ in _lib.SdmScalars._fields_}
+
+    def forces(self, replica: int = 0, which: int = _lib.FORCE_HYBRID, out=None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n, 3))
+        _lib.check(self._L.sdm_get_forces(self._h, replica, which, _ptr(out)))
+        return out
+
+    def forces_into_ptr(self, replica: int, host_ptr: int, which: int = _lib.FORCE_HYBRID):
+        _lib.check(self._L.sdm_get_forces(self._h, replica, which, C.c_void_p(host_ptr)))
+
+    def pairs(self, replica: int = 0) -> np.ndarray:
+        n = C.c_int64()
+        _lib.check(self._L.sdm_get_pairs(self._h, replica, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 2), np.int32)
+        if n.value:
+            _lib.check(self._L.sdm_get_pairs(self._h, replica, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    # -- introspection --------------------------------------------------------------------
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _lib.check(self._L.sdm_get_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def set_timing(self, enabled: bool):
+        _lib.check(self._L.sdm_set_timing(self._h, int(enabled)))
+
+    def last_timing(self):
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self._L.sdm_get_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def info(self, key: str) -> float:
+        v = C.c_double()
+        _lib.check(self._L.sdm_get_info(self._h, key.encode(), C.byref(v)))
+        return v.value

@@ -1,0 +1,657 @@
+// api.cu -- the C ABI of libsdmb200.so (include/sdmb200.h).  Host orchestration only: owns the
+// device buffers of a context, orders the sm_100a kernels on one stream, never computes a
+// pair interaction or a force on the CPU.
+#include <algorithm>
+#include <array>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "sdm_ctx.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define SDM_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                     \
+            return fail(SDM_ERR_CUDA, buf_);                                                  \
+        }                                                                                     \
+    } while (0)
+
+template <class T>
+int dev_alloc(sdm_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    SDM_CUDA(cudaMalloc(&q, bytes));
+    SDM_CUDA(cudaMemset(q, 0, bytes));
+    c->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return SDM_OK;
+}
+
+template <class T>
+int dev_upload(sdm_ctx* c, const T** p, const std::vector<T>& v) {
+    T* q = nullptr;
+    int rc = dev_alloc(c, &q, v.size());
+    if (rc) return rc;
+    if (!v.empty()) SDM_CUDA(cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *p = q;
+    return SDM_OK;
+}
+
+// OpenMM 7.3 NonbondedForceImpl::calcDispersionCorrection without a switching function
+// (SURVEY.md Appendix B.4).  O(classes^2) host arithmetic done once at creation.
+double dispersion_coefficient(const sdm_system* s) {
+    if (s->method != SDM_CUTOFF_PERIODIC) return 0.0;
+    std::map<std::pair<double, double>, int> classes;
+    for (int i = 0; i < s->n_atoms; i++) classes[{s->sigma[i], s->epsilon[i]}]++;
+    double sum1 = 0, sum2 = 0;
+    for (auto& c : classes) {
+        double sigma = c.first.first, eps = c.first.second, count = (double)c.second;
+        count *= (count + 1) / 2;
+        double s2 = sigma * sigma, s6 = s2 * s2 * s2;
+        sum1 += count * eps * s6 * s6;
+        sum2 += count * eps * s6;
+    }
+    for (auto a = classes.begin(); a != classes.end(); ++a)
+        for (auto b = classes.begin(); b != a; ++b) {
+            double sigma = 0.5 * (a->first.first + b->first.first);
+            double eps = std::sqrt(a->first.second * b->first.second);
+            double count = (double)a->second * (double)b->second;
+            double s2 = sigma * sigma, s6 = s2 * s2 * s2;
+            sum1 += count * eps * s6 * s6;
+            sum2 += count * eps * s6;
+        }
+    double np = (double)s->n_atoms, ni = np * (np + 1) / 2;
+    sum1 /= ni;
+    sum2 /= ni;
+    double rc = s->cutoff;
+    return 8 * np * np * M_PI * (sum1 / (9 * std::pow(rc, 9)) - sum2 / (3 * std::pow(rc, 3)));
+}
+
+int upload_displacement(sdm_ctx* c, const double* displacement) {
+    const int n = c->n;
+    std::vector<double> disp(3 * (size_t)n, 0.0);
+    if (displacement) std::copy(displacement, displacement + 3 * (size_t)n, disp.begin());
+    std::map<std::array<double, 3>, int> ids;
+    ids[{0.0, 0.0, 0.0}] = 0;
+    std::vector<int> group(n, 0), lig;
+    for (int i = 0; i < n; i++) {
+        std::array<double, 3> d = {disp[3 * i], disp[3 * i + 1], disp[3 * i + 2]};
+        // -0.0 and +0.0 displace identically
+        for (auto& v : d) if (v == 0.0) v = 0.0;
+        auto it = ids.find(d);
+        int g;
+        if (it == ids.end()) { g = (int)ids.size(); ids[d] = g; } else g = it->second;
+        group[i] = g;
+        if (g != 0) lig.push_back(i);
+    }
+    SDM_CUDA(cudaMemcpy(c->d_disp, disp.data(), disp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SDM_CUDA(cudaMemcpy(c->d_group, group.data(), group.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!lig.empty())
+        SDM_CUDA(cudaMemcpy(c->d_lig_idx, lig.data(), lig.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->T.n_lig = (int)lig.size();
+    c->h_group = group;
+    c->h_lig = lig;
+    return SDM_OK;
+}
+
+int check_ctx(sdm_ctx* c, int replica) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (replica < 0 || replica >= c->R) return fail(SDM_ERR_INVALID, "replica index out of range");
+    return SDM_OK;
+}
+
+}  // namespace
+
+int sdm_fail(int code, const char* msg) { return fail(code, msg); }
+
+extern "C" {
+
+int sdm_abi_version(void) { return SDM_ABI_VERSION; }
+
+const char* sdm_last_error(void) { return g_last_error.c_str(); }
+
+int sdm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void sdm_default_options(sdm_options* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->device = -1;
+    o->pair_mode = SDM_PAIR_AUTO;
+    o->skin = 0.06;
+    o->nstlist = 20;
+    o->exact_cutoff = 1;
+}
+
+void sdm_default_alch(sdm_alch* a) {
+    if (!a) return;
+    std::memset(a, 0, sizeof(*a));
+    // LangevinIntegratorSDM ctor (openmmapi/src/LangevinIntegratorSDM.cpp:48-85)
+    a->bias_method = SDM_BIAS_LINEAR;
+    a->softcore_method = SDM_SOFTCORE_NONE;
+    a->lambdac = 1.0;
+    a->gammac = 0.0;
+    a->wbcoeff = 1.0;
+    a->w0coeff = 0.0;
+    a->lambda1 = 1.0;
+    a->lambda2 = 1.0;
+    a->alpha = 1.0;
+    a->u0 = 0.0;
+    a->umax = 200.0;
+    a->acore = 0.25;
+    a->ubcore = 0.0;
+    a->nonequilibrium = 0;
+    a->noneq_tmax = 1.0;
+    a->step_size = 0.001;
+}
+
+int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
+    if (!s || !out) return fail(SDM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (s->n_atoms <= 0) return fail(SDM_ERR_INVALID, "n_atoms must be positive");
+    if (s->n_replicas < 1) return fail(SDM_ERR_INVALID, "n_replicas must be >= 1");
+    if (!s->charge || !s->sigma || !s->epsilon) return fail(SDM_ERR_INVALID, "null parameter array");
+    if (s->method < SDM_NOCUTOFF || s->method > SDM_CUTOFF_PERIODIC)
+        return fail(SDM_ERR_INVALID, "unknown nonbonded method");
+    if (s->method != SDM_NOCUTOFF && !(s->cutoff > 0)) return fail(SDM_ERR_INVALID, "cutoff must be positive");
+    if (s->method == SDM_CUTOFF_PERIODIC)
+        for (int d = 0; d < 3; d++)
+            if (!(s->box[d] > 0) || 2 * s->cutoff > s->box[d])
+                return fail(SDM_ERR_BOX, "The cutoff distance cannot be greater than half the periodic box size");
+    if ((s->n_exclusions > 0 && !s->exclusions) || (s->n_exceptions > 0 && (!s->exceptions || !s->exception_params)))
+        return fail(SDM_ERR_INVALID, "null exclusion/exception array");
+    if (sdm_device_count() <= 0)
+        return fail(SDM_ERR_NO_DEVICE, "no CUDA device available: libsdmb200 has no CPU fallback");
+
+    sdm_options opt;
+    sdm_default_options(&opt);
+    if (opt_in) {
+        opt = *opt_in;
+        if (opt.skin < 0) opt.skin = 0.06;
+        if (opt.nstlist <= 0) opt.nstlist = 20;
+    }
+    if (opt.device >= 0) SDM_CUDA(cudaSetDevice(opt.device));
+    int dev = 0;
+    SDM_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SDM_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(SDM_ERR_NO_DEVICE, "libsdmb200 is built for sm_100a (B200) only");
+
+    sdm_ctx* c = new sdm_ctx();
+    c->device = dev;
+    c->opt = opt;
+    c->n = s->n_atoms;
+    c->R = s->n_replicas;
+    c->num_sms = prop.multiProcessorCount;
+    const int n = c->n, R = c->R;
+    int rc = SDM_OK;
+#define TRY(x) do { rc = (x); if (rc) { sdm_destroy(c); return rc; } } while (0)
+#define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::string m_ = std::string(#x) + ": " + cudaGetErrorString(e_); sdm_destroy(c); return fail(SDM_ERR_CUDA, m_); } } while (0)
+
+    TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (int k = 0; k < 4; k++) TRYCUDA(cudaEventCreate(&c->ev[k]));
+
+    sdm::Topology& T = c->T;
+    std::memset(&T, 0, sizeof(T));
+    T.n = n;
+    T.method = s->method;
+    T.n_exceptions = s->n_exceptions;
+    T.rc = s->method == SDM_NOCUTOFF ? 0.0 : s->cutoff;
+    T.rc2 = T.rc * T.rc;
+    if (s->method != SDM_NOCUTOFF) {
+        T.krf = std::pow(T.rc, -3.0) * (s->eps_rf - 1.0) / (2.0 * s->eps_rf + 1.0);
+        T.crf = (1.0 / T.rc) * (3.0 * s->eps_rf) / (2.0 * s->eps_rf + 1.0);
+    }
+    double cmax = 64.0;  // coordinate magnitude bound used for the FP64 re-test band
+    for (int d = 0; d < 3; d++) {
+        T.box[d] = s->method == SDM_CUTOFF_PERIODIC ? s->box[d] : 0.0;
+        T.inv_box[d] = T.box[d] > 0 ? 1.0 / T.box[d] : 0.0;
+        T.boxf[d] = (float)T.box[d];
+        T.inv_boxf[d] = (float)T.inv_box[d];
+    }
+    if (s->method == SDM_CUTOFF_PERIODIC) cmax = std::max({T.box[0], T.box[1], T.box[2]});
+    T.rc2f = (float)T.rc2;
+    T.krff = (float)T.krf;
+    T.crff = (float)T.crf;
+    T.band = (float)(64.0 * FLT_EPSILON * T.rc * std::max(cmax, T.rc));
+    if (s->method == SDM_CUTOFF_PERIODIC && s->use_dispersion_correction)
+        T.e_disp = dispersion_coefficient(s) / (s->box[0] * s->box[1] * s->box[2]);
+
+    // per-atom parameters as the Reference kernel stores them: sigma/2, 2*sqrt(eps)
+    std::vector<double> q(n), hsig(n), heps(n);
+    std::vector<float4> parf(n);
+    const double sqrtK = std::sqrt(SDM_K_COULOMB);
+    for (int i = 0; i < n; i++) {
+        q[i] = s->charge[i];
+        hsig[i] = 0.5 * s->sigma[i];
+        heps[i] = 2.0 * std::sqrt(s->epsilon[i]);
+        parf[i] = make_float4((float)(q[i] * sqrtK), (float)hsig[i], (float)heps[i], 0.f);
+    }
+    TRY(dev_upload(c, &T.q, q));
+    TRY(dev_upload(c, &T.hsig, hsig));
+    TRY(dev_upload(c, &T.heps, heps));
+    TRY(dev_upload(c, &T.parf, parf));
+
+    // exclusions -> CSR over both directions, rows ascending, no self, no duplicates
+    {
+        std::vector<std::vector<int>> rows(n);
+        for (int k = 0; k < s->n_exclusions; k++) {
+            int a = s->exclusions[2 * k], b = s->exclusions[2 * k + 1];
+            if (a < 0 || b < 0 || a >= n || b >= n) { sdm_destroy(c); return fail(SDM_ERR_INVALID, "exclusion index out of range"); }
+            if (a == b) continue;
+            rows[a].push_back(b);
+            rows[b].push_back(a);
+        }
+        std::vector<int> start(n + 1, 0), idx;
+        for (int i = 0; i < n; i++) {
+            std::sort(rows[i].begin(), rows[i].end());
+            rows[i].erase(std::unique(rows[i].begin(), rows[i].end()), rows[i].end());
+            start[i + 1] = start[i] + (int)rows[i].size();
+            idx.insert(idx.end(), rows[i].begin(), rows[i].end());
+        }
+        TRY(dev_upload(c, &T.excl_start, start));
+        TRY(dev_upload(c, &T.excl_idx, idx));
+        c->h_excl_start = start;
+        c->h_excl_idx = idx;
+    }
+    {
+        std::vector<int> ep(s->exceptions, s->exceptions + 2 * (size_t)s->n_exceptions);
+        for (int v : ep)
+            if (v < 0 || v >= n) { sdm_destroy(c); return fail(SDM_ERR_INVALID, "exception index out of range"); }
+        std::vector<double> pp(s->exception_params, s->exception_params + 3 * (size_t)s->n_exceptions);
+        TRY(dev_upload(c, &T.exc_pairs, ep));
+        TRY(dev_upload(c, &T.exc_params, pp));
+    }
+    TRY(dev_alloc(c, &c->d_disp, 3 * (size_t)n));
+    TRY(dev_alloc(c, &c->d_group, (size_t)n));
+    TRY(dev_alloc(c, &c->d_lig_idx, (size_t)n));
+    T.disp = c->d_disp;
+    T.group = c->d_group;
+    T.lig_idx = c->d_lig_idx;
+    TRY(upload_displacement(c, s->displacement));
+
+    // per-replica buffers
+    sdm::EvalBuffers& B = c->B;
+    std::memset(&B, 0, sizeof(B));
+    B.R = R;
+    B.n_epart = sdm::allpairs_num_blocks(n);
+    B.n_excpart = sdm::exceptions_num_blocks(s->n_exceptions);
+    B.nslot = n;
+    B.slot_of = nullptr;
+    double *pos, *fb;
+    TRY(dev_alloc(c, &pos, (size_t)R * 3 * n));
+    TRY(dev_alloc(c, &fb, (size_t)R * 3 * n));
+    B.pos = pos;
+    B.fb = fb;
+    c->d_pos = pos;
+    c->d_fb = fb;
+    TRY(dev_alloc(c, &B.posq, (size_t)R * n));
+    TRY(dev_alloc(c, &B.f1acc, (size_t)R * 3 * B.nslot));
+    TRY(dev_alloc(c, &B.dF, (size_t)R * 3 * n));
+    TRY(dev_alloc(c, &B.F, (size_t)R * 3 * n));
+    TRY(dev_alloc(c, &B.F1, (size_t)R * 3 * n));
+    TRY(dev_alloc(c, &B.epart, (size_t)R * B.n_epart));
+    TRY(dev_alloc(c, &B.cpart, (size_t)R * B.n_epart));
+    TRY(dev_alloc(c, &B.eexc_part, (size_t)R * B.n_excpart));
+    TRY(dev_alloc(c, &B.uexc_part, (size_t)R * B.n_excpart));
+    TRY(dev_alloc(c, &B.upart, (size_t)R * n));
+    TRY(dev_alloc(c, &B.mcnt, (size_t)R * n * 2));
+    TRY(dev_alloc(c, &B.state, (size_t)R));
+    TRY(dev_alloc(c, &B.flags, (size_t)R));
+
+    c->h_alch.resize(R);
+    c->h_eb.assign(R, 0.0);
+    for (int r = 0; r < R; r++) {
+        sdm_default_alch(&c->h_alch[r]);
+        TRYCUDA(cudaMemcpy(&B.state[r].alch, &c->h_alch[r], sizeof(sdm_alch), cudaMemcpyHostToDevice));
+    }
+    TRYCUDA(cudaMallocHost((void**)&c->h_state, sizeof(sdm::ReplicaState) * (size_t)R));
+
+    c->pair_mode = opt.pair_mode == SDM_PAIR_AUTO ? SDM_PAIR_ALLPAIRS : opt.pair_mode;
+    TRY(sdm_ctx_init_pairlist(c));
+#undef TRY
+#undef TRYCUDA
+    *out = c;
+    return SDM_OK;
+}
+
+void sdm_destroy(sdm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    sdm_ctx_free_pairlist(c);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    for (int k = 0; k < 4; k++)
+        if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int sdm_set_stream(sdm_ctx* c, void* cuda_stream) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) SDM_CUDA(cudaStreamDestroy(c->stream));
+    c->own_stream = false;
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    return SDM_OK;
+}
+
+int sdm_synchronize(sdm_ctx* c) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    return SDM_OK;
+}
+
+int sdm_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return fail(SDM_ERR_INVALID, "null argument");
+    SDM_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return SDM_OK;
+}
+
+int sdm_host_free(void* ptr) {
+    if (ptr) SDM_CUDA(cudaFreeHost(ptr));
+    return SDM_OK;
+}
+
+int sdm_set_positions(sdm_ctx* c, int replica, const double* xyz) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!xyz) return fail(SDM_ERR_INVALID, "null positions");
+    SDM_CUDA(cudaMemcpyAsync(c->d_pos + (size_t)replica * 3 * c->n, xyz, sizeof(double) * 3 * (size_t)c->n,
+                             cudaMemcpyHostToDevice, c->stream));
+    return SDM_OK;
+}
+
+int sdm_set_positions_device(sdm_ctx* c, int replica, const double* d_xyz) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!d_xyz) return fail(SDM_ERR_INVALID, "null positions");
+    SDM_CUDA(cudaMemcpyAsync(c->d_pos + (size_t)replica * 3 * c->n, d_xyz, sizeof(double) * 3 * (size_t)c->n,
+                             cudaMemcpyDeviceToDevice, c->stream));
+    return SDM_OK;
+}
+
+int sdm_positions_device_ptr(sdm_ctx* c, int replica, double** d_xyz) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!d_xyz) return fail(SDM_ERR_INVALID, "null argument");
+    *d_xyz = c->d_pos + (size_t)replica * 3 * c->n;
+    return SDM_OK;
+}
+
+int sdm_set_bonded_forces(sdm_ctx* c, int replica, const double* fb, double eb) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    double* dst = c->d_fb + (size_t)replica * 3 * c->n;
+    if (fb)
+        SDM_CUDA(cudaMemcpyAsync(dst, fb, sizeof(double) * 3 * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    else
+        SDM_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * 3 * (size_t)c->n, c->stream));
+    c->h_eb[replica] = eb;
+    SDM_CUDA(cudaMemcpyAsync(&c->B.state[replica].sc.Eb, &c->h_eb[replica], sizeof(double),
+                             cudaMemcpyHostToDevice, c->stream));
+    return SDM_OK;
+}
+
+int sdm_set_alchemical(sdm_ctx* c, int replica, const sdm_alch* a) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!a) return fail(SDM_ERR_INVALID, "null argument");
+    c->h_alch[replica] = *a;
+    SDM_CUDA(cudaMemcpyAsync(&c->B.state[replica].alch, &c->h_alch[replica], sizeof(sdm_alch),
+                             cudaMemcpyHostToDevice, c->stream));
+    return SDM_OK;
+}
+
+int sdm_get_alchemical(sdm_ctx* c, int replica, sdm_alch* a) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!a) return fail(SDM_ERR_INVALID, "null argument");
+    SDM_CUDA(cudaMemcpyAsync(&c->h_state[replica].alch, &c->B.state[replica].alch, sizeof(sdm_alch),
+                             cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    *a = c->h_state[replica].alch;
+    c->h_alch[replica] = *a;
+    return SDM_OK;
+}
+
+int sdm_set_displacement(sdm_ctx* c, const double* displacement) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    if (int rc = upload_displacement(c, displacement)) return rc;
+    return SDM_OK;
+}
+
+int sdm_invalidate_list(sdm_ctx* c) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    c->list_valid = false;
+    return SDM_OK;
+}
+
+int sdm_eval(sdm_ctx* c) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    cudaStream_t s = c->stream;
+    const sdm::Topology& T = c->T;
+    sdm::EvalBuffers& B = c->B;
+    if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[0], s));
+    double e_scale = 1.0;
+    int c_div = 1, zero_acc = 0;
+    if (c->pair_mode == SDM_PAIR_ALLPAIRS) {
+        sdm::launch_prep_posq(T, B, s);
+        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[1], s));
+        sdm::launch_allpairs(T, B, c->opt.exact_cutoff, nullptr, nullptr, 0, -1, s);
+        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[2], s));
+        c->launches += 2;
+        e_scale = 0.5;
+        c_div = 2;
+    } else {
+        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[1], s));
+        if (int rc = sdm_ctx_pairlist_eval(c)) return rc;
+        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[2], s));
+        zero_acc = 1;
+    }
+    if (T.n_lig > 0) { sdm::launch_ligand_probe(T, B, s); c->launches++; }
+    sdm::launch_ligand_env(T, B, s);
+    sdm::launch_exceptions(T, B, s);
+    sdm::launch_scalars(T, B, e_scale, c_div, c->list_age, s);
+    sdm::launch_mix(T, B, zero_acc, s);
+    c->launches += 4;
+    if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timing_valid = c->timing;
+    SDM_CUDA(cudaGetLastError());
+    c->n_evals++;
+    return SDM_OK;
+}
+
+int sdm_get_scalars(sdm_ctx* c, int replica, sdm_scalars* out) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!out) return fail(SDM_ERR_INVALID, "null argument");
+    SDM_CUDA(cudaMemcpyAsync(&c->h_state[replica].sc, &c->B.state[replica].sc, sizeof(sdm_scalars),
+                             cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c->h_state[replica].sc;
+    return SDM_OK;
+}
+
+int sdm_get_forces(sdm_ctx* c, int replica, int which, double* out) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!out) return fail(SDM_ERR_INVALID, "null argument");
+    const size_t n3 = 3 * (size_t)c->n, off = (size_t)replica * n3;
+    const double* src = nullptr;
+    switch (which) {
+        case SDM_FORCE_HYBRID: src = c->B.F + off; break;
+        case SDM_FORCE_STATE1: src = c->B.F1 + off; break;
+        case SDM_FORCE_DELTA: src = c->B.dF + off; break;
+        case SDM_FORCE_STATE2: src = c->B.F1 + off; break;
+        default: return fail(SDM_ERR_INVALID, "unknown force selector");
+    }
+    SDM_CUDA(cudaMemcpyAsync(out, src, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    if (which == SDM_FORCE_STATE2) {
+        std::vector<double> d(n3);
+        SDM_CUDA(cudaMemcpy(d.data(), c->B.dF + off, sizeof(double) * n3, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < n3; k++) out[k] += d[k];  // debug accessor: F2 = F1 + dF
+    }
+    return SDM_OK;
+}
+
+int sdm_forces_device_ptr(sdm_ctx* c, int replica, double** d_f) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!d_f) return fail(SDM_ERR_INVALID, "null argument");
+    *d_f = c->B.F + (size_t)replica * 3 * c->n;
+    return SDM_OK;
+}
+
+int sdm_get_pairs(sdm_ctx* c, int replica, int32_t* pairs, int64_t max_pairs, int64_t* n_out) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!n_out) return fail(SDM_ERR_INVALID, "null argument");
+    cudaStream_t s = c->stream;
+    int* d_counter = nullptr;
+    SDM_CUDA(cudaMalloc((void**)&d_counter, sizeof(int)));
+    int h_count = 0;
+    int* d_pairs = nullptr;
+    int cap = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        SDM_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), s));
+        int rc = SDM_OK;
+        if (c->pair_mode == SDM_PAIR_ALLPAIRS) {
+            sdm::launch_prep_posq(c->T, c->B, s);
+            // emit_pairs must be non-null to enable emission; capacity 0 only counts
+            sdm::launch_allpairs(c->T, c->B, c->opt.exact_cutoff, d_counter,
+                                 d_pairs ? d_pairs : d_counter, cap, replica, s);
+        } else {
+            rc = sdm_ctx_pairlist_emit(c, replica, d_counter, d_pairs ? d_pairs : d_counter, cap);
+        }
+        if (rc) { cudaFree(d_counter); if (d_pairs) cudaFree(d_pairs); return rc; }
+        SDM_CUDA(cudaMemcpyAsync(&h_count, d_counter, sizeof(int), cudaMemcpyDeviceToHost, s));
+        SDM_CUDA(cudaStreamSynchronize(s));
+        if (pass == 0) {
+            if (!pairs || h_count == 0) break;
+            cap = h_count;
+            SDM_CUDA(cudaMalloc((void**)&d_pairs, sizeof(int) * 2 * (size_t)cap));
+        }
+    }
+    *n_out = h_count;
+    if (pairs && d_pairs) {
+        std::vector<std::pair<int, int>> v((size_t)h_count);
+        SDM_CUDA(cudaMemcpy(v.data(), d_pairs, sizeof(int) * 2 * (size_t)h_count, cudaMemcpyDeviceToHost));
+        std::sort(v.begin(), v.end());
+        int64_t m = std::min<int64_t>(h_count, max_pairs);
+        for (int64_t k = 0; k < m; k++) { pairs[2 * k] = v[k].first; pairs[2 * k + 1] = v[k].second; }
+    }
+    cudaFree(d_counter);
+    if (d_pairs) cudaFree(d_pairs);
+    return SDM_OK;
+}
+
+int sdm_get_launch_count(sdm_ctx* c, int64_t* n) {
+    if (!c || !n) return fail(SDM_ERR_INVALID, "null argument");
+    *n = c->launches;
+    return SDM_OK;
+}
+
+int sdm_set_timing(sdm_ctx* c, int enabled) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    c->timing = enabled != 0;
+    c->timing_valid = false;
+    return SDM_OK;
+}
+
+int sdm_get_last_timing(sdm_ctx* c, float* pair_ms, float* total_ms) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (!c->timing_valid) return fail(SDM_ERR_INVALID, "timing not enabled for the last eval");
+    SDM_CUDA(cudaEventSynchronize(c->ev[3]));
+    float a = 0, b = 0;
+    SDM_CUDA(cudaEventElapsedTime(&a, c->ev[1], c->ev[2]));
+    SDM_CUDA(cudaEventElapsedTime(&b, c->ev[0], c->ev[3]));
+    if (pair_ms) *pair_ms = a;
+    if (total_ms) *total_ms = b;
+    return SDM_OK;
+}
+
+int sdm_get_info(sdm_ctx* c, const char* key, double* value) {
+    if (!c || !key || !value) return fail(SDM_ERR_INVALID, "null argument");
+    std::string k(key);
+    if (k == "n_atoms") *value = c->n;
+    else if (k == "n_replicas") *value = c->R;
+    else if (k == "n_displaced") *value = c->T.n_lig;
+    else if (k == "pair_mode") *value = c->pair_mode;
+    else if (k == "n_evals") *value = (double)c->n_evals;
+    else if (k == "n_list_builds") *value = (double)c->n_builds;
+    else if (k == "e_dispersion") *value = c->T.e_disp;
+    else if (k == "num_sms") *value = c->num_sms;
+    else if (sdm_ctx_pairlist_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
+    else return fail(SDM_ERR_INVALID, "unknown info key: " + k);
+    return SDM_OK;
+}
+
+// ---- (B) literal kernel-interface operations ---------------------------------------------------
+int sdm_k_make_state2(void* stream, int n, void* posq, const void* displ) {
+    if (n < 0 || (n > 0 && (!posq || !displ))) return fail(SDM_ERR_INVALID, "bad argument");
+    sdm::launch_make_state2(n, (float4*)posq, (const float4*)displ, (cudaStream_t)stream);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_k_save_state1(void* stream, int n, const void* posq, const void* force, void* save_f, void* save_x) {
+    if (n < 0 || (n > 0 && (!posq || !force || !save_f || !save_x))) return fail(SDM_ERR_INVALID, "bad argument");
+    sdm::launch_save_state1(n, (const float4*)posq, (const float4*)force, (float4*)save_f, (float4*)save_x,
+                            (cudaStream_t)stream);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_k_save_state2(void* stream, int n, const void* force, void* save_f) {
+    if (n < 0 || (n > 0 && (!force || !save_f))) return fail(SDM_ERR_INVALID, "bad argument");
+    sdm::launch_copy4(n, (const float4*)force, (float4*)save_f, (cudaStream_t)stream);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_k_restore_state1(void* stream, int n, void* posq, const void* saved) {
+    if (n < 0 || (n > 0 && (!posq || !saved))) return fail(SDM_ERR_INVALID, "bad argument");
+    sdm::launch_copy4(n, (const float4*)saved, (float4*)posq, (cudaStream_t)stream);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_k_hybrid_force(void* stream, int n, const void* f1, const void* f2, void* force, float sp) {
+    if (n < 0 || (n > 0 && (!f1 || !f2 || !force))) return fail(SDM_ERR_INVALID, "bad argument");
+    sdm::launch_hybrid_force(n, (const float4*)f1, (const float4*)f2, (float4*)force, sp, (cudaStream_t)stream);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_execute_scalars(sdm_alch* alch, double E1, double E2, double Eb, sdm_scalars* out) {
+    if (!alch || !out) return fail(SDM_ERR_INVALID, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    out->E1 = E1;
+    out->E2 = E2;
+    out->Eb = Eb;
+    out->u = E2 - E1;
+    sdm::execute_scalars(alch, out);
+    if (out->status == SDM_ERR_SOFTCORE) return fail(SDM_ERR_SOFTCORE, "Unknown soft core method");
+    return SDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// kernels_elementwise.cu -- the literal kernel-interface operations of
+// SDMPlugin::IntegrateLangevinStepSDMKernel on device float4 buffers (sm_100a).
+//
+// Behaviour restated from platforms/opencl/src/kernels/langevin.cl:72-87 (sdmForce),
+// :147-155 (RestoreState1), :161-178 (SaveState1), :183-192 (SaveState2), :198-206
+// (MakeState2).  These are HBM-bound streaming kernels: 128-bit accesses, four independent
+// loads in flight per thread, grid sized in multiples of the SM count, no shared memory
+// (there is no reuse), streaming cache hints for write-once data.
+#include "sdm_kernels.h"
+
+namespace sdm {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// posq[i] += displ[i]   (48 B/atom)
+__global__ void __launch_bounds__(kThreads)
+make_state2_kernel(int n, float4* __restrict__ posq, const float4* __restrict__ displ) {
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        float4 p[kUnroll], d[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++) { p[k] = posq[i + k * stride]; d[k] = ld_stream(displ + i + k * stride); }
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++) posq[i + k * stride] = add4(p[k], d[k]);
+    }
+    for (; i < n; i += stride) posq[i] = add4(posq[i], displ[i]);
+}
+
+// dst = src   (32 B/atom); SaveState2 and RestoreState1
+__global__ void __launch_bounds__(kThreads)
+copy4_kernel(int n, const float4* __restrict__ src, float4* __restrict__ dst) {
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++) v[k] = src[i + k * stride];
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++) dst[i + k * stride] = v[k];
+    }
+    for (; i < n; i += stride) dst[i] = src[i];
+}
+
+// save_f = force ; save_x = posq   (64 B/atom) in one pass
+__global__ void __launch_bounds__(kThreads)
+save_state1_kernel(int n, const float4* __restrict__ posq, const float4* __restrict__ force,
+                   float4* __restrict__ save_f, float4* __restrict__ save_x) {
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        float4 f0 = force[i], f1 = force[i + stride], x0 = posq[i], x1 = posq[i + stride];
+        save_f[i] = f0; save_f[i + stride] = f1;
+        save_x[i] = x0; save_x[i + stride] = x1;
+    }
+    for (; i < n; i += stride) { save_f[i] = force[i]; save_x[i] = posq[i]; }
+}
+
+// force = (1-sp)*f1 + sp*f2 + force on all four lanes (64 B/atom)
+__global__ void __launch_bounds__(kThreads)
+hybrid_force_kernel(int n, const float4* __restrict__ f1, const float4* __restrict__ f2,
+                    float4* __restrict__ force, float sp) {
+    const float lmb = sp, lmb1 = 1.0f - sp;
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        float4 a0 = ld_stream(f1 + i), b0 = ld_stream(f2 + i), c0 = force[i];
+        float4 a1 = ld_stream(f1 + i + stride), b1 = ld_stream(f2 + i + stride), c1 = force[i + stride];
+        force[i] = make_float4(lmb1 * a0.x + lmb * b0.x + c0.x, lmb1 * a0.y + lmb * b0.y + c0.y,
+                               lmb1 * a0.z + lmb * b0.z + c0.z, lmb1 * a0.w + lmb * b0.w + c0.w);
+        force[i + stride] = make_float4(lmb1 * a1.x + lmb * b1.x + c1.x, lmb1 * a1.y + lmb * b1.y + c1.y,
+                                        lmb1 * a1.z + lmb * b1.z + c1.z, lmb1 * a1.w + lmb * b1.w + c1.w);
+    }
+    for (; i < n; i += stride) {
+        float4 a = f1[i], b = f2[i], c = force[i];
+        force[i] = make_float4(lmb1 * a.x + lmb * b.x + c.x, lmb1 * a.y + lmb * b.y + c.y,
+                               lmb1 * a.z + lmb * b.z + c.z, lmb1 * a.w + lmb * b.w + c.w);
+    }
+}
+
+int grid_for(int n, int per_thread) {
+    long long want = ((long long)n + (long long)kThreads * per_thread - 1) / ((long long)kThreads * per_thread);
+    const int cap = 148 * 8;  // 8 resident 256-thread CTAs per SM on B200
+    if (want < 1) want = 1;
+    return (int)(want > cap ? cap : want);
+}
+
+}  // namespace
+
+void launch_make_state2(int n, float4* posq, const float4* displ, cudaStream_t s) {
+    if (n <= 0) return;
+    make_state2_kernel<<<grid_for(n, kUnroll), kThreads, 0, s>>>(n, posq, displ);
+}
+void launch_save_state1(int n, const float4* posq, const float4* force, float4* save_f,
+                        float4* save_x, cudaStream_t s) {
+    if (n <= 0) return;
+    save_state1_kernel<<<grid_for(n, 2), kThreads, 0, s>>>(n, posq, force, save_f, save_x);
+}
+void launch_copy4(int n, const float4* src, float4* dst, cudaStream_t s) {
+    if (n <= 0) return;
+    copy4_kernel<<<grid_for(n, kUnroll), kThreads, 0, s>>>(n, src, dst);
+}
+void launch_hybrid_force(int n, const float4* f1, const float4* f2, float4* force, float sp,
+                         cudaStream_t s) {
+    if (n <= 0) return;
+    hybrid_force_kernel<<<grid_for(n, 2), kThreads, 0, s>>>(n, f1, f2, force, sp);
+}
+
+}  // namespace sdm

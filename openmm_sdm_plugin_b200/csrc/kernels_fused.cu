@@ -1,0 +1,537 @@
+// kernels_fused.cu -- stages of the fused dual-state evaluation that do not depend on the
+// neighbour-list machinery: position prep, the all-pairs tile kernel (small systems and
+// cross-check), the displaced-atom ("ligand") dual-state kernels, 1-4 exceptions, the device
+// scalar stage (soft-core + bias) and the hybrid-force mix.  sm_100a.
+//
+// Reference behaviour restated (never copied): LangevinIntegratorSDM.cpp:153-183 (sequence),
+// ReferenceSDMKernels.cpp:161-199 (state copies), :202-318 (execute), OpenMM 7.3 Reference
+// NonbondedForce arithmetic.
+#include "sdm_kernels.h"
+
+namespace sdm {
+
+namespace {
+
+constexpr int kTile = 128;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Fixed-order block reduction (deterministic): warp trees, then warp 0 adds the warp totals in
+// order.  Result valid in thread 0.  blockDim.x must be a multiple of 32, <= 1024.
+__device__ double block_sum(double v, double* smem /* >= 32 */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < nw; k++) t += smem[k];
+    return t;
+}
+
+__device__ long long block_sum_ll(long long v, long long* smem) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum_ll(v);
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    long long t = 0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < nw; k++) t += smem[k];
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: double positions -> float4 (wrapped into the box when periodic; .w = q*sqrt(K)).
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_posq_kernel(Topology T, const double* __restrict__ pos, float4* __restrict__ posq) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    if (i >= T.n) return;
+    const double* p = pos + (size_t)r * 3 * T.n + 3 * (size_t)i;
+    double x = p[0], y = p[1], z = p[2];
+    if (T.method == SDM_CUTOFF_PERIODIC) {
+        x -= floor(x * T.inv_box[0]) * T.box[0];
+        y -= floor(y * T.inv_box[1]) * T.box[1];
+        z -= floor(z * T.inv_box[2]) * T.box[2];
+    }
+    posq[(size_t)r * T.n + i] = make_float4((float)x, (float)y, (float)z, T.parf[i].x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// all-pairs tile kernel: thread i walks every j (tiles of 128 staged in shared memory), keeps
+// the force on i only, so every pair is visited from both sides (energy and counts are halved
+// by the scalar stage).  No atomics, deterministic.  FP32 pair arithmetic; per-tile partial sums
+// are flushed into FP64 accumulators.
+// ---------------------------------------------------------------------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(kTile)
+allpairs_kernel(Topology T, const float4* __restrict__ posq_all, const double* __restrict__ pos_all,
+                long long* __restrict__ f1acc, int nslot, double* __restrict__ epart,
+                long long* __restrict__ cpart, int n_epart, int exact, int* emit_counter,
+                int* emit_pairs, int emit_cap, int emit_replica) {
+    __shared__ float4 s_posq[kTile];
+    __shared__ float2 s_par[kTile];
+    __shared__ double s_red[32];
+    __shared__ long long s_redl[32];
+
+    const int n = T.n;
+    const int r = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * kTile + tid;
+    const bool valid = i < n;
+    const float4* posq = posq_all + (size_t)r * n;
+    const double* pos = pos_all + (size_t)r * 3 * n;
+    const bool emit = emit_pairs != nullptr && r == emit_replica;
+
+    float4 pi = valid ? posq[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pari = valid ? T.parf[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int ep = valid ? T.excl_start[i] : 0;
+    const int eend = valid ? T.excl_start[i + 1] : 0;
+    int enext = (ep < eend) ? T.excl_idx[ep] : 0x7fffffff;
+
+    double fx = 0.0, fy = 0.0, fz = 0.0, en = 0.0;
+    long long cnt = 0;
+
+    for (int jt = 0; jt < n; jt += kTile) {
+        int jl = jt + tid;
+        if (jl < n) {
+            s_posq[tid] = posq[jl];
+            float4 pj = T.parf[jl];
+            s_par[tid] = make_float2(pj.y, pj.z);
+        }
+        __syncthreads();
+        const int jmax = min(kTile, n - jt);
+        float tfx = 0.f, tfy = 0.f, tfz = 0.f, te = 0.f;
+        if (valid) {
+            for (int jj = 0; jj < jmax; jj++) {
+                const int j = jt + jj;
+                if (j == enext) {
+                    ep++;
+                    enext = (ep < eend) ? T.excl_idx[ep] : 0x7fffffff;
+                    continue;
+                }
+                if (j == i) continue;
+                const float4 pj = s_posq[jj];
+                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                if (METHOD == SDM_CUTOFF_PERIODIC) {
+                    dx -= T.boxf[0] * rintf(dx * T.inv_boxf[0]);
+                    dy -= T.boxf[1] * rintf(dy * T.inv_boxf[1]);
+                    dz -= T.boxf[2] * rintf(dz * T.inv_boxf[2]);
+                }
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                bool in = true;
+                if (METHOD != SDM_NOCUTOFF) {
+                    in = r2 <= T.rc2f;
+                    if (exact && fabsf(r2 - T.rc2f) < T.band) in = in_cutoff_f64(T, pos, i, j);
+                }
+                if (!in) continue;
+                const float2 parj = s_par[jj];
+                const float rinv = rsqrtf(r2);
+                const float rinv2 = rinv * rinv;
+                const float sig = pari.y + parj.x;
+                const float sr2 = sig * sig * rinv2;
+                const float sr6 = sr2 * sr2 * sr2;
+                const float eps = pari.z * parj.y;
+                const float qq = pi.w * pj.w;
+                float dEdR = eps * (12.f * sr6 - 6.f) * sr6;
+                float e = eps * (sr6 - 1.f) * sr6;
+                if (METHOD != SDM_NOCUTOFF) {
+                    dEdR += qq * (rinv - 2.f * T.krff * r2);
+                    e += qq * (rinv + T.krff * r2 - T.crff);
+                } else {
+                    dEdR += qq * rinv;
+                    e += qq * rinv;
+                }
+                const float fs = dEdR * rinv2;
+                tfx += fs * dx;
+                tfy += fs * dy;
+                tfz += fs * dz;
+                te += e;
+                cnt++;
+                if (emit && i < j) {
+                    int slot = atomicAdd(emit_counter, 1);
+                    if (slot < emit_cap) {
+                        emit_pairs[2 * slot] = i;
+                        emit_pairs[2 * slot + 1] = j;
+                    }
+                }
+            }
+        }
+        fx += tfx; fy += tfy; fz += tfz; en += te;
+        __syncthreads();
+    }
+    if (valid) {
+        long long* acc = f1acc + (size_t)r * 3 * nslot;
+        acc[i] = to_fixed(fx);
+        acc[nslot + i] = to_fixed(fy);
+        acc[2 * nslot + i] = to_fixed(fz);
+    }
+    double be = block_sum(en, s_red);
+    long long bc = block_sum_ll(cnt, s_redl);
+    if (tid == 0) {
+        epart[(size_t)r * n_epart + blockIdx.x] = be;
+        cpart[(size_t)r * n_epart + blockIdx.x] = bc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Displaced-atom kernels.  All FP64, positions straight from the double buffer, in-cutoff
+// decisions with the contraction-free expression of the oracle.  State 2 = x + d for EVERY atom
+// (ReferenceSDMKernels.cpp:192-199); a pair changes iff the two displacement vectors differ.
+//
+// probe kernel: one block per (displaced atom i, replica); walks all atoms k whose displacement
+// differs from i's, evaluates the pair at state 1 and state 2 and reduces
+//     dF_i = sum_k f_i(state 2) - f_i(state 1),   u_i = sum_k w_k (e2 - e1),
+// w_k = 1/2 when k is displaced too (that pair is seen from k's block as well), else 1.
+// ---------------------------------------------------------------------------------------------
+struct PairGeom {
+    double dx, dy, dz, r2;
+};
+
+__device__ __forceinline__ PairGeom geom(const Topology& T, double xi, double yi, double zi,
+                                         double xk, double yk, double zk) {
+    PairGeom g;
+    g.dx = xi - xk; g.dy = yi - yk; g.dz = zi - zk;
+    if (T.method == SDM_CUTOFF_PERIODIC) {
+        g.dx = min_image_exact(g.dx, T.box[0]);
+        g.dy = min_image_exact(g.dy, T.box[1]);
+        g.dz = min_image_exact(g.dz, T.box[2]);
+    }
+    g.r2 = norm2_exact(g.dx, g.dy, g.dz);
+    return g;
+}
+
+__global__ void __launch_bounds__(128)
+ligand_probe_kernel(Topology T, const double* __restrict__ pos_all, double* __restrict__ dF_all,
+                    double* __restrict__ upart, long long* __restrict__ mcnt) {
+    __shared__ double s_red[32];
+    __shared__ long long s_redl[32];
+    const int m = blockIdx.x, r = blockIdx.y, n = T.n;
+    const int i = T.lig_idx[m];
+    const double* pos = pos_all + (size_t)r * 3 * n;
+    const int gi = T.group[i];
+    const double xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+    const double xi2 = xi + T.disp[3 * i], yi2 = yi + T.disp[3 * i + 1], zi2 = zi + T.disp[3 * i + 2];
+    const double qi = T.q[i], hsi = T.hsig[i], hei = T.heps[i];
+    const bool cutoff = T.method != SDM_NOCUTOFF;
+
+    double fx = 0, fy = 0, fz = 0, u = 0;
+    long long c1 = 0, c2 = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int gk = T.group[k];
+        if (gk == gi) continue;  // same displacement (includes k == i): pair unchanged
+        const double xk = pos[3 * k], yk = pos[3 * k + 1], zk = pos[3 * k + 2];
+        PairGeom g1 = geom(T, xi, yi, zi, xk, yk, zk);
+        double xk2 = xk, yk2 = yk, zk2 = zk;
+        if (gk != 0) { xk2 += T.disp[3 * k]; yk2 += T.disp[3 * k + 1]; zk2 += T.disp[3 * k + 2]; }
+        PairGeom g2 = geom(T, xi2, yi2, zi2, xk2, yk2, zk2);
+        const bool in1 = !cutoff || g1.r2 <= T.rc2;
+        const bool in2 = !cutoff || g2.r2 <= T.rc2;
+        if (!(in1 || in2)) continue;
+        if (is_excluded(T, i, k)) continue;
+        const double sig = hsi + T.hsig[k], eps = hei * T.heps[k];
+        const double qq = SDM_K_COULOMB * qi * T.q[k];
+        const double w = (gk != 0) ? 0.5 : 1.0;
+        const int wc = (gk != 0) ? 1 : 2;
+        if (in1) {
+            double e;
+            double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+            fx -= fs * g1.dx; fy -= fs * g1.dy; fz -= fs * g1.dz;
+            u -= w * e;
+            c1 += wc;
+        }
+        if (in2) {
+            double e;
+            double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+            fx += fs * g2.dx; fy += fs * g2.dy; fz += fs * g2.dz;
+            u += w * e;
+            c2 += wc;
+        }
+    }
+    double sx = block_sum(fx, s_red);
+    double sy = block_sum(fy, s_red);
+    double sz = block_sum(fz, s_red);
+    double su = block_sum(u, s_red);
+    long long sc1 = block_sum_ll(c1, s_redl);
+    long long sc2 = block_sum_ll(c2, s_redl);
+    if (threadIdx.x == 0) {
+        double* dF = dF_all + (size_t)r * 3 * n;
+        dF[3 * i] = sx; dF[3 * i + 1] = sy; dF[3 * i + 2] = sz;
+        upart[(size_t)r * T.n_lig + m] = su;
+        mcnt[((size_t)r * T.n_lig + m) * 2] = sc1;
+        mcnt[((size_t)r * T.n_lig + m) * 2 + 1] = sc2;
+    }
+}
+
+// env kernel: one thread per NON-displaced atom j; loops over the displaced atoms (staged in
+// shared memory) and accumulates dF_j = sum_i f_j(state 2) - f_j(state 1).  Writes every dF_j
+// (zero when nothing is near), so no memset is needed.
+struct Probe {
+    double x1, y1, z1, x2, y2, z2, q, hsig, heps;
+    int idx, pad;
+};
+
+__global__ void __launch_bounds__(128)
+ligand_env_kernel(Topology T, const double* __restrict__ pos_all, double* __restrict__ dF_all) {
+    constexpr int kChunk = 64;
+    __shared__ Probe s_p[kChunk];
+    const int n = T.n, r = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* pos = pos_all + (size_t)r * 3 * n;
+    const bool active = j < n && T.group[j] == 0;
+    const bool cutoff = T.method != SDM_NOCUTOFF;
+    double xj = 0, yj = 0, zj = 0, qj = 0, hsj = 0, hej = 0;
+    if (active) {
+        xj = pos[3 * j]; yj = pos[3 * j + 1]; zj = pos[3 * j + 2];
+        qj = T.q[j]; hsj = T.hsig[j]; hej = T.heps[j];
+    }
+    double fx = 0, fy = 0, fz = 0;
+    for (int m0 = 0; m0 < T.n_lig; m0 += kChunk) {
+        const int mc = min(kChunk, T.n_lig - m0);
+        __syncthreads();
+        if (threadIdx.x < mc) {
+            const int i = T.lig_idx[m0 + threadIdx.x];
+            Probe p;
+            p.x1 = pos[3 * i]; p.y1 = pos[3 * i + 1]; p.z1 = pos[3 * i + 2];
+            p.x2 = p.x1 + T.disp[3 * i]; p.y2 = p.y1 + T.disp[3 * i + 1]; p.z2 = p.z1 + T.disp[3 * i + 2];
+            p.q = T.q[i]; p.hsig = T.hsig[i]; p.heps = T.heps[i];
+            p.idx = i; p.pad = 0;
+            s_p[threadIdx.x] = p;
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int m = 0; m < mc; m++) {
+            const Probe& p = s_p[m];
+            PairGeom g1 = geom(T, p.x1, p.y1, p.z1, xj, yj, zj);
+            PairGeom g2 = geom(T, p.x2, p.y2, p.z2, xj, yj, zj);
+            const bool in1 = !cutoff || g1.r2 <= T.rc2;
+            const bool in2 = !cutoff || g2.r2 <= T.rc2;
+            if (!(in1 || in2)) continue;
+            if (is_excluded(T, j, p.idx)) continue;
+            const double sig = p.hsig + hsj, eps = p.heps * hej;
+            const double qq = SDM_K_COULOMB * p.q * qj;
+            double e;
+            // d = x_i - x_j ; force on j is -fs*d
+            if (in1) {
+                double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+                fx += fs * g1.dx; fy += fs * g1.dy; fz += fs * g1.dz;
+            }
+            if (in2) {
+                double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+                fx -= fs * g2.dx; fy -= fs * g2.dy; fz -= fs * g2.dz;
+            }
+        }
+    }
+    if (active) {
+        double* dF = dF_all + (size_t)r * 3 * n;
+        dF[3 * j] = fx; dF[3 * j + 1] = fy; dF[3 * j + 2] = fz;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-4 exceptions (OpenMM 7.3 ReferenceLJCoulomb14: no cutoff, no reaction field, plain delta).
+// State-independent unless the two atoms carry different displacements; that rare case also
+// feeds dF and u (FP64 atomics on dF -- must run after the ligand kernels).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exc_term(double dx, double dy, double dz, double qq,
+                                           double sigma, double eps4, double* e) {
+    double r2 = dx * dx + dy * dy + dz * dz;
+    double inverseR = 1.0 / sqrt(r2);
+    double sig2 = inverseR * sigma;
+    sig2 *= sig2;
+    double sig6 = sig2 * sig2 * sig2;
+    double dEdR = eps4 * (12.0 * sig6 - 6.0) * sig6;
+    dEdR += SDM_K_COULOMB * qq * inverseR;
+    dEdR *= inverseR * inverseR;
+    *e = eps4 * (sig6 - 1.0) * sig6 + SDM_K_COULOMB * qq * inverseR;
+    return dEdR;
+}
+
+__global__ void __launch_bounds__(128)
+exceptions_kernel(Topology T, const double* __restrict__ pos_all, long long* __restrict__ f1acc,
+                  int nslot, const int* __restrict__ slot_of, double* __restrict__ dF_all,
+                  double* __restrict__ eexc_part, double* __restrict__ uexc_part, int n_excpart) {
+    __shared__ double s_red[32];
+    const int n = T.n, r = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* pos = pos_all + (size_t)r * 3 * n;
+    double e1 = 0.0, du = 0.0;
+    if (k < T.n_exceptions) {
+        const int a = T.exc_pairs[2 * k], b = T.exc_pairs[2 * k + 1];
+        const double qq = T.exc_params[3 * k], sigma = T.exc_params[3 * k + 1];
+        const double eps = T.exc_params[3 * k + 2];
+        if (qq != 0.0 || eps != 0.0) {
+            const double eps4 = 4.0 * eps;
+            double dx = pos[3 * a] - pos[3 * b], dy = pos[3 * a + 1] - pos[3 * b + 1],
+                   dz = pos[3 * a + 2] - pos[3 * b + 2];
+            double fs = exc_term(dx, dy, dz, qq, sigma, eps4, &e1);
+            long long* acc = f1acc + (size_t)r * 3 * nslot;
+            const int sa = slot_of ? slot_of[(size_t)r * n + a] : a;
+            const int sb = slot_of ? slot_of[(size_t)r * n + b] : b;
+            atomic_add_fixed(acc + sa, to_fixed(fs * dx));
+            atomic_add_fixed(acc + nslot + sa, to_fixed(fs * dy));
+            atomic_add_fixed(acc + 2 * nslot + sa, to_fixed(fs * dz));
+            atomic_add_fixed(acc + sb, to_fixed(-fs * dx));
+            atomic_add_fixed(acc + nslot + sb, to_fixed(-fs * dy));
+            atomic_add_fixed(acc + 2 * nslot + sb, to_fixed(-fs * dz));
+            if (T.group[a] != T.group[b]) {
+                double dx2 = (pos[3 * a] + T.disp[3 * a]) - (pos[3 * b] + T.disp[3 * b]);
+                double dy2 = (pos[3 * a + 1] + T.disp[3 * a + 1]) - (pos[3 * b + 1] + T.disp[3 * b + 1]);
+                double dz2 = (pos[3 * a + 2] + T.disp[3 * a + 2]) - (pos[3 * b + 2] + T.disp[3 * b + 2]);
+                double e2;
+                double fs2 = exc_term(dx2, dy2, dz2, qq, sigma, eps4, &e2);
+                double* dF = dF_all + (size_t)r * 3 * n;
+                atomicAdd(dF + 3 * a, fs2 * dx2 - fs * dx);
+                atomicAdd(dF + 3 * a + 1, fs2 * dy2 - fs * dy);
+                atomicAdd(dF + 3 * a + 2, fs2 * dz2 - fs * dz);
+                atomicAdd(dF + 3 * b, -(fs2 * dx2 - fs * dx));
+                atomicAdd(dF + 3 * b + 1, -(fs2 * dy2 - fs * dy));
+                atomicAdd(dF + 3 * b + 2, -(fs2 * dz2 - fs * dz));
+                du = e2 - e1;
+            }
+        }
+    }
+    double se = block_sum(e1, s_red);
+    double sd = block_sum(du, s_red);
+    if (threadIdx.x == 0) {
+        eexc_part[(size_t)r * n_excpart + blockIdx.x] = se;
+        uexc_part[(size_t)r * n_excpart + blockIdx.x] = sd;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar stage: one block per replica.  Fixed-order reductions of the partials, then thread 0
+// runs SoftCoreF + bias + bookkeeping on the device -- no host round trip (the reference pays
+// three D->H energy reads per step).
+// ---------------------------------------------------------------------------------------------
+__device__ double strided_sum(const double* v, int n, double* smem) {
+    double t = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) t += v[k];
+    return block_sum(t, smem);
+}
+
+__global__ void __launch_bounds__(256)
+scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div, int list_age) {
+    __shared__ double s_red[32];
+    __shared__ long long s_redl[32];
+    const int r = blockIdx.x;
+    double ep = strided_sum(B.epart + (size_t)r * B.n_epart, B.n_epart, s_red);
+    double ee = strided_sum(B.eexc_part + (size_t)r * B.n_excpart, B.n_excpart, s_red);
+    double ue = strided_sum(B.uexc_part + (size_t)r * B.n_excpart, B.n_excpart, s_red);
+    double ul = strided_sum(B.upart + (size_t)r * T.n_lig, T.n_lig, s_red);
+    long long c = 0, m1 = 0, m2 = 0;
+    for (int k = threadIdx.x; k < B.n_epart; k += blockDim.x) c += B.cpart[(size_t)r * B.n_epart + k];
+    for (int k = threadIdx.x; k < T.n_lig; k += blockDim.x) {
+        m1 += B.mcnt[((size_t)r * T.n_lig + k) * 2];
+        m2 += B.mcnt[((size_t)r * T.n_lig + k) * 2 + 1];
+    }
+    c = block_sum_ll(c, s_redl);
+    m1 = block_sum_ll(m1, s_redl);
+    m2 = block_sum_ll(m2, s_redl);
+    if (threadIdx.x == 0) {
+        ReplicaState* st = B.state + r;
+        sdm_scalars* sc = &st->sc;
+        sc->status = B.flags[r];
+        sc->E1_pair = ep * e_scale;
+        sc->E1_exc = ee;
+        sc->E1_disp = T.e_disp;
+        sc->E1 = sc->E1_pair + sc->E1_exc + sc->E1_disp;
+        sc->u = ul + ue;
+        sc->E2 = sc->E1 + sc->u;
+        sc->n_pairs1 = c / c_div;
+        sc->n_moved1 = m1 / 2;
+        sc->n_moved2 = m2 / 2;
+        sc->list_age = list_age;
+        // sc->Eb was stored by sdm_set_bonded_forces
+        execute_scalars(&st->alch, sc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mix: F = F1 + sp*(F2 - F1) + Fb  ==  sp*F2 + (1-sp)*F1 + Fb  (ReferenceSDMKernels.cpp:309-318),
+// sp read from the device scalar block.  Also converts F1 to double and (optionally) clears the
+// fixed-point accumulators for the next evaluation.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mix_kernel(Topology T, EvalBuffers B, int zero_acc) {
+    const int n = T.n, r = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0) B.flags[r] = 0;  // already copied into sc.status by the scalar stage
+    const double sp = B.state[r].sc.sp;
+    const int slot = B.slot_of ? B.slot_of[(size_t)r * n + i] : i;
+    long long* acc = B.f1acc + (size_t)r * 3 * B.nslot;
+    const size_t o = (size_t)r * 3 * n + 3 * (size_t)i;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double f1 = (double)acc[(size_t)c * B.nslot + slot] * SDM_INV_FORCE_SCALE;
+        const double f = f1 + sp * B.dF[o + c] + B.fb[o + c];
+        B.F1[o + c] = f1;
+        B.F[o + c] = f;
+        if (zero_acc) acc[(size_t)c * B.nslot + slot] = 0;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+int allpairs_num_blocks(int n) { return (n + kTile - 1) / kTile; }
+int exceptions_num_blocks(int n_exceptions) { return n_exceptions > 0 ? (n_exceptions + 127) / 128 : 1; }
+
+void launch_prep_posq(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+    dim3 grid((T.n + 255) / 256, B.R);
+    prep_posq_kernel<<<grid, 256, 0, s>>>(T, B.pos, B.posq);
+}
+
+void launch_allpairs(const Topology& T, const EvalBuffers& B, int exact, int* emit_counter,
+                     int* emit_pairs, int emit_cap, int emit_replica, cudaStream_t s) {
+    dim3 grid(allpairs_num_blocks(T.n), B.R);
+    if (T.method == SDM_NOCUTOFF)
+        allpairs_kernel<SDM_NOCUTOFF><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+    else if (T.method == SDM_CUTOFF_NONPERIODIC)
+        allpairs_kernel<SDM_CUTOFF_NONPERIODIC><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+    else
+        allpairs_kernel<SDM_CUTOFF_PERIODIC><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+}
+
+void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+    if (T.n_lig == 0) return;
+    dim3 grid(T.n_lig, B.R);
+    ligand_probe_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.dF, B.upart, B.mcnt);
+}
+
+void launch_ligand_env(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+    dim3 grid((T.n + 127) / 128, B.R);
+    ligand_env_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.dF);
+}
+
+void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+    dim3 grid(exceptions_num_blocks(T.n_exceptions), B.R);
+    exceptions_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.f1acc, B.nslot, B.slot_of, B.dF, B.eexc_part, B.uexc_part, B.n_excpart);
+}
+
+void launch_scalars(const Topology& T, const EvalBuffers& B, double e_scale, int c_div,
+                    int list_age, cudaStream_t s) {
+    scalars_kernel<<<B.R, 256, 0, s>>>(T, B, e_scale, c_div, list_age);
+}
+
+void launch_mix(const Topology& T, const EvalBuffers& B, int zero_acc, cudaStream_t s) {
+    dim3 grid((T.n + 255) / 256, B.R);
+    mix_kernel<<<grid, 256, 0, s>>>(T, B, zero_acc);
+}
+
+}  // namespace sdm

@@ -1,0 +1,54 @@
+// sdm_ctx.h -- the context object behind the opaque sdm_ctx handle (internal).
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "sdm_kernels.h"
+
+namespace sdm { struct PairList; }
+
+struct sdm_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    sdm_options opt{};
+    int n = 0, R = 0;
+    int pair_mode = SDM_PAIR_ALLPAIRS;
+
+    sdm::Topology T{};
+    sdm::EvalBuffers B{};
+    std::vector<void*> allocs;          // every cudaMalloc of this ctx (freed in sdm_destroy)
+    double* d_pos = nullptr;
+    double* d_fb = nullptr;
+    double* d_disp = nullptr;
+    int* d_group = nullptr;
+    int* d_lig_idx = nullptr;
+
+    std::vector<sdm_alch> h_alch;       // staging copies with ctx lifetime
+    std::vector<double> h_eb;
+    std::vector<int> h_group, h_lig, h_excl_start, h_excl_idx;
+    sdm::ReplicaState* h_state = nullptr;  // pinned read-back buffer
+
+    // cluster-pair list (pairlist.cu)
+    sdm::PairList* pl = nullptr;
+    bool list_valid = false;
+    int list_age = 0;
+    int64_t n_builds = 0;
+
+    int64_t launches = 0;
+    int64_t n_evals = 0;
+    bool timing = false, timing_valid = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// api.cu
+int sdm_fail(int code, const char* msg);
+
+// pairlist.cu -- cluster-pair list path (SDM_PAIR_CLUSTER)
+int sdm_ctx_init_pairlist(sdm_ctx* c);
+void sdm_ctx_free_pairlist(sdm_ctx* c);
+int sdm_ctx_pairlist_eval(sdm_ctx* c);   // (re)build if due, refresh sorted positions, pair kernel
+int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap);
+int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value);

@@ -1,0 +1,57 @@
+// sdm_kernels.h -- host-callable launchers of the sm_100a kernels (C++ linkage, internal).
+#pragma once
+
+#include "sdm_internal.cuh"
+
+namespace sdm {
+
+// Device buffers of one context that the per-eval kernels touch.  R = replicas, n = atoms.
+struct EvalBuffers {
+    int R;
+    const double* pos;      // [R][3n]   positions, System order, nm
+    const double* fb;       // [R][3n]   bonded/restraint forces (zero when absent)
+    float4* posq;           // [R][n]    (x,y,z wrapped into the box, q*sqrt(K)) float
+    long long* f1acc;       // [R][3][nslot] state-1 force accumulators, 2^32 fixed point
+    double* dF;             // [R][3n]   F2 - F1 (moved pairs only)
+    double* F;              // [R][3n]   hybrid force (output)
+    double* F1;             // [R][3n]   state-1 force in double (output)
+    double* epart;          // [R][n_epart] pair-energy partials
+    long long* cpart;       // [R][n_epart] in-cutoff pair count partials
+    double* eexc_part;      // [R][n_excpart] exception-energy partials
+    double* uexc_part;      // [R][n_excpart] exception contribution to u
+    double* upart;          // [R][n_lig] u partial per displaced atom
+    long long* mcnt;        // [R][n_lig][2] moved-pair counts (x2) per displaced atom
+    ReplicaState* state;    // [R]
+    int* flags;             // [R] status raised by kernels of this eval (0 = ok); cleared by mix
+    int n_epart, n_excpart;
+    int nslot;              // stride of f1acc planes (>= n)
+    const int* slot_of;     // [R][n] atom -> accumulator slot, or nullptr for identity
+};
+
+// ---- fused path, v0 (all-pairs tiles, System order) ------------------------------------------
+void launch_prep_posq(const Topology& T, const EvalBuffers& B, cudaStream_t s);
+// exact != 0: FP64 re-test in the band around the cutoff.  emit_*: optional pair dump.
+void launch_allpairs(const Topology& T, const EvalBuffers& B, int exact, int* emit_counter,
+                     int* emit_pairs, int emit_cap, int emit_replica, cudaStream_t s);
+int allpairs_num_blocks(int n);
+
+// ---- fused path, shared stages ----------------------------------------------------------------
+void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s);
+void launch_ligand_env(const Topology& T, const EvalBuffers& B, cudaStream_t s);
+void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s);
+int exceptions_num_blocks(int n_exceptions);
+// e_scale / c_div: 0.5 / 2 when every pair was visited from both sides (all-pairs), 1 / 1 for a
+// half list.
+void launch_scalars(const Topology& T, const EvalBuffers& B, double e_scale, int c_div,
+                    int list_age, cudaStream_t s);
+void launch_mix(const Topology& T, const EvalBuffers& B, int zero_acc, cudaStream_t s);
+
+// ---- literal kernel-interface operations (float4 device buffers) ------------------------------
+void launch_make_state2(int n, float4* posq, const float4* displ, cudaStream_t s);
+void launch_save_state1(int n, const float4* posq, const float4* force, float4* save_f,
+                        float4* save_x, cudaStream_t s);
+void launch_copy4(int n, const float4* src, float4* dst, cudaStream_t s);
+void launch_hybrid_force(int n, const float4* f1, const float4* f2, float4* force, float sp,
+                         cudaStream_t s);
+
+}  // namespace sdm
