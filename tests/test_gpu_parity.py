@@ -205,10 +205,17 @@ def test_alchemical_methods(cfg1, bias, soft):
 
 
 def test_unknown_softcore_method_is_reported(cfg1):
+    """LangevinIntegratorSDM.cpp:126-129,147: the u <= ub early return comes first, so an unknown
+    method only throws when u > ub.  The C ABI reports it as status SDM_ERR_SOFTCORE."""
     case, _ = cfg1
     al = S.AlchemicalState(**vars(case.alch))
     al.softcore_method = 7
     c2 = S.SDMCase(case.name, case.system, case.positions, case.displacement, al)
+    with run_case(c2, _lib.PAIR_ALLPAIRS) as ctx:
+        assert ctx.scalars(0)["status"] == 0          # u = 3.6 <= ub = 209.2: no throw
+    al.ubcore = 1.0                                    # now u > ub
+    with pytest.raises(ValueError):
+        O.sdm_eval(case.system, S.AlchemicalState(**vars(al)), case.displacement, case.positions)
     with run_case(c2, _lib.PAIR_ALLPAIRS) as ctx:
         assert ctx.scalars(0)["status"] == _lib.SDM_ERR_SOFTCORE
 
