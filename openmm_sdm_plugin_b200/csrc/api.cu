@@ -299,9 +299,10 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     sdm::EvalBuffers& B = c->B;
     std::memset(&B, 0, sizeof(B));
     B.R = R;
-    B.n_epart = sdm::allpairs_num_blocks(n);
+    B.n_epart_allpairs = sdm::allpairs_num_blocks(n);
     B.n_excpart = sdm::exceptions_num_blocks(s->n_exceptions);
     B.nslot = n;
+    B.acc_rstride = 3 * (size_t)n;
     B.slot_of = nullptr;
     double *pos, *fb;
     TRY(dev_alloc(c, &pos, (size_t)R * 3 * n));
@@ -315,8 +316,13 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     TRY(dev_alloc(c, &B.dF, (size_t)R * 3 * n));
     TRY(dev_alloc(c, &B.F, (size_t)R * 3 * n));
     TRY(dev_alloc(c, &B.F1, (size_t)R * 3 * n));
-    TRY(dev_alloc(c, &B.epart, (size_t)R * B.n_epart));
-    TRY(dev_alloc(c, &B.cpart, (size_t)R * B.n_epart));
+    TRY(dev_alloc(c, &B.epart, (size_t)R * B.n_epart_allpairs));
+    TRY(dev_alloc(c, &B.cpart, (size_t)R * B.n_epart_allpairs));
+    {
+        std::vector<int> off(R + 1);
+        for (int r = 0; r <= R; r++) off[r] = r * B.n_epart_allpairs;
+        TRY(dev_upload(c, &B.part_off, off));
+    }
     TRY(dev_alloc(c, &B.eexc_part, (size_t)R * B.n_excpart));
     TRY(dev_alloc(c, &B.uexc_part, (size_t)R * B.n_excpart));
     TRY(dev_alloc(c, &B.upart, (size_t)R * n));
@@ -332,7 +338,15 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     }
     TRYCUDA(cudaMallocHost((void**)&c->h_state, sizeof(sdm::ReplicaState) * (size_t)R));
 
-    c->pair_mode = opt.pair_mode == SDM_PAIR_AUTO ? SDM_PAIR_ALLPAIRS : opt.pair_mode;
+    c->pair_mode = opt.pair_mode;
+    if (c->pair_mode == SDM_PAIR_AUTO) {
+        // small systems and NoCutoff: all-pairs tiles; otherwise the cluster-pair list
+        bool small_box = false;
+        if (s->method == SDM_CUTOFF_PERIODIC)
+            for (int d = 0; d < 3; d++) small_box |= s->box[d] < 2.0 * (s->cutoff + opt.skin);
+        c->pair_mode = (s->method == SDM_NOCUTOFF || n < 3000 || small_box) ? SDM_PAIR_ALLPAIRS
+                                                                            : SDM_PAIR_CLUSTER;
+    }
     TRY(sdm_ctx_init_pairlist(c));
 #undef TRY
 #undef TRYCUDA

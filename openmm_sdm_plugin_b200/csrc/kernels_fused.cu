@@ -173,7 +173,7 @@ allpairs_kernel(Topology T, const float4* __restrict__ posq_all, const double* _
         __syncthreads();
     }
     if (valid) {
-        long long* acc = f1acc + (size_t)r * 3 * nslot;
+        long long* acc = f1acc + (size_t)r * 3 * nslot;  // all-pairs: acc_rstride == 3*nslot
         acc[i] = to_fixed(fx);
         acc[nslot + i] = to_fixed(fy);
         acc[2 * nslot + i] = to_fixed(fz);
@@ -361,7 +361,7 @@ __device__ __forceinline__ double exc_term(double dx, double dy, double dz, doub
 
 __global__ void __launch_bounds__(128)
 exceptions_kernel(Topology T, const double* __restrict__ pos_all, long long* __restrict__ f1acc,
-                  int nslot, const int* __restrict__ slot_of, double* __restrict__ dF_all,
+                  size_t acc_rstride, int nslot, const int* __restrict__ slot_of, double* __restrict__ dF_all,
                   double* __restrict__ eexc_part, double* __restrict__ uexc_part, int n_excpart) {
     __shared__ double s_red[32];
     const int n = T.n, r = blockIdx.y;
@@ -377,7 +377,7 @@ exceptions_kernel(Topology T, const double* __restrict__ pos_all, long long* __r
             double dx = pos[3 * a] - pos[3 * b], dy = pos[3 * a + 1] - pos[3 * b + 1],
                    dz = pos[3 * a + 2] - pos[3 * b + 2];
             double fs = exc_term(dx, dy, dz, qq, sigma, eps4, &e1);
-            long long* acc = f1acc + (size_t)r * 3 * nslot;
+            long long* acc = f1acc + (size_t)r * acc_rstride;
             const int sa = slot_of ? slot_of[(size_t)r * n + a] : a;
             const int sb = slot_of ? slot_of[(size_t)r * n + b] : b;
             atomic_add_fixed(acc + sa, to_fixed(fs * dx));
@@ -427,12 +427,13 @@ scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div, int list_ag
     __shared__ double s_red[32];
     __shared__ long long s_redl[32];
     const int r = blockIdx.x;
-    double ep = strided_sum(B.epart + (size_t)r * B.n_epart, B.n_epart, s_red);
+    const int p0 = B.part_off[r], np_ = B.part_off[r + 1] - p0;
+    double ep = strided_sum(B.epart + p0, np_, s_red);
     double ee = strided_sum(B.eexc_part + (size_t)r * B.n_excpart, B.n_excpart, s_red);
     double ue = strided_sum(B.uexc_part + (size_t)r * B.n_excpart, B.n_excpart, s_red);
     double ul = strided_sum(B.upart + (size_t)r * T.n_lig, T.n_lig, s_red);
     long long c = 0, m1 = 0, m2 = 0;
-    for (int k = threadIdx.x; k < B.n_epart; k += blockDim.x) c += B.cpart[(size_t)r * B.n_epart + k];
+    for (int k = threadIdx.x; k < np_; k += blockDim.x) c += B.cpart[p0 + k];
     for (int k = threadIdx.x; k < T.n_lig; k += blockDim.x) {
         m1 += B.mcnt[((size_t)r * T.n_lig + k) * 2];
         m2 += B.mcnt[((size_t)r * T.n_lig + k) * 2 + 1];
@@ -472,7 +473,7 @@ mix_kernel(Topology T, EvalBuffers B, int zero_acc) {
     if (i == 0) B.flags[r] = 0;  // already copied into sc.status by the scalar stage
     const double sp = B.state[r].sc.sp;
     const int slot = B.slot_of ? B.slot_of[(size_t)r * n + i] : i;
-    long long* acc = B.f1acc + (size_t)r * 3 * B.nslot;
+    long long* acc = B.f1acc + (size_t)r * B.acc_rstride;
     const size_t o = (size_t)r * 3 * n + 3 * (size_t)i;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -501,11 +502,11 @@ void launch_allpairs(const Topology& T, const EvalBuffers& B, int exact, int* em
                      int* emit_pairs, int emit_cap, int emit_replica, cudaStream_t s) {
     dim3 grid(allpairs_num_blocks(T.n), B.R);
     if (T.method == SDM_NOCUTOFF)
-        allpairs_kernel<SDM_NOCUTOFF><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+        allpairs_kernel<SDM_NOCUTOFF><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart_allpairs, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
     else if (T.method == SDM_CUTOFF_NONPERIODIC)
-        allpairs_kernel<SDM_CUTOFF_NONPERIODIC><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+        allpairs_kernel<SDM_CUTOFF_NONPERIODIC><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart_allpairs, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
     else
-        allpairs_kernel<SDM_CUTOFF_PERIODIC><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+        allpairs_kernel<SDM_CUTOFF_PERIODIC><<<grid, kTile, 0, s>>>(T, B.posq, B.pos, B.f1acc, B.nslot, B.epart, B.cpart, B.n_epart_allpairs, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
 }
 
 void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
@@ -521,7 +522,7 @@ void launch_ligand_env(const Topology& T, const EvalBuffers& B, cudaStream_t s) 
 
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
     dim3 grid(exceptions_num_blocks(T.n_exceptions), B.R);
-    exceptions_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.f1acc, B.nslot, B.slot_of, B.dF, B.eexc_part, B.uexc_part, B.n_excpart);
+    exceptions_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.f1acc, B.acc_rstride, B.nslot, B.slot_of, B.dF, B.eexc_part, B.uexc_part, B.n_excpart);
 }
 
 void launch_scalars(const Topology& T, const EvalBuffers& B, double e_scale, int c_div,

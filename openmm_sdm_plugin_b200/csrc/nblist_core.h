@@ -1,0 +1,283 @@
+// nblist_core.h -- cluster-pair list construction, written once as per-item bodies that compile
+// both for the device (thin __global__ wrappers in pairlist.cu) and for the host (the CPU
+// checker tests/hostcheck builds from this same header with g++ to validate pair coverage
+// against the oracle without a GPU).  No reference code corresponds to this: the reference
+// delegates neighbour lists to OpenMM; the layout below is designed
+// for the sm_100a pair kernel in kernels_cluster.cu.
+//
+// Layout
+//   * replicas live in disjoint cell ranges of ONE global index space: global cell
+//     g = r*ncell + cell.
+//   * atoms are sorted by (global cell, 9-bit Morton code of the position inside the cell) and
+//     every cell is padded to a multiple of 8 slots with dummy atoms, so a cluster (8 slots)
+//     or a j-group (4 slots) never straddles a cell.
+//   * an i-supercluster (sci) is a run of <= 8 clusters of one cell; its list holds j-group
+//     entries {j4 | shift<<26, imask | mask_index<<8}; imask bit ci says cluster ci of the sci
+//     interacts with the j-group.  Every unordered cluster pair is owned by exactly one side
+//     (checkerboard rule) and the diagonal uses a triangle mask, so each atom pair is
+//     evaluated once.
+//   * exclusion masks: 8 words per masked entry, bit (tj*8+ti) of word ci.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SDM_HD __host__ __device__ __forceinline__
+#else
+#define SDM_HD inline
+#include <cmath>
+#endif
+
+namespace sdm {
+namespace nbl {
+
+constexpr int kClusterSize = 8;      // atoms per i-cluster
+constexpr int kJGroup = 4;           // atoms per j-group (half a cluster)
+constexpr int kMaxCi = 8;            // clusters per supercluster
+constexpr int kSubBits = 9;          // Morton bits of the in-cell position in the sort key
+constexpr int kMaxSpan = 6;          // search stencil is at most kMaxSpan cells per dimension
+constexpr float kFar = 1.0e6f;       // coordinate of dummy (padding) atoms
+constexpr float kBoxEmptyLo = 3.0e38f;
+
+struct Grid {
+    int periodic;
+    int nc[3];
+    int ncell;          // cells per replica
+    int n;              // atoms per replica
+    int R;              // replicas
+    int span;           // stencil cells per dimension (<= kMaxSpan)
+    double lo[3];       // grid origin (0 when periodic)
+    double box[3];      // box edges (periodic) or grid extent (non-periodic)
+    double cs[3];       // cell side per dimension
+    double inv_cs[3];
+    float rlist, rlist2;
+    float boxf[3];
+};
+
+struct BBox {
+    float lo[3], hi[3];
+};
+
+struct SciDesc {
+    int c0;        // first cluster (global cluster index)
+    int nci;       // clusters in this sci (1..8)
+    int replica;
+    int pad;
+};
+
+// ---- small helpers ----------------------------------------------------------------------------
+SDM_HD uint32_t spread3(uint32_t v) {  // 3 bits -> every third bit
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4);
+}
+
+SDM_HD bool box_empty(const BBox& b) { return b.lo[0] > b.hi[0]; }
+
+SDM_HD float box_dist2(const BBox& a, const BBox& b, float sx, float sy, float sz) {
+    // squared distance between AABB a and AABB b shifted by (sx,sy,sz)
+    float d2 = 0.f;
+    const float s[3] = {sx, sy, sz};
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int d = 0; d < 3; d++) {
+        float g1 = (b.lo[d] + s[d]) - a.hi[d];
+        float g2 = a.lo[d] - (b.hi[d] + s[d]);
+        float g = g1 > g2 ? g1 : g2;
+        if (g > 0.f) d2 += g * g;
+    }
+    return d2;
+}
+
+// Which side of an unordered cluster pair (A != B) carries it in its list: true when the cluster
+// playing the i role is A.  Symmetric in (A,B), balanced.
+SDM_HD bool owner_is_i(int A, int B) {
+    int lo = A < B ? A : B;
+    int hi = A < B ? B : A;
+    bool i_is_lo = ((lo ^ hi) & 1) != 0;
+    return i_is_lo ? (A == lo) : (A == hi);
+}
+
+SDM_HD uint32_t shift_code(int sx, int sy, int sz) {  // each in {-1,0,1}
+    return (uint32_t)((sx + 1) | ((sy + 1) << 2) | ((sz + 1) << 4));
+}
+SDM_HD int shift_x(uint32_t code) { return (int)(code & 3u) - 1; }
+SDM_HD int shift_y(uint32_t code) { return (int)((code >> 2) & 3u) - 1; }
+SDM_HD int shift_z(uint32_t code) { return (int)((code >> 4) & 3u) - 1; }
+constexpr uint32_t kShiftZero = 1u | (1u << 2) | (1u << 4);
+
+// ---- stage 1: sort key of an atom -------------------------------------------------------------
+// Wraps the position into the box (periodic), returns the key (global cell << 9 | Morton sub
+// code), the wrapped coordinates and the integer image that was applied (xw = x + img*L).
+SDM_HD uint32_t atom_key(const Grid& G, int replica, double x, double y, double z, float* xw_out,
+                         int* img_out) {
+    double p[3] = {x, y, z};
+    int c[3];
+    uint32_t sub[3];
+    for (int d = 0; d < 3; d++) {
+        double w = p[d];
+        int img = 0;
+        if (G.periodic) {
+            double f = floor(w / G.box[d]);
+            w -= f * G.box[d];
+            img = -(int)f;
+            if (w >= G.box[d]) { w -= G.box[d]; img -= 1; }
+            if (w < 0) { w = 0; }
+        }
+        double t = (w - G.lo[d]) * G.inv_cs[d];
+        int k = (int)floor(t);
+        if (k < 0) k = 0;
+        if (k >= G.nc[d]) k = G.nc[d] - 1;
+        double fr = t - (double)k;
+        int s = (int)(fr * 8.0);
+        if (s < 0) s = 0;
+        if (s > 7) s = 7;
+        c[d] = k;
+        sub[d] = (uint32_t)s;
+        xw_out[d] = (float)w;
+        img_out[d] = img;
+    }
+    uint32_t cell = (uint32_t)((c[2] * G.nc[1] + c[1]) * G.nc[0] + c[0]);
+    uint32_t g = (uint32_t)replica * (uint32_t)G.ncell + cell;
+    uint32_t m = spread3(sub[0]) | (spread3(sub[1]) << 1) | (spread3(sub[2]) << 2);
+    return (g << kSubBits) | m;
+}
+
+// ---- stage 2: bounding boxes --------------------------------------------------------------------
+// posq: sorted slots (float4 as 4 floats); a dummy slot has x >= kFar/2.
+SDM_HD BBox group_bbox(const float* posq4, int first_slot, int count) {
+    BBox b;
+    for (int d = 0; d < 3; d++) { b.lo[d] = kBoxEmptyLo; b.hi[d] = -kBoxEmptyLo; }
+    for (int s = first_slot; s < first_slot + count; s++) {
+        const float* p = posq4 + 4 * (size_t)s;
+        if (p[0] >= 0.5f * kFar) continue;
+        for (int d = 0; d < 3; d++) {
+            if (p[d] < b.lo[d]) b.lo[d] = p[d];
+            if (p[d] > b.hi[d]) b.hi[d] = p[d];
+        }
+    }
+    return b;
+}
+
+SDM_HD BBox box_union(const BBox& a, const BBox& b) {
+    BBox u;
+    for (int d = 0; d < 3; d++) {
+        u.lo[d] = a.lo[d] < b.lo[d] ? a.lo[d] : b.lo[d];
+        u.hi[d] = a.hi[d] > b.hi[d] ? a.hi[d] : b.hi[d];
+    }
+    return u;
+}
+
+// ---- stage 3: pair search ---------------------------------------------------------------------
+// Read-only view of what the search needs.
+struct SearchView {
+    Grid G;
+    const SciDesc* sci;        // [nsci]
+    const BBox* sci_box;       // [nsci]
+    const BBox* cl_box;        // [ncluster]  8-slot cluster boxes
+    const BBox* j4_box;        // [ncluster*2]
+    const int* cell_slot;      // [R*ncell + 1] first slot of every global cell (padded layout)
+};
+
+// Cell-coordinate range (unwrapped for periodic, clamped for non-periodic) the sci must scan.
+SDM_HD void search_range(const Grid& G, const BBox& b, int cmin[3], int cmax[3]) {
+    const float eps = 1.0e-4f;
+    for (int d = 0; d < 3; d++) {
+        double a = ((double)b.lo[d] - (double)G.rlist - eps - G.lo[d]) * G.inv_cs[d];
+        double c = ((double)b.hi[d] + (double)G.rlist + eps - G.lo[d]) * G.inv_cs[d];
+        int ia = (int)floor(a), ic = (int)floor(c);
+        if (!G.periodic) {
+            if (ia < 0) ia = 0;
+            if (ic < 0) ic = 0;
+            if (ia >= G.nc[d]) ia = G.nc[d] - 1;
+            if (ic >= G.nc[d]) ic = G.nc[d] - 1;
+        }
+        if (ic - ia + 1 > G.span) ic = ia + G.span - 1;  // guarded by the host-side span check
+        cmin[d] = ia;
+        cmax[d] = ic;
+    }
+}
+
+// One search item = (sci, stencil offset).  Visits the j-groups of the addressed cell and calls
+// emit(j4, shift_code, imask, diag) for every group that interacts with at least one cluster of
+// the sci under the ownership rule.  Returns the number of entries.
+template <class Emit>
+SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
+    const Grid& G = V.G;
+    const SciDesc sd = V.sci[isci];
+    const BBox sb = V.sci_box[isci];
+    if (box_empty(sb)) return 0;
+    int cmin[3], cmax[3];
+    search_range(G, sb, cmin, cmax);
+    const int ox = off % G.span, oy = (off / G.span) % G.span, oz = off / (G.span * G.span);
+    int u[3] = {cmin[0] + ox, cmin[1] + oy, cmin[2] + oz};
+    if (u[0] > cmax[0] || u[1] > cmax[1] || u[2] > cmax[2]) return 0;
+    int w[3], sh[3];
+    for (int d = 0; d < 3; d++) {
+        if (G.periodic) {
+            int q = u[d] >= 0 ? u[d] / G.nc[d] : -((-u[d] + G.nc[d] - 1) / G.nc[d]);
+            w[d] = u[d] - q * G.nc[d];
+            sh[d] = q;
+            if (q < -1 || q > 1) return 0;  // excluded by the host-side box-size check
+        } else {
+            w[d] = u[d];
+            sh[d] = 0;
+        }
+    }
+    const float sx = sh[0] * G.boxf[0], sy = sh[1] * G.boxf[1], sz = sh[2] * G.boxf[2];
+    const uint32_t code = shift_code(sh[0], sh[1], sh[2]);
+    const int gcell = sd.replica * G.ncell + (w[2] * G.nc[1] + w[1]) * G.nc[0] + w[0];
+    const int s0 = V.cell_slot[gcell], s1 = V.cell_slot[gcell + 1];
+    int count = 0;
+    for (int j4 = s0 / kJGroup; j4 < s1 / kJGroup; j4++) {
+        const BBox jb = V.j4_box[j4];
+        if (box_empty(jb)) continue;
+        if (box_dist2(sb, jb, sx, sy, sz) >= G.rlist2) continue;
+        const int B = j4 >> 1;
+        uint32_t imask = 0;
+        bool diag = false;
+        for (int ci = 0; ci < sd.nci; ci++) {
+            const int A = sd.c0 + ci;
+            bool own;
+            if (A == B) {
+                // a cluster against itself: zero shift -> triangle; a non-zero shift only once
+                own = (code == kShiftZero) || (code > kShiftZero);
+                if (code == kShiftZero) diag = true;
+            } else {
+                own = owner_is_i(A, B);
+            }
+            if (!own) continue;
+            if (box_dist2(V.cl_box[A], jb, sx, sy, sz) < G.rlist2) imask |= 1u << ci;
+        }
+        if (imask) {
+            emit(count, (uint32_t)j4 | (code << 26), imask, diag && ((imask >> (B - sd.c0)) & 1u));
+            count++;
+        }
+    }
+    return count;
+}
+
+// ---- stage 4: exclusion masks -------------------------------------------------------------------
+// Resolve an excluded atom pair (slots sa, sb) to (i-slot, j-slot) under the ownership rule.
+SDM_HD void exclusion_roles(int sa, int sb, int* si, int* sj) {
+    const int A = sa / kClusterSize, B = sb / kClusterSize;
+    if (A == B) {
+        *si = sa < sb ? sa : sb;   // triangle keeps j-slot > i-slot
+        *sj = sa < sb ? sb : sa;
+    } else if (owner_is_i(A, B)) {
+        *si = sa; *sj = sb;
+    } else {
+        *si = sb; *sj = sa;
+    }
+}
+
+// Triangle mask word of cluster-against-itself for the j-group half h (0/1).
+SDM_HD uint32_t triangle_mask(int h) {
+    uint32_t m = 0;
+    for (int tj = 0; tj < kJGroup; tj++)
+        for (int ti = 0; ti < kClusterSize; ti++)
+            if (h * kJGroup + tj > ti) m |= 1u << (tj * kClusterSize + ti);
+    return m;
+}
+
+}  // namespace nbl
+}  // namespace sdm

@@ -1,11 +1,742 @@
-// pairlist.cu -- cluster-pair list path.  (placeholder until the cluster kernel lands)
+// pairlist.cu -- builds the cluster-pair list on the device (per-item bodies from
+// nblist_core.h, CUB for the sort and the scans) and drives the cluster pair kernel.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "pairlist.h"
 #include "sdm_ctx.h"
 
-int sdm_ctx_init_pairlist(sdm_ctx* c) {
-    if (c->pair_mode == SDM_PAIR_CLUSTER) return sdm_fail(SDM_ERR_INVALID, "cluster pair mode not built");
+namespace sdm {
+
+using nbl::BBox;
+using nbl::Grid;
+using nbl::SciDesc;
+
+constexpr int kChunk = 32;  // default j-group entries per work unit
+
+struct PairList {
+    Grid G{};
+    int ncells = 0;          // R * ncell
+    int cell_cap = 0;        // allocated cells per replica
+    int nslot_cap = 0, ncl_cap = 0, nsci_cap = 0;
+    size_t entries_cap = 0, masks_cap = 0, units_cap = 0, items_cap = 0;
+    int chunk = kChunk;
+    // sizes of the current list (host copies)
+    int nslot = 0, ncl = 0, nsci = 0, nentries = 0, nmasks = 0, nunits = 0;
+
+    uint32_t *keys = nullptr, *keys_sorted = nullptr;
+    int *vals = nullptr, *vals_sorted = nullptr;
+    int *cell_first = nullptr, *cell_count = nullptr, *cell_pcount = nullptr, *cell_nsci = nullptr;
+    int *cell_slot = nullptr, *cell_sci = nullptr;
+    float4 *posq = nullptr, *posq_build = nullptr;
+    float2* par = nullptr;
+    int *atom = nullptr, *img = nullptr, *slot_of = nullptr;
+    BBox *cl_box = nullptr, *j4_box = nullptr, *sci_box = nullptr;
+    SciDesc* sci = nullptr;
+    int* cl_sci = nullptr;
+    int *item_count = nullptr, *item_off = nullptr;
+    uint2* entries = nullptr;
+    int *entry_flag = nullptr, *entry_midx = nullptr;
+    uint32_t* masks = nullptr;
+    int *sci_nunits = nullptr, *sci_unit_off = nullptr;
+    Unit* units = nullptr;
+    int* part_off = nullptr;    // [R+1]
+    double* epart = nullptr;
+    long long* cpart = nullptr;
+    double* minmax = nullptr;   // [6] non-periodic extent reduction
+    const int* excl_pairs = nullptr;  // [2*n_excl_unique] a<b
+    int n_excl = 0;
+    void* cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    int* h_counts = nullptr;    // pinned [8]
+    double* h_minmax = nullptr; // pinned [6]
+    std::vector<void*> allocs;
+    double density_hint = 0;    // atoms / nm^3 used to size cells
+};
+
+namespace {
+
+#define PL_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            char buf_[512];                                                                    \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                      \
+            return sdm_fail(SDM_ERR_CUDA, buf_);                                               \
+        }                                                                                      \
+    } while (0)
+
+template <class T>
+int pl_alloc(PairList* pl, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    PL_CUDA(cudaMalloc(&q, bytes));
+    PL_CUDA(cudaMemset(q, 0, bytes));
+    pl->allocs.push_back(q);
+    *p = static_cast<T*>(q);
     return SDM_OK;
 }
-void sdm_ctx_free_pairlist(sdm_ctx*) {}
-int sdm_ctx_pairlist_eval(sdm_ctx*) { return sdm_fail(SDM_ERR_INVALID, "cluster pair mode not built"); }
-int sdm_ctx_pairlist_emit(sdm_ctx*, int, int*, int*, int) { return sdm_fail(SDM_ERR_INVALID, "cluster pair mode not built"); }
-int sdm_ctx_pairlist_info(sdm_ctx*, const char*, double*) { return SDM_ERR_INVALID; }
+
+template <class T>
+int pl_realloc(PairList* pl, T** p, size_t count) {
+    if (*p) {
+        auto it = std::find(pl->allocs.begin(), pl->allocs.end(), (void*)*p);
+        if (it != pl->allocs.end()) pl->allocs.erase(it);
+        PL_CUDA(cudaFree(*p));
+        *p = nullptr;
+    }
+    return pl_alloc(pl, p, count);
+}
+
+// ---- device wrappers around the per-item bodies ------------------------------------------------
+__global__ void key_kernel(Grid G, const double* __restrict__ pos_all, uint32_t* keys, int* vals) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G.R * G.n) return;
+    const int r = t / G.n;
+    const double* p = pos_all + 3 * (size_t)t;
+    float xw[3];
+    int img[3];
+    keys[t] = nbl::atom_key(G, r, p[0], p[1], p[2], xw, img);
+    vals[t] = t;
+}
+
+__global__ void cell_bounds_kernel(int total, const uint32_t* __restrict__ keys_sorted,
+                                   int* cell_first, int* cell_count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const uint32_t c = keys_sorted[k] >> nbl::kSubBits;
+    if (k == 0 || (keys_sorted[k - 1] >> nbl::kSubBits) != c) cell_first[c] = k;
+    if (k == total - 1 || (keys_sorted[k + 1] >> nbl::kSubBits) != c) {
+        // the matching "first" is written by another thread of this launch; store the end and
+        // let the next kernel subtract
+        cell_count[c] = k + 1;
+    }
+}
+
+__global__ void cell_sizes_kernel(int ncells, const int* __restrict__ cell_first,
+                                  int* cell_count /* in: end or 0, out: count */, int* cell_pcount,
+                                  int* cell_nsci) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int end = cell_count[c];
+    const int cnt = end > 0 ? end - cell_first[c] : 0;
+    cell_count[c] = cnt;
+    const int pc = (cnt + nbl::kClusterSize - 1) / nbl::kClusterSize * nbl::kClusterSize;
+    cell_pcount[c] = pc;
+    const int ncl = pc / nbl::kClusterSize;
+    cell_nsci[c] = (ncl + nbl::kMaxCi - 1) / nbl::kMaxCi;
+}
+
+__global__ void fill_slots_kernel(Grid G, Topology T, int total, const double* __restrict__ pos_all,
+                                  const uint32_t* __restrict__ keys_sorted,
+                                  const int* __restrict__ vals_sorted,
+                                  const int* __restrict__ cell_first, const int* __restrict__ cell_slot,
+                                  float4* posq, float2* par, int* atom, int* img, int* slot_of) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const uint32_t c = keys_sorted[k] >> nbl::kSubBits;
+    const int ga = vals_sorted[k];
+    const int r = ga / G.n, a = ga - r * G.n;
+    const int slot = cell_slot[c] + (k - cell_first[c]);
+    const double* p = pos_all + 3 * (size_t)ga;
+    float xw[3];
+    int im[3];
+    nbl::atom_key(G, r, p[0], p[1], p[2], xw, im);
+    const float4 pf = T.parf[a];
+    posq[slot] = make_float4(xw[0], xw[1], xw[2], pf.x);
+    par[slot] = make_float2(pf.y, pf.z);
+    atom[slot] = ga;
+    img[slot] = (im[0] + 512) | ((im[1] + 512) << 10) | ((im[2] + 512) << 20);
+    slot_of[ga] = slot;
+}
+
+__global__ void fill_dummies_kernel(int ncells, const int* __restrict__ cell_count,
+                                    const int* __restrict__ cell_slot, float4* posq, float2* par,
+                                    int* atom, int* img) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int s0 = cell_slot[c] + cell_count[c], s1 = cell_slot[c + 1];
+    for (int s = s0; s < s1; s++) {
+        posq[s] = make_float4(nbl::kFar, nbl::kFar, nbl::kFar, 0.f);
+        par[s] = make_float2(0.f, 0.f);
+        atom[s] = -1;
+        img[s] = 512 | (512 << 10) | (512 << 20);
+    }
+}
+
+__global__ void bbox_kernel(int ncl, const float4* __restrict__ posq, BBox* cl_box, BBox* j4_box) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncl) return;
+    const float* p = reinterpret_cast<const float*>(posq);
+    const BBox a = nbl::group_bbox(p, c * 8, 4), b = nbl::group_bbox(p, c * 8 + 4, 4);
+    j4_box[2 * c] = a;
+    j4_box[2 * c + 1] = b;
+    cl_box[c] = nbl::box_union(a, b);
+}
+
+__global__ void sci_kernel(Grid G, int ncells, const int* __restrict__ cell_slot,
+                           const int* __restrict__ cell_sci, const BBox* __restrict__ cl_box,
+                           SciDesc* sci, BBox* sci_box, int* cl_sci) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int cl0 = cell_slot[c] / nbl::kClusterSize, cl1 = cell_slot[c + 1] / nbl::kClusterSize;
+    int s = cell_sci[c];
+    for (int k = cl0; k < cl1; k += nbl::kMaxCi, s++) {
+        SciDesc d;
+        d.c0 = k;
+        d.nci = min(nbl::kMaxCi, cl1 - k);
+        d.replica = c / G.ncell;
+        d.pad = 0;
+        BBox b = cl_box[k];
+        cl_sci[k] = s;
+        for (int j = 1; j < d.nci; j++) {
+            b = nbl::box_union(b, cl_box[k + j]);
+            cl_sci[k + j] = s;
+        }
+        sci[s] = d;
+        sci_box[s] = b;
+    }
+}
+
+struct CountEmit {
+    __device__ void operator()(int, uint32_t, uint32_t, bool) const {}
+};
+struct FillEmit {
+    uint2* out;
+    int* flag;
+    int base;
+    __device__ void operator()(int k, uint32_t w0, uint32_t imask, bool diag) const {
+        out[base + k] = make_uint2(w0, imask);
+        flag[base + k] = diag ? 1 : 0;
+    }
+};
+
+__global__ void search_count_kernel(nbl::SearchView V, int nsci, int noff, int* item_count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsci * noff) return;
+    item_count[t] = nbl::search_item(V, t / noff, t % noff, CountEmit());
+}
+
+__global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
+                                   const int* __restrict__ item_off, uint2* entries, int* flag,
+                                   int cap) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsci * noff) return;
+    const int base = item_off[t];
+    if (base >= cap) return;
+    nbl::search_item(V, t / noff, t % noff, FillEmit{entries, flag, base});
+}
+
+// Exclusions.  pass 0 flags the entries that need a mask set, pass 1 clears the pair's bit.
+__global__ void exclusion_kernel(Grid G, int n_excl, const int* __restrict__ excl_pairs,
+                                 const int* __restrict__ slot_of, const int* __restrict__ cl_sci,
+                                 const SciDesc* __restrict__ sci, const int* __restrict__ item_off,
+                                 int noff, const uint2* __restrict__ entries, int* entry_flag,
+                                 uint32_t* masks, int pass) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G.R * n_excl) return;
+    const int r = t / n_excl, k = t - r * n_excl;
+    const int sa = slot_of[r * G.n + excl_pairs[2 * k]], sb = slot_of[r * G.n + excl_pairs[2 * k + 1]];
+    int si, sj;
+    nbl::exclusion_roles(sa, sb, &si, &sj);
+    const int isci = cl_sci[si / nbl::kClusterSize];
+    const int ci = si / nbl::kClusterSize - sci[isci].c0;
+    const uint32_t j4 = (uint32_t)(sj / nbl::kJGroup);
+    const uint32_t bit = 1u << ((sj % nbl::kJGroup) * nbl::kClusterSize + (si % nbl::kClusterSize));
+    const int e0 = item_off[isci * noff], e1 = item_off[(isci + 1) * noff];
+    for (int e = e0; e < e1; e++) {
+        const uint2 ent = entries[e];
+        if ((ent.x & 0x3ffffffu) != j4) continue;
+        if (pass == 0) {
+            entry_flag[e] = 1;
+        } else {
+            const uint32_t midx = ent.y >> 8;
+            atomicAnd(masks + (size_t)midx * nbl::kMaxCi + ci, ~bit);
+        }
+    }
+}
+
+// Assign mask-set indices (1-based; 0 = all ones) and initialise the sets.
+__global__ void mask_init_kernel(int nentries, const int* __restrict__ entry_flag,
+                                 const int* __restrict__ entry_midx, const int* __restrict__ item_off,
+                                 uint2* entries, uint32_t* masks, const SciDesc* __restrict__ sci,
+                                 const int* __restrict__ entry_sci) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nentries || !entry_flag[e]) return;
+    const uint32_t midx = (uint32_t)entry_midx[e] + 1u;
+    uint2 ent = entries[e];
+    ent.y = (ent.y & 0xffu) | (midx << 8);
+    entries[e] = ent;
+    const int j4 = (int)(ent.x & 0x3ffffffu);
+    const uint32_t code = ent.x >> 26;
+    const SciDesc sd = sci[entry_sci[e]];
+    for (int ci = 0; ci < nbl::kMaxCi; ci++) {
+        uint32_t m = 0xffffffffu;
+        if (code == nbl::kShiftZero && (j4 >> 1) == sd.c0 + ci) m = nbl::triangle_mask(j4 & 1);
+        masks[(size_t)midx * nbl::kMaxCi + ci] = m;
+    }
+}
+
+// entry -> sci map (needed by mask_init) and units
+__global__ void entry_sci_kernel(int nsci, int noff, const int* __restrict__ item_off, int* entry_sci) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsci) return;
+    for (int e = item_off[s * noff]; e < item_off[(s + 1) * noff]; e++) entry_sci[e] = s;
+}
+
+__global__ void sci_units_count_kernel(int nsci, int noff, const int* __restrict__ item_off, int chunk,
+                                       int* sci_nunits) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsci) return;
+    const int len = item_off[(s + 1) * noff] - item_off[s * noff];
+    sci_nunits[s] = (len + chunk - 1) / chunk;
+}
+
+__global__ void units_fill_kernel(int nsci, int noff, const int* __restrict__ item_off, int chunk,
+                                  const int* __restrict__ sci_unit_off, Unit* units) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsci) return;
+    const int e0 = item_off[s * noff], e1 = item_off[(s + 1) * noff];
+    int u = sci_unit_off[s];
+    for (int e = e0; e < e1; e += chunk, u++) units[u] = Unit{s, e, min(e + chunk, e1), 0};
+}
+
+__global__ void part_off_kernel(Grid G, const int* __restrict__ cell_sci,
+                                const int* __restrict__ sci_unit_off, int nsci, int nunits, int* part_off) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > G.R) return;
+    if (r == G.R) { part_off[r] = nunits; return; }
+    const int s = cell_sci[r * G.ncell];
+    part_off[r] = s < nsci ? sci_unit_off[s] : nunits;
+}
+
+__global__ void minmax_kernel(int total, const double* __restrict__ pos, double* out) {
+    // single block reduction; non-periodic systems only, at list-build time
+    __shared__ double smin[3][256], smax[3][256];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int k = threadIdx.x; k < total; k += blockDim.x)
+        for (int d = 0; d < 3; d++) {
+            const double v = pos[3 * (size_t)k + d];
+            lo[d] = fmin(lo[d], v);
+            hi[d] = fmax(hi[d], v);
+        }
+    for (int d = 0; d < 3; d++) { smin[d][threadIdx.x] = lo[d]; smax[d][threadIdx.x] = hi[d]; }
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int d = 0; d < 3; d++) {
+                smin[d][threadIdx.x] = fmin(smin[d][threadIdx.x], smin[d][threadIdx.x + s]);
+                smax[d][threadIdx.x] = fmax(smax[d][threadIdx.x], smax[d][threadIdx.x + s]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int d = 0; d < 3; d++) { out[d] = smin[d][0]; out[3 + d] = smax[d][0]; }
+}
+
+inline int blocks(long long n, int t = 256) { return (int)((n + t - 1) / t); }
+
+// Choose the cell grid.  Cells hold ~40 atoms (5 clusters) at the system's density and are at
+// least rlist/2 wide so that the search stencil stays within kMaxSpan cells per dimension.
+int setup_grid(sdm_ctx* c, PairList* pl, const double lo[3], const double ext[3]) {
+    Grid& G = pl->G;
+    const double rlist = c->T.rc + c->opt.skin;
+    G.periodic = c->T.method == SDM_CUTOFF_PERIODIC ? 1 : 0;
+    G.n = c->n;
+    G.R = c->R;
+    G.rlist = (float)rlist;
+    G.rlist2 = (float)(rlist * rlist);
+    double vol = ext[0] * ext[1] * ext[2];
+    double density = vol > 0 ? c->n / vol : 100.0;
+    double side = std::cbrt(40.0 / std::max(density, 1e-6));
+    side = std::max(side, 0.5 * rlist + 1e-3);
+    for (int iter = 0; iter < 64; iter++) {
+        long long ncell = 1;
+        int span = 1;
+        for (int d = 0; d < 3; d++) {
+            int nc = (int)std::floor(ext[d] / side);
+            if (nc < 1) nc = 1;
+            G.nc[d] = nc;
+            G.cs[d] = ext[d] / nc;
+            G.inv_cs[d] = 1.0 / G.cs[d];
+            G.lo[d] = lo[d];
+            G.box[d] = ext[d];
+            G.boxf[d] = (float)ext[d];
+            ncell *= nc;
+            int sp = (int)std::floor((G.cs[d] + 2 * rlist + 3e-4) / G.cs[d]) + 2;
+            if (!G.periodic) sp = std::min(sp, nc);
+            span = std::max(span, sp);
+        }
+        if (span <= nbl::kMaxSpan && ncell <= pl->cell_cap) {
+            G.ncell = (int)ncell;
+            G.span = span;
+            return SDM_OK;
+        }
+        side *= 1.1;
+    }
+    return sdm_fail(SDM_ERR_INVALID, "could not fit a cell grid (box too anisotropic for the cluster path)");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------------
+static int build_list(sdm_ctx* c) {
+    PairList* pl = c->pl;
+    cudaStream_t s = c->stream;
+    const int n = c->n, R = c->R, total = n * R;
+
+    if (c->T.method != SDM_CUTOFF_PERIODIC) {
+        minmax_kernel<<<1, 256, 0, s>>>(total, c->d_pos, pl->minmax);
+        PL_CUDA(cudaMemcpyAsync(pl->h_minmax, pl->minmax, 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        double lo[3], ext[3];
+        for (int d = 0; d < 3; d++) {
+            lo[d] = pl->h_minmax[d] - 1e-3;
+            ext[d] = std::max(pl->h_minmax[3 + d] - pl->h_minmax[d] + 2e-3, 1e-2);
+        }
+        if (int rc = setup_grid(c, pl, lo, ext)) return rc;
+        c->launches += 1;
+    }
+    const Grid& G = pl->G;
+    pl->ncells = R * G.ncell;
+    const int ncells = pl->ncells;
+    const int noff = G.span * G.span * G.span;
+
+    key_kernel<<<blocks(total), 256, 0, s>>>(G, c->d_pos, pl->keys, pl->vals);
+    int key_bits = nbl::kSubBits;
+    while ((1ll << (key_bits - nbl::kSubBits)) < ncells) key_bits++;
+    PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->keys, pl->keys_sorted,
+                                            pl->vals, pl->vals_sorted, total, 0, std::min(key_bits + 1, 32), s));
+    PL_CUDA(cudaMemsetAsync(pl->cell_count, 0, sizeof(int) * (size_t)(ncells + 1), s));
+    PL_CUDA(cudaMemsetAsync(pl->cell_first, 0, sizeof(int) * (size_t)(ncells + 1), s));
+    cell_bounds_kernel<<<blocks(total), 256, 0, s>>>(total, pl->keys_sorted, pl->cell_first, pl->cell_count);
+    cell_sizes_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_first, pl->cell_count,
+                                                    pl->cell_pcount, pl->cell_nsci);
+    // exclusive scans over ncells+1 elements (the extra zero element yields the totals)
+    PL_CUDA(cudaMemsetAsync(pl->cell_pcount + ncells, 0, sizeof(int), s));
+    PL_CUDA(cudaMemsetAsync(pl->cell_nsci + ncells, 0, sizeof(int), s));
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->cell_pcount, pl->cell_slot, ncells + 1, s));
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->cell_nsci, pl->cell_sci, ncells + 1, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[0], pl->cell_slot + ncells, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[1], pl->cell_sci + ncells, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+    pl->nslot = pl->h_counts[0];
+    pl->nsci = pl->h_counts[1];
+    pl->ncl = pl->nslot / nbl::kClusterSize;
+    if (pl->nslot > pl->nslot_cap || pl->nsci > pl->nsci_cap)
+        return sdm_fail(SDM_ERR_CAPACITY, "internal: slot capacity exceeded");
+
+    fill_slots_kernel<<<blocks(total), 256, 0, s>>>(G, c->T, total, c->d_pos, pl->keys_sorted, pl->vals_sorted,
+                                                   pl->cell_first, pl->cell_slot, pl->posq, pl->par,
+                                                   pl->atom, pl->img, pl->slot_of);
+    fill_dummies_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_count, pl->cell_slot, pl->posq,
+                                                      pl->par, pl->atom, pl->img);
+    bbox_kernel<<<blocks(pl->ncl), 256, 0, s>>>(pl->ncl, pl->posq, pl->cl_box, pl->j4_box);
+    sci_kernel<<<blocks(ncells), 256, 0, s>>>(G, ncells, pl->cell_slot, pl->cell_sci, pl->cl_box, pl->sci,
+                                             pl->sci_box, pl->cl_sci);
+    c->launches += 9;
+
+    nbl::SearchView V;
+    V.G = G;
+    V.sci = pl->sci;
+    V.sci_box = pl->sci_box;
+    V.cl_box = pl->cl_box;
+    V.j4_box = pl->j4_box;
+    V.cell_slot = pl->cell_slot;
+    const long long nitems = (long long)pl->nsci * noff;
+    if ((size_t)nitems + 1 > pl->items_cap) {
+        pl->items_cap = (size_t)nitems + 1;
+        if (int rc = pl_realloc(pl, &pl->item_count, pl->items_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->item_off, pl->items_cap)) return rc;
+    }
+    search_count_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_count);
+    PL_CUDA(cudaMemsetAsync(pl->item_count + nitems, 0, sizeof(int), s));
+    {
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, pl->item_count, pl->item_off, (int)nitems + 1, s);
+        if (need > pl->cub_tmp_bytes) {
+            if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
+            pl->cub_tmp_bytes = need;
+        }
+    }
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->item_count, pl->item_off, (int)nitems + 1, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[2], pl->item_off + nitems, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+    pl->nentries = pl->h_counts[2];
+    if ((size_t)pl->nentries > pl->entries_cap) {
+        pl->entries_cap = (size_t)(pl->nentries * 1.25) + 1024;
+        if (int rc = pl_realloc(pl, &pl->entries, pl->entries_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->entry_flag, pl->entries_cap + 1)) return rc;
+        if (int rc = pl_realloc(pl, &pl->entry_midx, pl->entries_cap + 1)) return rc;
+    }
+    search_fill_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_off, pl->entries,
+                                                          pl->entry_flag, (int)pl->entries_cap);
+    c->launches += 3;
+
+    // exclusion masks
+    if (pl->n_excl > 0)
+        exclusion_kernel<<<blocks((long long)R * pl->n_excl), 256, 0, s>>>(
+            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->item_off, noff,
+            pl->entries, pl->entry_flag, pl->masks, 0);
+    PL_CUDA(cudaMemsetAsync(pl->entry_flag + pl->nentries, 0, sizeof(int), s));
+    {
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, pl->entry_flag, pl->entry_midx, pl->nentries + 1, s);
+        if (need > pl->cub_tmp_bytes) {
+            if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
+            pl->cub_tmp_bytes = need;
+        }
+    }
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->entry_flag, pl->entry_midx, pl->nentries + 1, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[3], pl->entry_midx + pl->nentries, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // units
+    sci_units_count_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, noff, pl->item_off, pl->chunk, pl->sci_nunits);
+    PL_CUDA(cudaMemsetAsync(pl->sci_nunits + pl->nsci, 0, sizeof(int), s));
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->sci_nunits, pl->sci_unit_off, pl->nsci + 1, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[4], pl->sci_unit_off + pl->nsci, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+    pl->nmasks = pl->h_counts[3];
+    pl->nunits = pl->h_counts[4];
+    if ((size_t)pl->nmasks + 1 > pl->masks_cap) {
+        pl->masks_cap = (size_t)(pl->nmasks * 1.25) + 256;
+        if (int rc = pl_realloc(pl, &pl->masks, pl->masks_cap * nbl::kMaxCi)) return rc;
+    }
+    if ((size_t)pl->nunits > pl->units_cap) {
+        pl->units_cap = (size_t)(pl->nunits * 1.25) + 256;
+        if (int rc = pl_realloc(pl, &pl->units, pl->units_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->epart, pl->units_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->cpart, pl->units_cap)) return rc;
+    }
+    {
+        // entry -> sci map reuses item_count's storage when large enough, else a scratch alloc
+        int* entry_sci = nullptr;
+        if ((size_t)pl->nentries <= pl->items_cap) entry_sci = pl->item_count;
+        else {
+            pl->items_cap = (size_t)pl->nentries + 1;
+            if (int rc = pl_realloc(pl, &pl->item_count, pl->items_cap)) return rc;
+            entry_sci = pl->item_count;
+        }
+        entry_sci_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, noff, pl->item_off, entry_sci);
+        // mask set 0 = all ones
+        PL_CUDA(cudaMemsetAsync(pl->masks, 0xff, sizeof(uint32_t) * nbl::kMaxCi, s));
+        mask_init_kernel<<<blocks(pl->nentries), 256, 0, s>>>(pl->nentries, pl->entry_flag, pl->entry_midx,
+                                                             pl->item_off, pl->entries, pl->masks, pl->sci, entry_sci);
+    }
+    if (pl->n_excl > 0)
+        exclusion_kernel<<<blocks((long long)R * pl->n_excl), 256, 0, s>>>(
+            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->item_off, noff,
+            pl->entries, pl->entry_flag, pl->masks, 1);
+    units_fill_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, noff, pl->item_off, pl->chunk,
+                                                      pl->sci_unit_off, pl->units);
+    part_off_kernel<<<blocks(R + 1), 256, 0, s>>>(G, pl->cell_sci, pl->sci_unit_off, pl->nsci, pl->nunits, pl->part_off);
+    PL_CUDA(cudaMemcpyAsync(pl->posq_build, pl->posq, sizeof(float4) * (size_t)pl->nslot, cudaMemcpyDeviceToDevice, s));
+    c->launches += 8;
+    PL_CUDA(cudaGetLastError());
+
+    // the fixed-point accumulators are indexed by slot: start from zero for the new layout
+    PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
+    c->list_valid = true;
+    c->list_age = 0;
+    c->n_builds++;
+    return SDM_OK;
+}
+
+}  // namespace sdm
+
+// ---------------------------------------------------------------------------------------------
+// ctx hooks
+// ---------------------------------------------------------------------------------------------
+using namespace sdm;
+
+int sdm_ctx_init_pairlist(sdm_ctx* c) {
+    if (c->pair_mode != SDM_PAIR_CLUSTER) return SDM_OK;
+    if (c->T.method == SDM_NOCUTOFF)
+        return sdm_fail(SDM_ERR_INVALID, "the cluster pair path needs a cutoff method; use SDM_PAIR_ALLPAIRS");
+    const int n = c->n, R = c->R, total = n * R;
+    PairList* pl = new PairList();
+    c->pl = pl;
+    // capacities
+    const double rlist = c->T.rc + c->opt.skin;
+    if (c->T.method == SDM_CUTOFF_PERIODIC) {
+        for (int d = 0; d < 3; d++)
+            if (c->T.box[d] < 2.0 * rlist)
+                return sdm_fail(SDM_ERR_BOX, "periodic box smaller than 2*(cutoff+skin): use SDM_PAIR_ALLPAIRS or a smaller skin");
+    }
+    pl->cell_cap = std::max(64, n / 8 + 64);
+    if (c->T.method == SDM_CUTOFF_PERIODIC) {
+        double lo[3] = {0, 0, 0};
+        if (int rc = setup_grid(c, pl, lo, c->T.box)) return rc;
+    } else {
+        pl->G.ncell = pl->cell_cap;  // sized at build time from the positions
+    }
+    const int ncell_cap = c->T.method == SDM_CUTOFF_PERIODIC ? pl->G.ncell : pl->cell_cap;
+    const int ncells_cap = R * ncell_cap;
+    pl->nslot_cap = total + 7 * ncells_cap + 8;
+    pl->nslot_cap = (pl->nslot_cap + 7) / 8 * 8;
+    pl->ncl_cap = pl->nslot_cap / 8;
+    pl->nsci_cap = pl->ncl_cap / 8 + ncells_cap + 1;
+    pl->chunk = kChunk;
+
+#define A(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+    A(pl_alloc(pl, &pl->keys, total));
+    A(pl_alloc(pl, &pl->keys_sorted, total));
+    A(pl_alloc(pl, &pl->vals, total));
+    A(pl_alloc(pl, &pl->vals_sorted, total));
+    A(pl_alloc(pl, &pl->cell_first, ncells_cap + 1));
+    A(pl_alloc(pl, &pl->cell_count, ncells_cap + 1));
+    A(pl_alloc(pl, &pl->cell_pcount, ncells_cap + 1));
+    A(pl_alloc(pl, &pl->cell_nsci, ncells_cap + 1));
+    A(pl_alloc(pl, &pl->cell_slot, ncells_cap + 2));
+    A(pl_alloc(pl, &pl->cell_sci, ncells_cap + 2));
+    A(pl_alloc(pl, &pl->posq, pl->nslot_cap));
+    A(pl_alloc(pl, &pl->posq_build, pl->nslot_cap));
+    A(pl_alloc(pl, &pl->par, pl->nslot_cap));
+    A(pl_alloc(pl, &pl->atom, pl->nslot_cap));
+    A(pl_alloc(pl, &pl->img, pl->nslot_cap));
+    A(pl_alloc(pl, &pl->slot_of, total));
+    A(pl_alloc(pl, &pl->cl_box, pl->ncl_cap));
+    A(pl_alloc(pl, &pl->j4_box, 2 * (size_t)pl->ncl_cap));
+    A(pl_alloc(pl, &pl->sci_box, pl->nsci_cap));
+    A(pl_alloc(pl, &pl->sci, pl->nsci_cap));
+    A(pl_alloc(pl, &pl->cl_sci, pl->ncl_cap));
+    A(pl_alloc(pl, &pl->sci_nunits, pl->nsci_cap + 1));
+    A(pl_alloc(pl, &pl->sci_unit_off, pl->nsci_cap + 1));
+    A(pl_alloc(pl, &pl->part_off, R + 1));
+    A(pl_alloc(pl, &pl->minmax, 6));
+    pl->items_cap = (size_t)pl->nsci_cap * 64 + 1;
+    A(pl_alloc(pl, &pl->item_count, pl->items_cap));
+    A(pl_alloc(pl, &pl->item_off, pl->items_cap));
+    // initial guesses; grown on demand at build time
+    pl->entries_cap = (size_t)total * 8 + 1024;
+    A(pl_alloc(pl, &pl->entries, pl->entries_cap));
+    A(pl_alloc(pl, &pl->entry_flag, pl->entries_cap + 1));
+    A(pl_alloc(pl, &pl->entry_midx, pl->entries_cap + 1));
+    pl->masks_cap = (size_t)total / 2 + 256;
+    A(pl_alloc(pl, &pl->masks, pl->masks_cap * nbl::kMaxCi));
+    pl->units_cap = pl->entries_cap / 8 + 256;
+    A(pl_alloc(pl, &pl->units, pl->units_cap));
+    A(pl_alloc(pl, &pl->epart, pl->units_cap));
+    A(pl_alloc(pl, &pl->cpart, pl->units_cap));
+    {
+        // unique exclusion pairs a<b from the CSR the ctx already holds
+        std::vector<int> ex;
+        for (int i = 0; i < n; i++)
+            for (int k = c->h_excl_start[i]; k < c->h_excl_start[i + 1]; k++)
+                if (c->h_excl_idx[k] > i) { ex.push_back(i); ex.push_back(c->h_excl_idx[k]); }
+        pl->n_excl = (int)ex.size() / 2;
+        int* d = nullptr;
+        A(pl_alloc(pl, &d, ex.size()));
+        if (!ex.empty()) PL_CUDA(cudaMemcpy(d, ex.data(), ex.size() * sizeof(int), cudaMemcpyHostToDevice));
+        pl->excl_pairs = d;
+    }
+    {
+        size_t a = 0, b = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, a, pl->keys, pl->keys_sorted, pl->vals, pl->vals_sorted, total, 0, 32, c->stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, b, pl->item_count, pl->item_off, (int)std::max<size_t>(pl->items_cap, pl->entries_cap + 1), c->stream);
+        pl->cub_tmp_bytes = std::max(a, b) + 256;
+        A(pl_alloc(pl, (char**)&pl->cub_tmp, pl->cub_tmp_bytes));
+    }
+    PL_CUDA(cudaMallocHost((void**)&pl->h_counts, 8 * sizeof(int)));
+    PL_CUDA(cudaMallocHost((void**)&pl->h_minmax, 6 * sizeof(double)));
+    // the accumulators live in the global slot space for this path
+    {
+        long long* acc = nullptr;
+        A(pl_alloc(pl, &acc, 3 * (size_t)pl->nslot_cap));
+        c->B.f1acc = acc;
+        c->B.acc_rstride = 0;
+        c->B.nslot = pl->nslot_cap;
+        c->B.slot_of = pl->slot_of;
+    }
+#undef A
+    c->list_valid = false;
+    return SDM_OK;
+}
+
+void sdm_ctx_free_pairlist(sdm_ctx* c) {
+    if (!c->pl) return;
+    for (void* p : c->pl->allocs) cudaFree(p);
+    if (c->pl->h_counts) cudaFreeHost(c->pl->h_counts);
+    if (c->pl->h_minmax) cudaFreeHost(c->pl->h_minmax);
+    delete c->pl;
+    c->pl = nullptr;
+}
+
+static PairListView make_view(const sdm_ctx* c) {
+    const PairList* pl = c->pl;
+    PairListView V;
+    V.G = pl->G;
+    V.posq = pl->posq;
+    V.par = pl->par;
+    V.atom = pl->atom;
+    V.sci = pl->sci;
+    V.entries = pl->entries;
+    V.masks = pl->masks;
+    V.units = pl->units;
+    V.nunits = pl->nunits;
+    V.nslot_cap = pl->nslot_cap;
+    return V;
+}
+
+int sdm_ctx_pairlist_eval(sdm_ctx* c) {
+    PairList* pl = c->pl;
+    if (!pl) return sdm_fail(SDM_ERR_INVALID, "cluster pair list not initialised");
+    cudaStream_t s = c->stream;
+    const bool rebuild = !c->list_valid || c->list_age >= c->opt.nstlist;
+    if (rebuild) {
+        if (int rc = build_list(c)) return rc;
+    } else {
+        const float hs = 0.5f * (float)c->opt.skin;
+        launch_refresh(c->T, pl->G, pl->nslot, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq,
+                       hs * hs, c->B.flags, s);
+        c->launches++;
+    }
+    c->list_age++;
+    // partial-sum buffers of this path
+    c->B.epart = pl->epart;
+    c->B.cpart = pl->cpart;
+    c->B.part_off = pl->part_off;
+    launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart,
+                        c->opt.exact_cutoff, nullptr, nullptr, 0, -1, s);
+    c->launches++;
+    PL_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap) {
+    PairList* pl = c->pl;
+    if (!pl || !c->list_valid) return sdm_fail(SDM_ERR_INVALID, "no pair list built yet: call sdm_eval first");
+    // scratch accumulators so that the debug pass does not disturb the real ones
+    long long* scratch = nullptr;
+    PL_CUDA(cudaMalloc((void**)&scratch, sizeof(long long) * 3 * (size_t)pl->nslot_cap));
+    launch_pair_cluster(c->T, make_view(c), c->d_pos, scratch, pl->epart, pl->cpart, c->opt.exact_cutoff,
+                        d_counter, d_pairs, cap, replica, c->stream);
+    PL_CUDA(cudaStreamSynchronize(c->stream));
+    PL_CUDA(cudaFree(scratch));
+    return SDM_OK;
+}
+
+int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
+    if (!c->pl) return SDM_ERR_INVALID;
+    const PairList* pl = c->pl;
+    std::string k(key);
+    if (k == "n_slots") *value = pl->nslot;
+    else if (k == "n_clusters") *value = pl->ncl;
+    else if (k == "n_sci") *value = pl->nsci;
+    else if (k == "n_entries") *value = pl->nentries;
+    else if (k == "n_masks") *value = pl->nmasks;
+    else if (k == "n_units") *value = pl->nunits;
+    else if (k == "n_cells") *value = pl->G.ncell;
+    else if (k == "cell_span") *value = pl->G.span;
+    else if (k == "rlist") *value = pl->G.rlist;
+    else return SDM_ERR_INVALID;
+    return SDM_OK;
+}

@@ -1,0 +1,42 @@
+// pairlist.h -- device-resident cluster-pair list of a context and the launchers that build
+// and consume it (internal).
+#pragma once
+
+#include "nblist_core.h"
+#include "sdm_kernels.h"
+
+namespace sdm {
+
+struct Unit {
+    int sci;      // supercluster
+    int begin;    // first entry (global index into entries)
+    int end;      // one past the last entry
+    int pad;
+};
+
+// Everything the pair kernel reads.
+struct PairListView {
+    nbl::Grid G;
+    const float4* posq;          // [nslot] sorted, wrapped (+ image) positions, .w = q*sqrt(K)
+    const float2* par;           // [nslot] (sigma/2, 2*sqrt(eps)); (0,0) for dummies
+    const int* atom;             // [nslot] replica*n + atom, or -1 for a dummy slot
+    const nbl::SciDesc* sci;     // [nsci]
+    const uint2* entries;        // {j4 | shift<<26, imask | mask_index<<8}
+    const uint32_t* masks;       // [(nmasks+1)*8]; set 0 = all ones
+    const Unit* units;           // [nunits]
+    int nunits;
+    int nslot_cap;               // accumulator plane stride
+};
+
+void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
+                         long long* f1acc, double* epart, long long* cpart, int exact,
+                         int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
+                         cudaStream_t s);
+
+// Per-eval refresh of the sorted positions from the current double positions (same periodic
+// image as at build time) + staleness check against the build-time positions.
+void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,
+                    const int* atom, const int* img, const float4* posq_build, float4* posq,
+                    float half_skin2, int* flags, cudaStream_t s);
+
+}  // namespace sdm

@@ -11,21 +11,25 @@ struct EvalBuffers {
     const double* pos;      // [R][3n]   positions, System order, nm
     const double* fb;       // [R][3n]   bonded/restraint forces (zero when absent)
     float4* posq;           // [R][n]    (x,y,z wrapped into the box, q*sqrt(K)) float
-    long long* f1acc;       // [R][3][nslot] state-1 force accumulators, 2^32 fixed point
+    long long* f1acc;       // state-1 force accumulators, 2^32 fixed point: replica r, component c,
+                            // slot s at f1acc[r*acc_rstride + c*nslot + s]
+    size_t acc_rstride;     // 3*n (all-pairs, System order) or 0 (cluster path: global slot space)
     double* dF;             // [R][3n]   F2 - F1 (moved pairs only)
     double* F;              // [R][3n]   hybrid force (output)
     double* F1;             // [R][3n]   state-1 force in double (output)
-    double* epart;          // [R][n_epart] pair-energy partials
-    long long* cpart;       // [R][n_epart] in-cutoff pair count partials
+    double* epart;          // pair-energy partials; replica r owns [part_off[r], part_off[r+1])
+    long long* cpart;       // in-cutoff pair count partials, same ranges
+    const int* part_off;    // [R+1] device
     double* eexc_part;      // [R][n_excpart] exception-energy partials
     double* uexc_part;      // [R][n_excpart] exception contribution to u
     double* upart;          // [R][n_lig] u partial per displaced atom
     long long* mcnt;        // [R][n_lig][2] moved-pair counts (x2) per displaced atom
     ReplicaState* state;    // [R]
     int* flags;             // [R] status raised by kernels of this eval (0 = ok); cleared by mix
-    int n_epart, n_excpart;
+    int n_excpart;
     int nslot;              // stride of f1acc planes (>= n)
     const int* slot_of;     // [R][n] atom -> accumulator slot, or nullptr for identity
+    int n_epart_allpairs;   // blocks per replica of the all-pairs kernel
 };
 
 // ---- fused path, v0 (all-pairs tiles, System order) ------------------------------------------

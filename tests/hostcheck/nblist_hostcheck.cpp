@@ -1,0 +1,319 @@
+// nblist_hostcheck.cpp -- CPU checker for the cluster-pair list logic (TEST INFRASTRUCTURE).
+//
+// Compiles openmm_sdm_plugin_b200/csrc/nblist_core.h -- the very per-item bodies the device
+// kernels call -- with g++, drives them serially in the same order pairlist.cu does on the
+// device, then walks the list exactly like the pair kernel's (sci, entry, ci, lane) traversal
+// and reports every atom pair that passes the masks and the (double-precision) cutoff test.
+// tests/test_nblist_host.py compares that with the oracle's pair set: every in-cutoff
+// non-excluded pair must be covered exactly once.  Nothing here is part of the product path.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../openmm_sdm_plugin_b200/csrc/nblist_core.h"
+
+using namespace sdm::nbl;
+
+namespace {
+
+bool setup_grid(Grid& G, int n, int R, bool periodic, double rlist, const double lo[3],
+                const double ext[3], long long cell_cap) {
+    G.periodic = periodic ? 1 : 0;
+    G.n = n;
+    G.R = R;
+    G.rlist = (float)rlist;
+    G.rlist2 = (float)(rlist * rlist);
+    double vol = ext[0] * ext[1] * ext[2];
+    double density = vol > 0 ? n / vol : 100.0;
+    double side = std::cbrt(40.0 / std::max(density, 1e-6));
+    side = std::max(side, 0.5 * rlist + 1e-3);
+    for (int iter = 0; iter < 64; iter++) {
+        long long ncell = 1;
+        int span = 1;
+        for (int d = 0; d < 3; d++) {
+            int nc = (int)std::floor(ext[d] / side);
+            if (nc < 1) nc = 1;
+            G.nc[d] = nc;
+            G.cs[d] = ext[d] / nc;
+            G.inv_cs[d] = 1.0 / G.cs[d];
+            G.lo[d] = lo[d];
+            G.box[d] = ext[d];
+            G.boxf[d] = (float)ext[d];
+            ncell *= nc;
+            int sp = (int)std::floor((G.cs[d] + 2 * rlist + 3e-4) / G.cs[d]) + 2;
+            if (!G.periodic) sp = std::min(sp, nc);
+            span = std::max(span, sp);
+        }
+        if (span <= kMaxSpan && ncell <= cell_cap) {
+            G.ncell = (int)ncell;
+            G.span = span;
+            return true;
+        }
+        side *= 1.1;
+    }
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+// pos: [R][n][3] doubles.  excl: unique pairs a<b.  Returns the number of covered pairs of
+// replica `replica` (sorted (i<j) System indices written to out_pairs up to max_pairs), or <0.
+// stats[0..7]: nslot, nsci, nentries, nmasks, nunits, evaluated lane-pairs (all replicas),
+// ncell, span.
+long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const double* box,
+                          double rc, double skin, int n_excl, const int* excl, int chunk,
+                          int replica, int* out_pairs, long long max_pairs, double* stats) {
+    const double rlist = rc + skin;
+    Grid G;
+    std::memset(&G, 0, sizeof(G));
+    double lo[3] = {0, 0, 0}, ext[3];
+    const int total = n * R;
+    if (periodic) {
+        for (int d = 0; d < 3; d++) ext[d] = box[d];
+    } else {
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (int k = 0; k < total; k++)
+            for (int d = 0; d < 3; d++) {
+                mn[d] = std::min(mn[d], pos[3 * (size_t)k + d]);
+                mx[d] = std::max(mx[d], pos[3 * (size_t)k + d]);
+            }
+        for (int d = 0; d < 3; d++) { lo[d] = mn[d] - 1e-3; ext[d] = std::max(mx[d] - mn[d] + 2e-3, 1e-2); }
+    }
+    if (!setup_grid(G, n, R, periodic != 0, rlist, lo, ext, std::max(64, n / 8 + 64))) return -1;
+    const int ncells = R * G.ncell;
+    const int noff = G.span * G.span * G.span;
+
+    // keys + stable sort
+    std::vector<uint32_t> keys(total);
+    std::vector<int> vals(total);
+    for (int t = 0; t < total; t++) {
+        float xw[3];
+        int im[3];
+        keys[t] = atom_key(G, t / n, pos[3 * (size_t)t], pos[3 * (size_t)t + 1], pos[3 * (size_t)t + 2], xw, im);
+        vals[t] = t;
+    }
+    std::vector<int> order(total);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+    std::vector<uint32_t> ks(total);
+    std::vector<int> vs(total);
+    for (int k = 0; k < total; k++) { ks[k] = keys[order[k]]; vs[k] = vals[order[k]]; }
+
+    // cells
+    std::vector<int> cell_first(ncells + 1, 0), cell_count(ncells + 1, 0), cell_slot(ncells + 2, 0), cell_sci(ncells + 2, 0);
+    for (int k = 0; k < total; k++) {
+        uint32_t c = ks[k] >> kSubBits;
+        if (k == 0 || (ks[k - 1] >> kSubBits) != c) cell_first[c] = k;
+        cell_count[c]++;
+    }
+    int nslot = 0, nsci = 0;
+    for (int c = 0; c < ncells; c++) {
+        cell_slot[c] = nslot;
+        cell_sci[c] = nsci;
+        int pc = (cell_count[c] + kClusterSize - 1) / kClusterSize * kClusterSize;
+        nslot += pc;
+        nsci += (pc / kClusterSize + kMaxCi - 1) / kMaxCi;
+    }
+    cell_slot[ncells] = nslot;
+    cell_sci[ncells] = nsci;
+    const int ncl = nslot / kClusterSize;
+
+    // slots
+    std::vector<float> posq(4 * (size_t)nslot, 0.f);
+    std::vector<int> atom(nslot, -1), slot_of(total, -1);
+    std::vector<double> posw(3 * (size_t)nslot, 0.0);  // wrapped double coordinates per slot
+    for (int s = 0; s < nslot; s++) { posq[4 * (size_t)s] = posq[4 * (size_t)s + 1] = posq[4 * (size_t)s + 2] = kFar; }
+    for (int k = 0; k < total; k++) {
+        uint32_t c = ks[k] >> kSubBits;
+        int ga = vs[k];
+        int slot = cell_slot[c] + (k - cell_first[c]);
+        float xw[3];
+        int im[3];
+        atom_key(G, ga / n, pos[3 * (size_t)ga], pos[3 * (size_t)ga + 1], pos[3 * (size_t)ga + 2], xw, im);
+        for (int d = 0; d < 3; d++) {
+            posq[4 * (size_t)slot + d] = xw[d];
+            posw[3 * (size_t)slot + d] = pos[3 * (size_t)ga + d] + (periodic ? im[d] * box[d] : 0.0);
+        }
+        atom[slot] = ga;
+        slot_of[ga] = slot;
+    }
+    // boxes
+    std::vector<BBox> cl_box(ncl), j4_box(2 * (size_t)ncl), sci_box(nsci);
+    for (int c = 0; c < ncl; c++) {
+        j4_box[2 * c] = group_bbox(posq.data(), c * 8, 4);
+        j4_box[2 * c + 1] = group_bbox(posq.data(), c * 8 + 4, 4);
+        cl_box[c] = box_union(j4_box[2 * c], j4_box[2 * c + 1]);
+    }
+    std::vector<SciDesc> sci(nsci);
+    std::vector<int> cl_sci(ncl, -1);
+    for (int c = 0; c < ncells; c++) {
+        int cl0 = cell_slot[c] / kClusterSize, cl1 = cell_slot[c + 1] / kClusterSize, s = cell_sci[c];
+        for (int k = cl0; k < cl1; k += kMaxCi, s++) {
+            SciDesc d;
+            d.c0 = k;
+            d.nci = std::min(kMaxCi, cl1 - k);
+            d.replica = c / G.ncell;
+            d.pad = 0;
+            BBox b = cl_box[k];
+            cl_sci[k] = s;
+            for (int j = 1; j < d.nci; j++) { b = box_union(b, cl_box[k + j]); cl_sci[k + j] = s; }
+            sci[s] = d;
+            sci_box[s] = b;
+        }
+    }
+    // search: count, scan, fill
+    SearchView V;
+    V.G = G;
+    V.sci = sci.data();
+    V.sci_box = sci_box.data();
+    V.cl_box = cl_box.data();
+    V.j4_box = j4_box.data();
+    V.cell_slot = cell_slot.data();
+    const long long nitems = (long long)nsci * noff;
+    std::vector<int> item_off(nitems + 1, 0);
+    for (long long t = 0; t < nitems; t++)
+        item_off[t + 1] = item_off[t] + search_item(V, (int)(t / noff), (int)(t % noff), [](int, uint32_t, uint32_t, bool) {});
+    const int nentries = item_off[nitems];
+    std::vector<uint32_t> ex(nentries), ey(nentries);
+    std::vector<int> flag(nentries + 1, 0), esci(nentries);
+    for (long long t = 0; t < nitems; t++) {
+        int base = item_off[t];
+        search_item(V, (int)(t / noff), (int)(t % noff), [&](int k, uint32_t w0, uint32_t imask, bool diag) {
+            ex[base + k] = w0;
+            ey[base + k] = imask;
+            flag[base + k] = diag ? 1 : 0;
+            esci[base + k] = (int)(t / noff);
+        });
+    }
+    // exclusions pass 0
+    auto for_excl = [&](int pass, std::vector<uint32_t>* masks) {
+        for (int r = 0; r < R; r++)
+            for (int k = 0; k < n_excl; k++) {
+                int sa = slot_of[r * n + excl[2 * k]], sb = slot_of[r * n + excl[2 * k + 1]];
+                int si, sj;
+                exclusion_roles(sa, sb, &si, &sj);
+                int isci = cl_sci[si / kClusterSize];
+                int ci = si / kClusterSize - sci[isci].c0;
+                uint32_t j4 = (uint32_t)(sj / kJGroup);
+                uint32_t bit = 1u << ((sj % kJGroup) * kClusterSize + (si % kClusterSize));
+                for (int e = item_off[(long long)isci * noff]; e < item_off[(long long)(isci + 1) * noff]; e++) {
+                    if ((ex[e] & 0x3ffffffu) != j4) continue;
+                    if (pass == 0) flag[e] = 1;
+                    else (*masks)[(size_t)(ey[e] >> 8) * kMaxCi + ci] &= ~bit;
+                }
+            }
+    };
+    for_excl(0, nullptr);
+    int nmasks = 0;
+    std::vector<int> midx(nentries, 0);
+    for (int e = 0; e < nentries; e++) if (flag[e]) midx[e] = nmasks++;
+    std::vector<uint32_t> masks((size_t)(nmasks + 1) * kMaxCi, 0xffffffffu);
+    for (int e = 0; e < nentries; e++) {
+        if (!flag[e]) continue;
+        uint32_t m = (uint32_t)midx[e] + 1u;
+        ey[e] = (ey[e] & 0xffu) | (m << 8);
+        int j4 = (int)(ex[e] & 0x3ffffffu);
+        uint32_t code = ex[e] >> 26;
+        const SciDesc sd = sci[esci[e]];
+        for (int ci = 0; ci < kMaxCi; ci++) {
+            uint32_t w = 0xffffffffu;
+            if (code == kShiftZero && (j4 >> 1) == sd.c0 + ci) w = triangle_mask(j4 & 1);
+            masks[(size_t)m * kMaxCi + ci] = w;
+        }
+    }
+    for_excl(1, &masks);
+    int nunits = 0;
+    for (int s = 0; s < nsci; s++) {
+        int len = item_off[(long long)(s + 1) * noff] - item_off[(long long)s * noff];
+        nunits += (len + chunk - 1) / chunk;
+    }
+
+    if (getenv("NBL_TRACE")) {
+        int ta, tb;
+        sscanf(getenv("NBL_TRACE"), "%d,%d", &ta, &tb);
+        int sa = slot_of[ta], sb = slot_of[tb], si, sj;
+        exclusion_roles(sa, sb, &si, &sj);
+        int isci = cl_sci[si / 8];
+        printf("trace %d %d slots %d %d roles i=%d j=%d clusters %d %d isci %d c0 %d nci %d j4 %d\n", ta, tb, sa, sb, si, sj, si / 8, sj / 8, isci, sci[isci].c0, sci[isci].nci, sj / 4);
+        const BBox& sbx = sci_box[isci];
+        printf(" sci box lo %g %g %g hi %g %g %g\n", sbx.lo[0], sbx.lo[1], sbx.lo[2], sbx.hi[0], sbx.hi[1], sbx.hi[2]);
+        const BBox& jb = j4_box[sj / 4];
+        printf(" j4 box lo %g %g %g hi %g %g %g\n", jb.lo[0], jb.lo[1], jb.lo[2], jb.hi[0], jb.hi[1], jb.hi[2]);
+        int cmin[3], cmax[3];
+        search_range(G, sbx, cmin, cmax);
+        printf(" range %d..%d %d..%d %d..%d nc %d %d %d span %d\n", cmin[0], cmax[0], cmin[1], cmax[1], cmin[2], cmax[2], G.nc[0], G.nc[1], G.nc[2], G.span);
+        for (int e = item_off[(long long)isci * noff]; e < item_off[(long long)(isci + 1) * noff]; e++)
+            if ((int)(ex[e] & 0x3ffffffu) == sj / 4) {
+                printf(" entry %d code %u imask %x m %u flag %d midx %d\n", e, ex[e] >> 26, ey[e] & 0xff, ey[e] >> 8, flag[e], midx[e]);
+                for (int ci = 0; ci < 8; ci++) printf("   mask[%d]=%08x\n", ci, masks[(size_t)(ey[e] >> 8) * 8 + ci]);
+                for (int ti = 0; ti < 8; ti++) printf("   i slot %d atom %d\n", (si / 8) * 8 + ti, atom[(si / 8) * 8 + ti]);
+                for (int tj = 0; tj < 4; tj++) printf("   j slot %d atom %d\n", (sj / 4) * 4 + tj, atom[(sj / 4) * 4 + tj]);
+            }
+    }
+    // traversal exactly like the pair kernel
+    std::vector<std::pair<int, int>> found;
+    const double rc2 = rc * rc;
+    double lane_pairs = 0, pruned_pairs = 0;
+    for (int s = 0; s < nsci; s++) {
+        const SciDesc sd = sci[s];
+        for (int e = item_off[(long long)s * noff]; e < item_off[(long long)(s + 1) * noff]; e++) {
+            const int j4 = (int)(ex[e] & 0x3ffffffu);
+            const uint32_t imask = ey[e] & 0xffu, m = ey[e] >> 8;
+            for (int ci = 0; ci < kMaxCi; ci++) {
+                if (!((imask >> ci) & 1u)) continue;
+                lane_pairs += 32;
+                if (stats && stats[9] > 0) {  // exact-prune statistic: any atom pair within stats[9]
+                    const uint32_t code2 = ex[e] >> 26;
+                    const int sh2[3] = {shift_x(code2), shift_y(code2), shift_z(code2)};
+                    bool any = false;
+                    for (int lane = 0; lane < 32 && !any; lane++) {
+                        const int islot = (sd.c0 + ci) * kClusterSize + (lane & 7), jslot = j4 * kJGroup + (lane >> 3);
+                        if (atom[islot] < 0 || atom[jslot] < 0) continue;
+                        double r2 = 0;
+                        for (int k = 0; k < 3; k++) {
+                            double dd = posw[3 * (size_t)islot + k] - (posw[3 * (size_t)jslot + k] + (periodic ? sh2[k] * box[k] : 0.0));
+                            r2 += dd * dd;
+                        }
+                        any = r2 < stats[9] * stats[9];
+                    }
+                    if (any) pruned_pairs += 32;
+                }
+                if (sd.replica != replica) continue;
+                for (int lane = 0; lane < 32; lane++) {
+                    if (m && !((masks[(size_t)m * kMaxCi + ci] >> lane) & 1u)) continue;
+                    const int ti = lane & 7, tj = lane >> 3;
+                    const int islot = (sd.c0 + ci) * kClusterSize + ti, jslot = j4 * kJGroup + tj;
+                    const int ai = atom[islot], aj = atom[jslot];
+                    if (ai < 0 || aj < 0) continue;
+                    // the image this entry addresses (what the kernel evaluates), in double
+                    const uint32_t code = ex[e] >> 26;
+                    const int sh[3] = {shift_x(code), shift_y(code), shift_z(code)};
+                    double d[3];
+                    for (int k = 0; k < 3; k++)
+                        d[k] = posw[3 * (size_t)islot + k] - (posw[3 * (size_t)jslot + k] + (periodic ? sh[k] * box[k] : 0.0));
+                    if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] > rc2) continue;
+                    int a = ai % n, b = aj % n;
+                    found.emplace_back(std::min(a, b), std::max(a, b));
+                }
+            }
+        }
+    }
+    std::sort(found.begin(), found.end());
+    long long m = std::min<long long>((long long)found.size(), max_pairs);
+    for (long long k = 0; k < m; k++) { out_pairs[2 * k] = found[k].first; out_pairs[2 * k + 1] = found[k].second; }
+    if (stats) {
+        stats[0] = nslot; stats[1] = nsci; stats[2] = nentries; stats[3] = nmasks;
+        stats[4] = nunits; stats[5] = lane_pairs; stats[6] = G.ncell; stats[7] = G.span;
+        stats[8] = pruned_pairs;
+    }
+    return (long long)found.size();
+}
+
+}  // extern "C"
