@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- SDM dual-state force evals/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--replicas R] [--workload cfg2|cfg1|synthetic:N]
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port), all host threads
+
+One *step* = one dual-state evaluation (E1, u, u_sc, W, sp, PotEnergy, hybrid force F) of every
+lambda-replica resident on a GPU.  `value` = evals/s summed over all replicas and GPUs with the
+positions already in HBM; `e2e` = the same through the public C-ABI call path with HOST
+buffers (H2D of positions and D2H of forces + scalars inside the timed region).
+
+Multi-GPU: one process per GPU (torchrun), replicas sharded by rank, no data-path collective
+(weak scaling: R replicas per GPU); the only collective is the (u_sc, state) all-gather that a
+replica-exchange round needs, exercised once per step outside the kernel timing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = {2: 61.0, 1: 46.0, 0: 46.0}   # periodic / non-periodic
+
+
+def load_case(workload: str):
+    from openmm_sdm_plugin_b200 import system as S
+    if workload == "cfg2":
+        return S.cfg2(), "cfg2: TEMOA-G1/G4 explicit solvent (20446 atoms, CutoffPeriodic RF, rc=1.0 nm, 38 displaced atoms)"
+    if workload == "cfg1":
+        return S.cfg1(), "cfg1: OA-G6/G3 (230 atoms, CutoffNonPeriodic 15 nm, 38 displaced atoms)"
+    if workload.startswith("synthetic:"):
+        n = int(workload.split(":")[1])
+        return S.synthetic_case(n_atoms=n, ligand_atoms=60, seed=1234), \
+            "synthetic explicit-solvent ABFE box (%d atoms, CutoffPeriodic RF, rc=1.0 nm, 60 displaced atoms)" % n
+    raise SystemExit("unknown workload " + workload)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(case, seconds_budget=20.0, nthreads=1):
+    """The reference's algorithm (oracle port: two full list builds + pair loops per eval,
+    double precision, like LangevinIntegratorSDM::step on the Reference platform) timed on this
+    host.  Bounded sample: whole evals of the same workload until the budget is used."""
+    from openmm_sdm_plugin_b200 import system as S
+    from oracle import oracle as O
+    al = S.AlchemicalState(**vars(case.alch))
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.sdm_eval(case.system, al, case.displacement, case.positions, nthreads=nthreads,
+                   want_state_forces=False)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_budget or n >= 64:
+            break
+    return n / dt, n
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path (its Reference platform cannot be built
+    here -- OpenMM is not installed -- so this is the oracle port) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    case, wname = load_case(args.workload)
+    nt = O.max_threads()
+    from openmm_sdm_plugin_b200 import system as S
+    al = S.AlchemicalState(**vars(case.alch))
+    for _ in range(args.warmup):
+        O.sdm_eval(case.system, al, case.displacement, case.positions, nthreads=nt, want_state_forces=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.sdm_eval(case.system, al, case.displacement, case.positions, nthreads=nt, want_state_forces=False)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": "SDM dual-state force evals/s", "value": v, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "shipped fixture" if args.workload in ("cfg1", "cfg2") else "synthetic",
+            "config": {"workload": wname, "replicas_per_step": 1,
+                       "note": "one step = one dual-state eval of one replica on the host CPU"},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": nt, "kind": "port",
+                             "sample": "%d whole evals of the workload" % args.steps},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--replicas", type=int, default=16, help="lambda-replicas resident per GPU")
+    ap.add_argument("--nstlist", type=int, default=20)
+    ap.add_argument("--skin", type=float, default=0.06)
+    ap.add_argument("--pair-mode", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from openmm_sdm_plugin_b200 import _lib, system as S
+    from openmm_sdm_plugin_b200.context import PinnedArray, SDMContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the SDM path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    case, wname = load_case(args.workload)
+    n, R = case.system.n_atoms, args.replicas
+    states = S.atm_lambda_schedule(max(world * R, 2))
+    ctx = SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=args.pair_mode,
+                     device=local, skin=args.skin, nstlist=args.nstlist)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(1234 + rank)
+    # per-replica positions: the fixture plus a small replica-specific thermal-like jitter
+    h_pos = PinnedArray((R, n, 3))
+    h_pos_b = PinnedArray((R, n, 3))
+    h_f = PinnedArray((R, n, 3))
+    base = np.stack([case.positions + rng.normal(scale=0.002, size=(n, 3)) for _ in range(R)])
+    h_pos.array[...] = base
+    for r in range(R):
+        ctx.set_alchemical(r, states[(rank * R + r) % len(states)])
+    ctx.set_positions_all(h_pos.array)
+    # the e2e leg alternates between two host coordinate sets that differ by ~ the rms
+    # displacement of a 1 fs step at 300 K, so every step uploads genuinely new positions
+    h_pos_b.array[...] = base + rng.normal(scale=0.0006, size=(R, n, 3))
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def exchange_gather(scalars):
+        """(u_sc, state id) all-gather a replica-exchange round needs -- the path's only
+        collective; 16 bytes per replica."""
+        if world == 1:
+            return
+        t = torch.tensor([[s["u_sc"], float(rank * R + i)] for i, s in enumerate(scalars)],
+                         dtype=torch.float64, device="cuda")
+        out = torch.empty((world,) + t.shape, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(out, t)
+
+    # ---------------- resident leg: inputs already in HBM ----------------------------------
+    def resident_step():
+        ctx.eval()
+
+    for _ in range(args.warmup):
+        resident_step()
+    torch.cuda.synchronize()
+    ctx.set_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = ctx.launch_count()
+    pair_ms = []
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                       # evict the previous step's working set from L2
+        ev[k][0].record(stream)
+        resident_step()
+        ev[k][1].record(stream)
+        # kernel timing uses events the library records on the same stream around the pair kernel
+        pair_ms.append(ctx.last_timing()[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_resident = time.perf_counter() - wall0
+    sampler.stop_flag = True
+    launches = ctx.launch_count() - launches0
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    ctx.set_timing(False)
+    if world > 1:
+        tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt.item())
+    sc = ctx.read_results(None)
+    assert all(s["status"] == 0 for s in sc), [s["status"] for s in sc]
+    value = world * R * args.steps / (t_ms * 1e-3)
+
+    # ---------------- end-to-end leg: host buffers in, host buffers out ---------------------
+    def e2e_step(k):
+        ctx.set_positions_all(h_pos.array if k % 2 == 0 else h_pos_b.array)
+        ctx.eval()
+        s = ctx.read_results(h_f.array)
+        exchange_gather(s)
+        return s
+
+    for k in range(args.warmup):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_t = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s = e2e_step(k)
+        torch.cuda.synchronize()
+        e2e_t += time.perf_counter() - t0
+    assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
+    if world > 1:
+        tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_t = float(tt.item())
+    e2e_value = world * R * args.steps / e2e_t
+    h2d = R * n * 3 * 8
+    d2h = R * n * 3 * 8 + R * 8 * 20
+
+    # ---------------- roofline of the dominant kernel ----------------------------------------
+    pk = peaks()
+    algo_pairs = sum(s["n_pairs1"] + s["n_moved2"] for s in sc)          # per launch (all replicas)
+    flop = FLOP_PER_PAIR[int(case.system.method)] * algo_pairs
+    pair_ms_avg = float(np.mean(pair_ms))
+    achieved = flop / (pair_ms_avg * 1e-3) / 1e12
+    peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    mode = int(ctx.info("pair_mode"))
+    roofline = {"bound": "fp32_simt", "kernel": "pair_cluster_kernel" if mode == 2 else "allpairs_kernel",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json)" % pk["source"],
+                "algorithmic_pairs_per_launch": algo_pairs, "flop_per_pair": FLOP_PER_PAIR[int(case.system.method)],
+                "kernel_ms": pair_ms_avg, "kernel_share_of_step": pair_ms_avg * args.steps / t_ms}
+
+    line = {"metric": "SDM dual-state force evals/s", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 pair arithmetic, f64 moved-pair/u/scalars, 64-bit fixed-point force accumulation",
+            "data": "shipped fixture (positions+topology), replica jitter synthetic" if args.workload in ("cfg1", "cfg2") else "synthetic",
+            "config": {"workload": wname, "replicas_per_gpu": R, "lambda_schedule": "22-window ILogistic ladder",
+                       "pair_mode": {1: "allpairs", 2: "cluster"}[mode], "skin_nm": args.skin, "nstlist": args.nstlist,
+                       "l2": "flushed between timed steps (256 MiB write)", "timing": "CUDA events per step on the launching stream, max over ranks"},
+            "evals_per_s_per_replica": value / (world * R),
+            "ns_per_day_per_replica_upper_bound": value / (world * R) * 1e-6 * 86400,
+            "roofline": roofline, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_t / args.steps},
+            "clocks": sampler.result(), "wall_s_resident_leg": wall_resident}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, ns = cpu_baseline(case, args.cpu_seconds, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
+                                "sample": "%d whole dual-state evals of the same workload (1 replica each), "
+                                          "two-pass like the reference, 1 thread like OpenMM's Reference platform" % ns}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -169,6 +169,8 @@ int sdm_set_positions(sdm_ctx* ctx, int replica, const double* xyz);
 int sdm_set_positions_device(sdm_ctx* ctx, int replica, const double* d_xyz);
 /* Device address of the ctx-owned position buffer of a replica (for in-place integrators). */
 int sdm_positions_device_ptr(sdm_ctx* ctx, int replica, double** d_xyz);
+/* All replicas at once: xyz_all is [n_replicas][3*n_atoms] host doubles, one asynchronous copy. */
+int sdm_set_positions_all(sdm_ctx* ctx, const double* xyz_all);
 
 /* Result of the group-1 (bonded/restraint) evaluation the integrator does at :176: forces left
  * in the force buffer and RestraintEnergy.  fb may be NULL (zero).  Host pointers. */
@@ -191,6 +193,9 @@ int sdm_invalidate_list(sdm_ctx* ctx);
 int sdm_get_scalars(sdm_ctx* ctx, int replica, sdm_scalars* out);       /* synchronises */
 int sdm_get_forces(sdm_ctx* ctx, int replica, int which, double* out);  /* [3*n_atoms], synchronises */
 int sdm_forces_device_ptr(sdm_ctx* ctx, int replica, double** d_f);     /* hybrid force, device */
+/* All replicas at once: hybrid forces into forces_all ([n_replicas][3*n_atoms], may be NULL) and
+ * scalars into scalars_all ([n_replicas], may be NULL); two copies, one synchronisation. */
+int sdm_read_results(sdm_ctx* ctx, double* forces_all, sdm_scalars* scalars_all);
 /* Debug / parity: the sorted in-cutoff non-excluded (i<j) pair list the pair kernel evaluated at
  * state 1, System particle indices.  pairs may be NULL to query *n only.  Synchronises. */
 int sdm_get_pairs(sdm_ctx* ctx, int replica, int32_t* pairs, int64_t max_pairs, int64_t* n);

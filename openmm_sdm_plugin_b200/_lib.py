@@ -74,6 +74,8 @@ SYMBOLS = {
     "sdm_set_positions": (_I, [_VP, _I, _VP]),
     "sdm_set_positions_device": (_I, [_VP, _I, _VP]),
     "sdm_positions_device_ptr": (_I, [_VP, _I, C.POINTER(_VP)]),
+    "sdm_set_positions_all": (_I, [_VP, _VP]),
+    "sdm_read_results": (_I, [_VP, _VP, _VP]),
     "sdm_set_bonded_forces": (_I, [_VP, _I, _VP, _D]),
     "sdm_set_alchemical": (_I, [_VP, _I, C.POINTER(SdmAlch)]),
     "sdm_get_alchemical": (_I, [_VP, _I, C.POINTER(SdmAlch)]),

@@ -126,6 +126,25 @@ class SDMContext:
         _lib.check(self._L.sdm_set_positions(self._h, replica, _ptr(a)))
         self._keep_pos = a  # async copy source must outlive the call
 
+    def set_positions_all(self, xyz_all: np.ndarray):
+        """[n_replicas, n_atoms, 3] host doubles (ideally a PinnedArray view), one async copy."""
+        if xyz_all.dtype != np.float64 or not xyz_all.flags.c_contiguous or xyz_all.size != 3 * self.n * self.R:
+            raise ValueError("positions must be C-contiguous float64 [n_replicas, n_atoms, 3]")
+        _lib.check(self._L.sdm_set_positions_all(self._h, _ptr(xyz_all)))
+        self._keep_pos = xyz_all
+
+    def read_results(self, forces_out: np.ndarray | None = None, want_scalars: bool = True):
+        """Hybrid forces of all replicas into forces_out ([R, n, 3] float64) and the list of
+        scalar dicts; one synchronisation."""
+        if forces_out is not None and (forces_out.dtype != np.float64 or not forces_out.flags.c_contiguous
+                                       or forces_out.size != 3 * self.n * self.R):
+            raise ValueError("forces_out must be C-contiguous float64 [n_replicas, n_atoms, 3]")
+        sc = (_lib.SdmScalars * self.R)() if want_scalars else None
+        _lib.check(self._L.sdm_read_results(self._h, _ptr(forces_out), C.cast(sc, C.c_void_p) if sc else None))
+        if not want_scalars:
+            return None
+        return [{k: getattr(s, k) for k, _ in _lib.SdmScalars._fields_} for s in sc]
+
     def set_positions_ptr(self, replica: int, host_ptr: int):
         _lib.check(self._L.sdm_set_positions(self._h, replica, C.c_void_p(host_ptr)))
 

@@ -409,6 +409,14 @@ int sdm_set_positions_device(sdm_ctx* c, int replica, const double* d_xyz) {
     return SDM_OK;
 }
 
+int sdm_set_positions_all(sdm_ctx* c, const double* xyz_all) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (!xyz_all) return fail(SDM_ERR_INVALID, "null positions");
+    SDM_CUDA(cudaMemcpyAsync(c->d_pos, xyz_all, sizeof(double) * 3 * (size_t)c->n * c->R,
+                             cudaMemcpyHostToDevice, c->stream));
+    return SDM_OK;
+}
+
 int sdm_positions_device_ptr(sdm_ctx* c, int replica, double** d_xyz) {
     if (int rc = check_ctx(c, replica)) return rc;
     if (!d_xyz) return fail(SDM_ERR_INVALID, "null argument");
@@ -526,6 +534,20 @@ int sdm_get_forces(sdm_ctx* c, int replica, int which, double* out) {
         SDM_CUDA(cudaMemcpy(d.data(), c->B.dF + off, sizeof(double) * n3, cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < n3; k++) out[k] += d[k];  // debug accessor: F2 = F1 + dF
     }
+    return SDM_OK;
+}
+
+int sdm_read_results(sdm_ctx* c, double* forces_all, sdm_scalars* scalars_all) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (forces_all)
+        SDM_CUDA(cudaMemcpyAsync(forces_all, c->B.F, sizeof(double) * 3 * (size_t)c->n * c->R,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    if (scalars_all)
+        SDM_CUDA(cudaMemcpyAsync(c->h_state, c->B.state, sizeof(sdm::ReplicaState) * (size_t)c->R,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    if (scalars_all)
+        for (int r = 0; r < c->R; r++) scalars_all[r] = c->h_state[r].sc;
     return SDM_OK;
 }
 

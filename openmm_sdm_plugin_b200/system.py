@@ -223,8 +223,8 @@ def synthetic_case(n_atoms: int = 50_000, ligand_atoms: int = 60, seed: int = 12
     for mols, q_scale in ((lig_mol, 0.5), (prot_mol, 0.6)):
         for k in range(3):
             ids = 3 * mols + k
-            sigma[ids] = (0.34, 0.25, 0.30)[k]
-            epsilon[ids] = (0.45, 0.12, 0.30)[k]
+            sigma[ids] = (0.34, 0.1, 0.1)[k]
+            epsilon[ids] = (0.45, 0.0, 0.0)[k]     # H-like sites carry charge only, like water H
             charge[ids] = q_scale * (-0.5, 0.2, 0.3)[k]
     extra_excl, exc_pairs, exc_params = [], [], []
     for mols in (lig_mol, prot_mol):

@@ -7,9 +7,11 @@ from openmm_sdm_plugin_b200.context import SDMContext
 from oracle import oracle as O
 
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else _lib.PAIR_ALLPAIRS
-for name, case in (("cfg1", S.cfg1()), ("cfg2", S.cfg2())):
+RR = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+cases = (("cfg1", S.cfg1()), ("cfg2", S.cfg2())) if len(sys.argv) <= 3 else (("cfg2", S.cfg2()),)
+for name, case in cases:
     ref = O.sdm_eval(case.system, S.AlchemicalState(**vars(case.alch)), case.displacement, case.positions, nthreads=O.max_threads())
-    R = 4
+    R = RR
     ctx = SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=mode)
     for r in range(R):
         ctx.set_positions(r, case.positions); ctx.set_alchemical(r, case.alch)
@@ -31,4 +33,6 @@ for name, case in (("cfg1", S.cfg1()), ("cfg2", S.cfg2())):
     ctx.synchronize()
     dt = (time.perf_counter() - t) / 10
     print("  R=%d eval wall %.3f ms  (pair, total device ms) %s" % (R, dt * 1e3, ctx.last_timing()))
+    if mode == 2:
+        print("  list:", {k: ctx.info(k) for k in ("n_slots", "n_sci", "n_entries", "n_masks", "n_units", "n_cells", "cell_span", "n_list_builds")})
     ctx.close()
