@@ -27,54 +27,111 @@ struct Acc {
     float fx, fy, fz;
 };
 
-template <bool PERIODIC>
-__device__ __forceinline__ void pair_step(const Topology& T, const float4 xi, const float2 pi,
-                                          const float4 xj, const float2 pj, const bool allowed,
-                                          const int exact, const PairListView& V, const double* pos_all,
-                                          const int islot, const int jslot, Acc& fi, Acc& fj,
-                                          float& en, int& cnt, const bool emit, int* emit_counter,
-                                          int* emit_pairs, const int emit_cap) {
-    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-    const float r2 = dx * dx + dy * dy + dz * dz;
-    bool in = allowed && (r2 <= T.rc2f);
-    if (exact && allowed && fabsf(r2 - T.rc2f) < T.band) {
-        // rare: decide exactly like a double-precision evaluation would
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU.RSQ, no denormal fix-up
+    return y;
+}
+
+// Rare path: pairs whose FP32 r^2 lies within T.band of the cutoff are left out by the hot loop
+// and handled here, once per affected entry, with the FP64 in-cutoff test of the oracle.  Their
+// force goes straight to the fixed-point accumulators (both atoms); energy and count are
+// returned through en / cnt.  Out of line so that the hot loop stays small.
+__device__ __noinline__ void fix_rare_pairs(const Topology& T, const PairListView& V,
+                                            const double* __restrict__ pos_all,
+                                            long long* __restrict__ f1acc, const float4* s_xi,
+                                            const float2* s_pi, int ibase, int jslot, float4 xj,
+                                            float2 pj, uint32_t imask, uint32_t midx, int lane,
+                                            float* en, int* cnt, bool use_f64, bool all,
+                                            bool emit, int* emit_counter, int* emit_pairs,
+                                            int emit_cap) {
+    const int ti = lane & 7;
+    const size_t plane = (size_t)V.nslot_cap;
+    for (int ci = 0; ci < nbl::kMaxCi; ci++) {
+        if (!((imask >> ci) & 1u)) continue;
+        const uint32_t w = midx ? V.masks[(size_t)midx * nbl::kMaxCi + ci] : 0xffffffffu;
+        if (!((w >> lane) & 1u)) continue;
+        const int il = ci * nbl::kClusterSize + ti;
+        const float4 xi = s_xi[il];
+        const float2 pi = s_pi[il];
+        const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        const float r2 = dx * dx + dy * dy + dz * dz;
+        const float t = r2 - T.rc2f;
+        const bool near = fabsf(t) < T.band;
+        if (!(near || (all && t <= 0.f))) continue;
+        const int islot = ibase + il;
         const int ai = V.atom[islot], aj = V.atom[jslot];
-        in = false;
-        if (ai >= 0 && aj >= 0) {
-            const int r = ai / T.n;
-            in = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
+        if (ai < 0 || aj < 0) continue;
+        const int r = ai / T.n;
+        if (near && use_f64) {
+            if (!in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n)) continue;
+        } else if (!(t <= 0.f)) {
+            continue;
         }
-    }
-    const float rinv = rsqrtf(r2);
-    const float rinv2 = rinv * rinv;
-    const float sig = pi.x + pj.x;
-    const float sr2 = sig * sig * rinv2;
-    const float sr6 = sr2 * sr2 * sr2;
-    const float eps = pi.y * pj.y;
-    const float qq = xi.w * xj.w;
-    const float elj = eps * sr6;
-    float dEdR = elj * (12.f * sr6 - 6.f) + qq * (rinv - 2.f * T.krff * r2);
-    float e = elj * (sr6 - 1.f) + qq * (rinv + T.krff * r2 - T.crff);
-    const float fs = in ? dEdR * rinv2 : 0.f;
-    e = in ? e : 0.f;
-    fi.fx += fs * dx; fi.fy += fs * dy; fi.fz += fs * dz;
-    fj.fx -= fs * dx; fj.fy -= fs * dy; fj.fz -= fs * dz;
-    en += e;
-    cnt += in ? 1 : 0;
-    if (emit && in) {
-        const int ai = V.atom[islot] % T.n, aj = V.atom[jslot] % T.n;
-        const int slot = atomicAdd(emit_counter, 1);
-        if (slot < emit_cap) {
-            emit_pairs[2 * slot] = ai < aj ? ai : aj;
-            emit_pairs[2 * slot + 1] = ai < aj ? aj : ai;
+        const float rinv = rsqrtf(r2), rinv2 = rinv * rinv;
+        const float sig = pi.x + pj.x;
+        const float sr2 = (sig * sig) * rinv2;
+        const float sr6 = sr2 * sr2 * sr2;
+        const float elj = (pi.y * pj.y) * sr6;
+        const float qq = xi.w * xj.w;
+        const float kr2 = T.krff * r2;
+        const float fs = (elj * (12.f * sr6 - 6.f) + qq * (rinv - 2.f * kr2)) * rinv2;
+        *en += elj * (sr6 - 1.f) + qq * (rinv + kr2 - T.crff);
+        *cnt += 1;
+        const float f[3] = {fs * dx, fs * dy, fs * dz};
+        for (int c = 0; c < 3; c++) {
+            const long long v = __float2ll_rn(f[c] * 4294967296.0f);
+            atomic_add_fixed(f1acc + (size_t)c * plane + islot, v);
+            atomic_add_fixed(f1acc + (size_t)c * plane + jslot, -v);
+        }
+        if (emit) {
+            const int a = ai % T.n, b = aj % T.n;
+            const int slot = atomicAdd(emit_counter, 1);
+            if (slot < emit_cap) {
+                emit_pairs[2 * slot] = a < b ? a : b;
+                emit_pairs[2 * slot + 1] = a < b ? b : a;
+            }
         }
     }
 }
 
-template <bool PERIODIC, bool EMIT>
-__global__ void __launch_bounds__(kWarps * 32)
-pair_cluster_kernel(Topology T, PairListView V, const double* __restrict__ pos_all,
+// One (i-atom, j-atom) pair of the hot loop.  `rare` accumulates "this lane met a pair inside
+// the FP64 re-test band"; such pairs are skipped here and fixed up by fix_rare_pairs().
+template <bool EXACT, bool ALL>
+__device__ __forceinline__ void pair_step(const Topology& T, const float4 xi, const float2 pi,
+                                          const float4 xj, const float2 pj, const bool allowed,
+                                          bool& rare, Acc& fi, Acc& fj, float& en, int& cnt) {
+    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float t = r2 - T.rc2f;
+    bool in = allowed && (t <= 0.f);
+    if (EXACT) {
+        const bool near = allowed && (ALL ? t < T.band : fabsf(t) < T.band);
+        rare |= near;
+        in = in && !near;
+    }
+    const float rinv = rsqrt_approx(r2);
+    const float rinv2 = rinv * rinv;
+    const float sig = pi.x + pj.x;
+    const float sr2 = (sig * sig) * rinv2;
+    const float sr6 = sr2 * sr2 * sr2;
+    const float elj = (pi.y * pj.y) * sr6;
+    const float qq = xi.w * xj.w;
+    const float kr2 = T.krff * r2;
+    // dE/dr * r  and energy (OpenMM 7.3 ReferenceLJCoulombIxn, reaction field, LJ not shifted)
+    const float dEdR = elj * (12.f * sr6 - 6.f) + qq * (rinv - 2.f * kr2);
+    const float e = elj * (sr6 - 1.f) + qq * (rinv + kr2 - T.crff);
+    const float fs = in ? dEdR * rinv2 : 0.f;
+    en += in ? e : 0.f;
+    cnt += in;
+    fi.fx += fs * dx; fi.fy += fs * dy; fi.fz += fs * dz;
+    fj.fx -= fs * dx; fj.fy -= fs * dy; fj.fz -= fs * dz;
+}
+
+template <bool PERIODIC, bool EXACT, bool EMIT>
+__global__ void __launch_bounds__(kWarps * 32, 8)
+pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
+                    const double* __restrict__ pos_all,
                     long long* __restrict__ f1acc, double* __restrict__ epart,
                     long long* __restrict__ cpart, int exact, int* emit_counter, int* emit_pairs,
                     int emit_cap, int emit_replica) {
@@ -103,6 +160,7 @@ pair_cluster_kernel(Topology T, PairListView V, const double* __restrict__ pos_a
     __syncwarp();
 
     const int ti = lane & 7, tj = lane >> 3;
+    const uint32_t lanebit = 1u << lane;
     Acc fi[nbl::kMaxCi];
 #pragma unroll
     for (int ci = 0; ci < nbl::kMaxCi; ci++) fi[ci] = Acc{0.f, 0.f, 0.f};
@@ -125,28 +183,24 @@ pair_cluster_kernel(Topology T, PairListView V, const double* __restrict__ pos_a
             xj.z += (float)nbl::shift_z(code) * T.boxf[2];
         }
         Acc fj{0.f, 0.f, 0.f};
-        if (midx == 0) {
+        bool rare = false;
+        // mask set 0 is "all ones": only masked entries (diagonal / bonded neighbours) load words
+        const uint32_t* mw = V.masks + (size_t)midx * nbl::kMaxCi;
 #pragma unroll
-            for (int ci = 0; ci < nbl::kMaxCi; ci++) {
-                if ((imask >> ci) & 1u) {
-                    const int il = ci * nbl::kClusterSize + ti;
-                    pair_step<PERIODIC>(T, s_xi[warp][il], s_pi[warp][il], xj, pj, true, exact, V,
-                                        pos_all, ibase + il, jslot, fi[ci], fj, en, cnt, emit,
-                                        emit_counter, emit_pairs, emit_cap);
-                }
+        for (int ci = 0; ci < nbl::kMaxCi; ci++) {
+            if ((imask >> ci) & 1u) {
+                const int il = ci * nbl::kClusterSize + ti;
+                const uint32_t w = midx ? mw[ci] : 0xffffffffu;
+                const bool allowed = (w & lanebit) != 0u;
+                pair_step<EXACT || EMIT, EMIT>(T, s_xi[warp][il], s_pi[warp][il], xj, pj, allowed, rare,
+                                         fi[ci], fj, en, cnt);
             }
-        } else {
-            const uint32_t* mw = V.masks + (size_t)midx * nbl::kMaxCi;
-#pragma unroll
-            for (int ci = 0; ci < nbl::kMaxCi; ci++) {
-                if ((imask >> ci) & 1u) {
-                    const int il = ci * nbl::kClusterSize + ti;
-                    const bool allowed = (mw[ci] >> lane) & 1u;
-                    pair_step<PERIODIC>(T, s_xi[warp][il], s_pi[warp][il], xj, pj, allowed, exact, V,
-                                        pos_all, ibase + il, jslot, fi[ci], fj, en, cnt, emit,
-                                        emit_counter, emit_pairs, emit_cap);
-                }
-            }
+        }
+        if (EXACT || EMIT) {
+            if (__any_sync(0xffffffffu, rare))
+                fix_rare_pairs(T, V, pos_all, f1acc, s_xi[warp], s_pi[warp], ibase, jslot, xj, pj,
+                               imask, midx, lane, &en, &cnt, exact != 0, EMIT, emit, emit_counter, emit_pairs,
+                               emit_cap);
         }
         // j force: reduce over ti (lanes with equal tj), lanes ti = 0,1,2 write x,y,z
 #pragma unroll
@@ -233,17 +287,22 @@ void launch_pair_cluster(const Topology& T, const PairListView& V, const double*
     if (V.nunits <= 0) return;
     const int grid = (V.nunits + kWarps - 1) / kWarps;
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
+#define SDM_LAUNCH(P, X, E, TT)                                                                  \
+    pair_cluster_kernel<P, X, E><<<grid, kWarps * 32, 0, s>>>(TT, V, pos_all, f1acc, epart, cpart, \
+                                                             exact, emit_counter, emit_pairs,     \
+                                                             emit_cap, emit_replica)
     if (emit_pairs) {
-        if (periodic)
-            pair_cluster_kernel<true, true><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
-        else
-            pair_cluster_kernel<false, true><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+        // debug pass: every in-range pair takes the out-of-line path, which also records it
+        if (periodic) SDM_LAUNCH(true, true, true, T);
+        else SDM_LAUNCH(false, true, true, T);
+    } else if (exact) {
+        if (periodic) SDM_LAUNCH(true, true, false, T);
+        else SDM_LAUNCH(false, true, false, T);
     } else {
-        if (periodic)
-            pair_cluster_kernel<true, false><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, exact, nullptr, nullptr, 0, -1);
-        else
-            pair_cluster_kernel<false, false><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, exact, nullptr, nullptr, 0, -1);
+        if (periodic) SDM_LAUNCH(true, false, false, T);
+        else SDM_LAUNCH(false, false, false, T);
     }
+#undef SDM_LAUNCH
 }
 
 void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,

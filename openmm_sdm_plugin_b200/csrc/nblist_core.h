@@ -176,6 +176,7 @@ struct SearchView {
     const BBox* cl_box;        // [ncluster]  8-slot cluster boxes
     const BBox* j4_box;        // [ncluster*2]
     const int* cell_slot;      // [R*ncell + 1] first slot of every global cell (padded layout)
+    const float* posq4;        // [nslot][4] sorted positions: exact (atom-level) pruning of imask
 };
 
 // Cell-coordinate range (unwrapped for periodic, clamped for non-periodic) the sci must scan.
@@ -195,6 +196,23 @@ SDM_HD void search_range(const Grid& G, const BBox& b, int cmin[3], int cmax[3])
         cmin[d] = ia;
         cmax[d] = ic;
     }
+}
+
+// Is any atom of cluster A within rlist of any atom of j-group j4 (shifted)?  Dummies never are.
+SDM_HD bool any_pair_within(const float* posq4, int A, int j4, float sx, float sy, float sz,
+                            float rlist2) {
+    for (int tj = 0; tj < kJGroup; tj++) {
+        const float* pj = posq4 + 4 * (size_t)(j4 * kJGroup + tj);
+        if (pj[0] >= 0.5f * kFar) continue;
+        const float xj = pj[0] + sx, yj = pj[1] + sy, zj = pj[2] + sz;
+        for (int ti = 0; ti < kClusterSize; ti++) {
+            const float* pi = posq4 + 4 * (size_t)(A * kClusterSize + ti);
+            if (pi[0] >= 0.5f * kFar) continue;
+            const float dx = pi[0] - xj, dy = pi[1] - yj, dz = pi[2] - zj;
+            if (dx * dx + dy * dy + dz * dz < rlist2) return true;
+        }
+    }
+    return false;
 }
 
 // One search item = (sci, stencil offset).  Visits the j-groups of the addressed cell and calls
@@ -246,7 +264,8 @@ SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
                 own = owner_is_i(A, B);
             }
             if (!own) continue;
-            if (box_dist2(V.cl_box[A], jb, sx, sy, sz) < G.rlist2) imask |= 1u << ci;
+            if (box_dist2(V.cl_box[A], jb, sx, sy, sz) >= G.rlist2) continue;
+            if (any_pair_within(V.posq4, A, j4, sx, sy, sz, G.rlist2)) imask |= 1u << ci;
         }
         if (imask) {
             emit(count, (uint32_t)j4 | (code << 26), imask, diag && ((imask >> (B - sd.c0)) & 1u));

@@ -351,8 +351,9 @@ int setup_grid(sdm_ctx* c, PairList* pl, const double lo[3], const double ext[3]
     G.periodic = c->T.method == SDM_CUTOFF_PERIODIC ? 1 : 0;
     G.n = c->n;
     G.R = c->R;
-    G.rlist = (float)rlist;
-    G.rlist2 = (float)(rlist * rlist);
+    // + 1e-4 nm: the list is pruned with FP32 distances, the cutoff test may be decided in FP64
+    G.rlist = (float)(rlist + 1e-4);
+    G.rlist2 = (float)((rlist + 1e-4) * (rlist + 1e-4));
     double vol = ext[0] * ext[1] * ext[2];
     double density = vol > 0 ? c->n / vol : 100.0;
     double side = std::cbrt(40.0 / std::max(density, 1e-6));
@@ -452,6 +453,7 @@ static int build_list(sdm_ctx* c) {
     V.cl_box = pl->cl_box;
     V.j4_box = pl->j4_box;
     V.cell_slot = pl->cell_slot;
+    V.posq4 = reinterpret_cast<const float*>(pl->posq);
     const long long nitems = (long long)pl->nsci * noff;
     if ((size_t)nitems + 1 > pl->items_cap) {
         pl->items_cap = (size_t)nitems + 1;

@@ -26,8 +26,9 @@ bool setup_grid(Grid& G, int n, int R, bool periodic, double rlist, const double
     G.periodic = periodic ? 1 : 0;
     G.n = n;
     G.R = R;
-    G.rlist = (float)rlist;
-    G.rlist2 = (float)(rlist * rlist);
+    // + 1e-4 nm: the list is pruned with FP32 distances, the cutoff test may be decided in FP64
+    G.rlist = (float)(rlist + 1e-4);
+    G.rlist2 = (float)((rlist + 1e-4) * (rlist + 1e-4));
     double vol = ext[0] * ext[1] * ext[2];
     double density = vol > 0 ? n / vol : 100.0;
     double side = std::cbrt(40.0 / std::max(density, 1e-6));
@@ -61,7 +62,13 @@ bool setup_grid(Grid& G, int n, int R, bool periodic, double rlist, const double
 
 }  // namespace
 
+static const int* g_subkey = nullptr;  // experiment hook: per-atom in-cell rank replacing the Morton code
+
 extern "C" {
+
+void hostcheck_set_subkey(const int* k) { g_subkey = k; }
+static int* g_cell_out = nullptr;
+void hostcheck_set_cell_out(int* c) { g_cell_out = c; }
 
 // pos: [R][n][3] doubles.  excl: unique pairs a<b.  Returns the number of covered pairs of
 // replica `replica` (sorted (i<j) System indices written to out_pairs up to max_pairs), or <0.
@@ -97,7 +104,9 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
         float xw[3];
         int im[3];
         keys[t] = atom_key(G, t / n, pos[3 * (size_t)t], pos[3 * (size_t)t + 1], pos[3 * (size_t)t + 2], xw, im);
+        if (g_subkey) keys[t] = (keys[t] & ~((1u << kSubBits) - 1u)) | (uint32_t)(g_subkey[t] & ((1 << kSubBits) - 1));
         vals[t] = t;
+        if (g_cell_out) g_cell_out[t] = (int)(keys[t] >> kSubBits);
     }
     std::vector<int> order(total);
     std::iota(order.begin(), order.end(), 0);
@@ -176,6 +185,7 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     V.cl_box = cl_box.data();
     V.j4_box = j4_box.data();
     V.cell_slot = cell_slot.data();
+    V.posq4 = posq.data();
     const long long nitems = (long long)nsci * noff;
     std::vector<int> item_off(nitems + 1, 0);
     for (long long t = 0; t < nitems; t++)

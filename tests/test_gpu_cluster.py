@@ -112,8 +112,8 @@ def test_refresh_across_periodic_boundary():
         ctx.set_positions(0, pos)
         ctx.eval()
         mol = (i // 3) * 3
-        pos[mol:mol + 3, 0] -= pos[i, 0] + 0.02   # now at x = -0.02 (outside the box), moved < skin/2
-        assert abs(pos[i, 0] + 0.02) < 1e-12 and (case.positions[i, 0] + 0.02) < 0.05
+        pos[mol:mol + 3, 0] -= pos[i, 0] + 0.005  # now at x = -0.005 (outside the box), moved < skin/2
+        assert abs(pos[i, 0] + 0.005) < 1e-12 and (case.positions[i, 0] + 0.005) < 0.05
         ctx.set_positions(0, pos)
         ctx.eval()
         assert ctx.info("n_list_builds") == 1
