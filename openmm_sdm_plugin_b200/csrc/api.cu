@@ -487,9 +487,7 @@ int sdm_eval(sdm_ctx* c) {
         e_scale = 0.5;
         c_div = 2;
     } else {
-        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[1], s));
-        if (int rc = sdm_ctx_pairlist_eval(c)) return rc;
-        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[2], s));
+        if (int rc = sdm_ctx_pairlist_eval(c)) return rc;  // records ev[1], ev[2] around the pair kernel
         zero_acc = 1;
     }
     if (T.n_lig > 0) { sdm::launch_ligand_probe(T, B, s); c->launches++; }

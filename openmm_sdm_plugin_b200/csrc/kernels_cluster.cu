@@ -2,29 +2,53 @@
 // interactions over the cluster-pair list (sm_100a, FP32 SIMT pipe; not a dense contraction, so
 // no tensor cores).
 //
-// One warp per work unit (a supercluster = up to 8 clusters x 8 atoms, and a chunk of its
-// j-group list).  The 64 i-atoms are staged once in shared memory; lane (tj, ti) = (lane>>3,
-// lane&7) keeps j-atom tj of the current j-group in registers and walks the 8 i-clusters, so
-//   * the j force accumulates in registers across 8 pair steps and is reduced over ti with 3
-//     shuffles per component per ENTRY (not per pair),
-//   * the i forces accumulate in 24 registers across the whole unit and are reduced over tj
-//     once per unit,
-//   * each pair step costs two shared loads (float4 + float2, 8 distinct addresses per warp).
+// One warp per work unit (a supercluster = up to 8 clusters x 8 atoms, and a chunk of <= 32
+// entries of its j-cluster list).  A "tile" is one i-cluster against one j-cluster, 8 x 8 atom
+// pairs.  Lane (tj, ti) = (lane>>2, lane&3) keeps j-atom tj of the entry's j-cluster in registers
+// and evaluates it against i-atoms ti and ti+4 of every i-cluster named by the entry's imask --
+// the two i-atoms ride in the two halves of packed f32x2 registers, so the whole pair term is
+// FADD2/FMUL2/FFMA2 work: ~37 packed FP32 instructions + 2 MUFU + ~10 ALU + 3 LDS per 64 atom
+// pairs.  That makes the kernel FP32-pipe bound instead of issue bound (the scalar version
+// needed ~45 issue slots per 32 pairs for 35 FP32 operations).
+//   * i-atoms are staged once per unit in shared memory, already interleaved as (lo, hi) pairs,
+//     so a tile costs three LDS.128 with 4 distinct addresses per warp,
+//   * the i forces accumulate in 24 packed registers across the whole unit and are reduced over
+//     tj once per unit (transpose-reduction, 42 shuffles),
+//   * the j force accumulates in 3 packed registers across the tiles of an entry and is reduced
+//     over ti once per ENTRY with 3 shuffles,
+//   * the 32 entry words of a unit are fetched with one coalesced load and broadcast by shuffle,
+//     the j data of entry e+1 is requested before the tiles of entry e are computed, and the
+//     imask word goes through REDUX so that the per-cluster branches are uniform (BRA.U).
 // Forces go to 64-bit fixed-point accumulators (2^32), so the result is independent of the
 // order in which warps finish: bit-reproducible across runs, replicas-per-GPU and GPUs.
+//
+// Exact cutoff: the hot loop decides r^2 <= rc^2 in FP32 and tracks min |r^2 - rc^2| per entry;
+// when that falls inside the FP32 uncertainty band the (rare) out-of-line path re-decides those
+// pairs in FP64 exactly like the oracle and applies +/- corrections, so the in-cutoff pair set is
+// bit-identical to a double-precision evaluation.
 //
 // Arithmetic restated from OpenMM 7.3 ReferenceLJCoulombIxn::calculateOneIxn (SURVEY.md
 // Appendix B.3) in FP32: per-atom sigma/2 and 2*sqrt(eps), charges pre-scaled by
 // sqrt(ONE_4PI_EPS0), reaction field krf/crf, LJ not shifted.
+#include "f32x2.cuh"
 #include "pairlist.h"
 
 namespace sdm {
 namespace {
 
 constexpr int kWarps = 4;
+constexpr float kFix = 4294967296.0f;  // 2^32
+constexpr int kIRows = nbl::kMaxCi * 4;   // (cluster, ti) rows of staged i-atom pairs per unit
 
-struct Acc {
-    float fx, fy, fz;
+struct Acc2 {
+    f2 x, y, z;
+};
+
+// Staged i-atom pair (atoms ti and ti+4 of one cluster), 48 bytes: three LDS.128.
+struct __align__(16) IPair {
+    f2 x, y;      // (x_lo, x_hi), (y_lo, y_hi)
+    f2 z, q;      // (z_lo, z_hi), (q_lo, q_hi)
+    f2 s, e;      // sigma/2 and 2*sqrt(eps) pairs
 };
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -33,210 +57,347 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
-// Rare path: pairs whose FP32 r^2 lies within T.band of the cutoff are left out by the hot loop
-// and handled here, once per affected entry, with the FP64 in-cutoff test of the oracle.  Their
-// force goes straight to the fixed-point accumulators (both atoms); energy and count are
-// returned through en / cnt.  Out of line so that the hot loop stays small.
-__device__ __noinline__ void fix_rare_pairs(const Topology& T, const PairListView& V,
+// r^2 of an (i, j) pair with a fixed operation order: the packed hot loop, the fix-up path and
+// the debug pair dump must all see the same FP32 value (fma.rn.f32x2 rounds each half exactly
+// like fma.rn.f32).
+__device__ __forceinline__ float pair_r2(const float xi, const float yi, const float zi,
+                                         const float4 xj, float& dx, float& dy, float& dz) {
+    dx = __fsub_rn(xi, xj.x);
+    dy = __fsub_rn(yi, xj.y);
+    dz = __fsub_rn(zi, xj.z);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+struct PairConsts {
+    float rc2, krf, crf, band;
+};
+
+// Scalar FP32 pair term (fix-up path only); returns fs with F_i += fs*d, F_j -= fs*d.
+__device__ __forceinline__ float pair_term_f32(const float r2, const float qi, const float si,
+                                               const float ei, const float qj, const float2 pj,
+                                               const PairConsts& K, float& e) {
+    const float rinv = rsqrt_approx(r2);
+    const float rinv2 = rinv * rinv;
+    const float sig = si + pj.x;
+    const float sr2 = (sig * sig) * rinv2;
+    const float sr6 = sr2 * sr2 * sr2;
+    const float elj = (ei * pj.y) * sr6;
+    const float qq = qi * qj;
+    const float kr2 = K.krf * r2;
+    const float a = elj * sr6;
+    const float e_lj = a - elj;
+    const float dEdR = fmaf(a + e_lj, 6.f, qq * fmaf(-2.f, kr2, rinv));
+    e = fmaf(qq, (rinv + kr2) - K.crf, e_lj);
+    return dEdR * rinv2;
+}
+
+// One tile step of the hot loop: i-atoms (ci, ti) and (ci, ti+4) against the lane's j atom.
+//   dE/dr * r  and energy (OpenMM 7.3 ReferenceLJCoulombIxn, reaction field, LJ not shifted):
+//   e_lj = elj*(sr6 - 1) = a - elj,   elj*(12*sr6 - 6) = 6*(a + e_lj)   with a = elj*sr6
+template <bool MASKED, bool EXACT>
+__device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const float4 xj,
+                                          const float2 pj, const bool allow_lo, const bool allow_hi,
+                                          const PairConsts& K, Acc2& fi, Acc2& fj, f2& en, int& cnt,
+                                          float& tmin) {
+    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(&ip->x);
+    const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(&ip->z);
+    const ulonglong2 a2 = *reinterpret_cast<const ulonglong2*>(&ip->s);
+    const f2 dx = sub2(a0.x, bc(xj.x));
+    const f2 dy = sub2(a0.y, bc(xj.y));
+    const f2 dz = sub2(a1.x, bc(xj.z));
+    const f2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const f2 t = sub2(r2, bc(K.rc2));
+    const float t_lo = lo(t), t_hi = hi(t);
+    const bool in_lo = MASKED ? (allow_lo && t_lo <= 0.f) : (t_lo <= 0.f);
+    const bool in_hi = MASKED ? (allow_hi && t_hi <= 0.f) : (t_hi <= 0.f);
+    if (EXACT) tmin = fminf(tmin, fminf(fabsf(t_lo), fabsf(t_hi)));
+    const f2 rinv = pk(rsqrt_approx(lo(r2)), rsqrt_approx(hi(r2)));
+    const f2 rinv2 = mul2(rinv, rinv);
+    const f2 sig = add2(a2.x, bc(pj.x));
+    const f2 sr2 = mul2(mul2(sig, sig), rinv2);
+    const f2 sr6 = mul2(mul2(sr2, sr2), sr2);
+    const f2 elj = mul2(mul2(a2.y, bc(pj.y)), sr6);
+    const f2 qq = mul2(a1.y, bc(xj.w));
+    const f2 kr2 = mul2(r2, bc(K.krf));
+    const f2 a = mul2(elj, sr6);
+    const f2 e_lj = sub2(a, elj);
+    const f2 dEdR = fma2(add2(a, e_lj), bc(6.f), mul2(qq, fma2(kr2, bc(-2.f), rinv)));
+    const f2 e = fma2(qq, sub2(add2(rinv, kr2), bc(K.crf)), e_lj);
+    const f2 fsr = mul2(dEdR, rinv2);
+    const f2 fs = pk(in_lo ? lo(fsr) : 0.f, in_hi ? hi(fsr) : 0.f);
+    en = add2(en, pk(in_lo ? lo(e) : 0.f, in_hi ? hi(e) : 0.f));
+    // cnt += in as ONE predicated add per half (the compiler's own rendering takes three
+    // instructions); ptxas merges the setp with the one that feeds the selects above
+    if (MASKED) {
+        asm("{\n .reg .pred p, q;\n setp.ne.s32 q, %2, 0;\n setp.le.and.f32 p, %1, 0f00000000, q;\n"
+            " @p add.s32 %0, %0, 1;\n}" : "+r"(cnt) : "f"(t_lo), "r"((int)allow_lo));
+        asm("{\n .reg .pred p, q;\n setp.ne.s32 q, %2, 0;\n setp.le.and.f32 p, %1, 0f00000000, q;\n"
+            " @p add.s32 %0, %0, 1;\n}" : "+r"(cnt) : "f"(t_hi), "r"((int)allow_hi));
+    } else {
+        asm("{\n .reg .pred p;\n setp.le.f32 p, %1, 0f00000000;\n @p add.s32 %0, %0, 1;\n}"
+            : "+r"(cnt) : "f"(t_lo));
+        asm("{\n .reg .pred p;\n setp.le.f32 p, %1, 0f00000000;\n @p add.s32 %0, %0, 1;\n}"
+            : "+r"(cnt) : "f"(t_hi));
+    }
+    fi.x = fma2(fs, dx, fi.x); fi.y = fma2(fs, dy, fi.y); fi.z = fma2(fs, dz, fi.z);
+    // the j force is accumulated with the i sign and negated once per entry
+    fj.x = fma2(fs, dx, fj.x); fj.y = fma2(fs, dy, fj.y); fj.z = fma2(fs, dz, fj.z);
+}
+
+// Rare path: pairs whose FP32 r^2 lies within K.band of the cutoff are re-decided with the FP64
+// in-cutoff test of the oracle; where that differs from the FP32 decision of the hot loop the
+// pair's force/energy/count is added or taken back (forces straight to the fixed-point
+// accumulators of both atoms).  Out of line so that the hot loop stays small.
+__device__ __noinline__ void fix_band_pairs(const Topology& T, const PairListView& V,
                                             const double* __restrict__ pos_all,
-                                            long long* __restrict__ f1acc, const float4* s_xi,
-                                            const float2* s_pi, int ibase, int jslot, float4 xj,
-                                            float2 pj, uint32_t imask, uint32_t midx, int lane,
-                                            float* en, int* cnt, bool use_f64, bool all,
-                                            bool emit, int* emit_counter, int* emit_pairs,
-                                            int emit_cap) {
-    const int ti = lane & 7;
+                                            long long* __restrict__ f1acc, const IPair* s_ip,
+                                            int ibase, int jslot, float4 xj, float2 pj,
+                                            uint32_t imask, uint32_t midx, int lane, float* en,
+                                            int* cnt) {
+    const int ti = lane & 3;
     const size_t plane = (size_t)V.nslot_cap;
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
     for (int ci = 0; ci < nbl::kMaxCi; ci++) {
         if (!((imask >> ci) & 1u)) continue;
-        const uint32_t w = midx ? V.masks[(size_t)midx * nbl::kMaxCi + ci] : 0xffffffffu;
-        if (!((w >> lane) & 1u)) continue;
-        const int il = ci * nbl::kClusterSize + ti;
-        const float4 xi = s_xi[il];
-        const float2 pi = s_pi[il];
-        const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        const float r2 = dx * dx + dy * dy + dz * dz;
-        const float t = r2 - T.rc2f;
-        const bool near = fabsf(t) < T.band;
-        if (!(near || (all && t <= 0.f))) continue;
-        const int islot = ibase + il;
-        const int ai = V.atom[islot], aj = V.atom[jslot];
-        if (ai < 0 || aj < 0) continue;
-        const int r = ai / T.n;
-        if (near && use_f64) {
-            if (!in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n)) continue;
-        } else if (!(t <= 0.f)) {
-            continue;
-        }
-        const float rinv = rsqrtf(r2), rinv2 = rinv * rinv;
-        const float sig = pi.x + pj.x;
-        const float sr2 = (sig * sig) * rinv2;
-        const float sr6 = sr2 * sr2 * sr2;
-        const float elj = (pi.y * pj.y) * sr6;
-        const float qq = xi.w * xj.w;
-        const float kr2 = T.krff * r2;
-        const float fs = (elj * (12.f * sr6 - 6.f) + qq * (rinv - 2.f * kr2)) * rinv2;
-        *en += elj * (sr6 - 1.f) + qq * (rinv + kr2 - T.crff);
-        *cnt += 1;
-        const float f[3] = {fs * dx, fs * dy, fs * dz};
-        for (int c = 0; c < 3; c++) {
-            const long long v = __float2ll_rn(f[c] * 4294967296.0f);
-            atomic_add_fixed(f1acc + (size_t)c * plane + islot, v);
-            atomic_add_fixed(f1acc + (size_t)c * plane + jslot, -v);
-        }
-        if (emit) {
-            const int a = ai % T.n, b = aj % T.n;
-            const int slot = atomicAdd(emit_counter, 1);
-            if (slot < emit_cap) {
-                emit_pairs[2 * slot] = a < b ? a : b;
-                emit_pairs[2 * slot + 1] = a < b ? b : a;
+        const IPair ip = s_ip[ci * 4 + ti];
+        for (int h = 0; h < 2; h++) {
+            const uint32_t w = midx ? V.masks[(size_t)midx * nbl::kMaskWords + 2 * ci + h] : 0xffffffffu;
+            if (!((w >> lane) & 1u)) continue;
+            const float xi = h ? hi(ip.x) : lo(ip.x), yi = h ? hi(ip.y) : lo(ip.y);
+            const float zi = h ? hi(ip.z) : lo(ip.z), qi = h ? hi(ip.q) : lo(ip.q);
+            const float si = h ? hi(ip.s) : lo(ip.s), ei = h ? hi(ip.e) : lo(ip.e);
+            float dx, dy, dz;
+            const float r2 = pair_r2(xi, yi, zi, xj, dx, dy, dz);
+            const float t = r2 - K.rc2;
+            if (!(fabsf(t) < K.band)) continue;
+            const int islot = ibase + ci * nbl::kClusterSize + ti + 4 * h;
+            const int ai = V.atom[islot], aj = V.atom[jslot];
+            if (ai < 0 || aj < 0) continue;
+            const int r = ai / T.n;
+            const bool in64 = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
+            const bool in32 = t <= 0.f;
+            if (in64 == in32) continue;
+            const float sgn = in64 ? 1.f : -1.f;
+            float e;
+            const float fs = sgn * pair_term_f32(r2, qi, si, ei, xj.w, pj, K, e);
+            *en += sgn * e;
+            *cnt += in64 ? 1 : -1;
+            const float f[3] = {fs * dx, fs * dy, fs * dz};
+            for (int c = 0; c < 3; c++) {
+                const long long v = __float2ll_rn(f[c] * kFix);
+                atomic_add_fixed(f1acc + (size_t)c * plane + islot, v);
+                atomic_add_fixed(f1acc + (size_t)c * plane + jslot, -v);
             }
         }
     }
 }
 
-// One (i-atom, j-atom) pair of the hot loop.  `rare` accumulates "this lane met a pair inside
-// the FP64 re-test band"; such pairs are skipped here and fixed up by fix_rare_pairs().
-template <bool EXACT, bool ALL>
-__device__ __forceinline__ void pair_step(const Topology& T, const float4 xi, const float2 pi,
-                                          const float4 xj, const float2 pj, const bool allowed,
-                                          bool& rare, Acc& fi, Acc& fj, float& en, int& cnt) {
-    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-    const float r2 = dx * dx + dy * dy + dz * dz;
-    const float t = r2 - T.rc2f;
-    bool in = allowed && (t <= 0.f);
-    if (EXACT) {
-        const bool near = allowed && (ALL ? t < T.band : fabsf(t) < T.band);
-        rare |= near;
-        in = in && !near;
+template <bool MASKED, bool EXACT>
+__device__ __forceinline__ void entry_tiles(const uint32_t imask, const uint32_t* __restrict__ mw,
+                                            const int lane, const IPair* s_ip, const float4 xj,
+                                            const float2 pj, const PairConsts& K,
+                                            Acc2 (&fi)[nbl::kMaxCi], Acc2& fj, f2& en, int& cnt,
+                                            float& tmin) {
+    const int ti = lane & 3;
+    uint32_t w[nbl::kMaskWords];
+    if (MASKED) {
+#pragma unroll
+        for (int k = 0; k < nbl::kMaskWords / 4; k++) {
+            const uint4 a = reinterpret_cast<const uint4*>(mw)[k];
+            w[4 * k] = a.x; w[4 * k + 1] = a.y; w[4 * k + 2] = a.z; w[4 * k + 3] = a.w;
+        }
     }
-    const float rinv = rsqrt_approx(r2);
-    const float rinv2 = rinv * rinv;
-    const float sig = pi.x + pj.x;
-    const float sr2 = (sig * sig) * rinv2;
-    const float sr6 = sr2 * sr2 * sr2;
-    const float elj = (pi.y * pj.y) * sr6;
-    const float qq = xi.w * xj.w;
-    const float kr2 = T.krff * r2;
-    // dE/dr * r  and energy (OpenMM 7.3 ReferenceLJCoulombIxn, reaction field, LJ not shifted)
-    const float dEdR = elj * (12.f * sr6 - 6.f) + qq * (rinv - 2.f * kr2);
-    const float e = elj * (sr6 - 1.f) + qq * (rinv + kr2 - T.crff);
-    const float fs = in ? dEdR * rinv2 : 0.f;
-    en += in ? e : 0.f;
-    cnt += in;
-    fi.fx += fs * dx; fi.fy += fs * dy; fi.fz += fs * dz;
-    fj.fx -= fs * dx; fj.fy -= fs * dy; fj.fz -= fs * dz;
+#pragma unroll
+    for (int ci = 0; ci < nbl::kMaxCi; ci++) {
+        if (imask & (1u << ci)) {
+            const bool allow_lo = MASKED ? ((w[2 * ci] >> lane) & 1u) != 0u : true;
+            const bool allow_hi = MASKED ? ((w[2 * ci + 1] >> lane) & 1u) != 0u : true;
+            tile_step<MASKED, EXACT>(s_ip + ci * 4 + ti, xj, pj, allow_lo, allow_hi, K, fi[ci], fj, en,
+                                     cnt, tmin);
+        }
+    }
 }
 
-template <bool PERIODIC, bool EXACT, bool EMIT>
-__global__ void __launch_bounds__(kWarps * 32, 8)
+template <bool PERIODIC, bool EXACT>
+__global__ void __launch_bounds__(kWarps * 32)
 pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
-                    const double* __restrict__ pos_all,
-                    long long* __restrict__ f1acc, double* __restrict__ epart,
-                    long long* __restrict__ cpart, int exact, int* emit_counter, int* emit_pairs,
-                    int emit_cap, int emit_replica) {
-    __shared__ float4 s_xi[kWarps][64];
-    __shared__ float2 s_pi[kWarps][64];
+                    const double* __restrict__ pos_all, long long* __restrict__ f1acc,
+                    double* __restrict__ epart, long long* __restrict__ cpart) {
+    __shared__ IPair s_ip[kWarps][kIRows];
+    __shared__ float4 s_shift[64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (PERIODIC) {
+        if (threadIdx.x < 64) {
+            const uint32_t code = threadIdx.x;
+            s_shift[threadIdx.x] = make_float4((float)nbl::shift_x(code) * T.boxf[0],
+                                               (float)nbl::shift_y(code) * T.boxf[1],
+                                               (float)nbl::shift_z(code) * T.boxf[2], 0.f);
+        }
+        __syncthreads();
+    }
     const int unit = blockIdx.x * kWarps + warp;
     if (unit >= V.nunits) return;  // warp-uniform; no block-level barrier below
     const Unit u = V.units[unit];
     const nbl::SciDesc sd = V.sci[u.sci];
     const int ibase = sd.c0 * nbl::kClusterSize;
-    const int ni = sd.nci * nbl::kClusterSize;
-    const bool emit = EMIT && sd.replica == emit_replica;
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
+    const int ti = lane & 3, tj = lane >> 2;
 
+    // entry words of this unit: one coalesced load, broadcast by shuffle in the loop
+    const int nent = u.end - u.begin;  // <= 32
+    uint2 my_ent = make_uint2(0u, 0u);
+    if (lane < nent) my_ent = V.entries[u.begin + lane];
+
+    // stage the i-atoms: lane (c, t) = (lane>>2, lane&3) interleaves atoms t and t+4 of cluster c
+    {
+        float4 p[2];
+        float2 pr[2];
 #pragma unroll
-    for (int k = lane; k < 64; k += 32) {
-        float4 p = make_float4(-nbl::kFar, -nbl::kFar, -nbl::kFar, 0.f);
-        float2 pr = make_float2(0.f, 0.f);
-        if (k < ni) {
-            const float4 q = V.posq[ibase + k];
-            if (q.x < 0.5f * nbl::kFar) { p = q; pr = V.par[ibase + k]; }
+        for (int h = 0; h < 2; h++) {
+            p[h] = make_float4(-nbl::kFar, -nbl::kFar, -nbl::kFar, 0.f);
+            pr[h] = make_float2(0.f, 0.f);
+            if (tj < sd.nci) {
+                const int s = ibase + tj * nbl::kClusterSize + ti + 4 * h;
+                const float4 q = V.posq[s];
+                if (q.x < 0.5f * nbl::kFar) { p[h] = q; pr[h] = V.par[s]; }
+            }
         }
-        s_xi[warp][k] = p;
-        s_pi[warp][k] = pr;
+        IPair ip;
+        ip.x = pk(p[0].x, p[1].x); ip.y = pk(p[0].y, p[1].y);
+        ip.z = pk(p[0].z, p[1].z); ip.q = pk(p[0].w, p[1].w);
+        ip.s = pk(pr[0].x, pr[1].x); ip.e = pk(pr[0].y, pr[1].y);
+        s_ip[warp][lane] = ip;
     }
     __syncwarp();
 
-    const int ti = lane & 7, tj = lane >> 3;
-    const uint32_t lanebit = 1u << lane;
-    Acc fi[nbl::kMaxCi];
+    Acc2 fi[nbl::kMaxCi];
 #pragma unroll
-    for (int ci = 0; ci < nbl::kMaxCi; ci++) fi[ci] = Acc{0.f, 0.f, 0.f};
-    float en = 0.f;
+    for (int ci = 0; ci < nbl::kMaxCi; ci++) fi[ci] = Acc2{0ull, 0ull, 0ull};
+    f2 en = 0ull;
     int cnt = 0;
+    uint32_t fixmask = 0u;
     const size_t plane = (size_t)V.nslot_cap;
 
-    for (int e = u.begin; e < u.end; e++) {
-        const uint2 ent = V.entries[e];
-        const int j4 = (int)(ent.x & 0x3ffffffu);
-        const uint32_t code = ent.x >> 26;
-        const uint32_t imask = ent.y & 0xffu;
-        const uint32_t midx = ent.y >> 8;
-        const int jslot = j4 * nbl::kJGroup + tj;
-        float4 xj = V.posq[jslot];
-        const float2 pj = V.par[jslot];
+    // software pipeline: j data of the next entry is in flight while this entry is computed
+    uint32_t ex = __shfl_sync(0xffffffffu, my_ent.x, 0);
+    int jslot = (int)(ex & 0x3ffffffu) * nbl::kJGroup + tj;
+    float4 xj_n = V.posq[jslot];
+    float2 pj_n = V.par[jslot];
+
+    for (int k = 0; k < nent; k++) {
+        // uniform (REDUX) copy of the entry word: branches on imask need no reconvergence
+        const uint32_t ey = __reduce_or_sync(0xffffffffu, __shfl_sync(0xffffffffu, my_ent.y, k));
+        const uint32_t code = ex >> 26;
+        const uint32_t imask = ey & 0xffu;
+        const uint32_t midx = ey >> 8;
+        const int jslot_k = jslot;
+        float4 xj = xj_n;
+        const float2 pj = pj_n;
+        if (k + 1 < nent) {
+            ex = __shfl_sync(0xffffffffu, my_ent.x, k + 1);
+            jslot = (int)(ex & 0x3ffffffu) * nbl::kJGroup + tj;
+            xj_n = V.posq[jslot];
+            pj_n = V.par[jslot];
+        }
         if (PERIODIC) {
-            xj.x += (float)nbl::shift_x(code) * T.boxf[0];
-            xj.y += (float)nbl::shift_y(code) * T.boxf[1];
-            xj.z += (float)nbl::shift_z(code) * T.boxf[2];
+            const float4 sh = s_shift[code];
+            xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
         }
-        Acc fj{0.f, 0.f, 0.f};
-        bool rare = false;
-        // mask set 0 is "all ones": only masked entries (diagonal / bonded neighbours) load words
-        const uint32_t* mw = V.masks + (size_t)midx * nbl::kMaxCi;
-#pragma unroll
-        for (int ci = 0; ci < nbl::kMaxCi; ci++) {
-            if ((imask >> ci) & 1u) {
-                const int il = ci * nbl::kClusterSize + ti;
-                const uint32_t w = midx ? mw[ci] : 0xffffffffu;
-                const bool allowed = (w & lanebit) != 0u;
-                pair_step<EXACT || EMIT, EMIT>(T, s_xi[warp][il], s_pi[warp][il], xj, pj, allowed, rare,
-                                         fi[ci], fj, en, cnt);
-            }
+        Acc2 fj{0ull, 0ull, 0ull};
+        float tmin = 3.0e38f;
+        if (midx == 0)
+            entry_tiles<false, EXACT>(imask, nullptr, lane, s_ip[warp], xj, pj, K, fi, fj, en, cnt, tmin);
+        else
+            entry_tiles<true, EXACT>(imask, V.masks + (size_t)midx * nbl::kMaskWords, lane, s_ip[warp],
+                                     xj, pj, K, fi, fj, en, cnt, tmin);
+        if (EXACT) {
+            // entries with a pair inside the band are revisited after the loop (keeps the call
+            // and its register pressure out of the hot loop)
+            if (__any_sync(0xffffffffu, tmin < K.band)) fixmask |= 1u << k;
         }
-        if (EXACT || EMIT) {
-            if (__any_sync(0xffffffffu, rare))
-                fix_rare_pairs(T, V, pos_all, f1acc, s_xi[warp], s_pi[warp], ibase, jslot, xj, pj,
-                               imask, midx, lane, &en, &cnt, exact != 0, EMIT, emit, emit_counter, emit_pairs,
-                               emit_cap);
-        }
-        // j force: reduce over ti (lanes with equal tj), lanes ti = 0,1,2 write x,y,z
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            fj.fx += __shfl_xor_sync(0xffffffffu, fj.fx, o);
-            fj.fy += __shfl_xor_sync(0xffffffffu, fj.fy, o);
-            fj.fz += __shfl_xor_sync(0xffffffffu, fj.fz, o);
-        }
-        if (ti < 3) {
-            const float v = ti == 0 ? fj.fx : (ti == 1 ? fj.fy : fj.fz);
-            if (v != 0.f)
-                atomic_add_fixed(f1acc + (size_t)ti * plane + jslot, __float2ll_rn(v * 4294967296.0f));
+        // j force: add the two halves, then transpose-reduce (x, y, z) over the 4 ti lanes with 3
+        // shuffles.  Afterwards lane ti = 0 holds X, ti = 1 holds Y, ti = 2 (and 3) hold Z.
+        {
+            const float jx = lo(fj.x) + hi(fj.x), jy = lo(fj.y) + hi(fj.y), jz = lo(fj.z) + hi(fj.z);
+            const bool odd = (ti & 1) != 0;
+            const float send = odd ? jx : jy;
+            float keep = odd ? jy : jx;
+            keep += __shfl_xor_sync(0xffffffffu, send, 1);
+            const float z = jz + __shfl_xor_sync(0xffffffffu, jz, 1);
+            const bool up = (ti & 2) != 0;
+            const float send2 = up ? keep : z;
+            float v = up ? z : keep;
+            v += __shfl_xor_sync(0xffffffffu, send2, 2);
+            // lane ti: 0 -> X, 1 -> Y, 2 -> Z, 3 -> Z (duplicate, not written); sign: F_j = -sum
+            if (ti < 3 && v != 0.f)
+                atomic_add_fixed(f1acc + (size_t)ti * plane + jslot_k, __float2ll_rn(-v * kFix));
         }
     }
 
-    // i forces: reduce over tj, lane (tj, ti) writes clusters tj and tj+4
+    // i forces: transpose-reduce the 48 partial sums over the 8 tj lanes (xor 16, 8, 4); lane
+    // (tj, ti) ends up with cluster ci = tj, atoms ti (lo) and ti+4 (hi).
+    {
+        float v[48];
 #pragma unroll
-    for (int ci = 0; ci < nbl::kMaxCi; ci++) {
-        float x = fi[ci].fx, y = fi[ci].fy, z = fi[ci].fz;
-        x += __shfl_xor_sync(0xffffffffu, x, 8);
-        y += __shfl_xor_sync(0xffffffffu, y, 8);
-        z += __shfl_xor_sync(0xffffffffu, z, 8);
-        x += __shfl_xor_sync(0xffffffffu, x, 16);
-        y += __shfl_xor_sync(0xffffffffu, y, 16);
-        z += __shfl_xor_sync(0xffffffffu, z, 16);
-        if ((ci & 3) == tj && ci < sd.nci) {
-            const int islot = ibase + ci * nbl::kClusterSize + ti;
-            if (x != 0.f) atomic_add_fixed(f1acc + islot, __float2ll_rn(x * 4294967296.0f));
-            if (y != 0.f) atomic_add_fixed(f1acc + plane + islot, __float2ll_rn(y * 4294967296.0f));
-            if (z != 0.f) atomic_add_fixed(f1acc + 2 * plane + islot, __float2ll_rn(z * 4294967296.0f));
+        for (int ci = 0; ci < nbl::kMaxCi; ci++) {
+            v[6 * ci + 0] = lo(fi[ci].x); v[6 * ci + 1] = lo(fi[ci].y); v[6 * ci + 2] = lo(fi[ci].z);
+            v[6 * ci + 3] = hi(fi[ci].x); v[6 * ci + 4] = hi(fi[ci].y); v[6 * ci + 5] = hi(fi[ci].z);
         }
+        const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+        float a[24], b[12], c[6];
+#pragma unroll
+        for (int k = 0; k < 24; k++) {
+            const float send = b4 ? v[k] : v[k + 24];
+            a[k] = (b4 ? v[k + 24] : v[k]) + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            const float send = b3 ? a[k] : a[k + 12];
+            b[k] = (b3 ? a[k + 12] : a[k]) + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const float send = b2 ? b[k] : b[k + 6];
+            c[k] = (b2 ? b[k + 6] : b[k]) + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        if (tj < sd.nci) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int islot = ibase + tj * nbl::kClusterSize + ti + 4 * h;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const float f = c[3 * h + d];
+                    if (f != 0.f) atomic_add_fixed(f1acc + (size_t)d * plane + islot, __float2ll_rn(f * kFix));
+                }
+            }
+        }
+    }
+
+    float en1 = lo(en) + hi(en);
+    if (EXACT && fixmask) {
+        float en_fix = 0.f;   // separate variables: their address is taken by the call
+        int cnt_fix = 0;
+        while (fixmask) {
+            const int k = __ffs(fixmask) - 1;
+            fixmask &= fixmask - 1u;
+            const uint32_t fx = __shfl_sync(0xffffffffu, my_ent.x, k);
+            const uint32_t fy = __shfl_sync(0xffffffffu, my_ent.y, k);
+            const int js = (int)(fx & 0x3ffffffu) * nbl::kJGroup + tj;
+            float4 xj = V.posq[js];
+            if (PERIODIC) {
+                const float4 sh = s_shift[fx >> 26];
+                xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
+            }
+            fix_band_pairs(T, V, pos_all, f1acc, s_ip[warp], ibase, js, xj, V.par[js], fy & 0xffu,
+                           fy >> 8, lane, &en_fix, &cnt_fix);
+        }
+        en1 += en_fix;
+        cnt += cnt_fix;
     }
 
     // energy / count partials of this unit (fixed-order warp tree)
-    double de = (double)en;
-    long long dc = cnt;
+    double de = (double)en1;
+    int dc = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         de += __shfl_down_sync(0xffffffffu, de, o);
@@ -245,6 +406,65 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
     if (lane == 0) {
         epart[unit] = de;
         cpart[unit] = dc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Debug / parity pass: records the (i<j) System indices of every pair the pair kernel counts as
+// in-cutoff for one replica -- the same FP32 r^2, the same band rule, the same FP64 re-test.
+// Slow by design (one atomic per pair); never on the product path.
+// ---------------------------------------------------------------------------------------------
+template <bool PERIODIC>
+__global__ void __launch_bounds__(kWarps * 32)
+pair_emit_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
+                 const double* __restrict__ pos_all, int exact, int* emit_counter, int* emit_pairs,
+                 int emit_cap, int emit_replica) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * kWarps + warp;
+    if (unit >= V.nunits) return;
+    const Unit u = V.units[unit];
+    const nbl::SciDesc sd = V.sci[u.sci];
+    if (sd.replica != emit_replica) return;
+    const int ibase = sd.c0 * nbl::kClusterSize;
+    const int ti = lane & 3, tj = lane >> 2;
+    for (int e = u.begin; e < u.end; e++) {
+        const uint2 ent = V.entries[e];
+        const uint32_t code = ent.x >> 26, imask = ent.y & 0xffu, midx = ent.y >> 8;
+        const int jslot = (int)(ent.x & 0x3ffffffu) * nbl::kJGroup + tj;
+        float4 xj = V.posq[jslot];
+        if (PERIODIC) {
+            // same values and the same single rounding as the s_shift table of the pair kernel
+            xj.x += (float)nbl::shift_x(code) * T.boxf[0];
+            xj.y += (float)nbl::shift_y(code) * T.boxf[1];
+            xj.z += (float)nbl::shift_z(code) * T.boxf[2];
+        }
+        const int aj = V.atom[jslot];
+        for (int ci = 0; ci < sd.nci; ci++) {
+            if (!((imask >> ci) & 1u)) continue;
+            for (int h = 0; h < 2; h++) {
+                const uint32_t w = midx ? V.masks[(size_t)midx * nbl::kMaskWords + 2 * ci + h] : 0xffffffffu;
+                if (!((w >> lane) & 1u)) continue;
+                const int islot = ibase + ci * nbl::kClusterSize + ti + 4 * h;
+                const int ai = V.atom[islot];
+                if (ai < 0 || aj < 0) continue;
+                const float4 xi = V.posq[islot];
+                float dx, dy, dz;
+                const float r2 = pair_r2(xi.x, xi.y, xi.z, xj, dx, dy, dz);
+                const float t = r2 - T.rc2f;
+                bool in = t <= 0.f;
+                if (exact && fabsf(t) < T.band) {
+                    const int r = ai / T.n;
+                    in = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
+                }
+                if (!in) continue;
+                const int a = ai % T.n, b = aj % T.n;
+                const int slot = atomicAdd(emit_counter, 1);
+                if (slot < emit_cap) {
+                    emit_pairs[2 * slot] = a < b ? a : b;
+                    emit_pairs[2 * slot + 1] = a < b ? b : a;
+                }
+            }
+        }
     }
 }
 
@@ -282,27 +502,31 @@ refresh_kernel(Topology T, nbl::Grid G, int nslot, const double* __restrict__ po
 
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
-                         int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
                          cudaStream_t s) {
     if (V.nunits <= 0) return;
     const int grid = (V.nunits + kWarps - 1) / kWarps;
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
-#define SDM_LAUNCH(P, X, E, TT)                                                                  \
-    pair_cluster_kernel<P, X, E><<<grid, kWarps * 32, 0, s>>>(TT, V, pos_all, f1acc, epart, cpart, \
-                                                             exact, emit_counter, emit_pairs,     \
-                                                             emit_cap, emit_replica)
-    if (emit_pairs) {
-        // debug pass: every in-range pair takes the out-of-line path, which also records it
-        if (periodic) SDM_LAUNCH(true, true, true, T);
-        else SDM_LAUNCH(false, true, true, T);
-    } else if (exact) {
-        if (periodic) SDM_LAUNCH(true, true, false, T);
-        else SDM_LAUNCH(false, true, false, T);
+#define SDM_LAUNCH(P, X) \
+    pair_cluster_kernel<P, X><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart)
+    if (exact) {
+        if (periodic) SDM_LAUNCH(true, true);
+        else SDM_LAUNCH(false, true);
     } else {
-        if (periodic) SDM_LAUNCH(true, false, false, T);
-        else SDM_LAUNCH(false, false, false, T);
+        if (periodic) SDM_LAUNCH(true, false);
+        else SDM_LAUNCH(false, false);
     }
 #undef SDM_LAUNCH
+}
+
+void launch_pair_emit(const Topology& T, const PairListView& V, const double* pos_all, int exact,
+                      int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
+                      cudaStream_t s) {
+    if (V.nunits <= 0) return;
+    const int grid = (V.nunits + kWarps - 1) / kWarps;
+    if (T.method == SDM_CUTOFF_PERIODIC)
+        pair_emit_kernel<true><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
+    else
+        pair_emit_kernel<false><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
 }
 
 void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,

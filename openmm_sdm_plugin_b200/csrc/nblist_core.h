@@ -10,13 +10,15 @@
 //     g = r*ncell + cell.
 //   * atoms are sorted by (global cell, 9-bit Morton code of the position inside the cell) and
 //     every cell is padded to a multiple of 8 slots with dummy atoms, so a cluster (8 slots)
-//     or a j-group (4 slots) never straddles a cell.
-//   * an i-supercluster (sci) is a run of <= 8 clusters of one cell; its list holds j-group
-//     entries {j4 | shift<<26, imask | mask_index<<8}; imask bit ci says cluster ci of the sci
-//     interacts with the j-group.  Every unordered cluster pair is owned by exactly one side
-//     (checkerboard rule) and the diagonal uses a triangle mask, so each atom pair is
-//     evaluated once.
-//   * exclusion masks: 8 words per masked entry, bit (tj*8+ti) of word ci.
+//     never straddles a cell.
+//   * an i-supercluster (sci) is a run of <= 8 clusters of one cell; its list holds j-cluster
+//     entries {cj | shift<<26, imask | mask_index<<8}; imask bit ci says cluster ci of the sci
+//     interacts with j-cluster cj (an 8 x 8 "tile").  Every unordered cluster pair is owned by
+//     exactly one side (the lower cluster index) and the diagonal uses a triangle mask, so each
+//     atom pair is evaluated once.
+//   * exclusion masks: 16 words per masked entry; the pair kernel's lane (tj, ti) = (lane>>2,
+//     lane&3) evaluates i-atoms ti and ti+4 of a cluster against j-atom tj, so word 2*ci+h holds
+//     the pairs of i-atoms 4h..4h+3: bit (ja*4 + (ia&3)) == bit `lane`.
 #pragma once
 
 #include <stdint.h>
@@ -32,8 +34,9 @@ namespace sdm {
 namespace nbl {
 
 constexpr int kClusterSize = 8;      // atoms per i-cluster
-constexpr int kJGroup = 4;           // atoms per j-group (half a cluster)
+constexpr int kJGroup = 8;           // atoms per j-group (a whole cluster)
 constexpr int kMaxCi = 8;            // clusters per supercluster
+constexpr int kMaskWords = 2 * kMaxCi;  // words per exclusion-mask set
 constexpr int kSubBits = 9;          // Morton bits of the in-cell position in the sort key
 constexpr int kMaxSpan = 6;          // search stencil is at most kMaxSpan cells per dimension
 constexpr float kFar = 1.0e6f;       // coordinate of dummy (padding) atoms
@@ -88,14 +91,11 @@ SDM_HD float box_dist2(const BBox& a, const BBox& b, float sx, float sy, float s
     return d2;
 }
 
-// Which side of an unordered cluster pair (A != B) carries it in its list: true when the cluster
-// playing the i role is A.  Symmetric in (A,B), balanced.
-SDM_HD bool owner_is_i(int A, int B) {
-    int lo = A < B ? A : B;
-    int hi = A < B ? B : A;
-    bool i_is_lo = ((lo ^ hi) & 1) != 0;
-    return i_is_lo ? (A == lo) : (A == hi);
-}
+// Which side of an unordered cluster pair (A != B) carries it in its list: the cluster with the
+// lower index plays the i role.  (A parity checkerboard would balance list lengths, but it makes
+// neighbouring i-clusters of a supercluster alternate, halving the density of the imasks and with
+// it the reuse of every j load; list lengths are balanced by the unit chunking instead.)
+SDM_HD bool owner_is_i(int A, int B) { return A < B; }
 
 SDM_HD uint32_t shift_code(int sx, int sy, int sz) {  // each in {-1,0,1}
     return (uint32_t)((sx + 1) | ((sy + 1) << 2) | ((sz + 1) << 4));
@@ -174,7 +174,6 @@ struct SearchView {
     const SciDesc* sci;        // [nsci]
     const BBox* sci_box;       // [nsci]
     const BBox* cl_box;        // [ncluster]  8-slot cluster boxes
-    const BBox* j4_box;        // [ncluster*2]
     const int* cell_slot;      // [R*ncell + 1] first slot of every global cell (padded layout)
     const float* posq4;        // [nslot][4] sorted positions: exact (atom-level) pruning of imask
 };
@@ -198,11 +197,11 @@ SDM_HD void search_range(const Grid& G, const BBox& b, int cmin[3], int cmax[3])
     }
 }
 
-// Is any atom of cluster A within rlist of any atom of j-group j4 (shifted)?  Dummies never are.
-SDM_HD bool any_pair_within(const float* posq4, int A, int j4, float sx, float sy, float sz,
+// Is any atom of cluster A within rlist of any atom of cluster B (shifted)?  Dummies never are.
+SDM_HD bool any_pair_within(const float* posq4, int A, int B, float sx, float sy, float sz,
                             float rlist2) {
     for (int tj = 0; tj < kJGroup; tj++) {
-        const float* pj = posq4 + 4 * (size_t)(j4 * kJGroup + tj);
+        const float* pj = posq4 + 4 * (size_t)(B * kJGroup + tj);
         if (pj[0] >= 0.5f * kFar) continue;
         const float xj = pj[0] + sx, yj = pj[1] + sy, zj = pj[2] + sz;
         for (int ti = 0; ti < kClusterSize; ti++) {
@@ -215,9 +214,9 @@ SDM_HD bool any_pair_within(const float* posq4, int A, int j4, float sx, float s
     return false;
 }
 
-// One search item = (sci, stencil offset).  Visits the j-groups of the addressed cell and calls
-// emit(j4, shift_code, imask, diag) for every group that interacts with at least one cluster of
-// the sci under the ownership rule.  Returns the number of entries.
+// One search item = (sci, stencil offset).  Visits the clusters of the addressed cell and calls
+// emit(k, cj | shift<<26, imask, diag) for every j-cluster that interacts with at least one
+// cluster of the sci under the ownership rule.  Returns the number of entries.
 template <class Emit>
 SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
     const Grid& G = V.G;
@@ -246,11 +245,10 @@ SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
     const int gcell = sd.replica * G.ncell + (w[2] * G.nc[1] + w[1]) * G.nc[0] + w[0];
     const int s0 = V.cell_slot[gcell], s1 = V.cell_slot[gcell + 1];
     int count = 0;
-    for (int j4 = s0 / kJGroup; j4 < s1 / kJGroup; j4++) {
-        const BBox jb = V.j4_box[j4];
+    for (int B = s0 / kJGroup; B < s1 / kJGroup; B++) {
+        const BBox jb = V.cl_box[B];
         if (box_empty(jb)) continue;
         if (box_dist2(sb, jb, sx, sy, sz) >= G.rlist2) continue;
-        const int B = j4 >> 1;
         uint32_t imask = 0;
         bool diag = false;
         for (int ci = 0; ci < sd.nci; ci++) {
@@ -265,10 +263,10 @@ SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
             }
             if (!own) continue;
             if (box_dist2(V.cl_box[A], jb, sx, sy, sz) >= G.rlist2) continue;
-            if (any_pair_within(V.posq4, A, j4, sx, sy, sz, G.rlist2)) imask |= 1u << ci;
+            if (any_pair_within(V.posq4, A, B, sx, sy, sz, G.rlist2)) imask |= 1u << ci;
         }
         if (imask) {
-            emit(count, (uint32_t)j4 | (code << 26), imask, diag && ((imask >> (B - sd.c0)) & 1u));
+            emit(count, (uint32_t)B | (code << 26), imask, diag && ((imask >> (B - sd.c0)) & 1u));
             count++;
         }
     }
@@ -289,12 +287,19 @@ SDM_HD void exclusion_roles(int sa, int sb, int* si, int* sj) {
     }
 }
 
-// Triangle mask word of cluster-against-itself for the j-group half h (0/1).
+// Mask word and bit of the atom pair (i-slot si, j-slot sj) inside the mask set of its entry.
+SDM_HD int mask_word(int ci, int si) { return 2 * ci + ((si % kClusterSize) >> 2); }
+SDM_HD uint32_t mask_bit(int si, int sj) {
+    return 1u << ((sj % kJGroup) * 4 + ((si % kClusterSize) & 3));
+}
+
+// Triangle mask word of cluster-against-itself for the i-atom half h (i-atoms 4h..4h+3): keeps
+// the pairs with j index > i index.
 SDM_HD uint32_t triangle_mask(int h) {
     uint32_t m = 0;
     for (int tj = 0; tj < kJGroup; tj++)
-        for (int ti = 0; ti < kClusterSize; ti++)
-            if (h * kJGroup + tj > ti) m |= 1u << (tj * kClusterSize + ti);
+        for (int ti = 0; ti < 4; ti++)
+            if (tj > 4 * h + ti) m |= 1u << (tj * 4 + ti);
     return m;
 }
 

@@ -37,7 +37,7 @@ struct PairList {
     float4 *posq = nullptr, *posq_build = nullptr;
     float2* par = nullptr;
     int *atom = nullptr, *img = nullptr, *slot_of = nullptr;
-    BBox *cl_box = nullptr, *j4_box = nullptr, *sci_box = nullptr;
+    BBox *cl_box = nullptr, *sci_box = nullptr;
     SciDesc* sci = nullptr;
     int* cl_sci = nullptr;
     int *item_count = nullptr, *item_off = nullptr;
@@ -171,14 +171,11 @@ __global__ void fill_dummies_kernel(int ncells, const int* __restrict__ cell_cou
     }
 }
 
-__global__ void bbox_kernel(int ncl, const float4* __restrict__ posq, BBox* cl_box, BBox* j4_box) {
+__global__ void bbox_kernel(int ncl, const float4* __restrict__ posq, BBox* cl_box) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncl) return;
-    const float* p = reinterpret_cast<const float*>(posq);
-    const BBox a = nbl::group_bbox(p, c * 8, 4), b = nbl::group_bbox(p, c * 8 + 4, 4);
-    j4_box[2 * c] = a;
-    j4_box[2 * c + 1] = b;
-    cl_box[c] = nbl::box_union(a, b);
+    cl_box[c] = nbl::group_bbox(reinterpret_cast<const float*>(posq), c * nbl::kClusterSize,
+                                nbl::kClusterSize);
 }
 
 __global__ void sci_kernel(Grid G, int ncells, const int* __restrict__ cell_slot,
@@ -248,17 +245,17 @@ __global__ void exclusion_kernel(Grid G, int n_excl, const int* __restrict__ exc
     nbl::exclusion_roles(sa, sb, &si, &sj);
     const int isci = cl_sci[si / nbl::kClusterSize];
     const int ci = si / nbl::kClusterSize - sci[isci].c0;
-    const uint32_t j4 = (uint32_t)(sj / nbl::kJGroup);
-    const uint32_t bit = 1u << ((sj % nbl::kJGroup) * nbl::kClusterSize + (si % nbl::kClusterSize));
+    const uint32_t cj = (uint32_t)(sj / nbl::kJGroup);
+    const uint32_t bit = nbl::mask_bit(si, sj);
     const int e0 = item_off[isci * noff], e1 = item_off[(isci + 1) * noff];
     for (int e = e0; e < e1; e++) {
         const uint2 ent = entries[e];
-        if ((ent.x & 0x3ffffffu) != j4) continue;
+        if ((ent.x & 0x3ffffffu) != cj) continue;
         if (pass == 0) {
             entry_flag[e] = 1;
         } else {
             const uint32_t midx = ent.y >> 8;
-            atomicAnd(masks + (size_t)midx * nbl::kMaxCi + ci, ~bit);
+            atomicAnd(masks + (size_t)midx * nbl::kMaskWords + nbl::mask_word(ci, si), ~bit);
         }
     }
 }
@@ -274,13 +271,13 @@ __global__ void mask_init_kernel(int nentries, const int* __restrict__ entry_fla
     uint2 ent = entries[e];
     ent.y = (ent.y & 0xffu) | (midx << 8);
     entries[e] = ent;
-    const int j4 = (int)(ent.x & 0x3ffffffu);
+    const int cj = (int)(ent.x & 0x3ffffffu);
     const uint32_t code = ent.x >> 26;
     const SciDesc sd = sci[entry_sci[e]];
-    for (int ci = 0; ci < nbl::kMaxCi; ci++) {
+    for (int w = 0; w < nbl::kMaskWords; w++) {
         uint32_t m = 0xffffffffu;
-        if (code == nbl::kShiftZero && (j4 >> 1) == sd.c0 + ci) m = nbl::triangle_mask(j4 & 1);
-        masks[(size_t)midx * nbl::kMaxCi + ci] = m;
+        if (code == nbl::kShiftZero && cj == sd.c0 + (w >> 1)) m = nbl::triangle_mask(w & 1);
+        masks[(size_t)midx * nbl::kMaskWords + w] = m;
     }
 }
 
@@ -441,7 +438,7 @@ static int build_list(sdm_ctx* c) {
                                                    pl->atom, pl->img, pl->slot_of);
     fill_dummies_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_count, pl->cell_slot, pl->posq,
                                                       pl->par, pl->atom, pl->img);
-    bbox_kernel<<<blocks(pl->ncl), 256, 0, s>>>(pl->ncl, pl->posq, pl->cl_box, pl->j4_box);
+    bbox_kernel<<<blocks(pl->ncl), 256, 0, s>>>(pl->ncl, pl->posq, pl->cl_box);
     sci_kernel<<<blocks(ncells), 256, 0, s>>>(G, ncells, pl->cell_slot, pl->cell_sci, pl->cl_box, pl->sci,
                                              pl->sci_box, pl->cl_sci);
     c->launches += 9;
@@ -451,7 +448,6 @@ static int build_list(sdm_ctx* c) {
     V.sci = pl->sci;
     V.sci_box = pl->sci_box;
     V.cl_box = pl->cl_box;
-    V.j4_box = pl->j4_box;
     V.cell_slot = pl->cell_slot;
     V.posq4 = reinterpret_cast<const float*>(pl->posq);
     const long long nitems = (long long)pl->nsci * noff;
@@ -510,7 +506,7 @@ static int build_list(sdm_ctx* c) {
     pl->nunits = pl->h_counts[4];
     if ((size_t)pl->nmasks + 1 > pl->masks_cap) {
         pl->masks_cap = (size_t)(pl->nmasks * 1.25) + 256;
-        if (int rc = pl_realloc(pl, &pl->masks, pl->masks_cap * nbl::kMaxCi)) return rc;
+        if (int rc = pl_realloc(pl, &pl->masks, pl->masks_cap * nbl::kMaskWords)) return rc;
     }
     if ((size_t)pl->nunits > pl->units_cap) {
         pl->units_cap = (size_t)(pl->nunits * 1.25) + 256;
@@ -529,7 +525,7 @@ static int build_list(sdm_ctx* c) {
         }
         entry_sci_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, noff, pl->item_off, entry_sci);
         // mask set 0 = all ones
-        PL_CUDA(cudaMemsetAsync(pl->masks, 0xff, sizeof(uint32_t) * nbl::kMaxCi, s));
+        PL_CUDA(cudaMemsetAsync(pl->masks, 0xff, sizeof(uint32_t) * nbl::kMaskWords, s));
         mask_init_kernel<<<blocks(pl->nentries), 256, 0, s>>>(pl->nentries, pl->entry_flag, pl->entry_midx,
                                                              pl->item_off, pl->entries, pl->masks, pl->sci, entry_sci);
     }
@@ -606,7 +602,6 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->img, pl->nslot_cap));
     A(pl_alloc(pl, &pl->slot_of, total));
     A(pl_alloc(pl, &pl->cl_box, pl->ncl_cap));
-    A(pl_alloc(pl, &pl->j4_box, 2 * (size_t)pl->ncl_cap));
     A(pl_alloc(pl, &pl->sci_box, pl->nsci_cap));
     A(pl_alloc(pl, &pl->sci, pl->nsci_cap));
     A(pl_alloc(pl, &pl->cl_sci, pl->ncl_cap));
@@ -623,7 +618,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->entry_flag, pl->entries_cap + 1));
     A(pl_alloc(pl, &pl->entry_midx, pl->entries_cap + 1));
     pl->masks_cap = (size_t)total / 2 + 256;
-    A(pl_alloc(pl, &pl->masks, pl->masks_cap * nbl::kMaxCi));
+    A(pl_alloc(pl, &pl->masks, pl->masks_cap * nbl::kMaskWords));
     pl->units_cap = pl->entries_cap / 8 + 256;
     A(pl_alloc(pl, &pl->units, pl->units_cap));
     A(pl_alloc(pl, &pl->epart, pl->units_cap));
@@ -706,8 +701,11 @@ int sdm_ctx_pairlist_eval(sdm_ctx* c) {
     c->B.epart = pl->epart;
     c->B.cpart = pl->cpart;
     c->B.part_off = pl->part_off;
+    // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
+    if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
     launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart,
-                        c->opt.exact_cutoff, nullptr, nullptr, 0, -1, s);
+                        c->opt.exact_cutoff, s);
+    if (c->timing) PL_CUDA(cudaEventRecord(c->ev[2], s));
     c->launches++;
     PL_CUDA(cudaGetLastError());
     return SDM_OK;
@@ -716,13 +714,9 @@ int sdm_ctx_pairlist_eval(sdm_ctx* c) {
 int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap) {
     PairList* pl = c->pl;
     if (!pl || !c->list_valid) return sdm_fail(SDM_ERR_INVALID, "no pair list built yet: call sdm_eval first");
-    // scratch accumulators so that the debug pass does not disturb the real ones
-    long long* scratch = nullptr;
-    PL_CUDA(cudaMalloc((void**)&scratch, sizeof(long long) * 3 * (size_t)pl->nslot_cap));
-    launch_pair_cluster(c->T, make_view(c), c->d_pos, scratch, pl->epart, pl->cpart, c->opt.exact_cutoff,
-                        d_counter, d_pairs, cap, replica, c->stream);
+    launch_pair_emit(c->T, make_view(c), c->d_pos, c->opt.exact_cutoff, d_counter, d_pairs, cap, replica,
+                     c->stream);
     PL_CUDA(cudaStreamSynchronize(c->stream));
-    PL_CUDA(cudaFree(scratch));
     return SDM_OK;
 }
 

@@ -21,8 +21,8 @@ struct PairListView {
     const float2* par;           // [nslot] (sigma/2, 2*sqrt(eps)); (0,0) for dummies
     const int* atom;             // [nslot] replica*n + atom, or -1 for a dummy slot
     const nbl::SciDesc* sci;     // [nsci]
-    const uint2* entries;        // {j4 | shift<<26, imask | mask_index<<8}
-    const uint32_t* masks;       // [(nmasks+1)*8]; set 0 = all ones
+    const uint2* entries;        // {cj | shift<<26, imask | mask_index<<8}
+    const uint32_t* masks;       // [(nmasks+1)*16]; set 0 = all ones
     const Unit* units;           // [nunits]
     int nunits;
     int nslot_cap;               // accumulator plane stride
@@ -30,8 +30,11 @@ struct PairListView {
 
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
-                         int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
                          cudaStream_t s);
+// Debug / parity: dump the in-cutoff pairs of one replica exactly as the pair kernel decides them.
+void launch_pair_emit(const Topology& T, const PairListView& V, const double* pos_all, int exact,
+                      int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
+                      cudaStream_t s);
 
 // Per-eval refresh of the sorted positions from the current double positions (same periodic
 // image as at build time) + staleness check against the build-time positions.

@@ -154,12 +154,8 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
         slot_of[ga] = slot;
     }
     // boxes
-    std::vector<BBox> cl_box(ncl), j4_box(2 * (size_t)ncl), sci_box(nsci);
-    for (int c = 0; c < ncl; c++) {
-        j4_box[2 * c] = group_bbox(posq.data(), c * 8, 4);
-        j4_box[2 * c + 1] = group_bbox(posq.data(), c * 8 + 4, 4);
-        cl_box[c] = box_union(j4_box[2 * c], j4_box[2 * c + 1]);
-    }
+    std::vector<BBox> cl_box(ncl), sci_box(nsci);
+    for (int c = 0; c < ncl; c++) cl_box[c] = group_bbox(posq.data(), c * kClusterSize, kClusterSize);
     std::vector<SciDesc> sci(nsci);
     std::vector<int> cl_sci(ncl, -1);
     for (int c = 0; c < ncells; c++) {
@@ -183,7 +179,6 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     V.sci = sci.data();
     V.sci_box = sci_box.data();
     V.cl_box = cl_box.data();
-    V.j4_box = j4_box.data();
     V.cell_slot = cell_slot.data();
     V.posq4 = posq.data();
     const long long nitems = (long long)nsci * noff;
@@ -211,12 +206,12 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
                 exclusion_roles(sa, sb, &si, &sj);
                 int isci = cl_sci[si / kClusterSize];
                 int ci = si / kClusterSize - sci[isci].c0;
-                uint32_t j4 = (uint32_t)(sj / kJGroup);
-                uint32_t bit = 1u << ((sj % kJGroup) * kClusterSize + (si % kClusterSize));
+                uint32_t cj = (uint32_t)(sj / kJGroup);
+                uint32_t bit = mask_bit(si, sj);
                 for (int e = item_off[(long long)isci * noff]; e < item_off[(long long)(isci + 1) * noff]; e++) {
-                    if ((ex[e] & 0x3ffffffu) != j4) continue;
+                    if ((ex[e] & 0x3ffffffu) != cj) continue;
                     if (pass == 0) flag[e] = 1;
-                    else (*masks)[(size_t)(ey[e] >> 8) * kMaxCi + ci] &= ~bit;
+                    else (*masks)[(size_t)(ey[e] >> 8) * kMaskWords + mask_word(ci, si)] &= ~bit;
                 }
             }
     };
@@ -224,18 +219,18 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     int nmasks = 0;
     std::vector<int> midx(nentries, 0);
     for (int e = 0; e < nentries; e++) if (flag[e]) midx[e] = nmasks++;
-    std::vector<uint32_t> masks((size_t)(nmasks + 1) * kMaxCi, 0xffffffffu);
+    std::vector<uint32_t> masks((size_t)(nmasks + 1) * kMaskWords, 0xffffffffu);
     for (int e = 0; e < nentries; e++) {
         if (!flag[e]) continue;
         uint32_t m = (uint32_t)midx[e] + 1u;
         ey[e] = (ey[e] & 0xffu) | (m << 8);
-        int j4 = (int)(ex[e] & 0x3ffffffu);
+        int cj = (int)(ex[e] & 0x3ffffffu);
         uint32_t code = ex[e] >> 26;
         const SciDesc sd = sci[esci[e]];
-        for (int ci = 0; ci < kMaxCi; ci++) {
-            uint32_t w = 0xffffffffu;
-            if (code == kShiftZero && (j4 >> 1) == sd.c0 + ci) w = triangle_mask(j4 & 1);
-            masks[(size_t)m * kMaxCi + ci] = w;
+        for (int w = 0; w < kMaskWords; w++) {
+            uint32_t v = 0xffffffffu;
+            if (code == kShiftZero && cj == sd.c0 + (w >> 1)) v = triangle_mask(w & 1);
+            masks[(size_t)m * kMaskWords + w] = v;
         }
     }
     for_excl(1, &masks);
@@ -245,73 +240,37 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
         nunits += (len + chunk - 1) / chunk;
     }
 
-    if (getenv("NBL_TRACE")) {
-        int ta, tb;
-        sscanf(getenv("NBL_TRACE"), "%d,%d", &ta, &tb);
-        int sa = slot_of[ta], sb = slot_of[tb], si, sj;
-        exclusion_roles(sa, sb, &si, &sj);
-        int isci = cl_sci[si / 8];
-        printf("trace %d %d slots %d %d roles i=%d j=%d clusters %d %d isci %d c0 %d nci %d j4 %d\n", ta, tb, sa, sb, si, sj, si / 8, sj / 8, isci, sci[isci].c0, sci[isci].nci, sj / 4);
-        const BBox& sbx = sci_box[isci];
-        printf(" sci box lo %g %g %g hi %g %g %g\n", sbx.lo[0], sbx.lo[1], sbx.lo[2], sbx.hi[0], sbx.hi[1], sbx.hi[2]);
-        const BBox& jb = j4_box[sj / 4];
-        printf(" j4 box lo %g %g %g hi %g %g %g\n", jb.lo[0], jb.lo[1], jb.lo[2], jb.hi[0], jb.hi[1], jb.hi[2]);
-        int cmin[3], cmax[3];
-        search_range(G, sbx, cmin, cmax);
-        printf(" range %d..%d %d..%d %d..%d nc %d %d %d span %d\n", cmin[0], cmax[0], cmin[1], cmax[1], cmin[2], cmax[2], G.nc[0], G.nc[1], G.nc[2], G.span);
-        for (int e = item_off[(long long)isci * noff]; e < item_off[(long long)(isci + 1) * noff]; e++)
-            if ((int)(ex[e] & 0x3ffffffu) == sj / 4) {
-                printf(" entry %d code %u imask %x m %u flag %d midx %d\n", e, ex[e] >> 26, ey[e] & 0xff, ey[e] >> 8, flag[e], midx[e]);
-                for (int ci = 0; ci < 8; ci++) printf("   mask[%d]=%08x\n", ci, masks[(size_t)(ey[e] >> 8) * 8 + ci]);
-                for (int ti = 0; ti < 8; ti++) printf("   i slot %d atom %d\n", (si / 8) * 8 + ti, atom[(si / 8) * 8 + ti]);
-                for (int tj = 0; tj < 4; tj++) printf("   j slot %d atom %d\n", (sj / 4) * 4 + tj, atom[(sj / 4) * 4 + tj]);
-            }
-    }
-    // traversal exactly like the pair kernel
+    // traversal exactly like the pair kernel: lane (tj, ti) = (lane>>2, lane&3) evaluates i-atoms
+    // ti and ti+4 (halves h = 0, 1) of cluster ci against j-atom tj of the entry's j-cluster
     std::vector<std::pair<int, int>> found;
     const double rc2 = rc * rc;
-    double lane_pairs = 0, pruned_pairs = 0;
+    double lane_pairs = 0;
     for (int s = 0; s < nsci; s++) {
         const SciDesc sd = sci[s];
         for (int e = item_off[(long long)s * noff]; e < item_off[(long long)(s + 1) * noff]; e++) {
-            const int j4 = (int)(ex[e] & 0x3ffffffu);
+            const int cj = (int)(ex[e] & 0x3ffffffu);
             const uint32_t imask = ey[e] & 0xffu, m = ey[e] >> 8;
+            const uint32_t code = ex[e] >> 26;
+            const int sh[3] = {shift_x(code), shift_y(code), shift_z(code)};
             for (int ci = 0; ci < kMaxCi; ci++) {
                 if (!((imask >> ci) & 1u)) continue;
-                lane_pairs += 32;
-                if (stats && stats[9] > 0) {  // exact-prune statistic: any atom pair within stats[9]
-                    const uint32_t code2 = ex[e] >> 26;
-                    const int sh2[3] = {shift_x(code2), shift_y(code2), shift_z(code2)};
-                    bool any = false;
-                    for (int lane = 0; lane < 32 && !any; lane++) {
-                        const int islot = (sd.c0 + ci) * kClusterSize + (lane & 7), jslot = j4 * kJGroup + (lane >> 3);
-                        if (atom[islot] < 0 || atom[jslot] < 0) continue;
-                        double r2 = 0;
-                        for (int k = 0; k < 3; k++) {
-                            double dd = posw[3 * (size_t)islot + k] - (posw[3 * (size_t)jslot + k] + (periodic ? sh2[k] * box[k] : 0.0));
-                            r2 += dd * dd;
-                        }
-                        any = r2 < stats[9] * stats[9];
-                    }
-                    if (any) pruned_pairs += 32;
-                }
+                lane_pairs += 64;
                 if (sd.replica != replica) continue;
-                for (int lane = 0; lane < 32; lane++) {
-                    if (m && !((masks[(size_t)m * kMaxCi + ci] >> lane) & 1u)) continue;
-                    const int ti = lane & 7, tj = lane >> 3;
-                    const int islot = (sd.c0 + ci) * kClusterSize + ti, jslot = j4 * kJGroup + tj;
-                    const int ai = atom[islot], aj = atom[jslot];
-                    if (ai < 0 || aj < 0) continue;
-                    // the image this entry addresses (what the kernel evaluates), in double
-                    const uint32_t code = ex[e] >> 26;
-                    const int sh[3] = {shift_x(code), shift_y(code), shift_z(code)};
-                    double d[3];
-                    for (int k = 0; k < 3; k++)
-                        d[k] = posw[3 * (size_t)islot + k] - (posw[3 * (size_t)jslot + k] + (periodic ? sh[k] * box[k] : 0.0));
-                    if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] > rc2) continue;
-                    int a = ai % n, b = aj % n;
-                    found.emplace_back(std::min(a, b), std::max(a, b));
-                }
+                for (int h = 0; h < 2; h++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        if (m && !((masks[(size_t)m * kMaskWords + 2 * ci + h] >> lane) & 1u)) continue;
+                        const int ti = (lane & 3) + 4 * h, tj = lane >> 2;
+                        const int islot = (sd.c0 + ci) * kClusterSize + ti, jslot = cj * kJGroup + tj;
+                        const int ai = atom[islot], aj = atom[jslot];
+                        if (ai < 0 || aj < 0) continue;
+                        // the image this entry addresses (what the kernel evaluates), in double
+                        double d[3];
+                        for (int k = 0; k < 3; k++)
+                            d[k] = posw[3 * (size_t)islot + k] - (posw[3 * (size_t)jslot + k] + (periodic ? sh[k] * box[k] : 0.0));
+                        if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] > rc2) continue;
+                        int a = ai % n, b = aj % n;
+                        found.emplace_back(std::min(a, b), std::max(a, b));
+                    }
             }
         }
     }
@@ -321,7 +280,6 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     if (stats) {
         stats[0] = nslot; stats[1] = nsci; stats[2] = nentries; stats[3] = nmasks;
         stats[4] = nunits; stats[5] = lane_pairs; stats[6] = G.ncell; stats[7] = G.span;
-        stats[8] = pruned_pairs;
     }
     return (long long)found.size();
 }
