@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdmb200.so")
+# SDMB200_LIB: development override used to A/B kernel build variants on the GPU box
+LIB_PATH = os.environ.get("SDMB200_LIB") or os.path.join(_HERE, "libsdmb200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 SDM_OK = 0

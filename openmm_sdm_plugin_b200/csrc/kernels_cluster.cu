@@ -36,7 +36,15 @@
 namespace sdm {
 namespace {
 
-constexpr int kWarps = 4;
+#ifndef SDM_PAIR_WARPS
+#define SDM_PAIR_WARPS 1
+#endif
+#ifndef SDM_PAIR_MINB
+#define SDM_PAIR_MINB 16
+#endif
+// One warp per block: a warp that finishes its unit frees its slot at once (units differ in
+// length), which keeps the achieved occupancy at the register-limited maximum.
+constexpr int kWarps = SDM_PAIR_WARPS;
 constexpr float kFix = 4294967296.0f;  // 2^32
 constexpr int kIRows = nbl::kMaxCi * 4;   // (cluster, ti) rows of staged i-atom pairs per unit
 
@@ -219,7 +227,7 @@ __device__ __forceinline__ void entry_tiles(const uint32_t imask, const uint32_t
 }
 
 template <bool PERIODIC, bool EXACT>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, SDM_PAIR_MINB)
 pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
                     const double* __restrict__ pos_all, long long* __restrict__ f1acc,
                     double* __restrict__ epart, long long* __restrict__ cpart) {
@@ -227,12 +235,10 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
     __shared__ float4 s_shift[64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (PERIODIC) {
-        if (threadIdx.x < 64) {
-            const uint32_t code = threadIdx.x;
-            s_shift[threadIdx.x] = make_float4((float)nbl::shift_x(code) * T.boxf[0],
-                                               (float)nbl::shift_y(code) * T.boxf[1],
-                                               (float)nbl::shift_z(code) * T.boxf[2], 0.f);
-        }
+        for (uint32_t code = threadIdx.x; code < 64; code += kWarps * 32)
+            s_shift[code] = make_float4((float)nbl::shift_x(code) * T.boxf[0],
+                                        (float)nbl::shift_y(code) * T.boxf[1],
+                                        (float)nbl::shift_z(code) * T.boxf[2], 0.f);
         __syncthreads();
     }
     const int unit = blockIdx.x * kWarps + warp;
