@@ -312,6 +312,11 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     c->d_pos = pos;
     c->d_fb = fb;
     TRY(dev_alloc(c, &B.posq, (size_t)R * n));
+    B.scan_posq = B.posq;   // all-pairs path: System order (the cluster path installs its slots)
+    B.scan_atom = nullptr;
+    B.scan_off = nullptr;
+    B.scan_stride = 0;
+    B.scan_max = n;
     TRY(dev_alloc(c, &B.f1acc, (size_t)R * 3 * B.nslot));
     TRY(dev_alloc(c, &B.dF, (size_t)R * 3 * n));
     TRY(dev_alloc(c, &B.F, (size_t)R * 3 * n));

@@ -187,9 +187,16 @@ allpairs_kernel(Topology T, const float4* __restrict__ posq_all, const double* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// Displaced-atom kernels.  All FP64, positions straight from the double buffer, in-cutoff
-// decisions with the contraction-free expression of the oracle.  State 2 = x + d for EVERY atom
-// (ReferenceSDMKernels.cpp:192-199); a pair changes iff the two displacement vectors differ.
+// Displaced-atom kernels.  State 2 = x + d for EVERY atom (ReferenceSDMKernels.cpp:192-199); a
+// pair changes iff the two displacement vectors differ, so u = E2 - E1 and dF = F2 - F1 only need
+// the pairs between a displaced atom and an atom of another displacement group.
+//
+// Both kernels walk a spatially ordered scan list (EvalBuffers::scan_*) with a cheap FP32
+// minimum-image prefilter (conservative: margin >> FP32 rounding) and evaluate the ~2% of
+// survivors in FP64, positions straight from the double buffer, in-cutoff decisions with the
+// contraction-free expression of the oracle.  Warps scan consecutive slots of one cell, so the
+// FP64 branch is taken by whole warps near the displaced atoms and skipped elsewhere.  No
+// atomics: every output element has one owner and a fixed summation order (bit-reproducible).
 //
 // probe kernel: one block per (displaced atom i, replica); walks all atoms k whose displacement
 // differs from i's, evaluates the pair at state 1 and state 2 and reduces
@@ -205,97 +212,200 @@ __device__ __forceinline__ PairGeom geom(const Topology& T, double xi, double yi
     PairGeom g;
     g.dx = xi - xk; g.dy = yi - yk; g.dz = zi - zk;
     if (T.method == SDM_CUTOFF_PERIODIC) {
-        g.dx = min_image_exact(g.dx, T.box[0]);
-        g.dy = min_image_exact(g.dy, T.box[1]);
-        g.dz = min_image_exact(g.dz, T.box[2]);
+        g.dx = min_image_fast(g.dx, T.box[0], T.inv_box[0]);
+        g.dy = min_image_fast(g.dy, T.box[1], T.inv_box[1]);
+        g.dz = min_image_fast(g.dz, T.box[2], T.inv_box[2]);
     }
     g.r2 = norm2_exact(g.dx, g.dy, g.dz);
     return g;
 }
 
-__global__ void __launch_bounds__(128)
-ligand_probe_kernel(Topology T, const double* __restrict__ pos_all, double* __restrict__ dF_all,
-                    double* __restrict__ upart, long long* __restrict__ mcnt) {
-    __shared__ double s_red[32];
-    __shared__ long long s_redl[32];
-    const int m = blockIdx.x, r = blockIdx.y, n = T.n;
-    const int i = T.lig_idx[m];
-    const double* pos = pos_all + (size_t)r * 3 * n;
-    const int gi = T.group[i];
-    const double xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
-    const double xi2 = xi + T.disp[3 * i], yi2 = yi + T.disp[3 * i + 1], zi2 = zi + T.disp[3 * i + 2];
-    const double qi = T.q[i], hsi = T.hsig[i], hei = T.heps[i];
-    const bool cutoff = T.method != SDM_NOCUTOFF;
-
-    double fx = 0, fy = 0, fz = 0, u = 0;
-    long long c1 = 0, c2 = 0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const int gk = T.group[k];
-        if (gk == gi) continue;  // same displacement (includes k == i): pair unchanged
-        const double xk = pos[3 * k], yk = pos[3 * k + 1], zk = pos[3 * k + 2];
-        PairGeom g1 = geom(T, xi, yi, zi, xk, yk, zk);
-        double xk2 = xk, yk2 = yk, zk2 = zk;
-        if (gk != 0) { xk2 += T.disp[3 * k]; yk2 += T.disp[3 * k + 1]; zk2 += T.disp[3 * k + 2]; }
-        PairGeom g2 = geom(T, xi2, yi2, zi2, xk2, yk2, zk2);
-        const bool in1 = !cutoff || g1.r2 <= T.rc2;
-        const bool in2 = !cutoff || g2.r2 <= T.rc2;
-        if (!(in1 || in2)) continue;
-        if (is_excluded(T, i, k)) continue;
-        const double sig = hsi + T.hsig[k], eps = hei * T.heps[k];
-        const double qq = SDM_K_COULOMB * qi * T.q[k];
-        const double w = (gk != 0) ? 0.5 : 1.0;
-        const int wc = (gk != 0) ? 1 : 2;
-        if (in1) {
-            double e;
-            double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-            fx -= fs * g1.dx; fy -= fs * g1.dy; fz -= fs * g1.dz;
-            u -= w * e;
-            c1 += wc;
-        }
-        if (in2) {
-            double e;
-            double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-            fx += fs * g2.dx; fy += fs * g2.dy; fz += fs * g2.dz;
-            u += w * e;
-            c2 += wc;
-        }
+// FP32 minimum-image distance^2 for the prefilter.
+__device__ __forceinline__ float r2_prefilter(const Topology& T, float xi, float yi, float zi,
+                                              const float4 p) {
+    float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
+    if (T.method == SDM_CUTOFF_PERIODIC) {
+        dx -= T.boxf[0] * rintf(dx * T.inv_boxf[0]);
+        dy -= T.boxf[1] * rintf(dy * T.inv_boxf[1]);
+        dz -= T.boxf[2] * rintf(dz * T.inv_boxf[2]);
     }
-    double sx = block_sum(fx, s_red);
-    double sy = block_sum(fy, s_red);
-    double sz = block_sum(fz, s_red);
-    double su = block_sum(u, s_red);
-    long long sc1 = block_sum_ll(c1, s_redl);
-    long long sc2 = block_sum_ll(c2, s_redl);
-    if (threadIdx.x == 0) {
-        double* dF = dF_all + (size_t)r * 3 * n;
-        dF[3 * i] = sx; dF[3 * i + 1] = sy; dF[3 * i + 2] = sz;
-        upart[(size_t)r * T.n_lig + m] = su;
-        mcnt[((size_t)r * T.n_lig + m) * 2] = sc1;
-        mcnt[((size_t)r * T.n_lig + m) * 2 + 1] = sc2;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ void scan_range(const Topology& T, const EvalBuffers& B, int r, int* begin,
+                                           int* end) {
+    if (B.scan_off) {
+        *begin = B.scan_off[(size_t)r * B.scan_stride];
+        *end = B.scan_off[(size_t)(r + 1) * B.scan_stride];
+    } else {
+        *begin = r * T.n;
+        *end = (r + 1) * T.n;
     }
 }
 
-// env kernel: one thread per NON-displaced atom j; loops over the displaced atoms (staged in
-// shared memory) and accumulates dF_j = sum_i f_j(state 2) - f_j(state 1).  Writes every dF_j
-// (zero when nothing is near), so no memset is needed.
+// Accumulators of one displaced atom.
+struct ProbeAcc {
+    double fx, fy, fz, u;
+    long long c1, c2;
+};
+
+struct ProbeAtom {
+    int i, gi;
+    double x1, y1, z1, x2, y2, z2, q, hsig, heps;
+};
+
+// Exact (FP64) dual-state term of the pair (displaced atom P, atom k) added to A.
+__device__ __forceinline__ void probe_pair(const Topology& T, const double* __restrict__ pos,
+                                           const ProbeAtom& P, int k, ProbeAcc& A) {
+    const int gk = T.group[k];
+    if (gk == P.gi) return;  // same displacement (includes k == i): pair unchanged
+    const bool cutoff = T.method != SDM_NOCUTOFF;
+    const double xk = pos[3 * k], yk = pos[3 * k + 1], zk = pos[3 * k + 2];
+    PairGeom g1 = geom(T, P.x1, P.y1, P.z1, xk, yk, zk);
+    double xk2 = xk, yk2 = yk, zk2 = zk;
+    if (gk != 0) { xk2 += T.disp[3 * k]; yk2 += T.disp[3 * k + 1]; zk2 += T.disp[3 * k + 2]; }
+    PairGeom g2 = geom(T, P.x2, P.y2, P.z2, xk2, yk2, zk2);
+    const bool in1 = !cutoff || g1.r2 <= T.rc2;
+    const bool in2 = !cutoff || g2.r2 <= T.rc2;
+    if (!(in1 || in2)) return;
+    if (is_excluded(T, P.i, k)) return;
+    const double sig = P.hsig + T.hsig[k], eps = P.heps * T.heps[k];
+    const double qq = SDM_K_COULOMB * P.q * T.q[k];
+    const double w = (gk != 0) ? 0.5 : 1.0;
+    const int wc = (gk != 0) ? 1 : 2;
+    if (in1) {
+        double e;
+        double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+        A.fx -= fs * g1.dx; A.fy -= fs * g1.dy; A.fz -= fs * g1.dz;
+        A.u -= w * e;
+        A.c1 += wc;
+    }
+    if (in2) {
+        double e;
+        double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+        A.fx += fs * g2.dx; A.fy += fs * g2.dy; A.fz += fs * g2.dz;
+        A.u += w * e;
+        A.c2 += wc;
+    }
+}
+
+constexpr int kProbeThreads = 128;
+
+__global__ void __launch_bounds__(kProbeThreads)
+ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
+    __shared__ double s_red[32];
+    __shared__ long long s_redl[32];
+    __shared__ int s_queue[kProbeThreads / 32][64];
+    const int m = blockIdx.x, r = blockIdx.y, n = T.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* pos = B.pos + (size_t)r * 3 * n;
+    ProbeAtom P;
+    P.i = T.lig_idx[m];
+    P.gi = T.group[P.i];
+    P.x1 = pos[3 * P.i]; P.y1 = pos[3 * P.i + 1]; P.z1 = pos[3 * P.i + 2];
+    P.x2 = P.x1 + T.disp[3 * P.i]; P.y2 = P.y1 + T.disp[3 * P.i + 1]; P.z2 = P.z1 + T.disp[3 * P.i + 2];
+    P.q = T.q[P.i]; P.hsig = T.hsig[P.i]; P.heps = T.heps[P.i];
+    const float fx1 = (float)P.x1, fy1 = (float)P.y1, fz1 = (float)P.z1;
+    const float fx2 = (float)P.x2, fy2 = (float)P.y2, fz2 = (float)P.z2;
+    const bool cutoff = T.method != SDM_NOCUTOFF;
+    const float lim = T.rc2f * 1.0001f + 1.0e-4f;
+    int begin, end;
+    scan_range(T, B, r, &begin, &end);
+    ProbeAcc A{0, 0, 0, 0, 0, 0};
+
+    // (1) resting atoms: FP32 prefilter over the scan list, survivors are queued per warp and
+    // evaluated 32 at a time so that the FP64 code runs with full warps.  Queue order and
+    // lane assignment depend only on the data, never on timing.
+    int* q = s_queue[warp];
+    int qn = 0;
+    const int span = (end - begin + kProbeThreads - 1) / kProbeThreads * kProbeThreads;
+    for (int off = threadIdx.x; off < span; off += kProbeThreads) {
+        const int idx = begin + off;
+        bool hit = false;
+        if (idx < end) {
+            const float4 p = B.scan_posq[idx];  // padding slots sit far away and never pass
+            hit = !cutoff || r2_prefilter(T, fx1, fy1, fz1, p) <= lim ||
+                  r2_prefilter(T, fx2, fy2, fz2, p) <= lim;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (hit) q[qn + __popc(ballot & ((1u << lane) - 1u))] = idx;
+        qn += __popc(ballot);
+        __syncwarp();
+        if (qn >= 32) {
+            const int idx2 = q[lane];
+            int k = idx2 - begin;
+            if (B.scan_atom) k = B.scan_atom[idx2] - r * n;
+            if (k >= 0 && T.group[k] == 0) probe_pair(T, pos, P, k, A);
+            __syncwarp();
+            if (lane < qn - 32) q[lane] = q[32 + lane];
+            qn -= 32;
+            __syncwarp();
+        }
+    }
+    if (lane < qn) {
+        const int idx2 = q[lane];
+        int k = idx2 - begin;
+        if (B.scan_atom) k = B.scan_atom[idx2] - r * n;
+        if (k >= 0 && T.group[k] == 0) probe_pair(T, pos, P, k, A);
+    }
+    // (2) the other displaced atoms (different displacement group), no prefilter
+    for (int mm = threadIdx.x; mm < T.n_lig; mm += kProbeThreads) probe_pair(T, pos, P, T.lig_idx[mm], A);
+
+    double sx = block_sum(A.fx, s_red);
+    double sy = block_sum(A.fy, s_red);
+    double sz = block_sum(A.fz, s_red);
+    double su = block_sum(A.u, s_red);
+    long long sc1 = block_sum_ll(A.c1, s_redl);
+    long long sc2 = block_sum_ll(A.c2, s_redl);
+    if (threadIdx.x == 0) {
+        double* dF = B.dF + (size_t)r * 3 * n;
+        dF[3 * P.i] = sx; dF[3 * P.i + 1] = sy; dF[3 * P.i + 2] = sz;
+        B.upart[(size_t)r * T.n_lig + m] = su;
+        B.mcnt[((size_t)r * T.n_lig + m) * 2] = sc1;
+        B.mcnt[((size_t)r * T.n_lig + m) * 2 + 1] = sc2;
+    }
+}
+
+// env kernel: one thread per scan index (a NON-displaced atom j); loops over the displaced atoms
+// (staged in shared memory) and accumulates dF_j = sum_i f_j(state 2) - f_j(state 1).  Writes
+// every dF_j (zero when nothing is near), so no memset is needed.  The warps of a block take scan
+// positions that are a whole grid apart: the few warps that sit next to the displaced atoms (and
+// do all the FP64 work) end up in different blocks, i.e. on different SMs.
 struct Probe {
     double x1, y1, z1, x2, y2, z2, q, hsig, heps;
+    float fx1, fy1, fz1, fx2, fy2, fz2;
     int idx, pad;
 };
 
-__global__ void __launch_bounds__(128)
-ligand_env_kernel(Topology T, const double* __restrict__ pos_all, double* __restrict__ dF_all) {
+constexpr int kEnvThreads = 128;
+
+__global__ void __launch_bounds__(kEnvThreads)
+ligand_env_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
     constexpr int kChunk = 64;
     __shared__ Probe s_p[kChunk];
     const int n = T.n, r = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const double* pos = pos_all + (size_t)r * 3 * n;
-    const bool active = j < n && T.group[j] == 0;
+    const double* pos = B.pos + (size_t)r * 3 * n;
+    int begin, end;
+    scan_range(T, B, r, &begin, &end);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = begin + (warp * gridDim.x + blockIdx.x) * 32 + lane;
+    int j = -1;
+    if (idx < end) {
+        j = idx - begin;
+        if (B.scan_atom) {
+            const int ga = B.scan_atom[idx];
+            j = ga < 0 ? -1 : ga - r * n;
+        }
+    }
+    const bool active = j >= 0 && T.group[j] == 0;
     const bool cutoff = T.method != SDM_NOCUTOFF;
+    const float lim = T.rc2f * 1.0001f + 1.0e-4f;
     double xj = 0, yj = 0, zj = 0, qj = 0, hsj = 0, hej = 0;
+    float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
         xj = pos[3 * j]; yj = pos[3 * j + 1]; zj = pos[3 * j + 2];
         qj = T.q[j]; hsj = T.hsig[j]; hej = T.heps[j];
+        pf = B.scan_posq[idx];
     }
     double fx = 0, fy = 0, fz = 0;
     for (int m0 = 0; m0 < T.n_lig; m0 += kChunk) {
@@ -306,6 +416,8 @@ ligand_env_kernel(Topology T, const double* __restrict__ pos_all, double* __rest
             Probe p;
             p.x1 = pos[3 * i]; p.y1 = pos[3 * i + 1]; p.z1 = pos[3 * i + 2];
             p.x2 = p.x1 + T.disp[3 * i]; p.y2 = p.y1 + T.disp[3 * i + 1]; p.z2 = p.z1 + T.disp[3 * i + 2];
+            p.fx1 = (float)p.x1; p.fy1 = (float)p.y1; p.fz1 = (float)p.z1;
+            p.fx2 = (float)p.x2; p.fy2 = (float)p.y2; p.fz2 = (float)p.z2;
             p.q = T.q[i]; p.hsig = T.hsig[i]; p.heps = T.heps[i];
             p.idx = i; p.pad = 0;
             s_p[threadIdx.x] = p;
@@ -314,6 +426,9 @@ ligand_env_kernel(Topology T, const double* __restrict__ pos_all, double* __rest
         if (!active) continue;
         for (int m = 0; m < mc; m++) {
             const Probe& p = s_p[m];
+            if (cutoff && r2_prefilter(T, p.fx1, p.fy1, p.fz1, pf) > lim &&
+                r2_prefilter(T, p.fx2, p.fy2, p.fz2, pf) > lim)
+                continue;
             PairGeom g1 = geom(T, p.x1, p.y1, p.z1, xj, yj, zj);
             PairGeom g2 = geom(T, p.x2, p.y2, p.z2, xj, yj, zj);
             const bool in1 = !cutoff || g1.r2 <= T.rc2;
@@ -335,7 +450,7 @@ ligand_env_kernel(Topology T, const double* __restrict__ pos_all, double* __rest
         }
     }
     if (active) {
-        double* dF = dF_all + (size_t)r * 3 * n;
+        double* dF = B.dF + (size_t)r * 3 * n;
         dF[3 * j] = fx; dF[3 * j + 1] = fy; dF[3 * j + 2] = fz;
     }
 }
@@ -512,12 +627,12 @@ void launch_allpairs(const Topology& T, const EvalBuffers& B, int exact, int* em
 void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
     if (T.n_lig == 0) return;
     dim3 grid(T.n_lig, B.R);
-    ligand_probe_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.dF, B.upart, B.mcnt);
+    ligand_probe_kernel<<<grid, kProbeThreads, 0, s>>>(T, B);
 }
 
 void launch_ligand_env(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
-    dim3 grid((T.n + 127) / 128, B.R);
-    ligand_env_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.dF);
+    dim3 grid((B.scan_max + kEnvThreads - 1) / kEnvThreads, B.R);
+    ligand_env_kernel<<<grid, kEnvThreads, 0, s>>>(T, B);
 }
 
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) {

@@ -28,7 +28,7 @@ struct PairList {
     size_t entries_cap = 0, masks_cap = 0, units_cap = 0, items_cap = 0;
     int chunk = kChunk;
     // sizes of the current list (host copies)
-    int nslot = 0, ncl = 0, nsci = 0, nentries = 0, nmasks = 0, nunits = 0;
+    int nslot = 0, ncl = 0, nsci = 0, nentries = 0, nmasks = 0, nunits = 0, scan_max = 0;
 
     uint32_t *keys = nullptr, *keys_sorted = nullptr;
     int *vals = nullptr, *vals_sorted = nullptr;
@@ -429,6 +429,8 @@ static int build_list(sdm_ctx* c) {
     PL_CUDA(cudaStreamSynchronize(s));
     pl->nslot = pl->h_counts[0];
     pl->nsci = pl->h_counts[1];
+    // a replica holds n atoms and at most 7 padding slots per cell
+    pl->scan_max = std::min(pl->nslot, n + 7 * G.ncell);
     pl->ncl = pl->nslot / nbl::kClusterSize;
     if (pl->nslot > pl->nslot_cap || pl->nsci > pl->nsci_cap)
         return sdm_fail(SDM_ERR_CAPACITY, "internal: slot capacity exceeded");
@@ -701,6 +703,12 @@ int sdm_ctx_pairlist_eval(sdm_ctx* c) {
     c->B.epart = pl->epart;
     c->B.cpart = pl->cpart;
     c->B.part_off = pl->part_off;
+    // the displaced-atom kernels scan the cell-sorted slots (spatial locality per warp)
+    c->B.scan_posq = pl->posq;
+    c->B.scan_atom = pl->atom;
+    c->B.scan_off = pl->cell_slot;
+    c->B.scan_stride = pl->G.ncell;
+    c->B.scan_max = pl->scan_max;
     // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
     launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart,

@@ -140,7 +140,7 @@ __host__ __device__ inline void execute_scalars(sdm_alch* al, sdm_scalars* sc) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double pair_term_f64(double r2, double sig, double eps, double qq,
                                                 bool cutoff, double krf, double crf, double* e) {
-    double inverseR = 1.0 / sqrt(r2);
+    double inverseR = rsqrt(r2);  // within 2 ulp of 1/sqrt(r2) and three times cheaper
     double sig2 = inverseR * sig;
     sig2 *= sig2;
     double sig6 = sig2 * sig2 * sig2;
@@ -166,6 +166,14 @@ __device__ __forceinline__ double min_image_exact(double d, double L) {
 
 __device__ __forceinline__ double norm2_exact(double dx, double dy, double dz) {
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Same result as min_image_exact with the image INDEX chosen by a reciprocal multiplication (no
+// FP64 division): the two can only disagree when d/L + 1/2 is within an ulp of an integer, i.e.
+// |d_min| = L/2 >= cutoff, where the pair is out of range (or exactly at r = rc = L/2, where both
+// images give the same r^2) either way.  Used by the displaced-atom kernels.
+__device__ __forceinline__ double min_image_fast(double d, double L, double invL) {
+    return __dsub_rn(d, __dmul_rn(floor(__fma_rn(d, invL, 0.5)), L));
 }
 
 __device__ __forceinline__ bool in_cutoff_f64(const Topology& T, const double* __restrict__ pos,

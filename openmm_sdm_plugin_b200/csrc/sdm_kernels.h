@@ -30,6 +30,13 @@ struct EvalBuffers {
     int nslot;              // stride of f1acc planes (>= n)
     const int* slot_of;     // [R][n] atom -> accumulator slot, or nullptr for identity
     int n_epart_allpairs;   // blocks per replica of the all-pairs kernel
+    // Scan order of the displaced-atom kernels: FP32 positions (min-image prefilter) in an order
+    // with spatial locality.  Cluster path: the cell-sorted slots; all-pairs path: System order.
+    const float4* scan_posq; // [scan index]
+    const int* scan_atom;    // scan index -> replica*n + atom, -1 = padding; nullptr = identity
+    const int* scan_off;     // replica r owns scan indices [scan_off[r*scan_stride],
+    int scan_stride;         //   scan_off[(r+1)*scan_stride]); nullptr = [r*n, (r+1)*n)
+    int scan_max;            // upper bound of a replica's scan length (grid sizing)
 };
 
 // ---- fused path, v0 (all-pairs tiles, System order) ------------------------------------------

@@ -76,7 +76,8 @@ def test_cluster_matches_allpairs_and_is_deterministic(cfg2):
         assert np.array_equal(fa, fb)                       # fixed-point accumulation: bit-reproducible
         assert a.scalars(0) == b.scalars(0)
         assert rms_rel(fa, fc) < 5e-6
-        assert a.scalars(0)["u"] == c.scalars(0)["u"]       # moved-pair path is shared and FP64
+        # the moved-pair path is FP64 in both modes; only its (fixed) summation order differs
+        assert abs(a.scalars(0)["u"] - c.scalars(0)["u"]) <= 1e-10 * max(1.0, abs(c.scalars(0)["u"]))
 
 
 def test_list_reuse_refresh_and_rebuild(cfg2):
