@@ -106,6 +106,14 @@ int upload_displacement(sdm_ctx* c, const double* displacement) {
     if (!lig.empty())
         SDM_CUDA(cudaMemcpy(c->d_lig_idx, lig.data(), lig.size() * sizeof(int), cudaMemcpyHostToDevice));
     c->T.n_lig = (int)lig.size();
+    // displaced atoms that are excluded from (bonded to) a resting atom: only those need the
+    // exclusion lookup in the displaced-vs-resting pair loops
+    std::vector<int> flags(lig.size(), 0);
+    for (size_t m = 0; m < lig.size(); m++)
+        for (int k = c->h_excl_start[lig[m]]; k < c->h_excl_start[lig[m] + 1]; k++)
+            if (group[c->h_excl_idx[k]] == 0) flags[m] |= 1;
+    if (!lig.empty())
+        SDM_CUDA(cudaMemcpy(c->d_lig_flags, flags.data(), flags.size() * sizeof(int), cudaMemcpyHostToDevice));
     c->h_group = group;
     c->h_lig = lig;
     return SDM_OK;
@@ -290,9 +298,11 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     TRY(dev_alloc(c, &c->d_disp, 3 * (size_t)n));
     TRY(dev_alloc(c, &c->d_group, (size_t)n));
     TRY(dev_alloc(c, &c->d_lig_idx, (size_t)n));
+    TRY(dev_alloc(c, &c->d_lig_flags, (size_t)n));
     T.disp = c->d_disp;
     T.group = c->d_group;
     T.lig_idx = c->d_lig_idx;
+    T.lig_flags = c->d_lig_flags;
     TRY(upload_displacement(c, s->displacement));
 
     // per-replica buffers
@@ -495,8 +505,24 @@ int sdm_eval(sdm_ctx* c) {
         if (int rc = sdm_ctx_pairlist_eval(c)) return rc;  // records ev[1], ev[2] around the pair kernel
         zero_acc = 1;
     }
+    {
+        // prefilter bitmap of the displaced-atom kernels, grown on demand (never shrinks)
+        B.scan_words = (B.scan_max + 31) / 32;
+        const size_t need = (size_t)c->R * std::max(T.n_lig, 1) * B.scan_words;
+        if (need > c->hitbits_cap) {
+            if (c->d_hitbits) {
+                SDM_CUDA(cudaStreamSynchronize(s));
+                c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void*)c->d_hitbits), c->allocs.end());
+                SDM_CUDA(cudaFree(c->d_hitbits));
+                c->d_hitbits = nullptr;
+            }
+            c->hitbits_cap = need + need / 4;
+            if (int rc = dev_alloc(c, &c->d_hitbits, c->hitbits_cap)) return rc;
+        }
+        B.hitbits = c->d_hitbits;
+    }
+    sdm::launch_ligand_env(T, B, s);   // resting atoms + the prefilter bitmap the probe kernel reads
     if (T.n_lig > 0) { sdm::launch_ligand_probe(T, B, s); c->launches++; }
-    sdm::launch_ligand_env(T, B, s);
     sdm::launch_exceptions(T, B, s);
     sdm::launch_scalars(T, B, e_scale, c_div, c->list_age, s);
     sdm::launch_mix(T, B, zero_acc, s);

@@ -220,16 +220,28 @@ __device__ __forceinline__ PairGeom geom(const Topology& T, double xi, double yi
     return g;
 }
 
-// FP32 minimum-image distance^2 for the prefilter.
-__device__ __forceinline__ float r2_prefilter(const Topology& T, float xi, float yi, float zi,
-                                              const float4 p) {
+// FP32 minimum-image distance^2 for the prefilter.  Both points lie in [0, L) when periodic
+// (scan positions are wrapped at list-build / prep time, probes are wrapped when staged, and a
+// list reuse lets atoms drift by less than the skin), so |d| < 2L and one conditional shift per
+// dimension selects the nearest image -- no FRND.
+__device__ __forceinline__ float wrap1(float d, float L, float hL) {
+    d = d > hL ? d - L : d;
+    return d < -hL ? d + L : d;
+}
+
+__device__ __forceinline__ float r2_prefilter(const Topology& T, const float3 hbox, float xi, float yi,
+                                              float zi, const float4 p) {
     float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
     if (T.method == SDM_CUTOFF_PERIODIC) {
-        dx -= T.boxf[0] * rintf(dx * T.inv_boxf[0]);
-        dy -= T.boxf[1] * rintf(dy * T.inv_boxf[1]);
-        dz -= T.boxf[2] * rintf(dz * T.inv_boxf[2]);
+        dx = wrap1(dx, T.boxf[0], hbox.x);
+        dy = wrap1(dy, T.boxf[1], hbox.y);
+        dz = wrap1(dz, T.boxf[2], hbox.z);
     }
     return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ float wrap_into_box(double x, double L, double invL) {
+    return (float)(x - floor(x * invL) * L);
 }
 
 __device__ __forceinline__ void scan_range(const Topology& T, const EvalBuffers& B, int r, int* begin,
@@ -243,20 +255,159 @@ __device__ __forceinline__ void scan_range(const Topology& T, const EvalBuffers&
     }
 }
 
-// Accumulators of one displaced atom.
+// ---- env kernel ---------------------------------------------------------------------------------
+// One thread per scan index (a NON-displaced atom j); loops over the displaced atoms (staged in
+// shared memory in groups of 8 with a bounding sphere per state) and accumulates
+// dF_j = sum_i f_j(state 2) - f_j(state 1).  Writes every dF_j (zero when nothing is near), so no
+// memset is needed, and the prefilter bitmap hitbits[r][m][w] (bit = lane) that the probe kernel
+// consumes.  The warps of a block take scan positions that are a whole grid apart: the few warps
+// that sit next to the displaced atoms (and do all the FP64 work) end up on different SMs.
+struct Probe {
+    double x1, y1, z1, x2, y2, z2, q, hsig, heps;
+    float fx1, fy1, fz1, fx2, fy2, fz2;
+    int idx, flags;
+};
+
+constexpr int kEnvThreads = 128;
+constexpr int kProbeChunk = 64;   // displaced atoms staged per pass
+constexpr int kProbeGroup = 8;    // displaced atoms per bounding sphere
+
+__global__ void __launch_bounds__(kEnvThreads)
+ligand_env_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
+    __shared__ Probe s_p[kProbeChunk];
+    __shared__ float4 s_sph[kProbeChunk / kProbeGroup][2];   // (center, (radius + r_lim)^2) per state
+    const int n = T.n, r = blockIdx.y;
+    const double* pos = B.pos + (size_t)r * 3 * n;
+    int begin, end;
+    scan_range(T, B, r, &begin, &end);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sw = warp * gridDim.x + blockIdx.x;   // scan word (32 scan indices) of this warp
+    const int idx = begin + sw * 32 + lane;
+    int j = -1;
+    if (idx < end) {
+        j = idx - begin;
+        if (B.scan_atom) {
+            const int ga = B.scan_atom[idx];
+            j = ga < 0 ? -1 : ga - r * n;
+        }
+    }
+    const bool active = j >= 0 && T.group[j] == 0;
+    const bool cutoff = T.method != SDM_NOCUTOFF;
+    const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
+    const float lim = T.rc2f * 1.0001f + 1.0e-4f;
+    const float rlim = sqrtf(lim);
+    const float3 hbox = make_float3(0.5f * T.boxf[0], 0.5f * T.boxf[1], 0.5f * T.boxf[2]);
+    double xj = 0, yj = 0, zj = 0, qj = 0, hsj = 0, hej = 0;
+    float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        xj = pos[3 * j]; yj = pos[3 * j + 1]; zj = pos[3 * j + 2];
+        qj = T.q[j]; hsj = T.hsig[j]; hej = T.heps[j];
+        pf = B.scan_posq[idx];
+    }
+    uint32_t* bits = B.hitbits + (size_t)r * T.n_lig * B.scan_words + sw;
+    const bool store_bits = sw < B.scan_words;
+    double fx = 0, fy = 0, fz = 0;
+    for (int m0 = 0; m0 < T.n_lig; m0 += kProbeChunk) {
+        const int mc = min(kProbeChunk, T.n_lig - m0);
+        __syncthreads();
+        if (threadIdx.x < mc) {
+            const int i = T.lig_idx[m0 + threadIdx.x];
+            Probe p;
+            p.x1 = pos[3 * i]; p.y1 = pos[3 * i + 1]; p.z1 = pos[3 * i + 2];
+            p.x2 = p.x1 + T.disp[3 * i]; p.y2 = p.y1 + T.disp[3 * i + 1]; p.z2 = p.z1 + T.disp[3 * i + 2];
+            if (periodic) {
+                p.fx1 = wrap_into_box(p.x1, T.box[0], T.inv_box[0]); p.fx2 = wrap_into_box(p.x2, T.box[0], T.inv_box[0]);
+                p.fy1 = wrap_into_box(p.y1, T.box[1], T.inv_box[1]); p.fy2 = wrap_into_box(p.y2, T.box[1], T.inv_box[1]);
+                p.fz1 = wrap_into_box(p.z1, T.box[2], T.inv_box[2]); p.fz2 = wrap_into_box(p.z2, T.box[2], T.inv_box[2]);
+            } else {
+                p.fx1 = (float)p.x1; p.fy1 = (float)p.y1; p.fz1 = (float)p.z1;
+                p.fx2 = (float)p.x2; p.fy2 = (float)p.y2; p.fz2 = (float)p.z2;
+            }
+            p.q = T.q[i]; p.hsig = T.hsig[i]; p.heps = T.heps[i];
+            p.idx = i; p.flags = T.lig_flags[m0 + threadIdx.x];
+            s_p[threadIdx.x] = p;
+        }
+        __syncthreads();
+        const int ngroups = (mc + kProbeGroup - 1) / kProbeGroup;
+        if (threadIdx.x < 2 * ngroups) {
+            // bounding sphere of one group of displaced atoms in one state, centred on its first atom
+            const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
+            const Probe& c0 = s_p[g * kProbeGroup];
+            const float cx = st ? c0.fx2 : c0.fx1, cy = st ? c0.fy2 : c0.fy1, cz = st ? c0.fz2 : c0.fz1;
+            float rmax2 = 0.f;
+            for (int k = g * kProbeGroup + 1; k < min(mc, (g + 1) * kProbeGroup); k++) {
+                const Probe& q = s_p[k];
+                const float4 o = make_float4(st ? q.fx2 : q.fx1, st ? q.fy2 : q.fy1, st ? q.fz2 : q.fz1, 0.f);
+                rmax2 = fmaxf(rmax2, r2_prefilter(T, hbox, cx, cy, cz, o));
+            }
+            const float rr = sqrtf(rmax2) * 1.0001f + rlim + 1.0e-4f;
+            s_sph[g][st] = make_float4(cx, cy, cz, rr * rr);
+        }
+        __syncthreads();
+        for (int g = 0; g < ngroups; g++) {
+            const float4 s1 = s_sph[g][0], s2 = s_sph[g][1];
+            const bool near = active && (!cutoff || r2_prefilter(T, hbox, s1.x, s1.y, s1.z, pf) <= s1.w ||
+                                         r2_prefilter(T, hbox, s2.x, s2.y, s2.z, pf) <= s2.w);
+            const int mend = min(mc, (g + 1) * kProbeGroup);
+            if (!__any_sync(0xffffffffu, near)) {
+                if (store_bits && lane < mend - g * kProbeGroup)
+                    bits[(size_t)(m0 + g * kProbeGroup + lane) * B.scan_words] = 0u;
+                continue;
+            }
+            for (int m = g * kProbeGroup; m < mend; m++) {
+                const Probe& p = s_p[m];
+                const bool hit = near && (!cutoff || r2_prefilter(T, hbox, p.fx1, p.fy1, p.fz1, pf) <= lim ||
+                                          r2_prefilter(T, hbox, p.fx2, p.fy2, p.fz2, pf) <= lim);
+                const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                if (store_bits && lane == 0) bits[(size_t)(m0 + m) * B.scan_words] = ballot;
+                if (!hit) continue;
+                PairGeom g1 = geom(T, p.x1, p.y1, p.z1, xj, yj, zj);
+                PairGeom g2 = geom(T, p.x2, p.y2, p.z2, xj, yj, zj);
+                const bool in1 = !cutoff || g1.r2 <= T.rc2;
+                const bool in2 = !cutoff || g2.r2 <= T.rc2;
+                if (!(in1 || in2)) continue;
+                if ((p.flags & 1) && is_excluded(T, j, p.idx)) continue;
+                const double sig = p.hsig + hsj, eps = p.heps * hej;
+                const double qq = SDM_K_COULOMB * p.q * qj;
+                double e;
+                // d = x_i - x_j ; force on j is -fs*d
+                if (in1) {
+                    double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+                    fx += fs * g1.dx; fy += fs * g1.dy; fz += fs * g1.dz;
+                }
+                if (in2) {
+                    double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+                    fx -= fs * g2.dx; fy -= fs * g2.dy; fz -= fs * g2.dz;
+                }
+            }
+        }
+    }
+    if (active) {
+        double* dF = B.dF + (size_t)r * 3 * n;
+        dF[3 * j] = fx; dF[3 * j + 1] = fy; dF[3 * j + 2] = fz;
+    }
+}
+
+// ---- probe kernel -------------------------------------------------------------------------------
+// One block per (displaced atom i, replica).  Reads row (r, m) of the prefilter bitmap written by
+// the env kernel, spreads its set bits densely over the threads (prefix sum of popcounts, then
+// hit h -> thread h mod 128) and evaluates those pairs in FP64 at state 1 and state 2:
+//     dF_i = sum_k f_i(state 2) - f_i(state 1),   u_i = sum_k w_k (e2 - e1),
+// w_k = 1/2 when k is displaced too (that pair is seen from k's block as well), else 1.  The
+// other displaced atoms (different displacement group) are walked directly.
 struct ProbeAcc {
     double fx, fy, fz, u;
     long long c1, c2;
 };
 
 struct ProbeAtom {
-    int i, gi;
+    int i, gi, flags;
     double x1, y1, z1, x2, y2, z2, q, hsig, heps;
 };
 
 // Exact (FP64) dual-state term of the pair (displaced atom P, atom k) added to A.
 __device__ __forceinline__ void probe_pair(const Topology& T, const double* __restrict__ pos,
-                                           const ProbeAtom& P, int k, ProbeAcc& A) {
+                                           const ProbeAtom& P, int k, bool check_excl, ProbeAcc& A) {
     const int gk = T.group[k];
     if (gk == P.gi) return;  // same displacement (includes k == i): pair unchanged
     const bool cutoff = T.method != SDM_NOCUTOFF;
@@ -268,7 +419,7 @@ __device__ __forceinline__ void probe_pair(const Topology& T, const double* __re
     const bool in1 = !cutoff || g1.r2 <= T.rc2;
     const bool in2 = !cutoff || g2.r2 <= T.rc2;
     if (!(in1 || in2)) return;
-    if (is_excluded(T, P.i, k)) return;
+    if (check_excl && is_excluded(T, P.i, k)) return;
     const double sig = P.hsig + T.hsig[k], eps = P.heps * T.heps[k];
     const double qq = SDM_K_COULOMB * P.q * T.q[k];
     const double w = (gk != 0) ? 0.5 : 1.0;
@@ -290,66 +441,81 @@ __device__ __forceinline__ void probe_pair(const Topology& T, const double* __re
 }
 
 constexpr int kProbeThreads = 128;
+constexpr int kProbeWords = 1024;   // bitmap words handled per pass
 
 __global__ void __launch_bounds__(kProbeThreads)
 ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
     __shared__ double s_red[32];
     __shared__ long long s_redl[32];
-    __shared__ int s_queue[kProbeThreads / 32][64];
+    __shared__ uint32_t s_bits[kProbeWords];
+    __shared__ int s_pre[kProbeWords + 1];
+    __shared__ int s_wsum[kProbeThreads / 32 + 1];
     const int m = blockIdx.x, r = blockIdx.y, n = T.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* pos = B.pos + (size_t)r * 3 * n;
     ProbeAtom P;
     P.i = T.lig_idx[m];
     P.gi = T.group[P.i];
+    P.flags = T.lig_flags[m];
     P.x1 = pos[3 * P.i]; P.y1 = pos[3 * P.i + 1]; P.z1 = pos[3 * P.i + 2];
     P.x2 = P.x1 + T.disp[3 * P.i]; P.y2 = P.y1 + T.disp[3 * P.i + 1]; P.z2 = P.z1 + T.disp[3 * P.i + 2];
     P.q = T.q[P.i]; P.hsig = T.hsig[P.i]; P.heps = T.heps[P.i];
-    const float fx1 = (float)P.x1, fy1 = (float)P.y1, fz1 = (float)P.z1;
-    const float fx2 = (float)P.x2, fy2 = (float)P.y2, fz2 = (float)P.z2;
-    const bool cutoff = T.method != SDM_NOCUTOFF;
-    const float lim = T.rc2f * 1.0001f + 1.0e-4f;
     int begin, end;
     scan_range(T, B, r, &begin, &end);
+    const uint32_t* bits = B.hitbits + ((size_t)r * T.n_lig + m) * B.scan_words;
+    const int nwords = min(B.scan_words, (end - begin + 31) / 32);
     ProbeAcc A{0, 0, 0, 0, 0, 0};
 
-    // (1) resting atoms: FP32 prefilter over the scan list, survivors are queued per warp and
-    // evaluated 32 at a time so that the FP64 code runs with full warps.  Queue order and
-    // lane assignment depend only on the data, never on timing.
-    int* q = s_queue[warp];
-    int qn = 0;
-    const int span = (end - begin + kProbeThreads - 1) / kProbeThreads * kProbeThreads;
-    for (int off = threadIdx.x; off < span; off += kProbeThreads) {
-        const int idx = begin + off;
-        bool hit = false;
-        if (idx < end) {
-            const float4 p = B.scan_posq[idx];  // padding slots sit far away and never pass
-            hit = !cutoff || r2_prefilter(T, fx1, fy1, fz1, p) <= lim ||
-                  r2_prefilter(T, fx2, fy2, fz2, p) <= lim;
+    // (1) resting atoms named by the prefilter bitmap
+    for (int w0 = 0; w0 < nwords; w0 += kProbeWords) {
+        const int nw = min(kProbeWords, nwords - w0);
+        __syncthreads();
+        // popcounts and their block-wide exclusive prefix (each thread owns a contiguous run)
+        constexpr int kRun = kProbeWords / kProbeThreads;
+        int run = 0;
+        for (int k = 0; k < kRun; k++) {
+            const int w = threadIdx.x * kRun + k;
+            const uint32_t v = w < nw ? bits[w0 + w] : 0u;
+            s_bits[w] = v;
+            run += __popc(v);
         }
-        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-        if (hit) q[qn + __popc(ballot & ((1u << lane) - 1u))] = idx;
-        qn += __popc(ballot);
-        __syncwarp();
-        if (qn >= 32) {
-            const int idx2 = q[lane];
-            int k = idx2 - begin;
-            if (B.scan_atom) k = B.scan_atom[idx2] - r * n;
-            if (k >= 0 && T.group[k] == 0) probe_pair(T, pos, P, k, A);
-            __syncwarp();
-            if (lane < qn - 32) q[lane] = q[32 + lane];
-            qn -= 32;
-            __syncwarp();
+        int incl = run;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-    }
-    if (lane < qn) {
-        const int idx2 = q[lane];
-        int k = idx2 - begin;
-        if (B.scan_atom) k = B.scan_atom[idx2] - r * n;
-        if (k >= 0 && T.group[k] == 0) probe_pair(T, pos, P, k, A);
+        if (lane == 31) s_wsum[warp + 1] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_wsum[0] = 0;
+            for (int k = 1; k <= kProbeThreads / 32; k++) s_wsum[k] += s_wsum[k - 1];
+        }
+        __syncthreads();
+        int acc = s_wsum[warp] + incl - run;
+        for (int k = 0; k < kRun; k++) {
+            const int w = threadIdx.x * kRun + k;
+            s_pre[w] = acc;
+            acc += __popc(s_bits[w]);
+        }
+        if (threadIdx.x == kProbeThreads - 1) s_pre[kProbeWords] = acc;
+        __syncthreads();
+        const int total = s_pre[kProbeWords];
+        for (int h = threadIdx.x; h < total; h += kProbeThreads) {
+            // word holding hit h: last w with s_pre[w] <= h
+            int lo_ = 0, hi_ = kProbeWords;
+            while (hi_ - lo_ > 1) {
+                const int mid = (lo_ + hi_) >> 1;
+                if (s_pre[mid] <= h) lo_ = mid; else hi_ = mid;
+            }
+            const int bit = __fns(s_bits[lo_], 0, h - s_pre[lo_] + 1);
+            const int idx = begin + (w0 + lo_) * 32 + bit;
+            int k = idx - begin;
+            if (B.scan_atom) k = B.scan_atom[idx] - r * n;
+            probe_pair(T, pos, P, k, (P.flags & 1) != 0, A);
+        }
     }
     // (2) the other displaced atoms (different displacement group), no prefilter
-    for (int mm = threadIdx.x; mm < T.n_lig; mm += kProbeThreads) probe_pair(T, pos, P, T.lig_idx[mm], A);
+    for (int mm = threadIdx.x; mm < T.n_lig; mm += kProbeThreads) probe_pair(T, pos, P, T.lig_idx[mm], true, A);
 
     double sx = block_sum(A.fx, s_red);
     double sy = block_sum(A.fy, s_red);
@@ -363,95 +529,6 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         B.upart[(size_t)r * T.n_lig + m] = su;
         B.mcnt[((size_t)r * T.n_lig + m) * 2] = sc1;
         B.mcnt[((size_t)r * T.n_lig + m) * 2 + 1] = sc2;
-    }
-}
-
-// env kernel: one thread per scan index (a NON-displaced atom j); loops over the displaced atoms
-// (staged in shared memory) and accumulates dF_j = sum_i f_j(state 2) - f_j(state 1).  Writes
-// every dF_j (zero when nothing is near), so no memset is needed.  The warps of a block take scan
-// positions that are a whole grid apart: the few warps that sit next to the displaced atoms (and
-// do all the FP64 work) end up in different blocks, i.e. on different SMs.
-struct Probe {
-    double x1, y1, z1, x2, y2, z2, q, hsig, heps;
-    float fx1, fy1, fz1, fx2, fy2, fz2;
-    int idx, pad;
-};
-
-constexpr int kEnvThreads = 128;
-
-__global__ void __launch_bounds__(kEnvThreads)
-ligand_env_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
-    constexpr int kChunk = 64;
-    __shared__ Probe s_p[kChunk];
-    const int n = T.n, r = blockIdx.y;
-    const double* pos = B.pos + (size_t)r * 3 * n;
-    int begin, end;
-    scan_range(T, B, r, &begin, &end);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = begin + (warp * gridDim.x + blockIdx.x) * 32 + lane;
-    int j = -1;
-    if (idx < end) {
-        j = idx - begin;
-        if (B.scan_atom) {
-            const int ga = B.scan_atom[idx];
-            j = ga < 0 ? -1 : ga - r * n;
-        }
-    }
-    const bool active = j >= 0 && T.group[j] == 0;
-    const bool cutoff = T.method != SDM_NOCUTOFF;
-    const float lim = T.rc2f * 1.0001f + 1.0e-4f;
-    double xj = 0, yj = 0, zj = 0, qj = 0, hsj = 0, hej = 0;
-    float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        xj = pos[3 * j]; yj = pos[3 * j + 1]; zj = pos[3 * j + 2];
-        qj = T.q[j]; hsj = T.hsig[j]; hej = T.heps[j];
-        pf = B.scan_posq[idx];
-    }
-    double fx = 0, fy = 0, fz = 0;
-    for (int m0 = 0; m0 < T.n_lig; m0 += kChunk) {
-        const int mc = min(kChunk, T.n_lig - m0);
-        __syncthreads();
-        if (threadIdx.x < mc) {
-            const int i = T.lig_idx[m0 + threadIdx.x];
-            Probe p;
-            p.x1 = pos[3 * i]; p.y1 = pos[3 * i + 1]; p.z1 = pos[3 * i + 2];
-            p.x2 = p.x1 + T.disp[3 * i]; p.y2 = p.y1 + T.disp[3 * i + 1]; p.z2 = p.z1 + T.disp[3 * i + 2];
-            p.fx1 = (float)p.x1; p.fy1 = (float)p.y1; p.fz1 = (float)p.z1;
-            p.fx2 = (float)p.x2; p.fy2 = (float)p.y2; p.fz2 = (float)p.z2;
-            p.q = T.q[i]; p.hsig = T.hsig[i]; p.heps = T.heps[i];
-            p.idx = i; p.pad = 0;
-            s_p[threadIdx.x] = p;
-        }
-        __syncthreads();
-        if (!active) continue;
-        for (int m = 0; m < mc; m++) {
-            const Probe& p = s_p[m];
-            if (cutoff && r2_prefilter(T, p.fx1, p.fy1, p.fz1, pf) > lim &&
-                r2_prefilter(T, p.fx2, p.fy2, p.fz2, pf) > lim)
-                continue;
-            PairGeom g1 = geom(T, p.x1, p.y1, p.z1, xj, yj, zj);
-            PairGeom g2 = geom(T, p.x2, p.y2, p.z2, xj, yj, zj);
-            const bool in1 = !cutoff || g1.r2 <= T.rc2;
-            const bool in2 = !cutoff || g2.r2 <= T.rc2;
-            if (!(in1 || in2)) continue;
-            if (is_excluded(T, j, p.idx)) continue;
-            const double sig = p.hsig + hsj, eps = p.heps * hej;
-            const double qq = SDM_K_COULOMB * p.q * qj;
-            double e;
-            // d = x_i - x_j ; force on j is -fs*d
-            if (in1) {
-                double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-                fx += fs * g1.dx; fy += fs * g1.dy; fz += fs * g1.dz;
-            }
-            if (in2) {
-                double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-                fx -= fs * g2.dx; fy -= fs * g2.dy; fz -= fs * g2.dz;
-            }
-        }
-    }
-    if (active) {
-        double* dF = B.dF + (size_t)r * 3 * n;
-        dF[3 * j] = fx; dF[3 * j + 1] = fy; dF[3 * j + 2] = fz;
     }
 }
 
@@ -631,7 +708,8 @@ void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s
 }
 
 void launch_ligand_env(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
-    dim3 grid((B.scan_max + kEnvThreads - 1) / kEnvThreads, B.R);
+    // every scan word (32 scan indices) of a replica gets a warp: the bitmap rows are complete
+    dim3 grid((B.scan_words * 32 + kEnvThreads - 1) / kEnvThreads, B.R);
     ligand_env_kernel<<<grid, kEnvThreads, 0, s>>>(T, B);
 }
 

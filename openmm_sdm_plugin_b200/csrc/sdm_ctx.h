@@ -25,6 +25,9 @@ struct sdm_ctx {
     double* d_disp = nullptr;
     int* d_group = nullptr;
     int* d_lig_idx = nullptr;
+    int* d_lig_flags = nullptr;
+    uint32_t* d_hitbits = nullptr;      // displaced-atom prefilter bitmap (grown on demand)
+    size_t hitbits_cap = 0;
 
     std::vector<sdm_alch> h_alch;       // staging copies with ctx lifetime
     std::vector<double> h_eb;

@@ -32,6 +32,7 @@ struct Topology {
     const double* disp;    // [3n] displacement map
     const int* group;      // [n] id of the displacement vector (0 = not displaced)
     const int* lig_idx;    // [n_lig] displaced atoms, ascending
+    const int* lig_flags;  // [n_lig] bit 0: has an exclusion with a NON-displaced atom
     const int* excl_start; // [n+1] CSR over both directions, rows ascending
     const int* excl_idx;
     const int* exc_pairs;      // [2*n_exceptions]

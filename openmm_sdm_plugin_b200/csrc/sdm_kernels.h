@@ -37,6 +37,8 @@ struct EvalBuffers {
     const int* scan_off;     // replica r owns scan indices [scan_off[r*scan_stride],
     int scan_stride;         //   scan_off[(r+1)*scan_stride]); nullptr = [r*n, (r+1)*n)
     int scan_max;            // upper bound of a replica's scan length (grid sizing)
+    uint32_t* hitbits;       // [R][n_lig][scan_words] prefilter hits: bit b of word w = scan index 32*w+b
+    int scan_words;          // words per (replica, displaced atom) row = ceil(scan_max / 32)
 };
 
 // ---- fused path, v0 (all-pairs tiles, System order) ------------------------------------------

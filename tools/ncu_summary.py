@@ -58,6 +58,8 @@ def main():
                 if "Source" in r and any("Sampling" in c for c in r):
                     h = r
                 continue
+            if r == h:
+                continue   # the header repeats for every captured launch
             body.append(r)
         if h is None:
             print("no source page")
