@@ -245,8 +245,11 @@ SDM_HD bool boxes_atoms_within(const float* posq4, const BBox& boxA, const BBox&
     return false;
 }
 
+// Pruning done INSIDE the search (per item, one thread): 0 = cluster boxes only (default; the
+// exact atom-pair pruning then runs as a separate warp-per-entry pass, prune_imask below),
+// 1 = atoms against boxes, 2 = exact atom pairs.
 #ifndef SDM_NBL_PRUNE
-#define SDM_NBL_PRUNE 2   // 0: cluster boxes only, 1: atoms against boxes, 2: exact atom pairs
+#define SDM_NBL_PRUNE 0
 #endif
 
 // One search item = (sci, stencil offset).  Visits the clusters of the addressed cell and calls
@@ -312,6 +315,21 @@ SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
         }
     }
     return count;
+}
+
+// ---- stage 3b: exact pruning of a raw entry ----------------------------------------------------
+// Keeps imask bit ci only if some real atom pair of (cluster c0+ci, j-cluster B shifted by the
+// entry's image) is closer than rlist.  Scalar form (host checker); the device pass in
+// pairlist.cu evaluates the same predicate with one warp per entry.
+SDM_HD uint32_t prune_imask(const SearchView& V, const SciDesc& sd, uint32_t w0, uint32_t imask) {
+    const Grid& G = V.G;
+    const int B = (int)(w0 & 0x3ffffffu);
+    const uint32_t code = w0 >> 26;
+    const float sx = shift_x(code) * G.boxf[0], sy = shift_y(code) * G.boxf[1], sz = shift_z(code) * G.boxf[2];
+    uint32_t out = 0;
+    for (int ci = 0; ci < sd.nci; ci++)
+        if (((imask >> ci) & 1u) && any_pair_within(V.posq4, sd.c0 + ci, B, sx, sy, sz, G.rlist2)) out |= 1u << ci;
+    return out;
 }
 
 // ---- stage 4: exclusion masks -------------------------------------------------------------------

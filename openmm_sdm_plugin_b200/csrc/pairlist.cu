@@ -42,7 +42,13 @@ struct PairList {
     int* cl_sci = nullptr;
     int *item_count = nullptr, *item_off = nullptr;
     uint2* entries = nullptr;
-    int *entry_flag = nullptr, *entry_midx = nullptr;
+    int *entry_flag = nullptr, *entry_midx = nullptr, *entry_sci = nullptr;
+    // raw (box-pruned) entries of the search, before the exact prune + compaction
+    uint2* raw_entries = nullptr;
+    int *raw_flag = nullptr, *raw_sci = nullptr, *raw_keep = nullptr, *raw_pos = nullptr;
+    size_t raw_cap = 0;
+    int nraw = 0;
+    int* sci_off = nullptr;     // [nsci+1] first (compacted) entry of every sci
     uint32_t* masks = nullptr;
     int *sci_nunits = nullptr, *sci_unit_off = nullptr;
     Unit* units = nullptr;
@@ -208,10 +214,12 @@ struct CountEmit {
 struct FillEmit {
     uint2* out;
     int* flag;
-    int base;
+    int* esci;
+    int base, isci;
     __device__ void operator()(int k, uint32_t w0, uint32_t imask, bool diag) const {
         out[base + k] = make_uint2(w0, imask);
         flag[base + k] = diag ? 1 : 0;
+        esci[base + k] = isci;
     }
 };
 
@@ -223,19 +231,83 @@ __global__ void search_count_kernel(nbl::SearchView V, int nsci, int noff, int* 
 
 __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
                                    const int* __restrict__ item_off, uint2* entries, int* flag,
-                                   int cap) {
+                                   int* esci, int cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsci * noff) return;
     const int base = item_off[t];
     if (base >= cap) return;
-    nbl::search_item(V, t / noff, t % noff, FillEmit{entries, flag, base});
+    nbl::search_item(V, t / noff, t % noff, FillEmit{entries, flag, esci, base, t / noff});
+}
+
+// Exact pruning, one warp per raw entry: imask bit ci survives only if some real atom pair of
+// (cluster c0+ci, the entry's shifted j-cluster) is closer than rlist -- the predicate of
+// nbl::prune_imask.  Lane (tj, ti) = (lane>>2, lane&3) tests j-atom tj against i-atoms ti, ti+4.
+__global__ void __launch_bounds__(128)
+prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ raw_sci,
+             int* __restrict__ raw_flag, const SciDesc* __restrict__ sci,
+             const float4* __restrict__ posq, int* __restrict__ keep) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (e >= nraw) return;
+    const uint2 ent = raw[e];
+    const int B = (int)(ent.x & 0x3ffffffu);
+    const uint32_t code = ent.x >> 26;
+    const SciDesc sd = sci[raw_sci[e]];
+    const int tj = lane >> 2, ti = lane & 3;
+    float4 xj = posq[B * nbl::kJGroup + tj];
+    const bool jreal = xj.x < 0.5f * nbl::kFar;
+    xj.x += (float)nbl::shift_x(code) * G.boxf[0];
+    xj.y += (float)nbl::shift_y(code) * G.boxf[1];
+    xj.z += (float)nbl::shift_z(code) * G.boxf[2];
+    uint32_t todo = ent.y & 0xffu, out = 0u;
+    while (todo) {
+        const int ci = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const float4* pi = posq + (size_t)(sd.c0 + ci) * nbl::kClusterSize + ti;
+        const float4 a = pi[0], b = pi[4];
+        bool hit = false;
+        if (jreal) {
+            float dx = a.x - xj.x, dy = a.y - xj.y, dz = a.z - xj.z;
+            hit = a.x < 0.5f * nbl::kFar && dx * dx + dy * dy + dz * dz < G.rlist2;
+            dx = b.x - xj.x; dy = b.y - xj.y; dz = b.z - xj.z;
+            hit = hit || (b.x < 0.5f * nbl::kFar && dx * dx + dy * dy + dz * dz < G.rlist2);
+        }
+        if (__any_sync(0xffffffffu, hit)) out |= 1u << ci;
+    }
+    if (lane == 0) {
+        raw[e].y = out;
+        keep[e] = out != 0u;
+        // the diagonal flag needs the self tile, which always survives while the cluster has atoms
+        if (raw_flag[e] && !((out >> (B - sd.c0)) & 1u)) raw_flag[e] = 0;
+    }
+}
+
+__global__ void compact_kernel(int nraw, const uint2* __restrict__ raw, const int* __restrict__ raw_flag,
+                               const int* __restrict__ raw_sci, const int* __restrict__ keep,
+                               const int* __restrict__ pos, uint2* entries, int* entry_flag,
+                               int* entry_sci, int cap) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nraw || !keep[e]) return;
+    const int k = pos[e];
+    if (k >= cap) return;
+    entries[k] = raw[e];
+    entry_flag[k] = raw_flag[e];
+    entry_sci[k] = raw_sci[e];
+}
+
+__global__ void sci_off_kernel(int nsci, int noff, int nraw, const int* __restrict__ item_off,
+                               const int* __restrict__ pos, int* sci_off) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nsci) return;
+    const int first = s < nsci ? item_off[(size_t)s * noff] : nraw;
+    sci_off[s] = pos[first];   // pos has nraw+1 elements (exclusive scan incl. the total)
 }
 
 // Exclusions.  pass 0 flags the entries that need a mask set, pass 1 clears the pair's bit.
 __global__ void exclusion_kernel(Grid G, int n_excl, const int* __restrict__ excl_pairs,
                                  const int* __restrict__ slot_of, const int* __restrict__ cl_sci,
-                                 const SciDesc* __restrict__ sci, const int* __restrict__ item_off,
-                                 int noff, const uint2* __restrict__ entries, int* entry_flag,
+                                 const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
+                                 const uint2* __restrict__ entries, int* entry_flag,
                                  uint32_t* masks, int pass) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= G.R * n_excl) return;
@@ -247,7 +319,7 @@ __global__ void exclusion_kernel(Grid G, int n_excl, const int* __restrict__ exc
     const int ci = si / nbl::kClusterSize - sci[isci].c0;
     const uint32_t cj = (uint32_t)(sj / nbl::kJGroup);
     const uint32_t bit = nbl::mask_bit(si, sj);
-    const int e0 = item_off[isci * noff], e1 = item_off[(isci + 1) * noff];
+    const int e0 = sci_off[isci], e1 = sci_off[isci + 1];
     for (int e = e0; e < e1; e++) {
         const uint2 ent = entries[e];
         if ((ent.x & 0x3ffffffu) != cj) continue;
@@ -262,9 +334,8 @@ __global__ void exclusion_kernel(Grid G, int n_excl, const int* __restrict__ exc
 
 // Assign mask-set indices (1-based; 0 = all ones) and initialise the sets.
 __global__ void mask_init_kernel(int nentries, const int* __restrict__ entry_flag,
-                                 const int* __restrict__ entry_midx, const int* __restrict__ item_off,
-                                 uint2* entries, uint32_t* masks, const SciDesc* __restrict__ sci,
-                                 const int* __restrict__ entry_sci) {
+                                 const int* __restrict__ entry_midx, uint2* entries, uint32_t* masks,
+                                 const SciDesc* __restrict__ sci, const int* __restrict__ entry_sci) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nentries || !entry_flag[e]) return;
     const uint32_t midx = (uint32_t)entry_midx[e] + 1u;
@@ -281,26 +352,18 @@ __global__ void mask_init_kernel(int nentries, const int* __restrict__ entry_fla
     }
 }
 
-// entry -> sci map (needed by mask_init) and units
-__global__ void entry_sci_kernel(int nsci, int noff, const int* __restrict__ item_off, int* entry_sci) {
+__global__ void sci_units_count_kernel(int nsci, const int* __restrict__ sci_off, int chunk, int* sci_nunits) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsci) return;
-    for (int e = item_off[s * noff]; e < item_off[(s + 1) * noff]; e++) entry_sci[e] = s;
-}
-
-__global__ void sci_units_count_kernel(int nsci, int noff, const int* __restrict__ item_off, int chunk,
-                                       int* sci_nunits) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nsci) return;
-    const int len = item_off[(s + 1) * noff] - item_off[s * noff];
+    const int len = sci_off[s + 1] - sci_off[s];
     sci_nunits[s] = (len + chunk - 1) / chunk;
 }
 
-__global__ void units_fill_kernel(int nsci, int noff, const int* __restrict__ item_off, int chunk,
+__global__ void units_fill_kernel(int nsci, const int* __restrict__ sci_off, int chunk,
                                   const int* __restrict__ sci_unit_off, Unit* units) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsci) return;
-    const int e0 = item_off[s * noff], e1 = item_off[(s + 1) * noff];
+    const int e0 = sci_off[s], e1 = sci_off[s + 1];
     int u = sci_unit_off[s];
     for (int e = e0; e < e1; e += chunk, u++) units[u] = Unit{s, e, min(e + chunk, e1), 0};
 }
@@ -460,46 +523,66 @@ static int build_list(sdm_ctx* c) {
     }
     search_count_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_count);
     PL_CUDA(cudaMemsetAsync(pl->item_count + nitems, 0, sizeof(int), s));
-    {
+    auto ensure_cub = [&](size_t count) -> int {
         size_t need = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, need, pl->item_count, pl->item_off, (int)nitems + 1, s);
+        cub::DeviceScan::ExclusiveSum(nullptr, need, pl->item_count, pl->item_off, (int)count, s);
         if (need > pl->cub_tmp_bytes) {
             if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
             pl->cub_tmp_bytes = need;
         }
-    }
+        return SDM_OK;
+    };
+    if (int rc = ensure_cub((size_t)nitems + 1)) return rc;
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->item_count, pl->item_off, (int)nitems + 1, s));
     PL_CUDA(cudaMemcpyAsync(&pl->h_counts[2], pl->item_off + nitems, sizeof(int), cudaMemcpyDeviceToHost, s));
     PL_CUDA(cudaStreamSynchronize(s));
-    pl->nentries = pl->h_counts[2];
+    pl->nraw = pl->h_counts[2];
+    if ((size_t)pl->nraw > pl->raw_cap) {
+        pl->raw_cap = (size_t)(pl->nraw * 1.25) + 1024;
+        if (int rc = pl_realloc(pl, &pl->raw_entries, pl->raw_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->raw_flag, pl->raw_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->raw_sci, pl->raw_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->raw_keep, pl->raw_cap + 1)) return rc;
+        if (int rc = pl_realloc(pl, &pl->raw_pos, pl->raw_cap + 1)) return rc;
+    }
+    const int nraw = pl->nraw;
+    search_fill_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_off, pl->raw_entries,
+                                                          pl->raw_flag, pl->raw_sci, (int)pl->raw_cap);
+    // exact prune (one warp per raw entry), then order-preserving compaction
+    if (nraw > 0)
+        prune_kernel<<<blocks((long long)nraw * 32, 128), 128, 0, s>>>(G, nraw, pl->raw_entries, pl->raw_sci,
+                                                                      pl->raw_flag, pl->sci, pl->posq, pl->raw_keep);
+    PL_CUDA(cudaMemsetAsync(pl->raw_keep + nraw, 0, sizeof(int), s));
+    if (int rc = ensure_cub((size_t)nraw + 1)) return rc;
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->raw_keep, pl->raw_pos, nraw + 1, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[5], pl->raw_pos + nraw, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+    pl->nentries = pl->h_counts[5];
     if ((size_t)pl->nentries > pl->entries_cap) {
         pl->entries_cap = (size_t)(pl->nentries * 1.25) + 1024;
         if (int rc = pl_realloc(pl, &pl->entries, pl->entries_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_flag, pl->entries_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_midx, pl->entries_cap + 1)) return rc;
+        if (int rc = pl_realloc(pl, &pl->entry_sci, pl->entries_cap + 1)) return rc;
     }
-    search_fill_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_off, pl->entries,
-                                                          pl->entry_flag, (int)pl->entries_cap);
-    c->launches += 3;
+    if (nraw > 0)
+        compact_kernel<<<blocks(nraw), 256, 0, s>>>(nraw, pl->raw_entries, pl->raw_flag, pl->raw_sci, pl->raw_keep,
+                                                   pl->raw_pos, pl->entries, pl->entry_flag, pl->entry_sci,
+                                                   (int)pl->entries_cap);
+    sci_off_kernel<<<blocks(pl->nsci + 1), 256, 0, s>>>(pl->nsci, noff, nraw, pl->item_off, pl->raw_pos, pl->sci_off);
+    c->launches += 7;
 
     // exclusion masks
     if (pl->n_excl > 0)
         exclusion_kernel<<<blocks((long long)R * pl->n_excl), 256, 0, s>>>(
-            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->item_off, noff,
-            pl->entries, pl->entry_flag, pl->masks, 0);
+            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->sci_off, pl->entries,
+            pl->entry_flag, pl->masks, 0);
     PL_CUDA(cudaMemsetAsync(pl->entry_flag + pl->nentries, 0, sizeof(int), s));
-    {
-        size_t need = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, need, pl->entry_flag, pl->entry_midx, pl->nentries + 1, s);
-        if (need > pl->cub_tmp_bytes) {
-            if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
-            pl->cub_tmp_bytes = need;
-        }
-    }
+    if (int rc = ensure_cub((size_t)pl->nentries + 1)) return rc;
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->entry_flag, pl->entry_midx, pl->nentries + 1, s));
     PL_CUDA(cudaMemcpyAsync(&pl->h_counts[3], pl->entry_midx + pl->nentries, sizeof(int), cudaMemcpyDeviceToHost, s));
     // units
-    sci_units_count_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, noff, pl->item_off, pl->chunk, pl->sci_nunits);
+    sci_units_count_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_nunits);
     PL_CUDA(cudaMemsetAsync(pl->sci_nunits + pl->nsci, 0, sizeof(int), s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->sci_nunits, pl->sci_unit_off, pl->nsci + 1, s));
     PL_CUDA(cudaMemcpyAsync(&pl->h_counts[4], pl->sci_unit_off + pl->nsci, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -516,30 +599,19 @@ static int build_list(sdm_ctx* c) {
         if (int rc = pl_realloc(pl, &pl->epart, pl->units_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->cpart, pl->units_cap)) return rc;
     }
-    {
-        // entry -> sci map reuses item_count's storage when large enough, else a scratch alloc
-        int* entry_sci = nullptr;
-        if ((size_t)pl->nentries <= pl->items_cap) entry_sci = pl->item_count;
-        else {
-            pl->items_cap = (size_t)pl->nentries + 1;
-            if (int rc = pl_realloc(pl, &pl->item_count, pl->items_cap)) return rc;
-            entry_sci = pl->item_count;
-        }
-        entry_sci_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, noff, pl->item_off, entry_sci);
-        // mask set 0 = all ones
-        PL_CUDA(cudaMemsetAsync(pl->masks, 0xff, sizeof(uint32_t) * nbl::kMaskWords, s));
+    // mask set 0 = all ones
+    PL_CUDA(cudaMemsetAsync(pl->masks, 0xff, sizeof(uint32_t) * nbl::kMaskWords, s));
+    if (pl->nentries > 0)
         mask_init_kernel<<<blocks(pl->nentries), 256, 0, s>>>(pl->nentries, pl->entry_flag, pl->entry_midx,
-                                                             pl->item_off, pl->entries, pl->masks, pl->sci, entry_sci);
-    }
+                                                             pl->entries, pl->masks, pl->sci, pl->entry_sci);
     if (pl->n_excl > 0)
         exclusion_kernel<<<blocks((long long)R * pl->n_excl), 256, 0, s>>>(
-            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->item_off, noff,
-            pl->entries, pl->entry_flag, pl->masks, 1);
-    units_fill_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, noff, pl->item_off, pl->chunk,
-                                                      pl->sci_unit_off, pl->units);
+            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->sci_off, pl->entries,
+            pl->entry_flag, pl->masks, 1);
+    units_fill_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_unit_off, pl->units);
     part_off_kernel<<<blocks(R + 1), 256, 0, s>>>(G, pl->cell_sci, pl->sci_unit_off, pl->nsci, pl->nunits, pl->part_off);
     PL_CUDA(cudaMemcpyAsync(pl->posq_build, pl->posq, sizeof(float4) * (size_t)pl->nslot, cudaMemcpyDeviceToDevice, s));
-    c->launches += 8;
+    c->launches += 7;
     PL_CUDA(cudaGetLastError());
 
     // the fixed-point accumulators are indexed by slot: start from zero for the new layout
@@ -619,6 +691,14 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->entries, pl->entries_cap));
     A(pl_alloc(pl, &pl->entry_flag, pl->entries_cap + 1));
     A(pl_alloc(pl, &pl->entry_midx, pl->entries_cap + 1));
+    A(pl_alloc(pl, &pl->entry_sci, pl->entries_cap + 1));
+    pl->raw_cap = pl->entries_cap * 2;
+    A(pl_alloc(pl, &pl->raw_entries, pl->raw_cap));
+    A(pl_alloc(pl, &pl->raw_flag, pl->raw_cap));
+    A(pl_alloc(pl, &pl->raw_sci, pl->raw_cap));
+    A(pl_alloc(pl, &pl->raw_keep, pl->raw_cap + 1));
+    A(pl_alloc(pl, &pl->raw_pos, pl->raw_cap + 1));
+    A(pl_alloc(pl, &pl->sci_off, pl->nsci_cap + 2));
     pl->masks_cap = (size_t)total / 2 + 256;
     A(pl_alloc(pl, &pl->masks, pl->masks_cap * nbl::kMaskWords));
     pl->units_cap = pl->entries_cap / 8 + 256;
@@ -640,7 +720,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     {
         size_t a = 0, b = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, a, pl->keys, pl->keys_sorted, pl->vals, pl->vals_sorted, total, 0, 32, c->stream);
-        cub::DeviceScan::ExclusiveSum(nullptr, b, pl->item_count, pl->item_off, (int)std::max<size_t>(pl->items_cap, pl->entries_cap + 1), c->stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, b, pl->item_count, pl->item_off, (int)std::max<size_t>(pl->items_cap, pl->raw_cap + 1), c->stream);
         pl->cub_tmp_bytes = std::max(a, b) + 256;
         A(pl_alloc(pl, (char**)&pl->cub_tmp, pl->cub_tmp_bytes));
     }
@@ -736,6 +816,7 @@ int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "n_clusters") *value = pl->ncl;
     else if (k == "n_sci") *value = pl->nsci;
     else if (k == "n_entries") *value = pl->nentries;
+    else if (k == "n_raw_entries") *value = pl->nraw;
     else if (k == "n_masks") *value = pl->nmasks;
     else if (k == "n_units") *value = pl->nunits;
     else if (k == "n_cells") *value = pl->G.ncell;

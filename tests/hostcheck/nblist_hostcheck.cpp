@@ -185,18 +185,38 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     std::vector<int> item_off(nitems + 1, 0);
     for (long long t = 0; t < nitems; t++)
         item_off[t + 1] = item_off[t] + search_item(V, (int)(t / noff), (int)(t % noff), [](int, uint32_t, uint32_t, bool) {});
-    const int nentries = item_off[nitems];
-    std::vector<uint32_t> ex(nentries), ey(nentries);
-    std::vector<int> flag(nentries + 1, 0), esci(nentries);
+    const int nraw = item_off[nitems];
+    std::vector<uint32_t> rx(nraw), ry(nraw);
+    std::vector<int> rflag(nraw, 0), rsci(nraw);
     for (long long t = 0; t < nitems; t++) {
         int base = item_off[t];
         search_item(V, (int)(t / noff), (int)(t % noff), [&](int k, uint32_t w0, uint32_t imask, bool diag) {
-            ex[base + k] = w0;
-            ey[base + k] = imask;
-            flag[base + k] = diag ? 1 : 0;
-            esci[base + k] = (int)(t / noff);
+            rx[base + k] = w0;
+            ry[base + k] = imask;
+            rflag[base + k] = diag ? 1 : 0;
+            rsci[base + k] = (int)(t / noff);
         });
     }
+    // exact prune + order-preserving compaction (prune_kernel / compact_kernel / sci_off_kernel)
+    std::vector<uint32_t> ex, ey;
+    std::vector<int> flag, esci, sci_off(nsci + 1, 0);
+    {
+        int next_sci = 0;
+        for (int e = 0; e < nraw; e++) {
+            while (next_sci <= rsci[e]) sci_off[next_sci++] = (int)ex.size();
+            const SciDesc sd = sci[rsci[e]];
+            const uint32_t m = prune_imask(V, sd, rx[e], ry[e] & 0xffu);
+            if (!m) continue;
+            const int B = (int)(rx[e] & 0x3ffffffu);
+            ex.push_back(rx[e]);
+            ey.push_back(m);
+            flag.push_back(rflag[e] && ((m >> (B - sd.c0)) & 1u) ? 1 : 0);
+            esci.push_back(rsci[e]);
+        }
+        while (next_sci <= nsci) sci_off[next_sci++] = (int)ex.size();
+    }
+    const int nentries = (int)ex.size();
+    flag.push_back(0);
     // exclusions pass 0
     auto for_excl = [&](int pass, std::vector<uint32_t>* masks) {
         for (int r = 0; r < R; r++)
@@ -208,7 +228,7 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
                 int ci = si / kClusterSize - sci[isci].c0;
                 uint32_t cj = (uint32_t)(sj / kJGroup);
                 uint32_t bit = mask_bit(si, sj);
-                for (int e = item_off[(long long)isci * noff]; e < item_off[(long long)(isci + 1) * noff]; e++) {
+                for (int e = sci_off[isci]; e < sci_off[isci + 1]; e++) {
                     if ((ex[e] & 0x3ffffffu) != cj) continue;
                     if (pass == 0) flag[e] = 1;
                     else (*masks)[(size_t)(ey[e] >> 8) * kMaskWords + mask_word(ci, si)] &= ~bit;
@@ -236,7 +256,7 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     for_excl(1, &masks);
     int nunits = 0;
     for (int s = 0; s < nsci; s++) {
-        int len = item_off[(long long)(s + 1) * noff] - item_off[(long long)s * noff];
+        int len = sci_off[s + 1] - sci_off[s];
         nunits += (len + chunk - 1) / chunk;
     }
 
@@ -247,7 +267,7 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     double lane_pairs = 0;
     for (int s = 0; s < nsci; s++) {
         const SciDesc sd = sci[s];
-        for (int e = item_off[(long long)s * noff]; e < item_off[(long long)(s + 1) * noff]; e++) {
+        for (int e = sci_off[s]; e < sci_off[s + 1]; e++) {
             const int cj = (int)(ex[e] & 0x3ffffffu);
             const uint32_t imask = ey[e] & 0xffu, m = ey[e] >> 8;
             const uint32_t code = ex[e] >> 26;
