@@ -204,10 +204,8 @@ def main():
         collective; 16 bytes per replica."""
         if world == 1:
             return
-        t = torch.tensor([[s["u_sc"], float(rank * R + i)] for i, s in enumerate(scalars)],
-                         dtype=torch.float64, device="cuda")
-        out = torch.empty((world,) + t.shape, dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(out, t)
+        from openmm_sdm_plugin_b200 import exchange as X
+        X.all_gather_replica_info([s["u_sc"] for s in scalars], [rank * R + i for i in range(len(scalars))])
 
     # ---------------- resident leg: inputs already in HBM ----------------------------------
     def resident_step():

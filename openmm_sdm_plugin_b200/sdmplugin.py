@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference's Python surface for the dual-state force path.
+
+`LangevinIntegratorSDM` keeps the names, argument meaning, defaults, units (kJ/mol, nm, ps, K)
+and error behaviour of `SDMPlugin::LangevinIntegratorSDM` as SWIG exposes it
+(python/SDMplugin.i:86-145; ctor defaults openmmapi/src/LangevinIntegratorSDM.cpp:48-85), and
+`SDMUtils` keeps the method constants of python/SDMUtils.py:9-15.  What is NOT mirrored is the
+integrator proper: `step()` in the reference also integrates the Langevin equations
+(not part of the hot path); here `bind()` + `evaluate()` perform
+exactly the force column of `step()` -- LangevinIntegratorSDM.cpp:156-182 up to and including
+the hybrid force of ReferenceSDMKernels.cpp:309-318 -- on the GPU through the C ABI.
+
+All arithmetic happens in libsdmb200.so; this module only marshals state.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _lib
+from .system import AlchemicalState, NonbondedSystem
+
+
+class OpenMMException(Exception):
+    """Stands in for OpenMM::OpenMMException (the reference throws it from C++)."""
+
+
+class SDMUtils(object):
+    """Method constants exactly as python/SDMUtils.py:9-15 names them."""
+
+    def __init__(self, system=None):
+        self.system = system
+        self.RestraintControlParameterName = "SDMRestraintControlParameter"
+        self.LinearMethod = 0
+        self.QuadraticMethod = 1
+        self.ILogisticMethod = 2
+        self.NoSoftCoreMethod = 0
+        self.TanhSoftCoreMethod = 1
+        self.RationalSoftCoreMethod = 2
+
+    def getControlParameterName(self):
+        return self.RestraintControlParameterName
+
+
+class LangevinIntegratorSDM(object):
+    # LangevinIntegratorSDM.h:120-122 and :143-145
+    LinearMethod, QuadraticMethod, ILogisticMethod = 0, 1, 2
+    NoSoftCoreMethod, TanhMethod, RationalMethod = 0, 1, 2
+
+    def __init__(self, temperature, frictionCoeff, stepSize, nParticles):
+        self._temperature = float(temperature)
+        self._friction = float(frictionCoeff)
+        self._step_size = float(stepSize)
+        self._seed = int.from_bytes(os.urandom(4), "little") & 0x7fffffff   # osrngseed()
+        self._a = AlchemicalState()          # ctor defaults: umax 200, a 1/4, ub 0, lambda 1, ...
+        self._a.step_size = self._step_size
+        self._bind_e = 0.0
+        self._pot_energy = 0.0
+        self._n = int(nParticles)
+        self._displ = np.zeros((self._n, 3), np.float64)   # displ.push_back(Vec3(0,0,0)) x nParticles
+        self._ctx = None
+        self._displ_dirty = False
+
+    # ---- plain state (names as in SDMplugin.i) ------------------------------------------------
+    def setLambda(self, lambdac): self._a.lambdac = float(lambdac)
+    def getLambda(self): return self._a.lambdac
+    def getTemperature(self): return self._temperature
+    def setTemperature(self, temp): self._temperature = float(temp)
+    def getFriction(self): return self._friction
+    def setFriction(self, coeff): self._friction = float(coeff)
+    def getRandomNumberSeed(self): return self._seed
+    def setRandomNumberSeed(self, seed): self._seed = int(seed)
+    def getStepSize(self): return self._step_size
+
+    def setStepSize(self, size):
+        self._step_size = float(size)
+        self._a.step_size = self._step_size
+
+    def getBindE(self): return self._bind_e
+    def setBindE(self, be): self._bind_e = float(be)
+    def getPotEnergy(self): return self._pot_energy
+    def setPotEnergy(self, e): self._pot_energy = float(e)
+    def getUmax(self): return self._a.umax
+    def setUmax(self, um): self._a.umax = float(um)
+    def getAcore(self): return self._a.acore
+    def setAcore(self, a): self._a.acore = float(a)
+    def getUbcore(self): return self._a.ubcore
+    def setUbcore(self, a): self._a.ubcore = float(a)
+    def setBiasMethod(self, method): self._a.bias_method = int(method)
+    def getBiasMethod(self): return self._a.bias_method
+    def setSoftCoreMethod(self, method): self._a.softcore_method = int(method)
+    def getSoftCoreMethod(self): return self._a.softcore_method
+    def setGamma(self, gammat): self._a.gammac = float(gammat)
+    def getGamma(self): return self._a.gammac
+    def setWBcoeff(self, wbcoeff_t): self._a.wbcoeff = float(wbcoeff_t)
+    def getWBcoeff(self): return self._a.wbcoeff
+    def setW0coeff(self, w0coeff_t): self._a.w0coeff = float(w0coeff_t)
+    def getW0coeff(self): return self._a.w0coeff
+    def setLambda1(self, lambda1_t): self._a.lambda1 = float(lambda1_t)
+    def getLambda1(self): return self._a.lambda1
+    def setLambda2(self, lambda2_t): self._a.lambda2 = float(lambda2_t)
+    def getLambda2(self): return self._a.lambda2
+    def setAlpha(self, alpha_t): self._a.alpha = float(alpha_t)
+    def getAlpha(self): return self._a.alpha
+    def setU0(self, u0_t): self._a.u0 = float(u0_t)
+    def getU0(self): return self._a.u0
+    def setNoneqtmax(self, noneq_tmax): self._a.noneq_tmax = float(noneq_tmax)
+    def getNoneqtmax(self): return self._a.noneq_tmax
+    def getNonEquilibrium(self): return self._a.nonequilibrium
+    # setNonEquilibrium exists in C++ (LangevinIntegratorSDM.h) but SDMplugin.i:124 does not wrap
+    # it; it is provided so that the non-equilibrium schedule can be exercised at all.
+    def setNonEquilibrium(self, flag): self._a.nonequilibrium = int(flag)
+    def setNoneqWorkvalue(self, noneq_work): self._a.work_value = float(noneq_work)
+    def getNoneqWorkvalue(self): return self._a.work_value
+    def setlambda1Slope(self, ml1): self._a.m_lambda1 = float(ml1)
+    def getlambda1Slope(self): return self._a.m_lambda1
+    def setlambda2Slope(self, ml2): self._a.m_lambda2 = float(ml2)
+    def getlambda2Slope(self): return self._a.m_lambda2
+    def setu0Slope(self, mu0): self._a.m_u0 = float(mu0)
+    def getu0Slope(self): return self._a.m_u0
+    def setw0Slope(self, mw0): self._a.m_w0 = float(mw0)
+    def getw0Slope(self): return self._a.m_w0
+    def setlambda1intercept(self, bl1): self._a.b_lambda1 = float(bl1)
+    def getlambda1intercept(self): return self._a.b_lambda1
+    def setlambda2intercept(self, bl2): self._a.b_lambda2 = float(bl2)
+    def getlambda2intercept(self): return self._a.b_lambda2
+    def setu0intercept(self, bu0): self._a.b_u0 = float(bu0)
+    def getu0intercept(self): return self._a.b_u0
+    def setw0intercept(self, bw0): self._a.b_w0 = float(bw0)
+    def getw0intercept(self): return self._a.b_w0
+
+    # ---- displacement map (LangevinIntegratorSDM.h:467-472) -----------------------------------
+    def setDisplacement(self, atom, dx, dy, dz):
+        # the reference indexes a std::vector without a bounds check; Python raises instead of
+        # corrupting memory
+        if not 0 <= int(atom) < self._n:
+            raise IndexError("particle index %d out of range (nParticles = %d)" % (atom, self._n))
+        self._displ[int(atom)] = (float(dx), float(dy), float(dz))
+        self._displ_dirty = True
+
+    def getDisplacement(self, atom):
+        if not 0 <= int(atom) < self._n:
+            raise IndexError("particle index %d out of range (nParticles = %d)" % (atom, self._n))
+        return tuple(float(v) for v in self._displ[int(atom)])
+
+    # ---- the force path ------------------------------------------------------------------------
+    def bind(self, system: NonbondedSystem, device: int = -1, **ctx_options):
+        """What LangevinIntegratorSDM::initialize does for this path
+        (LangevinIntegratorSDM.cpp:89-106): bind to one context, snapshot the displacement map
+        (ReferenceSDMKernels.cpp:150-154)."""
+        from .context import SDMContext
+        if self._ctx is not None:
+            raise OpenMMException("This Integrator is already bound to a context")
+        if system.n_atoms != self._n:
+            raise OpenMMException("nParticles (%d) does not match the system (%d)" % (self._n, system.n_atoms))
+        self._ctx = SDMContext(system, self._displ, n_replicas=1, device=device, **ctx_options)
+        self._displ_dirty = False
+        return self
+
+    def cleanup(self):
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+    def evaluate(self, positions, bonded_forces=None, restraint_energy=0.0):
+        """The force column of one `step()`: both states, soft-core, bias, hybrid force.
+        Returns the hybrid force [nParticles, 3] (kJ/mol/nm) and updates getBindE()/getPotEnergy()
+        (and, in non-equilibrium mode, lambda1/lambda2/u0/w0/work like
+        ReferenceSDMKernels.cpp:231-245,289-302)."""
+        if self._ctx is None:
+            raise OpenMMException("the integrator is not bound to a context: call bind(system) first")
+        # the reference snapshots the map at initialize(); a later setDisplacement() needs
+        # Context::reinitialize there.  Here the new map is uploaded.
+        if self._displ_dirty:
+            self._ctx.set_displacement(self._displ)
+            self._displ_dirty = False
+        c = self._ctx
+        c.set_positions(0, np.ascontiguousarray(positions, np.float64))
+        c.set_bonded_forces(0, bonded_forces, float(restraint_energy))
+        c.set_alchemical(0, self._a)
+        c.eval()
+        sc = c.scalars(0)
+        if sc["status"] == _lib.SDM_ERR_SOFTCORE:
+            raise OpenMMException("Unknown soft core method")     # LangevinIntegratorSDM.cpp:147
+        if sc["status"] != 0:
+            raise OpenMMException("libsdmb200 status %d" % sc["status"])
+        self._bind_e = sc["bind_e"]
+        self._pot_energy = sc["pot_energy"]
+        c.get_alchemical(0, self._a)
+        self.last_scalars = sc
+        return c.forces(0, _lib.FORCE_HYBRID)
+
+    def step(self, steps):
+        raise OpenMMException(
+            "LangevinIntegratorSDM.step integrates the equations of motion, which is outside the "
+            "B200 hot path (SURVEY.md 8(f) N2); call evaluate(positions) for the force column of a step")
