@@ -8,9 +8,11 @@
 // Layout
 //   * replicas live in disjoint cell ranges of ONE global index space: global cell
 //     g = r*ncell + cell.
-//   * atoms are sorted by (global cell, 9-bit Morton code of the position inside the cell) and
-//     every cell is padded to a multiple of 8 slots with dummy atoms, so a cluster (8 slots)
-//     never straddles a cell.
+//   * atoms are sorted by global cell and, inside a cell, by a balanced three-level kd split
+//     (z, then y, then x; every split point is a multiple of 8 atoms), so the 8-atom clusters
+//     are compact boxes (28.8 % -> 31.8 % useful pairs per tile on the 20 k-atom fixture compared
+//     with a Morton order); every cell is padded to a multiple of 8 slots with dummy atoms, so a
+//     cluster (8 slots) never straddles a cell.
 //   * an i-supercluster (sci) is a run of <= 8 clusters of one cell; its list holds j-cluster
 //     entries {cj | shift<<26, imask | mask_index<<8}; imask bit ci says cluster ci of the sci
 //     interacts with j-cluster cj (an 8 x 8 "tile").  Every unordered cluster pair is owned by
@@ -37,7 +39,7 @@ constexpr int kClusterSize = 8;      // atoms per i-cluster
 constexpr int kJGroup = 8;           // atoms per j-group (a whole cluster)
 constexpr int kMaxCi = 8;            // clusters per supercluster
 constexpr int kMaskWords = 2 * kMaxCi;  // words per exclusion-mask set
-constexpr int kSubBits = 9;          // Morton bits of the in-cell position in the sort key
+constexpr int kSubBits = 34;         // sort key = cell << 34 | kd bucket (2 bits) << 32 | coordinate bits
 constexpr int kMaxSpan = 6;          // search stencil is at most kMaxSpan cells per dimension
 constexpr float kFar = 1.0e6f;       // coordinate of dummy (padding) atoms
 constexpr float kBoxEmptyLo = 3.0e38f;
@@ -105,14 +107,14 @@ SDM_HD int shift_y(uint32_t code) { return (int)((code >> 2) & 3u) - 1; }
 SDM_HD int shift_z(uint32_t code) { return (int)((code >> 4) & 3u) - 1; }
 constexpr uint32_t kShiftZero = 1u | (1u << 2) | (1u << 4);
 
-// ---- stage 1: sort key of an atom -------------------------------------------------------------
-// Wraps the position into the box (periodic), returns the key (global cell << 9 | Morton sub
-// code), the wrapped coordinates and the integer image that was applied (xw = x + img*L).
-SDM_HD uint32_t atom_key(const Grid& G, int replica, double x, double y, double z, float* xw_out,
-                         int* img_out) {
+// ---- stage 1: sort keys -------------------------------------------------------------------------
+// Wraps the position into the box (periodic), returns the global cell, the wrapped coordinates
+// (relative to the grid origin they are >= 0) and the integer image that was applied
+// (xw = x + img*L).
+SDM_HD uint32_t atom_cell(const Grid& G, int replica, double x, double y, double z, float* xw_out,
+                          int* img_out) {
     double p[3] = {x, y, z};
     int c[3];
-    uint32_t sub[3];
     for (int d = 0; d < 3; d++) {
         double w = p[d];
         int img = 0;
@@ -127,19 +129,46 @@ SDM_HD uint32_t atom_key(const Grid& G, int replica, double x, double y, double 
         int k = (int)floor(t);
         if (k < 0) k = 0;
         if (k >= G.nc[d]) k = G.nc[d] - 1;
-        double fr = t - (double)k;
-        int s = (int)(fr * 8.0);
-        if (s < 0) s = 0;
-        if (s > 7) s = 7;
         c[d] = k;
-        sub[d] = (uint32_t)s;
         xw_out[d] = (float)w;
         img_out[d] = img;
     }
     uint32_t cell = (uint32_t)((c[2] * G.nc[1] + c[1]) * G.nc[0] + c[0]);
-    uint32_t g = (uint32_t)replica * (uint32_t)G.ncell + cell;
-    uint32_t m = spread3(sub[0]) | (spread3(sub[1]) << 1) | (spread3(sub[2]) << 2);
-    return (g << kSubBits) | m;
+    return (uint32_t)replica * (uint32_t)G.ncell + cell;
+}
+
+// Order-preserving bits of a coordinate measured from the grid origin (non-negative float).
+SDM_HD uint32_t coord_bits(const Grid& G, float w, int d) {
+    float v = w - (float)G.lo[d];
+    if (!(v > 0.f)) v = 0.f;
+    union { float f; uint32_t u; } cv;
+    cv.f = v;
+    return cv.u;
+}
+
+SDM_HD uint64_t make_key(uint32_t gcell, uint32_t bucket, uint32_t cbits) {
+    return ((uint64_t)gcell << kSubBits) | ((uint64_t)(bucket & 3u) << 32) | (uint64_t)cbits;
+}
+
+// Atoms that go to the first half when a run of `count` atoms is split: half of its clusters
+// (rounded up), i.e. a multiple of 8.
+SDM_HD int split_first(int count) {
+    const int m = (count + kClusterSize - 1) / kClusterSize;
+    const int h = kClusterSize * ((m + 1) / 2);
+    return h < count ? h : count;
+}
+
+// kd refinement.  The sort runs three times: by (cell, z), by (cell, b1, y), by (cell, b1, b2, x),
+// where b1 / b2 say whether the atom fell into the second half of the previous split.  Given the
+// position p of an atom in the order produced by round `level` (1 or 2), the first position and
+// size of its cell and its previous bucket bits, returns the bucket bits for the next round.
+SDM_HD uint32_t kd_bucket(int level, int p, int cell_first, int cell_count, uint32_t prev_bucket) {
+    const int h1 = split_first(cell_count);
+    if (level == 1) return (uint32_t)((p - cell_first) >= h1) << 1;
+    const int b1 = (int)(prev_bucket >> 1) & 1;
+    const int seg0 = cell_first + (b1 ? h1 : 0);
+    const int segn = b1 ? cell_count - h1 : h1;
+    return (uint32_t)(b1 << 1) | (uint32_t)((p - seg0) >= split_first(segn));
 }
 
 // ---- stage 2: bounding boxes --------------------------------------------------------------------

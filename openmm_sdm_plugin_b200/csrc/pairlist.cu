@@ -30,7 +30,7 @@ struct PairList {
     // sizes of the current list (host copies)
     int nslot = 0, ncl = 0, nsci = 0, nentries = 0, nmasks = 0, nunits = 0, scan_max = 0;
 
-    uint32_t *keys = nullptr, *keys_sorted = nullptr;
+    uint64_t *keys = nullptr, *keys_sorted = nullptr;
     int *vals = nullptr, *vals_sorted = nullptr;
     int *cell_first = nullptr, *cell_count = nullptr, *cell_pcount = nullptr, *cell_nsci = nullptr;
     int *cell_slot = nullptr, *cell_sci = nullptr;
@@ -102,24 +102,46 @@ int pl_realloc(PairList* pl, T** p, size_t count) {
 }
 
 // ---- device wrappers around the per-item bodies ------------------------------------------------
-__global__ void key_kernel(Grid G, const double* __restrict__ pos_all, uint32_t* keys, int* vals) {
+// round 0 of the sort: (cell, z)
+__global__ void key_kernel(Grid G, const double* __restrict__ pos_all, uint64_t* keys, int* vals) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= G.R * G.n) return;
     const int r = t / G.n;
     const double* p = pos_all + 3 * (size_t)t;
     float xw[3];
     int img[3];
-    keys[t] = nbl::atom_key(G, r, p[0], p[1], p[2], xw, img);
+    const uint32_t g = nbl::atom_cell(G, r, p[0], p[1], p[2], xw, img);
+    keys[t] = nbl::make_key(g, 0u, nbl::coord_bits(G, xw[2], 2));
     vals[t] = t;
 }
 
-__global__ void cell_bounds_kernel(int total, const uint32_t* __restrict__ keys_sorted,
+// rounds 1 and 2: bucket of the previous split + the next coordinate (y, then x)
+__global__ void refine_key_kernel(Grid G, int level, int total, const double* __restrict__ pos_all,
+                                  const uint64_t* __restrict__ keys_sorted, const int* __restrict__ vals_sorted,
+                                  const int* __restrict__ cell_first, const int* __restrict__ cell_count,
+                                  uint64_t* keys, int* vals) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const uint64_t k = keys_sorted[p];
+    const uint32_t c = (uint32_t)(k >> nbl::kSubBits);
+    const int ga = vals_sorted[p];
+    const uint32_t b = nbl::kd_bucket(level, p, cell_first[c], cell_count[c], (uint32_t)(k >> 32) & 3u);
+    const double* q = pos_all + 3 * (size_t)ga;
+    float xw[3];
+    int img[3];
+    nbl::atom_cell(G, ga / G.n, q[0], q[1], q[2], xw, img);
+    const int d = level == 1 ? 1 : 0;
+    keys[p] = nbl::make_key(c, b, nbl::coord_bits(G, xw[d], d));
+    vals[p] = ga;
+}
+
+__global__ void cell_bounds_kernel(int total, const uint64_t* __restrict__ keys_sorted,
                                    int* cell_first, int* cell_count) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= total) return;
-    const uint32_t c = keys_sorted[k] >> nbl::kSubBits;
-    if (k == 0 || (keys_sorted[k - 1] >> nbl::kSubBits) != c) cell_first[c] = k;
-    if (k == total - 1 || (keys_sorted[k + 1] >> nbl::kSubBits) != c) {
+    const uint32_t c = (uint32_t)(keys_sorted[k] >> nbl::kSubBits);
+    if (k == 0 || (uint32_t)(keys_sorted[k - 1] >> nbl::kSubBits) != c) cell_first[c] = k;
+    if (k == total - 1 || (uint32_t)(keys_sorted[k + 1] >> nbl::kSubBits) != c) {
         // the matching "first" is written by another thread of this launch; store the end and
         // let the next kernel subtract
         cell_count[c] = k + 1;
@@ -141,20 +163,20 @@ __global__ void cell_sizes_kernel(int ncells, const int* __restrict__ cell_first
 }
 
 __global__ void fill_slots_kernel(Grid G, Topology T, int total, const double* __restrict__ pos_all,
-                                  const uint32_t* __restrict__ keys_sorted,
+                                  const uint64_t* __restrict__ keys_sorted,
                                   const int* __restrict__ vals_sorted,
                                   const int* __restrict__ cell_first, const int* __restrict__ cell_slot,
                                   float4* posq, float2* par, int* atom, int* img, int* slot_of) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= total) return;
-    const uint32_t c = keys_sorted[k] >> nbl::kSubBits;
+    const uint32_t c = (uint32_t)(keys_sorted[k] >> nbl::kSubBits);
     const int ga = vals_sorted[k];
     const int r = ga / G.n, a = ga - r * G.n;
     const int slot = cell_slot[c] + (k - cell_first[c]);
     const double* p = pos_all + 3 * (size_t)ga;
     float xw[3];
     int im[3];
-    nbl::atom_key(G, r, p[0], p[1], p[2], xw, im);
+    nbl::atom_cell(G, r, p[0], p[1], p[2], xw, im);
     const float4 pf = T.parf[a];
     posq[slot] = make_float4(xw[0], xw[1], xw[2], pf.x);
     par[slot] = make_float2(pf.y, pf.z);
@@ -472,16 +494,26 @@ static int build_list(sdm_ctx* c) {
     const int ncells = pl->ncells;
     const int noff = G.span * G.span * G.span;
 
+    // sort by (cell, z); the cell extents found here stay valid for the two refinement rounds
+    int cell_bits = 1;
+    while ((1ll << cell_bits) < ncells) cell_bits++;
+    const int key_end = std::min(nbl::kSubBits + cell_bits + 1, 64);
     key_kernel<<<blocks(total), 256, 0, s>>>(G, c->d_pos, pl->keys, pl->vals);
-    int key_bits = nbl::kSubBits;
-    while ((1ll << (key_bits - nbl::kSubBits)) < ncells) key_bits++;
     PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->keys, pl->keys_sorted,
-                                            pl->vals, pl->vals_sorted, total, 0, std::min(key_bits + 1, 32), s));
+                                            pl->vals, pl->vals_sorted, total, 0, key_end, s));
     PL_CUDA(cudaMemsetAsync(pl->cell_count, 0, sizeof(int) * (size_t)(ncells + 1), s));
     PL_CUDA(cudaMemsetAsync(pl->cell_first, 0, sizeof(int) * (size_t)(ncells + 1), s));
     cell_bounds_kernel<<<blocks(total), 256, 0, s>>>(total, pl->keys_sorted, pl->cell_first, pl->cell_count);
     cell_sizes_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_first, pl->cell_count,
                                                     pl->cell_pcount, pl->cell_nsci);
+    // kd refinement inside every cell: by y within the z halves, by x within the y halves
+    for (int level = 1; level <= 2; level++) {
+        refine_key_kernel<<<blocks(total), 256, 0, s>>>(G, level, total, c->d_pos, pl->keys_sorted, pl->vals_sorted,
+                                                       pl->cell_first, pl->cell_count, pl->keys, pl->vals);
+        PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->keys, pl->keys_sorted,
+                                                pl->vals, pl->vals_sorted, total, 0, key_end, s));
+    }
+    c->launches += 4;
     // exclusive scans over ncells+1 elements (the extra zero element yields the totals)
     PL_CUDA(cudaMemsetAsync(pl->cell_pcount + ncells, 0, sizeof(int), s));
     PL_CUDA(cudaMemsetAsync(pl->cell_nsci + ncells, 0, sizeof(int), s));
@@ -719,7 +751,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     }
     {
         size_t a = 0, b = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, a, pl->keys, pl->keys_sorted, pl->vals, pl->vals_sorted, total, 0, 32, c->stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, a, pl->keys, pl->keys_sorted, pl->vals, pl->vals_sorted, total, 0, 64, c->stream);
         cub::DeviceScan::ExclusiveSum(nullptr, b, pl->item_count, pl->item_off, (int)std::max<size_t>(pl->items_cap, pl->raw_cap + 1), c->stream);
         pl->cub_tmp_bytes = std::max(a, b) + 256;
         A(pl_alloc(pl, (char**)&pl->cub_tmp, pl->cub_tmp_bytes));

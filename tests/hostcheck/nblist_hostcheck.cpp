@@ -62,13 +62,8 @@ bool setup_grid(Grid& G, int n, int R, bool periodic, double rlist, const double
 
 }  // namespace
 
-static const int* g_subkey = nullptr;  // experiment hook: per-atom in-cell rank replacing the Morton code
-
 extern "C" {
 
-void hostcheck_set_subkey(const int* k) { g_subkey = k; }
-static int* g_cell_out = nullptr;
-void hostcheck_set_cell_out(int* c) { g_cell_out = c; }
 
 // pos: [R][n][3] doubles.  excl: unique pairs a<b.  Returns the number of covered pairs of
 // replica `replica` (sorted (i<j) System indices written to out_pairs up to max_pairs), or <0.
@@ -97,30 +92,45 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     const int ncells = R * G.ncell;
     const int noff = G.span * G.span * G.span;
 
-    // keys + stable sort
-    std::vector<uint32_t> keys(total);
-    std::vector<int> vals(total);
+    // keys + three stable sorts: (cell, z), then kd refinement by y and by x (key_kernel,
+    // refine_key_kernel and the radix sorts of pairlist.cu)
+    std::vector<uint64_t> keys(total), ks(total);
+    std::vector<int> vals(total), vs(total);
+    auto wrapped = [&](int ga, float* xw) {
+        int im[3];
+        return atom_cell(G, ga / n, pos[3 * (size_t)ga], pos[3 * (size_t)ga + 1], pos[3 * (size_t)ga + 2], xw, im);
+    };
     for (int t = 0; t < total; t++) {
         float xw[3];
-        int im[3];
-        keys[t] = atom_key(G, t / n, pos[3 * (size_t)t], pos[3 * (size_t)t + 1], pos[3 * (size_t)t + 2], xw, im);
-        if (g_subkey) keys[t] = (keys[t] & ~((1u << kSubBits) - 1u)) | (uint32_t)(g_subkey[t] & ((1 << kSubBits) - 1));
+        const uint32_t g = wrapped(t, xw);
+        keys[t] = make_key(g, 0u, coord_bits(G, xw[2], 2));
         vals[t] = t;
-        if (g_cell_out) g_cell_out[t] = (int)(keys[t] >> kSubBits);
     }
-    std::vector<int> order(total);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
-    std::vector<uint32_t> ks(total);
-    std::vector<int> vs(total);
-    for (int k = 0; k < total; k++) { ks[k] = keys[order[k]]; vs[k] = vals[order[k]]; }
-
+    auto sort_pairs = [&]() {
+        std::vector<int> order(total);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+        for (int k = 0; k < total; k++) { ks[k] = keys[order[k]]; vs[k] = vals[order[k]]; }
+    };
+    sort_pairs();
     // cells
     std::vector<int> cell_first(ncells + 1, 0), cell_count(ncells + 1, 0), cell_slot(ncells + 2, 0), cell_sci(ncells + 2, 0);
     for (int k = 0; k < total; k++) {
-        uint32_t c = ks[k] >> kSubBits;
-        if (k == 0 || (ks[k - 1] >> kSubBits) != c) cell_first[c] = k;
+        uint32_t c = (uint32_t)(ks[k] >> kSubBits);
+        if (k == 0 || (uint32_t)(ks[k - 1] >> kSubBits) != c) cell_first[c] = k;
         cell_count[c]++;
+    }
+    for (int level = 1; level <= 2; level++) {
+        for (int p = 0; p < total; p++) {
+            const uint32_t c = (uint32_t)(ks[p] >> kSubBits);
+            const uint32_t b = kd_bucket(level, p, cell_first[c], cell_count[c], (uint32_t)(ks[p] >> 32) & 3u);
+            float xw[3];
+            wrapped(vs[p], xw);
+            const int d = level == 1 ? 1 : 0;
+            keys[p] = make_key(c, b, coord_bits(G, xw[d], d));
+            vals[p] = vs[p];
+        }
+        sort_pairs();
     }
     int nslot = 0, nsci = 0;
     for (int c = 0; c < ncells; c++) {
@@ -140,12 +150,12 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     std::vector<double> posw(3 * (size_t)nslot, 0.0);  // wrapped double coordinates per slot
     for (int s = 0; s < nslot; s++) { posq[4 * (size_t)s] = posq[4 * (size_t)s + 1] = posq[4 * (size_t)s + 2] = kFar; }
     for (int k = 0; k < total; k++) {
-        uint32_t c = ks[k] >> kSubBits;
+        uint32_t c = (uint32_t)(ks[k] >> kSubBits);
         int ga = vs[k];
         int slot = cell_slot[c] + (k - cell_first[c]);
         float xw[3];
         int im[3];
-        atom_key(G, ga / n, pos[3 * (size_t)ga], pos[3 * (size_t)ga + 1], pos[3 * (size_t)ga + 2], xw, im);
+        atom_cell(G, ga / n, pos[3 * (size_t)ga], pos[3 * (size_t)ga + 1], pos[3 * (size_t)ga + 2], xw, im);
         for (int d = 0; d < 3; d++) {
             posq[4 * (size_t)slot + d] = xw[d];
             posw[3 * (size_t)slot + d] = pos[3 * (size_t)ga + d] + (periodic ? im[d] * box[d] : 0.0);
