@@ -30,6 +30,8 @@
 // Arithmetic restated from OpenMM 7.3 ReferenceLJCoulombIxn::calculateOneIxn (SURVEY.md
 // Appendix B.3) in FP32: per-atom sigma/2 and 2*sqrt(eps), charges pre-scaled by
 // sqrt(ONE_4PI_EPS0), reaction field krf/crf, LJ not shifted.
+#include <algorithm>
+
 #include "f32x2.cuh"
 #include "pairlist.h"
 
@@ -226,23 +228,14 @@ __device__ __forceinline__ void entry_tiles(const uint32_t imask, const uint32_t
     }
 }
 
+// One work unit (see the header comment).  s_ip: this warp's staging area, s_shift: the block's
+// table of periodic shift vectors.
 template <bool PERIODIC, bool EXACT>
-__global__ void __launch_bounds__(kWarps * 32, SDM_PAIR_MINB)
-pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
-                    const double* __restrict__ pos_all, long long* __restrict__ f1acc,
-                    double* __restrict__ epart, long long* __restrict__ cpart) {
-    __shared__ IPair s_ip[kWarps][kIRows];
-    __shared__ float4 s_shift[64];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (PERIODIC) {
-        for (uint32_t code = threadIdx.x; code < 64; code += kWarps * 32)
-            s_shift[code] = make_float4((float)nbl::shift_x(code) * T.boxf[0],
-                                        (float)nbl::shift_y(code) * T.boxf[1],
-                                        (float)nbl::shift_z(code) * T.boxf[2], 0.f);
-        __syncthreads();
-    }
-    const int unit = blockIdx.x * kWarps + warp;
-    if (unit >= V.nunits) return;  // warp-uniform; no block-level barrier below
+__device__ __forceinline__ void process_unit(const Topology& T, const PairListView& V,
+                                             const double* __restrict__ pos_all,
+                                             long long* __restrict__ f1acc, double* __restrict__ epart,
+                                             long long* __restrict__ cpart, const int unit,
+                                             const int lane, IPair* s_ip, const float4* s_shift) {
     const Unit u = V.units[unit];
     const nbl::SciDesc sd = V.sci[u.sci];
     const int ibase = sd.c0 * nbl::kClusterSize;
@@ -272,7 +265,7 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         ip.x = pk(p[0].x, p[1].x); ip.y = pk(p[0].y, p[1].y);
         ip.z = pk(p[0].z, p[1].z); ip.q = pk(p[0].w, p[1].w);
         ip.s = pk(pr[0].x, pr[1].x); ip.e = pk(pr[0].y, pr[1].y);
-        s_ip[warp][lane] = ip;
+        s_ip[lane] = ip;
     }
     __syncwarp();
 
@@ -312,10 +305,10 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         Acc2 fj{0ull, 0ull, 0ull};
         float tmin = 3.0e38f;
         if (midx == 0)
-            entry_tiles<false, EXACT>(imask, nullptr, lane, s_ip[warp], xj, pj, K, fi, fj, en, cnt, tmin);
+            entry_tiles<false, EXACT>(imask, nullptr, lane, s_ip, xj, pj, K, fi, fj, en, cnt, tmin);
         else
-            entry_tiles<true, EXACT>(imask, V.masks + (size_t)midx * nbl::kMaskWords, lane, s_ip[warp],
-                                     xj, pj, K, fi, fj, en, cnt, tmin);
+            entry_tiles<true, EXACT>(imask, V.masks + (size_t)midx * nbl::kMaskWords, lane, s_ip, xj, pj, K,
+                                     fi, fj, en, cnt, tmin);
         if (EXACT) {
             // entries with a pair inside the band are revisited after the loop (keeps the call
             // and its register pressure out of the hot loop)
@@ -394,8 +387,8 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
                 const float4 sh = s_shift[fx >> 26];
                 xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
             }
-            fix_band_pairs(T, V, pos_all, f1acc, s_ip[warp], ibase, js, xj, V.par[js], fy & 0xffu,
-                           fy >> 8, lane, &en_fix, &cnt_fix);
+            fix_band_pairs(T, V, pos_all, f1acc, s_ip, ibase, js, xj, V.par[js], fy & 0xffu, fy >> 8, lane,
+                           &en_fix, &cnt_fix);
         }
         en1 += en_fix;
         cnt += cnt_fix;
@@ -412,6 +405,37 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
     if (lane == 0) {
         epart[unit] = de;
         cpart[unit] = dc;
+    }
+    __syncwarp();   // the staging area is reused by the next unit of this warp
+}
+
+// Persistent kernel: the grid fills the machine once (register-limited number of resident warps)
+// and every warp draws units from a global counter until none is left.  Units differ a lot in
+// length (1..32 entries), so handing them out dynamically keeps all resident warps busy to the
+// end, and the shift table is built once per block instead of once per unit.  Which warp
+// computes which unit does not influence the result (fixed-point accumulation, per-unit energy
+// partials).
+template <bool PERIODIC, bool EXACT>
+__global__ void __launch_bounds__(kWarps * 32, SDM_PAIR_MINB)
+pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
+                    const double* __restrict__ pos_all, long long* __restrict__ f1acc,
+                    double* __restrict__ epart, long long* __restrict__ cpart, int* unit_counter) {
+    __shared__ IPair s_ip[kWarps][kIRows];
+    __shared__ float4 s_shift[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (PERIODIC) {
+        for (uint32_t code = threadIdx.x; code < 64; code += kWarps * 32)
+            s_shift[code] = make_float4((float)nbl::shift_x(code) * T.boxf[0],
+                                        (float)nbl::shift_y(code) * T.boxf[1],
+                                        (float)nbl::shift_z(code) * T.boxf[2], 0.f);
+        __syncthreads();
+    }
+    for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(unit_counter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= V.nunits) break;
+        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift);
     }
 }
 
@@ -508,12 +532,23 @@ refresh_kernel(Topology T, nbl::Grid G, int nslot, const double* __restrict__ po
 
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
-                         cudaStream_t s) {
+                         int* unit_counter, int num_sms, cudaStream_t s) {
     if (V.nunits <= 0) return;
-    const int grid = (V.nunits + kWarps - 1) / kWarps;
+    cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
-#define SDM_LAUNCH(P, X) \
-    pair_cluster_kernel<P, X><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart)
+#define SDM_LAUNCH(P, X)                                                                          \
+    do {                                                                                          \
+        static int resident = 0; /* blocks per SM the hardware keeps resident (register limited) */ \
+        if (!resident) {                                                                          \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_cluster_kernel<P, X>,  \
+                                                              kWarps * 32, 0) != cudaSuccess ||    \
+                resident < 1)                                                                     \
+                resident = SDM_PAIR_MINB;                                                         \
+        }                                                                                         \
+        const int grid = std::min((V.nunits + kWarps - 1) / kWarps, num_sms * resident);           \
+        pair_cluster_kernel<P, X><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
+                                                              unit_counter);                      \
+    } while (0)
     if (exact) {
         if (periodic) SDM_LAUNCH(true, true);
         else SDM_LAUNCH(false, true);

@@ -53,6 +53,7 @@ struct PairList {
     int *sci_nunits = nullptr, *sci_unit_off = nullptr;
     Unit* units = nullptr;
     int* part_off = nullptr;    // [R+1]
+    int* unit_counter = nullptr; // work counter of the persistent pair kernel
     double* epart = nullptr;
     long long* cpart = nullptr;
     double* minmax = nullptr;   // [6] non-periodic extent reduction
@@ -714,6 +715,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->sci_nunits, pl->nsci_cap + 1));
     A(pl_alloc(pl, &pl->sci_unit_off, pl->nsci_cap + 1));
     A(pl_alloc(pl, &pl->part_off, R + 1));
+    A(pl_alloc(pl, &pl->unit_counter, 1));
     A(pl_alloc(pl, &pl->minmax, 6));
     pl->items_cap = (size_t)pl->nsci_cap * 64 + 1;
     A(pl_alloc(pl, &pl->item_count, pl->items_cap));
@@ -824,7 +826,7 @@ int sdm_ctx_pairlist_eval(sdm_ctx* c) {
     // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
     launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart,
-                        c->opt.exact_cutoff, s);
+                        c->opt.exact_cutoff, pl->unit_counter, c->num_sms, s);
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[2], s));
     c->launches++;
     PL_CUDA(cudaGetLastError());

@@ -30,7 +30,7 @@ struct PairListView {
 
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
-                         cudaStream_t s);
+                         int* unit_counter, int num_sms, cudaStream_t s);
 // Debug / parity: dump the in-cutoff pairs of one replica exactly as the pair kernel decides them.
 void launch_pair_emit(const Topology& T, const PairListView& V, const double* pos_all, int exact,
                       int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
