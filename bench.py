@@ -120,7 +120,13 @@ def run_reference(args):
         return 0
     from oracle import oracle as O
     case, wname = load_case(args.workload)
-    nt = O.max_threads()
+    # all host threads the box offers: torchrun exports OMP_NUM_THREADS=1, which only describes
+    # its own default, so the affinity mask decides (the oracle takes an explicit thread count)
+    try:
+        nt = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nt = os.cpu_count() or 1
+    nt = max(nt, O.max_threads())
     from openmm_sdm_plugin_b200 import system as S
     al = S.AlchemicalState(**vars(case.alch))
     for _ in range(args.warmup):
@@ -144,6 +150,9 @@ def run_reference(args):
 
 
 def main():
+    # NCCL prints its version banner to stdout under NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
