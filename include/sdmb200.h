@@ -101,7 +101,9 @@ typedef struct {
     int32_t exact_cutoff;           /* 1: re-test pairs within 1 ulp-band of the cutoff in FP64 so
                                        the in-cutoff pair set is bit-identical to a double-precision
                                        evaluation (default 1) */
-    int32_t reserved[8];
+    int32_t use_graph;              /* 1: replay the per-eval kernel sequence of the cluster path as a
+                                       CUDA graph between list rebuilds (default 1) */
+    int32_t reserved[7];
 } sdm_options;
 
 /* Scalar state of LangevinIntegratorSDM that execute() reads

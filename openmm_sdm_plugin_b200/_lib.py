@@ -33,7 +33,8 @@ class SdmSystem(C.Structure):
 
 class SdmOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("pair_mode", C.c_int32), ("skin", C.c_double),
-                ("nstlist", C.c_int32), ("exact_cutoff", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("nstlist", C.c_int32), ("exact_cutoff", C.c_int32), ("use_graph", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
 
 
 class SdmAlch(C.Structure):

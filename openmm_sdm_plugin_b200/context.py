@@ -58,7 +58,7 @@ class PinnedArray:
 class SDMContext:
     def __init__(self, system: NonbondedSystem, displacement=None, n_replicas: int = 1,
                  pair_mode: int = _lib.PAIR_AUTO, device: int = -1, skin: float = -1.0,
-                 nstlist: int = 0, exact_cutoff: bool = True):
+                 nstlist: int = 0, exact_cutoff: bool = True, use_graph: bool = True):
         L = _lib.lib()
         self._L = L
         self.system = system
@@ -93,6 +93,7 @@ class SDMContext:
         o.skin = skin
         o.nstlist = nstlist
         o.exact_cutoff = int(exact_cutoff)
+        o.use_graph = int(use_graph)
         h = C.c_void_p()
         _lib.check(L.sdm_create(C.byref(s), C.byref(o), C.byref(h)))
         self._h = h

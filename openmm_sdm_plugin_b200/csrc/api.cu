@@ -152,6 +152,7 @@ void sdm_default_options(sdm_options* o) {
     o->skin = 0.06;
     o->nstlist = 20;
     o->exact_cutoff = 1;
+    o->use_graph = 1;
 }
 
 void sdm_default_alch(sdm_alch* a) {
@@ -344,6 +345,8 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     TRY(dev_alloc(c, &B.mcnt, (size_t)R * n * 2));
     TRY(dev_alloc(c, &B.state, (size_t)R));
     TRY(dev_alloc(c, &B.flags, (size_t)R));
+    TRY(dev_alloc(c, &c->d_list_age, 1));
+    B.list_age = c->d_list_age;
 
     c->h_alch.resize(R);
     c->h_eb.assign(R, 0.0);
@@ -376,6 +379,7 @@ void sdm_destroy(sdm_ctx* c) {
     sdm_ctx_free_pairlist(c);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (int k = 0; k < 4; k++)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -388,6 +392,7 @@ int sdm_set_stream(sdm_ctx* c, void* cuda_stream) {
     if (c->own_stream && c->stream) SDM_CUDA(cudaStreamDestroy(c->stream));
     c->own_stream = false;
     c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->graph_valid = false;
     return SDM_OK;
 }
 
@@ -476,6 +481,7 @@ int sdm_set_displacement(sdm_ctx* c, const double* displacement) {
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     if (int rc = upload_displacement(c, displacement)) return rc;
+    c->graph_valid = false;   // the number of displaced atoms sizes two launches
     return SDM_OK;
 }
 
@@ -485,48 +491,95 @@ int sdm_invalidate_list(sdm_ctx* c) {
     return SDM_OK;
 }
 
+// The kernels of one evaluation after the state-1 pair pass (shared by both pair modes).
+static int enqueue_tail(sdm_ctx* c, double e_scale, int c_div, int zero_acc) {
+    cudaStream_t s = c->stream;
+    const sdm::Topology& T = c->T;
+    sdm::EvalBuffers& B = c->B;
+    sdm::launch_ligand_env(T, B, s);   // resting atoms + the prefilter bitmap the probe kernel reads
+    if (T.n_lig > 0) { sdm::launch_ligand_probe(T, B, s); c->launches++; }
+    sdm::launch_exceptions(T, B, s);
+    sdm::launch_scalars(T, B, e_scale, c_div, s);
+    sdm::launch_mix(T, B, zero_acc, s);
+    c->launches += 4;
+    return SDM_OK;
+}
+
+static int ensure_hitbits(sdm_ctx* c) {
+    // prefilter bitmap of the displaced-atom kernels, grown on demand (never shrinks)
+    sdm::EvalBuffers& B = c->B;
+    B.scan_words = (B.scan_max + 31) / 32;
+    const size_t need = (size_t)c->R * std::max(c->T.n_lig, 1) * B.scan_words;
+    if (need > c->hitbits_cap) {
+        if (c->d_hitbits) {
+            SDM_CUDA(cudaStreamSynchronize(c->stream));
+            c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void*)c->d_hitbits), c->allocs.end());
+            SDM_CUDA(cudaFree(c->d_hitbits));
+            c->d_hitbits = nullptr;
+        }
+        c->hitbits_cap = need + need / 4;
+        if (int rc = dev_alloc(c, &c->d_hitbits, c->hitbits_cap)) return rc;
+        c->graph_valid = false;
+    }
+    B.hitbits = c->d_hitbits;
+    return SDM_OK;
+}
+
 int sdm_eval(sdm_ctx* c) {
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     cudaStream_t s = c->stream;
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;
-    if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[0], s));
-    double e_scale = 1.0;
-    int c_div = 1, zero_acc = 0;
     if (c->pair_mode == SDM_PAIR_ALLPAIRS) {
+        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[0], s));
+        if (int rc = ensure_hitbits(c)) return rc;
         sdm::launch_prep_posq(T, B, s);
         if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[1], s));
         sdm::launch_allpairs(T, B, c->opt.exact_cutoff, nullptr, nullptr, 0, -1, s);
         if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[2], s));
         c->launches += 2;
-        e_scale = 0.5;
-        c_div = 2;
+        if (int rc = enqueue_tail(c, 0.5, 2, 0)) return rc;
     } else {
-        if (int rc = sdm_ctx_pairlist_eval(c)) return rc;  // records ev[1], ev[2] around the pair kernel
-        zero_acc = 1;
-    }
-    {
-        // prefilter bitmap of the displaced-atom kernels, grown on demand (never shrinks)
-        B.scan_words = (B.scan_max + 31) / 32;
-        const size_t need = (size_t)c->R * std::max(T.n_lig, 1) * B.scan_words;
-        if (need > c->hitbits_cap) {
-            if (c->d_hitbits) {
-                SDM_CUDA(cudaStreamSynchronize(s));
-                c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void*)c->d_hitbits), c->allocs.end());
-                SDM_CUDA(cudaFree(c->d_hitbits));
-                c->d_hitbits = nullptr;
-            }
-            c->hitbits_cap = need + need / 4;
-            if (int rc = dev_alloc(c, &c->d_hitbits, c->hitbits_cap)) return rc;
+        // Between list rebuilds the kernel sequence is identical from one evaluation to the next
+        // (same grids, same pointers): it is captured once and replayed as a CUDA graph, which
+        // removes the per-launch CPU cost (8 launches per evaluation).
+        const bool graphable = c->opt.use_graph && !c->timing && s != nullptr &&
+                               !sdm_ctx_pairlist_rebuild_due(c);
+        if (graphable && c->graph_valid) {
+            SDM_CUDA(cudaGraphLaunch(c->graph_exec, s));
+            c->list_age++;
+            c->launches += c->graph_launches;
+            c->timing_valid = false;
+            c->n_evals++;
+            return SDM_OK;
         }
-        B.hitbits = c->d_hitbits;
+        if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[0], s));
+        bool capturing = false;
+        int64_t launches0 = c->launches;
+        if (graphable) {
+            if (int rc = ensure_hitbits(c)) return rc;
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) capturing = true;
+            else cudaGetLastError();
+        }
+        int rc = sdm_ctx_pairlist_eval(c);  // records ev[1], ev[2] around the pair kernel when timing
+        if (!rc && !capturing) rc = ensure_hitbits(c);
+        if (!rc) rc = enqueue_tail(c, 1.0, 1, 1);
+        if (capturing) {
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(s, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess || !g) return fail(SDM_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(SDM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            c->graph_valid = true;
+            c->graph_launches = (int)(c->launches - launches0);
+            SDM_CUDA(cudaGraphLaunch(c->graph_exec, s));
+        } else if (rc) {
+            return rc;
+        }
     }
-    sdm::launch_ligand_env(T, B, s);   // resting atoms + the prefilter bitmap the probe kernel reads
-    if (T.n_lig > 0) { sdm::launch_ligand_probe(T, B, s); c->launches++; }
-    sdm::launch_exceptions(T, B, s);
-    sdm::launch_scalars(T, B, e_scale, c_div, c->list_age, s);
-    sdm::launch_mix(T, B, zero_acc, s);
-    c->launches += 4;
     if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[3], s));
     c->timing_valid = c->timing;
     SDM_CUDA(cudaGetLastError());
@@ -639,6 +692,7 @@ int sdm_set_timing(sdm_ctx* c, int enabled) {
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     c->timing = enabled != 0;
     c->timing_valid = false;
+    c->graph_valid = false;
     return SDM_OK;
 }
 

@@ -506,8 +506,9 @@ __global__ void __launch_bounds__(256)
 refresh_kernel(Topology T, nbl::Grid G, int nslot, const double* __restrict__ pos_all,
                const int* __restrict__ atom, const int* __restrict__ img,
                const float4* __restrict__ posq_build, float4* __restrict__ posq, float half_skin2,
-               int* flags) {
+               int* flags, int* list_age) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) *list_age += 1;   // one more evaluation with this list (read by the scalar stage)
     if (s >= nslot) return;
     const int ga = atom[s];
     if (ga < 0) return;  // dummy slot keeps its far-away coordinates
@@ -572,10 +573,10 @@ void launch_pair_emit(const Topology& T, const PairListView& V, const double* po
 
 void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq,
-                    float half_skin2, int* flags, cudaStream_t s) {
+                    float half_skin2, int* flags, int* list_age, cudaStream_t s) {
     if (nslot <= 0) return;
     refresh_kernel<<<(nslot + 255) / 256, 256, 0, s>>>(T, G, nslot, pos_all, atom, img, posq_build,
-                                                      posq, half_skin2, flags);
+                                                      posq, half_skin2, flags, list_age);
 }
 
 }  // namespace sdm

@@ -615,7 +615,7 @@ __device__ double strided_sum(const double* v, int n, double* smem) {
 }
 
 __global__ void __launch_bounds__(256)
-scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div, int list_age) {
+scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div) {
     __shared__ double s_red[32];
     __shared__ long long s_redl[32];
     const int r = blockIdx.x;
@@ -646,7 +646,7 @@ scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div, int list_ag
         sc->n_pairs1 = c / c_div;
         sc->n_moved1 = m1 / 2;
         sc->n_moved2 = m2 / 2;
-        sc->list_age = list_age;
+        sc->list_age = *B.list_age;
         // sc->Eb was stored by sdm_set_bonded_forces
         execute_scalars(&st->alch, sc);
     }
@@ -719,8 +719,8 @@ void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) 
 }
 
 void launch_scalars(const Topology& T, const EvalBuffers& B, double e_scale, int c_div,
-                    int list_age, cudaStream_t s) {
-    scalars_kernel<<<B.R, 256, 0, s>>>(T, B, e_scale, c_div, list_age);
+                    cudaStream_t s) {
+    scalars_kernel<<<B.R, 256, 0, s>>>(T, B, e_scale, c_div);
 }
 
 void launch_mix(const Topology& T, const EvalBuffers& B, int zero_acc, cudaStream_t s) {

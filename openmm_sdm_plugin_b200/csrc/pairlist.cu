@@ -649,9 +649,14 @@ static int build_list(sdm_ctx* c) {
 
     // the fixed-point accumulators are indexed by slot: start from zero for the new layout
     PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
+    {
+        static const int one = 1;   // this evaluation is the first one with the new list
+        PL_CUDA(cudaMemcpyAsync(c->d_list_age, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    }
     c->list_valid = true;
     c->list_age = 0;
     c->n_builds++;
+    c->graph_valid = false;   // list arrays may have moved
     return SDM_OK;
 }
 
@@ -799,17 +804,21 @@ static PairListView make_view(const sdm_ctx* c) {
     return V;
 }
 
+bool sdm_ctx_pairlist_rebuild_due(const sdm_ctx* c) {
+    return !c->list_valid || c->list_age >= c->opt.nstlist;
+}
+
 int sdm_ctx_pairlist_eval(sdm_ctx* c) {
     PairList* pl = c->pl;
     if (!pl) return sdm_fail(SDM_ERR_INVALID, "cluster pair list not initialised");
     cudaStream_t s = c->stream;
-    const bool rebuild = !c->list_valid || c->list_age >= c->opt.nstlist;
+    const bool rebuild = sdm_ctx_pairlist_rebuild_due(c);
     if (rebuild) {
         if (int rc = build_list(c)) return rc;
     } else {
         const float hs = 0.5f * (float)c->opt.skin;
         launch_refresh(c->T, pl->G, pl->nslot, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq,
-                       hs * hs, c->B.flags, s);
+                       hs * hs, c->B.flags, c->d_list_age, s);
         c->launches++;
     }
     c->list_age++;

@@ -40,6 +40,6 @@ void launch_pair_emit(const Topology& T, const PairListView& V, const double* po
 // image as at build time) + staleness check against the build-time positions.
 void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq,
-                    float half_skin2, int* flags, cudaStream_t s);
+                    float half_skin2, int* flags, int* list_age, cudaStream_t s);
 
 }  // namespace sdm

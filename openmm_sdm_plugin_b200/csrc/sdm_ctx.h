@@ -40,6 +40,12 @@ struct sdm_ctx {
     int list_age = 0;
     int64_t n_builds = 0;
 
+    // CUDA graph of the per-eval kernel sequence (cluster path, between list rebuilds)
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_valid = false;
+    int graph_launches = 0;             // kernels inside the captured sequence
+    int* d_list_age = nullptr;          // evals since the list was built, kept on the device
+
     int64_t launches = 0;
     int64_t n_evals = 0;
     bool timing = false, timing_valid = false;
@@ -52,6 +58,7 @@ int sdm_fail(int code, const char* msg);
 // pairlist.cu -- cluster-pair list path (SDM_PAIR_CLUSTER)
 int sdm_ctx_init_pairlist(sdm_ctx* c);
 void sdm_ctx_free_pairlist(sdm_ctx* c);
+bool sdm_ctx_pairlist_rebuild_due(const sdm_ctx* c);
 int sdm_ctx_pairlist_eval(sdm_ctx* c);   // (re)build if due, refresh sorted positions, pair kernel
 int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap);
 int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value);

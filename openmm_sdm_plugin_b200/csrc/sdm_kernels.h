@@ -39,6 +39,7 @@ struct EvalBuffers {
     int scan_max;            // upper bound of a replica's scan length (grid sizing)
     uint32_t* hitbits;       // [R][n_lig][scan_words] prefilter hits: bit b of word w = scan index 32*w+b
     int scan_words;          // words per (replica, displaced atom) row = ceil(scan_max / 32)
+    int* list_age;           // device: evals since the cluster-pair list was built (0: no list)
 };
 
 // ---- fused path, v0 (all-pairs tiles, System order) ------------------------------------------
@@ -56,7 +57,7 @@ int exceptions_num_blocks(int n_exceptions);
 // e_scale / c_div: 0.5 / 2 when every pair was visited from both sides (all-pairs), 1 / 1 for a
 // half list.
 void launch_scalars(const Topology& T, const EvalBuffers& B, double e_scale, int c_div,
-                    int list_age, cudaStream_t s);
+                    cudaStream_t s);
 void launch_mix(const Topology& T, const EvalBuffers& B, int zero_acc, cudaStream_t s);
 
 // ---- literal kernel-interface operations (float4 device buffers) ------------------------------
