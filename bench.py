@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--skin", type=float, default=0.06)
     ap.add_argument("--pair-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-lambda", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -321,7 +322,7 @@ def main():
                     "ms_per_step": 1e3 * e2e_t / args.steps},
             "clocks": sampler.result(), "wall_s_resident_leg": wall_resident}
 
-    if rank == 0 and R > 1:
+    if rank == 0 and R > 1 and not args.no_single_lambda:
         # BASELINE.json configs[1] is quoted for a single lambda on one B200: the same workload
         # with ONE resident replica (latency bound: 8 kernels of ~20k atoms per evaluation)
         with SDMContext(case.system, case.displacement, n_replicas=1, pair_mode=args.pair_mode, device=local,

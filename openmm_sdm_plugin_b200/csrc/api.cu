@@ -496,8 +496,13 @@ static int enqueue_tail(sdm_ctx* c, double e_scale, int c_div, int zero_acc) {
     cudaStream_t s = c->stream;
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;
-    sdm::launch_ligand_env(T, B, s);   // resting atoms + the prefilter bitmap the probe kernel reads
-    if (T.n_lig > 0) { sdm::launch_ligand_probe(T, B, s); c->launches++; }
+    // displaced atoms: FP32 prefilter bitmap -> FP64 pair terms (once per pair) -> per-atom gather
+    if (T.n_lig > 0) {
+        sdm::launch_ligand_filter(T, B, s);
+        sdm::launch_ligand_probe(T, B, s);
+        c->launches += 2;
+    }
+    sdm::launch_ligand_gather(T, B, s);
     sdm::launch_exceptions(T, B, s);
     sdm::launch_scalars(T, B, e_scale, c_div, s);
     sdm::launch_mix(T, B, zero_acc, s);
@@ -505,23 +510,50 @@ static int enqueue_tail(sdm_ctx* c, double e_scale, int c_div, int zero_acc) {
     return SDM_OK;
 }
 
+// Scratch of the displaced-atom kernels, grown on demand (never shrinks): the prefilter bitmap,
+// its per-word prefix counts and the per-hit pair forces.
+static int regrow_bytes(sdm_ctx* c, void** p, size_t bytes) {
+    if (*p) {
+        SDM_CUDA(cudaStreamSynchronize(c->stream));
+        c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), *p), c->allocs.end());
+        SDM_CUDA(cudaFree(*p));
+        *p = nullptr;
+    }
+    c->graph_valid = false;
+    SDM_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    SDM_CUDA(cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+    c->allocs.push_back(*p);
+    return SDM_OK;
+}
+
 static int ensure_hitbits(sdm_ctx* c) {
-    // prefilter bitmap of the displaced-atom kernels, grown on demand (never shrinks)
     sdm::EvalBuffers& B = c->B;
+    const sdm::Topology& T = c->T;
     B.scan_words = (B.scan_max + 31) / 32;
-    const size_t need = (size_t)c->R * std::max(c->T.n_lig, 1) * B.scan_words;
+    const size_t rows = (size_t)c->R * std::max(T.n_lig, 1);
+    const size_t need = rows * B.scan_words;
     if (need > c->hitbits_cap) {
-        if (c->d_hitbits) {
-            SDM_CUDA(cudaStreamSynchronize(c->stream));
-            c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void*)c->d_hitbits), c->allocs.end());
-            SDM_CUDA(cudaFree(c->d_hitbits));
-            c->d_hitbits = nullptr;
-        }
         c->hitbits_cap = need + need / 4;
-        if (int rc = dev_alloc(c, &c->d_hitbits, c->hitbits_cap)) return rc;
-        c->graph_valid = false;
+        if (int rc = regrow_bytes(c, (void**)&c->d_hitbits, c->hitbits_cap * sizeof(uint32_t))) return rc;
+        if (int rc = regrow_bytes(c, (void**)&c->d_hitpre, c->hitbits_cap * sizeof(int))) return rc;
+    }
+    // hits per row: atoms within the cutoff of a displaced atom in either state, at up to ~2x
+    // liquid-water number density; everything when there is no cutoff
+    int cap = c->n;
+    if (T.method != SDM_NOCUTOFF) {
+        const double r = T.rc + 0.05;
+        cap = (int)std::min<double>(c->n, 2.0 * 4.19 * r * r * r * 200.0 + 64.0);
+    }
+    cap = std::max(cap, 32);
+    const size_t need_f = rows * (size_t)cap * 3;
+    if (need_f > c->pairf_alloc) {
+        c->pairf_alloc = need_f;
+        if (int rc = regrow_bytes(c, (void**)&c->d_pairf, c->pairf_alloc * sizeof(double))) return rc;
     }
     B.hitbits = c->d_hitbits;
+    B.hitpre = c->d_hitpre;
+    B.pairf = c->d_pairf;
+    B.pairf_cap = cap;
     return SDM_OK;
 }
 

@@ -255,33 +255,29 @@ __device__ __forceinline__ void scan_range(const Topology& T, const EvalBuffers&
     }
 }
 
-// ---- env kernel ---------------------------------------------------------------------------------
-// One thread per scan index (a NON-displaced atom j); loops over the displaced atoms (staged in
-// shared memory in groups of 8 with a bounding sphere per state) and accumulates
-// dF_j = sum_i f_j(state 2) - f_j(state 1).  Writes every dF_j (zero when nothing is near), so no
-// memset is needed, and the prefilter bitmap hitbits[r][m][w] (bit = lane) that the probe kernel
-// consumes.  The warps of a block take scan positions that are a whole grid apart: the few warps
-// that sit next to the displaced atoms (and do all the FP64 work) end up on different SMs.
-struct Probe {
-    double x1, y1, z1, x2, y2, z2, q, hsig, heps;
+// ---- filter kernel -------------------------------------------------------------------------------
+// One thread per scan index (a NON-displaced atom j).  FP32 only: tests j against the displaced
+// atoms (staged in shared memory in groups of 8 with a bounding sphere per state) and writes the
+// prefilter bitmap hitbits[r][m][w] (bit = lane) -- every word of every row, zero when nothing is
+// near.  No forces are computed here.
+struct ProbeF {
     float fx1, fy1, fz1, fx2, fy2, fz2;
-    int idx, flags;
 };
 
-constexpr int kEnvThreads = 128;
+constexpr int kFilterThreads = 128;
 constexpr int kProbeChunk = 64;   // displaced atoms staged per pass
 constexpr int kProbeGroup = 8;    // displaced atoms per bounding sphere
 
-__global__ void __launch_bounds__(kEnvThreads)
-ligand_env_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
-    __shared__ Probe s_p[kProbeChunk];
+__global__ void __launch_bounds__(kFilterThreads)
+ligand_filter_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
+    __shared__ ProbeF s_p[kProbeChunk];
     __shared__ float4 s_sph[kProbeChunk / kProbeGroup][2];   // (center, (radius + r_lim)^2) per state
     const int n = T.n, r = blockIdx.y;
     const double* pos = B.pos + (size_t)r * 3 * n;
     int begin, end;
     scan_range(T, B, r, &begin, &end);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sw = warp * gridDim.x + blockIdx.x;   // scan word (32 scan indices) of this warp
+    const int sw = blockIdx.x * (kFilterThreads / 32) + warp;   // scan word (32 scan indices) of this warp
     const int idx = begin + sw * 32 + lane;
     int j = -1;
     if (idx < end) {
@@ -297,34 +293,26 @@ ligand_env_kernel(const __grid_constant__ Topology T, const __grid_constant__ Ev
     const float lim = T.rc2f * 1.0001f + 1.0e-4f;
     const float rlim = sqrtf(lim);
     const float3 hbox = make_float3(0.5f * T.boxf[0], 0.5f * T.boxf[1], 0.5f * T.boxf[2]);
-    double xj = 0, yj = 0, zj = 0, qj = 0, hsj = 0, hej = 0;
-    float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        xj = pos[3 * j]; yj = pos[3 * j + 1]; zj = pos[3 * j + 2];
-        qj = T.q[j]; hsj = T.hsig[j]; hej = T.heps[j];
-        pf = B.scan_posq[idx];
-    }
-    uint32_t* bits = B.hitbits + (size_t)r * T.n_lig * B.scan_words + sw;
+    const float4 pf = active ? B.scan_posq[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // layout [replica][scan word][displaced atom]: the words of one warp are contiguous
+    uint32_t* bits = B.hitbits + ((size_t)r * B.scan_words + sw) * T.n_lig;
     const bool store_bits = sw < B.scan_words;
-    double fx = 0, fy = 0, fz = 0;
     for (int m0 = 0; m0 < T.n_lig; m0 += kProbeChunk) {
         const int mc = min(kProbeChunk, T.n_lig - m0);
         __syncthreads();
         if (threadIdx.x < mc) {
             const int i = T.lig_idx[m0 + threadIdx.x];
-            Probe p;
-            p.x1 = pos[3 * i]; p.y1 = pos[3 * i + 1]; p.z1 = pos[3 * i + 2];
-            p.x2 = p.x1 + T.disp[3 * i]; p.y2 = p.y1 + T.disp[3 * i + 1]; p.z2 = p.z1 + T.disp[3 * i + 2];
+            const double x1 = pos[3 * i], y1 = pos[3 * i + 1], z1 = pos[3 * i + 2];
+            const double x2 = x1 + T.disp[3 * i], y2 = y1 + T.disp[3 * i + 1], z2 = z1 + T.disp[3 * i + 2];
+            ProbeF p;
             if (periodic) {
-                p.fx1 = wrap_into_box(p.x1, T.box[0], T.inv_box[0]); p.fx2 = wrap_into_box(p.x2, T.box[0], T.inv_box[0]);
-                p.fy1 = wrap_into_box(p.y1, T.box[1], T.inv_box[1]); p.fy2 = wrap_into_box(p.y2, T.box[1], T.inv_box[1]);
-                p.fz1 = wrap_into_box(p.z1, T.box[2], T.inv_box[2]); p.fz2 = wrap_into_box(p.z2, T.box[2], T.inv_box[2]);
+                p.fx1 = wrap_into_box(x1, T.box[0], T.inv_box[0]); p.fx2 = wrap_into_box(x2, T.box[0], T.inv_box[0]);
+                p.fy1 = wrap_into_box(y1, T.box[1], T.inv_box[1]); p.fy2 = wrap_into_box(y2, T.box[1], T.inv_box[1]);
+                p.fz1 = wrap_into_box(z1, T.box[2], T.inv_box[2]); p.fz2 = wrap_into_box(z2, T.box[2], T.inv_box[2]);
             } else {
-                p.fx1 = (float)p.x1; p.fy1 = (float)p.y1; p.fz1 = (float)p.z1;
-                p.fx2 = (float)p.x2; p.fy2 = (float)p.y2; p.fz2 = (float)p.z2;
+                p.fx1 = (float)x1; p.fy1 = (float)y1; p.fz1 = (float)z1;
+                p.fx2 = (float)x2; p.fy2 = (float)y2; p.fz2 = (float)z2;
             }
-            p.q = T.q[i]; p.hsig = T.hsig[i]; p.heps = T.heps[i];
-            p.idx = i; p.flags = T.lig_flags[m0 + threadIdx.x];
             s_p[threadIdx.x] = p;
         }
         __syncthreads();
@@ -332,11 +320,11 @@ ligand_env_kernel(const __grid_constant__ Topology T, const __grid_constant__ Ev
         if (threadIdx.x < 2 * ngroups) {
             // bounding sphere of one group of displaced atoms in one state, centred on its first atom
             const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
-            const Probe& c0 = s_p[g * kProbeGroup];
+            const ProbeF& c0 = s_p[g * kProbeGroup];
             const float cx = st ? c0.fx2 : c0.fx1, cy = st ? c0.fy2 : c0.fy1, cz = st ? c0.fz2 : c0.fz1;
             float rmax2 = 0.f;
             for (int k = g * kProbeGroup + 1; k < min(mc, (g + 1) * kProbeGroup); k++) {
-                const Probe& q = s_p[k];
+                const ProbeF& q = s_p[k];
                 const float4 o = make_float4(st ? q.fx2 : q.fx1, st ? q.fy2 : q.fy1, st ? q.fz2 : q.fz1, 0.f);
                 rmax2 = fmaxf(rmax2, r2_prefilter(T, hbox, cx, cy, cz, o));
             }
@@ -350,51 +338,29 @@ ligand_env_kernel(const __grid_constant__ Topology T, const __grid_constant__ Ev
                                          r2_prefilter(T, hbox, s2.x, s2.y, s2.z, pf) <= s2.w);
             const int mend = min(mc, (g + 1) * kProbeGroup);
             if (!__any_sync(0xffffffffu, near)) {
-                if (store_bits && lane < mend - g * kProbeGroup)
-                    bits[(size_t)(m0 + g * kProbeGroup + lane) * B.scan_words] = 0u;
+                if (store_bits && lane < mend - g * kProbeGroup) bits[m0 + g * kProbeGroup + lane] = 0u;
                 continue;
             }
             for (int m = g * kProbeGroup; m < mend; m++) {
-                const Probe& p = s_p[m];
+                const ProbeF& p = s_p[m];
                 const bool hit = near && (!cutoff || r2_prefilter(T, hbox, p.fx1, p.fy1, p.fz1, pf) <= lim ||
                                           r2_prefilter(T, hbox, p.fx2, p.fy2, p.fz2, pf) <= lim);
                 const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-                if (store_bits && lane == 0) bits[(size_t)(m0 + m) * B.scan_words] = ballot;
-                if (!hit) continue;
-                PairGeom g1 = geom(T, p.x1, p.y1, p.z1, xj, yj, zj);
-                PairGeom g2 = geom(T, p.x2, p.y2, p.z2, xj, yj, zj);
-                const bool in1 = !cutoff || g1.r2 <= T.rc2;
-                const bool in2 = !cutoff || g2.r2 <= T.rc2;
-                if (!(in1 || in2)) continue;
-                if ((p.flags & 1) && is_excluded(T, j, p.idx)) continue;
-                const double sig = p.hsig + hsj, eps = p.heps * hej;
-                const double qq = SDM_K_COULOMB * p.q * qj;
-                double e;
-                // d = x_i - x_j ; force on j is -fs*d
-                if (in1) {
-                    double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-                    fx += fs * g1.dx; fy += fs * g1.dy; fz += fs * g1.dz;
-                }
-                if (in2) {
-                    double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-                    fx -= fs * g2.dx; fy -= fs * g2.dy; fz -= fs * g2.dz;
-                }
+                if (store_bits && lane == 0) bits[m0 + m] = ballot;
             }
         }
-    }
-    if (active) {
-        double* dF = B.dF + (size_t)r * 3 * n;
-        dF[3 * j] = fx; dF[3 * j + 1] = fy; dF[3 * j + 2] = fz;
     }
 }
 
 // ---- probe kernel -------------------------------------------------------------------------------
-// One block per (displaced atom i, replica).  Reads row (r, m) of the prefilter bitmap written by
-// the env kernel, spreads its set bits densely over the threads (prefix sum of popcounts, then
-// hit h -> thread h mod 128) and evaluates those pairs in FP64 at state 1 and state 2:
+// One block per (displaced atom i, replica).  Reads row (r, m) of the prefilter bitmap, spreads
+// its set bits densely over the threads (prefix sum of popcounts, then hit h -> thread h mod 128)
+// and evaluates those pairs ONCE, in FP64, at state 1 and state 2:
 //     dF_i = sum_k f_i(state 2) - f_i(state 1),   u_i = sum_k w_k (e2 - e1),
 // w_k = 1/2 when k is displaced too (that pair is seen from k's block as well), else 1.  The
-// other displaced atoms (different displacement group) are walked directly.
+// opposite force of every hit, pairf[row][h] = -(f_i(2) - f_i(1)), and the per-word prefix counts
+// hitpre[row][w] are left for the gather kernel, which sums them per resting atom.  The other
+// displaced atoms (different displacement group) are walked directly.
 struct ProbeAcc {
     double fx, fy, fz, u;
     long long c1, c2;
@@ -405,9 +371,12 @@ struct ProbeAtom {
     double x1, y1, z1, x2, y2, z2, q, hsig, heps;
 };
 
-// Exact (FP64) dual-state term of the pair (displaced atom P, atom k) added to A.
+// Exact (FP64) dual-state term of the pair (displaced atom P, atom k) added to A; returns the
+// force difference on i, f_i(state 2) - f_i(state 1), in (px, py, pz).
 __device__ __forceinline__ void probe_pair(const Topology& T, const double* __restrict__ pos,
-                                           const ProbeAtom& P, int k, bool check_excl, ProbeAcc& A) {
+                                           const ProbeAtom& P, int k, bool check_excl, ProbeAcc& A,
+                                           double& px, double& py, double& pz) {
+    px = py = pz = 0.0;
     const int gk = T.group[k];
     if (gk == P.gi) return;  // same displacement (includes k == i): pair unchanged
     const bool cutoff = T.method != SDM_NOCUTOFF;
@@ -427,17 +396,18 @@ __device__ __forceinline__ void probe_pair(const Topology& T, const double* __re
     if (in1) {
         double e;
         double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-        A.fx -= fs * g1.dx; A.fy -= fs * g1.dy; A.fz -= fs * g1.dz;
+        px -= fs * g1.dx; py -= fs * g1.dy; pz -= fs * g1.dz;
         A.u -= w * e;
         A.c1 += wc;
     }
     if (in2) {
         double e;
         double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
-        A.fx += fs * g2.dx; A.fy += fs * g2.dy; A.fz += fs * g2.dz;
+        px += fs * g2.dx; py += fs * g2.dy; pz += fs * g2.dz;
         A.u += w * e;
         A.c2 += wc;
     }
+    A.fx += px; A.fy += py; A.fz += pz;
 }
 
 constexpr int kProbeThreads = 128;
@@ -462,9 +432,15 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
     P.q = T.q[P.i]; P.hsig = T.hsig[P.i]; P.heps = T.heps[P.i];
     int begin, end;
     scan_range(T, B, r, &begin, &end);
-    const uint32_t* bits = B.hitbits + ((size_t)r * T.n_lig + m) * B.scan_words;
+    const size_t row = (size_t)r * T.n_lig + m;
+    // bitmap and prefix layout [replica][scan word][displaced atom]: stride n_lig between words
+    const uint32_t* bits = B.hitbits + (size_t)r * B.scan_words * T.n_lig + m;
+    int* pre_out = B.hitpre + (size_t)r * B.scan_words * T.n_lig + m;
+    const size_t wstride = (size_t)T.n_lig;
+    double* pf_out = B.pairf + row * (size_t)B.pairf_cap * 3;
     const int nwords = min(B.scan_words, (end - begin + 31) / 32);
     ProbeAcc A{0, 0, 0, 0, 0, 0};
+    int row_base = 0;   // hits in the words already handled
 
     // (1) resting atoms named by the prefilter bitmap
     for (int w0 = 0; w0 < nwords; w0 += kProbeWords) {
@@ -475,7 +451,7 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         int run = 0;
         for (int k = 0; k < kRun; k++) {
             const int w = threadIdx.x * kRun + k;
-            const uint32_t v = w < nw ? bits[w0 + w] : 0u;
+            const uint32_t v = w < nw ? bits[(size_t)(w0 + w) * wstride] : 0u;
             s_bits[w] = v;
             run += __popc(v);
         }
@@ -495,6 +471,7 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         for (int k = 0; k < kRun; k++) {
             const int w = threadIdx.x * kRun + k;
             s_pre[w] = acc;
+            if (w < nw) pre_out[(size_t)(w0 + w) * wstride] = row_base + acc;
             acc += __popc(s_bits[w]);
         }
         if (threadIdx.x == kProbeThreads - 1) s_pre[kProbeWords] = acc;
@@ -511,11 +488,21 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
             const int idx = begin + (w0 + lo_) * 32 + bit;
             int k = idx - begin;
             if (B.scan_atom) k = B.scan_atom[idx] - r * n;
-            probe_pair(T, pos, P, k, (P.flags & 1) != 0, A);
+            double px, py, pz;
+            probe_pair(T, pos, P, k, (P.flags & 1) != 0, A, px, py, pz);
+            const int hg = row_base + h;
+            if (hg < B.pairf_cap) {
+                pf_out[3 * (size_t)hg] = -px; pf_out[3 * (size_t)hg + 1] = -py; pf_out[3 * (size_t)hg + 2] = -pz;
+            }
         }
+        row_base += total;
     }
+    if (row_base > B.pairf_cap && threadIdx.x == 0) atomicExch(B.flags + r, SDM_ERR_CAPACITY);
     // (2) the other displaced atoms (different displacement group), no prefilter
-    for (int mm = threadIdx.x; mm < T.n_lig; mm += kProbeThreads) probe_pair(T, pos, P, T.lig_idx[mm], true, A);
+    for (int mm = threadIdx.x; mm < T.n_lig; mm += kProbeThreads) {
+        double px, py, pz;
+        probe_pair(T, pos, P, T.lig_idx[mm], true, A, px, py, pz);
+    }
 
     double sx = block_sum(A.fx, s_red);
     double sy = block_sum(A.fy, s_red);
@@ -529,6 +516,56 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         B.upart[(size_t)r * T.n_lig + m] = su;
         B.mcnt[((size_t)r * T.n_lig + m) * 2] = sc1;
         B.mcnt[((size_t)r * T.n_lig + m) * 2 + 1] = sc2;
+    }
+}
+
+// ---- gather kernel -------------------------------------------------------------------------------
+// One thread per scan index (a NON-displaced atom j): dF_j = sum over the displaced atoms m (in
+// index order: fixed summation order) of the force the probe kernel stored for the pair, found
+// through the bitmap: h = hitpre[row][w] + popc(bits below this lane).  Pure loads; writes every
+// dF_j (zero when nothing is near), so no memset is needed.
+constexpr int kGatherThreads = 128;
+
+__global__ void __launch_bounds__(kGatherThreads)
+ligand_gather_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
+    const int n = T.n, r = blockIdx.y;
+    int begin, end;
+    scan_range(T, B, r, &begin, &end);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sw = blockIdx.x * (kGatherThreads / 32) + warp;
+    if (sw >= B.scan_words) return;
+    const int idx = begin + sw * 32 + lane;
+    int j = -1;
+    if (idx < end) {
+        j = idx - begin;
+        if (B.scan_atom) {
+            const int ga = B.scan_atom[idx];
+            j = ga < 0 ? -1 : ga - r * n;
+        }
+    }
+    const bool active = j >= 0 && T.group[j] == 0;
+    double fx = 0, fy = 0, fz = 0;
+    const uint32_t below = (1u << lane) - 1u;
+    const size_t wbase = ((size_t)r * B.scan_words + sw) * T.n_lig;
+    for (int m0 = 0; m0 < T.n_lig; m0 += 32) {
+        // the words of this warp for 32 displaced atoms: one coalesced load, most warps see zeros
+        const uint32_t mine = m0 + lane < T.n_lig ? B.hitbits[wbase + m0 + lane] : 0u;
+        unsigned todo = __ballot_sync(0xffffffffu, mine != 0u);
+        while (todo) {
+            const int ml = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t word = __shfl_sync(0xffffffffu, mine, ml);
+            if (!((word >> lane) & 1u)) continue;
+            const int m = m0 + ml;
+            const int h = B.hitpre[wbase + m] + __popc(word & below);
+            if (h >= B.pairf_cap) continue;   // overflow was flagged by the probe kernel
+            const double* f = B.pairf + (((size_t)r * T.n_lig + m) * (size_t)B.pairf_cap + h) * 3;
+            fx += f[0]; fy += f[1]; fz += f[2];
+        }
+    }
+    if (active) {
+        double* dF = B.dF + (size_t)r * 3 * n;
+        dF[3 * j] = fx; dF[3 * j + 1] = fy; dF[3 * j + 2] = fz;
     }
 }
 
@@ -608,31 +645,43 @@ exceptions_kernel(Topology T, const double* __restrict__ pos_all, long long* __r
 // runs SoftCoreF + bias + bookkeeping on the device -- no host round trip (the reference pays
 // three D->H energy reads per step).
 // ---------------------------------------------------------------------------------------------
-__device__ double strided_sum(const double* v, int n, double* smem) {
-    double t = 0.0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) t += v[k];
-    return block_sum(t, smem);
-}
-
 __global__ void __launch_bounds__(256)
 scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div) {
-    __shared__ double s_red[32];
-    __shared__ long long s_redl[32];
+    // all seven sums in ONE pass: independent loads in flight together, one barrier, fixed order
+    __shared__ double s_d[4][8];
+    __shared__ long long s_l[3][8];
     const int r = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p0 = B.part_off[r], np_ = B.part_off[r + 1] - p0;
-    double ep = strided_sum(B.epart + p0, np_, s_red);
-    double ee = strided_sum(B.eexc_part + (size_t)r * B.n_excpart, B.n_excpart, s_red);
-    double ue = strided_sum(B.uexc_part + (size_t)r * B.n_excpart, B.n_excpart, s_red);
-    double ul = strided_sum(B.upart + (size_t)r * T.n_lig, T.n_lig, s_red);
-    long long c = 0, m1 = 0, m2 = 0;
-    for (int k = threadIdx.x; k < np_; k += blockDim.x) c += B.cpart[p0 + k];
-    for (int k = threadIdx.x; k < T.n_lig; k += blockDim.x) {
-        m1 += B.mcnt[((size_t)r * T.n_lig + k) * 2];
-        m2 += B.mcnt[((size_t)r * T.n_lig + k) * 2 + 1];
+    const int nmax = max(np_, max(B.n_excpart, T.n_lig));
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    long long b0 = 0, b1 = 0, b2 = 0;
+    for (int k = threadIdx.x; k < nmax; k += blockDim.x) {
+        if (k < np_) { a0 += B.epart[p0 + k]; b0 += B.cpart[p0 + k]; }
+        if (k < B.n_excpart) {
+            a1 += B.eexc_part[(size_t)r * B.n_excpart + k];
+            a2 += B.uexc_part[(size_t)r * B.n_excpart + k];
+        }
+        if (k < T.n_lig) {
+            a3 += B.upart[(size_t)r * T.n_lig + k];
+            b1 += B.mcnt[((size_t)r * T.n_lig + k) * 2];
+            b2 += B.mcnt[((size_t)r * T.n_lig + k) * 2 + 1];
+        }
     }
-    c = block_sum_ll(c, s_redl);
-    m1 = block_sum_ll(m1, s_redl);
-    m2 = block_sum_ll(m2, s_redl);
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    b0 = warp_sum_ll(b0); b1 = warp_sum_ll(b1); b2 = warp_sum_ll(b2);
+    if (lane == 0) {
+        s_d[0][warp] = a0; s_d[1][warp] = a1; s_d[2][warp] = a2; s_d[3][warp] = a3;
+        s_l[0][warp] = b0; s_l[1][warp] = b1; s_l[2][warp] = b2;
+    }
+    __syncthreads();
+    double ep = 0.0, ee = 0.0, ue = 0.0, ul = 0.0;
+    long long c = 0, m1 = 0, m2 = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; w++) {
+            ep += s_d[0][w]; ee += s_d[1][w]; ue += s_d[2][w]; ul += s_d[3][w];
+            c += s_l[0][w]; m1 += s_l[1][w]; m2 += s_l[2][w];
+        }
     if (threadIdx.x == 0) {
         ReplicaState* st = B.state + r;
         sdm_scalars* sc = &st->sc;
@@ -707,10 +756,16 @@ void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s
     ligand_probe_kernel<<<grid, kProbeThreads, 0, s>>>(T, B);
 }
 
-void launch_ligand_env(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+void launch_ligand_filter(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
     // every scan word (32 scan indices) of a replica gets a warp: the bitmap rows are complete
-    dim3 grid((B.scan_words * 32 + kEnvThreads - 1) / kEnvThreads, B.R);
-    ligand_env_kernel<<<grid, kEnvThreads, 0, s>>>(T, B);
+    if (T.n_lig == 0) return;
+    dim3 grid((B.scan_words * 32 + kFilterThreads - 1) / kFilterThreads, B.R);
+    ligand_filter_kernel<<<grid, kFilterThreads, 0, s>>>(T, B);
+}
+
+void launch_ligand_gather(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+    dim3 grid((B.scan_words * 32 + kGatherThreads - 1) / kGatherThreads, B.R);
+    ligand_gather_kernel<<<grid, kGatherThreads, 0, s>>>(T, B);
 }
 
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) {

@@ -28,6 +28,9 @@ struct sdm_ctx {
     int* d_lig_flags = nullptr;
     uint32_t* d_hitbits = nullptr;      // displaced-atom prefilter bitmap (grown on demand)
     size_t hitbits_cap = 0;
+    int* d_hitpre = nullptr;
+    double* d_pairf = nullptr;
+    size_t pairf_alloc = 0;             // doubles allocated for d_pairf
 
     std::vector<sdm_alch> h_alch;       // staging copies with ctx lifetime
     std::vector<double> h_eb;

@@ -39,6 +39,9 @@ struct EvalBuffers {
     int scan_max;            // upper bound of a replica's scan length (grid sizing)
     uint32_t* hitbits;       // [R][n_lig][scan_words] prefilter hits: bit b of word w = scan index 32*w+b
     int scan_words;          // words per (replica, displaced atom) row = ceil(scan_max / 32)
+    int* hitpre;             // [R][n_lig][scan_words] hits of the row before word w (probe kernel)
+    double* pairf;           // [R][n_lig][pairf_cap][3] force on the resting atom of every hit
+    int pairf_cap;           // hits a row can hold
     int* list_age;           // device: evals since the cluster-pair list was built (0: no list)
 };
 
@@ -51,7 +54,8 @@ int allpairs_num_blocks(int n);
 
 // ---- fused path, shared stages ----------------------------------------------------------------
 void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s);
-void launch_ligand_env(const Topology& T, const EvalBuffers& B, cudaStream_t s);
+void launch_ligand_filter(const Topology& T, const EvalBuffers& B, cudaStream_t s);
+void launch_ligand_gather(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 int exceptions_num_blocks(int n_exceptions);
 // e_scale / c_div: 0.5 / 2 when every pair was visited from both sides (all-pairs), 1 / 1 for a
