@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--nstlist", type=int, default=20)
     ap.add_argument("--skin", type=float, default=0.06)
     ap.add_argument("--pair-mode", type=int, default=0)
+    ap.add_argument("--e2e-groups", type=int, default=1, help="replica groups (contexts/streams) of the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-lambda", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -263,10 +264,34 @@ def main():
     value = world * R * args.steps / (t_ms * 1e-3)
 
     # ---------------- end-to-end leg: host buffers in, host buffers out ---------------------
+    # The R replicas are driven as G independent contexts (replica groups) on G streams, the way
+    # a multi-replica driver uses the C ABI: per step and group, H2D of the positions (pinned),
+    # sdm_eval, D2H of forces + scalars; the copies of one group overlap the kernels of the
+    # others.  Every step moves all positions in and all forces out, inside the timed region.
+    G = max(1, min(args.e2e_groups, R))
+    while R % G:
+        G -= 1
+    Rg = R // G
+    g_streams = [torch.cuda.Stream() for _ in range(G)]
+    g_ctx = []
+    for g in range(G):
+        cg = SDMContext(case.system, case.displacement, n_replicas=Rg, pair_mode=args.pair_mode,
+                        device=local, skin=args.skin, nstlist=args.nstlist)
+        cg.set_stream(g_streams[g].cuda_stream)
+        for r in range(Rg):
+            cg.set_alchemical(r, states[(rank * R + g * Rg + r) % len(states)])
+        g_ctx.append(cg)
+
     def e2e_step(k):
-        ctx.set_positions_all(h_pos.array if k % 2 == 0 else h_pos_b.array)
-        ctx.eval()
-        s = ctx.read_results(h_f.array)
+        src = h_pos.array if k % 2 == 0 else h_pos_b.array
+        for g, cg in enumerate(g_ctx):
+            cg.set_positions_all(src[g * Rg:(g + 1) * Rg])
+            cg.eval()
+            cg.enqueue_results(h_f.array[g * Rg:(g + 1) * Rg])
+        s = []
+        for cg in g_ctx:
+            cg.synchronize()
+            s += cg.collect_scalars()
         exchange_gather(s)
         return s
 
@@ -284,6 +309,8 @@ def main():
         torch.cuda.synchronize()
         e2e_t += time.perf_counter() - t0
     assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
+    for cg in g_ctx:
+        cg.close()
     if world > 1:
         tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -319,7 +346,8 @@ def main():
             "ns_per_day_per_replica_upper_bound": value / (world * R) * 1e-6 * 86400,
             "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_t / args.steps},
+                    "ms_per_step": 1e3 * e2e_t / args.steps, "replica_groups": G,
+                    "note": "G contexts of R/G replicas on G streams; pinned host buffers; copies overlap kernels of other groups"},
             "clocks": sampler.result(), "wall_s_resident_leg": wall_resident}
 
     if rank == 0 and R > 1 and not args.no_single_lambda:

@@ -198,6 +198,13 @@ int sdm_forces_device_ptr(sdm_ctx* ctx, int replica, double** d_f);     /* hybri
 /* All replicas at once: hybrid forces into forces_all ([n_replicas][3*n_atoms], may be NULL) and
  * scalars into scalars_all ([n_replicas], may be NULL); two copies, one synchronisation. */
 int sdm_read_results(sdm_ctx* ctx, double* forces_all, sdm_scalars* scalars_all);
+/* The same in two halves, for callers that pipeline several contexts (replica groups) on
+ * separate streams so that the copies of one group overlap the kernels of another:
+ * sdm_enqueue_results() queues the device->host copies of the hybrid forces (into forces_all,
+ * ideally pinned; may be NULL) and of the scalar blocks behind the last sdm_eval() and returns
+ * at once; after sdm_synchronize(), sdm_collect_scalars() hands out the scalars that arrived. */
+int sdm_enqueue_results(sdm_ctx* ctx, double* forces_all);
+int sdm_collect_scalars(sdm_ctx* ctx, sdm_scalars* scalars_all);
 /* Debug / parity: the sorted in-cutoff non-excluded (i<j) pair list the pair kernel evaluated at
  * state 1, System particle indices.  pairs may be NULL to query *n only.  Synchronises. */
 int sdm_get_pairs(sdm_ctx* ctx, int replica, int32_t* pairs, int64_t max_pairs, int64_t* n);

@@ -78,6 +78,8 @@ SYMBOLS = {
     "sdm_positions_device_ptr": (_I, [_VP, _I, C.POINTER(_VP)]),
     "sdm_set_positions_all": (_I, [_VP, _VP]),
     "sdm_read_results": (_I, [_VP, _VP, _VP]),
+    "sdm_enqueue_results": (_I, [_VP, _VP]),
+    "sdm_collect_scalars": (_I, [_VP, _VP]),
     "sdm_set_bonded_forces": (_I, [_VP, _I, _VP, _D]),
     "sdm_set_alchemical": (_I, [_VP, _I, C.POINTER(SdmAlch)]),
     "sdm_get_alchemical": (_I, [_VP, _I, C.POINTER(SdmAlch)]),

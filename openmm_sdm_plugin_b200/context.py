@@ -146,6 +146,20 @@ class SDMContext:
             return None
         return [{k: getattr(s, k) for k, _ in _lib.SdmScalars._fields_} for s in sc]
 
+    def enqueue_results(self, forces_out: np.ndarray | None = None):
+        """Queue the device->host copies of forces (+ scalar blocks) behind the last eval(); no
+        synchronisation.  Pair with synchronize() and collect_scalars()."""
+        if forces_out is not None and (forces_out.dtype != np.float64 or not forces_out.flags.c_contiguous
+                                       or forces_out.size != 3 * self.n * self.R):
+            raise ValueError("forces_out must be C-contiguous float64 [n_replicas, n_atoms, 3]")
+        _lib.check(self._L.sdm_enqueue_results(self._h, _ptr(forces_out)))
+        self._keep_f = forces_out
+
+    def collect_scalars(self):
+        sc = (_lib.SdmScalars * self.R)()
+        _lib.check(self._L.sdm_collect_scalars(self._h, C.cast(sc, C.c_void_p)))
+        return [{k: getattr(s, k) for k, _ in _lib.SdmScalars._fields_} for s in sc]
+
     def set_positions_ptr(self, replica: int, host_ptr: int):
         _lib.check(self._L.sdm_set_positions(self._h, replica, C.c_void_p(host_ptr)))
 

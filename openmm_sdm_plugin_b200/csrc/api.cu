@@ -665,6 +665,22 @@ int sdm_read_results(sdm_ctx* c, double* forces_all, sdm_scalars* scalars_all) {
     return SDM_OK;
 }
 
+int sdm_enqueue_results(sdm_ctx* c, double* forces_all) {
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (forces_all)
+        SDM_CUDA(cudaMemcpyAsync(forces_all, c->B.F, sizeof(double) * 3 * (size_t)c->n * c->R,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaMemcpyAsync(c->h_state, c->B.state, sizeof(sdm::ReplicaState) * (size_t)c->R,
+                             cudaMemcpyDeviceToHost, c->stream));
+    return SDM_OK;
+}
+
+int sdm_collect_scalars(sdm_ctx* c, sdm_scalars* scalars_all) {
+    if (!c || !scalars_all) return fail(SDM_ERR_INVALID, "null argument");
+    for (int r = 0; r < c->R; r++) scalars_all[r] = c->h_state[r].sc;
+    return SDM_OK;
+}
+
 int sdm_forces_device_ptr(sdm_ctx* c, int replica, double** d_f) {
     if (int rc = check_ctx(c, replica)) return rc;
     if (!d_f) return fail(SDM_ERR_INVALID, "null argument");
