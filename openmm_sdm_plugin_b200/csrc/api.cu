@@ -224,6 +224,9 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (int k = 0; k < 4; k++) TRYCUDA(cudaEventCreate(&c->ev[k]));
+    TRYCUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
     sdm::Topology& T = c->T;
     std::memset(&T, 0, sizeof(T));
@@ -382,6 +385,9 @@ void sdm_destroy(sdm_ctx* c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (int k = 0; k < 4; k++)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -492,17 +498,22 @@ int sdm_invalidate_list(sdm_ctx* c) {
 }
 
 // The kernels of one evaluation after the state-1 pair pass (shared by both pair modes).
+// Displaced atoms, first half: FP32 prefilter bitmap -> FP64 pair terms (once per pair).  Only
+// needs the positions, so the cluster path runs it on the side stream next to the pair kernel.
+static void enqueue_displaced(sdm_ctx* c, cudaStream_t s) {
+    if (c->T.n_lig > 0) {
+        sdm::launch_ligand_filter(c->T, c->B, s);
+        sdm::launch_ligand_probe(c->T, c->B, s);
+        c->launches += 2;
+    }
+}
+
+// The kernels of one evaluation after the state-1 pair pass and the displaced-atom pair terms.
 static int enqueue_tail(sdm_ctx* c, double e_scale, int c_div, int zero_acc) {
     cudaStream_t s = c->stream;
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;
-    // displaced atoms: FP32 prefilter bitmap -> FP64 pair terms (once per pair) -> per-atom gather
-    if (T.n_lig > 0) {
-        sdm::launch_ligand_filter(T, B, s);
-        sdm::launch_ligand_probe(T, B, s);
-        c->launches += 2;
-    }
-    sdm::launch_ligand_gather(T, B, s);
+    sdm::launch_ligand_gather(T, B, s);   // per-atom gather of the displaced-atom pair forces
     sdm::launch_exceptions(T, B, s);
     sdm::launch_scalars(T, B, e_scale, c_div, s);
     sdm::launch_mix(T, B, zero_acc, s);
@@ -570,6 +581,7 @@ int sdm_eval(sdm_ctx* c) {
         sdm::launch_allpairs(T, B, c->opt.exact_cutoff, nullptr, nullptr, 0, -1, s);
         if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[2], s));
         c->launches += 2;
+        enqueue_displaced(c, s);
         if (int rc = enqueue_tail(c, 0.5, 2, 0)) return rc;
     } else {
         // Between list rebuilds the kernel sequence is identical from one evaluation to the next
@@ -593,8 +605,25 @@ int sdm_eval(sdm_ctx* c) {
             if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) capturing = true;
             else cudaGetLastError();
         }
-        int rc = sdm_ctx_pairlist_eval(c);  // records ev[1], ev[2] around the pair kernel when timing
-        if (!rc && !capturing) rc = ensure_hitbits(c);
+        int rc = sdm_ctx_pairlist_prepare(c);   // list (re)build or refresh of the sorted positions
+        if (!rc) rc = ensure_hitbits(c);         // no-op while capturing (sized before the capture began)
+        if (!rc) {
+            // fork: the displaced-atom pair terms only need the positions; they fill the tail of
+            // the (persistent) pair kernel instead of waiting for it.  Serial when the pair kernel
+            // is being timed on its own.
+            const bool fork = !c->timing && c->T.n_lig > 0;
+            if (fork) {
+                cudaEventRecord(c->ev_fork, s);
+                cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0);
+                rc = sdm_ctx_pairlist_launch(c);
+                enqueue_displaced(c, c->side_stream);
+                cudaEventRecord(c->ev_join, c->side_stream);
+                cudaStreamWaitEvent(s, c->ev_join, 0);
+            } else {
+                rc = sdm_ctx_pairlist_launch(c);  // records ev[1], ev[2] around the pair kernel when timing
+                enqueue_displaced(c, s);
+            }
+        }
         if (!rc) rc = enqueue_tail(c, 1.0, 1, 1);
         if (capturing) {
             cudaGraph_t g = nullptr;

@@ -808,7 +808,7 @@ bool sdm_ctx_pairlist_rebuild_due(const sdm_ctx* c) {
     return !c->list_valid || c->list_age >= c->opt.nstlist;
 }
 
-int sdm_ctx_pairlist_eval(sdm_ctx* c) {
+int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
     PairList* pl = c->pl;
     if (!pl) return sdm_fail(SDM_ERR_INVALID, "cluster pair list not initialised");
     cudaStream_t s = c->stream;
@@ -832,6 +832,13 @@ int sdm_ctx_pairlist_eval(sdm_ctx* c) {
     c->B.scan_off = pl->cell_slot;
     c->B.scan_stride = pl->G.ncell;
     c->B.scan_max = pl->scan_max;
+    PL_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_ctx_pairlist_launch(sdm_ctx* c) {
+    PairList* pl = c->pl;
+    cudaStream_t s = c->stream;
     // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
     launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart,

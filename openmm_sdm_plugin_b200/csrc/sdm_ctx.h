@@ -12,6 +12,8 @@ struct sdm_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // displaced-atom kernels run here, next to the pair kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
     sdm_options opt{};
     int n = 0, R = 0;
@@ -62,6 +64,7 @@ int sdm_fail(int code, const char* msg);
 int sdm_ctx_init_pairlist(sdm_ctx* c);
 void sdm_ctx_free_pairlist(sdm_ctx* c);
 bool sdm_ctx_pairlist_rebuild_due(const sdm_ctx* c);
-int sdm_ctx_pairlist_eval(sdm_ctx* c);   // (re)build if due, refresh sorted positions, pair kernel
+int sdm_ctx_pairlist_prepare(sdm_ctx* c);  // (re)build the list if due, else refresh the sorted positions
+int sdm_ctx_pairlist_launch(sdm_ctx* c);   // the pair kernel
 int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap);
 int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value);
