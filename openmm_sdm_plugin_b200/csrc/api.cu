@@ -498,26 +498,29 @@ int sdm_invalidate_list(sdm_ctx* c) {
 }
 
 // The kernels of one evaluation after the state-1 pair pass (shared by both pair modes).
-// Displaced atoms, first half: FP32 prefilter bitmap -> FP64 pair terms (once per pair).  Only
-// needs the positions, so the cluster path runs it on the side stream next to the pair kernel.
-static void enqueue_displaced(sdm_ctx* c, cudaStream_t s) {
-    if (c->T.n_lig > 0) {
-        sdm::launch_ligand_filter(c->T, c->B, s);
-        sdm::launch_ligand_probe(c->T, c->B, s);
-        c->launches += 2;
-    }
-}
-
-// The kernels of one evaluation after the state-1 pair pass and the displaced-atom pair terms.
-static int enqueue_tail(sdm_ctx* c, double e_scale, int c_div, int zero_acc) {
-    cudaStream_t s = c->stream;
+// Everything that only needs the positions, not the state-1 pair pass: the displaced-atom pair
+// terms (FP32 prefilter bitmap -> FP64 pair terms, once per pair -> per-atom gather) and the 1-4
+// exceptions (fixed-point atomics on the state-1 accumulators commute with the pair kernel's).
+// The cluster path runs this on the side stream next to the pair kernel.
+static void enqueue_position_only(sdm_ctx* c, cudaStream_t s) {
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;
+    if (T.n_lig > 0) {
+        sdm::launch_ligand_filter(T, B, s);
+        sdm::launch_ligand_probe(T, B, s);
+        c->launches += 2;
+    }
     sdm::launch_ligand_gather(T, B, s);   // per-atom gather of the displaced-atom pair forces
-    sdm::launch_exceptions(T, B, s);
-    sdm::launch_scalars(T, B, e_scale, c_div, s);
-    sdm::launch_mix(T, B, zero_acc, s);
-    c->launches += 4;
+    sdm::launch_exceptions(T, B, s);      // after the probe kernel: adds to dF of displaced 1-4 pairs
+    c->launches += 2;
+}
+
+// The kernels that need both: scalar stage (soft-core, bias, bookkeeping) and the hybrid force.
+static int enqueue_tail(sdm_ctx* c, double e_scale, int c_div, int zero_acc) {
+    cudaStream_t s = c->stream;
+    sdm::launch_scalars(c->T, c->B, e_scale, c_div, s);
+    sdm::launch_mix(c->T, c->B, zero_acc, s);
+    c->launches += 2;
     return SDM_OK;
 }
 
@@ -581,7 +584,7 @@ int sdm_eval(sdm_ctx* c) {
         sdm::launch_allpairs(T, B, c->opt.exact_cutoff, nullptr, nullptr, 0, -1, s);
         if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[2], s));
         c->launches += 2;
-        enqueue_displaced(c, s);
+        enqueue_position_only(c, s);
         if (int rc = enqueue_tail(c, 0.5, 2, 0)) return rc;
     } else {
         // Between list rebuilds the kernel sequence is identical from one evaluation to the next
@@ -611,17 +614,19 @@ int sdm_eval(sdm_ctx* c) {
             // fork: the displaced-atom pair terms only need the positions; they fill the tail of
             // the (persistent) pair kernel instead of waiting for it.  Serial when the pair kernel
             // is being timed on its own.
-            const bool fork = !c->timing && c->T.n_lig > 0;
+            const bool fork = !c->timing;
             if (fork) {
                 cudaEventRecord(c->ev_fork, s);
                 cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0);
-                rc = sdm_ctx_pairlist_launch(c);
-                enqueue_displaced(c, c->side_stream);
+                // side work first: its (small) grids are dispatched ahead of the persistent pair
+                // kernel, whose blocks then fill every slot that is or becomes free
+                enqueue_position_only(c, c->side_stream);
                 cudaEventRecord(c->ev_join, c->side_stream);
+                rc = sdm_ctx_pairlist_launch(c);
                 cudaStreamWaitEvent(s, c->ev_join, 0);
             } else {
                 rc = sdm_ctx_pairlist_launch(c);  // records ev[1], ev[2] around the pair kernel when timing
-                enqueue_displaced(c, s);
+                enqueue_position_only(c, s);
             }
         }
         if (!rc) rc = enqueue_tail(c, 1.0, 1, 1);
