@@ -111,3 +111,16 @@ def test_argument_validation_happens_before_device_use():
     assert e.value.code == _lib.SDM_ERR_BOX
     assert L.sdm_get_scalars(None, 0, None) == _lib.SDM_ERR_INVALID
     assert L.sdm_k_make_state2(None, 10, None, None) == _lib.SDM_ERR_INVALID
+
+
+def test_cpp_host_mirror_of_the_integrator(tmp_path):
+    """The C++ mirror of SDMPlugin::LangevinIntegratorSDM (header only, on top of the C ABI):
+    compiled with g++ against libsdmb200.so and run here -- defaults, round trips, errors."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_api_check")
+    libdir = os.path.join(root, "openmm_sdm_plugin_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", os.path.join(root, "tests", "hostapi", "host_api_check.cpp"),
+                           "-o", exe, "-L" + libdir, "-lsdmb200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "host api ok" in out.stdout, out.stdout + out.stderr
