@@ -31,6 +31,7 @@
 // Appendix B.3) in FP32: per-atom sigma/2 and 2*sqrt(eps), charges pre-scaled by
 // sqrt(ONE_4PI_EPS0), reaction field krf/crf, LJ not shifted.
 #include <algorithm>
+#include <cstdlib>
 
 #include "f32x2.cuh"
 #include "pairlist.h"
@@ -545,6 +546,8 @@ void launch_pair_cluster(const Topology& T, const PairListView& V, const double*
                                                               kWarps * 32, 0) != cudaSuccess ||    \
                 resident < 1)                                                                     \
                 resident = SDM_PAIR_MINB;                                                         \
+            /* development knob: resident blocks per SM (occupancy sensitivity experiments) */    \
+            if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
         }                                                                                         \
         const int grid = std::min((V.nunits + kWarps - 1) / kWarps, num_sms * resident);           \
         pair_cluster_kernel<P, X><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
