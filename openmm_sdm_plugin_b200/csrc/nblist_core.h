@@ -39,7 +39,8 @@ constexpr int kClusterSize = 8;      // atoms per i-cluster
 constexpr int kJGroup = 8;           // atoms per j-group (a whole cluster)
 constexpr int kMaxCi = 8;            // clusters per supercluster
 constexpr int kMaskWords = 2 * kMaxCi;  // words per exclusion-mask set
-constexpr int kSubBits = 34;         // sort key = cell << 34 | kd bucket (2 bits) << 32 | coordinate bits
+constexpr int kCoordBits = 16;       // in-cell coordinate resolution of the sort key
+constexpr int kSubBits = kCoordBits + 2;  // sort key = cell << 18 | kd bucket (2 bits) << 16 | coordinate
 constexpr int kMaxSpan = 6;          // search stencil is at most kMaxSpan cells per dimension
 constexpr float kFar = 1.0e6f;       // coordinate of dummy (padding) atoms
 constexpr float kBoxEmptyLo = 3.0e38f;
@@ -112,7 +113,7 @@ constexpr uint32_t kShiftZero = 1u | (1u << 2) | (1u << 4);
 // (relative to the grid origin they are >= 0) and the integer image that was applied
 // (xw = x + img*L).
 SDM_HD uint32_t atom_cell(const Grid& G, int replica, double x, double y, double z, float* xw_out,
-                          int* img_out) {
+                          int* img_out, uint32_t* frac_out = nullptr) {
     double p[3] = {x, y, z};
     int c[3];
     for (int d = 0; d < 3; d++) {
@@ -132,23 +133,23 @@ SDM_HD uint32_t atom_cell(const Grid& G, int replica, double x, double y, double
         c[d] = k;
         xw_out[d] = (float)w;
         img_out[d] = img;
+        if (frac_out) {
+            // position inside the cell in kCoordBits bits (order-preserving; ties keep their order)
+            double fr = (t - (double)k) * (double)(1 << kCoordBits);
+            int q = (int)fr;
+            if (q < 0) q = 0;
+            if (q > (1 << kCoordBits) - 1) q = (1 << kCoordBits) - 1;
+            frac_out[d] = (uint32_t)q;
+        }
     }
     uint32_t cell = (uint32_t)((c[2] * G.nc[1] + c[1]) * G.nc[0] + c[0]);
     return (uint32_t)replica * (uint32_t)G.ncell + cell;
 }
 
-// Order-preserving bits of a coordinate measured from the grid origin (non-negative float).
-SDM_HD uint32_t coord_bits(const Grid& G, float w, int d) {
-    float v = w - (float)G.lo[d];
-    if (!(v > 0.f)) v = 0.f;
-    union { float f; uint32_t u; } cv;
-    cv.f = v;
-    return cv.u;
-}
-
 SDM_HD uint64_t make_key(uint32_t gcell, uint32_t bucket, uint32_t cbits) {
-    return ((uint64_t)gcell << kSubBits) | ((uint64_t)(bucket & 3u) << 32) | (uint64_t)cbits;
+    return ((uint64_t)gcell << kSubBits) | ((uint64_t)(bucket & 3u) << kCoordBits) | (uint64_t)cbits;
 }
+SDM_HD uint32_t key_bucket(uint64_t key) { return (uint32_t)(key >> kCoordBits) & 3u; }
 
 // Atoms that go to the first half when a run of `count` atoms is split: half of its clusters
 // (rounded up), i.e. a multiple of 8.

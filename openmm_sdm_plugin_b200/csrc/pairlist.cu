@@ -111,8 +111,9 @@ __global__ void key_kernel(Grid G, const double* __restrict__ pos_all, uint64_t*
     const double* p = pos_all + 3 * (size_t)t;
     float xw[3];
     int img[3];
-    const uint32_t g = nbl::atom_cell(G, r, p[0], p[1], p[2], xw, img);
-    keys[t] = nbl::make_key(g, 0u, nbl::coord_bits(G, xw[2], 2));
+    uint32_t fr[3];
+    const uint32_t g = nbl::atom_cell(G, r, p[0], p[1], p[2], xw, img, fr);
+    keys[t] = nbl::make_key(g, 0u, fr[2]);
     vals[t] = t;
 }
 
@@ -126,13 +127,13 @@ __global__ void refine_key_kernel(Grid G, int level, int total, const double* __
     const uint64_t k = keys_sorted[p];
     const uint32_t c = (uint32_t)(k >> nbl::kSubBits);
     const int ga = vals_sorted[p];
-    const uint32_t b = nbl::kd_bucket(level, p, cell_first[c], cell_count[c], (uint32_t)(k >> 32) & 3u);
+    const uint32_t b = nbl::kd_bucket(level, p, cell_first[c], cell_count[c], nbl::key_bucket(k));
     const double* q = pos_all + 3 * (size_t)ga;
     float xw[3];
     int img[3];
-    nbl::atom_cell(G, ga / G.n, q[0], q[1], q[2], xw, img);
-    const int d = level == 1 ? 1 : 0;
-    keys[p] = nbl::make_key(c, b, nbl::coord_bits(G, xw[d], d));
+    uint32_t fr[3];
+    nbl::atom_cell(G, ga / G.n, q[0], q[1], q[2], xw, img, fr);
+    keys[p] = nbl::make_key(c, b, fr[level == 1 ? 1 : 0]);
     vals[p] = ga;
 }
 
@@ -327,6 +328,7 @@ __global__ void sci_off_kernel(int nsci, int noff, int nraw, const int* __restri
 }
 
 // Exclusions.  pass 0 flags the entries that need a mask set, pass 1 clears the pair's bit.
+// (One thread per excluded pair; a warp-per-pair scan of the entries was measured slower.)
 __global__ void exclusion_kernel(Grid G, int n_excl, const int* __restrict__ excl_pairs,
                                  const int* __restrict__ slot_of, const int* __restrict__ cl_sci,
                                  const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,

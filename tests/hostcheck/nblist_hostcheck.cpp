@@ -96,14 +96,15 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     // refine_key_kernel and the radix sorts of pairlist.cu)
     std::vector<uint64_t> keys(total), ks(total);
     std::vector<int> vals(total), vs(total);
-    auto wrapped = [&](int ga, float* xw) {
+    auto wrapped = [&](int ga, uint32_t* fr) {
         int im[3];
-        return atom_cell(G, ga / n, pos[3 * (size_t)ga], pos[3 * (size_t)ga + 1], pos[3 * (size_t)ga + 2], xw, im);
+        float xw[3];
+        return atom_cell(G, ga / n, pos[3 * (size_t)ga], pos[3 * (size_t)ga + 1], pos[3 * (size_t)ga + 2], xw, im, fr);
     };
     for (int t = 0; t < total; t++) {
-        float xw[3];
-        const uint32_t g = wrapped(t, xw);
-        keys[t] = make_key(g, 0u, coord_bits(G, xw[2], 2));
+        uint32_t fr[3];
+        const uint32_t g = wrapped(t, fr);
+        keys[t] = make_key(g, 0u, fr[2]);
         vals[t] = t;
     }
     auto sort_pairs = [&]() {
@@ -123,11 +124,10 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     for (int level = 1; level <= 2; level++) {
         for (int p = 0; p < total; p++) {
             const uint32_t c = (uint32_t)(ks[p] >> kSubBits);
-            const uint32_t b = kd_bucket(level, p, cell_first[c], cell_count[c], (uint32_t)(ks[p] >> 32) & 3u);
-            float xw[3];
-            wrapped(vs[p], xw);
-            const int d = level == 1 ? 1 : 0;
-            keys[p] = make_key(c, b, coord_bits(G, xw[d], d));
+            const uint32_t b = kd_bucket(level, p, cell_first[c], cell_count[c], key_bucket(ks[p]));
+            uint32_t fr[3];
+            wrapped(vs[p], fr);
+            keys[p] = make_key(c, b, fr[level == 1 ? 1 : 0]);
             vals[p] = vs[p];
         }
         sort_pairs();
