@@ -277,6 +277,7 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
     int cnt = 0;
     uint32_t fixmask = 0u;
     const size_t plane = (size_t)V.nslot_cap;
+    long long* const facc_j = f1acc + (size_t)(ti < 3 ? ti : 2) * plane;   // lane ti adds component ti
 
     // software pipeline: j data of the next entry is in flight while this entry is computed
     uint32_t ex = __shfl_sync(0xffffffffu, my_ent.x, 0);
@@ -312,8 +313,8 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
                                      fi, fj, en, cnt, tmin);
         if (EXACT) {
             // entries with a pair inside the band are revisited after the loop (keeps the call
-            // and its register pressure out of the hot loop)
-            if (__any_sync(0xffffffffu, tmin < K.band)) fixmask |= 1u << k;
+            // and its register pressure out of the hot loop); per-lane bits, OR-reduced once
+            fixmask |= (tmin < K.band ? 1u : 0u) << k;
         }
         // j force: add the two halves, then transpose-reduce (x, y, z) over the 4 ti lanes with 3
         // shuffles.  Afterwards lane ti = 0 holds X, ti = 1 holds Y, ti = 2 (and 3) hold Z.
@@ -329,8 +330,7 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
             float v = up ? z : keep;
             v += __shfl_xor_sync(0xffffffffu, send2, 2);
             // lane ti: 0 -> X, 1 -> Y, 2 -> Z, 3 -> Z (duplicate, not written); sign: F_j = -sum
-            if (ti < 3 && v != 0.f)
-                atomic_add_fixed(f1acc + (size_t)ti * plane + jslot_k, __float2ll_rn(-v * kFix));
+            if (ti < 3 && v != 0.f) atomic_add_fixed(facc_j + jslot_k, __float2ll_rn(-v * kFix));
         }
     }
 
@@ -374,6 +374,7 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
     }
 
     float en1 = lo(en) + hi(en);
+    if (EXACT) fixmask = __reduce_or_sync(0xffffffffu, fixmask);
     if (EXACT && fixmask) {
         float en_fix = 0.f;   // separate variables: their address is taken by the call
         int cnt_fix = 0;
