@@ -629,7 +629,7 @@ int sdm_eval(sdm_ctx* c) {
                 enqueue_position_only(c, s);
             }
         }
-        if (!rc) rc = enqueue_tail(c, 1.0, 1, 1);
+        if (!rc) rc = enqueue_tail(c, 1.0, 1, 0);   // the accumulators are cleared by a memset before the pair pass
         if (capturing) {
             cudaGraph_t g = nullptr;
             cudaError_t e = cudaStreamEndCapture(s, &g);

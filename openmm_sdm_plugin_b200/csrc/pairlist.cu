@@ -822,6 +822,8 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
         launch_refresh(c->T, pl->G, pl->nslot, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq,
                        hs * hs, c->B.flags, c->d_list_age, s);
         c->launches++;
+        // fresh state-1 accumulators (one 8 MB memset is cheaper than scattered stores in the mix kernel)
+        PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
     }
     c->list_age++;
     // partial-sum buffers of this path
