@@ -556,7 +556,7 @@ static int ensure_hitbits(sdm_ctx* c) {
     int cap = c->n;
     if (T.method != SDM_NOCUTOFF) {
         const double r = T.rc + 0.05;
-        cap = (int)std::min<double>(c->n, 2.0 * 4.19 * r * r * r * 200.0 + 64.0);
+        cap = (int)std::min<double>(c->n, (2.0 * 4.19 * r * r * r * 200.0 + 64.0) * c->pairf_scale);
     }
     cap = std::max(cap, 32);
     const size_t need_f = rows * (size_t)cap * 3;
@@ -653,6 +653,15 @@ int sdm_eval(sdm_ctx* c) {
     return SDM_OK;
 }
 
+// An evaluation that ran out of per-hit scratch says so in its status; the next one gets twice
+// the room (the caller repeats the evaluation, as the header documents for SDM_ERR_CAPACITY).
+static void note_status(sdm_ctx* c, int status) {
+    if (status == SDM_ERR_CAPACITY && c->pairf_scale < (1 << 16)) {
+        c->pairf_scale *= 2;
+        c->graph_valid = false;
+    }
+}
+
 int sdm_get_scalars(sdm_ctx* c, int replica, sdm_scalars* out) {
     if (int rc = check_ctx(c, replica)) return rc;
     if (!out) return fail(SDM_ERR_INVALID, "null argument");
@@ -660,6 +669,7 @@ int sdm_get_scalars(sdm_ctx* c, int replica, sdm_scalars* out) {
                              cudaMemcpyDeviceToHost, c->stream));
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     *out = c->h_state[replica].sc;
+    note_status(c, out->status);
     return SDM_OK;
 }
 
@@ -695,7 +705,10 @@ int sdm_read_results(sdm_ctx* c, double* forces_all, sdm_scalars* scalars_all) {
                                  cudaMemcpyDeviceToHost, c->stream));
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     if (scalars_all)
-        for (int r = 0; r < c->R; r++) scalars_all[r] = c->h_state[r].sc;
+        for (int r = 0; r < c->R; r++) {
+            scalars_all[r] = c->h_state[r].sc;
+            note_status(c, scalars_all[r].status);
+        }
     return SDM_OK;
 }
 
@@ -711,7 +724,10 @@ int sdm_enqueue_results(sdm_ctx* c, double* forces_all) {
 
 int sdm_collect_scalars(sdm_ctx* c, sdm_scalars* scalars_all) {
     if (!c || !scalars_all) return fail(SDM_ERR_INVALID, "null argument");
-    for (int r = 0; r < c->R; r++) scalars_all[r] = c->h_state[r].sc;
+    for (int r = 0; r < c->R; r++) {
+        scalars_all[r] = c->h_state[r].sc;
+        note_status(c, scalars_all[r].status);
+    }
     return SDM_OK;
 }
 

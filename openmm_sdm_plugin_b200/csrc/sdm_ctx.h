@@ -33,6 +33,7 @@ struct sdm_ctx {
     int* d_hitpre = nullptr;
     double* d_pairf = nullptr;
     size_t pairf_alloc = 0;             // doubles allocated for d_pairf
+    int pairf_scale = 1;                // doubled whenever an eval reports SDM_ERR_CAPACITY
 
     std::vector<sdm_alch> h_alch;       // staging copies with ctx lifetime
     std::vector<double> h_eb;

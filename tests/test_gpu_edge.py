@@ -197,3 +197,35 @@ def test_forces_are_the_gradient_of_the_energies():
                 # u and dF are FP64 over moved pairs: limited by the O(h^2) truncation of the central
                 # difference (u ~ 1e6 kJ/mol here: the displaced ligand overlaps solvent)
                 assert abs(-(up - um) / (2 * h) - df[a, d]) <= 1e-3 * max(1.0, abs(df[a, d])), (a, d)
+
+
+def test_scratch_capacity_overflow_is_reported_and_repaired():
+    """A displaced atom with more neighbours than the per-hit scratch was sized for (here: an
+    absurdly dense blob) must not corrupt anything: the evaluation reports SDM_ERR_CAPACITY, the
+    context grows the scratch, and the repeated evaluation is correct."""
+    rng = np.random.default_rng(9)
+    n = 4000
+    # 4000 atoms inside a 1.2 nm ball: ~550 atoms / nm^3, far above the 200 / nm^3 the scratch assumes
+    v = rng.normal(size=(n, 3))
+    pos = 3.0 + 0.6 * v / np.linalg.norm(v, axis=1, keepdims=True) * rng.uniform(0, 1, (n, 1)) ** (1 / 3)
+    sysd = S.NonbondedSystem(np.zeros(n), np.full(n, 0.01), np.full(n, 1e-6), np.zeros((0, 2), np.int32),
+                             np.zeros((0, 2), np.int32), np.zeros((0, 3)), method=S.CUTOFF_NONPERIODIC,
+                             cutoff=1.0, eps_rf=78.3, box=np.zeros(3), use_dispersion_correction=False)
+    disp = np.zeros((n, 3))
+    disp[:4] = (0.2, 0.0, 0.0)
+    case = S.SDMCase("dense", sysd, pos, disp, S.AlchemicalState(lambdac=0.5))
+    ref = oracle_eval(case)
+    with SDMContext(sysd, disp, pair_mode=AP) as ctx:
+        ctx.set_alchemical(0, case.alch)
+        ctx.set_positions(0, pos)
+        ctx.eval()
+        first = ctx.scalars(0)["status"]
+        assert first in (0, _lib.SDM_ERR_CAPACITY)
+        tries = 0
+        while ctx.scalars(0)["status"] == _lib.SDM_ERR_CAPACITY and tries < 6:
+            ctx.eval()
+            tries += 1
+        sc = ctx.scalars(0)
+        assert sc["status"] == 0
+        assert abs(sc["u"] - ref["u"]) <= 1e-6 * max(1.0, abs(ref["u"]))
+        assert first == _lib.SDM_ERR_CAPACITY   # the scenario really overflowed the first time
