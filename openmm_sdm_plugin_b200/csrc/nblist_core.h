@@ -244,44 +244,6 @@ SDM_HD bool any_pair_within(const float* posq4, int A, int B, float sx, float sy
     return false;
 }
 
-// Squared distance from a point to an AABB shifted by (sx,sy,sz).
-SDM_HD float point_box_dist2(const float* p, float px, float py, float pz, const BBox& b) {
-    const float q[3] = {p[0] + px, p[1] + py, p[2] + pz};
-    float d2 = 0.f;
-    for (int d = 0; d < 3; d++) {
-        float g1 = b.lo[d] - q[d], g2 = q[d] - b.hi[d];
-        float g = g1 > g2 ? g1 : g2;
-        if (g > 0.f) d2 += g * g;
-    }
-    return d2;
-}
-
-// Cheaper, slightly looser stand-in for any_pair_within: some atom of B lies within rlist of the
-// box of A AND some atom of A lies within rlist of the (shifted) box of B.
-SDM_HD bool boxes_atoms_within(const float* posq4, const BBox& boxA, const BBox& boxB, int A, int B,
-                               float sx, float sy, float sz, float rlist2) {
-    bool any = false;
-    for (int t = 0; t < kJGroup && !any; t++) {
-        const float* pj = posq4 + 4 * (size_t)(B * kJGroup + t);
-        if (pj[0] >= 0.5f * kFar) continue;
-        any = point_box_dist2(pj, sx, sy, sz, boxA) < rlist2;
-    }
-    if (!any) return false;
-    for (int t = 0; t < kClusterSize; t++) {
-        const float* pi = posq4 + 4 * (size_t)(A * kClusterSize + t);
-        if (pi[0] >= 0.5f * kFar) continue;
-        if (point_box_dist2(pi, -sx, -sy, -sz, boxB) < rlist2) return true;
-    }
-    return false;
-}
-
-// Pruning done INSIDE the search (per item, one thread): 0 = cluster boxes only (default; the
-// exact atom-pair pruning then runs as a separate warp-per-entry pass, prune_imask below),
-// 1 = atoms against boxes, 2 = exact atom pairs.
-#ifndef SDM_NBL_PRUNE
-#define SDM_NBL_PRUNE 0
-#endif
-
 // One search item = (sci, stencil offset).  Visits the clusters of the addressed cell and calls
 // emit(k, cj | shift<<26, imask, diag) for every j-cluster that interacts with at least one
 // cluster of the sci under the ownership rule.  Returns the number of entries.
@@ -331,13 +293,7 @@ SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
             }
             if (!own) continue;
             if (box_dist2(V.cl_box[A], jb, sx, sy, sz) >= G.rlist2) continue;
-#if SDM_NBL_PRUNE == 0
-            imask |= 1u << ci;
-#elif SDM_NBL_PRUNE == 1
-            if (boxes_atoms_within(V.posq4, V.cl_box[A], jb, A, B, sx, sy, sz, G.rlist2)) imask |= 1u << ci;
-#else
-            if (any_pair_within(V.posq4, A, B, sx, sy, sz, G.rlist2)) imask |= 1u << ci;
-#endif
+            imask |= 1u << ci;   // box level only; the exact atom-pair prune is a separate pass
         }
         if (imask) {
             emit(count, (uint32_t)B | (code << 26), imask, diag && ((imask >> (B - sd.c0)) & 1u));
