@@ -41,7 +41,9 @@ typedef enum {
     SDM_ERR_CUDA = -3,         /* a CUDA runtime call failed; see sdm_last_error()          */
     SDM_ERR_BOX = -4,          /* periodic box smaller than 2*cutoff (OpenMM throws there)  */
     SDM_ERR_SOFTCORE = -5,     /* "Unknown soft core method" (LangevinIntegratorSDM.cpp:147)*/
-    SDM_ERR_STALE_LIST = -6,   /* an atom moved more than skin/2 since the list was built   */
+    SDM_ERR_STALE_LIST = -6,   /* an atom moved more than skin/2 since the list was built: reported in
+                                  sdm_scalars.status; the list is rebuilt at the next sdm_eval(),
+                                  repeat the evaluation                                          */
     SDM_ERR_CAPACITY = -7      /* internal scratch capacity exceeded: reported in sdm_scalars.status,
                                   the context grows the scratch, repeat the evaluation            */
 } sdm_status;

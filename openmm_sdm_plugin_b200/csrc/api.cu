@@ -660,6 +660,9 @@ static void note_status(sdm_ctx* c, int status) {
         c->pairf_scale *= 2;
         c->graph_valid = false;
     }
+    // an atom outran the list buffer: the next evaluation rebuilds the list (the caller repeats
+    // the evaluation; forces of the flagged one may miss pairs)
+    if (status == SDM_ERR_STALE_LIST) c->list_valid = false;
 }
 
 int sdm_get_scalars(sdm_ctx* c, int replica, sdm_scalars* out) {

@@ -45,7 +45,7 @@ struct PairList {
     int *entry_flag = nullptr, *entry_midx = nullptr, *entry_sci = nullptr;
     // raw (box-pruned) entries of the search, before the exact prune + compaction
     uint2* raw_entries = nullptr;
-    int *raw_flag = nullptr, *raw_sci = nullptr, *raw_keep = nullptr, *raw_pos = nullptr;
+    int *raw_flag = nullptr, *raw_sci = nullptr, *raw_c0nci = nullptr, *raw_keep = nullptr, *raw_pos = nullptr;
     size_t raw_cap = 0;
     int nraw = 0;
     int* sci_off = nullptr;     // [nsci+1] first (compacted) entry of every sci
@@ -239,11 +239,13 @@ struct FillEmit {
     uint2* out;
     int* flag;
     int* esci;
-    int base, isci;
+    int* c0nci;      // first cluster | cluster count << 27 of the owning supercluster (for the prune pass)
+    int base, isci, sd_c0nci;
     __device__ void operator()(int k, uint32_t w0, uint32_t imask, bool diag) const {
         out[base + k] = make_uint2(w0, imask);
         flag[base + k] = diag ? 1 : 0;
         esci[base + k] = isci;
+        c0nci[base + k] = sd_c0nci;
     }
 };
 
@@ -255,28 +257,28 @@ __global__ void search_count_kernel(nbl::SearchView V, int nsci, int noff, int* 
 
 __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
                                    const int* __restrict__ item_off, uint2* entries, int* flag,
-                                   int* esci, int cap) {
+                                   int* esci, int* c0nci, int cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsci * noff) return;
     const int base = item_off[t];
     if (base >= cap) return;
-    nbl::search_item(V, t / noff, t % noff, FillEmit{entries, flag, esci, base, t / noff});
+    const SciDesc sd = V.sci[t / noff];
+    nbl::search_item(V, t / noff, t % noff, FillEmit{entries, flag, esci, c0nci, base, t / noff, sd.c0 | (sd.nci << 27)});
 }
 
 // Exact pruning, one warp per raw entry: imask bit ci survives only if some real atom pair of
 // (cluster c0+ci, the entry's shifted j-cluster) is closer than rlist -- the predicate of
 // nbl::prune_imask.  Lane (tj, ti) = (lane>>2, lane&3) tests j-atom tj against i-atoms ti, ti+4.
 __global__ void __launch_bounds__(128)
-prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ raw_sci,
-             int* __restrict__ raw_flag, const SciDesc* __restrict__ sci,
-             const float4* __restrict__ posq, int* __restrict__ keep) {
+prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ raw_c0nci,
+             int* __restrict__ raw_flag, const float4* __restrict__ posq, int* __restrict__ keep) {
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (e >= nraw) return;
-    const uint2 ent = raw[e];
+    const uint2 ent = raw[e];                 // two independent loads, then the atoms: no
+    const int c0 = raw_c0nci[e] & 0x7ffffff;  // dependent descriptor chain per entry
     const int B = (int)(ent.x & 0x3ffffffu);
     const uint32_t code = ent.x >> 26;
-    const SciDesc sd = sci[raw_sci[e]];
     const int tj = lane >> 2, ti = lane & 3;
     float4 xj = posq[B * nbl::kJGroup + tj];
     const bool jreal = xj.x < 0.5f * nbl::kFar;
@@ -287,7 +289,7 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
     while (todo) {
         const int ci = __ffs(todo) - 1;
         todo &= todo - 1u;
-        const float4* pi = posq + (size_t)(sd.c0 + ci) * nbl::kClusterSize + ti;
+        const float4* pi = posq + (size_t)(c0 + ci) * nbl::kClusterSize + ti;
         const float4 a = pi[0], b = pi[4];
         bool hit = false;
         if (jreal) {
@@ -302,7 +304,7 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
         raw[e].y = out;
         keep[e] = out != 0u;
         // the diagonal flag needs the self tile, which always survives while the cluster has atoms
-        if (raw_flag[e] && !((out >> (B - sd.c0)) & 1u)) raw_flag[e] = 0;
+        if (raw_flag[e] && !((out >> (B - c0)) & 1u)) raw_flag[e] = 0;
     }
 }
 
@@ -577,16 +579,17 @@ static int build_list(sdm_ctx* c) {
         if (int rc = pl_realloc(pl, &pl->raw_entries, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_flag, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_sci, pl->raw_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->raw_c0nci, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_keep, pl->raw_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_pos, pl->raw_cap + 1)) return rc;
     }
     const int nraw = pl->nraw;
     search_fill_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_off, pl->raw_entries,
-                                                          pl->raw_flag, pl->raw_sci, (int)pl->raw_cap);
+                                                          pl->raw_flag, pl->raw_sci, pl->raw_c0nci, (int)pl->raw_cap);
     // exact prune (one warp per raw entry), then order-preserving compaction
     if (nraw > 0)
-        prune_kernel<<<blocks((long long)nraw * 32, 128), 128, 0, s>>>(G, nraw, pl->raw_entries, pl->raw_sci,
-                                                                      pl->raw_flag, pl->sci, pl->posq, pl->raw_keep);
+        prune_kernel<<<blocks((long long)nraw * 32, 128), 128, 0, s>>>(G, nraw, pl->raw_entries, pl->raw_c0nci,
+                                                                      pl->raw_flag, pl->posq, pl->raw_keep);
     PL_CUDA(cudaMemsetAsync(pl->raw_keep + nraw, 0, sizeof(int), s));
     if (int rc = ensure_cub((size_t)nraw + 1)) return rc;
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->raw_keep, pl->raw_pos, nraw + 1, s));
@@ -737,6 +740,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->raw_entries, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_flag, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_sci, pl->raw_cap));
+    A(pl_alloc(pl, &pl->raw_c0nci, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_keep, pl->raw_cap + 1));
     A(pl_alloc(pl, &pl->raw_pos, pl->raw_cap + 1));
     A(pl_alloc(pl, &pl->sci_off, pl->nsci_cap + 2));
