@@ -336,7 +336,7 @@ def main():
             traffic = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "fp32_simt", "kernel": "pair_cluster_kernel" if mode == 2 else "allpairs_kernel",
+    roofline = {"bound": "fp32_simt", "bound_note": "neither hbm nor tensor: the pair kernel is bound by the FP32 SIMT pipe (SURVEY.md 8d)", "kernel": "pair_cluster_kernel" if mode == 2 else "allpairs_kernel",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json)" % pk["source"],
@@ -346,7 +346,8 @@ def main():
     line = {"metric": "SDM dual-state force evals/s", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 pair arithmetic, f64 moved-pair/u/scalars, 64-bit fixed-point force accumulation",
+            "vs_baseline": None, "dtype": "f32",
+            "dtype_detail": "f32 pair terms (packed f32x2), f64 moved-pair terms / u / scalars / mix, 64-bit fixed-point force accumulation",
             "data": "shipped fixture (positions+topology), replica jitter synthetic" if args.workload in ("cfg1", "cfg2") else "synthetic",
             "config": {"workload": wname, "replicas_per_gpu": R, "lambda_schedule": "22-window ILogistic ladder",
                        "pair_mode": {1: "allpairs", 2: "cluster"}[mode], "skin_nm": args.skin, "nstlist": args.nstlist,
@@ -356,7 +357,8 @@ def main():
             "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_t / args.steps, "replica_groups": G,
-                    "note": "G contexts of R/G replicas on G streams; pinned host buffers; copies overlap kernels of other groups"},
+                    "note": "C-ABI calls with pinned HOST buffers: sdm_set_positions_all (H2D) + sdm_eval + sdm_enqueue_results (D2H of forces and scalars) "
+                            "per step inside the timed region; G replica groups = G contexts on G streams"},
             "clocks": sampler.result(), "wall_s_resident_leg": wall_resident}
 
     if rank == 0 and R > 1 and not args.no_single_lambda:
