@@ -235,6 +235,22 @@ int sdm_k_restore_state1(void* cuda_stream, int n, void* posq, const void* saved
  * (langevin.cl:72-87, OpenCLSDMKernels.cpp:273-275) */
 int sdm_k_hybrid_force(void* cuda_stream, int n, const void* f1, const void* f2, void* force,
                        float sp);
+/* The two integration kernels the plugin owns (langevin.cl:7-31 and :37-69, single-precision
+ * form; constraints are applied by OpenMM between them, OpenCLSDMKernels.cpp:357-372).
+ * velm = (vx, vy, vz, 1/mass); atoms with 1/mass == 0 are left untouched.  `random` holds
+ * normally distributed numbers, one float4 per atom starting at random_index.
+ *   part 1: v = vscale*v + fscale*(1/m)*F + noisescale*sqrt(1/m)*xi ; posDelta = stepSize*v
+ *   part 2: posq.xyz += posDelta.xyz ; v.xyz = posDelta.xyz/stepSize */
+int sdm_k_langevin_part1(void* cuda_stream, int n, void* velm, const void* force, void* pos_delta,
+                         float vscale, float fscale, float noisescale, float step_size,
+                         const void* random, uint32_t random_index);
+int sdm_k_langevin_part2(void* cuda_stream, int n, void* posq, const void* pos_delta, void* velm,
+                         float step_size);
+/* vscale = exp(-dt*friction), fscale = (1-vscale)/friction (dt when friction == 0),
+ * noisescale = sqrt(kT*(1-vscale^2)), kT = BOLTZ*temperature (OpenCLSDMKernels.cpp:331-336,
+ * BOLTZ at :57-60).  Units: K, 1/ps, ps. */
+int sdm_langevin_params(double temperature, double friction, double step_size, double* vscale,
+                        double* fscale, double* noisescale);
 /* Scalar half of execute() (ReferenceSDMKernels.cpp:205-302): from E1, E2, Eb and the
  * integrator state compute u_sc, fp, ebias, bfp, sp, PotEnergy, BindE and update the
  * non-equilibrium state in *alch.  O(1) host arithmetic, exactly as the reference does it on

@@ -99,6 +99,9 @@ SYMBOLS = {
     "sdm_k_save_state2": (_I, [_VP, _I, _VP, _VP]),
     "sdm_k_restore_state1": (_I, [_VP, _I, _VP, _VP]),
     "sdm_k_hybrid_force": (_I, [_VP, _I, _VP, _VP, _VP, C.c_float]),
+    "sdm_k_langevin_part1": (_I, [_VP, _I, _VP, _VP, _VP, C.c_float, C.c_float, C.c_float, C.c_float, _VP, C.c_uint32]),
+    "sdm_k_langevin_part2": (_I, [_VP, _I, _VP, _VP, _VP, C.c_float]),
+    "sdm_langevin_params": (_I, [_D, _D, _D, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D)]),
     "sdm_execute_scalars": (_I, [C.POINTER(SdmAlch), _D, _D, _D, C.POINTER(SdmScalars)]),
 }
 

@@ -862,6 +862,36 @@ int sdm_k_hybrid_force(void* stream, int n, const void* f1, const void* f2, void
     return SDM_OK;
 }
 
+int sdm_k_langevin_part1(void* stream, int n, void* velm, const void* force, void* pos_delta, float vscale,
+                         float fscale, float noisescale, float step_size, const void* random,
+                         uint32_t random_index) {
+    if (n < 0 || (n > 0 && (!velm || !force || !pos_delta || !random))) return fail(SDM_ERR_INVALID, "bad argument");
+    sdm::launch_langevin_part1(n, (float4*)velm, (const float4*)force, (float4*)pos_delta, vscale, fscale,
+                               noisescale, step_size, (const float4*)random, random_index, (cudaStream_t)stream);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_k_langevin_part2(void* stream, int n, void* posq, const void* pos_delta, void* velm, float step_size) {
+    if (n < 0 || (n > 0 && (!posq || !pos_delta || !velm))) return fail(SDM_ERR_INVALID, "bad argument");
+    if (!(step_size > 0.f)) return fail(SDM_ERR_INVALID, "step size must be positive");
+    sdm::launch_langevin_part2(n, (float4*)posq, (const float4*)pos_delta, (float4*)velm, step_size,
+                               (cudaStream_t)stream);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_langevin_params(double temperature, double friction, double step_size, double* vscale,
+                        double* fscale, double* noisescale) {
+    if (!vscale || !fscale || !noisescale) return fail(SDM_ERR_INVALID, "null argument");
+    const double BOLTZ = 1.380658e-23 * 6.0221367e23 / 1000.0;   // kJ/mol/K, OpenCLSDMKernels.cpp:57-60
+    const double kT = BOLTZ * temperature;
+    *vscale = std::exp(-step_size * friction);
+    *fscale = friction == 0 ? step_size : (1 - *vscale) / friction;
+    *noisescale = std::sqrt(kT * (1 - *vscale * *vscale));
+    return SDM_OK;
+}
+
 int sdm_execute_scalars(sdm_alch* alch, double E1, double E2, double Eb, sdm_scalars* out) {
     if (!alch || !out) return fail(SDM_ERR_INVALID, "null argument");
     std::memset(out, 0, sizeof(*out));

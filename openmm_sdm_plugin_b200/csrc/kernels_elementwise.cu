@@ -3,7 +3,7 @@
 //
 // Behaviour restated from platforms/opencl/src/kernels/langevin.cl:72-87 (sdmForce),
 // :147-155 (RestoreState1), :161-178 (SaveState1), :183-192 (SaveState2), :198-206
-// (MakeState2).  These are HBM-bound streaming kernels: 128-bit accesses, four independent
+// (MakeState2) and :7-69 (integrateLangevinPart1 / Part2, single-precision form).  These are HBM-bound streaming kernels: 128-bit accesses, four independent
 // loads in flight per thread, grid sized in multiples of the SM count, no shared memory
 // (there is no reuse), streaming cache hints for write-once data.
 #include "sdm_kernels.h"
@@ -87,6 +87,54 @@ hybrid_force_kernel(int n, const float4* __restrict__ f1, const float4* __restri
     }
 }
 
+// integrateLangevinPart1 (langevin.cl:7-31): for atoms with velm.w (inverse mass) != 0
+//   v = vscale*v + fscale*w*F + noisescale*sqrt(w)*xi ;  posDelta = stepSize*v   (all four lanes)
+// 80 B/atom.  Products and sums are evaluated left to right without FMA contraction, so the
+// result is the float32 expression as written (the tests compare bit for bit).
+__global__ void __launch_bounds__(kThreads)
+langevin_part1_kernel(int n, float4* __restrict__ velm, const float4* __restrict__ force,
+                      float4* __restrict__ pos_delta, float vscale, float fscale, float noisescale,
+                      float step_size, const float4* __restrict__ random, unsigned random_index) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 v = velm[i];
+        if (v.w != 0.0f) {
+            const float4 f = ld_stream(force + i), r = ld_stream(random + random_index + i);
+            const float s = sqrtf(v.w), fw = __fmul_rn(fscale, v.w), ns = __fmul_rn(noisescale, s);
+            v.x = __fadd_rn(__fadd_rn(__fmul_rn(vscale, v.x), __fmul_rn(fw, f.x)), __fmul_rn(ns, r.x));
+            v.y = __fadd_rn(__fadd_rn(__fmul_rn(vscale, v.y), __fmul_rn(fw, f.y)), __fmul_rn(ns, r.y));
+            v.z = __fadd_rn(__fadd_rn(__fmul_rn(vscale, v.z), __fmul_rn(fw, f.z)), __fmul_rn(ns, r.z));
+            velm[i] = v;
+            st_stream(pos_delta + i, make_float4(__fmul_rn(step_size, v.x), __fmul_rn(step_size, v.y),
+                                                 __fmul_rn(step_size, v.z), __fmul_rn(step_size, v.w)));
+        }
+    }
+}
+
+// integrateLangevinPart2 (langevin.cl:37-69, single precision branch): for atoms with velm.w != 0
+//   posq.xyz += posDelta.xyz ;  vel.xyz = invStep*delta.xyz + correction*delta.xyz
+// with invStep = 1/dt and correction = (1 - invStep*dt)/dt.  80 B/atom.
+__global__ void __launch_bounds__(kThreads)
+langevin_part2_kernel(int n, float4* __restrict__ posq, const float4* __restrict__ pos_delta,
+                      float4* __restrict__ velm, float step_size) {
+    const float inv = __fdiv_rn(1.0f, step_size);
+    const float corr = __fdiv_rn(__fsub_rn(1.0f, __fmul_rn(inv, step_size)), step_size);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 v = velm[i];
+        if (v.w != 0.0f) {
+            float4 p = posq[i];
+            const float4 d = ld_stream(pos_delta + i);
+            p.x = __fadd_rn(p.x, d.x); p.y = __fadd_rn(p.y, d.y); p.z = __fadd_rn(p.z, d.z);
+            v.x = __fadd_rn(__fmul_rn(inv, d.x), __fmul_rn(corr, d.x));
+            v.y = __fadd_rn(__fmul_rn(inv, d.y), __fmul_rn(corr, d.y));
+            v.z = __fadd_rn(__fmul_rn(inv, d.z), __fmul_rn(corr, d.z));
+            posq[i] = p;
+            velm[i] = v;
+        }
+    }
+}
+
 int grid_for(int n, int per_thread) {
     long long want = ((long long)n + (long long)kThreads * per_thread - 1) / ((long long)kThreads * per_thread);
     const int cap = 148 * 8;  // 8 resident 256-thread CTAs per SM on B200
@@ -113,6 +161,19 @@ void launch_hybrid_force(int n, const float4* f1, const float4* f2, float4* forc
                          cudaStream_t s) {
     if (n <= 0) return;
     hybrid_force_kernel<<<grid_for(n, 2), kThreads, 0, s>>>(n, f1, f2, force, sp);
+}
+
+void launch_langevin_part1(int n, float4* velm, const float4* force, float4* pos_delta, float vscale,
+                           float fscale, float noisescale, float step_size, const float4* random,
+                           unsigned random_index, cudaStream_t s) {
+    if (n <= 0) return;
+    langevin_part1_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(n, velm, force, pos_delta, vscale, fscale,
+                                                             noisescale, step_size, random, random_index);
+}
+void launch_langevin_part2(int n, float4* posq, const float4* pos_delta, float4* velm, float step_size,
+                           cudaStream_t s) {
+    if (n <= 0) return;
+    langevin_part2_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(n, posq, pos_delta, velm, step_size);
 }
 
 }  // namespace sdm

@@ -71,5 +71,10 @@ void launch_save_state1(int n, const float4* posq, const float4* force, float4* 
 void launch_copy4(int n, const float4* src, float4* dst, cudaStream_t s);
 void launch_hybrid_force(int n, const float4* f1, const float4* f2, float4* force, float sp,
                          cudaStream_t s);
+void launch_langevin_part1(int n, float4* velm, const float4* force, float4* pos_delta, float vscale,
+                           float fscale, float noisescale, float step_size, const float4* random,
+                           unsigned random_index, cudaStream_t s);
+void launch_langevin_part2(int n, float4* posq, const float4* pos_delta, float4* velm, float step_size,
+                           cudaStream_t s);
 
 }  // namespace sdm

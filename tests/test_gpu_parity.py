@@ -272,3 +272,56 @@ def test_elementwise_kernel_interface_ops():
     torch.cuda.synchronize()
     want = (np.float32(1.0) - sp) * f1.cpu().numpy() + sp * f2.cpu().numpy() + fo0.cpu().numpy()
     assert np.allclose(force.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+
+
+def test_langevin_kernel_interface_ops():
+    """(B) integrateLangevinPart1 / Part2 (langevin.cl:7-69, single-precision form) on device float4
+    buffers, bit for bit against the same float32 expressions in numpy; parameters from
+    sdm_langevin_params (OpenCLSDMKernels.cpp:331-336)."""
+    import ctypes as C
+    import torch
+    L = _lib.lib()
+    vs, fs, ns = C.c_double(), C.c_double(), C.c_double()
+    _lib.check(L.sdm_langevin_params(300.0, 0.5, 0.001, C.byref(vs), C.byref(fs), C.byref(ns)))
+    kT = 1.380658e-23 * 6.0221367e23 / 1000.0 * 300.0
+    assert vs.value == np.exp(-0.001 * 0.5) and abs(fs.value - (1 - vs.value) / 0.5) < 1e-18
+    assert abs(ns.value - np.sqrt(kT * (1 - vs.value ** 2))) < 1e-15
+    _lib.check(L.sdm_langevin_params(300.0, 0.0, 0.002, C.byref(vs), C.byref(fs), C.byref(ns)))
+    assert fs.value == 0.002 and ns.value == 0.0          # friction == 0: fscale = dt, no noise
+    _lib.check(L.sdm_langevin_params(300.0, 0.5, 0.001, C.byref(vs), C.byref(fs), C.byref(ns)))
+
+    n, off = 50_001, 17
+    rng = np.random.default_rng(4)
+    velm = rng.normal(size=(n, 4)).astype(np.float32)
+    velm[:, 3] = 1.0 / rng.uniform(1.0, 16.0, n).astype(np.float32)
+    velm[::97, 3] = 0.0                                     # massless particles are left alone
+    force = rng.normal(scale=300.0, size=(n, 4)).astype(np.float32)
+    posq = rng.uniform(0, 5, size=(n, 4)).astype(np.float32)
+    rnd = rng.normal(size=(n + off, 4)).astype(np.float32)
+    d_velm, d_force, d_posq, d_rnd = (torch.from_numpy(a).cuda() for a in (velm, force, posq, rnd))
+    d_delta = torch.full((n, 4), 7.0, dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    f32 = np.float32
+    vscale, fscale, noise, dt = f32(vs.value), f32(fs.value), f32(ns.value), f32(0.001)
+    _lib.check(L.sdm_k_langevin_part1(st, n, d_velm.data_ptr(), d_force.data_ptr(), d_delta.data_ptr(),
+                                      float(vscale), float(fscale), float(noise), float(dt), d_rnd.data_ptr(), off))
+    torch.cuda.synchronize()
+    w = velm[:, 3:4]
+    live = (w != 0)[:, 0]
+    v1 = velm.copy()
+    v1[:, :3] = (vscale * velm[:, :3] + (fscale * w) * force[:, :3]) + (noise * np.sqrt(w)) * rnd[off:off + n, :3]
+    v1[~live] = velm[~live]
+    delta = np.full((n, 4), 7.0, np.float32)
+    delta[live] = dt * v1[live]
+    assert np.array_equal(d_velm.cpu().numpy(), v1)
+    assert np.array_equal(d_delta.cpu().numpy(), delta)
+
+    _lib.check(L.sdm_k_langevin_part2(st, n, d_posq.data_ptr(), d_delta.data_ptr(), d_velm.data_ptr(), float(dt)))
+    torch.cuda.synchronize()
+    inv = f32(1.0) / dt
+    corr = (f32(1.0) - inv * dt) / dt
+    p2, v2 = posq.copy(), v1.copy()
+    p2[live, :3] = posq[live, :3] + delta[live, :3]
+    v2[live, :3] = inv * delta[live, :3] + corr * delta[live, :3]
+    assert np.array_equal(d_posq.cpu().numpy(), p2)
+    assert np.array_equal(d_velm.cpu().numpy(), v2)
