@@ -224,7 +224,12 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (int k = 0; k < 4; k++) TRYCUDA(cudaEventCreate(&c->ev[k]));
-    TRYCUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    {
+        // the side stream gets the highest priority: its small kernels take every slot that frees up
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        TRYCUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi_p));
+    }
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
