@@ -410,13 +410,17 @@ __device__ __forceinline__ void probe_pair(const Topology& T, const double* __re
     A.fx += px; A.fy += py; A.fz += pz;
 }
 
-constexpr int kProbeThreads = 128;
+#ifndef SDM_PROBE_THREADS
+#define SDM_PROBE_THREADS 512
+#endif
+constexpr int kProbeThreads = SDM_PROBE_THREADS;
+constexpr int kProbeWarps = kProbeThreads / 32;
 constexpr int kProbeWords = 1024;   // bitmap words handled per pass
 
 __global__ void __launch_bounds__(kProbeThreads)
 ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
-    __shared__ double s_red[32];
-    __shared__ long long s_redl[32];
+    __shared__ double s_red[4 * kProbeWarps];
+    __shared__ long long s_redl[2 * kProbeWarps];
     __shared__ uint32_t s_bits[kProbeWords];
     __shared__ int s_pre[kProbeWords + 1];
     __shared__ int s_wsum[kProbeThreads / 32 + 1];
@@ -504,12 +508,26 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         probe_pair(T, pos, P, T.lig_idx[mm], true, A, px, py, pz);
     }
 
-    double sx = block_sum(A.fx, s_red);
-    double sy = block_sum(A.fy, s_red);
-    double sz = block_sum(A.fz, s_red);
-    double su = block_sum(A.u, s_red);
-    long long sc1 = block_sum_ll(A.c1, s_redl);
-    long long sc2 = block_sum_ll(A.c2, s_redl);
+    // one fixed-order block reduction for all six sums: warp trees, then thread 0 adds the warp
+    // totals in warp order
+    double sx = warp_sum(A.fx), sy = warp_sum(A.fy), sz = warp_sum(A.fz), su = warp_sum(A.u);
+    long long sc1 = warp_sum_ll(A.c1), sc2 = warp_sum_ll(A.c2);
+    __syncthreads();
+    if (lane == 0) {
+        s_red[warp] = sx; s_red[kProbeWarps + warp] = sy; s_red[2 * kProbeWarps + warp] = sz;
+        s_red[3 * kProbeWarps + warp] = su;
+        s_redl[warp] = sc1; s_redl[kProbeWarps + warp] = sc2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sx = sy = sz = su = 0.0;
+        sc1 = sc2 = 0;
+        for (int k = 0; k < kProbeWarps; k++) {
+            sx += s_red[k]; sy += s_red[kProbeWarps + k]; sz += s_red[2 * kProbeWarps + k];
+            su += s_red[3 * kProbeWarps + k];
+            sc1 += s_redl[k]; sc2 += s_redl[kProbeWarps + k];
+        }
+    }
     if (threadIdx.x == 0) {
         double* dF = B.dF + (size_t)r * 3 * n;
         dF[3 * P.i] = sx; dF[3 * P.i + 1] = sy; dF[3 * P.i + 2] = sz;
@@ -525,6 +543,7 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
 // through the bitmap: h = hitpre[row][w] + popc(bits below this lane).  Pure loads; writes every
 // dF_j (zero when nothing is near), so no memset is needed.
 constexpr int kGatherThreads = 128;
+constexpr int kGatherBatch = 4;
 
 __global__ void __launch_bounds__(kGatherThreads)
 ligand_gather_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
@@ -548,19 +567,33 @@ ligand_gather_kernel(const __grid_constant__ Topology T, const __grid_constant__
     const uint32_t below = (1u << lane) - 1u;
     const size_t wbase = ((size_t)r * B.scan_words + sw) * T.n_lig;
     for (int m0 = 0; m0 < T.n_lig; m0 += 32) {
-        // the words of this warp for 32 displaced atoms: one coalesced load, most warps see zeros
-        const uint32_t mine = m0 + lane < T.n_lig ? B.hitbits[wbase + m0 + lane] : 0u;
+        // the words (and their hit prefixes) of this warp for 32 displaced atoms: two coalesced
+        // loads, most warps see zeros
+        const bool mv = m0 + lane < T.n_lig;
+        const uint32_t mine = mv ? B.hitbits[wbase + m0 + lane] : 0u;
+        const int pre_mine = mv ? B.hitpre[wbase + m0 + lane] : 0;
         unsigned todo = __ballot_sync(0xffffffffu, mine != 0u);
         while (todo) {
-            const int ml = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const uint32_t word = __shfl_sync(0xffffffffu, mine, ml);
-            if (!((word >> lane) & 1u)) continue;
-            const int m = m0 + ml;
-            const int h = B.hitpre[wbase + m] + __popc(word & below);
-            if (h >= B.pairf_cap) continue;   // overflow was flagged by the probe kernel
-            const double* f = B.pairf + (((size_t)r * T.n_lig + m) * (size_t)B.pairf_cap + h) * 3;
-            fx += f[0]; fy += f[1]; fz += f[2];
+            // four displaced atoms per round: their loads are in flight together; the sums keep
+            // the displaced-atom order (a skipped term adds +0.0)
+            double v[kGatherBatch][3];
+#pragma unroll
+            for (int b = 0; b < kGatherBatch; b++) {
+                v[b][0] = v[b][1] = v[b][2] = 0.0;
+                if (todo) {   // uniform
+                    const int ml = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const uint32_t word = __shfl_sync(0xffffffffu, mine, ml);
+                    const int h = __shfl_sync(0xffffffffu, pre_mine, ml) + __popc(word & below);
+                    // h >= cap: overflow was flagged by the probe kernel
+                    if (((word >> lane) & 1u) && h < B.pairf_cap) {
+                        const double* f = B.pairf + (((size_t)r * T.n_lig + m0 + ml) * (size_t)B.pairf_cap + h) * 3;
+                        v[b][0] = f[0]; v[b][1] = f[1]; v[b][2] = f[2];
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < kGatherBatch; b++) { fx += v[b][0]; fy += v[b][1]; fz += v[b][2]; }
         }
     }
     if (active) {

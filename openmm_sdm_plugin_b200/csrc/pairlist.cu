@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,7 +19,7 @@ using nbl::BBox;
 using nbl::Grid;
 using nbl::SciDesc;
 
-constexpr int kChunk = 32;  // default j-group entries per work unit
+constexpr int kChunk = 32;  // j-group entries per work unit (one per lane; shorter units measured slower at every size)
 
 struct PairList {
     Grid G{};
@@ -620,6 +621,7 @@ static int build_list(sdm_ctx* c) {
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->entry_flag, pl->entry_midx, pl->nentries + 1, s));
     PL_CUDA(cudaMemcpyAsync(&pl->h_counts[3], pl->entry_midx + pl->nentries, sizeof(int), cudaMemcpyDeviceToHost, s));
     // units
+    if (const char* e = getenv("SDMB200_CHUNK")) pl->chunk = std::min(kChunk, std::max(1, atoi(e)));   // development knob
     sci_units_count_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_nunits);
     PL_CUDA(cudaMemsetAsync(pl->sci_nunits + pl->nsci, 0, sizeof(int), s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->sci_nunits, pl->sci_unit_off, pl->nsci + 1, s));

@@ -270,6 +270,57 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
         nunits += (len + chunk - 1) / chunk;
     }
 
+    if (getenv("SDM_HOSTCHECK_STATS")) {
+        // pairing statistics: consecutive unmasked entries of a unit taken two at a time
+        long both = 0, one = 0, single_tiles = 0, masked_tiles = 0, npairs = 0, nsingle = 0, nmasked = 0;
+        for (int s = 0; s < nsci; s++)
+            for (int b = sci_off[s]; b < sci_off[s + 1]; b += chunk) {
+                const int e1 = std::min(b + chunk, sci_off[s + 1]);
+                std::vector<uint32_t> um;
+                for (int e = b; e < e1; e++) {
+                    if (ey[e] >> 8) { nmasked++; masked_tiles += __builtin_popcount(ey[e] & 0xffu); }
+                    else um.push_back(ey[e] & 0xffu);
+                }
+                size_t k = 0;
+                for (; k + 1 < um.size(); k += 2) {
+                    npairs++;
+                    both += __builtin_popcount(um[k] & um[k + 1]);
+                    one += __builtin_popcount(um[k] ^ um[k + 1]);
+                }
+                if (k < um.size()) { nsingle++; single_tiles += __builtin_popcount(um[k]); }
+            }
+        {
+            // all entries of a unit (masked too), ordered by imask value, then paired; and a greedy
+            // minimum-Hamming-distance pairing for comparison
+            long tiles = 0, un_sorted = 0, un_plain = 0, un_greedy = 0, steps = 0;
+            for (int s = 0; s < nsci; s++)
+                for (int b = sci_off[s]; b < sci_off[s + 1]; b += chunk) {
+                    const int e1 = std::min(b + chunk, sci_off[s + 1]);
+                    std::vector<uint32_t> m;
+                    for (int e = b; e < e1; e++) { m.push_back(ey[e] & 0xffu); tiles += __builtin_popcount(ey[e] & 0xffu); }
+                    steps += ((long)m.size() + 1) / 2;
+                    for (size_t k = 0; k < m.size(); k += 2) un_plain += __builtin_popcount(m[k] | (k + 1 < m.size() ? m[k + 1] : 0u));
+                    std::vector<uint32_t> q = m;
+                    std::sort(q.begin(), q.end());
+                    for (size_t k = 0; k < q.size(); k += 2) un_sorted += __builtin_popcount(q[k] | (k + 1 < q.size() ? q[k + 1] : 0u));
+                    std::vector<char> used(m.size(), 0);
+                    for (size_t a = 0; a < m.size(); a++) {
+                        if (used[a]) continue;
+                        used[a] = 1;
+                        int best = -1, bd = 99;
+                        for (size_t c = a + 1; c < m.size(); c++)
+                            if (!used[c] && __builtin_popcount(m[a] ^ m[c]) < bd) { bd = __builtin_popcount(m[a] ^ m[c]); best = (int)c; }
+                        if (best >= 0) { used[best] = 1; un_greedy += __builtin_popcount(m[a] | m[best]); }
+                        else un_greedy += __builtin_popcount(m[a]);
+                    }
+                }
+            fprintf(stderr, "union pairing: tiles %ld steps %ld | 2*union plain %ld sorted %ld greedy %ld\n", tiles, steps,
+                    2 * un_plain, 2 * un_sorted, 2 * un_greedy);
+        }
+        fprintf(stderr, "pairing: pairs %ld both %ld one %ld | singles %ld tiles %ld | masked %ld tiles %ld | units %d\n",
+                npairs, both, one, nsingle, single_tiles, nmasked, masked_tiles, nunits);
+    }
+
     // traversal exactly like the pair kernel: lane (tj, ti) = (lane>>2, lane&3) evaluates i-atoms
     // ti and ti+4 (halves h = 0, 1) of cluster ci against j-atom tj of the entry's j-cluster
     std::vector<std::pair<int, int>> found;
