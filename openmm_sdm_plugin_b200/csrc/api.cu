@@ -493,6 +493,7 @@ int sdm_set_displacement(sdm_ctx* c, const double* displacement) {
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     if (int rc = upload_displacement(c, displacement)) return rc;
     c->graph_valid = false;   // the number of displaced atoms sizes two launches
+    c->list_valid = false;    // the candidate lists of the displaced atoms are built with the pair list
     return SDM_OK;
 }
 
@@ -510,7 +511,10 @@ int sdm_invalidate_list(sdm_ctx* c) {
 static void enqueue_position_only(sdm_ctx* c, cudaStream_t s) {
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;
-    if (T.n_lig > 0) {
+    if (T.n_lig > 0 && c->pair_mode == SDM_PAIR_CLUSTER) {
+        sdm::launch_ligand_probe_list(T, B, s);   // candidates were laid down at the list build
+        c->launches += 1;
+    } else if (T.n_lig > 0) {
         sdm::launch_ligand_filter(T, B, s);
         sdm::launch_ligand_probe(T, B, s);
         c->launches += 2;
@@ -559,8 +563,10 @@ static int ensure_hitbits(sdm_ctx* c) {
     // hits per row: atoms within the cutoff of a displaced atom in either state, at up to ~2x
     // liquid-water number density; everything when there is no cutoff
     int cap = c->n;
+    const bool static_cand = c->pair_mode == SDM_PAIR_CLUSTER;
+    B.filter_skin = static_cand ? (float)c->opt.skin : 0.f;
     if (T.method != SDM_NOCUTOFF) {
-        const double r = T.rc + 0.05;
+        const double r = T.rc + B.filter_skin + 0.05;
         cap = (int)std::min<double>(c->n, (2.0 * 4.19 * r * r * r * 200.0 + 64.0) * c->pairf_scale);
     }
     cap = std::max(cap, 32);
@@ -569,10 +575,26 @@ static int ensure_hitbits(sdm_ctx* c) {
         c->pairf_alloc = need_f;
         if (int rc = regrow_bytes(c, (void**)&c->d_pairf, c->pairf_alloc * sizeof(double))) return rc;
     }
+    if (static_cand) {
+        const size_t need_c = rows * (size_t)cap;
+        if (need_c > c->cand_alloc) {
+            c->cand_alloc = need_c;
+            if (int rc = regrow_bytes(c, (void**)&c->d_cand, c->cand_alloc * sizeof(int))) return rc;
+            c->lig_built_for = -1;
+        }
+        if (rows > c->cand_rows) {
+            c->cand_rows = rows;
+            if (int rc = regrow_bytes(c, (void**)&c->d_cand_count, c->cand_rows * sizeof(int))) return rc;
+            c->lig_built_for = -1;
+        }
+    }
+    if (cap != B.pairf_cap) c->lig_built_for = -1;   // the candidate rows are laid out with this stride
     B.hitbits = c->d_hitbits;
     B.hitpre = c->d_hitpre;
     B.pairf = c->d_pairf;
     B.pairf_cap = cap;
+    B.cand = c->d_cand;
+    B.cand_count = c->d_cand_count;
     return SDM_OK;
 }
 
@@ -615,6 +637,14 @@ int sdm_eval(sdm_ctx* c) {
         }
         int rc = sdm_ctx_pairlist_prepare(c);   // list (re)build or refresh of the sorted positions
         if (!rc) rc = ensure_hitbits(c);         // no-op while capturing (sized before the capture began)
+        if (!rc && T.n_lig > 0 && c->lig_built_for != c->n_builds) {
+            // new list (never inside a capture: a rebuild is not graphable): prefilter with the
+            // list's skin, rows expanded into the candidate lists the evaluations walk
+            sdm::launch_ligand_filter(T, B, s);
+            sdm::launch_ligand_compact(T, B, s);
+            c->launches += 2;
+            c->lig_built_for = c->n_builds;
+        }
         if (!rc) {
             // fork: the displaced-atom pair terms only need the positions; they fill the tail of
             // the (persistent) pair kernel instead of waiting for it.  Serial when the pair kernel
@@ -664,6 +694,7 @@ static void note_status(sdm_ctx* c, int status) {
     if (status == SDM_ERR_CAPACITY && c->pairf_scale < (1 << 16)) {
         c->pairf_scale *= 2;
         c->graph_valid = false;
+        c->list_valid = false;   // cluster path: the candidate lists are laid down with the list
     }
     // an atom outran the list buffer: the next evaluation rebuilds the list (the caller repeats
     // the evaluation; forces of the flagged one may miss pairs)

@@ -290,7 +290,8 @@ ligand_filter_kernel(const __grid_constant__ Topology T, const __grid_constant__
     const bool active = j >= 0 && T.group[j] == 0;
     const bool cutoff = T.method != SDM_NOCUTOFF;
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
-    const float lim = T.rc2f * 1.0001f + 1.0e-4f;
+    const float rl = sqrtf(T.rc2f) + B.filter_skin;   // cluster path: + skin, the bitmap outlives this eval
+    const float lim = rl * rl * 1.0001f + 1.0e-4f;
     const float rlim = sqrtf(lim);
     const float3 hbox = make_float3(0.5f * T.boxf[0], 0.5f * T.boxf[1], 0.5f * T.boxf[2]);
     const float4 pf = active ? B.scan_posq[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -417,6 +418,54 @@ constexpr int kProbeThreads = SDM_PROBE_THREADS;
 constexpr int kProbeWarps = kProbeThreads / 32;
 constexpr int kProbeWords = 1024;   // bitmap words handled per pass
 
+// Second half of both probe kernels: the other displaced atoms (different displacement group;
+// walked directly, no prefilter), then ONE fixed-order block reduction for all six sums (warp
+// trees, thread 0 adds the warp totals in warp order) and the per-atom outputs.
+__device__ __forceinline__ void probe_finish(const Topology& T, const EvalBuffers& B, const ProbeAtom& P,
+                                             ProbeAcc& A, const double* __restrict__ pos, int m, int r,
+                                             double* s_red /* 4*kProbeWarps */,
+                                             long long* s_redl /* 2*kProbeWarps */) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n = T.n;
+    for (int mm = threadIdx.x; mm < T.n_lig; mm += kProbeThreads) {
+        double px, py, pz;
+        probe_pair(T, pos, P, T.lig_idx[mm], true, A, px, py, pz);
+    }
+    double sx = warp_sum(A.fx), sy = warp_sum(A.fy), sz = warp_sum(A.fz), su = warp_sum(A.u);
+    long long sc1 = warp_sum_ll(A.c1), sc2 = warp_sum_ll(A.c2);
+    __syncthreads();
+    if (lane == 0) {
+        s_red[warp] = sx; s_red[kProbeWarps + warp] = sy; s_red[2 * kProbeWarps + warp] = sz;
+        s_red[3 * kProbeWarps + warp] = su;
+        s_redl[warp] = sc1; s_redl[kProbeWarps + warp] = sc2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sx = sy = sz = su = 0.0;
+        sc1 = sc2 = 0;
+        for (int k = 0; k < kProbeWarps; k++) {
+            sx += s_red[k]; sy += s_red[kProbeWarps + k]; sz += s_red[2 * kProbeWarps + k];
+            su += s_red[3 * kProbeWarps + k];
+            sc1 += s_redl[k]; sc2 += s_redl[kProbeWarps + k];
+        }
+        double* dF = B.dF + (size_t)r * 3 * n;
+        dF[3 * P.i] = sx; dF[3 * P.i + 1] = sy; dF[3 * P.i + 2] = sz;
+        B.upart[(size_t)r * T.n_lig + m] = su;
+        B.mcnt[((size_t)r * T.n_lig + m) * 2] = sc1;
+        B.mcnt[((size_t)r * T.n_lig + m) * 2 + 1] = sc2;
+    }
+}
+
+__device__ __forceinline__ ProbeAtom load_probe_atom(const Topology& T, const double* __restrict__ pos, int m) {
+    ProbeAtom P;
+    P.i = T.lig_idx[m];
+    P.gi = T.group[P.i];
+    P.flags = T.lig_flags[m];
+    P.x1 = pos[3 * P.i]; P.y1 = pos[3 * P.i + 1]; P.z1 = pos[3 * P.i + 2];
+    P.x2 = P.x1 + T.disp[3 * P.i]; P.y2 = P.y1 + T.disp[3 * P.i + 1]; P.z2 = P.z1 + T.disp[3 * P.i + 2];
+    P.q = T.q[P.i]; P.hsig = T.hsig[P.i]; P.heps = T.heps[P.i];
+    return P;
+}
+
 __global__ void __launch_bounds__(kProbeThreads)
 ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
     __shared__ double s_red[4 * kProbeWarps];
@@ -427,13 +476,7 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
     const int m = blockIdx.x, r = blockIdx.y, n = T.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* pos = B.pos + (size_t)r * 3 * n;
-    ProbeAtom P;
-    P.i = T.lig_idx[m];
-    P.gi = T.group[P.i];
-    P.flags = T.lig_flags[m];
-    P.x1 = pos[3 * P.i]; P.y1 = pos[3 * P.i + 1]; P.z1 = pos[3 * P.i + 2];
-    P.x2 = P.x1 + T.disp[3 * P.i]; P.y2 = P.y1 + T.disp[3 * P.i + 1]; P.z2 = P.z1 + T.disp[3 * P.i + 2];
-    P.q = T.q[P.i]; P.hsig = T.hsig[P.i]; P.heps = T.heps[P.i];
+    const ProbeAtom P = load_probe_atom(T, pos, m);
     int begin, end;
     scan_range(T, B, r, &begin, &end);
     const size_t row = (size_t)r * T.n_lig + m;
@@ -502,39 +545,98 @@ ligand_probe_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         row_base += total;
     }
     if (row_base > B.pairf_cap && threadIdx.x == 0) atomicExch(B.flags + r, SDM_ERR_CAPACITY);
-    // (2) the other displaced atoms (different displacement group), no prefilter
-    for (int mm = threadIdx.x; mm < T.n_lig; mm += kProbeThreads) {
-        double px, py, pz;
-        probe_pair(T, pos, P, T.lig_idx[mm], true, A, px, py, pz);
-    }
+    probe_finish(T, B, P, A, pos, m, r, s_red, s_redl);
+}
 
-    // one fixed-order block reduction for all six sums: warp trees, then thread 0 adds the warp
-    // totals in warp order
-    double sx = warp_sum(A.fx), sy = warp_sum(A.fy), sz = warp_sum(A.fz), su = warp_sum(A.u);
-    long long sc1 = warp_sum_ll(A.c1), sc2 = warp_sum_ll(A.c2);
-    __syncthreads();
-    if (lane == 0) {
-        s_red[warp] = sx; s_red[kProbeWarps + warp] = sy; s_red[2 * kProbeWarps + warp] = sz;
-        s_red[3 * kProbeWarps + warp] = su;
-        s_redl[warp] = sc1; s_redl[kProbeWarps + warp] = sc2;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        sx = sy = sz = su = 0.0;
-        sc1 = sc2 = 0;
-        for (int k = 0; k < kProbeWarps; k++) {
-            sx += s_red[k]; sy += s_red[kProbeWarps + k]; sz += s_red[2 * kProbeWarps + k];
-            su += s_red[3 * kProbeWarps + k];
-            sc1 += s_redl[k]; sc2 += s_redl[kProbeWarps + k];
+// ---- static candidates (cluster path) -------------------------------------------------------------
+// At every list rebuild the prefilter runs once with the list's skin added to the cutoff; this
+// kernel (one block per (displaced atom, replica)) expands the bitmap row into the candidate list
+// cand[row][h] = resting atom of hit h, in scan order, and writes the per-word prefix hitpre the
+// gather kernel needs.  Bitmap, prefix and candidates stay valid as long as the pair list does (no
+// atom further than skin/2 from its position at build time), so an evaluation only runs the
+// probe-list and gather kernels.
+constexpr int kCompactThreads = 256;
+
+__global__ void __launch_bounds__(kCompactThreads)
+ligand_compact_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
+    __shared__ uint32_t s_bits[kProbeWords];
+    __shared__ int s_wsum[kCompactThreads / 32 + 1];
+    const int m = blockIdx.x, r = blockIdx.y, n = T.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int begin, end;
+    scan_range(T, B, r, &begin, &end);
+    const size_t row = (size_t)r * T.n_lig + m;
+    const uint32_t* bits = B.hitbits + (size_t)r * B.scan_words * T.n_lig + m;
+    int* pre_out = B.hitpre + (size_t)r * B.scan_words * T.n_lig + m;
+    const size_t wstride = (size_t)T.n_lig;
+    int* cand = B.cand + row * (size_t)B.pairf_cap;
+    const int nwords = min(B.scan_words, (end - begin + 31) / 32);
+    int row_base = 0;
+    for (int w0 = 0; w0 < nwords; w0 += kProbeWords) {
+        const int nw = min(kProbeWords, nwords - w0);
+        __syncthreads();
+        constexpr int kRun = kProbeWords / kCompactThreads;
+        int run = 0;
+        for (int k = 0; k < kRun; k++) {
+            const int w = threadIdx.x * kRun + k;
+            const uint32_t v = w < nw ? bits[(size_t)(w0 + w) * wstride] : 0u;
+            s_bits[w] = v;
+            run += __popc(v);
         }
+        int incl = run;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp + 1] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_wsum[0] = 0;
+            for (int k = 1; k <= kCompactThreads / 32; k++) s_wsum[k] += s_wsum[k - 1];
+        }
+        __syncthreads();
+        int acc = row_base + s_wsum[warp] + incl - run;
+        for (int k = 0; k < kRun; k++) {
+            const int w = threadIdx.x * kRun + k;
+            if (w >= nw) break;
+            pre_out[(size_t)(w0 + w) * wstride] = acc;
+            uint32_t v = s_bits[w];
+            while (v) {
+                const int bit = __ffs(v) - 1;
+                v &= v - 1u;
+                const int idx = begin + (w0 + w) * 32 + bit;
+                if (acc < B.pairf_cap) cand[acc] = B.scan_atom ? B.scan_atom[idx] - r * n : idx - begin;
+                acc++;
+            }
+        }
+        row_base += s_wsum[kCompactThreads / 32];
     }
-    if (threadIdx.x == 0) {
-        double* dF = B.dF + (size_t)r * 3 * n;
-        dF[3 * P.i] = sx; dF[3 * P.i + 1] = sy; dF[3 * P.i + 2] = sz;
-        B.upart[(size_t)r * T.n_lig + m] = su;
-        B.mcnt[((size_t)r * T.n_lig + m) * 2] = sc1;
-        B.mcnt[((size_t)r * T.n_lig + m) * 2 + 1] = sc2;
+    if (threadIdx.x == 0) B.cand_count[row] = row_base;   // > pairf_cap: reported by every evaluation
+}
+
+// Per evaluation: the exact (FP64) dual-state terms of the candidates of one displaced atom, one
+// block per (displaced atom, replica).  pairf[row][h] = -(f_i(2) - f_i(1)) for the gather kernel
+// (zero for a candidate that is outside the cutoff in both states).
+__global__ void __launch_bounds__(kProbeThreads)
+ligand_probe_list_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
+    __shared__ double s_red[4 * kProbeWarps];
+    __shared__ long long s_redl[2 * kProbeWarps];
+    const int m = blockIdx.x, r = blockIdx.y, n = T.n;
+    const double* pos = B.pos + (size_t)r * 3 * n;
+    const ProbeAtom P = load_probe_atom(T, pos, m);
+    const size_t row = (size_t)r * T.n_lig + m;
+    const int* cand = B.cand + row * (size_t)B.pairf_cap;
+    double* pf_out = B.pairf + row * (size_t)B.pairf_cap * 3;
+    const int total = B.cand_count[row];
+    if (total > B.pairf_cap && threadIdx.x == 0) atomicExch(B.flags + r, SDM_ERR_CAPACITY);
+    const int cnt = min(total, B.pairf_cap);
+    ProbeAcc A{0, 0, 0, 0, 0, 0};
+    for (int h = threadIdx.x; h < cnt; h += kProbeThreads) {
+        double px, py, pz;
+        probe_pair(T, pos, P, cand[h], (P.flags & 1) != 0, A, px, py, pz);
+        pf_out[3 * (size_t)h] = -px; pf_out[3 * (size_t)h + 1] = -py; pf_out[3 * (size_t)h + 2] = -pz;
     }
+    probe_finish(T, B, P, A, pos, m, r, s_red, s_redl);
 }
 
 // ---- gather kernel -------------------------------------------------------------------------------
@@ -799,6 +901,18 @@ void launch_ligand_filter(const Topology& T, const EvalBuffers& B, cudaStream_t 
 void launch_ligand_gather(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
     dim3 grid((B.scan_words * 32 + kGatherThreads - 1) / kGatherThreads, B.R);
     ligand_gather_kernel<<<grid, kGatherThreads, 0, s>>>(T, B);
+}
+
+void launch_ligand_compact(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+    if (T.n_lig <= 0) return;
+    dim3 grid(T.n_lig, B.R);
+    ligand_compact_kernel<<<grid, kCompactThreads, 0, s>>>(T, B);
+}
+
+void launch_ligand_probe_list(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+    if (T.n_lig <= 0) return;
+    dim3 grid(T.n_lig, B.R);
+    ligand_probe_list_kernel<<<grid, kProbeThreads, 0, s>>>(T, B);
 }
 
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) {

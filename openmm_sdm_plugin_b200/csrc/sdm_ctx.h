@@ -34,6 +34,10 @@ struct sdm_ctx {
     double* d_pairf = nullptr;
     size_t pairf_alloc = 0;             // doubles allocated for d_pairf
     int pairf_scale = 1;                // doubled whenever an eval reports SDM_ERR_CAPACITY
+    int* d_cand = nullptr;              // cluster path: candidate resting atoms per displaced atom
+    int* d_cand_count = nullptr;
+    size_t cand_alloc = 0, cand_rows = 0;
+    int64_t lig_built_for = -1;         // n_builds the candidates were built with
 
     std::vector<sdm_alch> h_alch;       // staging copies with ctx lifetime
     std::vector<double> h_eb;

@@ -42,6 +42,12 @@ struct EvalBuffers {
     int* hitpre;             // [R][n_lig][scan_words] hits of the row before word w (probe kernel)
     double* pairf;           // [R][n_lig][pairf_cap][3] force on the resting atom of every hit
     int pairf_cap;           // hits a row can hold
+    // Cluster path: the prefilter runs once per list build with the list's skin added to the
+    // cutoff (filter_skin > 0) and its rows are expanded into candidate lists that stay valid
+    // exactly as long as the pair list does.
+    float filter_skin;       // nm added to the cutoff by the prefilter (0: per-eval prefilter)
+    int* cand;               // [R][n_lig][pairf_cap] resting atom (System index) of hit h
+    int* cand_count;         // [R][n_lig] hits of the row (may exceed pairf_cap: overflow)
     int* list_age;           // device: evals since the cluster-pair list was built (0: no list)
 };
 
@@ -56,6 +62,8 @@ int allpairs_num_blocks(int n);
 void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 void launch_ligand_filter(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 void launch_ligand_gather(const Topology& T, const EvalBuffers& B, cudaStream_t s);
+void launch_ligand_compact(const Topology& T, const EvalBuffers& B, cudaStream_t s);      // list build: bitmap -> candidates
+void launch_ligand_probe_list(const Topology& T, const EvalBuffers& B, cudaStream_t s);   // per eval, from the candidates
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 int exceptions_num_blocks(int n_exceptions);
 // e_scale / c_div: 0.5 / 2 when every pair was visited from both sides (all-pairs), 1 / 1 for a
