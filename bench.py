@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--nstlist", type=int, default=20)
     ap.add_argument("--skin", type=float, default=0.06)
     ap.add_argument("--pair-mode", type=int, default=0)
-    ap.add_argument("--e2e-groups", type=int, default=1, help="replica groups (contexts/streams) of the e2e leg")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the pipelined e2e leg (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-lambda", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -264,57 +264,74 @@ def main():
     value = world * R * args.steps / (t_ms * 1e-3)
 
     # ---------------- end-to-end leg: host buffers in, host buffers out ---------------------
-    # The R replicas are driven as G independent contexts (replica groups) on G streams, the way
-    # a multi-replica driver uses the C ABI: per step and group, H2D of the positions (pinned),
-    # sdm_eval, D2H of forces + scalars; the copies of one group overlap the kernels of the
-    # others.  Every step moves all positions in and all forces out, inside the timed region.
-    G = max(1, min(args.e2e_groups, R))
-    while R % G:
-        G -= 1
-    Rg = R // G
-    g_streams = [torch.cuda.Stream() for _ in range(G)]
-    g_ctx = []
-    for g in range(G):
-        cg = SDMContext(case.system, case.displacement, n_replicas=Rg, pair_mode=args.pair_mode,
+    # Every step moves all positions in (pinned host -> HBM) and all forces + scalars out, through
+    # the C-ABI calls a multi-replica driver makes: sdm_set_positions_all, sdm_eval,
+    # sdm_enqueue_results, sdm_synchronize + sdm_collect_scalars.
+    #  * serial: one batch in flight, the host waits for every step's results (latency);
+    #  * pipelined (the reported e2e value): D batches of R replicas in flight, each on its own
+    #    context + stream, so the H2D of batch k+1 and the D2H of batch k-1 ride the two copy
+    #    engines while batch k computes.  A batch's results are consumed on the host (scalars read,
+    #    exchange all-gather) before its context is reused.  Each step is still one batch of R
+    #    evaluations; K steps are timed as a whole with a synchronize on both sides.
+    D = max(1, args.e2e_depth)
+    e_streams = [torch.cuda.Stream() for _ in range(D)]
+    e_ctx, e_hf = [], []
+    for d in range(D):
+        cg = SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=args.pair_mode,
                         device=local, skin=args.skin, nstlist=args.nstlist)
-        cg.set_stream(g_streams[g].cuda_stream)
-        for r in range(Rg):
-            cg.set_alchemical(r, states[(rank * R + g * Rg + r) % len(states)])
-        g_ctx.append(cg)
+        cg.set_stream(e_streams[d].cuda_stream)
+        for r in range(R):
+            cg.set_alchemical(r, states[(rank * R + r) % len(states)])
+        e_ctx.append(cg)
+        e_hf.append(h_f if d == 0 else PinnedArray((R, n, 3)))
+    flush_stream = torch.cuda.Stream()
 
-    def e2e_step(k):
-        src = h_pos.array if k % 2 == 0 else h_pos_b.array
-        for g, cg in enumerate(g_ctx):
-            cg.set_positions_all(src[g * Rg:(g + 1) * Rg])
-            cg.eval()
-            cg.enqueue_results(h_f.array[g * Rg:(g + 1) * Rg])
-        s = []
-        for cg in g_ctx:
+    def e2e_submit(k, depth):
+        d = k % depth
+        cg = e_ctx[d]
+        s = None
+        if k >= depth:                       # consume the results of step k - depth
             cg.synchronize()
-            s += cg.collect_scalars()
-        exchange_gather(s)
+            s = cg.collect_scalars()
+            exchange_gather(s)
+        cg.set_positions_all(h_pos.array if k % 2 == 0 else h_pos_b.array)
+        cg.eval()
+        cg.enqueue_results(e_hf[d].array)
         return s
 
-    for k in range(args.warmup):
-        e2e_step(k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e2e_t = 0.0
-    for k in range(args.steps):
-        flush.zero_()
+    def e2e_run(nsteps, depth, timed):
+        """nsteps steps with `depth` batches in flight; returns (seconds, last scalars)."""
+        torch.cuda.synchronize()
+        if world > 1 and timed:
+            dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        s = e2e_step(k)
+        last = None
+        for k in range(nsteps):
+            if timed:
+                with torch.cuda.stream(flush_stream):
+                    flush.zero_()            # keeps evicting L2 next to the pipeline, unordered
+            last = e2e_submit(k, depth) or last
+        for k in range(nsteps, nsteps + min(depth, nsteps)):   # drain in submission order
+            cg = e_ctx[k % depth]
+            cg.synchronize()
+            last = cg.collect_scalars()
+            exchange_gather(last)
         torch.cuda.synchronize()
-        e2e_t += time.perf_counter() - t0
+        return time.perf_counter() - t0, last
+
+    e2e_run(max(args.warmup, D), D, False)
+    e2e_t, s = e2e_run(args.steps, D, True)
     assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
-    for cg in g_ctx:
+    e2e_run(args.warmup, 1, False)
+    e2e_serial_t, s = e2e_run(args.steps, 1, True)
+    assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
+    for cg in e_ctx:
         cg.close()
     if world > 1:
-        tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([e2e_t, e2e_serial_t], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t = float(tt.item())
+        e2e_t, e2e_serial_t = float(tt[0].item()), float(tt[1].item())
     e2e_value = world * R * args.steps / e2e_t
     h2d = R * n * 3 * 8
     d2h = R * n * 3 * 8 + R * 8 * 20
@@ -356,9 +373,13 @@ def main():
             "ns_per_day_per_replica_upper_bound": value / (world * R) * 1e-6 * 86400,
             "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_t / args.steps, "replica_groups": G,
+                    "ms_per_step": 1e3 * e2e_t / args.steps, "batches_in_flight": D,
+                    "serial": {"value": world * R * args.steps / e2e_serial_t, "ms_per_step": 1e3 * e2e_serial_t / args.steps,
+                               "note": "one batch in flight, host waits for each step's results"},
                     "note": "C-ABI calls with pinned HOST buffers: sdm_set_positions_all (H2D) + sdm_eval + sdm_enqueue_results (D2H of forces and scalars) "
-                            "per step inside the timed region; G replica groups = G contexts on G streams"},
+                            "+ sdm_synchronize/sdm_collect_scalars per step inside the timed region (host wall clock over all K steps, synchronize on both "
+                            "sides); D batches of R replicas in flight on D contexts/streams so copies overlap the kernels of the neighbouring batches; "
+                            "the D working sets (D x ~60 MB) rotate through the 126 MB L2 and a 256 MiB flush write runs beside every step"},
             "clocks": sampler.result(), "wall_s_resident_leg": wall_resident}
 
     if rank == 0 and R > 1 and not args.no_single_lambda:

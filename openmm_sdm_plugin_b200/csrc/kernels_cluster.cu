@@ -32,6 +32,7 @@
 // sqrt(ONE_4PI_EPS0), reaction field krf/crf, LJ not shifted.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "f32x2.cuh"
 #include "pairlist.h"
@@ -44,6 +45,12 @@ namespace {
 #endif
 #ifndef SDM_PAIR_MINB
 #define SDM_PAIR_MINB 16
+#endif
+#ifndef SDM_PAIR_SEL2
+#define SDM_PAIR_SEL2 1
+#endif
+#ifndef SDM_PAIR_JRED_ALWAYS
+#define SDM_PAIR_JRED_ALWAYS 0
 #endif
 // One warp per block: a warp that finishes its unit frees its slot at once (units differ in
 // length), which keeps the achieved occupancy at the register-limited maximum.
@@ -77,6 +84,15 @@ __device__ __forceinline__ float pair_r2(const float xi, const float yi, const f
     dy = __fsub_rn(yi, xj.y);
     dz = __fsub_rn(zi, xj.z);
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// (c_lo ? lo(v) : 0, c_hi ? hi(v) : 0) as two FSEL writing one register pair
+__device__ __forceinline__ f2 sel2_or_zero(const f2 v, const bool c_lo, const bool c_hi) {
+    f2 r;
+    asm("{\n .reg .f32 a, b;\n .reg .pred p, q;\n mov.b64 {a, b}, %1;\n setp.ne.s32 p, %2, 0;\n"
+        " setp.ne.s32 q, %3, 0;\n selp.f32 a, a, 0f00000000, p;\n selp.f32 b, b, 0f00000000, q;\n"
+        " mov.b64 %0, {a, b};\n}" : "=l"(r) : "l"(v), "r"((int)c_lo), "r"((int)c_hi));
+    return r;
 }
 
 struct PairConsts {
@@ -135,8 +151,13 @@ __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const fl
     const f2 dEdR = fma2(add2(a, e_lj), bc(6.f), mul2(qq, fma2(kr2, bc(-2.f), rinv)));
     const f2 e = fma2(qq, sub2(add2(rinv, kr2), bc(K.crf)), e_lj);
     const f2 fsr = mul2(dEdR, rinv2);
+#if SDM_PAIR_SEL2
+    const f2 fs = sel2_or_zero(fsr, in_lo, in_hi);
+    en = add2(en, sel2_or_zero(e, in_lo, in_hi));
+#else
     const f2 fs = pk(in_lo ? lo(fsr) : 0.f, in_hi ? hi(fsr) : 0.f);
     en = add2(en, pk(in_lo ? lo(e) : 0.f, in_hi ? hi(e) : 0.f));
+#endif
     // cnt += in as ONE predicated add per half (the compiler's own rendering takes three
     // instructions); ptxas merges the setp with the one that feeds the selects above
     if (MASKED) {
@@ -330,7 +351,11 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
             float v = up ? z : keep;
             v += __shfl_xor_sync(0xffffffffu, send2, 2);
             // lane ti: 0 -> X, 1 -> Y, 2 -> Z, 3 -> Z (duplicate, not written); sign: F_j = -sum
+#if SDM_PAIR_JRED_ALWAYS
+            if (ti < 3) atomic_add_fixed(facc_j + jslot_k, __float2ll_rn(-v * kFix));
+#else
             if (ti < 3 && v != 0.f) atomic_add_fixed(facc_j + jslot_k, __float2ll_rn(-v * kFix));
+#endif
         }
     }
 
@@ -438,6 +463,342 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= V.nunits) break;
         process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift);
+    }
+}
+
+// =============================================================================================
+// Tile-list kernel (pair_tile_kernel): the same 8 x 8 tiles and the same FP32 arithmetic, but the
+// warp owns ONE i-cluster whose eight atoms stay in registers, and walks that cluster's own tile
+// list (built from the entries by tile_fill_kernel in pairlist.cu) two tiles at a time:
+//   lane = (half, tj, ti) = (lane>>4, (lane>>1)&7, lane&1); half-warp `half` works on tile
+//   2s+half of step s, its lane holds j-atom tj and evaluates the FOUR i-atoms ti, ti+2, ti+4,
+//   ti+6 as two independent packed chains A = (ti, ti+4), B = (ti+2, ti+6)  (ILP 2).
+// Compared with pair_cluster_kernel: no shared-memory loads, no imask branches / REDUX, 12
+// instead of 48 i-force accumulator registers (more resident warps), a hot loop of ~2 KB instead
+// of ~15 KB, and the j force is reduced over only two lanes (one SHFL level) per tile.  The price
+// is one j load and one j reduction per tile instead of per entry.
+// The FP32 r^2 expression, the band rule and the FP64 re-test are the ones of pair_cluster_kernel,
+// so the in-cutoff pair set is identical (pair_emit_kernel serves both).
+// =============================================================================================
+struct IAtoms {     // two i-atoms (a, a+4) of the warp's cluster, packed (lo, hi)
+    f2 x, y, z, q, s, e;
+};
+
+template <bool MASKED, bool EXACT>
+__device__ __forceinline__ void tile_chain(const IAtoms& I, const float4 xj, const float2 pj,
+                                           const bool allow_lo, const bool allow_hi, const PairConsts& K,
+                                           Acc2& fi, Acc2& fj, f2& en, int& cnt, float& tmin) {
+    const f2 dx = sub2(I.x, bc(xj.x));
+    const f2 dy = sub2(I.y, bc(xj.y));
+    const f2 dz = sub2(I.z, bc(xj.z));
+    const f2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const f2 t = sub2(r2, bc(K.rc2));
+    const float t_lo = lo(t), t_hi = hi(t);
+    const bool in_lo = MASKED ? (allow_lo && t_lo <= 0.f) : (t_lo <= 0.f);
+    const bool in_hi = MASKED ? (allow_hi && t_hi <= 0.f) : (t_hi <= 0.f);
+    if (EXACT) tmin = fminf(tmin, fminf(fabsf(t_lo), fabsf(t_hi)));
+    const f2 rinv = pk(rsqrt_approx(lo(r2)), rsqrt_approx(hi(r2)));
+    const f2 rinv2 = mul2(rinv, rinv);
+    const f2 sig = add2(I.s, bc(pj.x));
+    const f2 sr2 = mul2(mul2(sig, sig), rinv2);
+    const f2 sr6 = mul2(mul2(sr2, sr2), sr2);
+    const f2 elj = mul2(mul2(I.e, bc(pj.y)), sr6);
+    const f2 qq = mul2(I.q, bc(xj.w));
+    const f2 kr2 = mul2(r2, bc(K.krf));
+    const f2 a = mul2(elj, sr6);
+    const f2 e_lj = sub2(a, elj);
+    const f2 dEdR = fma2(add2(a, e_lj), bc(6.f), mul2(qq, fma2(kr2, bc(-2.f), rinv)));
+    const f2 e = fma2(qq, sub2(add2(rinv, kr2), bc(K.crf)), e_lj);
+    const f2 fsr = mul2(dEdR, rinv2);
+    const f2 fs = pk(in_lo ? lo(fsr) : 0.f, in_hi ? hi(fsr) : 0.f);
+    en = add2(en, pk(in_lo ? lo(e) : 0.f, in_hi ? hi(e) : 0.f));
+    asm("{\n .reg .pred p;\n setp.ne.s32 p, %1, 0;\n @p add.s32 %0, %0, 1;\n}" : "+r"(cnt) : "r"((int)in_lo));
+    asm("{\n .reg .pred p;\n setp.ne.s32 p, %1, 0;\n @p add.s32 %0, %0, 1;\n}" : "+r"(cnt) : "r"((int)in_hi));
+    fi.x = fma2(fs, dx, fi.x); fi.y = fma2(fs, dy, fi.y); fi.z = fma2(fs, dz, fi.z);
+    fj.x = fma2(fs, dx, fj.x); fj.y = fma2(fs, dy, fj.y); fj.z = fma2(fs, dz, fj.z);
+}
+
+constexpr uint32_t kTileDummyCode = 63u;   // shift code of a padding record (3,3,3 is no valid shift)
+
+// Rare path of the tile-list kernel: the steps (two tiles each) that saw a pair inside the FP32
+// uncertainty band are walked once more, straight from global memory, and the FP64 decision is
+// applied like in fix_band_pairs above.
+__device__ __noinline__ void fix_band_unit(const Topology& T, const PairListView& V, const TileListView& TL,
+                                           const double* __restrict__ pos_all,
+                                           long long* __restrict__ f1acc, const TileUnit u, const int lane,
+                                           uint32_t stepmask, float* en, int* cnt) {
+    const int half = lane >> 4, tj = (lane >> 1) & 7, ti = lane & 1;
+    const size_t plane = (size_t)V.nslot_cap;
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
+    const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
+    while (stepmask) {
+        const int s2 = 2 * (__ffs(stepmask) - 1);
+        stepmask &= stepmask - 1u;
+        const uint2 rec = TL.recs[(size_t)u.begin + s2 + half];
+        const uint32_t code = rec.x >> 26;
+        if (code == kTileDummyCode) continue;
+        const int jslot = (int)(rec.x & 0x3ffffffu) * nbl::kJGroup + tj;
+        float4 xj = V.posq[jslot];
+        const float2 pj = V.par[jslot];
+        if (periodic) {
+            xj.x += (float)nbl::shift_x(code) * T.boxf[0];
+            xj.y += (float)nbl::shift_y(code) * T.boxf[1];
+            xj.z += (float)nbl::shift_z(code) * T.boxf[2];
+        }
+        const uint32_t w[2] = {V.masks[rec.y], V.masks[rec.y + 1]};
+        for (int m = 0; m < 4; m++) {
+            const int a = ti + 2 * m;
+            if (!((w[a >> 2] >> (tj * 4 + (a & 3))) & 1u)) continue;
+            const int islot = u.islot + a;
+            const float4 xi = V.posq[islot];
+            const float2 pi = V.par[islot];
+            float dx, dy, dz;
+            const float r2 = pair_r2(xi.x, xi.y, xi.z, xj, dx, dy, dz);
+            const float t = r2 - K.rc2;
+            if (!(fabsf(t) < K.band)) continue;
+            const int ai = V.atom[islot], aj = V.atom[jslot];
+            if (ai < 0 || aj < 0) continue;
+            const int r = ai / T.n;
+            const bool in64 = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
+            const bool in32 = t <= 0.f;
+            if (in64 == in32) continue;
+            const float sgn = in64 ? 1.f : -1.f;
+            float e;
+            const float fs = sgn * pair_term_f32(r2, xi.w, pi.x, pi.y, xj.w, pj, K, e);
+            *en += sgn * e;
+            *cnt += in64 ? 1 : -1;
+            const float f[3] = {fs * dx, fs * dy, fs * dz};
+            for (int c = 0; c < 3; c++) {
+                const long long v = __float2ll_rn(f[c] * kFix);
+                atomic_add_fixed(f1acc + (size_t)c * plane + islot, v);
+                atomic_add_fixed(f1acc + (size_t)c * plane + jslot, -v);
+            }
+        }
+    }
+}
+
+// add v (fixed point of f * scale) to *p unless f == 0: one predicated RED, no branch
+__device__ __forceinline__ void red_fixed_nonzero(long long* p, const float f, const float scale) {
+    const long long v = __float2ll_rn(f * scale);
+    asm volatile("{\n .reg .pred p;\n setp.neu.f32 p, %2, 0f00000000;\n @p red.global.add.u64 [%0], %1;\n}"
+                 :: "l"(p), "l"(v), "f"(f) : "memory");
+}
+
+struct JBuf {       // one step's j side: record word, slot, coordinates/charge, LJ parameters
+    uint32_t ex;
+    int jslot;
+    float4 xj;
+    float2 pj;
+};
+
+template <bool PERIODIC, bool EXACT>
+__device__ __forceinline__ void process_tile_unit(const Topology& T, const PairListView& V,
+                                                  const TileListView& TL,
+                                                  const double* __restrict__ pos_all,
+                                                  long long* __restrict__ f1acc,
+                                                  double* __restrict__ epart, long long* __restrict__ cpart,
+                                                  const int unit, const int lane, IPair* s_ip,
+                                                  const float4* s_shift) {
+    const TileUnit u = TL.units[unit];
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
+    const int half = lane >> 4, tj = (lane >> 1) & 7, ti = lane & 1;
+    const size_t plane = (size_t)V.nslot_cap;
+    // loop bounds through REDUX: uniform registers, so the loops below need no divergence handling
+    const int nrec = (int)__reduce_or_sync(0xffffffffu, (unsigned)u.nrec);
+    const int nmask = (int)__reduce_or_sync(0xffffffffu, (unsigned)u.nmask);
+
+    // the warp's i-cluster: lanes 0..3 pack atoms (a, a+4) through shared memory so that every
+    // lane gets them back as 64-bit register pairs; chains A = (ti, ti+4), B = (ti+2, ti+6)
+    if (lane < 4) {
+        float4 p[2];
+        float2 pr[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int sl = u.islot + lane + 4 * h;
+            const float4 q = V.posq[sl];
+            p[h] = make_float4(-nbl::kFar, -nbl::kFar, -nbl::kFar, 0.f);
+            pr[h] = make_float2(0.f, 0.f);
+            if (q.x < 0.5f * nbl::kFar) { p[h] = q; pr[h] = V.par[sl]; }
+        }
+        IPair ip;
+        ip.x = pk(p[0].x, p[1].x); ip.y = pk(p[0].y, p[1].y);
+        ip.z = pk(p[0].z, p[1].z); ip.q = pk(p[0].w, p[1].w);
+        ip.s = pk(pr[0].x, pr[1].x); ip.e = pk(pr[0].y, pr[1].y);
+        s_ip[lane] = ip;
+    }
+    __syncwarp();
+    IAtoms IA, IB;
+    {
+        const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti].x);
+        const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti].z);
+        const ulonglong2 a2 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti].s);
+        IA.x = a0.x; IA.y = a0.y; IA.z = a1.x; IA.q = a1.y; IA.s = a2.x; IA.e = a2.y;
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti + 2].x);
+        const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti + 2].z);
+        const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti + 2].s);
+        IB.x = b0.x; IB.y = b0.y; IB.z = b1.x; IB.q = b1.y; IB.s = b2.x; IB.e = b2.y;
+    }
+    __syncwarp();   // the staging area is reused by the next unit of this warp
+
+    Acc2 fA{0ull, 0ull, 0ull}, fB{0ull, 0ull, 0ull};
+    f2 en = 0ull;
+    int cnt = 0;
+    uint32_t fixmask = 0u;   // bit s: step s of this unit (<= 32 steps) saw a pair inside the band
+    uint32_t stepbit = 1u;
+    long long* const facc_xy = f1acc + (size_t)ti * plane;   // lane ti adds component ti (x or y)
+    long long* const facc_z = f1acc + 2 * plane;             // ... and lane ti = 0 also z
+    const int bitA = tj * 4 + ti, bitB = bitA + 2;
+
+    for (int b0 = 0; b0 < nrec; b0 += 32) {
+        const int nb = min(32, nrec - b0);              // records of this batch (even)
+        const int nm = max(0, min(nb, nmask - b0));     // of which masked (even, they come first)
+        uint2 my = make_uint2(kTileDummyCode << 26, 0u);
+        if (lane < nb) my = TL.recs[(size_t)u.begin + b0 + lane];
+
+        auto fetch = [&](JBuf& J, const int s2) {
+            J.ex = __shfl_sync(0xffffffffu, my.x, s2 + half);
+            J.jslot = (int)(J.ex & 0x3ffffffu) * nbl::kJGroup + tj;
+            J.xj = V.posq[J.jslot];
+            J.pj = V.par[J.jslot];
+        };
+        auto compute = [&](const JBuf& J, const int s2, auto masked_tag) {
+            constexpr bool MASKED = decltype(masked_tag)::value;
+            const uint32_t code = J.ex >> 26;
+            float4 xj = J.xj;
+            uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
+            if (MASKED) {
+                const uint32_t ey = __shfl_sync(0xffffffffu, my.y, s2 + half);
+                w0 = V.masks[ey];          // unmasked and padding records point at mask set 0 (all ones)
+                w1 = V.masks[ey + 1];
+            }
+            if (PERIODIC) {
+                const float4 sh = s_shift[code];    // entry 63 moves a padding record out of range
+                xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
+            } else {
+                xj.x += code == kTileDummyCode ? 4.f * nbl::kFar : 0.f;
+            }
+            Acc2 fj{0ull, 0ull, 0ull};
+            float tmin = 3.0e38f;
+            tile_chain<MASKED, EXACT>(IA, xj, J.pj, (w0 >> bitA) & 1u, (w1 >> bitA) & 1u, K, fA, fj, en, cnt, tmin);
+            tile_chain<MASKED, EXACT>(IB, xj, J.pj, (w0 >> bitB) & 1u, (w1 >> bitB) & 1u, K, fB, fj, en, cnt, tmin);
+            if (EXACT) {
+                if (tmin < K.band) fixmask |= stepbit;
+                stepbit <<= 1;
+            }
+            // j force: halves added, then exchanged between the two ti lanes: ti = 0 ends up with
+            // X and Z, ti = 1 with Y (sign: F_j = -sum)
+            const float jx = lo(fj.x) + hi(fj.x), jy = lo(fj.y) + hi(fj.y), jz = lo(fj.z) + hi(fj.z);
+            const float send = ti ? jx : jy;
+            float keep = ti ? jy : jx;
+            keep += __shfl_xor_sync(0xffffffffu, send, 1);
+            const float z = jz + __shfl_xor_sync(0xffffffffu, jz, 1);
+            red_fixed_nonzero(facc_xy + J.jslot, keep, -kFix);
+            red_fixed_nonzero(facc_z + J.jslot, ti ? 0.f : z, -kFix);
+        };
+        // two steps per trip with ping-pong buffers: the j data of the next step is in flight
+        // while this one is computed and no register rotation is needed.  A trip that straddles
+        // the masked/unmasked boundary runs the masked code for both of its steps.
+        JBuf Ja, Jb;
+        fetch(Ja, 0);
+        int s2 = 0;
+        for (; s2 < nm; s2 += 4) {
+            if (s2 + 2 < nb) fetch(Jb, s2 + 2);
+            compute(Ja, s2, std::true_type{});
+            if (s2 + 2 < nb) {
+                if (s2 + 4 < nb) fetch(Ja, s2 + 4);
+                compute(Jb, s2 + 2, std::true_type{});
+            }
+        }
+        for (; s2 < nb; s2 += 4) {
+            if (s2 + 2 < nb) fetch(Jb, s2 + 2);
+            compute(Ja, s2, std::false_type{});
+            if (s2 + 2 < nb) {
+                if (s2 + 4 < nb) fetch(Ja, s2 + 4);
+                compute(Jb, s2 + 2, std::false_type{});
+            }
+        }
+    }
+
+    // i forces: 12 partial sums per lane (4 atoms x 3), reduced over the 16 (half, tj) lanes.
+    // xor 16 and xor 8 halve the value count (transpose-reduction), xor 4 and xor 2 are plain
+    // butterflies; afterwards lane (b4, b3, *, *, ti) holds the force of atom ti + 2*(2*b4 + b3).
+    {
+        const float v[12] = {lo(fA.x), lo(fA.y), lo(fA.z), lo(fB.x), lo(fB.y), lo(fB.z),
+                             hi(fA.x), hi(fA.y), hi(fA.z), hi(fB.x), hi(fB.y), hi(fB.z)};   // m = 0,1,2,3
+        const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+        float a[6], b[3];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const float send = b4 ? v[k] : v[k + 6];
+            a[k] = (b4 ? v[k + 6] : v[k]) + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float send = b3 ? a[k] : a[k + 3];
+            b[k] = (b3 ? a[k + 3] : a[k]) + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            b[k] += __shfl_xor_sync(0xffffffffu, b[k], 4);
+            b[k] += __shfl_xor_sync(0xffffffffu, b[k], 2);
+        }
+        const int m = (b4 ? 2 : 0) + (b3 ? 1 : 0);
+        const int d = (lane >> 1) & 3;   // the four duplicate lanes write one component each
+        const float f = d == 0 ? b[0] : (d == 1 ? b[1] : b[2]);
+        if (d < 3 && f != 0.f)
+            atomic_add_fixed(f1acc + (size_t)d * plane + u.islot + ti + 2 * m, __float2ll_rn(f * kFix));
+    }
+
+    float en1 = lo(en) + hi(en);
+    if (EXACT) fixmask = __reduce_or_sync(0xffffffffu, fixmask);
+    if (EXACT && fixmask) {
+        float en_fix = 0.f;   // separate variables: their address is taken by the call
+        int cnt_fix = 0;
+        fix_band_unit(T, V, TL, pos_all, f1acc, u, lane, fixmask, &en_fix, &cnt_fix);
+        en1 += en_fix;
+        cnt += cnt_fix;
+    }
+    double de = (double)en1;
+    int dc = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        de += __shfl_down_sync(0xffffffffu, de, o);
+        dc += __shfl_down_sync(0xffffffffu, dc, o);
+    }
+    if (lane == 0) {
+        epart[unit] = de;
+        cpart[unit] = dc;
+    }
+}
+
+#ifndef SDM_TILE_MINB
+#define SDM_TILE_MINB 16
+#endif
+
+template <bool PERIODIC, bool EXACT>
+__global__ void __launch_bounds__(32, SDM_TILE_MINB)
+pair_tile_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
+                 const __grid_constant__ TileListView TL, const double* __restrict__ pos_all,
+                 long long* __restrict__ f1acc, double* __restrict__ epart,
+                 long long* __restrict__ cpart, int* unit_counter) {
+    __shared__ float4 s_shift[64];
+    __shared__ IPair s_ip[4];
+    const int lane = threadIdx.x;
+    if (PERIODIC) {
+        for (uint32_t code = lane; code < 64; code += 32)
+            s_shift[code] = code == kTileDummyCode
+                                ? make_float4(4.f * nbl::kFar, 0.f, 0.f, 0.f)
+                                : make_float4((float)nbl::shift_x(code) * T.boxf[0],
+                                              (float)nbl::shift_y(code) * T.boxf[1],
+                                              (float)nbl::shift_z(code) * T.boxf[2], 0.f);
+        __syncwarp();
+    }
+    for (;;) {
+        unsigned mine = 0u;
+        if (lane == 0) mine = (unsigned)atomicAdd(unit_counter, 1);
+        const int unit = (int)__reduce_or_sync(0xffffffffu, mine);   // lane 0's value, in a uniform register
+        if (unit >= TL.nunits) break;
+        process_tile_unit<PERIODIC, EXACT>(T, V, TL, pos_all, f1acc, epart, cpart, unit, lane, s_ip, s_shift);
     }
 }
 
@@ -553,6 +914,34 @@ void launch_pair_cluster(const Topology& T, const PairListView& V, const double*
         const int grid = std::min((V.nunits + kWarps - 1) / kWarps, num_sms * resident);           \
         pair_cluster_kernel<P, X><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
                                                               unit_counter);                      \
+    } while (0)
+    if (exact) {
+        if (periodic) SDM_LAUNCH(true, true);
+        else SDM_LAUNCH(false, true);
+    } else {
+        if (periodic) SDM_LAUNCH(true, false);
+        else SDM_LAUNCH(false, false);
+    }
+#undef SDM_LAUNCH
+}
+
+void launch_pair_tiles(const Topology& T, const PairListView& V, const TileListView& TL,
+                       const double* pos_all, long long* f1acc, double* epart, long long* cpart,
+                       int exact, int* unit_counter, int num_sms, cudaStream_t s) {
+    if (TL.nunits <= 0) return;
+    cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
+    const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
+#define SDM_LAUNCH(P, X)                                                                          \
+    do {                                                                                          \
+        static int resident = 0; /* blocks per SM the hardware keeps resident */                  \
+        if (!resident) {                                                                          \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_tile_kernel<P, X>, 32, 0) != \
+                    cudaSuccess || resident < 1)                                                  \
+                resident = SDM_TILE_MINB;                                                         \
+            if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
+        }                                                                                         \
+        const int grid = std::min(TL.nunits, num_sms * resident);                                 \
+        pair_tile_kernel<P, X><<<grid, 32, 0, s>>>(T, V, TL, pos_all, f1acc, epart, cpart, unit_counter); \
     } while (0)
     if (exact) {
         if (periodic) SDM_LAUNCH(true, true);

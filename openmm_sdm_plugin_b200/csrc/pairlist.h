@@ -28,6 +28,26 @@ struct PairListView {
     int nslot_cap;               // accumulator plane stride
 };
 
+// Tile list: the entries expanded into one record per (i-cluster, j-cluster) tile, grouped by
+// i-cluster, for pair_tile_kernel.  Within an i-cluster the tiles of masked entries come first;
+// both groups are padded to an even count with dummy records (shift code 63, cluster 0, mask 0).
+struct TileUnit {
+    int islot;    // first slot of the i-cluster
+    int begin;    // first record (index into recs)
+    int nrec;     // records of this unit (even, <= chunk)
+    int nmask;    // how many of them (from the start) carry exclusion masks (even)
+};
+
+struct TileListView {
+    const uint2* recs;           // {cj | shift<<26, index of the tile's two mask words (0 = all ones)}
+    const TileUnit* units;
+    int nunits;
+};
+
+void launch_pair_tiles(const Topology& T, const PairListView& V, const TileListView& TL,
+                       const double* pos_all, long long* f1acc, double* epart, long long* cpart,
+                       int exact, int* unit_counter, int num_sms, cudaStream_t s);
+
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
                          int* unit_counter, int num_sms, cudaStream_t s);
