@@ -128,14 +128,39 @@ def run_reference(args):
         nt = os.cpu_count() or 1
     nt = max(nt, O.max_threads())
     from openmm_sdm_plugin_b200 import system as S
+    from oracle import reference as R
     al = S.AlchemicalState(**vars(case.alch))
+    use_ref = R.available()
+    if use_ref:
+        # the reference's OWN step code (oracle/_ref: its integrator + Reference-platform kernels
+        # compiled from its sources): three force evaluations, state copies, execute(), Langevin
+        # update.  OpenMM's NonbondedForce -- not available in this image -- is the oracle port,
+        # called back for force group 2 with all host threads; force group 1 (bonded) is zero.
+        n = case.system.n_atoms
+        zeros = np.zeros((n, 3))
+        params = R.params_from_alch(al)
+
+        def force_fn(groups, pos):
+            if groups == 4:
+                r = O.nonbonded(case.system, pos, nthreads=nt)
+                return r["E"], r["forces"]
+            return 0.0, zeros
+
+        def one_step():
+            R.run(case.masses, case.positions, zeros, case.displacement, params, force_fn, steps=1)
+    else:
+        def one_step():
+            O.sdm_eval(case.system, al, case.displacement, case.positions, nthreads=nt, want_state_forces=False)
     for _ in range(args.warmup):
-        O.sdm_eval(case.system, al, case.displacement, case.positions, nthreads=nt, want_state_forces=False)
+        one_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.sdm_eval(case.system, al, case.displacement, case.positions, nthreads=nt, want_state_forces=False)
+        one_step()
     dt = time.perf_counter() - t0
     v = args.steps / dt
+    sample = ("%d whole steps of the workload; step sequence, state handling, execute() and Langevin update by the reference's "
+              "own compiled sources (oracle/_ref), NonbondedForce by the oracle port (OpenMM is not installable here)"
+              if use_ref else "%d whole evals of the workload (oracle port; oracle/_ref not built)") % args.steps
     line = {"impl": "reference", "metric": "SDM dual-state force evals/s", "value": v, "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -143,7 +168,7 @@ def run_reference(args):
             "config": {"workload": wname, "replicas_per_step": 1,
                        "note": "one step = one dual-state eval of one replica on the host CPU"},
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": nt, "kind": "port",
-                             "sample": "%d whole evals of the workload" % args.steps},
+                             "sample": sample},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
