@@ -51,6 +51,26 @@ def peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
 
 
+def bind_near_gpu(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (same NUMA node / PCIe
+    root), before CUDA and the pinned host buffers are created: with one rank per GPU the
+    host<->device copies of the e2e leg then do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        pick = cpus & os.sched_getaffinity(0)
+        if pick:
+            os.sched_setaffinity(0, pick)
+            return len(pick)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml)."""
 
@@ -176,8 +196,6 @@ def run_reference(args):
 
 def main():
     # NCCL prints its version banner to stdout under NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -189,12 +207,21 @@ def main():
     ap.add_argument("--skin", type=float, default=0.06)
     ap.add_argument("--pair-mode", type=int, default=0)
     ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the pipelined e2e leg (contexts/streams)")
+    ap.add_argument("--exchange-every", type=int, default=10,
+                    help="steps between replica-exchange all-gathers of (u_sc, state) in the e2e leg (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-lambda", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly ONE line, the JSON result: whatever libraries print there (NCCL writes its
+    # version banner to stdout when NCCL_DEBUG is set in the environment) is routed to stderr by
+    # pointing fd 1 at fd 2; the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    result_out = os.fdopen(result_fd, "w")
     if args.warmup < 3:
         args.warmup = 3
 
@@ -208,6 +235,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the SDM path has no CPU fallback")
+    n_local_cpus = bind_near_gpu(local)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -318,7 +346,8 @@ def main():
         if k >= depth:                       # consume the results of step k - depth
             cg.synchronize()
             s = cg.collect_scalars()
-            exchange_gather(s)
+            if (k - depth) % args.exchange_every == 0:
+                exchange_gather(s)           # one exchange period: the path's only collective
         cg.set_positions_all(h_pos.array if k % 2 == 0 else h_pos_b.array)
         cg.eval()
         cg.enqueue_results(e_hf[d].array)
@@ -341,7 +370,8 @@ def main():
             cg = e_ctx[k % depth]
             cg.synchronize()
             last = cg.collect_scalars()
-            exchange_gather(last)
+            if (k - depth) % args.exchange_every == 0:
+                exchange_gather(last)
         torch.cuda.synchronize()
         return time.perf_counter() - t0, last
 
@@ -399,6 +429,8 @@ def main():
             "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_t / args.steps, "batches_in_flight": D,
+                    "exchange_every_steps": args.exchange_every if world > 1 else None,
+                    "host_cpus_local_to_gpu": n_local_cpus,
                     "serial": {"value": world * R * args.steps / e2e_serial_t, "ms_per_step": 1e3 * e2e_serial_t / args.steps,
                                "note": "one batch in flight, host waits for each step's results"},
                     "note": "C-ABI calls with pinned HOST buffers: sdm_set_positions_all (H2D) + sdm_eval + sdm_enqueue_results (D2H of forces and scalars) "
@@ -436,7 +468,8 @@ def main():
                                 "sample": "%d whole dual-state evals of the same workload (1 replica each), "
                                           "two-pass like the reference, 1 thread like OpenMM's Reference platform" % ns}
     if rank == 0:
-        print(json.dumps(line))
+        result_out.write(json.dumps(line) + "\n")
+        result_out.flush()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
