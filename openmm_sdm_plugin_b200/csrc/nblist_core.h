@@ -13,6 +13,12 @@
 //     are compact boxes (28.8 % -> 31.8 % useful pairs per tile on the 20 k-atom fixture compared
 //     with a Morton order); every cell is padded to a multiple of 8 slots with dummy atoms, so a
 //     cluster (8 slots) never straddles a cell.
+//   * column layout (Grid::columns, the default): the cells are xy columns of the box cut along z
+//     into chunks of exactly 64 atoms (the last chunk of a column takes the remainder), found
+//     with one extra sort by (column, z).  Every chunk is one full supercluster of 8 full
+//     clusters, so padding exists only at the top of a column (0.8 % dummy slots instead of 6.3 %
+//     on the 20 k-atom fixture) and the imasks are denser: 9 % fewer tiles, 15 % fewer entries,
+//     35.5 % instead of 31.8 % useful pairs per tile than with geometric 3-D cells of ~52 atoms.
 //   * an i-supercluster (sci) is a run of <= 8 clusters of one cell; its list holds j-cluster
 //     entries {cj | shift<<26, imask | mask_index<<8}; imask bit ci says cluster ci of the sci
 //     interacts with j-cluster cj (an 8 x 8 "tile").  Every unordered cluster pair is owned by
@@ -25,6 +31,7 @@
 
 #include <stdint.h>
 
+#include <cmath>
 #if defined(__CUDACC__)
 #define SDM_HD __host__ __device__ __forceinline__
 #else
@@ -42,6 +49,7 @@ constexpr int kMaskWords = 2 * kMaxCi;  // words per exclusion-mask set
 constexpr int kCoordBits = 16;       // in-cell coordinate resolution of the sort key
 constexpr int kSubBits = kCoordBits + 2;  // sort key = cell << 18 | kd bucket (2 bits) << 16 | coordinate
 constexpr int kMaxSpan = 6;          // search stencil is at most kMaxSpan cells per dimension
+constexpr int kChunkAtoms = kClusterSize * kMaxCi;  // atoms per chunk cell of the column layout
 constexpr float kFar = 1.0e6f;       // coordinate of dummy (padding) atoms
 constexpr float kBoxEmptyLo = 3.0e38f;
 
@@ -58,6 +66,11 @@ struct Grid {
     double inv_cs[3];
     float rlist, rlist2;
     float boxf[3];
+    // column layout (see "Layout" above): cells are xy columns cut along z into runs of
+    // kChunkAtoms atoms; nc[2] == kz is the number of such chunk cells a column can hold and
+    // the z index of a cell is the chunk number, not a coordinate.  0 = geometric 3-D cells.
+    int columns;
+    int kz;
 };
 
 struct BBox {
@@ -108,6 +121,66 @@ SDM_HD int shift_y(uint32_t code) { return (int)((code >> 2) & 3u) - 1; }
 SDM_HD int shift_z(uint32_t code) { return (int)((code >> 4) & 3u) - 1; }
 constexpr uint32_t kShiftZero = 1u | (1u << 2) | (1u << 4);
 
+// ---- stage 0 (host): grid sizing -----------------------------------------------------------------
+// Chooses the cell grid for a box of extent `ext` at origin `lo` holding n atoms per replica.
+// Fills periodic / n / R / rlist / nc / cs / inv_cs / lo / box / boxf / ncell / span / columns / kz.
+// Returns false when no grid with span <= kMaxSpan and ncell <= cell_cap exists.
+inline bool size_grid(Grid& G, int n, int R, bool periodic, double rlist, const double lo[3],
+                      const double ext[3], long long cell_cap, bool columns) {
+    G.periodic = periodic ? 1 : 0;
+    G.n = n;
+    G.R = R;
+    // + 1e-4 nm: the list is pruned with FP32 distances, the cutoff test may be decided in FP64
+    G.rlist = (float)(rlist + 1e-4);
+    G.rlist2 = (float)((rlist + 1e-4) * (rlist + 1e-4));
+    const double vol = ext[0] * ext[1] * ext[2];
+    const double density = vol > 0 ? n / vol : 100.0;
+    G.columns = columns ? 1 : 0;
+    G.kz = 1;
+    for (int d = 0; d < 3; d++) {
+        G.lo[d] = lo[d];
+        G.box[d] = ext[d];
+        G.boxf[d] = (float)ext[d];
+    }
+    // cells of ~40 atoms on average (one supercluster) or, column layout, xy columns with the
+    // cross-section of one 64-atom chunk's cube
+    double side = std::cbrt((columns ? (double)kChunkAtoms : 40.0) / (density > 1e-6 ? density : 1e-6));
+    if (side < 0.5 * rlist + 1e-3) side = 0.5 * rlist + 1e-3;
+    for (int iter = 0; iter < 64; iter++) {
+        long long ncell = 1;
+        int span = 1;
+        const int ngeo = columns ? 2 : 3;
+        for (int d = 0; d < ngeo; d++) {
+            int nc = (int)std::floor(ext[d] / side + (columns ? 0.5 : 0.0));
+            if (nc < 1) nc = 1;
+            G.nc[d] = nc;
+            G.cs[d] = ext[d] / nc;
+            ncell *= nc;
+            int sp = (int)std::floor((G.cs[d] + 2 * rlist + 3e-4) / G.cs[d]) + 2;
+            if (!G.periodic && sp > nc) sp = nc;
+            if (sp > span) span = sp;
+        }
+        if (columns) {
+            // along z the cells are the chunks themselves: kz chunk cells per column, 25 % + 1
+            // more than the average column needs (a fuller column keeps the rest in its last
+            // cell); one geometric cell along z, so atom_cell returns the column
+            const int kz = (int)std::ceil(1.25 * n / (double)(ncell * kChunkAtoms)) + 1;
+            G.nc[2] = kz;
+            G.cs[2] = ext[2];
+            G.kz = kz;
+            ncell *= kz;
+        }
+        for (int d = 0; d < 3; d++) G.inv_cs[d] = 1.0 / G.cs[d];
+        if (span <= kMaxSpan && ncell <= cell_cap) {
+            G.ncell = (int)ncell;
+            G.span = span;
+            return true;
+        }
+        side *= 1.1;
+    }
+    return false;
+}
+
 // ---- stage 1: sort keys -------------------------------------------------------------------------
 // Wraps the position into the box (periodic), returns the global cell, the wrapped coordinates
 // (relative to the grid origin they are >= 0) and the integer image that was applied
@@ -150,6 +223,19 @@ SDM_HD uint64_t make_key(uint32_t gcell, uint32_t bucket, uint32_t cbits) {
     return ((uint64_t)gcell << kSubBits) | ((uint64_t)(bucket & 3u) << kCoordBits) | (uint64_t)cbits;
 }
 SDM_HD uint32_t key_bucket(uint64_t key) { return (uint32_t)(key >> kCoordBits) & 3u; }
+
+// Column layout, between the (column, z) sort and the (cell, z) sort: the atom at rank `rank` of
+// its column (pseudo cell = replica*ncell + column, what atom_cell returns when the grid has one
+// geometric cell along z) goes to chunk cell rank / 64 -- the last cell of a column takes what
+// is left -- and keeps its z order through its rank inside the chunk.
+SDM_HD uint32_t chunk_cell(const Grid& G, uint32_t pseudo_cell, int rank, uint32_t* rank_in_chunk) {
+    const uint32_t r = pseudo_cell / (uint32_t)G.ncell, col = pseudo_cell % (uint32_t)G.ncell;
+    int chunk = rank / kChunkAtoms;
+    if (chunk > G.kz - 1) chunk = G.kz - 1;
+    const int rin = rank - chunk * kChunkAtoms;
+    *rank_in_chunk = (uint32_t)(rin < (1 << kCoordBits) - 1 ? rin : (1 << kCoordBits) - 1);
+    return r * (uint32_t)G.ncell + (uint32_t)chunk * (uint32_t)(G.nc[0] * G.nc[1]) + col;
+}
 
 // Atoms that go to the first half when a run of `count` atoms is split: half of its clusters
 // (rounded up), i.e. a multiple of 8.
@@ -205,6 +291,7 @@ struct SearchView {
     const BBox* sci_box;       // [nsci]
     const BBox* cl_box;        // [ncluster]  8-slot cluster boxes
     const int* cell_slot;      // [R*ncell + 1] first slot of every global cell (padded layout)
+    const BBox* cell_box;      // [R*ncell] box of the cell's real atoms (column layout: early exit)
     const float* posq4;        // [nslot][4] sorted positions: exact (atom-level) pruning of imask
 };
 
@@ -244,6 +331,41 @@ SDM_HD bool any_pair_within(const float* posq4, int A, int B, float sx, float sy
     return false;
 }
 
+// Clusters of the slot range [s0, s1) (one cell) against the sci, for one periodic image: calls
+// emit(k, cj | shift<<26, imask, diag) for every j-cluster that interacts with at least one
+// cluster of the sci under the ownership rule; k counts on from `count`.  Returns the new count.
+template <class Emit>
+SDM_HD int scan_cell_clusters(const SearchView& V, const SciDesc& sd, const BBox& sb, int s0, int s1,
+                              float sx, float sy, float sz, uint32_t code, int count, Emit& emit) {
+    const Grid& G = V.G;
+    for (int B = s0 / kJGroup; B < s1 / kJGroup; B++) {
+        const BBox jb = V.cl_box[B];
+        if (box_empty(jb)) continue;
+        if (box_dist2(sb, jb, sx, sy, sz) >= G.rlist2) continue;
+        uint32_t imask = 0;
+        bool diag = false;
+        for (int ci = 0; ci < sd.nci; ci++) {
+            const int A = sd.c0 + ci;
+            bool own;
+            if (A == B) {
+                // a cluster against itself: zero shift -> triangle; a non-zero shift only once
+                own = (code == kShiftZero) || (code > kShiftZero);
+                if (code == kShiftZero) diag = true;
+            } else {
+                own = owner_is_i(A, B);
+            }
+            if (!own) continue;
+            if (box_dist2(V.cl_box[A], jb, sx, sy, sz) >= G.rlist2) continue;
+            imask |= 1u << ci;   // box level only; the exact atom-pair prune is a separate pass
+        }
+        if (imask) {
+            emit(count, (uint32_t)B | (code << 26), imask, diag && ((imask >> (B - sd.c0)) & 1u));
+            count++;
+        }
+    }
+    return count;
+}
+
 // One search item = (sci, stencil offset).  Visits the clusters of the addressed cell and calls
 // emit(k, cj | shift<<26, imask, diag) for every j-cluster that interacts with at least one
 // cluster of the sci under the ownership rule.  Returns the number of entries.
@@ -273,34 +395,53 @@ SDM_HD int search_item(const SearchView& V, int isci, int off, Emit emit) {
     const float sx = sh[0] * G.boxf[0], sy = sh[1] * G.boxf[1], sz = sh[2] * G.boxf[2];
     const uint32_t code = shift_code(sh[0], sh[1], sh[2]);
     const int gcell = sd.replica * G.ncell + (w[2] * G.nc[1] + w[1]) * G.nc[0] + w[0];
-    const int s0 = V.cell_slot[gcell], s1 = V.cell_slot[gcell + 1];
-    int count = 0;
-    for (int B = s0 / kJGroup; B < s1 / kJGroup; B++) {
-        const BBox jb = V.cl_box[B];
-        if (box_empty(jb)) continue;
-        if (box_dist2(sb, jb, sx, sy, sz) >= G.rlist2) continue;
-        uint32_t imask = 0;
-        bool diag = false;
-        for (int ci = 0; ci < sd.nci; ci++) {
-            const int A = sd.c0 + ci;
-            bool own;
-            if (A == B) {
-                // a cluster against itself: zero shift -> triangle; a non-zero shift only once
-                own = (code == kShiftZero) || (code > kShiftZero);
-                if (code == kShiftZero) diag = true;
-            } else {
-                own = owner_is_i(A, B);
-            }
-            if (!own) continue;
-            if (box_dist2(V.cl_box[A], jb, sx, sy, sz) >= G.rlist2) continue;
-            imask |= 1u << ci;   // box level only; the exact atom-pair prune is a separate pass
-        }
-        if (imask) {
-            emit(count, (uint32_t)B | (code << 26), imask, diag && ((imask >> (B - sd.c0)) & 1u));
-            count++;
+    return scan_cell_clusters(V, sd, sb, V.cell_slot[gcell], V.cell_slot[gcell + 1], sx, sy, sz, code, 0, emit);
+}
+
+// Column layout: one search item = (sci, xy stencil offset, chunk cell of that column).  The z
+// index of a cell is a chunk number, so every chunk of the neighbour column is a candidate and
+// the (up to three) periodic images along z are tried against the cell's box.
+template <class Emit>
+SDM_HD int search_item_columns(const SearchView& V, int isci, int off, Emit emit) {
+    const Grid& G = V.G;
+    const SciDesc sd = V.sci[isci];
+    const BBox sb = V.sci_box[isci];
+    if (box_empty(sb)) return 0;
+    int cmin[3], cmax[3];
+    search_range(G, sb, cmin, cmax);   // x and y only
+    const int ox = off % G.span, oy = (off / G.span) % G.span, chunk = off / (G.span * G.span);
+    const int u[2] = {cmin[0] + ox, cmin[1] + oy};
+    if (u[0] > cmax[0] || u[1] > cmax[1]) return 0;
+    int w[2], sh[2];
+    for (int d = 0; d < 2; d++) {
+        if (G.periodic) {
+            int q = u[d] >= 0 ? u[d] / G.nc[d] : -((-u[d] + G.nc[d] - 1) / G.nc[d]);
+            w[d] = u[d] - q * G.nc[d];
+            sh[d] = q;
+            if (q < -1 || q > 1) return 0;  // excluded by the host-side box-size check
+        } else {
+            w[d] = u[d];
+            sh[d] = 0;
         }
     }
+    const int gcell = sd.replica * G.ncell + (chunk * G.nc[1] + w[1]) * G.nc[0] + w[0];
+    const int s0 = V.cell_slot[gcell], s1 = V.cell_slot[gcell + 1];
+    if (s0 == s1) return 0;
+    const BBox cb = V.cell_box[gcell];
+    if (box_empty(cb)) return 0;
+    const float sx = sh[0] * G.boxf[0], sy = sh[1] * G.boxf[1];
+    int count = 0;
+    for (int iz = (G.periodic ? -1 : 0); iz <= (G.periodic ? 1 : 0); iz++) {
+        const float sz = iz * G.boxf[2];
+        if (box_dist2(sb, cb, sx, sy, sz) >= G.rlist2) continue;
+        count = scan_cell_clusters(V, sd, sb, s0, s1, sx, sy, sz, shift_code(sh[0], sh[1], iz), count, emit);
+    }
     return count;
+}
+
+template <class Emit>
+SDM_HD int search_any(const SearchView& V, int isci, int off, Emit emit) {
+    return V.G.columns ? search_item_columns(V, isci, off, emit) : search_item(V, isci, off, emit);
 }
 
 // ---- stage 3b: exact pruning of a raw entry ----------------------------------------------------

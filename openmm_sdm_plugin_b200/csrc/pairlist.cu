@@ -38,7 +38,8 @@ struct PairList {
     float4 *posq = nullptr, *posq_build = nullptr;
     float2* par = nullptr;
     int *atom = nullptr, *img = nullptr, *slot_of = nullptr;
-    BBox *cl_box = nullptr, *sci_box = nullptr;
+    BBox *cl_box = nullptr, *sci_box = nullptr, *cell_box = nullptr;
+    int use_columns = 1;        // column layout (default) or geometric 3-D cells (SDMB200_LAYOUT=cells)
     SciDesc* sci = nullptr;
     int* cl_sci = nullptr;
     int *item_count = nullptr, *item_off = nullptr;
@@ -128,6 +129,30 @@ __global__ void key_kernel(Grid G, const double* __restrict__ pos_all, uint64_t*
     const uint32_t g = nbl::atom_cell(G, r, p[0], p[1], p[2], xw, img, fr);
     keys[t] = nbl::make_key(g, 0u, fr[2]);
     vals[t] = t;
+}
+
+// column layout: from the (column, z) order to the key of the chunk cell (see nbl::chunk_cell)
+__global__ void chunk_key_kernel(Grid G, int total, const uint64_t* __restrict__ keys_sorted,
+                                 const int* __restrict__ vals_sorted, const int* __restrict__ col_first,
+                                 uint64_t* keys, int* vals) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const uint32_t pc = (uint32_t)(keys_sorted[p] >> nbl::kSubBits);
+    uint32_t rin;
+    const uint32_t g = nbl::chunk_cell(G, pc, p - col_first[pc], &rin);
+    keys[p] = nbl::make_key(g, 0u, rin);
+    vals[p] = vals_sorted[p];
+}
+
+__global__ void cell_box_kernel(int ncells, const int* __restrict__ cell_slot, const BBox* __restrict__ cl_box,
+                                BBox* cell_box) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    BBox b;
+    for (int d = 0; d < 3; d++) { b.lo[d] = nbl::kBoxEmptyLo; b.hi[d] = -nbl::kBoxEmptyLo; }
+    for (int k = cell_slot[c] / nbl::kClusterSize; k < cell_slot[c + 1] / nbl::kClusterSize; k++)
+        if (!nbl::box_empty(cl_box[k])) b = nbl::box_union(b, cl_box[k]);
+    cell_box[c] = b;
 }
 
 // rounds 1 and 2: bucket of the previous split + the next coordinate (y, then x)
@@ -265,7 +290,7 @@ struct FillEmit {
 __global__ void search_count_kernel(nbl::SearchView V, int nsci, int noff, int* item_count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsci * noff) return;
-    item_count[t] = nbl::search_item(V, t / noff, t % noff, CountEmit());
+    item_count[t] = nbl::search_any(V, t / noff, t % noff, CountEmit());
 }
 
 __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
@@ -276,7 +301,7 @@ __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
     const int base = item_off[t];
     if (base >= cap) return;
     const SciDesc sd = V.sci[t / noff];
-    nbl::search_item(V, t / noff, t % noff, FillEmit{entries, flag, esci, c0nci, base, t / noff, sd.c0 | (sd.nci << 27)});
+    nbl::search_any(V, t / noff, t % noff, FillEmit{entries, flag, esci, c0nci, base, t / noff, sd.c0 | (sd.nci << 27)});
 }
 
 // Exact pruning, one warp per raw entry: imask bit ci survives only if some real atom pair of
@@ -509,43 +534,11 @@ inline int blocks(long long n, int t = 256) { return (int)((n + t - 1) / t); }
 // Choose the cell grid.  Cells hold ~40 atoms (5 clusters) at the system's density and are at
 // least rlist/2 wide so that the search stencil stays within kMaxSpan cells per dimension.
 int setup_grid(sdm_ctx* c, PairList* pl, const double lo[3], const double ext[3]) {
-    Grid& G = pl->G;
-    const double rlist = c->T.rc + c->opt.skin;
-    G.periodic = c->T.method == SDM_CUTOFF_PERIODIC ? 1 : 0;
-    G.n = c->n;
-    G.R = c->R;
-    // + 1e-4 nm: the list is pruned with FP32 distances, the cutoff test may be decided in FP64
-    G.rlist = (float)(rlist + 1e-4);
-    G.rlist2 = (float)((rlist + 1e-4) * (rlist + 1e-4));
-    double vol = ext[0] * ext[1] * ext[2];
-    double density = vol > 0 ? c->n / vol : 100.0;
-    double side = std::cbrt(40.0 / std::max(density, 1e-6));
-    side = std::max(side, 0.5 * rlist + 1e-3);
-    for (int iter = 0; iter < 64; iter++) {
-        long long ncell = 1;
-        int span = 1;
-        for (int d = 0; d < 3; d++) {
-            int nc = (int)std::floor(ext[d] / side);
-            if (nc < 1) nc = 1;
-            G.nc[d] = nc;
-            G.cs[d] = ext[d] / nc;
-            G.inv_cs[d] = 1.0 / G.cs[d];
-            G.lo[d] = lo[d];
-            G.box[d] = ext[d];
-            G.boxf[d] = (float)ext[d];
-            ncell *= nc;
-            int sp = (int)std::floor((G.cs[d] + 2 * rlist + 3e-4) / G.cs[d]) + 2;
-            if (!G.periodic) sp = std::min(sp, nc);
-            span = std::max(span, sp);
-        }
-        if (span <= nbl::kMaxSpan && ncell <= pl->cell_cap) {
-            G.ncell = (int)ncell;
-            G.span = span;
-            return SDM_OK;
-        }
-        side *= 1.1;
-    }
-    return sdm_fail(SDM_ERR_INVALID, "could not fit a cell grid (box too anisotropic for the cluster path)");
+    const bool periodic = c->T.method == SDM_CUTOFF_PERIODIC;
+    if (!nbl::size_grid(pl->G, c->n, c->R, periodic, c->T.rc + c->opt.skin, lo, ext, pl->cell_cap,
+                        pl->use_columns != 0))
+        return sdm_fail(SDM_ERR_INVALID, "could not fit a cell grid (box too anisotropic for the cluster path)");
+    return SDM_OK;
 }
 
 }  // namespace
@@ -573,7 +566,7 @@ static int build_list(sdm_ctx* c) {
     const Grid& G = pl->G;
     pl->ncells = R * G.ncell;
     const int ncells = pl->ncells;
-    const int noff = G.span * G.span * G.span;
+    const int noff = G.span * G.span * (G.columns ? G.kz : G.span);
 
     // sort by (cell, z); the cell extents found here stay valid for the two refinement rounds
     int cell_bits = 1;
@@ -582,6 +575,18 @@ static int build_list(sdm_ctx* c) {
     key_kernel<<<blocks(total), 256, 0, s>>>(G, c->d_pos, pl->keys, pl->vals);
     PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->keys, pl->keys_sorted,
                                             pl->vals, pl->vals_sorted, total, 0, key_end, s));
+    if (G.columns) {
+        // the first sort was by (column, z): cut every column into chunk cells of 64 atoms and
+        // sort again by (cell, z rank)
+        PL_CUDA(cudaMemsetAsync(pl->cell_count, 0, sizeof(int) * (size_t)(ncells + 1), s));
+        PL_CUDA(cudaMemsetAsync(pl->cell_first, 0, sizeof(int) * (size_t)(ncells + 1), s));
+        cell_bounds_kernel<<<blocks(total), 256, 0, s>>>(total, pl->keys_sorted, pl->cell_first, pl->cell_count);
+        chunk_key_kernel<<<blocks(total), 256, 0, s>>>(G, total, pl->keys_sorted, pl->vals_sorted, pl->cell_first,
+                                                      pl->keys, pl->vals);
+        PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->keys, pl->keys_sorted,
+                                                pl->vals, pl->vals_sorted, total, 0, key_end, s));
+        c->launches += 3;
+    }
     PL_CUDA(cudaMemsetAsync(pl->cell_count, 0, sizeof(int) * (size_t)(ncells + 1), s));
     PL_CUDA(cudaMemsetAsync(pl->cell_first, 0, sizeof(int) * (size_t)(ncells + 1), s));
     cell_bounds_kernel<<<blocks(total), 256, 0, s>>>(total, pl->keys_sorted, pl->cell_first, pl->cell_count);
@@ -619,7 +624,8 @@ static int build_list(sdm_ctx* c) {
     bbox_kernel<<<blocks(pl->ncl), 256, 0, s>>>(pl->ncl, pl->posq, pl->cl_box);
     sci_kernel<<<blocks(ncells), 256, 0, s>>>(G, ncells, pl->cell_slot, pl->cell_sci, pl->cl_box, pl->sci,
                                              pl->sci_box, pl->cl_sci);
-    c->launches += 9;
+    if (G.columns) cell_box_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_slot, pl->cl_box, pl->cell_box);
+    c->launches += 10;
 
     nbl::SearchView V;
     V.G = G;
@@ -627,6 +633,7 @@ static int build_list(sdm_ctx* c) {
     V.sci_box = pl->sci_box;
     V.cl_box = pl->cl_box;
     V.cell_slot = pl->cell_slot;
+    V.cell_box = pl->cell_box;
     V.posq4 = reinterpret_cast<const float*>(pl->posq);
     const long long nitems = (long long)pl->nsci * noff;
     if ((size_t)nitems + 1 > pl->items_cap) {
@@ -806,6 +813,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
                 return sdm_fail(SDM_ERR_BOX, "periodic box smaller than 2*(cutoff+skin): use SDM_PAIR_ALLPAIRS or a smaller skin");
     }
     pl->cell_cap = std::max(64, n / 8 + 64);
+    if (const char* e = getenv("SDMB200_LAYOUT")) pl->use_columns = std::string(e) != "cells";   // development knob
     if (c->T.method == SDM_CUTOFF_PERIODIC) {
         double lo[3] = {0, 0, 0};
         if (int rc = setup_grid(c, pl, lo, c->T.box)) return rc;
@@ -838,6 +846,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->img, pl->nslot_cap));
     A(pl_alloc(pl, &pl->slot_of, total));
     A(pl_alloc(pl, &pl->cl_box, pl->ncl_cap));
+    A(pl_alloc(pl, &pl->cell_box, ncells_cap + 1));
     A(pl_alloc(pl, &pl->sci_box, pl->nsci_cap));
     A(pl_alloc(pl, &pl->sci, pl->nsci_cap));
     A(pl_alloc(pl, &pl->cl_sci, pl->ncl_cap));
@@ -1012,6 +1021,8 @@ int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "pair_kernel_tiles") *value = pl->use_tiles;
     else if (k == "n_cells") *value = pl->G.ncell;
     else if (k == "cell_span") *value = pl->G.span;
+    else if (k == "layout_columns") *value = pl->G.columns;
+    else if (k == "chunk_cells_per_column") *value = pl->G.kz;
     else if (k == "rlist") *value = pl->G.rlist;
     else return SDM_ERR_INVALID;
     return SDM_OK;

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <string>
 #include <vector>
 
 #include "../../openmm_sdm_plugin_b200/csrc/nblist_core.h"
@@ -23,41 +24,10 @@ namespace {
 
 bool setup_grid(Grid& G, int n, int R, bool periodic, double rlist, const double lo[3],
                 const double ext[3], long long cell_cap) {
-    G.periodic = periodic ? 1 : 0;
-    G.n = n;
-    G.R = R;
-    // + 1e-4 nm: the list is pruned with FP32 distances, the cutoff test may be decided in FP64
-    G.rlist = (float)(rlist + 1e-4);
-    G.rlist2 = (float)((rlist + 1e-4) * (rlist + 1e-4));
-    double vol = ext[0] * ext[1] * ext[2];
-    double density = vol > 0 ? n / vol : 100.0;
-    double side = std::cbrt(40.0 / std::max(density, 1e-6));
-    side = std::max(side, 0.5 * rlist + 1e-3);
-    for (int iter = 0; iter < 64; iter++) {
-        long long ncell = 1;
-        int span = 1;
-        for (int d = 0; d < 3; d++) {
-            int nc = (int)std::floor(ext[d] / side);
-            if (nc < 1) nc = 1;
-            G.nc[d] = nc;
-            G.cs[d] = ext[d] / nc;
-            G.inv_cs[d] = 1.0 / G.cs[d];
-            G.lo[d] = lo[d];
-            G.box[d] = ext[d];
-            G.boxf[d] = (float)ext[d];
-            ncell *= nc;
-            int sp = (int)std::floor((G.cs[d] + 2 * rlist + 3e-4) / G.cs[d]) + 2;
-            if (!G.periodic) sp = std::min(sp, nc);
-            span = std::max(span, sp);
-        }
-        if (span <= kMaxSpan && ncell <= cell_cap) {
-            G.ncell = (int)ncell;
-            G.span = span;
-            return true;
-        }
-        side *= 1.1;
-    }
-    return false;
+    // the very function pairlist.cu sizes its grid with; SDMB200_LAYOUT=cells selects the
+    // geometric 3-D cells like there
+    const char* e = std::getenv("SDMB200_LAYOUT");
+    return size_grid(G, n, R, periodic, rlist, lo, ext, cell_cap, !(e && std::string(e) == "cells"));
 }
 
 }  // namespace
@@ -90,7 +60,7 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     }
     if (!setup_grid(G, n, R, periodic != 0, rlist, lo, ext, std::max(64, n / 8 + 64))) return -1;
     const int ncells = R * G.ncell;
-    const int noff = G.span * G.span * G.span;
+    const int noff = G.span * G.span * (G.columns ? G.kz : G.span);
 
     // keys + three stable sorts: (cell, z), then kd refinement by y and by x (key_kernel,
     // refine_key_kernel and the radix sorts of pairlist.cu)
@@ -114,6 +84,23 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
         for (int k = 0; k < total; k++) { ks[k] = keys[order[k]]; vs[k] = vals[order[k]]; }
     };
     sort_pairs();
+    if (G.columns) {
+        // column layout: that was the (column, z) order; cut the columns into chunk cells
+        // (chunk_key_kernel) and sort by (cell, z rank)
+        std::vector<int> col_first(ncells + 1, 0);
+        for (int k = 0; k < total; k++) {
+            uint32_t c = (uint32_t)(ks[k] >> kSubBits);
+            if (k == 0 || (uint32_t)(ks[k - 1] >> kSubBits) != c) col_first[c] = k;
+        }
+        for (int p = 0; p < total; p++) {
+            const uint32_t pc = (uint32_t)(ks[p] >> kSubBits);
+            uint32_t rin;
+            const uint32_t g = chunk_cell(G, pc, p - col_first[pc], &rin);
+            keys[p] = make_key(g, 0u, rin);
+            vals[p] = vs[p];
+        }
+        sort_pairs();
+    }
     // cells
     std::vector<int> cell_first(ncells + 1, 0), cell_count(ncells + 1, 0), cell_slot(ncells + 2, 0), cell_sci(ncells + 2, 0);
     for (int k = 0; k < total; k++) {
@@ -190,17 +177,26 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     V.sci_box = sci_box.data();
     V.cl_box = cl_box.data();
     V.cell_slot = cell_slot.data();
+    std::vector<BBox> cell_box(ncells);   // cell_box_kernel
+    for (int c = 0; c < ncells; c++) {
+        BBox b;
+        for (int d = 0; d < 3; d++) { b.lo[d] = kBoxEmptyLo; b.hi[d] = -kBoxEmptyLo; }
+        for (int k = cell_slot[c] / kClusterSize; k < cell_slot[c + 1] / kClusterSize; k++)
+            if (!box_empty(cl_box[k])) b = box_union(b, cl_box[k]);
+        cell_box[c] = b;
+    }
+    V.cell_box = cell_box.data();
     V.posq4 = posq.data();
     const long long nitems = (long long)nsci * noff;
     std::vector<int> item_off(nitems + 1, 0);
     for (long long t = 0; t < nitems; t++)
-        item_off[t + 1] = item_off[t] + search_item(V, (int)(t / noff), (int)(t % noff), [](int, uint32_t, uint32_t, bool) {});
+        item_off[t + 1] = item_off[t] + search_any(V, (int)(t / noff), (int)(t % noff), [](int, uint32_t, uint32_t, bool) {});
     const int nraw = item_off[nitems];
     std::vector<uint32_t> rx(nraw), ry(nraw);
     std::vector<int> rflag(nraw, 0), rsci(nraw);
     for (long long t = 0; t < nitems; t++) {
         int base = item_off[t];
-        search_item(V, (int)(t / noff), (int)(t % noff), [&](int k, uint32_t w0, uint32_t imask, bool diag) {
+        search_any(V, (int)(t / noff), (int)(t % noff), [&](int k, uint32_t w0, uint32_t imask, bool diag) {
             rx[base + k] = w0;
             ry[base + k] = imask;
             rflag[base + k] = diag ? 1 : 0;
