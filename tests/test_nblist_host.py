@@ -91,3 +91,42 @@ def test_skin_does_not_change_the_in_cutoff_set(chk, skin):
     case = S.synthetic_case(6000, 60, seed=2, protein_atoms=600)
     got, ref, _ = covered_pairs(chk, case, skin=skin)
     assert np.array_equal(got, ref)
+
+
+# ---- column layout (xy columns cut along z into 64-atom chunk cells): shapes that stress it -------
+
+def test_columns_overflow_their_chunk_cells(chk):
+    """All atoms squeezed into a quarter of the xy plane: those columns hold four times the
+    average, more than the kz chunk cells a column has, so their last cell keeps the rest (several
+    superclusters in one cell) while most columns are empty."""
+    case = S.synthetic_case(6000, 30, seed=21, protein_atoms=0)
+    case.positions = np.mod(case.positions, case.system.box)
+    case.positions[:, :2] *= 0.5
+    got, ref, st = covered_pairs(chk, case)
+    assert st[1] > 6000 / 64            # more superclusters than chunk cells would give
+    assert np.array_equal(got, ref)
+
+
+def test_tall_and_flat_boxes(chk):
+    """Same atoms in a box stretched along z (many chunks per column, the three z images are all
+    visited) and in one squeezed to just over two list radii along z (every chunk sees its own
+    periodic images)."""
+    base = S.synthetic_case(4200, 30, seed=22, protein_atoms=0)
+    L = base.system.box[0]
+    for scale in ((0.8, 0.8, 1.0 / 0.64), (1.35, 1.35, 2.2 / L)):
+        case = S.synthetic_case(4200, 30, seed=22, protein_atoms=0)
+        sc = np.array(scale)
+        case.system.box = case.system.box * sc
+        case.positions = np.mod(case.positions, base.system.box) * sc
+        assert np.all(case.system.box >= 2.0 * (case.system.cutoff + 0.06))
+        got, ref, _ = covered_pairs(chk, case)
+        assert np.array_equal(got, ref)
+
+
+def test_both_layouts_cover_the_same_pairs(chk, monkeypatch):
+    case = S.synthetic_case(3000, 30, seed=23, protein_atoms=300)
+    got_c, ref, st_c = covered_pairs(chk, case)
+    monkeypatch.setenv("SDMB200_LAYOUT", "cells")
+    got_g, _, st_g = covered_pairs(chk, case)
+    assert np.array_equal(got_c, ref) and np.array_equal(got_g, ref)
+    assert st_c[0] < st_g[0]            # fewer padded slots with columns
