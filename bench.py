@@ -113,6 +113,38 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def elementwise_hbm(peak_gbs, n=16_000_000):
+    """The path's two bandwidth-bound kernels as the reference's kernel interface has them --
+    displace (MakeState2, langevin.cl:198-206: 48 B/atom) and hybrid-force mix (langevin.cl:72-87:
+    64 B/atom) -- on arrays larger than L2 (256 MB each), timed with CUDA events; best of 10."""
+    import torch
+    from openmm_sdm_plugin_b200 import _lib
+    L = _lib.lib()
+    a, b, c = (torch.randn(n, 4, dtype=torch.float32, device="cuda") for _ in range(3))
+    b[:, 3] = 0
+    st = torch.cuda.current_stream().cuda_stream
+    ops = [("sdm_k_make_state2", 48, lambda: L.sdm_k_make_state2(st, n, a.data_ptr(), b.data_ptr())),
+           ("sdm_k_hybrid_force", 64, lambda: L.sdm_k_hybrid_force(st, n, a.data_ptr(), b.data_ptr(), c.data_ptr(), 0.37))]
+    out = []
+    for name, bpa, fn in ops:
+        for _ in range(3):
+            _lib.check(fn())
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for e0, e1 in ev:
+            e0.record()
+            _lib.check(fn())
+            e1.record()
+        torch.cuda.synchronize()
+        ms = min(x.elapsed_time(y) for x, y in ev)
+        gbs = bpa * n / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": gbs / peak_gbs, "bytes_per_atom": bpa, "n_atoms": n, "ms": ms})
+    del a, b, c
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline(case, seconds_budget=20.0, nthreads=1):
     """The reference's algorithm (oracle port: two full list builds + pair loops per eval,
     double precision, like LangevinIntegratorSDM::step on the Reference platform) timed on this
@@ -210,6 +242,7 @@ def main():
     ap.add_argument("--exchange-every", type=int, default=10,
                     help="steps between replica-exchange all-gathers of (u_sc, state) in the e2e leg (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-elementwise", action="store_true")
     ap.add_argument("--no-single-lambda", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
@@ -462,6 +495,9 @@ def main():
         line["single_lambda"] = {"value": 1e3 / ms1, "unit": "evals/s", "ms_per_step": ms1, "replicas": 1,
                                  "ns_per_day_upper_bound": 1e3 / ms1 * 1e-6 * 86400,
                                  "note": "one resident replica, positions in HBM, list rebuilds included, no L2 flush"}
+    if rank == 0 and not args.no_elementwise:
+        # the bandwidth-bound kernels of the path against the measured HBM copy bandwidth
+        line["roofline_elementwise"] = elementwise_hbm(pk["hbm_gbs"])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, ns = cpu_baseline(case, args.cpu_seconds, 1)
         line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
