@@ -243,6 +243,7 @@ def main():
                     help="steps between replica-exchange all-gathers of (u_sc, state) in the e2e leg (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-elementwise", action="store_true")
+    ap.add_argument("--no-md-loop", action="store_true")
     ap.add_argument("--no-single-lambda", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
@@ -294,7 +295,7 @@ def main():
     # displacement of a 1 fs step at 300 K, so every step uploads genuinely new positions
     h_pos_b.array[...] = base + rng.normal(scale=0.0006, size=(R, n, 3))
 
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # 168 MB > 126 MB L2
 
     def exchange_gather(scalars):
         """(u_sc, state id) all-gather a replica-exchange round needs -- the path's only
@@ -456,7 +457,7 @@ def main():
             "data": "shipped fixture (positions+topology), replica jitter synthetic" if args.workload in ("cfg1", "cfg2") else "synthetic",
             "config": {"workload": wname, "replicas_per_gpu": R, "lambda_schedule": "22-window ILogistic ladder",
                        "pair_mode": {1: "allpairs", 2: "cluster"}[mode], "skin_nm": args.skin, "nstlist": args.nstlist,
-                       "l2": "flushed between timed steps (256 MiB write)", "timing": "CUDA events per step on the launching stream, max over ranks"},
+                       "l2": "flushed between timed steps (160 MiB write, L2 = 126 MB)", "timing": "CUDA events per step on the launching stream, max over ranks"},
             "evals_per_s_per_replica": value / (world * R),
             "ns_per_day_per_replica_upper_bound": value / (world * R) * 1e-6 * 86400,
             "roofline": roofline, "gpu_launches": int(launches),
@@ -469,7 +470,7 @@ def main():
                     "note": "C-ABI calls with pinned HOST buffers: sdm_set_positions_all (H2D) + sdm_eval + sdm_enqueue_results (D2H of forces and scalars) "
                             "+ sdm_synchronize/sdm_collect_scalars per step inside the timed region (host wall clock over all K steps, synchronize on both "
                             "sides); D batches of R replicas in flight on D contexts/streams so copies overlap the kernels of the neighbouring batches; "
-                            "the D working sets (D x ~60 MB) rotate through the 126 MB L2 and a 256 MiB flush write runs beside every step"},
+                            "the D working sets (D x ~60 MB) rotate through the 126 MB L2 and a 160 MiB flush write runs beside every step"},
             "clocks": sampler.result(), "wall_s_resident_leg": wall_resident}
 
     if rank == 0 and R > 1 and not args.no_single_lambda:
@@ -495,6 +496,34 @@ def main():
         line["single_lambda"] = {"value": 1e3 / ms1, "unit": "evals/s", "ms_per_step": ms1, "replicas": 1,
                                  "ns_per_day_upper_bound": 1e3 / ms1 * 1e-6 * 86400,
                                  "note": "one resident replica, positions in HBM, list rebuilds included, no L2 flush"}
+    if rank == 0 and not args.no_md_loop and case.masses is not None:
+        # device-resident loop (sdm_md_step = sdm_eval + FP64 Langevin update): positions
+        # and velocities never leave HBM.  The path owns only the nonbonded force group and no
+        # constraints, so real masses would let the bond-less fixture fly apart within a few fs; the
+        # particles are made 1e6 times heavier to time the loop's mechanics, nothing else.
+        try:
+            ctx.md_init(case.masses * 1.0e6, 300.0, 1.0, 0.001, seed=1234)
+            for _ in range(3):
+                ctx.md_step(1)
+            torch.cuda.synchronize()
+            evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for k in range(args.steps):
+                flush.zero_()
+                evm[k][0].record(stream)
+                ctx.md_step(1)
+                evm[k][1].record(stream)
+            torch.cuda.synchronize()
+            md_ms = sum(a.elapsed_time(b) for a, b in evm) / args.steps
+            scm = ctx.read_results(None)
+            if all(x["status"] == 0 for x in scm):
+                line["md_loop"] = {"value": R / (md_ms * 1e-3), "unit": "replica-steps/s", "ms_per_step": md_ms,
+                                   "ns_per_day_per_replica_at_1fs": 1e3 / md_ms * 1e-6 * 86400,
+                                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                   "note": "sdm_md_step: eval + FP64 Langevin update (bit-identical to the reference's "
+                                           "ReferenceStochasticDynamicsSDM::update given the same force and noise), no "
+                                           "constraints, no bonded forces; masses x 1e6 (mechanical timing only)"}
+        except Exception as ex:   # an extra, never the reason for a missing bench line
+            line["md_loop"] = {"error": str(ex)[:200]}
     if rank == 0 and not args.no_elementwise:
         # the bandwidth-bound kernels of the path against the measured HBM copy bandwidth
         line["roofline_elementwise"] = elementwise_hbm(pk["hbm_gbs"])

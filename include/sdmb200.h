@@ -251,6 +251,33 @@ int sdm_k_langevin_part2(void* cuda_stream, int n, void* posq, const void* pos_d
  * BOLTZ at :57-60).  Units: K, 1/ps, ps. */
 int sdm_langevin_params(double temperature, double friction, double step_size, double* vscale,
                         double* fscale, double* noisescale);
+/* ---- device-resident Langevin dynamics -------------------------------------
+ * The update the reference applies after the hybrid force, Reference-platform algorithm
+ * (platforms/reference/src/ReferenceStochasticDynamicsSDM.cpp:131-266; the OpenCL kernels
+ * langevin.cl:7-69 are its float form): v = vscale*v + fscale*F/m + noisescale*xi/sqrt(m),
+ * x' = x + dt*v, v = (x'-x)/dt.  Positions and velocities of all replicas stay in HBM, FP64, with
+ * the reference's operation order, so a step needs no host<->device copy.  Constraints (OpenMM's
+ * SETTLE / CCMA, ReferenceStochasticDynamicsSDM.cpp:250-252) are NOT applied: meant for
+ * unconstrained systems and for measuring the device-resident loop. */
+/* masses [n_atoms] (0 = particle does not move); velocities start at zero.  friction (1/ps) must be
+ * > 0 (the reference divides by it); seed keys the Philox4x32-10 noise stream. */
+int sdm_md_init(sdm_ctx* ctx, const double* masses, double temperature, double friction,
+                double step_size, uint64_t seed);
+int sdm_md_set_velocities(sdm_ctx* ctx, int replica, const double* v);   /* [3*n_atoms] nm/ps */
+int sdm_md_get_velocities(sdm_ctx* ctx, int replica, double* v);         /* synchronises */
+int sdm_get_positions(sdm_ctx* ctx, int replica, double* xyz);           /* current positions, synchronises */
+/* nsteps x (sdm_eval + Langevin update), asynchronous on the context's stream. */
+int sdm_md_step(sdm_ctx* ctx, int nsteps);
+/* The update alone, with the hybrid force already on the device (forces_all == NULL) or with
+ * forces_all [R][n][3] uploaded first (test hook: the reference's forces in, its x and v out). */
+int sdm_md_update(sdm_ctx* ctx, const double* forces_all);
+/* Test hook: the NEXT update draws its normals from xi_all [R][n][3] (atom-major, x y z: the order
+ * the reference consumes SimTKOpenMMUtilities::getNormallyDistributedRandomNumber) instead of the
+ * Philox stream; NULL cancels. */
+int sdm_md_set_noise(sdm_ctx* ctx, const double* xi_all);
+/* 0.5 * sum m v^2 of one replica (ReferenceSDMKernels.cpp:105-137 without constraints). */
+int sdm_md_kinetic_energy(sdm_ctx* ctx, int replica, double* ke);
+
 /* Scalar half of execute() (ReferenceSDMKernels.cpp:205-302): from E1, E2, Eb and the
  * integrator state compute u_sc, fp, ebias, bfp, sp, PotEnergy, BindE and update the
  * non-equilibrium state in *alch.  O(1) host arithmetic, exactly as the reference does it on

@@ -103,6 +103,14 @@ SYMBOLS = {
     "sdm_k_langevin_part2": (_I, [_VP, _I, _VP, _VP, _VP, C.c_float]),
     "sdm_langevin_params": (_I, [_D, _D, _D, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D)]),
     "sdm_execute_scalars": (_I, [C.POINTER(SdmAlch), _D, _D, _D, C.POINTER(SdmScalars)]),
+    "sdm_md_init": (_I, [_VP, _VP, _D, _D, _D, C.c_uint64]),
+    "sdm_md_set_velocities": (_I, [_VP, _I, _VP]),
+    "sdm_md_get_velocities": (_I, [_VP, _I, _VP]),
+    "sdm_get_positions": (_I, [_VP, _I, _VP]),
+    "sdm_md_step": (_I, [_VP, _I]),
+    "sdm_md_update": (_I, [_VP, _VP]),
+    "sdm_md_set_noise": (_I, [_VP, _VP]),
+    "sdm_md_kinetic_energy": (_I, [_VP, _I, C.POINTER(_D)]),
 }
 
 _LIB = None

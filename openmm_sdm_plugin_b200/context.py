@@ -229,6 +229,52 @@ class SDMContext:
         _lib.check(self._L.sdm_get_last_timing(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    # ---- device-resident Langevin dynamics (sdm_md_*; SURVEY N2, no constraints) --------------
+    def md_init(self, masses, temperature: float, friction: float, step_size: float, seed: int = 0):
+        m = np.ascontiguousarray(masses, np.float64)
+        if m.size != self.n:
+            raise ValueError("masses must be [n_atoms]")
+        _lib.check(self._L.sdm_md_init(self._h, _ptr(m), float(temperature), float(friction),
+                                       float(step_size), int(seed)))
+
+    def md_set_velocities(self, replica: int, v):
+        a = np.ascontiguousarray(v, np.float64)
+        if a.size != 3 * self.n:
+            raise ValueError("velocities must be [n_atoms, 3]")
+        _lib.check(self._L.sdm_md_set_velocities(self._h, replica, _ptr(a)))
+
+    def md_velocities(self, replica: int) -> np.ndarray:
+        out = np.empty((self.n, 3))
+        _lib.check(self._L.sdm_md_get_velocities(self._h, replica, _ptr(out)))
+        return out
+
+    def positions(self, replica: int) -> np.ndarray:
+        out = np.empty((self.n, 3))
+        _lib.check(self._L.sdm_get_positions(self._h, replica, _ptr(out)))
+        return out
+
+    def md_step(self, nsteps: int = 1):
+        _lib.check(self._L.sdm_md_step(self._h, int(nsteps)))
+
+    def md_update(self, forces_all=None):
+        a = None if forces_all is None else np.ascontiguousarray(forces_all, np.float64)
+        if a is not None and a.size != 3 * self.n * self.R:
+            raise ValueError("forces must be [n_replicas, n_atoms, 3]")
+        _lib.check(self._L.sdm_md_update(self._h, _ptr(a) if a is not None else None))
+        if a is not None:
+            self.synchronize()      # the upload source is a temporary
+
+    def md_set_noise(self, xi_all):
+        a = None if xi_all is None else np.ascontiguousarray(xi_all, np.float64)
+        if a is not None and a.size != 3 * self.n * self.R:
+            raise ValueError("noise must be [n_replicas, n_atoms, 3]")
+        _lib.check(self._L.sdm_md_set_noise(self._h, _ptr(a) if a is not None else None))
+
+    def md_kinetic_energy(self, replica: int) -> float:
+        v = C.c_double()
+        _lib.check(self._L.sdm_md_kinetic_energy(self._h, replica, C.byref(v)))
+        return v.value
+
     def info(self, key: str) -> float:
         v = C.c_double()
         _lib.check(self._L.sdm_get_info(self._h, key.encode(), C.byref(v)))

@@ -928,6 +928,126 @@ int sdm_langevin_params(double temperature, double friction, double step_size, d
     return SDM_OK;
 }
 
+// ---- device-resident Langevin dynamics (no constraints) -----------------------------
+
+int sdm_md_init(sdm_ctx* c, const double* masses, double temperature, double friction, double step_size,
+                uint64_t seed) {
+    if (!c || !masses) return fail(SDM_ERR_INVALID, "null argument");
+    if (!(friction > 0.0) || !(step_size > 0.0) || !(temperature >= 0.0))
+        return fail(SDM_ERR_INVALID, "sdm_md_init needs friction > 0, step_size > 0, temperature >= 0 "
+                                     "(the reference's update divides by the friction)");
+    const int n = c->n, R = c->R;
+    if (!c->md_ready) {
+        if (int rc = dev_alloc(c, &c->d_vel, 3 * (size_t)n * R)) return rc;
+        if (int rc = dev_alloc(c, &c->d_noise, 3 * (size_t)n * R)) return rc;
+        if (int rc = dev_alloc(c, &c->d_invm, (size_t)n)) return rc;
+        if (int rc = dev_alloc(c, &c->d_mass, (size_t)n)) return rc;
+        if (int rc = dev_alloc(c, &c->d_ke, (size_t)R)) return rc;
+    }
+    std::vector<double> invm(n);
+    for (int i = 0; i < n; i++) invm[i] = masses[i] == 0.0 ? 0.0 : 1.0 / masses[i];   // ReferenceStochasticDynamicsSDM.cpp:233-240
+    SDM_CUDA(cudaMemcpyAsync(c->d_invm, invm.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    SDM_CUDA(cudaMemcpyAsync(c->d_mass, masses, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    SDM_CUDA(cudaMemsetAsync(c->d_vel, 0, sizeof(double) * 3 * (size_t)n * R, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));   // invm is a host temporary
+    // the reference's constants, same expressions (ReferenceStochasticDynamicsSDM.cpp:144-148)
+    const double tau = 1.0 / friction;
+    const double BOLTZ = 1.380658e-23 * 6.0221367e23 / 1000.0;
+    const double kT = BOLTZ * temperature;
+    c->md_dt = step_size;
+    c->md_vscale = std::exp(-step_size / tau);
+    c->md_fscale = (1 - c->md_vscale) * tau;
+    c->md_noisescale = std::sqrt(2 * kT / tau) * std::sqrt(0.5 * (1 - c->md_vscale * c->md_vscale) * tau);
+    c->md_seed = seed;
+    c->md_steps = 0;
+    c->md_noise_pending = false;
+    c->md_ready = true;
+    return SDM_OK;
+}
+
+static int md_check(sdm_ctx* c, int replica) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!c->md_ready) return fail(SDM_ERR_INVALID, "call sdm_md_init first");
+    return SDM_OK;
+}
+
+int sdm_md_set_velocities(sdm_ctx* c, int replica, const double* v) {
+    if (int rc = md_check(c, replica)) return rc;
+    if (!v) return fail(SDM_ERR_INVALID, "null velocities");
+    SDM_CUDA(cudaMemcpyAsync(c->d_vel + (size_t)replica * 3 * c->n, v, sizeof(double) * 3 * (size_t)c->n,
+                             cudaMemcpyHostToDevice, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    return SDM_OK;
+}
+
+int sdm_md_get_velocities(sdm_ctx* c, int replica, double* v) {
+    if (int rc = md_check(c, replica)) return rc;
+    if (!v) return fail(SDM_ERR_INVALID, "null argument");
+    SDM_CUDA(cudaMemcpyAsync(v, c->d_vel + (size_t)replica * 3 * c->n, sizeof(double) * 3 * (size_t)c->n,
+                             cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    return SDM_OK;
+}
+
+int sdm_get_positions(sdm_ctx* c, int replica, double* xyz) {
+    if (int rc = check_ctx(c, replica)) return rc;
+    if (!xyz) return fail(SDM_ERR_INVALID, "null argument");
+    SDM_CUDA(cudaMemcpyAsync(xyz, c->d_pos + (size_t)replica * 3 * c->n, sizeof(double) * 3 * (size_t)c->n,
+                             cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    return SDM_OK;
+}
+
+int sdm_md_set_noise(sdm_ctx* c, const double* xi_all) {
+    if (int rc = md_check(c, 0)) return rc;
+    c->md_noise_pending = xi_all != nullptr;
+    if (xi_all) {
+        SDM_CUDA(cudaMemcpyAsync(c->d_noise, xi_all, sizeof(double) * 3 * (size_t)c->n * c->R,
+                                 cudaMemcpyHostToDevice, c->stream));
+        SDM_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return SDM_OK;
+}
+
+static void md_enqueue_update(sdm_ctx* c) {
+    sdm::launch_langevin_fp64(c->n, c->R, c->d_pos, c->d_vel, c->B.F, c->d_invm, c->md_vscale, c->md_fscale,
+                              c->md_noisescale, c->md_dt, c->md_noise_pending ? c->d_noise : nullptr,
+                              c->md_seed, c->md_steps, c->stream);
+    c->md_noise_pending = false;
+    c->md_steps++;
+    c->launches++;
+}
+
+int sdm_md_update(sdm_ctx* c, const double* forces_all) {
+    if (int rc = md_check(c, 0)) return rc;
+    if (forces_all)
+        SDM_CUDA(cudaMemcpyAsync(c->B.F, forces_all, sizeof(double) * 3 * (size_t)c->n * c->R,
+                                 cudaMemcpyHostToDevice, c->stream));
+    md_enqueue_update(c);
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_md_step(sdm_ctx* c, int nsteps) {
+    if (int rc = md_check(c, 0)) return rc;
+    for (int k = 0; k < nsteps; k++) {
+        if (int rc = sdm_eval(c)) return rc;   // hybrid force of every replica at the current positions
+        md_enqueue_update(c);                  // positions and velocities advance on the device
+    }
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
+int sdm_md_kinetic_energy(sdm_ctx* c, int replica, double* ke) {
+    if (int rc = md_check(c, replica)) return rc;
+    if (!ke) return fail(SDM_ERR_INVALID, "null argument");
+    sdm::launch_kinetic_energy(c->n, c->R, c->d_vel, c->d_mass, c->d_ke, c->stream);
+    c->launches++;
+    SDM_CUDA(cudaMemcpyAsync(ke, c->d_ke + replica, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    return SDM_OK;
+}
+
 int sdm_execute_scalars(sdm_alch* alch, double E1, double E2, double Eb, sdm_scalars* out) {
     if (!alch || !out) return fail(SDM_ERR_INVALID, "null argument");
     std::memset(out, 0, sizeof(*out));

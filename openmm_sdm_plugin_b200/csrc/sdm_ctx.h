@@ -56,6 +56,17 @@ struct sdm_ctx {
     int graph_launches = 0;             // kernels inside the captured sequence
     int* d_list_age = nullptr;          // evals since the list was built, kept on the device
 
+    // device-resident Langevin dynamics (sdm_md_*; no constraints)
+    bool md_ready = false;
+    double* d_vel = nullptr;            // [R][n][3]
+    double* d_invm = nullptr;           // [n] 1/mass, 0 for massless particles
+    double* d_mass = nullptr;           // [n]
+    double* d_noise = nullptr;          // [R][n][3] explicit normals for the next update (test hook)
+    double* d_ke = nullptr;             // [R] kinetic energies
+    bool md_noise_pending = false;
+    double md_dt = 0, md_vscale = 0, md_fscale = 0, md_noisescale = 0;
+    unsigned long long md_seed = 0, md_steps = 0;
+
     int64_t launches = 0;
     int64_t n_evals = 0;
     bool timing = false, timing_valid = false;

@@ -84,5 +84,9 @@ void launch_langevin_part1(int n, float4* velm, const float4* force, float4* pos
                            unsigned random_index, cudaStream_t s);
 void launch_langevin_part2(int n, float4* posq, const float4* pos_delta, float4* velm, float step_size,
                            cudaStream_t s);
+void launch_langevin_fp64(int n, int R, double* pos, double* vel, const double* force, const double* invm,
+                          double vscale, double fscale, double noisescale, double dt, const double* noise,
+                          unsigned long long seed, unsigned long long step, cudaStream_t s);
+void launch_kinetic_energy(int n, int R, const double* vel, const double* mass, double* ke, cudaStream_t s);
 
 }  // namespace sdm
