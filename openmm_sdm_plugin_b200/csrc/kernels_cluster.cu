@@ -16,9 +16,12 @@
 //     tj once per unit (transpose-reduction, 42 shuffles),
 //   * the j force accumulates in 3 packed registers across the tiles of an entry and is reduced
 //     over ti once per ENTRY with 3 shuffles,
-//   * the 32 entry words of a unit are fetched with one coalesced load and broadcast by shuffle,
-//     the j data of entry e+1 is requested before the tiles of entry e are computed, and the
-//     imask word goes through REDUX so that the per-cluster branches are uniform (BRA.U).
+//   * the 32 entry words of a unit are fetched with one coalesced load and broadcast by shuffle;
+//     the j-clusters of the whole unit (<= 32 x 8 atoms) are staged in shared memory up front,
+//     already shifted to their periodic image -- eight independent loads per lane in flight
+//     instead of one dependent pair per entry, no prefetch registers to rotate, no shift per
+//     entry -- and the imask word goes through REDUX so that the per-cluster branches are
+//     uniform (BRA.U).
 // Forces go to 64-bit fixed-point accumulators (2^32), so the result is independent of the
 // order in which warps finish: bit-reproducible across runs, replicas-per-GPU and GPUs.
 //
@@ -45,6 +48,9 @@ namespace {
 #endif
 #ifndef SDM_PAIR_MINB
 #define SDM_PAIR_MINB 16
+#endif
+#ifndef SDM_PAIR_JSMEM
+#define SDM_PAIR_JSMEM 1
 #endif
 #ifndef SDM_PAIR_SEL2
 #define SDM_PAIR_SEL2 1
@@ -257,7 +263,8 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
                                              const double* __restrict__ pos_all,
                                              long long* __restrict__ f1acc, double* __restrict__ epart,
                                              long long* __restrict__ cpart, const int unit,
-                                             const int lane, IPair* s_ip, const float4* s_shift) {
+                                             const int lane, IPair* s_ip, const float4* s_shift,
+                                             float4* s_jx, float2* s_jp) {
     const Unit u = V.units[unit];
     const nbl::SciDesc sd = V.sci[u.sci];
     const int ibase = sd.c0 * nbl::kClusterSize;
@@ -291,6 +298,29 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
     }
     __syncwarp();
 
+#if SDM_PAIR_JSMEM
+    // stage the j-clusters of the whole unit (<= 32 entries x 8 atoms), already shifted to their
+    // periodic image: eight independent loads per lane are in flight at once, and the entry loop
+    // below reads its j atom with two LDS instead of two dependent global loads + a shift
+    {
+#pragma unroll
+        for (int m = 0; m < nbl::kJGroup; m++) {
+            const int a = lane + 32 * m;                    // staged atom: entry a>>3, atom a&7
+            const uint32_t w = __shfl_sync(0xffffffffu, my_ent.x, a >> 3);
+            if ((a >> 3) < nent) {
+                const int sl = (int)(w & 0x3ffffffu) * nbl::kJGroup + (a & 7);
+                float4 x = V.posq[sl];
+                if (PERIODIC) {
+                    const float4 sh = s_shift[w >> 26];
+                    x.x += sh.x; x.y += sh.y; x.z += sh.z;
+                }
+                s_jx[a] = x;
+                s_jp[a] = V.par[sl];
+            }
+        }
+    }
+    __syncwarp();
+#endif
     Acc2 fi[nbl::kMaxCi];
 #pragma unroll
     for (int ci = 0; ci < nbl::kMaxCi; ci++) fi[ci] = Acc2{0ull, 0ull, 0ull};
@@ -300,6 +330,16 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
     const size_t plane = (size_t)V.nslot_cap;
     long long* const facc_j = f1acc + (size_t)(ti < 3 ? ti : 2) * plane;   // lane ti adds component ti
 
+#if SDM_PAIR_JSMEM
+    for (int k = 0; k < nent; k++) {
+        // uniform (REDUX) copy of the entry word: branches on imask need no reconvergence
+        const uint32_t ey = __reduce_or_sync(0xffffffffu, __shfl_sync(0xffffffffu, my_ent.y, k));
+        const uint32_t imask = ey & 0xffu;
+        const uint32_t midx = ey >> 8;
+        const int jslot_k = (int)(__shfl_sync(0xffffffffu, my_ent.x, k) & 0x3ffffffu) * nbl::kJGroup + tj;
+        const float4 xj = s_jx[k * nbl::kJGroup + tj];
+        const float2 pj = s_jp[k * nbl::kJGroup + tj];
+#else
     // software pipeline: j data of the next entry is in flight while this entry is computed
     uint32_t ex = __shfl_sync(0xffffffffu, my_ent.x, 0);
     int jslot = (int)(ex & 0x3ffffffu) * nbl::kJGroup + tj;
@@ -325,6 +365,7 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
             const float4 sh = s_shift[code];
             xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
         }
+#endif
         Acc2 fj{0ull, 0ull, 0ull};
         float tmin = 3.0e38f;
         if (midx == 0)
@@ -443,12 +484,20 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
 // computes which unit does not influence the result (fixed-point accumulation, per-unit energy
 // partials).
 template <bool PERIODIC, bool EXACT>
+#ifdef SDM_PAIR_MAXNREG   /* development knob: cap the registers directly instead of via min blocks */
+__global__ void __maxnreg__(SDM_PAIR_MAXNREG)
+#else
 __global__ void __launch_bounds__(kWarps * 32, SDM_PAIR_MINB)
+#endif
 pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
                     const double* __restrict__ pos_all, long long* __restrict__ f1acc,
                     double* __restrict__ epart, long long* __restrict__ cpart, int* unit_counter) {
     __shared__ IPair s_ip[kWarps][kIRows];
     __shared__ float4 s_shift[64];
+#if SDM_PAIR_JSMEM
+    __shared__ float4 s_jx[kWarps][32 * nbl::kJGroup];
+    __shared__ float2 s_jp[kWarps][32 * nbl::kJGroup];
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (PERIODIC) {
         for (uint32_t code = threadIdx.x; code < 64; code += kWarps * 32)
@@ -462,7 +511,13 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         if (lane == 0) unit = atomicAdd(unit_counter, 1);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= V.nunits) break;
-        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift);
+#if SDM_PAIR_JSMEM
+        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
+                                      s_jx[warp], s_jp[warp]);
+#else
+        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
+                                      nullptr, nullptr);
+#endif
     }
 }
 
@@ -904,6 +959,9 @@ void launch_pair_cluster(const Topology& T, const PairListView& V, const double*
     do {                                                                                          \
         static int resident = 0; /* blocks per SM the hardware keeps resident (register limited) */ \
         if (!resident) {                                                                          \
+            if (SDM_PAIR_JSMEM) /* 8.7 KB per one-warp block: ask for the large shared-memory carve-out */ \
+                cudaFuncSetAttribute(pair_cluster_kernel<P, X>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                     cudaSharedmemCarveoutMaxShared);                             \
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_cluster_kernel<P, X>,  \
                                                               kWarps * 32, 0) != cudaSuccess ||    \
                 resident < 1)                                                                     \
