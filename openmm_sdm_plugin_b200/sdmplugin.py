@@ -190,7 +190,67 @@ class LangevinIntegratorSDM(object):
         self.last_scalars = sc
         return c.forces(0, _lib.FORCE_HYBRID)
 
+    # ---- dynamics on the device (no constraints) ----------------------------
+    def setState(self, positions, velocities=None, masses=None):
+        """What the reference's Context holds for the integrator: positions (nm), velocities (nm/ps,
+        zero if omitted) and the particle masses (amu; needed once).  The state then lives on the
+        device; `step()` advances it there."""
+        if self._ctx is None:
+            raise OpenMMException("the integrator is not bound to a context: call bind(system) first")
+        if masses is not None:
+            self._masses = np.ascontiguousarray(masses, np.float64).copy()
+            self._md_params = None
+        self._ctx.set_positions(0, np.ascontiguousarray(positions, np.float64))
+        self._pending_vel = (np.zeros((self._n, 3)) if velocities is None
+                             else np.ascontiguousarray(velocities, np.float64).copy())
+
+    def getPositions(self):
+        return self._ctx.positions(0)
+
+    def getVelocities(self):
+        return self._ctx.md_velocities(0)
+
+    def computeKineticEnergy(self):
+        """LangevinIntegratorSDM::computeKineticEnergy (ReferenceSDMKernels.cpp:105-137, no constraints)."""
+        return self._ctx.md_kinetic_energy(0)
+
     def step(self, steps):
-        raise OpenMMException(
-            "LangevinIntegratorSDM.step integrates the equations of motion, which is outside the "
-            "B200 hot path (SURVEY.md 8(f) N2); call evaluate(positions) for the force column of a step")
+        """LangevinIntegratorSDM::step (LangevinIntegratorSDM.cpp:153-183) with the state on the
+        device: per step the fused dual-state evaluation and the reference's Langevin update
+        (ReferenceStochasticDynamicsSDM.cpp:131-266, FP64, no constraints).  Force group 1 is
+        whatever was last handed over with the context's set_bonded_forces (zero by default)."""
+        if self._ctx is None:
+            raise OpenMMException("the integrator is not bound to a context: call bind(system) first")
+        if getattr(self, "_masses", None) is None:
+            raise OpenMMException("step() needs the particle masses: call setState(positions, velocities, masses) "
+                                  "first, or evaluate(positions) for the force column of a step alone")
+        c = self._ctx
+        params = (self._temperature, self._friction, self._step_size)
+        if getattr(self, "_md_params", None) != params:
+            # like the Reference kernel, the dynamics object is recreated when T, friction or dt change
+            # (ReferenceSDMKernels.cpp:320-337); velocities survive
+            keep = None if getattr(self, "_md_params", None) is None else c.md_velocities(0)
+            c.md_init(self._masses, self._temperature, self._friction, self._step_size, self._seed & (2 ** 63 - 1))
+            if keep is not None:
+                c.md_set_velocities(0, keep)
+            self._md_params = params
+        if getattr(self, "_pending_vel", None) is not None:
+            c.md_set_velocities(0, self._pending_vel)
+            self._pending_vel = None
+        if self._displ_dirty:
+            c.set_displacement(self._displ)
+            self._displ_dirty = False
+        for _ in range(int(steps)):
+            c.set_alchemical(0, self._a)       # non-equilibrium schedules advance with the integrator object
+            c.md_step(1)
+            sc = c.scalars(0)
+            if sc["status"] == _lib.SDM_ERR_SOFTCORE:
+                raise OpenMMException("Unknown soft core method")     # LangevinIntegratorSDM.cpp:147
+            if sc["status"] not in (0, _lib.SDM_ERR_STALE_LIST):
+                raise OpenMMException("libsdmb200 status %d" % sc["status"])
+            if sc["status"] == _lib.SDM_ERR_STALE_LIST:
+                c.invalidate_list()            # an atom left the list's skin: rebuild before the next step
+            c.get_alchemical(0, self._a)
+            self._bind_e = sc["bind_e"]
+            self._pot_energy = sc["pot_energy"]
+            self.last_scalars = sc

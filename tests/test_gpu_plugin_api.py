@@ -59,3 +59,52 @@ def test_unknown_softcore_method_raises_like_the_reference():
     with pytest.raises(OpenMMException, match="Unknown soft core method"):
         integrator.evaluate(case.positions)
     integrator.cleanup()
+
+
+def test_step_runs_the_dynamics_on_the_device_like_the_reference():
+    """integrator.step(n) of the mirror = the reference's step with the state on the device: two
+    steps of the 230-atom fixture with the reference's noise follow oracle/_ref (the reference's own
+    integrator + kernels compiled in place) to 1e-8 nm; BindE/PotEnergy are those of the last step."""
+    from oracle import oracle as O
+    from oracle import reference as R
+    if not R.available():
+        pytest.skip("oracle/_ref is built only where /root/reference exists")
+    case = S.cfg1()
+    n = case.system.n_atoms
+    rng = np.random.default_rng(21)
+    vel = rng.normal(scale=0.3, size=(n, 3))
+    xi = rng.normal(size=(2, n, 3))
+
+    def force_fn(groups, pos):
+        if groups == 4:
+            r = O.nonbonded(case.system, pos, nthreads=1)
+            return r["E"], r["forces"]
+        return 0.0, np.zeros_like(pos)
+    ref = R.run(case.masses, case.positions, vel, case.displacement,
+                R.params_from_alch(case.alch, temperature=300.0, friction=0.5), force_fn, steps=2, noise=xi.ravel())
+
+    integ = LangevinIntegratorSDM(300.0, 0.5, case.alch.step_size, n)
+    integ.setBiasMethod(case.alch.bias_method)
+    integ.setSoftCoreMethod(case.alch.softcore_method)
+    integ.setLambda1(case.alch.lambda1); integ.setLambda2(case.alch.lambda2); integ.setAlpha(case.alch.alpha)
+    integ.setU0(case.alch.u0); integ.setW0coeff(case.alch.w0coeff)
+    integ.setUmax(case.alch.umax); integ.setUbcore(case.alch.ubcore); integ.setAcore(case.alch.acore)
+    for i in np.nonzero(np.abs(case.displacement).sum(1))[0]:
+        integ.setDisplacement(int(i), *case.displacement[i])
+    integ.bind(case.system)
+    try:
+        with pytest.raises(Exception, match="masses"):
+            integ.step(1)
+        integ.setState(case.positions, vel, case.masses)
+        for k in range(2):
+            if k == 0:
+                integ.step(0)                       # creates the dynamics object, moves nothing
+            integ._ctx.md_set_noise(xi[k][None])    # test hook: the reference's normals
+            integ.step(1)
+        assert np.abs(integ.getPositions() - ref["positions"]).max() < 1e-8
+        assert np.abs(integ.getVelocities() - ref["velocities"]).max() < 1e-5 * np.abs(ref["velocities"]).max()
+        assert integ.getBindE() == pytest.approx(ref["bind_e"], abs=1e-6)
+        assert integ.getPotEnergy() == pytest.approx(ref["pot_energy"], rel=1e-5)
+        assert integ.computeKineticEnergy() == pytest.approx(ref["kinetic_energy"], rel=1e-5)
+    finally:
+        integ.cleanup()
