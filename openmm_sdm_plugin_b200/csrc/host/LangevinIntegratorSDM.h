@@ -164,9 +164,72 @@ public:
     }
     const sdm_scalars& getLastScalars() const { return lastScalars; }
 
-    void step(int) {
-        throw SDMException("LangevinIntegratorSDM::step integrates the equations of motion, which is "
-                           "outside the B200 hot path; call evaluate() for the force column of a step");
+    // ---- dynamics on the device (no constraints) ------------------------
+    // What the reference's Context holds for the integrator: positions [3*nParticles] (nm),
+    // velocities (nm/ps; null = zero) and the particle masses (amu; needed once, null = keep).
+    void setState(const double* positions, const double* velocities, const double* particleMasses) {
+        if (!ctx) throw SDMException("the integrator is not bound to a context");
+        if (particleMasses) {
+            masses.assign(particleMasses, particleMasses + nParticles);
+            mdTemperature = -1;   // forces a new dynamics object
+        }
+        check(sdm_set_positions(ctx, 0, positions));
+        check(sdm_synchronize(ctx));
+        pendingVel.assign(3 * (size_t)nParticles, 0.0);
+        if (velocities) pendingVel.assign(velocities, velocities + 3 * (size_t)nParticles);
+        havePendingVel = true;
+    }
+    void getPositions(double* positions) { check(sdm_get_positions(ctx, 0, positions)); }
+    void getVelocities(double* velocities) { check(sdm_md_get_velocities(ctx, 0, velocities)); }
+    double computeKineticEnergy() {
+        double ke = 0;
+        check(sdm_md_kinetic_energy(ctx, 0, &ke));
+        return ke;
+    }
+
+    // LangevinIntegratorSDM::step (LangevinIntegratorSDM.cpp:153-183) with the state on the device:
+    // per step the fused dual-state evaluation and the reference's Langevin update
+    // (ReferenceStochasticDynamicsSDM.cpp:131-266, FP64, no constraints).  Force group 1 is whatever
+    // evaluate() / sdm_set_bonded_forces last handed over (zero by default).
+    void step(int steps) {
+        if (!ctx) throw SDMException("the integrator is not bound to a context");
+        if (masses.empty())
+            throw SDMException("LangevinIntegratorSDM::step needs the particle masses: call setState() first, "
+                               "or evaluate() for the force column of a step alone");
+        if (mdTemperature != temperature || mdFriction != friction || mdStepSize != stepSize) {
+            // like the Reference kernel, the dynamics object is recreated when T, friction or dt
+            // change (ReferenceSDMKernels.cpp:320-337); velocities survive
+            std::vector<double> keep;
+            if (mdTemperature >= 0) {
+                keep.resize(3 * (size_t)nParticles);
+                check(sdm_md_get_velocities(ctx, 0, keep.data()));
+            }
+            check(sdm_md_init(ctx, masses.data(), temperature, friction, stepSize, (uint64_t)randomNumberSeed));
+            if (!keep.empty()) check(sdm_md_set_velocities(ctx, 0, keep.data()));
+            mdTemperature = temperature; mdFriction = friction; mdStepSize = stepSize;
+        }
+        if (havePendingVel) {
+            check(sdm_md_set_velocities(ctx, 0, pendingVel.data()));
+            havePendingVel = false;
+        }
+        if (displDirty) {
+            std::vector<double> flat = flatDisplacement();
+            check(sdm_set_displacement(ctx, flat.data()));
+            displDirty = false;
+        }
+        for (int k = 0; k < steps; k++) {
+            check(sdm_set_alchemical(ctx, 0, &alch));
+            check(sdm_md_step(ctx, 1));
+            sdm_scalars sc;
+            check(sdm_get_scalars(ctx, 0, &sc));
+            if (sc.status == SDM_ERR_SOFTCORE) throw SDMException("Unknown soft core method");
+            if (sc.status == SDM_ERR_STALE_LIST) check(sdm_invalidate_list(ctx));   // rebuild before the next step
+            else if (sc.status != SDM_OK) throw SDMException("libsdmb200 status " + std::to_string(sc.status));
+            BindE = sc.bind_e;
+            PotEnergy = sc.pot_energy;
+            lastScalars = sc;
+            check(sdm_get_alchemical(ctx, 0, &alch));
+        }
     }
 
 private:
@@ -192,6 +255,9 @@ private:
     sdm_scalars lastScalars{};
     sdm_ctx* ctx;
     bool displDirty;
+    std::vector<double> masses, pendingVel;
+    bool havePendingVel = false;
+    double mdTemperature = -1, mdFriction = -1, mdStepSize = -1;
 };
 
 }  // namespace SDMPlugin

@@ -3,6 +3,7 @@
 // round trips, the displacement map, and the error behaviour of an unbound integrator and of
 // sdm_create without a device.  Exit code 0 = all checks passed.  (test infrastructure)
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -48,6 +49,36 @@ int main() {
         threw = false;
         try { g.bind(s); } catch (const SDMPlugin::SDMException& e) { threw = std::strstr(e.what(), "no CPU fallback") != nullptr; }
         CHECK(threw);
+    }
+    if (sdm_device_count() > 0) {
+        // with a device: bind a tiny system, one evaluation, then two steps of device dynamics
+        const int n = 4;
+        std::vector<double> q = {0.3, -0.3, 0.2, -0.2}, sg(n, 0.3), ep(n, 0.5), m = {12.0, 16.0, 1.0, 0.0};
+        std::vector<double> pos = {0.0, 0.0, 0.0, 0.45, 0.0, 0.0, 0.0, 0.5, 0.0, 0.0, 0.0, 0.55};
+        sdm_system s;
+        std::memset(&s, 0, sizeof(s));
+        s.n_atoms = n; s.method = SDM_NOCUTOFF; s.charge = q.data(); s.sigma = sg.data(); s.epsilon = ep.data();
+        SDMPlugin::LangevinIntegratorSDM h(300.0, 1.0, 0.001, n);
+        h.setDisplacement(3, 1.0, 0.0, 0.0);
+        h.bind(s);
+        std::vector<double> force(3 * n);
+        h.evaluate(pos.data(), nullptr, 0.0, force.data());
+        const double pe0 = h.getPotEnergy();
+        threw = false;
+        try { h.step(1); } catch (const SDMPlugin::SDMException&) { threw = true; }   // no masses yet
+        CHECK(threw);
+        h.setState(pos.data(), nullptr, m.data());
+        h.step(2);
+        std::vector<double> x1(3 * n), v1(3 * n);
+        h.getPositions(x1.data());
+        h.getVelocities(v1.data());
+        double moved = 0;
+        for (int i = 0; i < 9; i++) moved += std::fabs(x1[i] - pos[i]);
+        CHECK(moved > 0.0);
+        for (int d = 0; d < 3; d++) CHECK(x1[9 + d] == pos[9 + d] && v1[9 + d] == 0.0);   // massless particle stays
+        CHECK(h.computeKineticEnergy() > 0.0);
+        CHECK(std::isfinite(h.getPotEnergy()) && std::isfinite(pe0));
+        h.cleanup();
     }
     std::printf("host api ok\n");
     return 0;

@@ -108,3 +108,17 @@ def test_step_runs_the_dynamics_on_the_device_like_the_reference():
         assert integ.computeKineticEnergy() == pytest.approx(ref["kinetic_energy"], rel=1e-5)
     finally:
         integ.cleanup()
+
+
+def test_cpp_host_mirror_on_the_device(tmp_path):
+    """tests/hostapi/host_api_check.cpp with a device present: the C++ mirror binds a tiny system,
+    evaluates, and runs two steps of device dynamics (massless particle stays, the rest moves)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_api_check")
+    libdir = os.path.join(root, "openmm_sdm_plugin_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", os.path.join(root, "tests", "hostapi", "host_api_check.cpp"),
+                           "-o", exe, "-L" + libdir, "-lsdmb200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "host api ok" in out.stdout, out.stdout + out.stderr
