@@ -52,6 +52,9 @@ namespace {
 #ifndef SDM_PAIR_JSMEM
 #define SDM_PAIR_JSMEM 1
 #endif
+#ifndef SDM_PAIR_MASKSMEM
+#define SDM_PAIR_MASKSMEM 1
+#endif
 #ifndef SDM_PAIR_SEL2
 #define SDM_PAIR_SEL2 1
 #endif
@@ -264,7 +267,7 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
                                              long long* __restrict__ f1acc, double* __restrict__ epart,
                                              long long* __restrict__ cpart, const int unit,
                                              const int lane, IPair* s_ip, const float4* s_shift,
-                                             float4* s_jx, float2* s_jp) {
+                                             float4* s_jx, float2* s_jp, uint32_t* s_mask) {
     const Unit u = V.units[unit];
     const nbl::SciDesc sd = V.sci[u.sci];
     const int ibase = sd.c0 * nbl::kClusterSize;
@@ -298,6 +301,17 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
     }
     __syncwarp();
 
+#if SDM_PAIR_JSMEM && SDM_PAIR_MASKSMEM
+    // exclusion-mask sets of the unit's masked entries (about one entry in ten): lane k fetches the
+    // 16 words of entry k now, so the entry loop reads them from shared memory instead of waiting
+    // for four dependent global loads right before the first tile of the entry
+    if (lane < nent && (my_ent.y >> 8)) {
+        const uint4* src = reinterpret_cast<const uint4*>(V.masks + (size_t)(my_ent.y >> 8) * nbl::kMaskWords);
+        uint4* dst = reinterpret_cast<uint4*>(s_mask + lane * nbl::kMaskWords);
+#pragma unroll
+        for (int q = 0; q < nbl::kMaskWords / 4; q++) dst[q] = src[q];
+    }
+#endif
 #if SDM_PAIR_JSMEM
     // stage the j-clusters of the whole unit (<= 32 entries x 8 atoms), already shifted to their
     // periodic image: eight independent loads per lane are in flight at once, and the entry loop
@@ -371,8 +385,13 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
         if (midx == 0)
             entry_tiles<false, EXACT>(imask, nullptr, lane, s_ip, xj, pj, K, fi, fj, en, cnt, tmin);
         else
+#if SDM_PAIR_JSMEM && SDM_PAIR_MASKSMEM
+            entry_tiles<true, EXACT>(imask, s_mask + k * nbl::kMaskWords, lane, s_ip, xj, pj, K,
+                                     fi, fj, en, cnt, tmin);
+#else
             entry_tiles<true, EXACT>(imask, V.masks + (size_t)midx * nbl::kMaskWords, lane, s_ip, xj, pj, K,
                                      fi, fj, en, cnt, tmin);
+#endif
         if (EXACT) {
             // entries with a pair inside the band are revisited after the loop (keeps the call
             // and its register pressure out of the hot loop); per-lane bits, OR-reduced once
@@ -497,6 +516,9 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
 #if SDM_PAIR_JSMEM
     __shared__ float4 s_jx[kWarps][32 * nbl::kJGroup];
     __shared__ float2 s_jp[kWarps][32 * nbl::kJGroup];
+#if SDM_PAIR_MASKSMEM
+    __shared__ __align__(16) uint32_t s_mask[kWarps][32 * nbl::kMaskWords];
+#endif
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (PERIODIC) {
@@ -512,11 +534,16 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= V.nunits) break;
 #if SDM_PAIR_JSMEM
+#if SDM_PAIR_MASKSMEM
         process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
-                                      s_jx[warp], s_jp[warp]);
+                                      s_jx[warp], s_jp[warp], s_mask[warp]);
 #else
         process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
-                                      nullptr, nullptr);
+                                      s_jx[warp], s_jp[warp], nullptr);
+#endif
+#else
+        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
+                                      nullptr, nullptr, nullptr);
 #endif
     }
 }
