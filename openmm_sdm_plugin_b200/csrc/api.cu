@@ -854,6 +854,7 @@ int sdm_get_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "pair_mode") *value = c->pair_mode;
     else if (k == "n_evals") *value = (double)c->n_evals;
     else if (k == "n_list_builds") *value = (double)c->n_builds;
+    else if (k == "list_age") *value = c->list_valid ? (double)c->list_age : 0.0;   // evaluations since the list was built
     else if (k == "e_dispersion") *value = c->T.e_disp;
     else if (k == "num_sms") *value = c->num_sms;
     else if (sdm_ctx_pairlist_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
