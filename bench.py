@@ -238,7 +238,7 @@ def main():
     ap.add_argument("--nstlist", type=int, default=20)
     ap.add_argument("--skin", type=float, default=0.06)
     ap.add_argument("--pair-mode", type=int, default=0)
-    ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the pipelined e2e leg (contexts/streams)")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="batches in flight in the pipelined e2e leg (contexts/streams)")
     ap.add_argument("--exchange-every", type=int, default=10,
                     help="steps between replica-exchange all-gathers of (u_sc, state) in the e2e leg (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
