@@ -239,6 +239,9 @@ def main():
     ap.add_argument("--skin", type=float, default=0.06)
     ap.add_argument("--pair-mode", type=int, default=0)
     ap.add_argument("--e2e-depth", type=int, default=4, help="batches in flight in the pipelined e2e leg (contexts/streams)")
+    ap.add_argument("--e2e-threads", type=int, default=0,
+                    help="1: one host thread per in-flight batch in the e2e leg (single GPU; measured no faster: "
+                         "28.7k vs 30.0k evals/s); 0: one thread drives all batches")
     ap.add_argument("--exchange-every", type=int, default=10,
                     help="steps between replica-exchange all-gathers of (u_sc, state) in the e2e leg (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -387,8 +390,52 @@ def main():
         cg.enqueue_results(e_hf[d].array)
         return s
 
+    def e2e_run_threaded(nsteps, depth):
+        """One host thread per context (the C ABI's threading rule: distinct contexts may be driven
+        from distinct threads): thread d submits steps d, d+depth, ... of its own batch, so a list
+        build -- whose host synchronisations block the submitting thread for about a millisecond --
+        stalls only that batch while the others keep the GPU fed.  Same work per step as the
+        single-threaded loop; wall clock over all steps with a synchronize on both sides."""
+        errors, lasts = [], [None] * depth
+
+        def worker(d):
+            try:
+                torch.cuda.set_device(local)
+                cg = e_ctx[d]
+                first = True
+                for k in range(d, nsteps, depth):
+                    with torch.cuda.stream(flush_stream):
+                        flush.zero_()
+                    if not first:
+                        cg.synchronize()
+                        cg.collect_scalars()
+                    cg.set_positions_all(h_pos.array if k % 2 == 0 else h_pos_b.array)
+                    cg.eval()
+                    cg.enqueue_results(e_hf[d].array)
+                    first = False
+                if not first:
+                    cg.synchronize()
+                    lasts[d] = cg.collect_scalars()
+            except Exception as ex:   # reported by the caller
+                errors.append(ex)
+
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=worker, args=(d,)) for d in range(depth)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if errors:
+            raise errors[0]
+        return dt, [x for x in lasts if x is not None][-1]
+
     def e2e_run(nsteps, depth, timed):
         """nsteps steps with `depth` batches in flight; returns (seconds, last scalars)."""
+        if timed and depth > 1 and world == 1 and args.e2e_threads:
+            return e2e_run_threaded(nsteps, depth)
         torch.cuda.synchronize()
         if world > 1 and timed:
             dist.barrier()
@@ -476,6 +523,7 @@ def main():
                     "ms_per_step": 1e3 * e2e_t / args.steps, "batches_in_flight": D,
                     "exchange_every_steps": args.exchange_every if world > 1 else None,
                     "list_builds": "lists pre-aged to staggered ages: the timed steps carry K/nstlist list builds",
+                    "host_threads": D if (world == 1 and args.e2e_threads and D > 1) else 1,
                     "host_cpus_local_to_gpu": n_local_cpus,
                     "serial": {"value": world * R * args.steps / e2e_serial_t, "ms_per_step": 1e3 * e2e_serial_t / args.steps,
                                "note": "one batch in flight, host waits for each step's results"},
