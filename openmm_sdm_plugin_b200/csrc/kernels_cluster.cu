@@ -49,17 +49,8 @@ namespace {
 #ifndef SDM_PAIR_MINB
 #define SDM_PAIR_MINB 16
 #endif
-#ifndef SDM_PAIR_JSMEM
-#define SDM_PAIR_JSMEM 1
-#endif
-#ifndef SDM_PAIR_MASKSMEM
-#define SDM_PAIR_MASKSMEM 1
-#endif
 #ifndef SDM_PAIR_SEL2
 #define SDM_PAIR_SEL2 1
-#endif
-#ifndef SDM_PAIR_JRED_ALWAYS
-#define SDM_PAIR_JRED_ALWAYS 0
 #endif
 // One warp per block: a warp that finishes its unit frees its slot at once (units differ in
 // length), which keeps the achieved occupancy at the register-limited maximum.
@@ -108,6 +99,26 @@ struct PairConsts {
     float rc2, krf, crf, band;
 };
 
+// Debug build of the hot kernel (template flag EMIT): every pair the kernel ACCEPTS -- in the tile
+// loop and in the band fix-up -- is also recorded with its System indices, so
+// sdm_get_pairs() returns the hot kernel's own decisions.  All of it compiles away when !EMIT.
+struct EmitCtx {
+    PairEmit em;
+    const int* atom;   // slot -> replica*n + atom
+    int n;
+};
+
+__device__ __forceinline__ void emit_pair(const EmitCtx& ec, const int islot, const int jslot) {
+    const int gi = ec.atom[islot], gj = ec.atom[jslot];
+    if (gi < 0 || gj < 0 || gi / ec.n != ec.em.replica) return;
+    const int a = gi % ec.n, b = gj % ec.n;
+    const int k = atomicAdd(ec.em.counter, 1);
+    if (k < ec.em.cap) {
+        ec.em.pairs[2 * k] = a < b ? a : b;
+        ec.em.pairs[2 * k + 1] = a < b ? b : a;
+    }
+}
+
 // Scalar FP32 pair term (fix-up path only); returns fs with F_i += fs*d, F_j -= fs*d.
 __device__ __forceinline__ float pair_term_f32(const float r2, const float qi, const float si,
                                                const float ei, const float qj, const float2 pj,
@@ -130,11 +141,12 @@ __device__ __forceinline__ float pair_term_f32(const float r2, const float qi, c
 // One tile step of the hot loop: i-atoms (ci, ti) and (ci, ti+4) against the lane's j atom.
 //   dE/dr * r  and energy (OpenMM 7.3 ReferenceLJCoulombIxn, reaction field, LJ not shifted):
 //   e_lj = elj*(sr6 - 1) = a - elj,   elj*(12*sr6 - 6) = 6*(a + e_lj)   with a = elj*sr6
-template <bool MASKED, bool EXACT>
+template <bool MASKED, bool EXACT, bool EMIT>
 __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const float4 xj,
                                           const float2 pj, const bool allow_lo, const bool allow_hi,
                                           const PairConsts& K, Acc2& fi, Acc2& fj, f2& en, int& cnt,
-                                          float& tmin) {
+                                          float& tmin, const EmitCtx* ec, const int islot_lo,
+                                          const int jslot) {
     const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(&ip->x);
     const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(&ip->z);
     const ulonglong2 a2 = *reinterpret_cast<const ulonglong2*>(&ip->s);
@@ -147,6 +159,10 @@ __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const fl
     const bool in_lo = MASKED ? (allow_lo && t_lo <= 0.f) : (t_lo <= 0.f);
     const bool in_hi = MASKED ? (allow_hi && t_hi <= 0.f) : (t_hi <= 0.f);
     if (EXACT) tmin = fminf(tmin, fminf(fabsf(t_lo), fabsf(t_hi)));
+    if (EMIT) {   // pairs inside the band are recorded by the fix-up path, which re-decides them
+        if (in_lo && !(EXACT && fabsf(t_lo) < K.band)) emit_pair(*ec, islot_lo, jslot);
+        if (in_hi && !(EXACT && fabsf(t_hi) < K.band)) emit_pair(*ec, islot_lo + 4, jslot);
+    }
     const f2 rinv = pk(rsqrt_approx(lo(r2)), rsqrt_approx(hi(r2)));
     const f2 rinv2 = mul2(rinv, rinv);
     const f2 sig = add2(a2.x, bc(pj.x));
@@ -189,12 +205,13 @@ __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const fl
 // in-cutoff test of the oracle; where that differs from the FP32 decision of the hot loop the
 // pair's force/energy/count is added or taken back (forces straight to the fixed-point
 // accumulators of both atoms).  Out of line so that the hot loop stays small.
+template <bool EMIT>
 __device__ __noinline__ void fix_band_pairs(const Topology& T, const PairListView& V,
                                             const double* __restrict__ pos_all,
                                             long long* __restrict__ f1acc, const IPair* s_ip,
                                             int ibase, int jslot, float4 xj, float2 pj,
                                             uint32_t imask, uint32_t midx, int lane, float* en,
-                                            int* cnt) {
+                                            int* cnt, const EmitCtx* ec) {
     const int ti = lane & 3;
     const size_t plane = (size_t)V.nslot_cap;
     const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
@@ -217,6 +234,7 @@ __device__ __noinline__ void fix_band_pairs(const Topology& T, const PairListVie
             const int r = ai / T.n;
             const bool in64 = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
             const bool in32 = t <= 0.f;
+            if (EMIT && in64) emit_pair(*ec, islot, jslot);
             if (in64 == in32) continue;
             const float sgn = in64 ? 1.f : -1.f;
             float e;
@@ -233,12 +251,13 @@ __device__ __noinline__ void fix_band_pairs(const Topology& T, const PairListVie
     }
 }
 
-template <bool MASKED, bool EXACT>
+template <bool MASKED, bool EXACT, bool EMIT>
 __device__ __forceinline__ void entry_tiles(const uint32_t imask, const uint32_t* __restrict__ mw,
                                             const int lane, const IPair* s_ip, const float4 xj,
                                             const float2 pj, const PairConsts& K,
                                             Acc2 (&fi)[nbl::kMaxCi], Acc2& fj, f2& en, int& cnt,
-                                            float& tmin) {
+                                            float& tmin, const EmitCtx* ec, const int ibase,
+                                            const int jslot) {
     const int ti = lane & 3;
     uint32_t w[nbl::kMaskWords];
     if (MASKED) {
@@ -253,21 +272,29 @@ __device__ __forceinline__ void entry_tiles(const uint32_t imask, const uint32_t
         if (imask & (1u << ci)) {
             const bool allow_lo = MASKED ? ((w[2 * ci] >> lane) & 1u) != 0u : true;
             const bool allow_hi = MASKED ? ((w[2 * ci + 1] >> lane) & 1u) != 0u : true;
-            tile_step<MASKED, EXACT>(s_ip + ci * 4 + ti, xj, pj, allow_lo, allow_hi, K, fi[ci], fj, en,
-                                     cnt, tmin);
+            tile_step<MASKED, EXACT, EMIT>(s_ip + ci * 4 + ti, xj, pj, allow_lo, allow_hi, K, fi[ci], fj,
+                                           en, cnt, tmin, ec, ibase + ci * nbl::kClusterSize + ti, jslot);
         }
     }
 }
 
+// add v = f * scale (fixed point) to *p unless f == 0: one predicated RED, no branch
+__device__ __forceinline__ void red_fixed_nonzero(long long* p, const float f, const float scale) {
+    const long long v = __float2ll_rn(f * scale);
+    asm volatile("{\n .reg .pred p;\n setp.neu.f32 p, %2, 0f00000000;\n @p red.global.add.u64 [%0], %1;\n}"
+                 :: "l"(p), "l"(v), "f"(f) : "memory");
+}
+
 // One work unit (see the header comment).  s_ip: this warp's staging area, s_shift: the block's
 // table of periodic shift vectors.
-template <bool PERIODIC, bool EXACT>
+template <bool PERIODIC, bool EXACT, bool EMIT>
 __device__ __forceinline__ void process_unit(const Topology& T, const PairListView& V,
                                              const double* __restrict__ pos_all,
                                              long long* __restrict__ f1acc, double* __restrict__ epart,
                                              long long* __restrict__ cpart, const int unit,
                                              const int lane, IPair* s_ip, const float4* s_shift,
-                                             float4* s_jx, float2* s_jp, uint32_t* s_mask) {
+                                             float4* s_jx, float2* s_jp, uint32_t* s_mask,
+                                             const EmitCtx* ec) {
     const Unit u = V.units[unit];
     const nbl::SciDesc sd = V.sci[u.sci];
     const int ibase = sd.c0 * nbl::kClusterSize;
@@ -301,7 +328,6 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
     }
     __syncwarp();
 
-#if SDM_PAIR_JSMEM && SDM_PAIR_MASKSMEM
     // exclusion-mask sets of the unit's masked entries (about one entry in ten): lane k fetches the
     // 16 words of entry k now, so the entry loop reads them from shared memory instead of waiting
     // for four dependent global loads right before the first tile of the entry
@@ -311,8 +337,6 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
 #pragma unroll
         for (int q = 0; q < nbl::kMaskWords / 4; q++) dst[q] = src[q];
     }
-#endif
-#if SDM_PAIR_JSMEM
     // stage the j-clusters of the whole unit (<= 32 entries x 8 atoms), already shifted to their
     // periodic image: eight independent loads per lane are in flight at once, and the entry loop
     // below reads its j atom with two LDS instead of two dependent global loads + a shift
@@ -334,7 +358,6 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
         }
     }
     __syncwarp();
-#endif
     Acc2 fi[nbl::kMaxCi];
 #pragma unroll
     for (int ci = 0; ci < nbl::kMaxCi; ci++) fi[ci] = Acc2{0ull, 0ull, 0ull};
@@ -342,56 +365,26 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
     int cnt = 0;
     uint32_t fixmask = 0u;
     const size_t plane = (size_t)V.nslot_cap;
-    long long* const facc_j = f1acc + (size_t)(ti < 3 ? ti : 2) * plane;   // lane ti adds component ti
+    // lane ti adds component ti of the j force (ti = 3 duplicates z and stays silent); a 32-bit
+    // element offset keeps the per-entry address arithmetic at one wide multiply-add
+    const uint32_t jplane = (uint32_t)(ti < 3 ? ti : 2) * (uint32_t)V.nslot_cap + (uint32_t)tj;
 
-#if SDM_PAIR_JSMEM
     for (int k = 0; k < nent; k++) {
         // uniform (REDUX) copy of the entry word: branches on imask need no reconvergence
         const uint32_t ey = __reduce_or_sync(0xffffffffu, __shfl_sync(0xffffffffu, my_ent.y, k));
         const uint32_t imask = ey & 0xffu;
         const uint32_t midx = ey >> 8;
-        const int jslot_k = (int)(__shfl_sync(0xffffffffu, my_ent.x, k) & 0x3ffffffu) * nbl::kJGroup + tj;
+        const uint32_t jcl8 = (__shfl_sync(0xffffffffu, my_ent.x, k) & 0x3ffffffu) * nbl::kJGroup;
         const float4 xj = s_jx[k * nbl::kJGroup + tj];
         const float2 pj = s_jp[k * nbl::kJGroup + tj];
-#else
-    // software pipeline: j data of the next entry is in flight while this entry is computed
-    uint32_t ex = __shfl_sync(0xffffffffu, my_ent.x, 0);
-    int jslot = (int)(ex & 0x3ffffffu) * nbl::kJGroup + tj;
-    float4 xj_n = V.posq[jslot];
-    float2 pj_n = V.par[jslot];
-
-    for (int k = 0; k < nent; k++) {
-        // uniform (REDUX) copy of the entry word: branches on imask need no reconvergence
-        const uint32_t ey = __reduce_or_sync(0xffffffffu, __shfl_sync(0xffffffffu, my_ent.y, k));
-        const uint32_t code = ex >> 26;
-        const uint32_t imask = ey & 0xffu;
-        const uint32_t midx = ey >> 8;
-        const int jslot_k = jslot;
-        float4 xj = xj_n;
-        const float2 pj = pj_n;
-        if (k + 1 < nent) {
-            ex = __shfl_sync(0xffffffffu, my_ent.x, k + 1);
-            jslot = (int)(ex & 0x3ffffffu) * nbl::kJGroup + tj;
-            xj_n = V.posq[jslot];
-            pj_n = V.par[jslot];
-        }
-        if (PERIODIC) {
-            const float4 sh = s_shift[code];
-            xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
-        }
-#endif
         Acc2 fj{0ull, 0ull, 0ull};
         float tmin = 3.0e38f;
         if (midx == 0)
-            entry_tiles<false, EXACT>(imask, nullptr, lane, s_ip, xj, pj, K, fi, fj, en, cnt, tmin);
+            entry_tiles<false, EXACT, EMIT>(imask, nullptr, lane, s_ip, xj, pj, K, fi, fj, en, cnt, tmin, ec,
+                                            ibase, (int)jcl8 + tj);
         else
-#if SDM_PAIR_JSMEM && SDM_PAIR_MASKSMEM
-            entry_tiles<true, EXACT>(imask, s_mask + k * nbl::kMaskWords, lane, s_ip, xj, pj, K,
-                                     fi, fj, en, cnt, tmin);
-#else
-            entry_tiles<true, EXACT>(imask, V.masks + (size_t)midx * nbl::kMaskWords, lane, s_ip, xj, pj, K,
-                                     fi, fj, en, cnt, tmin);
-#endif
+            entry_tiles<true, EXACT, EMIT>(imask, s_mask + k * nbl::kMaskWords, lane, s_ip, xj, pj, K,
+                                           fi, fj, en, cnt, tmin, ec, ibase, (int)jcl8 + tj);
         if (EXACT) {
             // entries with a pair inside the band are revisited after the loop (keeps the call
             // and its register pressure out of the hot loop); per-lane bits, OR-reduced once
@@ -411,11 +404,7 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
             float v = up ? z : keep;
             v += __shfl_xor_sync(0xffffffffu, send2, 2);
             // lane ti: 0 -> X, 1 -> Y, 2 -> Z, 3 -> Z (duplicate, not written); sign: F_j = -sum
-#if SDM_PAIR_JRED_ALWAYS
-            if (ti < 3) atomic_add_fixed(facc_j + jslot_k, __float2ll_rn(-v * kFix));
-#else
-            if (ti < 3 && v != 0.f) atomic_add_fixed(facc_j + jslot_k, __float2ll_rn(-v * kFix));
-#endif
+            red_fixed_nonzero(f1acc + (jplane + jcl8), ti < 3 ? v : 0.f, -kFix);
         }
     }
 
@@ -450,10 +439,7 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
             for (int h = 0; h < 2; h++) {
                 const int islot = ibase + tj * nbl::kClusterSize + ti + 4 * h;
 #pragma unroll
-                for (int d = 0; d < 3; d++) {
-                    const float f = c[3 * h + d];
-                    if (f != 0.f) atomic_add_fixed(f1acc + (size_t)d * plane + islot, __float2ll_rn(f * kFix));
-                }
+                for (int d = 0; d < 3; d++) red_fixed_nonzero(f1acc + (size_t)d * plane + islot, c[3 * h + d], kFix);
             }
         }
     }
@@ -474,8 +460,8 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
                 const float4 sh = s_shift[fx >> 26];
                 xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
             }
-            fix_band_pairs(T, V, pos_all, f1acc, s_ip, ibase, js, xj, V.par[js], fy & 0xffu, fy >> 8, lane,
-                           &en_fix, &cnt_fix);
+            fix_band_pairs<EMIT>(T, V, pos_all, f1acc, s_ip, ibase, js, xj, V.par[js], fy & 0xffu, fy >> 8,
+                                 lane, &en_fix, &cnt_fix, ec);
         }
         en1 += en_fix;
         cnt += cnt_fix;
@@ -501,8 +487,8 @@ __device__ __forceinline__ void process_unit(const Topology& T, const PairListVi
 // length (1..32 entries), so handing them out dynamically keeps all resident warps busy to the
 // end, and the shift table is built once per block instead of once per unit.  Which warp
 // computes which unit does not influence the result (fixed-point accumulation, per-unit energy
-// partials).
-template <bool PERIODIC, bool EXACT>
+// partials).  EMIT selects the debug build that also records the accepted pairs (sdm_get_pairs).
+template <bool PERIODIC, bool EXACT, bool EMIT>
 #ifdef SDM_PAIR_MAXNREG   /* development knob: cap the registers directly instead of via min blocks */
 __global__ void __maxnreg__(SDM_PAIR_MAXNREG)
 #else
@@ -510,16 +496,13 @@ __global__ void __launch_bounds__(kWarps * 32, SDM_PAIR_MINB)
 #endif
 pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
                     const double* __restrict__ pos_all, long long* __restrict__ f1acc,
-                    double* __restrict__ epart, long long* __restrict__ cpart, int* unit_counter) {
+                    double* __restrict__ epart, long long* __restrict__ cpart, int* unit_counter,
+                    const __grid_constant__ PairEmit em) {
     __shared__ IPair s_ip[kWarps][kIRows];
     __shared__ float4 s_shift[64];
-#if SDM_PAIR_JSMEM
     __shared__ float4 s_jx[kWarps][32 * nbl::kJGroup];
     __shared__ float2 s_jp[kWarps][32 * nbl::kJGroup];
-#if SDM_PAIR_MASKSMEM
     __shared__ __align__(16) uint32_t s_mask[kWarps][32 * nbl::kMaskWords];
-#endif
-#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (PERIODIC) {
         for (uint32_t code = threadIdx.x; code < 64; code += kWarps * 32)
@@ -528,418 +511,21 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
                                         (float)nbl::shift_z(code) * T.boxf[2], 0.f);
         __syncthreads();
     }
+    EmitCtx ec_store;
+    const EmitCtx* ec = nullptr;
+    if (EMIT) {
+        ec_store.em = em;
+        ec_store.atom = V.atom;
+        ec_store.n = T.n;
+        ec = &ec_store;
+    }
     for (;;) {
         int unit = 0;
         if (lane == 0) unit = atomicAdd(unit_counter, 1);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= V.nunits) break;
-#if SDM_PAIR_JSMEM
-#if SDM_PAIR_MASKSMEM
-        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
-                                      s_jx[warp], s_jp[warp], s_mask[warp]);
-#else
-        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
-                                      s_jx[warp], s_jp[warp], nullptr);
-#endif
-#else
-        process_unit<PERIODIC, EXACT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
-                                      nullptr, nullptr, nullptr);
-#endif
-    }
-}
-
-// =============================================================================================
-// Tile-list kernel (pair_tile_kernel): the same 8 x 8 tiles and the same FP32 arithmetic, but the
-// warp owns ONE i-cluster whose eight atoms stay in registers, and walks that cluster's own tile
-// list (built from the entries by tile_fill_kernel in pairlist.cu) two tiles at a time:
-//   lane = (half, tj, ti) = (lane>>4, (lane>>1)&7, lane&1); half-warp `half` works on tile
-//   2s+half of step s, its lane holds j-atom tj and evaluates the FOUR i-atoms ti, ti+2, ti+4,
-//   ti+6 as two independent packed chains A = (ti, ti+4), B = (ti+2, ti+6)  (ILP 2).
-// Compared with pair_cluster_kernel: no shared-memory loads, no imask branches / REDUX, 12
-// instead of 48 i-force accumulator registers (more resident warps), a hot loop of ~2 KB instead
-// of ~15 KB, and the j force is reduced over only two lanes (one SHFL level) per tile.  The price
-// is one j load and one j reduction per tile instead of per entry.
-// The FP32 r^2 expression, the band rule and the FP64 re-test are the ones of pair_cluster_kernel,
-// so the in-cutoff pair set is identical (pair_emit_kernel serves both).
-// =============================================================================================
-struct IAtoms {     // two i-atoms (a, a+4) of the warp's cluster, packed (lo, hi)
-    f2 x, y, z, q, s, e;
-};
-
-template <bool MASKED, bool EXACT>
-__device__ __forceinline__ void tile_chain(const IAtoms& I, const float4 xj, const float2 pj,
-                                           const bool allow_lo, const bool allow_hi, const PairConsts& K,
-                                           Acc2& fi, Acc2& fj, f2& en, int& cnt, float& tmin) {
-    const f2 dx = sub2(I.x, bc(xj.x));
-    const f2 dy = sub2(I.y, bc(xj.y));
-    const f2 dz = sub2(I.z, bc(xj.z));
-    const f2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-    const f2 t = sub2(r2, bc(K.rc2));
-    const float t_lo = lo(t), t_hi = hi(t);
-    const bool in_lo = MASKED ? (allow_lo && t_lo <= 0.f) : (t_lo <= 0.f);
-    const bool in_hi = MASKED ? (allow_hi && t_hi <= 0.f) : (t_hi <= 0.f);
-    if (EXACT) tmin = fminf(tmin, fminf(fabsf(t_lo), fabsf(t_hi)));
-    const f2 rinv = pk(rsqrt_approx(lo(r2)), rsqrt_approx(hi(r2)));
-    const f2 rinv2 = mul2(rinv, rinv);
-    const f2 sig = add2(I.s, bc(pj.x));
-    const f2 sr2 = mul2(mul2(sig, sig), rinv2);
-    const f2 sr6 = mul2(mul2(sr2, sr2), sr2);
-    const f2 elj = mul2(mul2(I.e, bc(pj.y)), sr6);
-    const f2 qq = mul2(I.q, bc(xj.w));
-    const f2 kr2 = mul2(r2, bc(K.krf));
-    const f2 a = mul2(elj, sr6);
-    const f2 e_lj = sub2(a, elj);
-    const f2 dEdR = fma2(add2(a, e_lj), bc(6.f), mul2(qq, fma2(kr2, bc(-2.f), rinv)));
-    const f2 e = fma2(qq, sub2(add2(rinv, kr2), bc(K.crf)), e_lj);
-    const f2 fsr = mul2(dEdR, rinv2);
-    const f2 fs = pk(in_lo ? lo(fsr) : 0.f, in_hi ? hi(fsr) : 0.f);
-    en = add2(en, pk(in_lo ? lo(e) : 0.f, in_hi ? hi(e) : 0.f));
-    asm("{\n .reg .pred p;\n setp.ne.s32 p, %1, 0;\n @p add.s32 %0, %0, 1;\n}" : "+r"(cnt) : "r"((int)in_lo));
-    asm("{\n .reg .pred p;\n setp.ne.s32 p, %1, 0;\n @p add.s32 %0, %0, 1;\n}" : "+r"(cnt) : "r"((int)in_hi));
-    fi.x = fma2(fs, dx, fi.x); fi.y = fma2(fs, dy, fi.y); fi.z = fma2(fs, dz, fi.z);
-    fj.x = fma2(fs, dx, fj.x); fj.y = fma2(fs, dy, fj.y); fj.z = fma2(fs, dz, fj.z);
-}
-
-constexpr uint32_t kTileDummyCode = 63u;   // shift code of a padding record (3,3,3 is no valid shift)
-
-// Rare path of the tile-list kernel: the steps (two tiles each) that saw a pair inside the FP32
-// uncertainty band are walked once more, straight from global memory, and the FP64 decision is
-// applied like in fix_band_pairs above.
-__device__ __noinline__ void fix_band_unit(const Topology& T, const PairListView& V, const TileListView& TL,
-                                           const double* __restrict__ pos_all,
-                                           long long* __restrict__ f1acc, const TileUnit u, const int lane,
-                                           uint32_t stepmask, float* en, int* cnt) {
-    const int half = lane >> 4, tj = (lane >> 1) & 7, ti = lane & 1;
-    const size_t plane = (size_t)V.nslot_cap;
-    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
-    const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
-    while (stepmask) {
-        const int s2 = 2 * (__ffs(stepmask) - 1);
-        stepmask &= stepmask - 1u;
-        const uint2 rec = TL.recs[(size_t)u.begin + s2 + half];
-        const uint32_t code = rec.x >> 26;
-        if (code == kTileDummyCode) continue;
-        const int jslot = (int)(rec.x & 0x3ffffffu) * nbl::kJGroup + tj;
-        float4 xj = V.posq[jslot];
-        const float2 pj = V.par[jslot];
-        if (periodic) {
-            xj.x += (float)nbl::shift_x(code) * T.boxf[0];
-            xj.y += (float)nbl::shift_y(code) * T.boxf[1];
-            xj.z += (float)nbl::shift_z(code) * T.boxf[2];
-        }
-        const uint32_t w[2] = {V.masks[rec.y], V.masks[rec.y + 1]};
-        for (int m = 0; m < 4; m++) {
-            const int a = ti + 2 * m;
-            if (!((w[a >> 2] >> (tj * 4 + (a & 3))) & 1u)) continue;
-            const int islot = u.islot + a;
-            const float4 xi = V.posq[islot];
-            const float2 pi = V.par[islot];
-            float dx, dy, dz;
-            const float r2 = pair_r2(xi.x, xi.y, xi.z, xj, dx, dy, dz);
-            const float t = r2 - K.rc2;
-            if (!(fabsf(t) < K.band)) continue;
-            const int ai = V.atom[islot], aj = V.atom[jslot];
-            if (ai < 0 || aj < 0) continue;
-            const int r = ai / T.n;
-            const bool in64 = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
-            const bool in32 = t <= 0.f;
-            if (in64 == in32) continue;
-            const float sgn = in64 ? 1.f : -1.f;
-            float e;
-            const float fs = sgn * pair_term_f32(r2, xi.w, pi.x, pi.y, xj.w, pj, K, e);
-            *en += sgn * e;
-            *cnt += in64 ? 1 : -1;
-            const float f[3] = {fs * dx, fs * dy, fs * dz};
-            for (int c = 0; c < 3; c++) {
-                const long long v = __float2ll_rn(f[c] * kFix);
-                atomic_add_fixed(f1acc + (size_t)c * plane + islot, v);
-                atomic_add_fixed(f1acc + (size_t)c * plane + jslot, -v);
-            }
-        }
-    }
-}
-
-// add v (fixed point of f * scale) to *p unless f == 0: one predicated RED, no branch
-__device__ __forceinline__ void red_fixed_nonzero(long long* p, const float f, const float scale) {
-    const long long v = __float2ll_rn(f * scale);
-    asm volatile("{\n .reg .pred p;\n setp.neu.f32 p, %2, 0f00000000;\n @p red.global.add.u64 [%0], %1;\n}"
-                 :: "l"(p), "l"(v), "f"(f) : "memory");
-}
-
-struct JBuf {       // one step's j side: record word, slot, coordinates/charge, LJ parameters
-    uint32_t ex;
-    int jslot;
-    float4 xj;
-    float2 pj;
-};
-
-template <bool PERIODIC, bool EXACT>
-__device__ __forceinline__ void process_tile_unit(const Topology& T, const PairListView& V,
-                                                  const TileListView& TL,
-                                                  const double* __restrict__ pos_all,
-                                                  long long* __restrict__ f1acc,
-                                                  double* __restrict__ epart, long long* __restrict__ cpart,
-                                                  const int unit, const int lane, IPair* s_ip,
-                                                  const float4* s_shift) {
-    const TileUnit u = TL.units[unit];
-    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
-    const int half = lane >> 4, tj = (lane >> 1) & 7, ti = lane & 1;
-    const size_t plane = (size_t)V.nslot_cap;
-    // loop bounds through REDUX: uniform registers, so the loops below need no divergence handling
-    const int nrec = (int)__reduce_or_sync(0xffffffffu, (unsigned)u.nrec);
-    const int nmask = (int)__reduce_or_sync(0xffffffffu, (unsigned)u.nmask);
-
-    // the warp's i-cluster: lanes 0..3 pack atoms (a, a+4) through shared memory so that every
-    // lane gets them back as 64-bit register pairs; chains A = (ti, ti+4), B = (ti+2, ti+6)
-    if (lane < 4) {
-        float4 p[2];
-        float2 pr[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int sl = u.islot + lane + 4 * h;
-            const float4 q = V.posq[sl];
-            p[h] = make_float4(-nbl::kFar, -nbl::kFar, -nbl::kFar, 0.f);
-            pr[h] = make_float2(0.f, 0.f);
-            if (q.x < 0.5f * nbl::kFar) { p[h] = q; pr[h] = V.par[sl]; }
-        }
-        IPair ip;
-        ip.x = pk(p[0].x, p[1].x); ip.y = pk(p[0].y, p[1].y);
-        ip.z = pk(p[0].z, p[1].z); ip.q = pk(p[0].w, p[1].w);
-        ip.s = pk(pr[0].x, pr[1].x); ip.e = pk(pr[0].y, pr[1].y);
-        s_ip[lane] = ip;
-    }
-    __syncwarp();
-    IAtoms IA, IB;
-    {
-        const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti].x);
-        const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti].z);
-        const ulonglong2 a2 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti].s);
-        IA.x = a0.x; IA.y = a0.y; IA.z = a1.x; IA.q = a1.y; IA.s = a2.x; IA.e = a2.y;
-        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti + 2].x);
-        const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti + 2].z);
-        const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(&s_ip[ti + 2].s);
-        IB.x = b0.x; IB.y = b0.y; IB.z = b1.x; IB.q = b1.y; IB.s = b2.x; IB.e = b2.y;
-    }
-    __syncwarp();   // the staging area is reused by the next unit of this warp
-
-    Acc2 fA{0ull, 0ull, 0ull}, fB{0ull, 0ull, 0ull};
-    f2 en = 0ull;
-    int cnt = 0;
-    uint32_t fixmask = 0u;   // bit s: step s of this unit (<= 32 steps) saw a pair inside the band
-    uint32_t stepbit = 1u;
-    long long* const facc_xy = f1acc + (size_t)ti * plane;   // lane ti adds component ti (x or y)
-    long long* const facc_z = f1acc + 2 * plane;             // ... and lane ti = 0 also z
-    const int bitA = tj * 4 + ti, bitB = bitA + 2;
-
-    for (int b0 = 0; b0 < nrec; b0 += 32) {
-        const int nb = min(32, nrec - b0);              // records of this batch (even)
-        const int nm = max(0, min(nb, nmask - b0));     // of which masked (even, they come first)
-        uint2 my = make_uint2(kTileDummyCode << 26, 0u);
-        if (lane < nb) my = TL.recs[(size_t)u.begin + b0 + lane];
-
-        auto fetch = [&](JBuf& J, const int s2) {
-            J.ex = __shfl_sync(0xffffffffu, my.x, s2 + half);
-            J.jslot = (int)(J.ex & 0x3ffffffu) * nbl::kJGroup + tj;
-            J.xj = V.posq[J.jslot];
-            J.pj = V.par[J.jslot];
-        };
-        auto compute = [&](const JBuf& J, const int s2, auto masked_tag) {
-            constexpr bool MASKED = decltype(masked_tag)::value;
-            const uint32_t code = J.ex >> 26;
-            float4 xj = J.xj;
-            uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
-            if (MASKED) {
-                const uint32_t ey = __shfl_sync(0xffffffffu, my.y, s2 + half);
-                w0 = V.masks[ey];          // unmasked and padding records point at mask set 0 (all ones)
-                w1 = V.masks[ey + 1];
-            }
-            if (PERIODIC) {
-                const float4 sh = s_shift[code];    // entry 63 moves a padding record out of range
-                xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
-            } else {
-                xj.x += code == kTileDummyCode ? 4.f * nbl::kFar : 0.f;
-            }
-            Acc2 fj{0ull, 0ull, 0ull};
-            float tmin = 3.0e38f;
-            tile_chain<MASKED, EXACT>(IA, xj, J.pj, (w0 >> bitA) & 1u, (w1 >> bitA) & 1u, K, fA, fj, en, cnt, tmin);
-            tile_chain<MASKED, EXACT>(IB, xj, J.pj, (w0 >> bitB) & 1u, (w1 >> bitB) & 1u, K, fB, fj, en, cnt, tmin);
-            if (EXACT) {
-                if (tmin < K.band) fixmask |= stepbit;
-                stepbit <<= 1;
-            }
-            // j force: halves added, then exchanged between the two ti lanes: ti = 0 ends up with
-            // X and Z, ti = 1 with Y (sign: F_j = -sum)
-            const float jx = lo(fj.x) + hi(fj.x), jy = lo(fj.y) + hi(fj.y), jz = lo(fj.z) + hi(fj.z);
-            const float send = ti ? jx : jy;
-            float keep = ti ? jy : jx;
-            keep += __shfl_xor_sync(0xffffffffu, send, 1);
-            const float z = jz + __shfl_xor_sync(0xffffffffu, jz, 1);
-            red_fixed_nonzero(facc_xy + J.jslot, keep, -kFix);
-            red_fixed_nonzero(facc_z + J.jslot, ti ? 0.f : z, -kFix);
-        };
-        // two steps per trip with ping-pong buffers: the j data of the next step is in flight
-        // while this one is computed and no register rotation is needed.  A trip that straddles
-        // the masked/unmasked boundary runs the masked code for both of its steps.
-        JBuf Ja, Jb;
-        fetch(Ja, 0);
-        int s2 = 0;
-        for (; s2 < nm; s2 += 4) {
-            if (s2 + 2 < nb) fetch(Jb, s2 + 2);
-            compute(Ja, s2, std::true_type{});
-            if (s2 + 2 < nb) {
-                if (s2 + 4 < nb) fetch(Ja, s2 + 4);
-                compute(Jb, s2 + 2, std::true_type{});
-            }
-        }
-        for (; s2 < nb; s2 += 4) {
-            if (s2 + 2 < nb) fetch(Jb, s2 + 2);
-            compute(Ja, s2, std::false_type{});
-            if (s2 + 2 < nb) {
-                if (s2 + 4 < nb) fetch(Ja, s2 + 4);
-                compute(Jb, s2 + 2, std::false_type{});
-            }
-        }
-    }
-
-    // i forces: 12 partial sums per lane (4 atoms x 3), reduced over the 16 (half, tj) lanes.
-    // xor 16 and xor 8 halve the value count (transpose-reduction), xor 4 and xor 2 are plain
-    // butterflies; afterwards lane (b4, b3, *, *, ti) holds the force of atom ti + 2*(2*b4 + b3).
-    {
-        const float v[12] = {lo(fA.x), lo(fA.y), lo(fA.z), lo(fB.x), lo(fB.y), lo(fB.z),
-                             hi(fA.x), hi(fA.y), hi(fA.z), hi(fB.x), hi(fB.y), hi(fB.z)};   // m = 0,1,2,3
-        const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
-        float a[6], b[3];
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const float send = b4 ? v[k] : v[k + 6];
-            a[k] = (b4 ? v[k + 6] : v[k]) + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float send = b3 ? a[k] : a[k + 3];
-            b[k] = (b3 ? a[k + 3] : a[k]) + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            b[k] += __shfl_xor_sync(0xffffffffu, b[k], 4);
-            b[k] += __shfl_xor_sync(0xffffffffu, b[k], 2);
-        }
-        const int m = (b4 ? 2 : 0) + (b3 ? 1 : 0);
-        const int d = (lane >> 1) & 3;   // the four duplicate lanes write one component each
-        const float f = d == 0 ? b[0] : (d == 1 ? b[1] : b[2]);
-        if (d < 3 && f != 0.f)
-            atomic_add_fixed(f1acc + (size_t)d * plane + u.islot + ti + 2 * m, __float2ll_rn(f * kFix));
-    }
-
-    float en1 = lo(en) + hi(en);
-    if (EXACT) fixmask = __reduce_or_sync(0xffffffffu, fixmask);
-    if (EXACT && fixmask) {
-        float en_fix = 0.f;   // separate variables: their address is taken by the call
-        int cnt_fix = 0;
-        fix_band_unit(T, V, TL, pos_all, f1acc, u, lane, fixmask, &en_fix, &cnt_fix);
-        en1 += en_fix;
-        cnt += cnt_fix;
-    }
-    double de = (double)en1;
-    int dc = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        de += __shfl_down_sync(0xffffffffu, de, o);
-        dc += __shfl_down_sync(0xffffffffu, dc, o);
-    }
-    if (lane == 0) {
-        epart[unit] = de;
-        cpart[unit] = dc;
-    }
-}
-
-#ifndef SDM_TILE_MINB
-#define SDM_TILE_MINB 16
-#endif
-
-template <bool PERIODIC, bool EXACT>
-__global__ void __launch_bounds__(32, SDM_TILE_MINB)
-pair_tile_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
-                 const __grid_constant__ TileListView TL, const double* __restrict__ pos_all,
-                 long long* __restrict__ f1acc, double* __restrict__ epart,
-                 long long* __restrict__ cpart, int* unit_counter) {
-    __shared__ float4 s_shift[64];
-    __shared__ IPair s_ip[4];
-    const int lane = threadIdx.x;
-    if (PERIODIC) {
-        for (uint32_t code = lane; code < 64; code += 32)
-            s_shift[code] = code == kTileDummyCode
-                                ? make_float4(4.f * nbl::kFar, 0.f, 0.f, 0.f)
-                                : make_float4((float)nbl::shift_x(code) * T.boxf[0],
-                                              (float)nbl::shift_y(code) * T.boxf[1],
-                                              (float)nbl::shift_z(code) * T.boxf[2], 0.f);
-        __syncwarp();
-    }
-    for (;;) {
-        unsigned mine = 0u;
-        if (lane == 0) mine = (unsigned)atomicAdd(unit_counter, 1);
-        const int unit = (int)__reduce_or_sync(0xffffffffu, mine);   // lane 0's value, in a uniform register
-        if (unit >= TL.nunits) break;
-        process_tile_unit<PERIODIC, EXACT>(T, V, TL, pos_all, f1acc, epart, cpart, unit, lane, s_ip, s_shift);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Debug / parity pass: records the (i<j) System indices of every pair the pair kernel counts as
-// in-cutoff for one replica -- the same FP32 r^2, the same band rule, the same FP64 re-test.
-// Slow by design (one atomic per pair); never on the product path.
-// ---------------------------------------------------------------------------------------------
-template <bool PERIODIC>
-__global__ void __launch_bounds__(kWarps * 32)
-pair_emit_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
-                 const double* __restrict__ pos_all, int exact, int* emit_counter, int* emit_pairs,
-                 int emit_cap, int emit_replica) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int unit = blockIdx.x * kWarps + warp;
-    if (unit >= V.nunits) return;
-    const Unit u = V.units[unit];
-    const nbl::SciDesc sd = V.sci[u.sci];
-    if (sd.replica != emit_replica) return;
-    const int ibase = sd.c0 * nbl::kClusterSize;
-    const int ti = lane & 3, tj = lane >> 2;
-    for (int e = u.begin; e < u.end; e++) {
-        const uint2 ent = V.entries[e];
-        const uint32_t code = ent.x >> 26, imask = ent.y & 0xffu, midx = ent.y >> 8;
-        const int jslot = (int)(ent.x & 0x3ffffffu) * nbl::kJGroup + tj;
-        float4 xj = V.posq[jslot];
-        if (PERIODIC) {
-            // same values and the same single rounding as the s_shift table of the pair kernel
-            xj.x += (float)nbl::shift_x(code) * T.boxf[0];
-            xj.y += (float)nbl::shift_y(code) * T.boxf[1];
-            xj.z += (float)nbl::shift_z(code) * T.boxf[2];
-        }
-        const int aj = V.atom[jslot];
-        for (int ci = 0; ci < sd.nci; ci++) {
-            if (!((imask >> ci) & 1u)) continue;
-            for (int h = 0; h < 2; h++) {
-                const uint32_t w = midx ? V.masks[(size_t)midx * nbl::kMaskWords + 2 * ci + h] : 0xffffffffu;
-                if (!((w >> lane) & 1u)) continue;
-                const int islot = ibase + ci * nbl::kClusterSize + ti + 4 * h;
-                const int ai = V.atom[islot];
-                if (ai < 0 || aj < 0) continue;
-                const float4 xi = V.posq[islot];
-                float dx, dy, dz;
-                const float r2 = pair_r2(xi.x, xi.y, xi.z, xj, dx, dy, dz);
-                const float t = r2 - T.rc2f;
-                bool in = t <= 0.f;
-                if (exact && fabsf(t) < T.band) {
-                    const int r = ai / T.n;
-                    in = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
-                }
-                if (!in) continue;
-                const int a = ai % T.n, b = aj % T.n;
-                const int slot = atomicAdd(emit_counter, 1);
-                if (slot < emit_cap) {
-                    emit_pairs[2 * slot] = a < b ? a : b;
-                    emit_pairs[2 * slot + 1] = a < b ? b : a;
-                }
-            }
-        }
+        process_unit<PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp], s_shift,
+                                            s_jx[warp], s_jp[warp], s_mask[warp], ec);
     }
 }
 
@@ -978,18 +564,19 @@ refresh_kernel(Topology T, nbl::Grid G, int nslot, const double* __restrict__ po
 
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
-                         int* unit_counter, int num_sms, cudaStream_t s) {
+                         int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s) {
     if (V.nunits <= 0) return;
     cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
-#define SDM_LAUNCH(P, X)                                                                          \
+    const PairEmit em = emit ? *emit : PairEmit{nullptr, nullptr, 0, -1};
+#define SDM_LAUNCH(P, X, E)                                                                       \
     do {                                                                                          \
         static int resident = 0; /* blocks per SM the hardware keeps resident (register limited) */ \
         if (!resident) {                                                                          \
-            if (SDM_PAIR_JSMEM) /* 8.7 KB per one-warp block: ask for the large shared-memory carve-out */ \
-                cudaFuncSetAttribute(pair_cluster_kernel<P, X>, cudaFuncAttributePreferredSharedMemoryCarveout, \
-                                     cudaSharedmemCarveoutMaxShared);                             \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_cluster_kernel<P, X>,  \
+            /* 10.8 KB per one-warp block: ask for the large shared-memory carve-out */          \
+            cudaFuncSetAttribute(pair_cluster_kernel<P, X, E>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                 cudaSharedmemCarveoutMaxShared);                                 \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_cluster_kernel<P, X, E>, \
                                                               kWarps * 32, 0) != cudaSuccess ||    \
                 resident < 1)                                                                     \
                 resident = SDM_PAIR_MINB;                                                         \
@@ -997,56 +584,20 @@ void launch_pair_cluster(const Topology& T, const PairListView& V, const double*
             if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
         }                                                                                         \
         const int grid = std::min((V.nunits + kWarps - 1) / kWarps, num_sms * resident);           \
-        pair_cluster_kernel<P, X><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
-                                                              unit_counter);                      \
+        pair_cluster_kernel<P, X, E><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
+                                                                 unit_counter, em);               \
     } while (0)
-    if (exact) {
-        if (periodic) SDM_LAUNCH(true, true);
-        else SDM_LAUNCH(false, true);
+    if (emit) {   // debug build of the same kernel: records the accepted pairs
+        if (exact) { if (periodic) SDM_LAUNCH(true, true, true); else SDM_LAUNCH(false, true, true); }
+        else { if (periodic) SDM_LAUNCH(true, false, true); else SDM_LAUNCH(false, false, true); }
+    } else if (exact) {
+        if (periodic) SDM_LAUNCH(true, true, false);
+        else SDM_LAUNCH(false, true, false);
     } else {
-        if (periodic) SDM_LAUNCH(true, false);
-        else SDM_LAUNCH(false, false);
+        if (periodic) SDM_LAUNCH(true, false, false);
+        else SDM_LAUNCH(false, false, false);
     }
 #undef SDM_LAUNCH
-}
-
-void launch_pair_tiles(const Topology& T, const PairListView& V, const TileListView& TL,
-                       const double* pos_all, long long* f1acc, double* epart, long long* cpart,
-                       int exact, int* unit_counter, int num_sms, cudaStream_t s) {
-    if (TL.nunits <= 0) return;
-    cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
-    const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
-#define SDM_LAUNCH(P, X)                                                                          \
-    do {                                                                                          \
-        static int resident = 0; /* blocks per SM the hardware keeps resident */                  \
-        if (!resident) {                                                                          \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_tile_kernel<P, X>, 32, 0) != \
-                    cudaSuccess || resident < 1)                                                  \
-                resident = SDM_TILE_MINB;                                                         \
-            if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
-        }                                                                                         \
-        const int grid = std::min(TL.nunits, num_sms * resident);                                 \
-        pair_tile_kernel<P, X><<<grid, 32, 0, s>>>(T, V, TL, pos_all, f1acc, epart, cpart, unit_counter); \
-    } while (0)
-    if (exact) {
-        if (periodic) SDM_LAUNCH(true, true);
-        else SDM_LAUNCH(false, true);
-    } else {
-        if (periodic) SDM_LAUNCH(true, false);
-        else SDM_LAUNCH(false, false);
-    }
-#undef SDM_LAUNCH
-}
-
-void launch_pair_emit(const Topology& T, const PairListView& V, const double* pos_all, int exact,
-                      int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
-                      cudaStream_t s) {
-    if (V.nunits <= 0) return;
-    const int grid = (V.nunits + kWarps - 1) / kWarps;
-    if (T.method == SDM_CUTOFF_PERIODIC)
-        pair_emit_kernel<true><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
-    else
-        pair_emit_kernel<false><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, exact, emit_counter, emit_pairs, emit_cap, emit_replica);
 }
 
 void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,

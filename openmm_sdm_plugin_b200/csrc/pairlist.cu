@@ -55,18 +55,6 @@ struct PairList {
     int *sci_nunits = nullptr, *sci_unit_off = nullptr;
     Unit* units = nullptr;
     int* part_off = nullptr;    // [R+1]
-    // tile list of pair_tile_kernel (one record per tile, grouped by i-cluster)
-    int use_tiles = 0;          // 0: pair_cluster_kernel (product path); 1: pair_tile_kernel, the measured-slower
-                                // alternative kept for A/B runs (SDMB200_PAIR_KERNEL=tiles)
-    int tile_chunk = 64;        // records per unit (even)
-    int *t_nrec = nullptr, *t_rec_off = nullptr, *t_nunits = nullptr, *t_unit_off = nullptr;  // [8*nsci+1]
-    uint2* t_recs = nullptr;
-    TileUnit* t_units = nullptr;
-    size_t t_recs_cap = 0, t_units_cap = 0, t_idx_cap = 0;
-    int t_nrecs = 0, t_nunits_total = 0;
-    int* t_part_off = nullptr;  // [R+1]
-    double* t_epart = nullptr;
-    long long* t_cpart = nullptr;
     int* unit_counter = nullptr; // work counter of the persistent pair kernel
     double* epart = nullptr;
     long long* cpart = nullptr;
@@ -442,69 +430,6 @@ __global__ void part_off_kernel(Grid G, const int* __restrict__ cell_sci,
     part_off[r] = s < nsci ? sci_unit_off[s] : nunits;
 }
 
-// ---- tile list (pair_tile_kernel) -----------------------------------------------------------------
-// One thread per (sci, ci): walks the sci's entries in order and counts / writes the tiles of its
-// i-cluster -- first those of masked entries, then the others, each group padded to an even count
-// (the kernel takes two tiles per step).  Deterministic order, no atomics.
-__global__ void tile_count_kernel(int nsci, const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
-                                  const uint2* __restrict__ entries, int chunk, int* t_nrec, int* t_nunits) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nsci * nbl::kMaxCi) return;
-    const int s = t / nbl::kMaxCi, ci = t % nbl::kMaxCi;
-    int nm = 0, nu = 0;
-    if (ci < sci[s].nci) {
-        const int e1 = sci_off[s + 1];
-        for (int e = sci_off[s]; e < e1; e++) {
-            const uint32_t y = entries[e].y;
-            if ((y >> ci) & 1u) { if (y >> 8) nm++; else nu++; }
-        }
-    }
-    const int nrec = ((nm + 1) & ~1) + ((nu + 1) & ~1);
-    t_nrec[t] = nrec;
-    t_nunits[t] = (nrec + chunk - 1) / chunk;
-}
-
-__global__ void tile_fill_kernel(int nsci, const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
-                                 const uint2* __restrict__ entries, int chunk,
-                                 const int* __restrict__ t_rec_off, const int* __restrict__ t_unit_off,
-                                 uint2* recs, TileUnit* units) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nsci * nbl::kMaxCi) return;
-    const int s = t / nbl::kMaxCi, ci = t % nbl::kMaxCi;
-    const SciDesc sd = sci[s];
-    if (ci >= sd.nci) return;
-    const int base = t_rec_off[t], e0 = sci_off[s], e1 = sci_off[s + 1];
-    const uint2 dummy = make_uint2(63u << 26, 0u);
-    int k = 0;
-    for (int e = e0; e < e1; e++) {
-        const uint2 ent = entries[e];
-        if (((ent.y >> ci) & 1u) && (ent.y >> 8))
-            recs[base + k++] = make_uint2(ent.x, (ent.y >> 8) * nbl::kMaskWords + 2 * ci);
-    }
-    if (k & 1) recs[base + k++] = dummy;
-    const int pm = k;
-    for (int e = e0; e < e1; e++) {
-        const uint2 ent = entries[e];
-        if (((ent.y >> ci) & 1u) && !(ent.y >> 8)) recs[base + k++] = make_uint2(ent.x, 0u);
-    }
-    if (k & 1) recs[base + k++] = dummy;
-    const int nrec = k;
-    int u = t_unit_off[t];
-    for (int c0 = 0; c0 < nrec; c0 += chunk, u++) {
-        const int len = min(chunk, nrec - c0);
-        units[u] = TileUnit{(sd.c0 + ci) * nbl::kClusterSize, base + c0, len, max(0, min(len, pm - c0))};
-    }
-}
-
-__global__ void tile_part_off_kernel(Grid G, const int* __restrict__ cell_sci,
-                                     const int* __restrict__ t_unit_off, int nsci, int nunits, int* part_off) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > G.R) return;
-    if (r == G.R) { part_off[r] = nunits; return; }
-    const int s = cell_sci[r * G.ncell];
-    part_off[r] = s < nsci ? t_unit_off[s * nbl::kMaxCi] : nunits;
-}
-
 __global__ void minmax_kernel(int total, const double* __restrict__ pos, double* out) {
     // single block reduction; non-periodic systems only, at list-build time
     __shared__ double smin[3][256], smax[3][256];
@@ -736,48 +661,6 @@ static int build_list(sdm_ctx* c) {
     c->launches += 7;
     PL_CUDA(cudaGetLastError());
 
-    // tile list for pair_tile_kernel: count, scan, (re)allocate, fill
-    if (pl->use_tiles) {
-        const int nt = pl->nsci * nbl::kMaxCi;
-        if ((size_t)nt + 1 > pl->t_idx_cap) {
-            pl->t_idx_cap = (size_t)(nt * 1.25) + 64;
-            if (int rc = pl_realloc(pl, &pl->t_nrec, pl->t_idx_cap)) return rc;
-            if (int rc = pl_realloc(pl, &pl->t_rec_off, pl->t_idx_cap)) return rc;
-            if (int rc = pl_realloc(pl, &pl->t_nunits, pl->t_idx_cap)) return rc;
-            if (int rc = pl_realloc(pl, &pl->t_unit_off, pl->t_idx_cap)) return rc;
-        }
-        if (nt > 0)
-            tile_count_kernel<<<blocks(nt), 256, 0, s>>>(pl->nsci, pl->sci, pl->sci_off, pl->entries,
-                                                        pl->tile_chunk, pl->t_nrec, pl->t_nunits);
-        PL_CUDA(cudaMemsetAsync(pl->t_nrec + nt, 0, sizeof(int), s));
-        PL_CUDA(cudaMemsetAsync(pl->t_nunits + nt, 0, sizeof(int), s));
-        if (int rc = ensure_cub((size_t)nt + 1)) return rc;
-        PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->t_nrec, pl->t_rec_off, nt + 1, s));
-        PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->t_nunits, pl->t_unit_off, nt + 1, s));
-        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[6], pl->t_rec_off + nt, sizeof(int), cudaMemcpyDeviceToHost, s));
-        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[7], pl->t_unit_off + nt, sizeof(int), cudaMemcpyDeviceToHost, s));
-        PL_CUDA(cudaStreamSynchronize(s));
-        pl->t_nrecs = pl->h_counts[6];
-        pl->t_nunits_total = pl->h_counts[7];
-        if ((size_t)pl->t_nrecs > pl->t_recs_cap) {
-            pl->t_recs_cap = (size_t)(pl->t_nrecs * 1.25) + 1024;
-            if (int rc = pl_realloc(pl, &pl->t_recs, pl->t_recs_cap)) return rc;
-        }
-        if ((size_t)pl->t_nunits_total > pl->t_units_cap) {
-            pl->t_units_cap = (size_t)(pl->t_nunits_total * 1.25) + 256;
-            if (int rc = pl_realloc(pl, &pl->t_units, pl->t_units_cap)) return rc;
-            if (int rc = pl_realloc(pl, &pl->t_epart, pl->t_units_cap)) return rc;
-            if (int rc = pl_realloc(pl, &pl->t_cpart, pl->t_units_cap)) return rc;
-        }
-        if (nt > 0)
-            tile_fill_kernel<<<blocks(nt), 256, 0, s>>>(pl->nsci, pl->sci, pl->sci_off, pl->entries, pl->tile_chunk,
-                                                       pl->t_rec_off, pl->t_unit_off, pl->t_recs, pl->t_units);
-        tile_part_off_kernel<<<blocks(R + 1), 256, 0, s>>>(G, pl->cell_sci, pl->t_unit_off, pl->nsci,
-                                                          pl->t_nunits_total, pl->t_part_off);
-        c->launches += 5;
-        PL_CUDA(cudaGetLastError());
-    }
-
     // the fixed-point accumulators are indexed by slot: start from zero for the new layout
     PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
     {
@@ -853,9 +736,6 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->sci_nunits, pl->nsci_cap + 1));
     A(pl_alloc(pl, &pl->sci_unit_off, pl->nsci_cap + 1));
     A(pl_alloc(pl, &pl->part_off, R + 1));
-    A(pl_alloc(pl, &pl->t_part_off, R + 1));
-    if (const char* e = getenv("SDMB200_PAIR_KERNEL")) pl->use_tiles = std::string(e) == "tiles";   // development knob
-    if (const char* e = getenv("SDMB200_TILE_CHUNK")) pl->tile_chunk = std::min(64, std::max(2, atoi(e) & ~1));   // <= 32 steps: one fix-up bit per step
     A(pl_alloc(pl, &pl->unit_counter, 1));
     A(pl_alloc(pl, &pl->minmax, 6));
     pl->items_cap = (size_t)pl->nsci_cap * 64 + 1;
@@ -962,9 +842,9 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
     }
     c->list_age++;
     // partial-sum buffers of this path
-    c->B.epart = pl->use_tiles ? pl->t_epart : pl->epart;
-    c->B.cpart = pl->use_tiles ? pl->t_cpart : pl->cpart;
-    c->B.part_off = pl->use_tiles ? pl->t_part_off : pl->part_off;
+    c->B.epart = pl->epart;
+    c->B.cpart = pl->cpart;
+    c->B.part_off = pl->part_off;
     // the displaced-atom kernels scan the cell-sorted slots (spatial locality per warp)
     c->B.scan_posq = pl->posq;
     c->B.scan_atom = pl->atom;
@@ -980,17 +860,8 @@ int sdm_ctx_pairlist_launch(sdm_ctx* c) {
     cudaStream_t s = c->stream;
     // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
-    if (pl->use_tiles) {
-        TileListView TL;
-        TL.recs = pl->t_recs;
-        TL.units = pl->t_units;
-        TL.nunits = pl->t_nunits_total;
-        launch_pair_tiles(c->T, make_view(c), TL, c->d_pos, c->B.f1acc, pl->t_epart, pl->t_cpart,
-                          c->opt.exact_cutoff, pl->unit_counter, c->num_sms, s);
-    } else {
-        launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart,
-                            c->opt.exact_cutoff, pl->unit_counter, c->num_sms, s);
-    }
+    launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
+                        pl->unit_counter, c->num_sms, nullptr, s);
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[2], s));
     c->launches++;
     PL_CUDA(cudaGetLastError());
@@ -1000,8 +871,11 @@ int sdm_ctx_pairlist_launch(sdm_ctx* c) {
 int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap) {
     PairList* pl = c->pl;
     if (!pl || !c->list_valid) return sdm_fail(SDM_ERR_INVALID, "no pair list built yet: call sdm_eval first");
-    launch_pair_emit(c->T, make_view(c), c->d_pos, c->opt.exact_cutoff, d_counter, d_pairs, cap, replica,
-                     c->stream);
+    // the debug build of the hot kernel itself: same list, same code, plus the pair records.  It adds
+    // its forces to the accumulators a second time; they are cleared before the next evaluation.
+    const PairEmit em{d_counter, d_pairs, cap, replica};
+    launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
+                        pl->unit_counter, c->num_sms, &em, c->stream);
     PL_CUDA(cudaStreamSynchronize(c->stream));
     return SDM_OK;
 }
@@ -1016,9 +890,7 @@ int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "n_entries") *value = pl->nentries;
     else if (k == "n_raw_entries") *value = pl->nraw;
     else if (k == "n_masks") *value = pl->nmasks;
-    else if (k == "n_units") *value = pl->use_tiles ? pl->t_nunits_total : pl->nunits;
-    else if (k == "n_tile_records") *value = pl->t_nrecs;
-    else if (k == "pair_kernel_tiles") *value = pl->use_tiles;
+    else if (k == "n_units") *value = pl->nunits;
     else if (k == "n_cells") *value = pl->G.ncell;
     else if (k == "cell_span") *value = pl->G.span;
     else if (k == "layout_columns") *value = pl->G.columns;

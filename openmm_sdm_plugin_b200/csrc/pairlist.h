@@ -28,33 +28,18 @@ struct PairListView {
     int nslot_cap;               // accumulator plane stride
 };
 
-// Tile list: the entries expanded into one record per (i-cluster, j-cluster) tile, grouped by
-// i-cluster, for pair_tile_kernel.  Within an i-cluster the tiles of masked entries come first;
-// both groups are padded to an even count with dummy records (shift code 63, cluster 0, mask 0).
-struct TileUnit {
-    int islot;    // first slot of the i-cluster
-    int begin;    // first record (index into recs)
-    int nrec;     // records of this unit (even, <= chunk)
-    int nmask;    // how many of them (from the start) carry exclusion masks (even)
+// The pair kernel.  emit != nullptr selects the debug build of the SAME kernel, which also records
+// the System indices (i < j) of every pair it accepts for replica emit->replica -- the bit-exact
+// pair-set tests read the hot kernel's own decisions, not a re-implementation.
+struct PairEmit {
+    int* counter;    // device: pairs accepted so far
+    int* pairs;      // device: [2*cap]
+    int cap;
+    int replica;
 };
-
-struct TileListView {
-    const uint2* recs;           // {cj | shift<<26, index of the tile's two mask words (0 = all ones)}
-    const TileUnit* units;
-    int nunits;
-};
-
-void launch_pair_tiles(const Topology& T, const PairListView& V, const TileListView& TL,
-                       const double* pos_all, long long* f1acc, double* epart, long long* cpart,
-                       int exact, int* unit_counter, int num_sms, cudaStream_t s);
-
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
-                         int* unit_counter, int num_sms, cudaStream_t s);
-// Debug / parity: dump the in-cutoff pairs of one replica exactly as the pair kernel decides them.
-void launch_pair_emit(const Topology& T, const PairListView& V, const double* pos_all, int exact,
-                      int* emit_counter, int* emit_pairs, int emit_cap, int emit_replica,
-                      cudaStream_t s);
+                         int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s);
 
 // Per-eval refresh of the sorted positions from the current double positions (same periodic
 // image as at build time) + staleness check against the build-time positions.

@@ -172,23 +172,3 @@ def test_auto_mode_picks_cluster_for_large_and_allpairs_for_small(cfg2):
         assert ctx.info("pair_mode") == CL
     with SDMContext(S.cfg1().system, None) as ctx:
         assert ctx.info("pair_mode") == _lib.PAIR_ALLPAIRS
-
-
-def test_cfg2_tile_list_kernel_matches_oracle(cfg2, monkeypatch):
-    """pair_tile_kernel (the per-i-cluster alternative kept for A/B runs) walks
-    the same tiles with the same FP32 arithmetic: same pair count, same parity bar."""
-    case, ref = cfg2
-    monkeypatch.setenv("SDMB200_PAIR_KERNEL", "tiles")
-    with run_case(case, CL) as ctx:
-        assert ctx.info("pair_kernel_tiles") == 1
-        sc = check_against_oracle(ctx, case, ref)
-        assert sc["n_pairs1"] == 4197871
-
-
-def test_cfg1_tile_list_kernel_nonperiodic(monkeypatch):
-    case = S.cfg1()
-    case.system.cutoff = 1.2
-    ref = oracle_eval(case)
-    monkeypatch.setenv("SDMB200_PAIR_KERNEL", "tiles")
-    with run_case(case, CL) as ctx:
-        check_against_oracle(ctx, case, ref)
