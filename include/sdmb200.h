@@ -43,9 +43,13 @@ typedef enum {
     SDM_ERR_SOFTCORE = -5,     /* "Unknown soft core method" (LangevinIntegratorSDM.cpp:147)*/
     SDM_ERR_STALE_LIST = -6,   /* an atom moved more than skin/2 since the list was built: reported in
                                   sdm_scalars.status; the list is rebuilt at the next sdm_eval(),
-                                  repeat the evaluation                                          */
-    SDM_ERR_CAPACITY = -7      /* internal scratch capacity exceeded: reported in sdm_scalars.status,
+                                  repeat the evaluation.  The status is STICKY: it stays in
+                                  sdm_scalars.status of later evaluations until the host has read it
+                                  (sdm_get_scalars / sdm_read_results / sdm_enqueue_results), so a
+                                  pipelined sequence of sdm_eval calls cannot lose it              */
+    SDM_ERR_CAPACITY = -7,     /* internal scratch capacity exceeded: reported in sdm_scalars.status,
                                   the context grows the scratch, repeat the evaluation            */
+    SDM_ERR_CONSTRAINT = -8    /* a constraint cluster did not converge (sdm_md_step)              */
 } sdm_status;
 
 /* NonbondedForce::NonbondedMethod as the reference's reader sets it
@@ -256,9 +260,9 @@ int sdm_langevin_params(double temperature, double friction, double step_size, d
  * (platforms/reference/src/ReferenceStochasticDynamicsSDM.cpp:131-266; the OpenCL kernels
  * langevin.cl:7-69 are its float form): v = vscale*v + fscale*F/m + noisescale*xi/sqrt(m),
  * x' = x + dt*v, v = (x'-x)/dt.  Positions and velocities of all replicas stay in HBM, FP64, with
- * the reference's operation order, so a step needs no host<->device copy.  Constraints (OpenMM's
- * SETTLE / CCMA, ReferenceStochasticDynamicsSDM.cpp:250-252) are NOT applied: meant for
- * unconstrained systems and for measuring the device-resident loop. */
+ * the reference's operation order, so a step needs no host<->device copy.  Distance constraints
+ * are applied where the reference applies them (between x' and the velocity/position copy,
+ * ReferenceStochasticDynamicsSDM.cpp:250-262) once sdm_md_set_constraints() has been called. */
 /* masses [n_atoms] (0 = particle does not move); velocities start at zero.  friction (1/ps) must be
  * > 0 (the reference divides by it); seed keys the Philox4x32-10 noise stream. */
 int sdm_md_init(sdm_ctx* ctx, const double* masses, double temperature, double friction,
@@ -266,8 +270,25 @@ int sdm_md_init(sdm_ctx* ctx, const double* masses, double temperature, double f
 int sdm_md_set_velocities(sdm_ctx* ctx, int replica, const double* v);   /* [3*n_atoms] nm/ps */
 int sdm_md_get_velocities(sdm_ctx* ctx, int replica, double* v);         /* synchronises */
 int sdm_get_positions(sdm_ctx* ctx, int replica, double* xyz);           /* current positions, synchronises */
-/* nsteps x (sdm_eval + Langevin update), asynchronous on the context's stream. */
+/* The System's distance constraints (System::addConstraint as the reference's reader fills it,
+ * example/desmonddmsfile75.py:560-561,589-595,603-637): pairs [2*n], distances [n] (nm), relative
+ * tolerance (Integrator::getConstraintTolerance, LangevinIntegratorSDM.cpp:52: 1e-5; <= 0 = 1e-5).
+ * Rigid three-site molecules (three mutual constraints, two equal legs to atoms of equal mass: the
+ * constraint_hoh waters) are solved analytically (SETTLE), every other cluster of coupled
+ * constraints (a heavy atom and its hydrogens; at most 8 atoms / 16 constraints) by an in-thread
+ * SHAKE iteration to the tolerance.  Call after sdm_md_init(); n = 0 removes them. */
+int sdm_md_set_constraints(sdm_ctx* ctx, int32_t n_constraints, const int32_t* pairs,
+                           const double* distances, double tolerance);
+/* nsteps x (sdm_eval + Langevin update [+ constraints]) on the device; returns when they are done.
+ * A step whose evaluation reports SDM_ERR_STALE_LIST / SDM_ERR_CAPACITY is NOT taken (nor are the
+ * steps enqueued behind it): the list is rebuilt / the scratch grown and the missing steps are
+ * repeated, so the trajectory never integrates a force that misses pairs.  Fails with
+ * SDM_ERR_STALE_LIST if a freshly built list goes stale within a single step (skin too small for
+ * the step size), with SDM_ERR_CONSTRAINT if a cluster does not converge. */
 int sdm_md_step(sdm_ctx* ctx, int nsteps);
+/* Steps taken since sdm_md_init() and how many of the enqueued steps had to be repeated because of
+ * a stale list. */
+int sdm_md_get_counters(sdm_ctx* ctx, uint64_t* steps_taken, uint64_t* steps_repeated);
 /* The update alone, with the hybrid force already on the device (forces_all == NULL) or with
  * forces_all [R][n][3] uploaded first (test hook: the reference's forces in, its x and v out). */
 int sdm_md_update(sdm_ctx* ctx, const double* forces_all);

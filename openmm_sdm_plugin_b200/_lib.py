@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 SDM_OK = 0
 SDM_ERR_INVALID, SDM_ERR_NO_DEVICE, SDM_ERR_CUDA, SDM_ERR_BOX = -1, -2, -3, -4
-SDM_ERR_SOFTCORE, SDM_ERR_STALE_LIST, SDM_ERR_CAPACITY = -5, -6, -7
+SDM_ERR_SOFTCORE, SDM_ERR_STALE_LIST, SDM_ERR_CAPACITY, SDM_ERR_CONSTRAINT = -5, -6, -7, -8
 FORCE_HYBRID, FORCE_STATE1, FORCE_STATE2, FORCE_DELTA = 0, 1, 2, 3
 PAIR_AUTO, PAIR_ALLPAIRS, PAIR_CLUSTER = 0, 1, 2
 
@@ -107,7 +107,9 @@ SYMBOLS = {
     "sdm_md_set_velocities": (_I, [_VP, _I, _VP]),
     "sdm_md_get_velocities": (_I, [_VP, _I, _VP]),
     "sdm_get_positions": (_I, [_VP, _I, _VP]),
+    "sdm_md_set_constraints": (_I, [_VP, C.c_int32, _VP, _VP, _D]),
     "sdm_md_step": (_I, [_VP, _I]),
+    "sdm_md_get_counters": (_I, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sdm_md_update": (_I, [_VP, _VP]),
     "sdm_md_set_noise": (_I, [_VP, _VP]),
     "sdm_md_kinetic_energy": (_I, [_VP, _I, C.POINTER(_D)]),

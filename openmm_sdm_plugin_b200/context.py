@@ -229,7 +229,7 @@ class SDMContext:
         _lib.check(self._L.sdm_get_last_timing(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    # ---- device-resident Langevin dynamics (sdm_md_*; SURVEY N2, no constraints) --------------
+    # ---- device-resident Langevin dynamics (sdm_md_*) ------------------------------
     def md_init(self, masses, temperature: float, friction: float, step_size: float, seed: int = 0):
         m = np.ascontiguousarray(masses, np.float64)
         if m.size != self.n:
@@ -253,8 +253,24 @@ class SDMContext:
         _lib.check(self._L.sdm_get_positions(self._h, replica, _ptr(out)))
         return out
 
+    def md_set_constraints(self, pairs, distances, tolerance: float = 1e-5):
+        """System.addConstraint pairs [n, 2] and distances [n] (nm); applied between the two halves
+        of the update like ReferenceStochasticDynamicsSDM.cpp:250-252."""
+        p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        d = np.ascontiguousarray(distances, np.float64).reshape(-1)
+        if len(p) != len(d):
+            raise ValueError("pairs [n, 2] and distances [n] must have the same length")
+        _lib.check(self._L.sdm_md_set_constraints(self._h, len(d), _ptr(p) if len(d) else None,
+                                                  _ptr(d) if len(d) else None, float(tolerance)))
+
     def md_step(self, nsteps: int = 1):
         _lib.check(self._L.sdm_md_step(self._h, int(nsteps)))
+
+    def md_counters(self):
+        """(steps taken since md_init, enqueued steps that were repeated because of a stale list)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        _lib.check(self._L.sdm_md_get_counters(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def md_update(self, forces_all=None):
         a = None if forces_all is None else np.ascontiguousarray(forces_all, np.float64)

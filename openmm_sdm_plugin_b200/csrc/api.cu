@@ -119,6 +119,23 @@ int upload_displacement(sdm_ctx* c, const double* displacement) {
     return SDM_OK;
 }
 
+// Every entry point that takes a context runs on the context's device and leaves the calling
+// thread's current device as it found it, so one host thread can drive contexts on several GPUs.
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    explicit DeviceGuard(int device) : dev(device) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define SDM_ON_CTX_DEVICE(c) DeviceGuard device_guard_((c) ? (c)->device : -1)
+
 int check_ctx(sdm_ctx* c, int replica) {
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     if (replica < 0 || replica >= c->R) return fail(SDM_ERR_INVALID, "replica index out of range");
@@ -202,13 +219,14 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
         if (opt.skin < 0) opt.skin = 0.06;
         if (opt.nstlist <= 0) opt.nstlist = 20;
     }
-    if (opt.device >= 0) SDM_CUDA(cudaSetDevice(opt.device));
     int dev = 0;
     SDM_CUDA(cudaGetDevice(&dev));
+    if (opt.device >= 0) dev = opt.device;
+    DeviceGuard device_guard_(dev);   // the caller's current device is restored on return
     cudaDeviceProp prop;
     SDM_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10)
-        return fail(SDM_ERR_NO_DEVICE, "libsdmb200 is built for sm_100a (B200) only");
+    if (prop.major != 10)   // the binary holds sm_100a code only: it loads on compute capability 10.x, nothing else
+        return fail(SDM_ERR_NO_DEVICE, "libsdmb200 is built for sm_100a (B200, compute capability 10.x) only");
 
     sdm_ctx* c = new sdm_ctx();
     c->device = dev;
@@ -353,6 +371,9 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     TRY(dev_alloc(c, &B.mcnt, (size_t)R * n * 2));
     TRY(dev_alloc(c, &B.state, (size_t)R));
     TRY(dev_alloc(c, &B.flags, (size_t)R));
+    TRY(dev_alloc(c, &c->d_sticky, (size_t)R));
+    B.sticky = c->d_sticky;
+    B.md_ctl = nullptr;   // set by sdm_md_init
     TRY(dev_alloc(c, &c->d_list_age, 1));
     B.list_age = c->d_list_age;
 
@@ -381,8 +402,8 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
 }
 
 void sdm_destroy(sdm_ctx* c) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return;
-    cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     sdm_ctx_free_pairlist(c);
     for (void* p : c->allocs) cudaFree(p);
@@ -398,6 +419,7 @@ void sdm_destroy(sdm_ctx* c) {
 }
 
 int sdm_set_stream(sdm_ctx* c, void* cuda_stream) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     if (c->own_stream && c->stream) SDM_CUDA(cudaStreamDestroy(c->stream));
@@ -408,6 +430,7 @@ int sdm_set_stream(sdm_ctx* c, void* cuda_stream) {
 }
 
 int sdm_synchronize(sdm_ctx* c) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     return SDM_OK;
@@ -425,6 +448,7 @@ int sdm_host_free(void* ptr) {
 }
 
 int sdm_set_positions(sdm_ctx* c, int replica, const double* xyz) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!xyz) return fail(SDM_ERR_INVALID, "null positions");
     SDM_CUDA(cudaMemcpyAsync(c->d_pos + (size_t)replica * 3 * c->n, xyz, sizeof(double) * 3 * (size_t)c->n,
@@ -433,6 +457,7 @@ int sdm_set_positions(sdm_ctx* c, int replica, const double* xyz) {
 }
 
 int sdm_set_positions_device(sdm_ctx* c, int replica, const double* d_xyz) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!d_xyz) return fail(SDM_ERR_INVALID, "null positions");
     SDM_CUDA(cudaMemcpyAsync(c->d_pos + (size_t)replica * 3 * c->n, d_xyz, sizeof(double) * 3 * (size_t)c->n,
@@ -441,6 +466,7 @@ int sdm_set_positions_device(sdm_ctx* c, int replica, const double* d_xyz) {
 }
 
 int sdm_set_positions_all(sdm_ctx* c, const double* xyz_all) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     if (!xyz_all) return fail(SDM_ERR_INVALID, "null positions");
     SDM_CUDA(cudaMemcpyAsync(c->d_pos, xyz_all, sizeof(double) * 3 * (size_t)c->n * c->R,
@@ -449,6 +475,7 @@ int sdm_set_positions_all(sdm_ctx* c, const double* xyz_all) {
 }
 
 int sdm_positions_device_ptr(sdm_ctx* c, int replica, double** d_xyz) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!d_xyz) return fail(SDM_ERR_INVALID, "null argument");
     *d_xyz = c->d_pos + (size_t)replica * 3 * c->n;
@@ -456,6 +483,7 @@ int sdm_positions_device_ptr(sdm_ctx* c, int replica, double** d_xyz) {
 }
 
 int sdm_set_bonded_forces(sdm_ctx* c, int replica, const double* fb, double eb) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     double* dst = c->d_fb + (size_t)replica * 3 * c->n;
     if (fb)
@@ -469,6 +497,7 @@ int sdm_set_bonded_forces(sdm_ctx* c, int replica, const double* fb, double eb) 
 }
 
 int sdm_set_alchemical(sdm_ctx* c, int replica, const sdm_alch* a) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!a) return fail(SDM_ERR_INVALID, "null argument");
     c->h_alch[replica] = *a;
@@ -478,6 +507,7 @@ int sdm_set_alchemical(sdm_ctx* c, int replica, const sdm_alch* a) {
 }
 
 int sdm_get_alchemical(sdm_ctx* c, int replica, sdm_alch* a) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!a) return fail(SDM_ERR_INVALID, "null argument");
     SDM_CUDA(cudaMemcpyAsync(&c->h_state[replica].alch, &c->B.state[replica].alch, sizeof(sdm_alch),
@@ -489,6 +519,7 @@ int sdm_get_alchemical(sdm_ctx* c, int replica, sdm_alch* a) {
 }
 
 int sdm_set_displacement(sdm_ctx* c, const double* displacement) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     if (int rc = upload_displacement(c, displacement)) return rc;
@@ -498,6 +529,7 @@ int sdm_set_displacement(sdm_ctx* c, const double* displacement) {
 }
 
 int sdm_invalidate_list(sdm_ctx* c) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     c->list_valid = false;
     return SDM_OK;
@@ -599,6 +631,7 @@ static int ensure_hitbits(sdm_ctx* c) {
 }
 
 int sdm_eval(sdm_ctx* c) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     cudaStream_t s = c->stream;
     const sdm::Topology& T = c->T;
@@ -702,10 +735,12 @@ static void note_status(sdm_ctx* c, int status) {
 }
 
 int sdm_get_scalars(sdm_ctx* c, int replica, sdm_scalars* out) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!out) return fail(SDM_ERR_INVALID, "null argument");
     SDM_CUDA(cudaMemcpyAsync(&c->h_state[replica].sc, &c->B.state[replica].sc, sizeof(sdm_scalars),
                              cudaMemcpyDeviceToHost, c->stream));
+    SDM_CUDA(cudaMemsetAsync(c->d_sticky + replica, 0, sizeof(int), c->stream));   // the host has it now
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     *out = c->h_state[replica].sc;
     note_status(c, out->status);
@@ -713,6 +748,7 @@ int sdm_get_scalars(sdm_ctx* c, int replica, sdm_scalars* out) {
 }
 
 int sdm_get_forces(sdm_ctx* c, int replica, int which, double* out) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!out) return fail(SDM_ERR_INVALID, "null argument");
     const size_t n3 = 3 * (size_t)c->n, off = (size_t)replica * n3;
@@ -735,13 +771,16 @@ int sdm_get_forces(sdm_ctx* c, int replica, int which, double* out) {
 }
 
 int sdm_read_results(sdm_ctx* c, double* forces_all, sdm_scalars* scalars_all) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     if (forces_all)
         SDM_CUDA(cudaMemcpyAsync(forces_all, c->B.F, sizeof(double) * 3 * (size_t)c->n * c->R,
                                  cudaMemcpyDeviceToHost, c->stream));
-    if (scalars_all)
+    if (scalars_all) {
         SDM_CUDA(cudaMemcpyAsync(c->h_state, c->B.state, sizeof(sdm::ReplicaState) * (size_t)c->R,
                                  cudaMemcpyDeviceToHost, c->stream));
+        SDM_CUDA(cudaMemsetAsync(c->d_sticky, 0, sizeof(int) * (size_t)c->R, c->stream));
+    }
     SDM_CUDA(cudaStreamSynchronize(c->stream));
     if (scalars_all)
         for (int r = 0; r < c->R; r++) {
@@ -752,16 +791,21 @@ int sdm_read_results(sdm_ctx* c, double* forces_all, sdm_scalars* scalars_all) {
 }
 
 int sdm_enqueue_results(sdm_ctx* c, double* forces_all) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     if (forces_all)
         SDM_CUDA(cudaMemcpyAsync(forces_all, c->B.F, sizeof(double) * 3 * (size_t)c->n * c->R,
                                  cudaMemcpyDeviceToHost, c->stream));
     SDM_CUDA(cudaMemcpyAsync(c->h_state, c->B.state, sizeof(sdm::ReplicaState) * (size_t)c->R,
                              cudaMemcpyDeviceToHost, c->stream));
+    // the copy above carries the sticky status to the host; later evaluations start clean (an
+    // evaluation that still runs on the stale list raises it again)
+    SDM_CUDA(cudaMemsetAsync(c->d_sticky, 0, sizeof(int) * (size_t)c->R, c->stream));
     return SDM_OK;
 }
 
 int sdm_collect_scalars(sdm_ctx* c, sdm_scalars* scalars_all) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c || !scalars_all) return fail(SDM_ERR_INVALID, "null argument");
     for (int r = 0; r < c->R; r++) {
         scalars_all[r] = c->h_state[r].sc;
@@ -771,6 +815,7 @@ int sdm_collect_scalars(sdm_ctx* c, sdm_scalars* scalars_all) {
 }
 
 int sdm_forces_device_ptr(sdm_ctx* c, int replica, double** d_f) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!d_f) return fail(SDM_ERR_INVALID, "null argument");
     *d_f = c->B.F + (size_t)replica * 3 * c->n;
@@ -778,6 +823,7 @@ int sdm_forces_device_ptr(sdm_ctx* c, int replica, double** d_f) {
 }
 
 int sdm_get_pairs(sdm_ctx* c, int replica, int32_t* pairs, int64_t max_pairs, int64_t* n_out) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!n_out) return fail(SDM_ERR_INVALID, "null argument");
     cudaStream_t s = c->stream;
@@ -820,12 +866,14 @@ int sdm_get_pairs(sdm_ctx* c, int replica, int32_t* pairs, int64_t max_pairs, in
 }
 
 int sdm_get_launch_count(sdm_ctx* c, int64_t* n) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c || !n) return fail(SDM_ERR_INVALID, "null argument");
     *n = c->launches;
     return SDM_OK;
 }
 
 int sdm_set_timing(sdm_ctx* c, int enabled) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     c->timing = enabled != 0;
     c->timing_valid = false;
@@ -834,6 +882,7 @@ int sdm_set_timing(sdm_ctx* c, int enabled) {
 }
 
 int sdm_get_last_timing(sdm_ctx* c, float* pair_ms, float* total_ms) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     if (!c->timing_valid) return fail(SDM_ERR_INVALID, "timing not enabled for the last eval");
     SDM_CUDA(cudaEventSynchronize(c->ev[3]));
@@ -846,6 +895,7 @@ int sdm_get_last_timing(sdm_ctx* c, float* pair_ms, float* total_ms) {
 }
 
 int sdm_get_info(sdm_ctx* c, const char* key, double* value) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c || !key || !value) return fail(SDM_ERR_INVALID, "null argument");
     std::string k(key);
     if (k == "n_atoms") *value = c->n;
@@ -933,6 +983,7 @@ int sdm_langevin_params(double temperature, double friction, double step_size, d
 
 int sdm_md_init(sdm_ctx* c, const double* masses, double temperature, double friction, double step_size,
                 uint64_t seed) {
+    SDM_ON_CTX_DEVICE(c);
     if (!c || !masses) return fail(SDM_ERR_INVALID, "null argument");
     if (!(friction > 0.0) || !(step_size > 0.0) || !(temperature >= 0.0))
         return fail(SDM_ERR_INVALID, "sdm_md_init needs friction > 0, step_size > 0, temperature >= 0 "
@@ -959,10 +1010,120 @@ int sdm_md_init(sdm_ctx* c, const double* masses, double temperature, double fri
     c->md_vscale = std::exp(-step_size / tau);
     c->md_fscale = (1 - c->md_vscale) * tau;
     c->md_noisescale = std::sqrt(2 * kT / tau) * std::sqrt(0.5 * (1 - c->md_vscale * c->md_vscale) * tau);
+    // The noise of step k is Philox(seed, atom, offset 8*k).  Re-initialising with new parameters
+    // (the mirrors do that when temperature, friction or step size change: "dynamics object
+    // recreated", LangevinIntegratorSDM.cpp:160-168) must not replay the stream from step 0 -- the
+    // reference's SimTK generator is global and carries on -- so the step counter survives unless
+    // the seed changes.
+    if (!c->md_ready || seed != c->md_seed) c->md_steps = 0;
     c->md_seed = seed;
-    c->md_steps = 0;
     c->md_noise_pending = false;
+    if (!c->d_md_ctl) {
+        if (int rc = dev_alloc(c, &c->d_md_ctl, 4)) return rc;
+        SDM_CUDA(cudaMallocHost((void**)&c->h_md_ctl, 4 * sizeof(unsigned long long)));
+        c->B.md_ctl = c->d_md_ctl;
+        c->graph_valid = false;   // the captured scalar stage must see the control words
+    }
+    {
+        const unsigned long long ctl0[4] = {0ull, c->md_steps, 0ull, 0ull};
+        SDM_CUDA(cudaMemcpy(c->d_md_ctl, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice));
+    }
     c->md_ready = true;
+    return SDM_OK;
+}
+
+// Distance constraints: connected clusters of the constraint graph; rigid three-site molecules get
+// SETTLE, everything else an in-thread SHAKE (kernels_md.cu).
+int sdm_md_set_constraints(sdm_ctx* c, int32_t n_constraints, const int32_t* pairs, const double* distances,
+                           double tolerance) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (!c->md_ready) return fail(SDM_ERR_INVALID, "call sdm_md_init first");
+    if (n_constraints < 0 || (n_constraints > 0 && (!pairs || !distances)))
+        return fail(SDM_ERR_INVALID, "bad constraint arguments");
+    const int n = c->n, R = c->R;
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    c->cons_tol = tolerance > 0 ? tolerance : 1e-5;
+    c->h_cons_pairs.assign(pairs, pairs + 2 * (size_t)n_constraints);
+    c->h_cons_dist.assign(distances, distances + n_constraints);
+    c->mdc = sdm::MdConstraints{};
+    c->mdc.tol = c->cons_tol;
+    if (n_constraints == 0) return SDM_OK;
+    std::vector<double> mass(n);
+    SDM_CUDA(cudaMemcpy(mass.data(), c->d_mass, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    // union-find over the constraint graph
+    std::vector<int> parent(n);
+    for (int i = 0; i < n; i++) parent[i] = i;
+    auto find = [&](int a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
+    for (int k = 0; k < n_constraints; k++) {
+        const int a = pairs[2 * k], b = pairs[2 * k + 1];
+        if (a < 0 || b < 0 || a >= n || b >= n || a == b || !(distances[k] > 0))
+            return fail(SDM_ERR_INVALID, "constraint with a bad particle index or distance");
+        parent[find(a)] = find(b);
+    }
+    std::vector<std::vector<int>> cons_of(n), atoms_of(n);   // keyed by cluster root
+    for (int k = 0; k < n_constraints; k++) cons_of[find(pairs[2 * k])].push_back(k);
+    std::vector<unsigned char> in_cluster(n, 0);
+    for (int i = 0; i < n; i++)
+        if (!cons_of[find(i)].empty()) { atoms_of[find(i)].push_back(i); in_cluster[i] = 1; }
+    std::vector<int> settle_atoms, shake_off{0}, shake_ij, shake_aoff{0}, shake_atoms;
+    std::vector<double> settle_par, shake_d;
+    for (int root = 0; root < n; root++) {
+        const std::vector<int>& ks = cons_of[root];
+        const std::vector<int>& as = atoms_of[root];
+        if (ks.empty()) continue;
+        bool settled = false;
+        if (as.size() == 3 && ks.size() == 3) {
+            // three mutual constraints: find the apex (two equal legs to atoms of equal, non-zero mass)
+            auto dist = [&](int a, int b) {
+                for (int k : ks)
+                    if ((pairs[2 * k] == a && pairs[2 * k + 1] == b) || (pairs[2 * k] == b && pairs[2 * k + 1] == a))
+                        return distances[k];
+                return -1.0;
+            };
+            for (int t = 0; t < 3 && !settled; t++) {
+                const int a0 = as[t], a1 = as[(t + 1) % 3], a2 = as[(t + 2) % 3];
+                const double d01 = dist(a0, a1), d02 = dist(a0, a2), d12 = dist(a1, a2);
+                if (d01 > 0 && d02 > 0 && d12 > 0 && std::fabs(d01 - d02) <= 1e-12 * d01 && mass[a1] == mass[a2] &&
+                    mass[a0] > 0 && mass[a1] > 0 && d12 < 2 * d01) {
+                    settle_atoms.insert(settle_atoms.end(), {a0, a1, a2});
+                    settle_par.insert(settle_par.end(), {d01, d12});
+                    settled = true;
+                }
+            }
+        }
+        if (settled) continue;
+        for (int k : ks) {
+            shake_ij.push_back(pairs[2 * k]);
+            shake_ij.push_back(pairs[2 * k + 1]);
+            shake_d.push_back(distances[k]);
+        }
+        shake_off.push_back((int)shake_d.size());
+        shake_atoms.insert(shake_atoms.end(), as.begin(), as.end());
+        shake_aoff.push_back((int)shake_atoms.size());
+    }
+    sdm::MdConstraints& M = c->mdc;
+    M.n_settle = (int)settle_atoms.size() / 3;
+    M.n_shake = (int)shake_off.size() - 1;
+    if (int rc = dev_upload(c, &M.settle_atoms, settle_atoms)) return rc;
+    if (int rc = dev_upload(c, &M.settle_par, settle_par)) return rc;
+    if (int rc = dev_upload(c, &M.shake_off, shake_off)) return rc;
+    if (int rc = dev_upload(c, &M.shake_ij, shake_ij)) return rc;
+    if (int rc = dev_upload(c, &M.shake_d, shake_d)) return rc;
+    if (int rc = dev_upload(c, &M.shake_aoff, shake_aoff)) return rc;
+    if (int rc = dev_upload(c, &M.shake_atoms, shake_atoms)) return rc;
+    if (int rc = dev_upload(c, &M.in_cluster, in_cluster)) return rc;
+    if (!c->d_xprime)
+        if (int rc = dev_alloc(c, &c->d_xprime, 3 * (size_t)n * R)) return rc;
+    return SDM_OK;
+}
+
+int sdm_md_get_counters(sdm_ctx* c, uint64_t* steps_taken, uint64_t* steps_repeated) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (!c->md_ready) return fail(SDM_ERR_INVALID, "call sdm_md_init first");
+    if (steps_taken) *steps_taken = c->md_steps;
+    if (steps_repeated) *steps_repeated = c->md_repeated;
     return SDM_OK;
 }
 
@@ -973,6 +1134,7 @@ static int md_check(sdm_ctx* c, int replica) {
 }
 
 int sdm_md_set_velocities(sdm_ctx* c, int replica, const double* v) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = md_check(c, replica)) return rc;
     if (!v) return fail(SDM_ERR_INVALID, "null velocities");
     SDM_CUDA(cudaMemcpyAsync(c->d_vel + (size_t)replica * 3 * c->n, v, sizeof(double) * 3 * (size_t)c->n,
@@ -982,6 +1144,7 @@ int sdm_md_set_velocities(sdm_ctx* c, int replica, const double* v) {
 }
 
 int sdm_md_get_velocities(sdm_ctx* c, int replica, double* v) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = md_check(c, replica)) return rc;
     if (!v) return fail(SDM_ERR_INVALID, "null argument");
     SDM_CUDA(cudaMemcpyAsync(v, c->d_vel + (size_t)replica * 3 * c->n, sizeof(double) * 3 * (size_t)c->n,
@@ -991,6 +1154,7 @@ int sdm_md_get_velocities(sdm_ctx* c, int replica, double* v) {
 }
 
 int sdm_get_positions(sdm_ctx* c, int replica, double* xyz) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
     if (!xyz) return fail(SDM_ERR_INVALID, "null argument");
     SDM_CUDA(cudaMemcpyAsync(xyz, c->d_pos + (size_t)replica * 3 * c->n, sizeof(double) * 3 * (size_t)c->n,
@@ -1000,6 +1164,7 @@ int sdm_get_positions(sdm_ctx* c, int replica, double* xyz) {
 }
 
 int sdm_md_set_noise(sdm_ctx* c, const double* xi_all) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = md_check(c, 0)) return rc;
     c->md_noise_pending = xi_all != nullptr;
     if (xi_all) {
@@ -1010,36 +1175,74 @@ int sdm_md_set_noise(sdm_ctx* c, const double* xi_all) {
     return SDM_OK;
 }
 
-static void md_enqueue_update(sdm_ctx* c) {
-    sdm::launch_langevin_fp64(c->n, c->R, c->d_pos, c->d_vel, c->B.F, c->d_invm, c->md_vscale, c->md_fscale,
-                              c->md_noisescale, c->md_dt, c->md_noise_pending ? c->d_noise : nullptr,
-                              c->md_seed, c->md_steps, c->stream);
+// One Langevin update (+ constraints) of all replicas at step number c->md_steps.  guarded: the
+// kernels obey the control words (a stale list reported by this step's evaluation turns the update
+// into a no-op); sdm_md_update passes false, it integrates whatever force it is given.
+static void md_enqueue_update(sdm_ctx* c, bool guarded) {
+    sdm::launch_md_update(c->n, c->R, c->d_pos, c->d_vel, c->B.F, c->d_invm, c->md_vscale, c->md_fscale,
+                          c->md_noisescale, c->md_dt, c->md_noise_pending ? c->d_noise : nullptr, c->md_seed,
+                          c->md_steps, &c->mdc, c->d_xprime, guarded ? c->d_md_ctl : nullptr, c->B.flags, c->stream);
     c->md_noise_pending = false;
     c->md_steps++;
-    c->launches++;
+    c->launches += (c->mdc.n_settle + c->mdc.n_shake) > 0 ? 2 : 1;
 }
 
 int sdm_md_update(sdm_ctx* c, const double* forces_all) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = md_check(c, 0)) return rc;
     if (forces_all)
         SDM_CUDA(cudaMemcpyAsync(c->B.F, forces_all, sizeof(double) * 3 * (size_t)c->n * c->R,
                                  cudaMemcpyHostToDevice, c->stream));
-    md_enqueue_update(c);
+    md_enqueue_update(c, false);
     SDM_CUDA(cudaGetLastError());
     return SDM_OK;
 }
 
 int sdm_md_step(sdm_ctx* c, int nsteps) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = md_check(c, 0)) return rc;
-    for (int k = 0; k < nsteps; k++) {
-        if (int rc = sdm_eval(c)) return rc;   // hybrid force of every replica at the current positions
-        md_enqueue_update(c);                  // positions and velocities advance on the device
+    if (nsteps <= 0) return SDM_OK;
+    const unsigned long long target = c->md_steps + (unsigned long long)nsteps;
+    const int chunk = std::max(1, c->opt.nstlist > 0 ? c->opt.nstlist : 20);
+    int futile = 0;   // consecutive chunks that did not advance at all
+    while (c->md_steps < target) {
+        const unsigned long long start = c->md_steps;
+        const int todo = (int)std::min<unsigned long long>(target - start, (unsigned long long)chunk);
+        for (int k = 0; k < todo; k++) {
+            if (int rc = sdm_eval(c)) return rc;   // hybrid force of every replica at the current positions
+            md_enqueue_update(c, true);            // positions and velocities advance on the device
+        }
+        // how far did the device get?  ([0] stale list / capacity, [1] steps taken, [2] constraints)
+        SDM_CUDA(cudaMemcpyAsync(c->h_md_ctl, c->d_md_ctl, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                 c->stream));
+        SDM_CUDA(cudaMemcpyAsync(c->h_state, c->B.state, sizeof(sdm::ReplicaState) * (size_t)c->R,
+                                 cudaMemcpyDeviceToHost, c->stream));
+        SDM_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->h_md_ctl[2] != 0ull) {
+            c->md_steps = c->h_md_ctl[1];
+            return fail(SDM_ERR_CONSTRAINT, "a constraint cluster did not converge (step size too large?)");
+        }
+        if (c->h_md_ctl[0] == 0ull) continue;   // all of them taken
+        // the evaluation of step h_md_ctl[1] reported a stale list / full scratch: that step and the
+        // ones behind it were not taken.  Rebuild / grow (note_status), clear the flags, go again.
+        const unsigned long long taken = c->h_md_ctl[1];
+        c->md_repeated += start + (unsigned long long)todo - taken;
+        c->md_steps = taken;
+        for (int r = 0; r < c->R; r++) note_status(c, c->h_state[r].sc.status);
+        c->list_valid = false;
+        SDM_CUDA(cudaMemsetAsync(c->d_md_ctl, 0, sizeof(unsigned long long), c->stream));
+        SDM_CUDA(cudaMemsetAsync(c->d_sticky, 0, sizeof(int) * (size_t)c->R, c->stream));
+        futile = taken == start ? futile + 1 : 0;
+        if (futile >= 3)
+            return fail(SDM_ERR_STALE_LIST, "a freshly built pair list goes stale within one step: "
+                                            "skin too small for this step size");
     }
     SDM_CUDA(cudaGetLastError());
     return SDM_OK;
 }
 
 int sdm_md_kinetic_energy(sdm_ctx* c, int replica, double* ke) {
+    SDM_ON_CTX_DEVICE(c);
     if (int rc = md_check(c, replica)) return rc;
     if (!ke) return fail(SDM_ERR_INVALID, "null argument");
     sdm::launch_kinetic_energy(c->n, c->R, c->d_vel, c->d_mass, c->d_ke, c->stream);

@@ -150,10 +150,16 @@ public:
         }
         check(sdm_set_positions(ctx, 0, positions));
         check(sdm_set_bonded_forces(ctx, 0, bondedForces, restraintEnergy));
-        check(sdm_set_alchemical(ctx, 0, &alch));
-        check(sdm_eval(ctx));
         sdm_scalars sc;
-        check(sdm_get_scalars(ctx, 0, &sc));
+        for (int attempt = 0; attempt < 4; attempt++) {
+            // SDM_ERR_STALE_LIST / SDM_ERR_CAPACITY heal themselves (sdmb200.h): reading the scalars
+            // made the library rebuild its list / grow its scratch; the evaluation is repeated from
+            // the same alchemical state.  The reference's force path never fails this way.
+            check(sdm_set_alchemical(ctx, 0, &alch));
+            check(sdm_eval(ctx));
+            check(sdm_get_scalars(ctx, 0, &sc));
+            if (sc.status != SDM_ERR_STALE_LIST && sc.status != SDM_ERR_CAPACITY) break;
+        }
         if (sc.status == SDM_ERR_SOFTCORE) throw SDMException("Unknown soft core method");
         if (sc.status != SDM_OK) throw SDMException("libsdmb200 status " + std::to_string(sc.status));
         BindE = sc.bind_e;

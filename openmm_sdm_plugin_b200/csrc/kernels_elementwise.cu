@@ -144,50 +144,6 @@ int grid_for(int n, int per_thread) {
     return (int)(want > cap ? cap : want);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Device-resident Langevin update in FP64 on the fused path's own buffers ([R][n][3] doubles),
-// the Reference-platform algorithm without constraints
-// (platforms/reference/src/ReferenceStochasticDynamicsSDM.cpp:131-266):
-//   v  = vscale*v + fscale*invm*F + noisescale*sqrt(invm)*xi        (updatePart1, :156-162)
-//   x' = x + dt*v                                                   (updatePart2, :196-200)
-//   v  = (1/dt)*(x' - x);  x = x'                                    (update, :256-262)
-// evaluated with the reference's operation order and without FMA contraction, so that with the
-// same forces and the same normals the result is bit-identical.  xi comes from `noise` when given
-// (test hook) and from a Philox4x32-10 stream keyed by (seed, atom, step) otherwise.  Massless
-// particles (invm == 0) do not move.  120 B/atom of traffic: HBM bound.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-langevin_fp64_kernel(int n, int total, double* __restrict__ pos, double* __restrict__ vel,
-                     const double* __restrict__ force, const double* __restrict__ invm,
-                     double vscale, double fscale, double noisescale, double dt, double inv_dt,
-                     const double* __restrict__ noise, unsigned long long seed, unsigned long long step) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // replica*n + atom
-    if (i >= total) return;
-    const double im = invm[i % n];
-    if (im == 0.0) return;
-    const double sim = sqrt(im);
-    double xi[3];
-    if (noise) {
-        xi[0] = noise[3 * (size_t)i]; xi[1] = noise[3 * (size_t)i + 1]; xi[2] = noise[3 * (size_t)i + 2];
-    } else {
-        curandStatePhilox4_32_10_t st;
-        // two curand_normal2_double calls consume 8 32-bit outputs of the atom's subsequence per step
-        curand_init(seed, (unsigned long long)i, 8ull * step, &st);
-        const double2 a = curand_normal2_double(&st), b = curand_normal2_double(&st);
-        xi[0] = a.x; xi[1] = a.y; xi[2] = b.x;
-    }
-    const double fi = __dmul_rn(fscale, im), ns = __dmul_rn(noisescale, sim);
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        const size_t k = 3 * (size_t)i + d;
-        const double x = pos[k];
-        const double v = __dadd_rn(__dadd_rn(__dmul_rn(vscale, vel[k]), __dmul_rn(fi, force[k])), __dmul_rn(ns, xi[d]));
-        const double xp = __dadd_rn(x, __dmul_rn(dt, v));
-        vel[k] = __dmul_rn(inv_dt, __dsub_rn(xp, x));
-        pos[k] = xp;
-    }
-}
-
 // 0.5 * sum m v^2 per replica (ReferenceSDMKernels.cpp:105-137 without constraints); one block per
 // replica, fixed-order reduction.
 __global__ void __launch_bounds__(256)
@@ -242,14 +198,6 @@ void launch_langevin_part2(int n, float4* posq, const float4* pos_delta, float4*
     langevin_part2_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(n, posq, pos_delta, velm, step_size);
 }
 
-void launch_langevin_fp64(int n, int R, double* pos, double* vel, const double* force, const double* invm,
-                          double vscale, double fscale, double noisescale, double dt, const double* noise,
-                          unsigned long long seed, unsigned long long step, cudaStream_t s) {
-    const int total = n * R;
-    if (total <= 0) return;
-    langevin_fp64_kernel<<<(total + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        n, total, pos, vel, force, invm, vscale, fscale, noisescale, dt, 1.0 / dt, noise, seed, step);
-}
 void launch_kinetic_energy(int n, int R, const double* vel, const double* mass, double* ke, cudaStream_t s) {
     if (R <= 0) return;
     kinetic_energy_kernel<<<R, 256, 0, s>>>(n, vel, mass, ke);

@@ -820,7 +820,14 @@ scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div) {
     if (threadIdx.x == 0) {
         ReplicaState* st = B.state + r;
         sdm_scalars* sc = &st->sc;
-        sc->status = B.flags[r];
+        // sticky status: the first stale-list / capacity report since the host last looked survives
+        // later evaluations; a device-resident MD loop is told to stop advancing the state
+        int status = B.flags[r];
+        if (status != 0 && B.sticky[r] == 0) B.sticky[r] = status;
+        if (B.sticky[r] != 0) status = B.sticky[r];
+        if (B.md_ctl && (status == SDM_ERR_STALE_LIST || status == SDM_ERR_CAPACITY || status == SDM_ERR_CONSTRAINT))
+            B.md_ctl[0] = 1ull;
+        sc->status = status;
         sc->E1_pair = ep * e_scale;
         sc->E1_exc = ee;
         sc->E1_disp = T.e_disp;

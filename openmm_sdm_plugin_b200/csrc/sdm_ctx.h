@@ -64,6 +64,17 @@ struct sdm_ctx {
     double* d_noise = nullptr;          // [R][n][3] explicit normals for the next update (test hook)
     double* d_ke = nullptr;             // [R] kinetic energies
     bool md_noise_pending = false;
+    // distance constraints of the MD loop (sdm_md_set_constraints)
+    std::vector<int> h_cons_pairs;
+    std::vector<double> h_cons_dist;
+    double cons_tol = 1e-5;
+    sdm::MdConstraints mdc{};           // device tables
+    double* d_xprime = nullptr;         // [R][n][3] unconstrained new positions of the clustered atoms
+    unsigned long long* d_md_ctl = nullptr;   // [0] abort flag, [1] steps taken
+    unsigned long long* h_md_ctl = nullptr;   // pinned read-back
+    unsigned long long md_repeated = 0;
+    int* d_sticky = nullptr;            // [R] sticky status (see EvalBuffers::sticky)
+    int* h_sticky = nullptr;            // pinned [R]
     double md_dt = 0, md_vscale = 0, md_fscale = 0, md_noisescale = 0;
     unsigned long long md_seed = 0, md_steps = 0;
 

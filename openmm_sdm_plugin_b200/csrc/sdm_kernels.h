@@ -26,6 +26,10 @@ struct EvalBuffers {
     long long* mcnt;        // [R][n_lig][2] moved-pair counts (x2) per displaced atom
     ReplicaState* state;    // [R]
     int* flags;             // [R] status raised by kernels of this eval (0 = ok); cleared by mix
+    int* sticky;            // [R] first non-zero status since the host last read the scalars: pipelined
+                            //     evaluations and multi-step MD calls cannot lose a stale-list report
+    unsigned long long* md_ctl;  // device-resident MD: [0] raised on a stale list / capacity status,
+                            //     [1] steps taken (kernels_md.cu); nullptr without sdm_md_init
     int n_excpart;
     int nslot;              // stride of f1acc planes (>= n)
     const int* slot_of;     // [R][n] atom -> accumulator slot, or nullptr for identity
@@ -84,9 +88,27 @@ void launch_langevin_part1(int n, float4* velm, const float4* force, float4* pos
                            unsigned random_index, cudaStream_t s);
 void launch_langevin_part2(int n, float4* posq, const float4* pos_delta, float4* velm, float step_size,
                            cudaStream_t s);
-void launch_langevin_fp64(int n, int R, double* pos, double* vel, const double* force, const double* invm,
-                          double vscale, double fscale, double noisescale, double dt, const double* noise,
-                          unsigned long long seed, unsigned long long step, cudaStream_t s);
+// Distance constraints of the device-resident Langevin step (kernels_md.cu): device tables shared
+// by all replicas.  Rigid three-site molecules (SETTLE) and small clusters (SHAKE).
+struct MdConstraints {
+    int n_settle, n_shake;
+    const int* settle_atoms;         // [3*n_settle] apex, b, c
+    const double* settle_par;        // [2*n_settle] d(apex,b) = d(apex,c), d(b,c)
+    const int* shake_off;            // [n_shake+1] constraint range of every cluster
+    const int* shake_ij;             // [2*ncons]
+    const double* shake_d;           // [ncons]
+    const int* shake_aoff;           // [n_shake+1] atom range of every cluster
+    const int* shake_atoms;          // atoms of the clusters
+    const unsigned char* in_cluster; // [n] 1: the atom is finished by the constraint kernel
+    double tol;                      // relative tolerance (Integrator::getConstraintTolerance, 1e-5)
+};
+// One Langevin step of all replicas: part 1 + 2 per atom, then the constraint units.  ctl[0] != 0
+// (raised by the scalar stage on SDM_ERR_STALE_LIST / SDM_ERR_CAPACITY) turns the step into a no-op;
+// ctl[1] receives step + 1 when the step is really taken.
+void launch_md_update(int n, int R, double* pos, double* vel, const double* force, const double* invm,
+                      double vscale, double fscale, double noisescale, double dt, const double* noise,
+                      unsigned long long seed, unsigned long long step, const MdConstraints* C,
+                      double* xprime, unsigned long long* ctl, int* flags, cudaStream_t s);
 void launch_kinetic_energy(int n, int R, const double* vel, const double* mass, double* ke, cudaStream_t s);
 
 }  // namespace sdm

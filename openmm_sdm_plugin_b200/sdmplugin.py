@@ -15,6 +15,8 @@ from __future__ import annotations
 
 import os
 
+import copy
+
 import numpy as np
 
 from . import _lib
@@ -178,8 +180,16 @@ class LangevinIntegratorSDM(object):
         c.set_positions(0, np.ascontiguousarray(positions, np.float64))
         c.set_bonded_forces(0, bonded_forces, float(restraint_energy))
         c.set_alchemical(0, self._a)
-        c.eval()
-        sc = c.scalars(0)
+        alch0 = copy.copy(self._a)
+        for attempt in range(4):
+            c.eval()
+            sc = c.scalars(0)
+            # SDM_ERR_STALE_LIST / SDM_ERR_CAPACITY heal themselves (include/sdmb200.h): reading the
+            # scalars made the library rebuild its list / grow its scratch, the evaluation is repeated
+            # from the same alchemical state.  The reference's force path never fails this way.
+            if sc["status"] not in (_lib.SDM_ERR_STALE_LIST, _lib.SDM_ERR_CAPACITY):
+                break
+            c.set_alchemical(0, alch0)
         if sc["status"] == _lib.SDM_ERR_SOFTCORE:
             raise OpenMMException("Unknown soft core method")     # LangevinIntegratorSDM.cpp:147
         if sc["status"] != 0:

@@ -94,6 +94,8 @@ class SDMCase:
     alch: AlchemicalState
     velocities: np.ndarray | None = None
     masses: np.ndarray | None = None
+    constraint_pairs: np.ndarray | None = None   # [nc,2] System.addConstraint pairs (desmonddmsfile75.py:560-637)
+    constraint_dist: np.ndarray | None = None    # [nc] nm
 
 
 def _load(name):
@@ -123,7 +125,8 @@ def cfg1() -> SDMCase:
                          lambdac=0.025, lambda1=0.025, lambda2=0.025, alpha=0.0, u0=0.0,
                          w0coeff=0.0, umax=100.0 * KCAL, ubcore=50.0 * KCAL, acore=0.0625)
     return SDMCase("cfg1_oa_g6_g3", sysd, z["positions"].copy(), disp, al,
-                   z["velocities"].copy(), z["masses"].copy())
+                   z["velocities"].copy(), z["masses"].copy(),
+                   z["constraint_pairs"].copy(), z["constraint_dist"].copy())
 
 
 def cfg2() -> SDMCase:
@@ -142,7 +145,8 @@ def cfg2() -> SDMCase:
                          lambdac=0.5, lambda1=0.5, lambda2=0.5, alpha=0.0, u0=0.0,
                          w0coeff=0.0, umax=100.0 * KCAL, ubcore=50.0 * KCAL, acore=0.0625)
     return SDMCase("cfg2_temoa_g1_g4_rf", sysd, z["positions"].copy(), disp, al,
-                   z["velocities"].copy(), z["masses"].copy())
+                   z["velocities"].copy(), z["masses"].copy(),
+                   z["constraint_pairs"].copy(), z["constraint_dist"].copy())
 
 
 def atm_lambda_schedule(n_windows: int = 22):

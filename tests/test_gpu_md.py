@@ -123,3 +123,110 @@ def test_philox_noise_has_the_right_temperature_and_is_reproducible():
         b = ctx.md_velocities(0)
     corr = (a * b).mean() / (a * a).mean()
     assert corr == pytest.approx(np.exp(-50.0 * 0.001), abs=0.03)
+
+
+# ---- distance constraints (sdm_md_set_constraints): SETTLE waters + SHAKE clusters -----------------
+from oracle import constraints as OC   # noqa: E402
+
+
+def _thermal(case, seed):
+    rng = np.random.default_rng(seed)
+    n = case.system.n_atoms
+    kT = 1.380658e-23 * 6.0221367e23 / 1000.0 * T
+    v = rng.normal(size=(n, 3)) * np.sqrt(kT / case.masses)[:, None]
+    return rng, v
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_constrained_update_matches_the_constraint_oracle(name):
+    """One update with given forces and normals: part 1 + 2 are the reference's expressions, the
+    constraint stage must land where the tightly converged oracle lands (SHAKE clusters to the
+    integrator's 1e-5 tolerance, SETTLE waters to rounding), ReferenceStochasticDynamicsSDM.cpp:250-262."""
+    case = getattr(S, name)()
+    n = case.system.n_atoms
+    rng, vel = _thermal(case, 21)
+    f = rng.normal(scale=300.0, size=(n, 3))
+    xi = rng.normal(size=(n, 3))
+    dt = 0.001
+    x_ref, v_ref, xp = OC.langevin_step(case.positions, vel, f, case.masses, T, GAMMA, dt, xi,
+                                        case.constraint_pairs, case.constraint_dist)
+    p, d0 = case.constraint_pairs, case.constraint_dist
+    with SDMContext(case.system, case.displacement, n_replicas=2, pair_mode=_lib.PAIR_CLUSTER) as ctx:
+        ctx.md_init(case.masses, T, GAMMA, dt, seed=1)
+        ctx.md_set_constraints(p, d0, 1e-5)
+        for r in range(2):
+            ctx.set_positions(r, case.positions)
+            ctx.set_alchemical(r, case.alch)
+            ctx.md_set_velocities(r, vel)
+        ctx.md_set_noise(np.stack([xi, xi]))
+        ctx.md_update(np.stack([f, f]))
+        for r in range(2):
+            x, v = ctx.positions(r), ctx.md_velocities(r)
+            d = np.linalg.norm(x[p[:, 0]] - x[p[:, 1]], axis=1)
+            assert np.abs(d / d0 - 1).max() < 1.01e-5
+            assert np.abs(x - x_ref).max() < 3e-6                       # nm
+            assert np.abs(v - v_ref).max() < 3e-6 / dt
+            assert np.allclose(v, (x - case.positions) / dt, rtol=0, atol=1e-9)
+            # atoms outside every cluster went through the unconstrained expressions exactly
+            free = np.ones(n, bool)
+            free[p.ravel()] = False
+            assert np.array_equal(x[free], xp[free])
+            # rigid waters: hydrogen pairs constrained to each other -> SETTLE, exact to rounding
+            anum = np.load(S.GOLDEN_DIR + "/%s.npz" % ("cfg1_oa_g6_g3" if name == "cfg1" else "cfg2_temoa_g1_g4"))["anum"]
+            hh = (anum[p[:, 0]] == 1) & (anum[p[:, 1]] == 1)
+            if hh.any():
+                assert np.abs(d[hh] / d0[hh] - 1).max() < 1e-11
+                wat = np.unique(p[hh].ravel())
+                assert np.abs(x[wat] - x_ref[wat]).max() < 1e-10
+
+
+def test_constrained_dynamics_of_the_explicit_solvent_fixture():
+    """cfg2 with its real masses, thermal velocities and all 20 278 constraints, 40 steps of 1 fs on
+    the device (Philox noise): constraints hold to the tolerance, the kinetic temperature stays
+    thermal, every step was taken."""
+    case = S.cfg2()
+    n = case.system.n_atoms
+    _, vel = _thermal(case, 5)
+    p, d0 = case.constraint_pairs, case.constraint_dist
+    kT = 1.380658e-23 * 6.0221367e23 / 1000.0 * T
+    with SDMContext(case.system, case.displacement, n_replicas=2, pair_mode=_lib.PAIR_CLUSTER) as ctx:
+        ctx.md_init(case.masses, T, GAMMA, 0.001, seed=9)
+        ctx.md_set_constraints(p, d0, 1e-5)
+        for r in range(2):
+            ctx.set_positions(r, case.positions)
+            ctx.set_alchemical(r, case.alch)
+            ctx.md_set_velocities(r, vel)
+        ctx.md_step(40)
+        taken, repeated = ctx.md_counters()
+        assert taken == 40
+        for r in range(2):
+            assert ctx.scalars(r)["status"] == 0
+            x = ctx.positions(r)
+            d = np.linalg.norm(x[p[:, 0]] - x[p[:, 1]], axis=1)
+            assert np.abs(d / d0 - 1).max() < 1.01e-5
+            ke = ctx.md_kinetic_energy(r)
+            t_kin = 2.0 * ke / ((3 * n - len(d0)) * kT) * T
+            assert 200.0 < t_kin < 400.0, t_kin
+        assert not np.array_equal(ctx.positions(0), ctx.positions(1))      # replicas draw different noise
+
+
+def test_stale_list_steps_are_repeated_not_integrated():
+    """A skin far too small for the list lifetime: the list goes stale inside sdm_md_step, the
+    affected steps are not taken, the list is rebuilt and they are repeated -- the trajectory is the
+    one a comfortable skin gives (forces are independent of the list: exact cutoff, fixed point)."""
+    case = S.synthetic_case(6000, 30, seed=8)
+    n = case.system.n_atoms
+    _, vel = _thermal(case, 6)
+    out = {}
+    for tag, skin, nstlist in (("wide", 0.16, 8), ("tight", 0.012, 200)):
+        with SDMContext(case.system, case.displacement, n_replicas=1, pair_mode=_lib.PAIR_CLUSTER,
+                        skin=skin, nstlist=nstlist) as ctx:
+            ctx.md_init(case.masses, T, GAMMA, 0.001, seed=4)
+            ctx.set_positions(0, case.positions)
+            ctx.set_alchemical(0, case.alch)
+            ctx.md_set_velocities(0, vel)
+            ctx.md_step(60)
+            out[tag] = (ctx.positions(0), ctx.md_counters(), ctx.info("n_list_builds"))
+    assert out["wide"][1] == (60, 0)
+    assert out["tight"][1][0] == 60 and out["tight"][1][1] > 0
+    assert np.abs(out["tight"][0] - out["wide"][0]).max() < 1e-9

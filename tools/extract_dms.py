@@ -71,6 +71,41 @@ def extract(dms_path):
     es = {(min(a, b), max(a, b)) for a, b in excl.tolist()}
     assert all((min(a, b), max(a, b)) in es for a, b in exc_pairs.tolist())
 
+    # distance constraints, in the order the reference's reader adds them to the System
+    # (desmonddmsfile75.py:542-571 constrained stretches, :573-596 constrained angles -> a 1-3
+    # distance, :603-637 constraint_a* rows that are not bonds, constraint_hoh -> the H-H distance)
+    cons, bonds, angle_c = [], {}, set()
+    if "stretch_harm_term" in tables:
+        q = """SELECT p0, p1, r0, fc, constrained FROM stretch_harm_term INNER JOIN stretch_harm_param
+               ON stretch_harm_term.param=stretch_harm_param.id"""
+        for p0, p1, r0, fc, constrained in conn.execute(q):
+            if constrained:
+                cons.append((p0, p1, r0 * ANG))
+            bonds[(p0, p1)] = bonds[(p1, p0)] = r0 * ANG
+    if "angle_harm_term" in tables:
+        q = """SELECT p0, p1, p2, theta0, fc, constrained FROM angle_harm_term INNER JOIN angle_harm_param
+               ON angle_harm_term.param=angle_harm_param.id"""
+        for p0, p1, p2, theta0, fc, constrained in conn.execute(q):
+            if constrained:
+                l1, l2 = bonds[(p1, p0)], bonds[(p1, p2)]
+                cons.append((p0, p2, float(np.sqrt(l1 * l1 + l2 * l2 - 2 * l1 * l2 * np.cos(np.deg2rad(theta0))))))
+                angle_c.add((p1, p0, p2))
+    for t in sorted(n for n in tables if n.startswith("constraint_a") and n.endswith("term")):
+        q = "SELECT p0, p1, r1 FROM %s INNER JOIN %s ON %s.param=%s.id" % (t, t.replace("term", "param"), t, t.replace("term", "param"))
+        for p0, p1, r1 in conn.execute(q):
+            if (p0, p1) not in bonds:
+                cons.append((p0, p1, r1 * ANG))
+                bonds[(p0, p1)] = bonds[(p1, p0)] = r1 * ANG
+    if "constraint_hoh_term" in tables:
+        q = """SELECT p0, p1, p2, r1, r2, theta FROM constraint_hoh_term INNER JOIN constraint_hoh_param
+               ON constraint_hoh_term.param=constraint_hoh_param.id"""
+        for p0, p1, p2, r1, r2, theta in conn.execute(q):
+            if (p0, p1, p2) not in angle_c:
+                r1, r2 = r1 * ANG, r2 * ANG
+                cons.append((p1, p2, float(np.sqrt(r1 * r1 + r2 * r2 - 2 * r1 * r2 * np.cos(np.deg2rad(theta))))))
+    cons_pairs = np.array([(a, b) for a, b, _ in cons], dtype=np.int32).reshape(-1, 2)
+    cons_dist = np.array([d for _, _, d in cons], dtype=np.float64)
+
     box = np.zeros(3)
     if "global_cell" in tables:
         cell = conn.execute("SELECT x, y, z FROM global_cell ORDER BY id").fetchall()
@@ -79,7 +114,8 @@ def extract(dms_path):
     conn.close()
     return dict(positions=pos, velocities=vel, masses=mass, resid=resid, anum=anum,
                 charge=charge, sigma=sigma, epsilon=epsilon, exclusions=excl,
-                exception_pairs=exc_pairs, exception_params=exc_params, box=box)
+                exception_pairs=exc_pairs, exception_params=exc_params, box=box,
+                constraint_pairs=cons_pairs, constraint_dist=cons_dist)
 
 
 def main():
@@ -90,7 +126,7 @@ def main():
         d = extract(os.path.join(REF, src))
         np.savez_compressed(os.path.join(OUT, dst), **d)
         print(dst, "atoms", len(d["charge"]), "excl", len(d["exclusions"]),
-              "exc", len(d["exception_pairs"]), "box", d["box"],
+              "exc", len(d["exception_pairs"]), "constraints", len(d["constraint_dist"]), "box", d["box"],
               "bytes", os.path.getsize(os.path.join(OUT, dst)))
 
 
