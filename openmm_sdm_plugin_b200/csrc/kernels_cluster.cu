@@ -141,7 +141,7 @@ __device__ __forceinline__ float pair_term_f32(const float r2, const float qi, c
 // One tile step of the hot loop: i-atoms (ci, ti) and (ci, ti+4) against the lane's j atom.
 //   dE/dr * r  and energy (OpenMM 7.3 ReferenceLJCoulombIxn, reaction field, LJ not shifted):
 //   e_lj = elj*(sr6 - 1) = a - elj,   elj*(12*sr6 - 6) = 6*(a + e_lj)   with a = elj*sr6
-template <bool MASKED, bool EXACT, bool EMIT>
+template <bool MASKED, bool EXACT, bool EMIT, int HI_OFF = 4>
 __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const float4 xj,
                                           const float2 pj, const bool allow_lo, const bool allow_hi,
                                           const PairConsts& K, Acc2& fi, Acc2& fj, f2& en, int& cnt,
@@ -161,7 +161,7 @@ __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const fl
     if (EXACT) tmin = fminf(tmin, fminf(fabsf(t_lo), fabsf(t_hi)));
     if (EMIT) {   // pairs inside the band are recorded by the fix-up path, which re-decides them
         if (in_lo && !(EXACT && fabsf(t_lo) < K.band)) emit_pair(*ec, islot_lo, jslot);
-        if (in_hi && !(EXACT && fabsf(t_hi) < K.band)) emit_pair(*ec, islot_lo + 4, jslot);
+        if (in_hi && !(EXACT && fabsf(t_hi) < K.band)) emit_pair(*ec, islot_lo + HI_OFF, jslot);
     }
     const f2 rinv = pk(rsqrt_approx(lo(r2)), rsqrt_approx(hi(r2)));
     const f2 rinv2 = mul2(rinv, rinv);
@@ -530,6 +530,294 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row kernel (the product kernel): one warp per work unit = an i-group of NI = 8 or 16 atoms (one
+// or two clusters) and a chunk of its ROW of individual j-atoms (nblist_core.h stage 5).  Lane =
+// j-atom: every step the warp takes the next 32 row entries, each lane fetches its own j-atom
+// (position + image shift, parameters) and evaluates it against all NI i-atoms, two at a time in
+// packed f32x2 registers, with the same tile_step arithmetic as above.  The i-atoms are staged
+// once per unit in shared memory as NI/2 (even, odd) pairs and read by broadcast LDS.128.
+//   * i forces: NI*3 packed partial sums per lane for the whole unit, transpose-reduced over the
+//     32 lanes once per unit;
+//   * j force: complete in the lane after the NI/2 tile steps -- no shuffle -- and added with three
+//     64-bit fixed-point REDs (row entries of one j-cluster sit in neighbouring lanes, so a warp
+//     RED touches few sectors);
+//   * row entries two steps ahead and j-atom data one step ahead are requested before the current
+//     step's arithmetic, so the gathers overlap the FP32 work of the same warp;
+//   * masked entries (exclusions, the cluster against itself) come first in a row: only the first
+//     ceil(mend / 32) steps take the masked path and load allow words.
+// Lanes past the end of the row hold a far-away dummy atom.  Exact cutoff and the debug pair record
+// work as in the cluster kernel, per lane: a lane that saw |r^2 - rc^2| inside the band in step k
+// re-decides its NI pairs of that step in FP64 after the loop.
+// ---------------------------------------------------------------------------------------------
+#ifndef SDM_ROW_MINB
+#define SDM_ROW_MINB 20
+#endif
+
+template <int NI, bool EMIT>
+__device__ __noinline__ void fix_band_row(const Topology& T, const PairListView& V,
+                                          const double* __restrict__ pos_all,
+                                          long long* __restrict__ f1acc, const IPair* s_ip, int ibase,
+                                          int jslot, float4 xj, float2 pj, uint32_t allow, float* en,
+                                          int* cnt, const EmitCtx* ec) {
+    const size_t plane = (size_t)V.nslot_cap;
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
+    const int aj = V.atom[jslot];
+    if (aj < 0) return;
+    for (int a = 0; a < NI; a++) {
+        if (!((allow >> a) & 1u)) continue;
+        const IPair ip = s_ip[a >> 1];
+        const int h = a & 1;
+        const float xi = h ? hi(ip.x) : lo(ip.x), yi = h ? hi(ip.y) : lo(ip.y);
+        const float zi = h ? hi(ip.z) : lo(ip.z), qi = h ? hi(ip.q) : lo(ip.q);
+        const float si = h ? hi(ip.s) : lo(ip.s), ei = h ? hi(ip.e) : lo(ip.e);
+        float dx, dy, dz;
+        const float r2 = pair_r2(xi, yi, zi, xj, dx, dy, dz);
+        const float t = r2 - K.rc2;
+        if (!(fabsf(t) < K.band)) continue;
+        const int islot = ibase + a;
+        const int ai = V.atom[islot];
+        if (ai < 0) continue;
+        const int r = ai / T.n;
+        const bool in64 = in_cutoff_f64(T, pos_all + (size_t)r * 3 * T.n, ai - r * T.n, aj - r * T.n);
+        const bool in32 = t <= 0.f;
+        if (EMIT && in64) emit_pair(*ec, islot, jslot);
+        if (in64 == in32) continue;
+        const float sgn = in64 ? 1.f : -1.f;
+        float e;
+        const float fs = sgn * pair_term_f32(r2, qi, si, ei, xj.w, pj, K, e);
+        *en += sgn * e;
+        *cnt += in64 ? 1 : -1;
+        const float f[3] = {fs * dx, fs * dy, fs * dz};
+        for (int c = 0; c < 3; c++) {
+            const long long v = __float2ll_rn(f[c] * kFix);
+            atomic_add_fixed(f1acc + (size_t)c * plane + islot, v);
+            atomic_add_fixed(f1acc + (size_t)c * plane + jslot, -v);
+        }
+    }
+}
+
+// Sum of v[0..N) over the 32 lanes by halving: after the exchange with lane^W every lane keeps the
+// half of the values its bit selects.  Ends with 3 values per lane (one atom's x, y, z), which the
+// remaining lanes of the atom's group share through a butterfly.
+template <int N, int W>
+__device__ __forceinline__ void row_halve(float (&v)[N], const int lane) {
+    const bool up = (lane & W) != 0;
+#pragma unroll
+    for (int k = 0; k < N / 2; k++) {
+        const float send = up ? v[k] : v[k + N / 2];
+        v[k] = (up ? v[k + N / 2] : v[k]) + __shfl_xor_sync(0xffffffffu, send, W);
+    }
+}
+
+template <int NI, bool PERIODIC, bool EXACT, bool EMIT>
+__device__ __forceinline__ void process_row_unit(const Topology& T, const PairListView& V,
+                                                 const double* __restrict__ pos_all,
+                                                 long long* __restrict__ f1acc, double* __restrict__ epart,
+                                                 long long* __restrict__ cpart, const int unit,
+                                                 const int lane, IPair* s_ip, const float4* s_shift,
+                                                 const EmitCtx* ec) {
+    constexpr int NP = NI / 2;
+    const RowUnit u = V.runits[unit];
+    const int ibase = (u.c0n & 0xfffffff) * nbl::kClusterSize;
+    const int ni = (u.c0n >> 28) * nbl::kClusterSize;
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
+    const uint32_t dummy_ent = (uint32_t)V.dummy_slot | (nbl::kShiftZero << 26);
+
+    // row entries two steps ahead, j-atom data one step ahead
+    const int nsteps = (u.end - u.begin + 31) >> 5;
+    const int msteps = (u.mend - u.begin + 31) >> 5;
+    int idx = u.begin + lane;
+    uint32_t ent1 = idx < u.end ? V.jent[idx] : dummy_ent;
+    uint32_t ent2 = idx + 32 < u.end ? V.jent[idx + 32] : dummy_ent;
+
+    // stage the i-atoms: atom a goes to half (a & 1) of pair a >> 1
+    if (lane < NI) {
+        float4 q = make_float4(-nbl::kFar, -nbl::kFar, -nbl::kFar, 0.f);
+        float2 pr = make_float2(0.f, 0.f);
+        if (lane < ni) {
+            const float4 g = V.posq[ibase + lane];
+            if (g.x < 0.5f * nbl::kFar) { q = g; pr = V.par[ibase + lane]; }
+        }
+        float* dst = reinterpret_cast<float*>(s_ip + (lane >> 1)) + (lane & 1);
+        dst[0] = q.x; dst[2] = q.y; dst[4] = q.z; dst[6] = q.w; dst[8] = pr.x; dst[10] = pr.y;
+    }
+    float4 xj1 = V.posq[ent1 & 0x3ffffffu];
+    float2 pj1 = V.par[ent1 & 0x3ffffffu];
+    __syncwarp();
+
+    Acc2 fi[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) fi[p] = Acc2{0ull, 0ull, 0ull};
+    f2 en = 0ull;
+    int cnt = 0;
+    uint32_t fixmask = 0u;
+    const size_t plane = (size_t)V.nslot_cap;
+
+    for (int k = 0; k < nsteps; k++, idx += 32) {
+        const uint32_t ent = ent1;
+        float4 xj = xj1;
+        const float2 pj = pj1;
+        ent1 = ent2;
+        ent2 = idx + 64 < u.end ? V.jent[idx + 64] : dummy_ent;
+        xj1 = V.posq[ent1 & 0x3ffffffu];
+        pj1 = V.par[ent1 & 0x3ffffffu];
+        const int jslot = (int)(ent & 0x3ffffffu);
+        if (PERIODIC) {
+            const float4 sh = s_shift[ent >> 26];
+            xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
+        }
+        Acc2 fj{0ull, 0ull, 0ull};
+        float tmin = 3.0e38f;
+        if (k < msteps) {
+            const uint32_t allow = idx < u.mend ? (uint32_t)V.jallow[idx] : 0xffffu;
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+                tile_step<true, EXACT, EMIT, 1>(s_ip + p, xj, pj, ((allow >> (2 * p)) & 1u) != 0u,
+                                                ((allow >> (2 * p + 1)) & 1u) != 0u, K, fi[p], fj, en, cnt,
+                                                tmin, ec, ibase + 2 * p, jslot);
+        } else {
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+                tile_step<false, EXACT, EMIT, 1>(s_ip + p, xj, pj, true, true, K, fi[p], fj, en, cnt, tmin, ec,
+                                                 ibase + 2 * p, jslot);
+        }
+        if (EXACT) fixmask |= (tmin < K.band ? 1u : 0u) << k;
+        // j force: complete in this lane (sign: F_j = -sum)
+        long long* fjp = f1acc + jslot;
+        red_fixed_nonzero(fjp, lo(fj.x) + hi(fj.x), -kFix);
+        red_fixed_nonzero(fjp + plane, lo(fj.y) + hi(fj.y), -kFix);
+        red_fixed_nonzero(fjp + 2 * plane, lo(fj.z) + hi(fj.z), -kFix);
+    }
+
+    // i forces: v[3*a + d] of atom a, summed over the lanes
+    {
+        float v[3 * NI];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            v[6 * p + 0] = lo(fi[p].x); v[6 * p + 1] = lo(fi[p].y); v[6 * p + 2] = lo(fi[p].z);
+            v[6 * p + 3] = hi(fi[p].x); v[6 * p + 4] = hi(fi[p].y); v[6 * p + 5] = hi(fi[p].z);
+        }
+        // halving stages pick the atom by the high lane bits; what is left is one atom per lane group
+        if constexpr (NI == 16) {
+            float a24[24], a12[12], a6[6];
+            row_halve<48, 16>(v, lane);
+#pragma unroll
+            for (int k = 0; k < 24; k++) a24[k] = v[k];
+            row_halve<24, 8>(a24, lane);
+#pragma unroll
+            for (int k = 0; k < 12; k++) a12[k] = a24[k];
+            row_halve<12, 4>(a12, lane);
+#pragma unroll
+            for (int k = 0; k < 6; k++) a6[k] = a12[k];
+            row_halve<6, 2>(a6, lane);
+            float w[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) w[d] = a6[d] + __shfl_xor_sync(0xffffffffu, a6[d], 1);
+            const int atom = lane >> 1;   // lane 0 of the pair writes x and y, lane 1 writes z
+            if (atom < ni) {
+                long long* fp = f1acc + ibase + atom;
+                if ((lane & 1) == 0) {
+                    red_fixed_nonzero(fp, w[0], kFix);
+                    red_fixed_nonzero(fp + plane, w[1], kFix);
+                } else {
+                    red_fixed_nonzero(fp + 2 * plane, w[2], kFix);
+                }
+            }
+        } else {
+            float a12[12], a6[6];
+            row_halve<24, 16>(v, lane);
+#pragma unroll
+            for (int k = 0; k < 12; k++) a12[k] = v[k];
+            row_halve<12, 8>(a12, lane);
+#pragma unroll
+            for (int k = 0; k < 6; k++) a6[k] = a12[k];
+            row_halve<6, 4>(a6, lane);
+            float w[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                w[d] = a6[d] + __shfl_xor_sync(0xffffffffu, a6[d], 2);
+                w[d] += __shfl_xor_sync(0xffffffffu, w[d], 1);
+            }
+            const int atom = lane >> 2, comp = lane & 3;
+            if (atom < ni && comp < 3)
+                red_fixed_nonzero(f1acc + (size_t)comp * plane + ibase + atom,
+                                  comp == 0 ? w[0] : comp == 1 ? w[1] : w[2], kFix);
+        }
+    }
+
+    float en1 = lo(en) + hi(en);
+    if (EXACT && fixmask) {
+        float en_fix = 0.f;   // separate variables: their address is taken by the call
+        int cnt_fix = 0;
+        while (fixmask) {
+            const int k = __ffs(fixmask) - 1;
+            fixmask &= fixmask - 1u;
+            const int id = u.begin + 32 * k + lane;
+            const uint32_t fe = V.jent[id];
+            const int js = (int)(fe & 0x3ffffffu);
+            float4 xj = V.posq[js];
+            if (PERIODIC) {
+                const float4 sh = s_shift[fe >> 26];
+                xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
+            }
+            const uint32_t allow = id < u.mend ? (uint32_t)V.jallow[id] : 0xffffu;
+            fix_band_row<NI, EMIT>(T, V, pos_all, f1acc, s_ip, ibase, js, xj, V.par[js], allow, &en_fix, &cnt_fix, ec);
+        }
+        en1 += en_fix;
+        cnt += cnt_fix;
+    }
+    __syncwarp();
+
+    // energy / count partials of this unit (fixed-order warp tree)
+    double de = (double)en1;
+    int dc = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        de += __shfl_down_sync(0xffffffffu, de, o);
+        dc += __shfl_down_sync(0xffffffffu, dc, o);
+    }
+    if (lane == 0) {
+        epart[unit] = de;
+        cpart[unit] = dc;
+    }
+    __syncwarp();   // the staging area is reused by the next unit of this warp
+}
+
+template <int NI, bool PERIODIC, bool EXACT, bool EMIT>
+__global__ void __launch_bounds__(kWarps * 32, NI == 16 ? 16 : SDM_ROW_MINB)
+pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
+                const double* __restrict__ pos_all, long long* __restrict__ f1acc,
+                double* __restrict__ epart, long long* __restrict__ cpart, int* unit_counter,
+                const __grid_constant__ PairEmit em) {
+    __shared__ IPair s_ip[kWarps][NI / 2];
+    __shared__ float4 s_shift[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (PERIODIC) {
+        for (uint32_t code = threadIdx.x; code < 64; code += kWarps * 32)
+            s_shift[code] = make_float4((float)nbl::shift_x(code) * T.boxf[0],
+                                        (float)nbl::shift_y(code) * T.boxf[1],
+                                        (float)nbl::shift_z(code) * T.boxf[2], 0.f);
+        __syncthreads();
+    }
+    EmitCtx ec_store;
+    const EmitCtx* ec = nullptr;
+    if (EMIT) {
+        ec_store.em = em;
+        ec_store.atom = V.atom;
+        ec_store.n = T.n;
+        ec = &ec_store;
+    }
+    for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(unit_counter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= V.nrunits) break;
+        process_row_unit<NI, PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp],
+                                                    s_shift, ec);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // refresh: sorted float positions from the current double positions, keeping the periodic image
 // chosen at build time; raises SDM_ERR_STALE_LIST when an atom moved more than skin/2.
 // ---------------------------------------------------------------------------------------------
@@ -597,6 +885,46 @@ void launch_pair_cluster(const Topology& T, const PairListView& V, const double*
         if (periodic) SDM_LAUNCH(true, false, false);
         else SDM_LAUNCH(false, false, false);
     }
+#undef SDM_LAUNCH
+}
+
+void launch_pair_rows(const Topology& T, const PairListView& V, const double* pos_all,
+                      long long* f1acc, double* epart, long long* cpart, int exact,
+                      int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s) {
+    if (V.nrunits <= 0) return;
+    cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
+    const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
+    const PairEmit em = emit ? *emit : PairEmit{nullptr, nullptr, 0, -1};
+#define SDM_LAUNCH(N, P, X, E)                                                                    \
+    do {                                                                                          \
+        static int resident = 0; /* blocks per SM the hardware keeps resident (register limited) */ \
+        if (!resident) {                                                                          \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_row_kernel<N, P, X, E>, \
+                                                              kWarps * 32, 0) != cudaSuccess ||    \
+                resident < 1)                                                                     \
+                resident = SDM_ROW_MINB;                                                          \
+            if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
+        }                                                                                         \
+        const int grid = std::min((V.nrunits + kWarps - 1) / kWarps, num_sms * resident);          \
+        pair_row_kernel<N, P, X, E><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
+                                                                unit_counter, em);                \
+    } while (0)
+#define SDM_LAUNCH_N(P, X, E)                                                                     \
+    do {                                                                                          \
+        if (V.row_group == 2) SDM_LAUNCH(16, P, X, E);                                            \
+        else SDM_LAUNCH(8, P, X, E);                                                              \
+    } while (0)
+    if (emit) {   // debug build of the same kernel: records the accepted pairs
+        if (exact) { if (periodic) SDM_LAUNCH_N(true, true, true); else SDM_LAUNCH_N(false, true, true); }
+        else { if (periodic) SDM_LAUNCH_N(true, false, true); else SDM_LAUNCH_N(false, false, true); }
+    } else if (exact) {
+        if (periodic) SDM_LAUNCH_N(true, true, false);
+        else SDM_LAUNCH_N(false, true, false);
+    } else {
+        if (periodic) SDM_LAUNCH_N(true, false, false);
+        else SDM_LAUNCH_N(false, false, false);
+    }
+#undef SDM_LAUNCH_N
 #undef SDM_LAUNCH
 }
 

@@ -50,6 +50,21 @@ struct PairList {
     int *raw_flag = nullptr, *raw_sci = nullptr, *raw_c0nci = nullptr, *raw_keep = nullptr, *raw_pos = nullptr;
     size_t raw_cap = 0;
     int nraw = 0;
+    // per-atom j rows (nblist_core.h stage 5): the list the product kernel walks
+    int use_rows = 1;           // 0: the cluster kernel walks the entries (SDMB200_PAIR_KERNEL=cluster)
+    int row_group = 1;          // clusters per i-group (SDMB200_ROW_GROUP = 1 | 2)
+    int row_chunk = nbl::kRowChunkSteps;   // warp steps per unit (SDMB200_ROW_CHUNK)
+    uint2 *raw_jhit = nullptr, *entry_jhit = nullptr;   // per (cluster of the sci, j-atom) hit bits of an entry
+    int *row_cnt = nullptr, *row_scan = nullptr;        // [2 * (8 / G) * nentries + 1] masked / unmasked counts
+    size_t row_cnt_cap = 0;
+    uint32_t* jent = nullptr;
+    uint16_t* jallow = nullptr;
+    size_t jent_cap = 0;
+    int *row_nunits = nullptr, *row_unit_off = nullptr; // [nsci * (8 / G) + 1]
+    RowUnit* runits = nullptr;
+    size_t runits_cap = 0;
+    int njent = 0, nrunits = 0;
+    int dummy_slot = 0;
     int* sci_off = nullptr;     // [nsci+1] first (compacted) entry of every sci
     uint32_t* masks = nullptr;
     int *sci_nunits = nullptr, *sci_unit_off = nullptr;
@@ -297,7 +312,8 @@ __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
 // nbl::prune_imask.  Lane (tj, ti) = (lane>>2, lane&3) tests j-atom tj against i-atoms ti, ti+4.
 __global__ void __launch_bounds__(128)
 prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ raw_c0nci,
-             int* __restrict__ raw_flag, const float4* __restrict__ posq, int* __restrict__ keep) {
+             int* __restrict__ raw_flag, const float4* __restrict__ posq, int* __restrict__ keep,
+             uint2* __restrict__ jhit) {
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (e >= nraw) return;
@@ -312,6 +328,7 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
     xj.y += (float)nbl::shift_y(code) * G.boxf[1];
     xj.z += (float)nbl::shift_z(code) * G.boxf[2];
     uint32_t todo = ent.y & 0xffu, out = 0u;
+    uint32_t jh_lo = 0u, jh_hi = 0u;   // per cluster of the sci: which j-atoms have an i-atom within rlist
     while (todo) {
         const int ci = __ffs(todo) - 1;
         todo &= todo - 1u;
@@ -324,9 +341,16 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
             dx = b.x - xj.x; dy = b.y - xj.y; dz = b.z - xj.z;
             hit = hit || (b.x < 0.5f * nbl::kFar && dx * dx + dy * dy + dz * dz < G.rlist2);
         }
-        if (__any_sync(0xffffffffu, hit)) out |= 1u << ci;
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            out |= 1u << ci;
+            const uint32_t h8 = nbl::compress_nibbles(bal);
+            if (ci < 4) jh_lo |= h8 << (8 * ci);
+            else jh_hi |= h8 << (8 * (ci - 4));
+        }
     }
     if (lane == 0) {
+        jhit[e] = make_uint2(jh_lo, jh_hi);
         raw[e].y = out;
         keep[e] = out != 0u;
         // the diagonal flag needs the self tile, which always survives while the cluster has atoms
@@ -337,12 +361,13 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
 __global__ void compact_kernel(int nraw, const uint2* __restrict__ raw, const int* __restrict__ raw_flag,
                                const int* __restrict__ raw_sci, const int* __restrict__ keep,
                                const int* __restrict__ pos, uint2* entries, int* entry_flag,
-                               int* entry_sci, int cap) {
+                               int* entry_sci, int cap, const uint2* __restrict__ raw_jhit, uint2* entry_jhit) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nraw || !keep[e]) return;
     const int k = pos[e];
     if (k >= cap) return;
     entries[k] = raw[e];
+    entry_jhit[k] = raw_jhit[e];
     entry_flag[k] = raw_flag[e];
     entry_sci[k] = raw_sci[e];
 }
@@ -403,6 +428,145 @@ __global__ void mask_init_kernel(int nentries, const int* __restrict__ entry_fla
         if (code == nbl::kShiftZero && cj == sd.c0 + (w >> 1)) m = nbl::triangle_mask(w & 1);
         masks[(size_t)midx * nbl::kMaskWords + w] = m;
     }
+}
+
+// ---- per-atom j rows (nblist_core.h stage 5) -----------------------------------------------------
+// The counts of all (entry, i-group) cells of a supercluster are laid out [group][masked | unmasked]
+// [entry of the sci], so ONE exclusive scan over the whole array yields, in order, every row's
+// masked entries followed by its unmasked ones, rows in cluster order.
+struct RowCell {
+    size_t base;       // index of (group 0, masked, entry 0 of the sci) in the count array
+    int len, k;        // entries of the sci, this entry's rank among them
+    uint32_t imask;
+    const uint32_t* maskset;
+    bool same_sci;
+    uint2 jh;
+};
+
+__device__ __forceinline__ RowCell row_cell(int e, int ng, const uint2* __restrict__ entries,
+                                            const uint2* __restrict__ jhit, const int* __restrict__ entry_sci,
+                                            const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
+                                            const uint32_t* __restrict__ masks, uint2* ent_out) {
+    RowCell c;
+    const int s = entry_sci[e];
+    const int e0 = sci_off[s];
+    const uint2 ent = entries[e];
+    const SciDesc sd = sci[s];
+    const int B = (int)(ent.x & 0x3ffffffu);
+    c.base = (size_t)e0 * 2 * ng;
+    c.len = sci_off[s + 1] - e0;
+    c.k = e - e0;
+    c.imask = ent.y & 0xffu;
+    c.maskset = (ent.y >> 8) ? masks + (size_t)(ent.y >> 8) * nbl::kMaskWords : nullptr;
+    c.same_sci = B >= sd.c0 && B < sd.c0 + sd.nci;
+    c.jh = jhit[e];
+    *ent_out = ent;
+    return c;
+}
+
+__global__ void rows_count_kernel(int nentries, int G, const uint2* __restrict__ entries,
+                                  const uint2* __restrict__ jhit, const int* __restrict__ entry_sci,
+                                  const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
+                                  const uint32_t* __restrict__ masks, int* __restrict__ cnt) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nentries) return;
+    const int ng = nbl::kMaxCi / G;
+    const uint32_t full = G == 2 ? 0xffffu : 0xffu;
+    uint2 ent;
+    const RowCell c = row_cell(e, ng, entries, jhit, entry_sci, sci, sci_off, masks, &ent);
+    for (int g = 0; g < ng; g++) {
+        int cm = 0, cu = 0;
+        uint32_t hits = nbl::row_hits(c.jh.x, c.jh.y, c.imask, g, G);
+        while (hits) {
+            const int tj = __ffs(hits) - 1;
+            hits &= hits - 1u;
+            const uint32_t allow = nbl::row_allow(c.maskset, c.imask, c.same_sci, g, G, tj);
+            if (allow == 0u) continue;
+            if (allow == full) cu++; else cm++;
+        }
+        cnt[c.base + (size_t)g * 2 * c.len + c.k] = cm;
+        cnt[c.base + (size_t)g * 2 * c.len + c.len + c.k] = cu;
+    }
+}
+
+__global__ void rows_fill_kernel(int nentries, int G, const uint2* __restrict__ entries,
+                                 const uint2* __restrict__ jhit, const int* __restrict__ entry_sci,
+                                 const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
+                                 const uint32_t* __restrict__ masks, const int* __restrict__ scan,
+                                 uint32_t* __restrict__ jent, uint16_t* __restrict__ jallow, int cap) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nentries) return;
+    const int ng = nbl::kMaxCi / G;
+    const uint32_t full = G == 2 ? 0xffffu : 0xffu;
+    uint2 ent;
+    const RowCell c = row_cell(e, ng, entries, jhit, entry_sci, sci, sci_off, masks, &ent);
+    const uint32_t jbase = (ent.x & 0x3ffffffu) * nbl::kJGroup;
+    const uint32_t code = ent.x & ~0x3ffffffu;
+    for (int g = 0; g < ng; g++) {
+        int pm = scan[c.base + (size_t)g * 2 * c.len + c.k];
+        int pu = scan[c.base + (size_t)g * 2 * c.len + c.len + c.k];
+        uint32_t hits = nbl::row_hits(c.jh.x, c.jh.y, c.imask, g, G);
+        while (hits) {
+            const int tj = __ffs(hits) - 1;
+            hits &= hits - 1u;
+            const uint32_t allow = nbl::row_allow(c.maskset, c.imask, c.same_sci, g, G, tj);
+            if (allow == 0u) continue;
+            const int pos = allow == full ? pu++ : pm++;
+            if (pos < cap) {
+                jent[pos] = (jbase + (uint32_t)tj) | code;
+                jallow[pos] = (uint16_t)allow;
+            }
+        }
+    }
+}
+
+// row (s, g): [begin, mend) masked, [mend, end) unmasked entries; units of <= chunk steps
+__device__ __forceinline__ void row_bounds(int s, int g, int ng, const int* __restrict__ sci_off,
+                                           const int* __restrict__ scan, int* begin, int* mend, int* end) {
+    const int e0 = sci_off[s], len = sci_off[s + 1] - e0;
+    const size_t b = (size_t)e0 * 2 * ng + (size_t)g * 2 * len;
+    *begin = scan[b];
+    *mend = scan[b + len];
+    *end = scan[b + 2 * (size_t)len];
+}
+
+__global__ void rows_units_count_kernel(int nsci, int ng, int chunk, const int* __restrict__ sci_off,
+                                        const int* __restrict__ scan, int* __restrict__ row_nunits) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsci * ng) return;
+    int b, m, e;
+    row_bounds(t / ng, t % ng, ng, sci_off, scan, &b, &m, &e);
+    row_nunits[t] = (e - b + 32 * chunk - 1) / (32 * chunk);
+}
+
+__global__ void rows_units_fill_kernel(int nsci, int ng, int G, int chunk, const SciDesc* __restrict__ sci,
+                                       const int* __restrict__ sci_off, const int* __restrict__ scan,
+                                       const int* __restrict__ row_unit_off, RowUnit* __restrict__ units, int cap) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsci * ng) return;
+    const int s = t / ng, g = t % ng;
+    int b, m, e;
+    row_bounds(s, g, ng, sci_off, scan, &b, &m, &e);
+    const SciDesc sd = sci[s];
+    const int ncl = min(G, sd.nci - g * G);
+    int u = row_unit_off[t];
+    for (int x = b; x < e; x += 32 * chunk, u++)
+        if (u < cap) units[u] = RowUnit{(sd.c0 + g * G) | (ncl << 28), x, min(x + 32 * chunk, e), max(x, min(m, x + 32 * chunk))};
+}
+
+__global__ void rows_part_off_kernel(Grid G, int ng, const int* __restrict__ cell_sci,
+                                     const int* __restrict__ row_unit_off, int nsci, int* part_off) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > G.R) return;
+    const int s = r == G.R ? nsci : min(cell_sci[r * G.ncell], nsci);
+    part_off[r] = row_unit_off[(size_t)s * ng];
+}
+
+__global__ void dummy_slot_kernel(int slot, float4* posq, float4* posq_build, float2* par, int* atom, int* img) {
+    posq[slot] = posq_build[slot] = make_float4(nbl::kFar, nbl::kFar, nbl::kFar, 0.f);
+    par[slot] = make_float2(0.f, 0.f);
+    atom[slot] = -1;
+    img[slot] = 512 | (512 << 10) | (512 << 20);
 }
 
 __global__ void sci_units_count_kernel(int nsci, const int* __restrict__ sci_off, int chunk, int* sci_nunits) {
@@ -467,6 +631,66 @@ int setup_grid(sdm_ctx* c, PairList* pl, const double lo[3], const double ext[3]
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// per-atom j rows from the final entries + exclusion masks (nblist_core.h stage 5)
+// ---------------------------------------------------------------------------------------------
+static int build_rows(sdm_ctx* c) {
+    PairList* pl = c->pl;
+    cudaStream_t s = c->stream;
+    const int G = pl->row_group, ng = nbl::kMaxCi / G;
+    const size_t ncnt = (size_t)pl->nentries * 2 * ng;
+    const int nrows = pl->nsci * ng;
+    if (ncnt + 1 > (size_t)0x7fffffff) return sdm_fail(SDM_ERR_CAPACITY, "pair list too large for the row scan");
+    if (ncnt + 1 > pl->row_cnt_cap) {
+        pl->row_cnt_cap = (size_t)(ncnt * 1.25) + 1024;
+        if (int rc = pl_realloc(pl, &pl->row_cnt, pl->row_cnt_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->row_scan, pl->row_cnt_cap)) return rc;
+    }
+    {
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, pl->row_cnt, pl->row_scan, (int)(ncnt + 1), s);
+        if (need > pl->cub_tmp_bytes) {
+            if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
+            pl->cub_tmp_bytes = need;
+        }
+    }
+    if (pl->nentries > 0)
+        rows_count_kernel<<<blocks(pl->nentries, 128), 128, 0, s>>>(pl->nentries, G, pl->entries, pl->entry_jhit,
+                                                                   pl->entry_sci, pl->sci, pl->sci_off, pl->masks,
+                                                                   pl->row_cnt);
+    PL_CUDA(cudaMemsetAsync(pl->row_cnt + ncnt, 0, sizeof(int), s));
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->row_cnt, pl->row_scan, (int)(ncnt + 1), s));
+    rows_units_count_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, pl->row_chunk, pl->sci_off, pl->row_scan,
+                                                         pl->row_nunits);
+    PL_CUDA(cudaMemsetAsync(pl->row_nunits + nrows, 0, sizeof(int), s));
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->row_nunits, pl->row_unit_off, nrows + 1, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[6], pl->row_scan + ncnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[7], pl->row_unit_off + nrows, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+    pl->njent = pl->h_counts[6];
+    pl->nrunits = pl->h_counts[7];
+    if ((size_t)pl->njent > pl->jent_cap) {
+        pl->jent_cap = (size_t)(pl->njent * 1.25) + 4096;
+        if (int rc = pl_realloc(pl, &pl->jent, pl->jent_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->jallow, pl->jent_cap)) return rc;
+    }
+    if ((size_t)pl->nrunits > pl->runits_cap) {
+        pl->runits_cap = (size_t)(pl->nrunits * 1.25) + 256;
+        if (int rc = pl_realloc(pl, &pl->runits, pl->runits_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->epart, pl->runits_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->cpart, pl->runits_cap)) return rc;
+    }
+    if (pl->nentries > 0)
+        rows_fill_kernel<<<blocks(pl->nentries, 128), 128, 0, s>>>(pl->nentries, G, pl->entries, pl->entry_jhit,
+                                                                  pl->entry_sci, pl->sci, pl->sci_off, pl->masks,
+                                                                  pl->row_scan, pl->jent, pl->jallow, (int)pl->jent_cap);
+    rows_units_fill_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, G, pl->row_chunk, pl->sci, pl->sci_off,
+                                                        pl->row_scan, pl->row_unit_off, pl->runits, (int)pl->runits_cap);
+    rows_part_off_kernel<<<blocks(c->R + 1), 256, 0, s>>>(pl->G, ng, pl->cell_sci, pl->row_unit_off, pl->nsci, pl->part_off);
+    c->launches += 7;
+    return SDM_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // build
@@ -588,6 +812,7 @@ static int build_list(sdm_ctx* c) {
         if (int rc = pl_realloc(pl, &pl->raw_flag, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_sci, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_c0nci, pl->raw_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->raw_jhit, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_keep, pl->raw_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_pos, pl->raw_cap + 1)) return rc;
     }
@@ -597,7 +822,7 @@ static int build_list(sdm_ctx* c) {
     // exact prune (one warp per raw entry), then order-preserving compaction
     if (nraw > 0)
         prune_kernel<<<blocks((long long)nraw * 32, 128), 128, 0, s>>>(G, nraw, pl->raw_entries, pl->raw_c0nci,
-                                                                      pl->raw_flag, pl->posq, pl->raw_keep);
+                                                                      pl->raw_flag, pl->posq, pl->raw_keep, pl->raw_jhit);
     PL_CUDA(cudaMemsetAsync(pl->raw_keep + nraw, 0, sizeof(int), s));
     if (int rc = ensure_cub((size_t)nraw + 1)) return rc;
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->raw_keep, pl->raw_pos, nraw + 1, s));
@@ -610,11 +835,12 @@ static int build_list(sdm_ctx* c) {
         if (int rc = pl_realloc(pl, &pl->entry_flag, pl->entries_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_midx, pl->entries_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_sci, pl->entries_cap + 1)) return rc;
+        if (int rc = pl_realloc(pl, &pl->entry_jhit, pl->entries_cap + 1)) return rc;
     }
     if (nraw > 0)
         compact_kernel<<<blocks(nraw), 256, 0, s>>>(nraw, pl->raw_entries, pl->raw_flag, pl->raw_sci, pl->raw_keep,
                                                    pl->raw_pos, pl->entries, pl->entry_flag, pl->entry_sci,
-                                                   (int)pl->entries_cap);
+                                                   (int)pl->entries_cap, pl->raw_jhit, pl->entry_jhit);
     sci_off_kernel<<<blocks(pl->nsci + 1), 256, 0, s>>>(pl->nsci, noff, nraw, pl->item_off, pl->raw_pos, pl->sci_off);
     c->launches += 7;
 
@@ -627,12 +853,15 @@ static int build_list(sdm_ctx* c) {
     if (int rc = ensure_cub((size_t)pl->nentries + 1)) return rc;
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->entry_flag, pl->entry_midx, pl->nentries + 1, s));
     PL_CUDA(cudaMemcpyAsync(&pl->h_counts[3], pl->entry_midx + pl->nentries, sizeof(int), cudaMemcpyDeviceToHost, s));
-    // units
-    if (const char* e = getenv("SDMB200_CHUNK")) pl->chunk = std::min(kChunk, std::max(1, atoi(e)));   // development knob
-    sci_units_count_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_nunits);
-    PL_CUDA(cudaMemsetAsync(pl->sci_nunits + pl->nsci, 0, sizeof(int), s));
-    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->sci_nunits, pl->sci_unit_off, pl->nsci + 1, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[4], pl->sci_unit_off + pl->nsci, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // units of the cluster kernel (only when it is selected; the row kernel has its own below)
+    pl->h_counts[4] = 0;
+    if (!pl->use_rows) {
+        if (const char* e = getenv("SDMB200_CHUNK")) pl->chunk = std::min(kChunk, std::max(1, atoi(e)));   // development knob
+        sci_units_count_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_nunits);
+        PL_CUDA(cudaMemsetAsync(pl->sci_nunits + pl->nsci, 0, sizeof(int), s));
+        PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->sci_nunits, pl->sci_unit_off, pl->nsci + 1, s));
+        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[4], pl->sci_unit_off + pl->nsci, sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
     PL_CUDA(cudaStreamSynchronize(s));
     pl->nmasks = pl->h_counts[3];
     pl->nunits = pl->h_counts[4];
@@ -640,7 +869,7 @@ static int build_list(sdm_ctx* c) {
         pl->masks_cap = (size_t)(pl->nmasks * 1.25) + 256;
         if (int rc = pl_realloc(pl, &pl->masks, pl->masks_cap * nbl::kMaskWords)) return rc;
     }
-    if ((size_t)pl->nunits > pl->units_cap) {
+    if (!pl->use_rows && (size_t)pl->nunits > pl->units_cap) {
         pl->units_cap = (size_t)(pl->nunits * 1.25) + 256;
         if (int rc = pl_realloc(pl, &pl->units, pl->units_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->epart, pl->units_cap)) return rc;
@@ -655,8 +884,12 @@ static int build_list(sdm_ctx* c) {
         exclusion_kernel<<<blocks((long long)R * pl->n_excl), 256, 0, s>>>(
             G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->sci_off, pl->entries,
             pl->entry_flag, pl->masks, 1);
-    units_fill_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_unit_off, pl->units);
-    part_off_kernel<<<blocks(R + 1), 256, 0, s>>>(G, pl->cell_sci, pl->sci_unit_off, pl->nsci, pl->nunits, pl->part_off);
+    if (pl->use_rows) {
+        if (int rc = build_rows(c)) return rc;
+    } else {
+        units_fill_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_unit_off, pl->units);
+        part_off_kernel<<<blocks(R + 1), 256, 0, s>>>(G, pl->cell_sci, pl->sci_unit_off, pl->nsci, pl->nunits, pl->part_off);
+    }
     PL_CUDA(cudaMemcpyAsync(pl->posq_build, pl->posq, sizeof(float4) * (size_t)pl->nslot, cudaMemcpyDeviceToDevice, s));
     c->launches += 7;
     PL_CUDA(cudaGetLastError());
@@ -752,15 +985,39 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->raw_flag, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_sci, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_c0nci, pl->raw_cap));
+    A(pl_alloc(pl, &pl->raw_jhit, pl->raw_cap));
+    A(pl_alloc(pl, &pl->entry_jhit, pl->entries_cap + 1));
     A(pl_alloc(pl, &pl->raw_keep, pl->raw_cap + 1));
     A(pl_alloc(pl, &pl->raw_pos, pl->raw_cap + 1));
     A(pl_alloc(pl, &pl->sci_off, pl->nsci_cap + 2));
     pl->masks_cap = (size_t)total / 2 + 256;
     A(pl_alloc(pl, &pl->masks, pl->masks_cap * nbl::kMaskWords));
+    if (const char* e = getenv("SDMB200_PAIR_KERNEL")) pl->use_rows = std::string(e) != "cluster";   // development knob
+    if (const char* e = getenv("SDMB200_ROW_GROUP")) pl->row_group = atoi(e) == 2 ? 2 : 1;            // development knob
+    if (const char* e = getenv("SDMB200_ROW_CHUNK")) pl->row_chunk = std::min(nbl::kRowChunkSteps, std::max(1, atoi(e)));
     pl->units_cap = pl->entries_cap / 8 + 256;
     A(pl_alloc(pl, &pl->units, pl->units_cap));
-    A(pl_alloc(pl, &pl->epart, pl->units_cap));
-    A(pl_alloc(pl, &pl->cpart, pl->units_cap));
+    if (pl->use_rows) {
+        const int ng = nbl::kMaxCi / pl->row_group;
+        pl->row_cnt_cap = pl->entries_cap * 2 * ng + 1;
+        A(pl_alloc(pl, &pl->row_cnt, pl->row_cnt_cap));
+        A(pl_alloc(pl, &pl->row_scan, pl->row_cnt_cap));
+        A(pl_alloc(pl, &pl->row_nunits, (size_t)pl->nsci_cap * ng + 1));
+        A(pl_alloc(pl, &pl->row_unit_off, (size_t)pl->nsci_cap * ng + 1));
+        // ~50 row entries per atom at 100 atoms/nm^3 and rlist 1.06 nm; grown on demand
+        pl->jent_cap = (size_t)total * 64 + 4096;
+        A(pl_alloc(pl, &pl->jent, pl->jent_cap));
+        A(pl_alloc(pl, &pl->jallow, pl->jent_cap));
+        pl->runits_cap = pl->jent_cap / 256 + (size_t)pl->nsci_cap * ng + 256;
+        A(pl_alloc(pl, &pl->runits, pl->runits_cap));
+        A(pl_alloc(pl, &pl->epart, pl->runits_cap));
+        A(pl_alloc(pl, &pl->cpart, pl->runits_cap));
+        pl->dummy_slot = pl->nslot_cap - 1;   // never a real slot: nslot <= nslot_cap - 8
+        dummy_slot_kernel<<<1, 1, 0, c->stream>>>(pl->dummy_slot, pl->posq, pl->posq_build, pl->par, pl->atom, pl->img);
+    } else {
+        A(pl_alloc(pl, &pl->epart, pl->units_cap));
+        A(pl_alloc(pl, &pl->cpart, pl->units_cap));
+    }
     {
         // unique exclusion pairs a<b from the CSR the ctx already holds
         std::vector<int> ex;
@@ -818,6 +1075,12 @@ static PairListView make_view(const sdm_ctx* c) {
     V.units = pl->units;
     V.nunits = pl->nunits;
     V.nslot_cap = pl->nslot_cap;
+    V.jent = pl->jent;
+    V.jallow = pl->jallow;
+    V.runits = pl->runits;
+    V.nrunits = pl->nrunits;
+    V.row_group = pl->row_group;
+    V.dummy_slot = pl->dummy_slot;
     return V;
 }
 
@@ -860,8 +1123,9 @@ int sdm_ctx_pairlist_launch(sdm_ctx* c) {
     cudaStream_t s = c->stream;
     // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
-    launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
-                        pl->unit_counter, c->num_sms, nullptr, s);
+    (pl->use_rows ? launch_pair_rows : launch_pair_cluster)(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart,
+                                                            pl->cpart, c->opt.exact_cutoff, pl->unit_counter,
+                                                            c->num_sms, nullptr, s);
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[2], s));
     c->launches++;
     PL_CUDA(cudaGetLastError());
@@ -874,8 +1138,9 @@ int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs,
     // the debug build of the hot kernel itself: same list, same code, plus the pair records.  It adds
     // its forces to the accumulators a second time; they are cleared before the next evaluation.
     const PairEmit em{d_counter, d_pairs, cap, replica};
-    launch_pair_cluster(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
-                        pl->unit_counter, c->num_sms, &em, c->stream);
+    (pl->use_rows ? launch_pair_rows : launch_pair_cluster)(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart,
+                                                            pl->cpart, c->opt.exact_cutoff, pl->unit_counter,
+                                                            c->num_sms, &em, c->stream);
     PL_CUDA(cudaStreamSynchronize(c->stream));
     return SDM_OK;
 }
@@ -890,7 +1155,9 @@ int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "n_entries") *value = pl->nentries;
     else if (k == "n_raw_entries") *value = pl->nraw;
     else if (k == "n_masks") *value = pl->nmasks;
-    else if (k == "n_units") *value = pl->nunits;
+    else if (k == "n_units") *value = pl->use_rows ? pl->nrunits : pl->nunits;
+    else if (k == "n_row_entries") *value = pl->njent;
+    else if (k == "row_group") *value = pl->use_rows ? pl->row_group : 0;
     else if (k == "n_cells") *value = pl->G.ncell;
     else if (k == "cell_span") *value = pl->G.span;
     else if (k == "layout_columns") *value = pl->G.columns;

@@ -14,6 +14,14 @@ struct Unit {
     int pad;
 };
 
+// Work unit of the row kernel: an i-group and a chunk (<= 32 warp steps) of its row of j-atoms.
+struct RowUnit {
+    int c0n;      // first cluster of the i-group | clusters in it (1..2) << 28
+    int begin;    // first row entry (global index into jent)
+    int end;      // one past the last
+    int mend;     // entries [begin, mend) carry an allow word (exclusions / triangle)
+};
+
 // Everything the pair kernel reads.
 struct PairListView {
     nbl::Grid G;
@@ -26,6 +34,13 @@ struct PairListView {
     const Unit* units;           // [nunits]
     int nunits;
     int nslot_cap;               // accumulator plane stride
+    // per-atom j rows (the product kernel)
+    const uint32_t* jent;        // row entries: j slot | shift << 26
+    const uint16_t* jallow;      // allow word per row entry (read for the masked prefix of a row only)
+    const RowUnit* runits;       // [nrunits]
+    int nrunits;
+    int row_group;               // clusters per i-group (1 or 2)
+    int dummy_slot;              // a slot that holds a far-away dummy atom (padding lanes)
 };
 
 // The pair kernel.  emit != nullptr selects the debug build of the SAME kernel, which also records
@@ -40,6 +55,10 @@ struct PairEmit {
 void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
                          long long* f1acc, double* epart, long long* cpart, int exact,
                          int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s);
+// The row kernel: same contract, walks V.runits / V.jent.
+void launch_pair_rows(const Topology& T, const PairListView& V, const double* pos_all,
+                      long long* f1acc, double* epart, long long* cpart, int exact,
+                      int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s);
 
 // Per-eval refresh of the sorted positions from the current double positions (same periodic
 // image as at build time) + staleness check against the build-time positions.
