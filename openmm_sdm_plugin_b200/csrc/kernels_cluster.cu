@@ -552,6 +552,15 @@ pair_cluster_kernel(const __grid_constant__ Topology T, const __grid_constant__ 
 #ifndef SDM_ROW_MINB
 #define SDM_ROW_MINB 20
 #endif
+#ifndef SDM_ROW_JPREFETCH
+#define SDM_ROW_JPREFETCH 1   // 1: j-atom data one step ahead (row entries two ahead); 0: entries one ahead only
+#endif
+#ifndef SDM_ROW_AHEAD
+#define SDM_ROW_AHEAD 0    // 1: unit index two ahead, descriptor one ahead
+#endif
+#ifndef SDM_ROW_STATIC
+#define SDM_ROW_STATIC 0   // 1: units dealt round-robin (longest first) instead of drawn from a counter
+#endif
 
 template <int NI, bool EMIT>
 __device__ __noinline__ void fix_band_row(const Topology& T, const PairListView& V,
@@ -614,10 +623,9 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
                                                  const double* __restrict__ pos_all,
                                                  long long* __restrict__ f1acc, double* __restrict__ epart,
                                                  long long* __restrict__ cpart, const int unit,
-                                                 const int lane, IPair* s_ip, const float4* s_shift,
-                                                 const EmitCtx* ec) {
+                                                 const RowUnit u, const int lane, IPair* s_ip,
+                                                 const float4* s_shift, const EmitCtx* ec) {
     constexpr int NP = NI / 2;
-    const RowUnit u = V.runits[unit];
     const int ibase = (u.c0n & 0xfffffff) * nbl::kClusterSize;
     const int ni = (u.c0n >> 28) * nbl::kClusterSize;
     const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
@@ -641,8 +649,10 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
         float* dst = reinterpret_cast<float*>(s_ip + (lane >> 1)) + (lane & 1);
         dst[0] = q.x; dst[2] = q.y; dst[4] = q.z; dst[6] = q.w; dst[8] = pr.x; dst[10] = pr.y;
     }
+#if SDM_ROW_JPREFETCH
     float4 xj1 = V.posq[ent1 & 0x3ffffffu];
     float2 pj1 = V.par[ent1 & 0x3ffffffu];
+#endif
     __syncwarp();
 
     Acc2 fi[NP];
@@ -655,12 +665,19 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
 
     for (int k = 0; k < nsteps; k++, idx += 32) {
         const uint32_t ent = ent1;
+#if SDM_ROW_JPREFETCH
         float4 xj = xj1;
         const float2 pj = pj1;
         ent1 = ent2;
         ent2 = idx + 64 < u.end ? V.jent[idx + 64] : dummy_ent;
         xj1 = V.posq[ent1 & 0x3ffffffu];
         pj1 = V.par[ent1 & 0x3ffffffu];
+#else
+        float4 xj = V.posq[ent & 0x3ffffffu];
+        const float2 pj = V.par[ent & 0x3ffffffu];
+        ent1 = ent2;
+        ent2 = idx + 64 < u.end ? V.jent[idx + 64] : dummy_ent;
+#endif
         const int jslot = (int)(ent & 0x3ffffffu);
         if (PERIODIC) {
             const float4 sh = s_shift[ent >> 26];
@@ -683,6 +700,9 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
         }
         if (EXACT) fixmask |= (tmin < K.band ? 1u : 0u) << k;
         // j force: complete in this lane (sign: F_j = -sum)
+        // a j-atom of the row that has no partner inside the cutoff (one in six: the list reaches to
+        // rc + skin) and the padding lanes stay silent; ptxas renders each predicated RED as a short
+        // branch region that also skips the 64-bit conversion
         long long* fjp = f1acc + jslot;
         red_fixed_nonzero(fjp, lo(fj.x) + hi(fj.x), -kFix);
         red_fixed_nonzero(fjp + plane, lo(fj.y) + hi(fj.y), -kFix);
@@ -807,14 +827,67 @@ pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ Pair
         ec_store.n = T.n;
         ec = &ec_store;
     }
+#if SDM_ROW_STATIC
+    // Static schedule: the units are ordered longest first and dealt round-robin to the resident
+    // warps, so every warp gets the same mix of lengths; no work counter, and the descriptor of the
+    // warp's next unit is requested a whole unit ahead (the chain atomic -> order -> descriptor ->
+    // row entries -> j-atoms at the start of a unit shrinks to the last two links).
+    const int nw = gridDim.x * kWarps;
+    int k = blockIdx.x * kWarps + warp;
+    if (k >= V.nrunits) return;
+    int unit = V.runit_order ? V.runit_order[k] : k;
+    RowUnit u = V.runits[unit];
+    for (;;) {
+        const int kn = k + nw;
+        int unit_n = 0;
+        RowUnit un = RowUnit{0, 0, 0, 0};
+        if (kn < V.nrunits) {
+            unit_n = V.runit_order ? V.runit_order[kn] : kn;
+            un = V.runits[unit_n];
+        }
+        process_row_unit<NI, PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, u, lane, s_ip[warp],
+                                                    s_shift, ec);
+        if (kn >= V.nrunits) break;
+        k = kn;
+        unit = unit_n;
+        u = un;
+    }
+#elif SDM_ROW_AHEAD
+    // Units are drawn from the work counter two ahead: the index of the unit after next is requested
+    // at the top of a unit and the descriptor of the next one (order -> descriptor, two dependent
+    // loads) is in flight while the current unit is computed, so a unit starts with its row entries.
+    int a2 = 0, i1 = 0;
+    if (lane == 0) { i1 = atomicAdd(unit_counter, 1); a2 = atomicAdd(unit_counter, 1); }
+    i1 = __shfl_sync(0xffffffffu, i1, 0);
+    int unit1 = 0;
+    RowUnit u1 = RowUnit{0, 0, 0, 0};
+    if (i1 < V.nrunits) {
+        unit1 = V.runit_order ? V.runit_order[i1] : i1;
+        u1 = V.runits[unit1];
+    }
+    while (i1 < V.nrunits) {
+        const RowUnit u = u1;
+        const int unit = unit1;
+        i1 = __shfl_sync(0xffffffffu, a2, 0);
+        if (lane == 0) a2 = atomicAdd(unit_counter, 1);
+        if (i1 < V.nrunits) {
+            unit1 = V.runit_order ? V.runit_order[i1] : i1;
+            u1 = V.runits[unit1];
+        }
+        process_row_unit<NI, PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, u, lane, s_ip[warp],
+                                                    s_shift, ec);
+    }
+#else
     for (;;) {
         int unit = 0;
         if (lane == 0) unit = atomicAdd(unit_counter, 1);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= V.nrunits) break;
-        process_row_unit<NI, PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, lane, s_ip[warp],
-                                                    s_shift, ec);
+        if (V.runit_order) unit = V.runit_order[unit];   // longest units first
+        process_row_unit<NI, PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, V.runits[unit], lane,
+                                                    s_ip[warp], s_shift, ec);
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -459,6 +459,35 @@ SDM_HD uint32_t prune_imask(const SearchView& V, const SciDesc& sd, uint32_t w0,
     return out;
 }
 
+// Per-cluster hit bytes of an entry (scalar form of what prune_kernel records next to the pruned
+// imask): bit tj of byte ci = j-atom tj of the entry's shifted j-cluster is closer than rlist to
+// some real atom of cluster c0+ci.  jh_lo holds clusters 0..3, jh_hi clusters 4..7.
+SDM_HD void entry_hits(const SearchView& V, const SciDesc& sd, uint32_t w0, uint32_t imask,
+                       uint32_t* jh_lo, uint32_t* jh_hi) {
+    const Grid& G = V.G;
+    const int B = (int)(w0 & 0x3ffffffu);
+    const uint32_t code = w0 >> 26;
+    const float sx = shift_x(code) * G.boxf[0], sy = shift_y(code) * G.boxf[1], sz = shift_z(code) * G.boxf[2];
+    *jh_lo = *jh_hi = 0u;
+    for (int ci = 0; ci < sd.nci; ci++) {
+        if (!((imask >> ci) & 1u)) continue;
+        uint32_t h8 = 0u;
+        for (int tj = 0; tj < kJGroup; tj++) {
+            const float* pj = V.posq4 + 4 * (size_t)(B * kJGroup + tj);
+            if (pj[0] >= 0.5f * kFar) continue;
+            const float xj = pj[0] + sx, yj = pj[1] + sy, zj = pj[2] + sz;
+            for (int ti = 0; ti < kClusterSize; ti++) {
+                const float* pi = V.posq4 + 4 * (size_t)((sd.c0 + ci) * kClusterSize + ti);
+                if (pi[0] >= 0.5f * kFar) continue;
+                const float dx = pi[0] - xj, dy = pi[1] - yj, dz = pi[2] - zj;
+                if (dx * dx + dy * dy + dz * dz < G.rlist2) { h8 |= 1u << tj; break; }
+            }
+        }
+        if (ci < 4) *jh_lo |= h8 << (8 * ci);
+        else *jh_hi |= h8 << (8 * (ci - 4));
+    }
+}
+
 // ---- stage 4: exclusion masks -------------------------------------------------------------------
 // Resolve an excluded atom pair (slots sa, sb) to (i-slot, j-slot) under the ownership rule.
 SDM_HD void exclusion_roles(int sa, int sb, int* si, int* sj) {

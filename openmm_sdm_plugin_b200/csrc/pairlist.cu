@@ -63,6 +63,9 @@ struct PairList {
     int *row_nunits = nullptr, *row_unit_off = nullptr; // [nsci * (8 / G) + 1]
     RowUnit* runits = nullptr;
     size_t runits_cap = 0;
+    int row_lpt = 1;            // draw the longest units first (SDMB200_ROW_LPT=0: list order)
+    uint32_t *ru_key = nullptr, *ru_key_sorted = nullptr;
+    int *ru_val = nullptr, *ru_order = nullptr;
     int njent = 0, nrunits = 0;
     int dummy_slot = 0;
     int* sci_off = nullptr;     // [nsci+1] first (compacted) entry of every sci
@@ -554,6 +557,15 @@ __global__ void rows_units_fill_kernel(int nsci, int ng, int G, int chunk, const
         if (u < cap) units[u] = RowUnit{(sd.c0 + g * G) | (ncl << 28), x, min(x + 32 * chunk, e), max(x, min(m, x + 32 * chunk))};
 }
 
+// sort key of a unit: longer units first; the radix sort is stable, so units of equal length keep
+// the list order (neighbouring i-clusters, which share their j-atoms in L1)
+__global__ void rows_unit_key_kernel(int nunits, const RowUnit* __restrict__ units, uint32_t* key, int* val) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nunits) return;
+    key[u] = 63u - (uint32_t)min(63, (units[u].end - units[u].begin + 31) >> 5);
+    val[u] = u;
+}
+
 __global__ void rows_part_off_kernel(Grid G, int ng, const int* __restrict__ cell_sci,
                                      const int* __restrict__ row_unit_off, int nsci, int* part_off) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -680,6 +692,10 @@ static int build_rows(sdm_ctx* c) {
         if (int rc = pl_realloc(pl, &pl->runits, pl->runits_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->epart, pl->runits_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->cpart, pl->runits_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->ru_key, pl->runits_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->ru_key_sorted, pl->runits_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->ru_val, pl->runits_cap)) return rc;
+        if (int rc = pl_realloc(pl, &pl->ru_order, pl->runits_cap)) return rc;
     }
     if (pl->nentries > 0)
         rows_fill_kernel<<<blocks(pl->nentries, 128), 128, 0, s>>>(pl->nentries, G, pl->entries, pl->entry_jhit,
@@ -688,6 +704,18 @@ static int build_rows(sdm_ctx* c) {
     rows_units_fill_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, G, pl->row_chunk, pl->sci, pl->sci_off,
                                                         pl->row_scan, pl->row_unit_off, pl->runits, (int)pl->runits_cap);
     rows_part_off_kernel<<<blocks(c->R + 1), 256, 0, s>>>(pl->G, ng, pl->cell_sci, pl->row_unit_off, pl->nsci, pl->part_off);
+    if (pl->row_lpt && pl->nrunits > 0) {
+        rows_unit_key_kernel<<<blocks(pl->nrunits), 256, 0, s>>>(pl->nrunits, pl->runits, pl->ru_key, pl->ru_val);
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, pl->ru_key, pl->ru_key_sorted, pl->ru_val, pl->ru_order, pl->nrunits, 0, 6, s);
+        if (need > pl->cub_tmp_bytes) {
+            if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
+            pl->cub_tmp_bytes = need;
+        }
+        PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->ru_key, pl->ru_key_sorted, pl->ru_val,
+                                                pl->ru_order, pl->nrunits, 0, 6, s));
+        c->launches += 2;
+    }
     c->launches += 7;
     return SDM_OK;
 }
@@ -1012,6 +1040,11 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
         A(pl_alloc(pl, &pl->runits, pl->runits_cap));
         A(pl_alloc(pl, &pl->epart, pl->runits_cap));
         A(pl_alloc(pl, &pl->cpart, pl->runits_cap));
+        A(pl_alloc(pl, &pl->ru_key, pl->runits_cap));
+        A(pl_alloc(pl, &pl->ru_key_sorted, pl->runits_cap));
+        A(pl_alloc(pl, &pl->ru_val, pl->runits_cap));
+        A(pl_alloc(pl, &pl->ru_order, pl->runits_cap));
+        if (const char* e = getenv("SDMB200_ROW_LPT")) pl->row_lpt = atoi(e) != 0;   // development knob
         pl->dummy_slot = pl->nslot_cap - 1;   // never a real slot: nslot <= nslot_cap - 8
         dummy_slot_kernel<<<1, 1, 0, c->stream>>>(pl->dummy_slot, pl->posq, pl->posq_build, pl->par, pl->atom, pl->img);
     } else {
@@ -1078,6 +1111,7 @@ static PairListView make_view(const sdm_ctx* c) {
     V.jent = pl->jent;
     V.jallow = pl->jallow;
     V.runits = pl->runits;
+    V.runit_order = pl->row_lpt ? pl->ru_order : nullptr;
     V.nrunits = pl->nrunits;
     V.row_group = pl->row_group;
     V.dummy_slot = pl->dummy_slot;

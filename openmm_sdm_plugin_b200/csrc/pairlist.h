@@ -38,6 +38,7 @@ struct PairListView {
     const uint32_t* jent;        // row entries: j slot | shift << 26
     const uint16_t* jallow;      // allow word per row entry (read for the masked prefix of a row only)
     const RowUnit* runits;       // [nrunits]
+    const int* runit_order;      // [nrunits] the order in which the warps draw the units (longest first), or nullptr
     int nrunits;
     int row_group;               // clusters per i-group (1 or 2)
     int dummy_slot;              // a slot that holds a far-away dummy atom (padding lanes)

@@ -317,11 +317,16 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
                 npairs, both, one, nsingle, single_tiles, nmasked, masked_tiles, nunits);
     }
 
-    // traversal exactly like the pair kernel: lane (tj, ti) = (lane>>2, lane&3) evaluates i-atoms
-    // ti and ti+4 (halves h = 0, 1) of cluster ci against j-atom tj of the entry's j-cluster
+    // traversal exactly like the row kernel (kernels_cluster.cu, pair_row_kernel): every i-group
+    // (G consecutive clusters of a supercluster) walks its row of individual j-atoms -- the atoms
+    // of its entries' j-clusters that row_hits() keeps and whose allow word is not empty -- and a
+    // lane evaluates its j-atom against the allowed i-atoms of the group.
+    int Grow = 1;
+    if (const char* e = getenv("SDMB200_ROW_GROUP")) Grow = atoi(e) == 2 ? 2 : 1;
+    const int ng = kMaxCi / Grow;
     std::vector<std::pair<int, int>> found;
     const double rc2 = rc * rc;
-    double lane_pairs = 0;
+    double lane_pairs = 0, row_entries = 0, row_masked = 0;
     for (int s = 0; s < nsci; s++) {
         const SciDesc sd = sci[s];
         for (int e = sci_off[s]; e < sci_off[s + 1]; e++) {
@@ -329,25 +334,39 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
             const uint32_t imask = ey[e] & 0xffu, m = ey[e] >> 8;
             const uint32_t code = ex[e] >> 26;
             const int sh[3] = {shift_x(code), shift_y(code), shift_z(code)};
-            for (int ci = 0; ci < kMaxCi; ci++) {
-                if (!((imask >> ci) & 1u)) continue;
-                lane_pairs += 64;
-                if (sd.replica != replica) continue;
-                for (int h = 0; h < 2; h++)
-                    for (int lane = 0; lane < 32; lane++) {
-                        if (m && !((masks[(size_t)m * kMaskWords + 2 * ci + h] >> lane) & 1u)) continue;
-                        const int ti = (lane & 3) + 4 * h, tj = lane >> 2;
-                        const int islot = (sd.c0 + ci) * kClusterSize + ti, jslot = cj * kJGroup + tj;
-                        const int ai = atom[islot], aj = atom[jslot];
-                        if (ai < 0 || aj < 0) continue;
+            uint32_t jh_lo, jh_hi;
+            entry_hits(V, sd, ex[e], imask, &jh_lo, &jh_hi);
+            const uint32_t* maskset = m ? &masks[(size_t)m * kMaskWords] : nullptr;
+            const bool same_sci = cj >= sd.c0 && cj < sd.c0 + sd.nci;
+            for (int g = 0; g < ng; g++) {
+                const uint32_t hits = row_hits(jh_lo, jh_hi, imask, g, Grow);
+                for (int tj = 0; tj < kJGroup; tj++) {
+                    if (!((hits >> tj) & 1u)) continue;
+                    const uint32_t allow = row_allow(maskset, imask, same_sci, g, Grow, tj);
+                    if (!allow) continue;
+                    row_entries += 1;
+                    if (allow != (Grow == 2 ? 0xffffu : 0xffu)) row_masked += 1;
+                    lane_pairs += 8 * Grow;
+                    if (sd.replica != replica) continue;
+                    const int jslot = cj * kJGroup + tj;
+                    const int aj = atom[jslot];
+                    if (aj < 0) continue;
+                    for (int a = 0; a < 8 * Grow; a++) {
+                        if (!((allow >> a) & 1u)) continue;
+                        const int ci = g * Grow + a / kClusterSize;
+                        if (ci >= sd.nci) continue;   // the kernel stages these lanes as dummies
+                        const int islot = (sd.c0 + ci) * kClusterSize + a % kClusterSize;
+                        const int ai = atom[islot];
+                        if (ai < 0) continue;
                         // the image this entry addresses (what the kernel evaluates), in double
                         double d[3];
                         for (int k = 0; k < 3; k++)
                             d[k] = posw[3 * (size_t)islot + k] - (posw[3 * (size_t)jslot + k] + (periodic ? sh[k] * box[k] : 0.0));
                         if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] > rc2) continue;
-                        int a = ai % n, b = aj % n;
-                        found.emplace_back(std::min(a, b), std::max(a, b));
+                        const int p = ai % n, q = aj % n;
+                        found.emplace_back(std::min(p, q), std::max(p, q));
                     }
+                }
             }
         }
     }
@@ -357,6 +376,7 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     if (stats) {
         stats[0] = nslot; stats[1] = nsci; stats[2] = nentries; stats[3] = nmasks;
         stats[4] = nunits; stats[5] = lane_pairs; stats[6] = G.ncell; stats[7] = G.span;
+        stats[8] = row_entries; stats[9] = row_masked;
     }
     return (long long)found.size();
 }

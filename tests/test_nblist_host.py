@@ -82,8 +82,12 @@ def test_cfg2_two_replicas(chk):
     got, ref, st = covered_pairs(chk, case, R=2, replica=1, jitter=jit)
     assert len(ref) > 4_000_000
     assert np.array_equal(got, ref)
-    # list statistics that DESIGN.md quotes
-    assert 0.15 < len(ref) * 2 / st[5] < 1.0
+    # list statistics that DESIGN.md quotes: half of the lane pairs the row kernel evaluates are
+    # inside the cutoff (35 % with the 8 x 8 tiles of the cluster-pair entries themselves), about
+    # one row entry in twelve carries an allow word
+    assert 0.48 < len(ref) * 2 / st[5] < 0.56
+    assert 45.0 < st[8] / (2 * case.system.n_atoms) < 55.0
+    assert st[9] / st[8] < 0.12
 
 
 @pytest.mark.parametrize("skin", [0.0, 0.12])
@@ -120,6 +124,15 @@ def test_tall_and_flat_boxes(chk):
         case.positions = np.mod(case.positions, base.system.box) * sc
         assert np.all(case.system.box >= 2.0 * (case.system.cutoff + 0.06))
         got, ref, _ = covered_pairs(chk, case)
+        assert np.array_equal(got, ref)
+
+
+def test_rows_of_two_clusters_cover_the_same_pairs(chk, monkeypatch):
+    """i-groups of two clusters (16 i-atoms per row, SDMB200_ROW_GROUP=2): the allow words switch
+    off the half of a group that does not own a j-cluster of its own supercluster."""
+    monkeypatch.setenv("SDMB200_ROW_GROUP", "2")
+    for case in (S.cfg1(), S.synthetic_case(3000, 30, seed=5, protein_atoms=300, displacement=(0, 0, 1.5))):
+        got, ref, st = covered_pairs(chk, case)
         assert np.array_equal(got, ref)
 
 
