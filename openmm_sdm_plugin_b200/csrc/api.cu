@@ -1020,7 +1020,7 @@ int sdm_md_init(sdm_ctx* c, const double* masses, double temperature, double fri
     c->md_noise_pending = false;
     if (!c->d_md_ctl) {
         if (int rc = dev_alloc(c, &c->d_md_ctl, 4)) return rc;
-        SDM_CUDA(cudaMallocHost((void**)&c->h_md_ctl, 4 * sizeof(unsigned long long)));
+        SDM_CUDA(cudaMallocHost((void**)&c->h_md_ctl, 8 * sizeof(unsigned long long)));
         c->B.md_ctl = c->d_md_ctl;
         c->graph_valid = false;   // the captured scalar stage must see the control words
     }
@@ -1203,11 +1203,19 @@ int sdm_md_step(sdm_ctx* c, int nsteps) {
     if (int rc = md_check(c, 0)) return rc;
     if (nsteps <= 0) return SDM_OK;
     const unsigned long long target = c->md_steps + (unsigned long long)nsteps;
-    const int chunk = std::max(1, c->opt.nstlist > 0 ? c->opt.nstlist : 20);
+    const int nst = std::max(1, c->opt.nstlist > 0 ? c->opt.nstlist : 20);
+    unsigned int* d_disp = sdm_ctx_pairlist_max_disp_ptr(c);
+    // Planned list lifetime: the list is rebuilt BEFORE its fastest atom has used up half the skin --
+    // an evaluation on a stale list is wasted work (it is never integrated) -- so the host watches
+    // how fast the largest displacement grows and schedules the rebuild at 80 % of the predicted
+    // lifetime, never later than opt.nstlist.  A stale list that slips through is still caught.
+    if (c->md_plan <= 0 || c->md_plan > nst) c->md_plan = nst;
     int futile = 0;   // consecutive chunks that did not advance at all
     while (c->md_steps < target) {
         const unsigned long long start = c->md_steps;
-        const int todo = (int)std::min<unsigned long long>(target - start, (unsigned long long)chunk);
+        if (d_disp && c->list_valid && c->list_age >= c->md_plan) c->list_valid = false;
+        const int age = (d_disp && c->list_valid) ? c->list_age : 0;
+        const int todo = (int)std::min<unsigned long long>(target - start, (unsigned long long)std::max(1, (d_disp ? c->md_plan : nst) - age));
         for (int k = 0; k < todo; k++) {
             if (int rc = sdm_eval(c)) return rc;   // hybrid force of every replica at the current positions
             md_enqueue_update(c, true);            // positions and velocities advance on the device
@@ -1215,6 +1223,8 @@ int sdm_md_step(sdm_ctx* c, int nsteps) {
         // how far did the device get?  ([0] stale list / capacity, [1] steps taken, [2] constraints)
         SDM_CUDA(cudaMemcpyAsync(c->h_md_ctl, c->d_md_ctl, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                  c->stream));
+        if (d_disp)
+            SDM_CUDA(cudaMemcpyAsync(&c->h_md_ctl[4], d_disp, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
         SDM_CUDA(cudaMemcpyAsync(c->h_state, c->B.state, sizeof(sdm::ReplicaState) * (size_t)c->R,
                                  cudaMemcpyDeviceToHost, c->stream));
         SDM_CUDA(cudaStreamSynchronize(c->stream));
@@ -1222,7 +1232,19 @@ int sdm_md_step(sdm_ctx* c, int nsteps) {
             c->md_steps = c->h_md_ctl[1];
             return fail(SDM_ERR_CONSTRAINT, "a constraint cluster did not converge (step size too large?)");
         }
-        if (c->h_md_ctl[0] == 0ull) continue;   // all of them taken
+        if (c->h_md_ctl[0] == 0ull) {   // all of them taken
+            if (d_disp && c->list_valid && c->list_age >= 2) {
+                float d2;
+                const unsigned int bits = (unsigned int)c->h_md_ctl[4];
+                std::memcpy(&d2, &bits, sizeof(d2));
+                const double rate = std::sqrt((double)d2) / (double)(c->list_age - 1);   // nm per step, so far
+                if (rate > 0) {
+                    const double life = 0.5 * c->opt.skin / rate;
+                    c->md_plan = std::max(2, std::min(nst, (int)std::floor(0.8 * life)));
+                }
+            }
+            continue;
+        }
         // the evaluation of step h_md_ctl[1] reported a stale list / full scratch: that step and the
         // ones behind it were not taken.  Rebuild / grow (note_status), clear the flags, go again.
         const unsigned long long taken = c->h_md_ctl[1];
@@ -1230,6 +1252,7 @@ int sdm_md_step(sdm_ctx* c, int nsteps) {
         c->md_steps = taken;
         for (int r = 0; r < c->R; r++) note_status(c, c->h_state[r].sc.status);
         c->list_valid = false;
+        c->md_plan = std::max(2, (int)(0.7 * c->md_plan));
         SDM_CUDA(cudaMemsetAsync(c->d_md_ctl, 0, sizeof(unsigned long long), c->stream));
         SDM_CUDA(cudaMemsetAsync(c->d_sticky, 0, sizeof(int) * (size_t)c->R, c->stream));
         futile = taken == start ? futile + 1 : 0;

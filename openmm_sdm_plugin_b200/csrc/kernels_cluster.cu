@@ -898,27 +898,36 @@ __global__ void __launch_bounds__(256)
 refresh_kernel(Topology T, nbl::Grid G, int nslot, const double* __restrict__ pos_all,
                const int* __restrict__ atom, const int* __restrict__ img,
                const float4* __restrict__ posq_build, float4* __restrict__ posq, float half_skin2,
-               int* flags, int* list_age) {
+               int* flags, int* list_age, unsigned int* max_disp2) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) *list_age += 1;   // one more evaluation with this list (read by the scalar stage)
-    if (s >= nslot) return;
-    const int ga = atom[s];
-    if (ga < 0) return;  // dummy slot keeps its far-away coordinates
-    const int r = ga / T.n;
-    const double* p = pos_all + 3 * (size_t)ga;  // ga = r*n + a
-    const int im = img[s];
-    const int ix = (im & 0x3ff) - 512, iy = ((im >> 10) & 0x3ff) - 512, iz = ((im >> 20) & 0x3ff) - 512;
-    double x = p[0], y = p[1], z = p[2];
-    if (G.periodic) {
-        x += ix * G.box[0];
-        y += iy * G.box[1];
-        z += iz * G.box[2];
+    float d2 = 0.f;
+    const int ga = s < nslot ? atom[s] : -1;
+    if (ga >= 0) {   // a dummy slot keeps its far-away coordinates
+        const int r = ga / T.n;
+        const double* p = pos_all + 3 * (size_t)ga;  // ga = r*n + a
+        const int im = img[s];
+        const int ix = (im & 0x3ff) - 512, iy = ((im >> 10) & 0x3ff) - 512, iz = ((im >> 20) & 0x3ff) - 512;
+        double x = p[0], y = p[1], z = p[2];
+        if (G.periodic) {
+            x += ix * G.box[0];
+            y += iy * G.box[1];
+            z += iz * G.box[2];
+        }
+        const float4 b = posq_build[s];
+        const float fx = (float)x, fy = (float)y, fz = (float)z;
+        const float dx = fx - b.x, dy = fy - b.y, dz = fz - b.z;
+        d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > half_skin2) atomicExch(flags + r, SDM_ERR_STALE_LIST);
+        posq[s] = make_float4(fx, fy, fz, b.w);
     }
-    const float4 b = posq_build[s];
-    const float fx = (float)x, fy = (float)y, fz = (float)z;
-    const float dx = fx - b.x, dy = fy - b.y, dz = fz - b.z;
-    if (dx * dx + dy * dy + dz * dz > half_skin2) atomicExch(flags + r, SDM_ERR_STALE_LIST);
-    posq[s] = make_float4(fx, fy, fz, b.w);
+    // largest squared displacement since the list was built, over all replicas: the host plans the
+    // next rebuild from its growth (non-negative floats order like their bit patterns)
+    if (max_disp2) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        if ((threadIdx.x & 31) == 0 && __float_as_uint(d2) > *max_disp2) atomicMax(max_disp2, __float_as_uint(d2));
+    }
 }
 
 }  // namespace
@@ -1003,10 +1012,10 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
 
 void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq,
-                    float half_skin2, int* flags, int* list_age, cudaStream_t s) {
+                    float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s) {
     if (nslot <= 0) return;
     refresh_kernel<<<(nslot + 255) / 256, 256, 0, s>>>(T, G, nslot, pos_all, atom, img, posq_build,
-                                                      posq, half_skin2, flags, list_age);
+                                                      posq, half_skin2, flags, list_age, max_disp2);
 }
 
 }  // namespace sdm

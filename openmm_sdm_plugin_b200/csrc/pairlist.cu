@@ -74,6 +74,7 @@ struct PairList {
     Unit* units = nullptr;
     int* part_off = nullptr;    // [R+1]
     int* unit_counter = nullptr; // work counter of the persistent pair kernel
+    unsigned int* max_disp2 = nullptr;   // largest squared displacement since the build (float bits)
     double* epart = nullptr;
     long long* cpart = nullptr;
     double* minmax = nullptr;   // [6] non-periodic extent reduction
@@ -928,6 +929,7 @@ static int build_list(sdm_ctx* c) {
         static const int one = 1;   // this evaluation is the first one with the new list
         PL_CUDA(cudaMemcpyAsync(c->d_list_age, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     }
+    PL_CUDA(cudaMemsetAsync(pl->max_disp2, 0, sizeof(unsigned int), s));
     c->list_valid = true;
     c->list_age = 0;
     c->n_builds++;
@@ -998,6 +1000,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->sci_unit_off, pl->nsci_cap + 1));
     A(pl_alloc(pl, &pl->part_off, R + 1));
     A(pl_alloc(pl, &pl->unit_counter, 1));
+    A(pl_alloc(pl, &pl->max_disp2, 1));
     A(pl_alloc(pl, &pl->minmax, 6));
     pl->items_cap = (size_t)pl->nsci_cap * 64 + 1;
     A(pl_alloc(pl, &pl->item_count, pl->items_cap));
@@ -1132,7 +1135,7 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
     } else {
         const float hs = 0.5f * (float)c->opt.skin;
         launch_refresh(c->T, pl->G, pl->nslot, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq,
-                       hs * hs, c->B.flags, c->d_list_age, s);
+                       hs * hs, c->B.flags, c->d_list_age, pl->max_disp2, s);
         c->launches++;
         // fresh state-1 accumulators (one 8 MB memset is cheaper than scattered stores in the mix kernel)
         PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
@@ -1178,6 +1181,8 @@ int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs,
     PL_CUDA(cudaStreamSynchronize(c->stream));
     return SDM_OK;
 }
+
+unsigned int* sdm_ctx_pairlist_max_disp_ptr(sdm_ctx* c) { return c->pl ? c->pl->max_disp2 : nullptr; }
 
 int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     if (!c->pl) return SDM_ERR_INVALID;

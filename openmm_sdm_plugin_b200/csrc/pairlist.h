@@ -62,9 +62,10 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
                       int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s);
 
 // Per-eval refresh of the sorted positions from the current double positions (same periodic
-// image as at build time) + staleness check against the build-time positions.
+// image as at build time) + staleness check against the build-time positions; max_disp2 (may be
+// null) receives the largest squared displacement since the build, as float bits.
 void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq,
-                    float half_skin2, int* flags, int* list_age, cudaStream_t s);
+                    float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s);
 
 }  // namespace sdm

@@ -73,6 +73,7 @@ struct sdm_ctx {
     unsigned long long* d_md_ctl = nullptr;   // [0] abort flag, [1] steps taken
     unsigned long long* h_md_ctl = nullptr;   // pinned read-back
     unsigned long long md_repeated = 0;
+    int md_plan = 0;                    // planned list lifetime in steps (adapted to the observed motion)
     int* d_sticky = nullptr;            // [R] sticky status (see EvalBuffers::sticky)
     int* h_sticky = nullptr;            // pinned [R]
     double md_dt = 0, md_vscale = 0, md_fscale = 0, md_noisescale = 0;
@@ -95,3 +96,4 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c);  // (re)build the list if due, else re
 int sdm_ctx_pairlist_launch(sdm_ctx* c);   // the pair kernel
 int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap);
 int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value);
+unsigned int* sdm_ctx_pairlist_max_disp_ptr(sdm_ctx* c);   // device word: largest squared displacement since the build (float bits)
