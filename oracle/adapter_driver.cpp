@@ -1,33 +1,28 @@
-// ref_driver.cpp -- C entry points around the REFERENCE's own sources, compiled where they lie
-// under /root/reference (oracle/Makefile target _ref/libsdmref.so):
-//     openmmapi/src/LangevinIntegratorSDM.cpp            (integrator: step sequence, SoftCoreF)
-//     platforms/reference/src/ReferenceSDMKernels.cpp    (Save/Make/Restore state, execute)
-//     platforms/reference/src/ReferenceSDMKernelFactory.cpp
-//     platforms/reference/src/ReferenceStochasticDynamicsSDM.cpp
-// OpenMM itself is not available in this image, so those files are compiled against the small
-// stand-in headers in oracle/openmm_stub/ (our own declarations of the handful of OpenMM classes
-// the plugin touches).  What OpenMM would compute -- the force-group evaluations behind
-// ContextImpl::calcForcesAndEnergy -- is delegated to a callback the test supplies (the oracle's
-// restated nonbonded evaluation), and the Gaussian noise comes from a queue the test fills.
-// Everything the PLUGIN owns (SURVEY.md rows a1-a4, a6, a8, a9, a11-a15 and the Langevin update)
-// is therefore executed by the reference's unmodified code.
+// adapter_driver.cpp -- C entry point that runs the REFERENCE's unmodified integrator
+// (openmmapi/src/LangevinIntegratorSDM.cpp, compiled where it lies under /root/reference) with the
+// B200 kernel of openmm_sdm_plugin_b200/csrc/openmm/ registered for
+// IntegrateLangevinStepSDMKernel::Name() -- the same stand-in Context, the same noise queue and the
+// same parameter block as ref_driver.cpp, which runs it with the reference's own Reference-platform
+// kernel.  tests/test_gpu_openmm_adapter.py compares the two.
 //
-// TEST INFRASTRUCTURE ONLY (like the rest of oracle/): used by tests/ and by
-// tools/make_ref_golden.py to pin the restated oracle; never linked into libsdmb200.
+// TEST INFRASTRUCTURE (like the rest of oracle/).  The adapter sources themselves are product code;
+// this file only drives them against oracle/openmm_stub.  level = 0: the System carries a
+// B200NonbondedForce (fused path, the callback is only asked for force group 1);  level = 1: the
+// System carries plain forces and the callback evaluates group 2 as OpenMM would (literal operations).
 #include <cstring>
 #include <deque>
 #include <string>
 #include <vector>
 
+#include "B200NonbondedForce.h"
 #include "LangevinIntegratorSDM.h"
-#include "ReferenceSDMKernelFactory.h"
 #include "SDMKernels.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/ContextImpl.h"
 #include "openmm/reference/ReferencePlatform.h"
 #include "openmm/reference/SimTKOpenMMUtilities.h"
 
-extern "C" void registerKernelFactories();   // ReferenceSDMKernelFactory.cpp:44
+extern "C" void registerKernelFactories();   // B200SDMKernelFactory.cpp
 
 namespace {
 std::deque<double> g_noise;
@@ -43,8 +38,6 @@ RealOpenMM SimTKOpenMMUtilities::getNormallyDistributedRandomNumber() {
     return v;
 }
 
-// What OpenMM's ContextImpl does here: clear the force buffer, evaluate the forces whose group is
-// in the mask at the current positions, return their energy.
 double ContextImpl::calcForcesAndEnergy(bool, bool, int groups) {
     ReferencePlatform::PlatformData* data = static_cast<ReferencePlatform::PlatformData*>(platformData);
     std::vector<Vec3>& pos = *data->positions;
@@ -62,8 +55,7 @@ double ContextImpl::calcForcesAndEnergy(bool, bool, int groups) {
 
 extern "C" {
 
-// Scalar state of LangevinIntegratorSDM, in the order of its setters (SDMplugin.i:86-145).
-struct sdmref_params {
+struct sdmref_params {   // ref_driver.cpp
     double temperature, friction, step_size;
     int bias_method, softcore_method;
     double lambdac, gammac, wbcoeff, w0coeff, lambda1, lambda2, alpha, u0;
@@ -72,81 +64,59 @@ struct sdmref_params {
     double noneq_tmax, work_value, time;
     double m_lambda1, m_lambda2, m_u0, m_w0, b_lambda1, b_lambda2, b_u0, b_w0;
 };
-
 struct sdmref_out {
     double bind_e, pot_energy, work_value, lambdac, lambda1, lambda2, u0, w0coeff, time, kinetic_energy;
     int step_count, pad_;
 };
+// force group 2 as the B200NonbondedForce carries it (level 0)
+struct sdmb200_nonbonded {
+    int method, n_exceptions, use_dispersion_correction, pad_;
+    double cutoff, eps_rf, box[3];
+    const double *charge, *sigma, *epsilon;       // [n]
+    const int* exception_pairs;                   // [2*n_exceptions] every addException pair
+    const double* exception_params;               // [3*n_exceptions] chargeProd, sigma, epsilon
+};
 
-const char* sdmref_last_error() { return g_error.c_str(); }
+const char* sdmb200_adapter_last_error() { return g_error.c_str(); }
 
-void sdmref_set_noise(const double* values, int n) {
+void sdmb200_adapter_set_noise(const double* values, int n) {
     g_noise.clear();
     for (int i = 0; i < n; i++) g_noise.push_back(values[i]);
 }
 
-// LangevinIntegratorSDM::SoftCoreF (LangevinIntegratorSDM.cpp:125-149).  Returns 0, or -1 when the
-// reference throws (unknown method).
-int sdmref_softcore(int method, double u, double umax, double a, double ub, double* u_sc, double* fp) {
-    try {
-        SDMPlugin::LangevinIntegratorSDM integ(300.0, 1.0, 0.001, 1);
-        integ.setSoftCoreMethod(method);
-        *u_sc = integ.SoftCoreF(u, umax, a, ub, *fp);
-        return 0;
-    } catch (const std::exception& e) {
-        g_error = e.what();
-        return -1;
-    }
-}
-
-// Defaults of the constructor (LangevinIntegratorSDM.cpp:48-85) as the reference sets them.
-int sdmref_defaults(sdmref_params* p) {
-    SDMPlugin::LangevinIntegratorSDM integ(300.0, 0.5, 0.001, 3);
-    std::memset(p, 0, sizeof(*p));
-    p->temperature = integ.getTemperature();
-    p->friction = integ.getFriction();
-    p->step_size = integ.getStepSize();
-    p->bias_method = integ.getBiasMethod();
-    p->softcore_method = integ.getSoftCoreMethod();
-    p->lambdac = integ.getLambda();
-    p->gammac = integ.getGamma();
-    p->wbcoeff = integ.getWBcoeff();
-    p->w0coeff = integ.getW0coeff();
-    p->lambda1 = integ.getLambda1();
-    p->lambda2 = integ.getLambda2();
-    p->alpha = integ.getAlpha();
-    p->u0 = integ.getU0();
-    p->umax = integ.getUmax();
-    p->acore = integ.getAcore();
-    p->ubcore = integ.getUbcore();
-    p->nonequilibrium = integ.getNonEquilibrium();
-    p->work_value = integ.getNoneqWorkvalue();
-    return 0;
-}
-
-// `steps` calls of LangevinIntegratorSDM::step(1) on a stand-in Context of n particles.
-//   positions / velocities [3n]: in = initial state, out = state after the last step
-//   displacement [3n]: the displacement map, set atom by atom through setDisplacement
-//   force_groups [n_forces]: the force groups present in the System (the integrator rejects
-//       anything but 1 and 2, LangevinIntegratorSDM.cpp:92-100)
-//   hybrid_force [3n]: out, the force buffer after the last execute() (= the hybrid force)
-//   traj (optional) [steps][2]: BindE and PotEnergy after every step
-// Returns 0, or -1 with sdmref_last_error() set when the reference throws.
-int sdmref_run(int n, const double* masses, double* positions, double* velocities,
-               const double* displacement, const int* force_groups, int n_forces,
-               const sdmref_params* p, OpenMM::StubForceCallback cb, void* user, int steps,
-               sdmref_out* out, double* hybrid_force, double* traj) {
+int sdmb200_adapter_run(int level, int n, const double* masses, double* positions, double* velocities,
+                        const double* displacement, const sdmb200_nonbonded* nb, int n_constraints,
+                        const int* constraint_pairs, const double* constraint_dist, const sdmref_params* p,
+                        OpenMM::StubForceCallback cb, void* user, int steps, sdmref_out* out,
+                        double* hybrid_force, double* traj) {
     using namespace OpenMM;
     try {
         static ReferencePlatform* platform = 0;
         if (!platform) {
             platform = new ReferencePlatform();
             Platform::registerPlatform(platform);
-            registerKernelFactories();   // the reference's own plugin entry point
+            registerKernelFactories();   // the B200 plugin's entry point
         }
         System system;
         for (int i = 0; i < n; i++) system.addParticle(masses[i]);
-        for (int i = 0; i < n_forces; i++) system.addForce(new Force(force_groups[i]));
+        for (int k = 0; k < n_constraints; k++)
+            system.addConstraint(constraint_pairs[2 * k], constraint_pairs[2 * k + 1], constraint_dist[k]);
+        if (level == 0) {
+            SDMB200::B200NonbondedForce* f = new SDMB200::B200NonbondedForce();
+            for (int i = 0; i < n; i++) f->addParticle(nb->charge[i], nb->sigma[i], nb->epsilon[i]);
+            for (int k = 0; k < nb->n_exceptions; k++)
+                f->addException(nb->exception_pairs[2 * k], nb->exception_pairs[2 * k + 1], nb->exception_params[3 * k],
+                                nb->exception_params[3 * k + 1], nb->exception_params[3 * k + 2]);
+            f->setNonbondedMethod((SDMB200::B200NonbondedForce::NonbondedMethod)nb->method);
+            f->setCutoffDistance(nb->cutoff);
+            f->setReactionFieldDielectric(nb->eps_rf);
+            f->setUseDispersionCorrection(nb->use_dispersion_correction != 0);
+            f->setPeriodicBox(nb->box[0], nb->box[1], nb->box[2]);
+            system.addForce(f);               // force group 2, evaluates to nothing on the OpenMM side
+        } else {
+            system.addForce(new Force(2));    // OpenMM's own NonbondedForce (the callback)
+        }
+        system.addForce(new Force(1));        // bonded + restraints
         ReferencePlatform::PlatformData data(n);
         data.time = p->time;
         for (int i = 0; i < n; i++) {
@@ -183,15 +153,10 @@ int sdmref_run(int n, const double* masses, double* positions, double* velocitie
         integ.setw0intercept(p->b_w0);
         for (int i = 0; i < n; i++)
             integ.setDisplacement(i, displacement[3 * i], displacement[3 * i + 1], displacement[3 * i + 2]);
-        for (int i = 0; i < n; i++) {   // the map reads back what was written, atom by atom
-            const Vec3 d = integ.getDisplacement(i);
-            if (d[0] != displacement[3 * i] || d[1] != displacement[3 * i + 1] || d[2] != displacement[3 * i + 2])
-                throw OpenMMException("getDisplacement does not return what setDisplacement stored");
-        }
 
-        impl.bindIntegrator(integ);   // LangevinIntegratorSDM::initialize -> kernel initialize (snapshot of the map)
+        impl.bindIntegrator(integ);   // LangevinIntegratorSDM::initialize -> createKernel -> B200 kernel initialize
         for (int s = 0; s < steps; s++) {
-            integ.step(1);
+            integ.step(1);            // the reference's own step sequence, LangevinIntegratorSDM.cpp:153-183
             if (traj) {
                 traj[2 * s] = integ.getBindE();
                 traj[2 * s + 1] = integ.getPotEnergy();

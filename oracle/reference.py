@@ -137,3 +137,97 @@ def run(masses, positions, velocities, displacement, params: RefParams, force_fn
     res = {k: getattr(out, k) for k, _ in RefOut._fields_ if k != "pad_"}
     res.update(positions=x, velocities=v, hybrid_force=hyb, traj=traj)
     return res
+
+
+# ---- the reference's integrator with the PRODUCT's OpenMM-side kernel (oracle/adapter_driver.cpp) -----
+_SO_B200 = os.path.join(_HERE, "_ref", "libsdmb200_openmm.so")
+_LIB_B200 = None
+
+
+class B200Nonbonded(C.Structure):
+    _fields_ = [("method", C.c_int), ("n_exceptions", C.c_int), ("use_dispersion_correction", C.c_int), ("pad_", C.c_int),
+                ("cutoff", C.c_double), ("eps_rf", C.c_double), ("box", C.c_double * 3),
+                ("charge", C.c_void_p), ("sigma", C.c_void_p), ("epsilon", C.c_void_p),
+                ("exception_pairs", C.c_void_p), ("exception_params", C.c_void_p)]
+
+
+def b200_adapter_available() -> bool:
+    if os.path.isdir(REFERENCE_ROOT):
+        build()
+    return os.path.exists(_SO_B200)
+
+
+def _lib_b200():
+    global _LIB_B200
+    if _LIB_B200 is None:
+        from openmm_sdm_plugin_b200 import _lib as product
+        product.lib()                       # the product library is built and resolvable before the adapter loads it
+        L = C.CDLL(_SO_B200)
+        L.sdmb200_adapter_last_error.restype = C.c_char_p
+        L.sdmb200_adapter_run.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(B200Nonbonded), C.c_int, C.c_void_p, C.c_void_p,
+                                          C.POINTER(RefParams), FORCE_CB, C.c_void_p, C.c_int, C.POINTER(RefOut),
+                                          C.c_void_p, C.c_void_p]
+        _LIB_B200 = L
+    return _LIB_B200
+
+
+def run_b200(level, system, masses, positions, velocities, displacement, params: RefParams, force_fn, steps=1,
+             noise=None, constraint_pairs=None, constraint_dist=None):
+    """The same `steps` x LangevinIntegratorSDM::step(1) as run(), with the B200 kernel registered for
+    IntegrateLangevinStepSDMKernel.  level 0 = fused (the System carries a B200NonbondedForce built from
+    `system`, force_fn is only asked for group mask 2 and gets zero work for mask 4), level 1 = literal
+    operations (force_fn evaluates mask 4 like OpenMM would)."""
+    L = _lib_b200()
+    n = len(masses)
+    m = np.ascontiguousarray(masses, np.float64)
+    x = np.array(positions, np.float64, order="C").reshape(n, 3)
+    v = np.array(velocities, np.float64, order="C").reshape(n, 3)
+    d = np.ascontiguousarray(displacement, np.float64).reshape(n, 3)
+    hyb = np.zeros((n, 3))
+    traj = np.zeros((steps, 2))
+    nz = np.ascontiguousarray(noise if noise is not None else [], np.float64).ravel()
+    L.sdmb200_adapter_set_noise(nz.ctypes.data_as(C.c_void_p), len(nz))
+    # every addException of the reader: zero-parameter exclusions and the parameterised 1-4 pairs
+    q = np.ascontiguousarray(system.charge, np.float64)
+    sg = np.ascontiguousarray(system.sigma, np.float64)
+    ep = np.ascontiguousarray(system.epsilon, np.float64)
+    excl = np.ascontiguousarray(system.exclusions, np.int32).reshape(-1, 2)
+    par = {(min(a, b), max(a, b)): p for (a, b), p in zip(np.asarray(system.exception_pairs).reshape(-1, 2).tolist(),
+                                                           np.asarray(system.exception_params).reshape(-1, 3).tolist())}
+    ex_pairs = np.ascontiguousarray(excl, np.int32)
+    ex_par = np.ascontiguousarray([par.get((min(a, b), max(a, b)), (0.0, 1.0, 0.0)) for a, b in excl.tolist()],
+                                  np.float64).reshape(-1, 3)
+    nb = B200Nonbonded()
+    nb.method, nb.n_exceptions = int(system.method), len(ex_pairs)
+    nb.use_dispersion_correction = int(bool(system.use_dispersion_correction))
+    nb.cutoff, nb.eps_rf = float(system.cutoff), float(system.eps_rf)
+    for k in range(3):
+        nb.box[k] = float(system.box[k])
+    nb.charge, nb.sigma, nb.epsilon = q.ctypes.data, sg.ctypes.data, ep.ctypes.data
+    nb.exception_pairs, nb.exception_params = ex_pairs.ctypes.data, ex_par.ctypes.data
+    cp = np.ascontiguousarray(constraint_pairs if constraint_pairs is not None else np.zeros((0, 2)), np.int32)
+    cd = np.ascontiguousarray(constraint_dist if constraint_dist is not None else np.zeros(0), np.float64)
+    err = []
+
+    def cb(user, groups, nn, pos_p, f_p):
+        try:
+            pos = np.ctypeslib.as_array(pos_p, shape=(nn, 3))
+            e, f = force_fn(int(groups), pos.copy())
+            np.ctypeslib.as_array(f_p, shape=(nn, 3))[...] = f
+            return float(e)
+        except Exception as ex:   # never let an exception cross the C frame
+            err.append(ex)
+            return 0.0
+
+    out = RefOut()
+    rc = L.sdmb200_adapter_run(int(level), n, m.ctypes.data, x.ctypes.data, v.ctypes.data, d.ctypes.data, C.byref(nb),
+                               len(cd), cp.ctypes.data, cd.ctypes.data, C.byref(params), FORCE_CB(cb), None, steps,
+                               C.byref(out), hyb.ctypes.data, traj.ctypes.data)
+    if err:
+        raise err[0]
+    if rc:
+        raise RuntimeError(L.sdmb200_adapter_last_error().decode())
+    res = {k: getattr(out, k) for k, _ in RefOut._fields_ if k != "pad_"}
+    res.update(positions=x, velocities=v, hybrid_force=hyb, traj=traj)
+    return res

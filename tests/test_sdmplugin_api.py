@@ -65,3 +65,15 @@ def test_unbound_integrator_and_step_report_errors():
         g.evaluate([[0, 0, 0]] * 3)
     with pytest.raises(OpenMMException):
         g.step(1)
+
+
+def test_reference_import_line_resolves():
+    """example/test.py:11 and example/test_explicit.py:11: `from SDMplugin import *`."""
+    ns = {}
+    exec("from SDMplugin import *", ns)
+    assert {"LangevinIntegratorSDM", "SDMUtils", "OpenMMException"} <= set(ns)
+    from openmm_sdm_plugin_b200 import sdmplugin
+    assert ns["LangevinIntegratorSDM"] is sdmplugin.LangevinIntegratorSDM
+    integ = ns["LangevinIntegratorSDM"](300.0, 0.5, 0.001, 10)        # SDMplugin.i:86
+    integ.setLambda1(0.025)
+    assert integ.getLambda1() == 0.025 and integ.ILogisticMethod == 2
