@@ -429,6 +429,13 @@ def main():
         e_ctx.append(cg)
         e_hf.append(h_f if d == 0 else PinnedArray((R, n, 3)))
     flush_stream = torch.cuda.Stream()
+    # single-precision transfers (sdm_set_positions_all_f32 / sdm_enqueue_results_f32): the precision
+    # positions and forces have on the reference's live OpenCL path; half the PCIe bytes
+    h_pos32, h_pos_b32 = PinnedArray((R, n, 3), np.float32), PinnedArray((R, n, 3), np.float32)
+    h_pos32.array[...] = h_pos.array
+    h_pos_b32.array[...] = h_pos_b.array
+    e_hf32 = [PinnedArray((R, n, 3), np.float32) for _ in range(D)]
+    io32 = [False]
 
     def e2e_submit(k, depth):
         d = k % depth
@@ -439,9 +446,14 @@ def main():
             s = cg.collect_scalars()
             if (k - depth) % args.exchange_every == 0:
                 exchange_gather(s)           # one exchange period: the path's only collective
-        cg.set_positions_all(h_pos.array if k % 2 == 0 else h_pos_b.array)
-        cg.eval()
-        cg.enqueue_results(e_hf[d].array)
+        if io32[0]:
+            cg.set_positions_all(h_pos32.array if k % 2 == 0 else h_pos_b32.array)
+            cg.eval()
+            cg.enqueue_results(e_hf32[d].array)
+        else:
+            cg.set_positions_all(h_pos.array if k % 2 == 0 else h_pos_b.array)
+            cg.eval()
+            cg.enqueue_results(e_hf[d].array)
         return s
 
     def e2e_run_threaded(nsteps, depth):
@@ -524,15 +536,21 @@ def main():
         e_ctx[d].synchronize()
     e2e_t, s = e2e_run(args.steps, D, True)
     assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
+    io32[0] = True
+    e2e_run(max(args.warmup, D), D, False)
+    e2e32_t, s = e2e_run(args.steps, D, True)
+    assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
+    f32_dev = float(np.abs(e_hf32[0].array - e_hf[0].array).max() / max(np.abs(e_hf[0].array).max(), 1e-30))
+    io32[0] = False
     e2e_run(args.warmup, 1, False)
     e2e_serial_t, s = e2e_run(args.steps, 1, True)
     assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
     for cg in e_ctx:
         cg.close()
     if world > 1:
-        tt = torch.tensor([e2e_t, e2e_serial_t], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([e2e_t, e2e_serial_t, e2e32_t], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t, e2e_serial_t = float(tt[0].item()), float(tt[1].item())
+        e2e_t, e2e_serial_t, e2e32_t = float(tt[0].item()), float(tt[1].item()), float(tt[2].item())
     e2e_value = world * R * args.steps / e2e_t
     h2d = R * n * 3 * 8
     d2h = R * n * 3 * 8 + R * 8 * 20
@@ -575,6 +593,15 @@ def main():
             "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_t / args.steps, "batches_in_flight": D,
+                    "pcie_gb_s_per_rank": (h2d + d2h) * args.steps / e2e_t / 1e9,
+                    "f32_io": {"value": world * R * args.steps / e2e32_t, "unit": "evals/s",
+                               "ms_per_step": 1e3 * e2e32_t / args.steps,
+                               "h2d_bytes_per_step": R * n * 3 * 4, "d2h_bytes_per_step": R * n * 3 * 4 + R * 8 * 20,
+                               "pcie_gb_s_per_rank": (R * n * 3 * 8 + R * 8 * 20) * args.steps / e2e32_t / 1e9,
+                               "max_rel_force_deviation_from_f64_io": f32_dev,
+                               "note": "same pipeline through sdm_set_positions_all_f32 / sdm_enqueue_results_f32: positions and "
+                                       "forces cross PCIe in single precision (the precision of the reference's OpenCL path, "
+                                       "OpenCLSDMKernels.cpp:96-103); arithmetic on the device unchanged"},
                     "exchange_every_steps": args.exchange_every if world > 1 else None,
                     "list_builds": "lists pre-aged to staggered ages: the timed steps carry K/nstlist list builds",
                     "host_threads": D if (world == 1 and args.e2e_threads and D > 1) else 1,

@@ -180,6 +180,11 @@ int sdm_set_positions_device(sdm_ctx* ctx, int replica, const double* d_xyz);
 int sdm_positions_device_ptr(sdm_ctx* ctx, int replica, double** d_xyz);
 /* All replicas at once: xyz_all is [n_replicas][3*n_atoms] host doubles, one asynchronous copy. */
 int sdm_set_positions_all(sdm_ctx* ctx, const double* xyz_all);
+/* The same in single precision -- the precision positions and forces have on the reference's live
+ * OpenCL path (posq / force are float4 there, platforms/opencl/src/OpenCLSDMKernels.cpp:96-103):
+ * half the bytes over PCIe.  The copy lands in a device staging buffer and is widened to the ctx's
+ * FP64 positions by a kernel on the ctx stream. */
+int sdm_set_positions_all_f32(sdm_ctx* ctx, const float* xyz_all);
 
 /* Result of the group-1 (bonded/restraint) evaluation the integrator does at :176: forces left
  * in the force buffer and RestraintEnergy.  fb may be NULL (zero).  Host pointers. */
@@ -211,6 +216,9 @@ int sdm_read_results(sdm_ctx* ctx, double* forces_all, sdm_scalars* scalars_all)
  * ideally pinned; may be NULL) and of the scalar blocks behind the last sdm_eval() and returns
  * at once; after sdm_synchronize(), sdm_collect_scalars() hands out the scalars that arrived. */
 int sdm_enqueue_results(sdm_ctx* ctx, double* forces_all);
+/* The same with the hybrid forces narrowed to single precision on the device first
+ * ([n_replicas][3*n_atoms] floats, 12 B/atom instead of 24); the scalars stay FP64. */
+int sdm_enqueue_results_f32(sdm_ctx* ctx, float* forces_all);
 int sdm_collect_scalars(sdm_ctx* ctx, sdm_scalars* scalars_all);
 /* Debug / parity: the sorted in-cutoff non-excluded (i<j) pair list the pair kernel evaluated at
  * state 1, System particle indices.  pairs may be NULL to query *n only.  Synchronises. */

@@ -77,8 +77,10 @@ SYMBOLS = {
     "sdm_set_positions_device": (_I, [_VP, _I, _VP]),
     "sdm_positions_device_ptr": (_I, [_VP, _I, C.POINTER(_VP)]),
     "sdm_set_positions_all": (_I, [_VP, _VP]),
+    "sdm_set_positions_all_f32": (_I, [_VP, _VP]),
     "sdm_read_results": (_I, [_VP, _VP, _VP]),
     "sdm_enqueue_results": (_I, [_VP, _VP]),
+    "sdm_enqueue_results_f32": (_I, [_VP, _VP]),
     "sdm_collect_scalars": (_I, [_VP, _VP]),
     "sdm_set_bonded_forces": (_I, [_VP, _I, _VP, _D]),
     "sdm_set_alchemical": (_I, [_VP, _I, C.POINTER(SdmAlch)]),

@@ -128,10 +128,13 @@ class SDMContext:
         self._keep_pos = a  # async copy source must outlive the call
 
     def set_positions_all(self, xyz_all: np.ndarray):
-        """[n_replicas, n_atoms, 3] host doubles (ideally a PinnedArray view), one async copy."""
-        if xyz_all.dtype != np.float64 or not xyz_all.flags.c_contiguous or xyz_all.size != 3 * self.n * self.R:
-            raise ValueError("positions must be C-contiguous float64 [n_replicas, n_atoms, 3]")
-        _lib.check(self._L.sdm_set_positions_all(self._h, _ptr(xyz_all)))
+        """[n_replicas, n_atoms, 3] host doubles -- or float32 for the single-precision transfer
+        (half the PCIe bytes) -- ideally a PinnedArray view; one async copy."""
+        if xyz_all.dtype not in (np.float64, np.float32) or not xyz_all.flags.c_contiguous \
+                or xyz_all.size != 3 * self.n * self.R:
+            raise ValueError("positions must be C-contiguous float64 / float32 [n_replicas, n_atoms, 3]")
+        fn = self._L.sdm_set_positions_all if xyz_all.dtype == np.float64 else self._L.sdm_set_positions_all_f32
+        _lib.check(fn(self._h, _ptr(xyz_all)))
         self._keep_pos = xyz_all
 
     def read_results(self, forces_out: np.ndarray | None = None, want_scalars: bool = True):
@@ -149,10 +152,11 @@ class SDMContext:
     def enqueue_results(self, forces_out: np.ndarray | None = None):
         """Queue the device->host copies of forces (+ scalar blocks) behind the last eval(); no
         synchronisation.  Pair with synchronize() and collect_scalars()."""
-        if forces_out is not None and (forces_out.dtype != np.float64 or not forces_out.flags.c_contiguous
+        if forces_out is not None and (forces_out.dtype not in (np.float64, np.float32) or not forces_out.flags.c_contiguous
                                        or forces_out.size != 3 * self.n * self.R):
-            raise ValueError("forces_out must be C-contiguous float64 [n_replicas, n_atoms, 3]")
-        _lib.check(self._L.sdm_enqueue_results(self._h, _ptr(forces_out)))
+            raise ValueError("forces_out must be C-contiguous float64 / float32 [n_replicas, n_atoms, 3]")
+        f32 = forces_out is not None and forces_out.dtype == np.float32
+        _lib.check((self._L.sdm_enqueue_results_f32 if f32 else self._L.sdm_enqueue_results)(self._h, _ptr(forces_out)))
         self._keep_f = forces_out
 
     def collect_scalars(self):

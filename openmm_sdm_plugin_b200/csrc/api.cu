@@ -474,6 +474,24 @@ int sdm_set_positions_all(sdm_ctx* c, const double* xyz_all) {
     return SDM_OK;
 }
 
+static int ensure_stage32(sdm_ctx* c) {
+    if (c->d_stage32) return SDM_OK;
+    return dev_alloc(c, &c->d_stage32, 3 * (size_t)c->n * c->R);
+}
+
+int sdm_set_positions_all_f32(sdm_ctx* c, const float* xyz_all) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (!xyz_all) return fail(SDM_ERR_INVALID, "null positions");
+    if (int rc = ensure_stage32(c)) return rc;
+    const size_t count = 3 * (size_t)c->n * c->R;
+    SDM_CUDA(cudaMemcpyAsync(c->d_stage32, xyz_all, sizeof(float) * count, cudaMemcpyHostToDevice, c->stream));
+    sdm::launch_widen(count, c->d_stage32, c->d_pos, c->stream);
+    c->launches++;
+    SDM_CUDA(cudaGetLastError());
+    return SDM_OK;
+}
+
 int sdm_positions_device_ptr(sdm_ctx* c, int replica, double** d_xyz) {
     SDM_ON_CTX_DEVICE(c);
     if (int rc = check_ctx(c, replica)) return rc;
@@ -800,6 +818,22 @@ int sdm_enqueue_results(sdm_ctx* c, double* forces_all) {
                              cudaMemcpyDeviceToHost, c->stream));
     // the copy above carries the sticky status to the host; later evaluations start clean (an
     // evaluation that still runs on the stale list raises it again)
+    SDM_CUDA(cudaMemsetAsync(c->d_sticky, 0, sizeof(int) * (size_t)c->R, c->stream));
+    return SDM_OK;
+}
+
+int sdm_enqueue_results_f32(sdm_ctx* c, float* forces_all) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (forces_all) {
+        if (int rc = ensure_stage32(c)) return rc;
+        const size_t count = 3 * (size_t)c->n * c->R;
+        sdm::launch_narrow(count, c->B.F, c->d_stage32, c->stream);
+        c->launches++;
+        SDM_CUDA(cudaMemcpyAsync(forces_all, c->d_stage32, sizeof(float) * count, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SDM_CUDA(cudaMemcpyAsync(c->h_state, c->B.state, sizeof(sdm::ReplicaState) * (size_t)c->R,
+                             cudaMemcpyDeviceToHost, c->stream));
     SDM_CUDA(cudaMemsetAsync(c->d_sticky, 0, sizeof(int) * (size_t)c->R, c->stream));
     return SDM_OK;
 }

@@ -8,6 +8,8 @@
 // (there is no reuse), streaming cache hints for write-once data.
 #include <curand_kernel.h>
 
+#include <algorithm>
+
 #include "sdm_kernels.h"
 
 namespace sdm {
@@ -196,6 +198,27 @@ void launch_langevin_part2(int n, float4* posq, const float4* pos_delta, float4*
                            cudaStream_t s) {
     if (n <= 0) return;
     langevin_part2_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(n, posq, pos_delta, velm, step_size);
+}
+
+// FP32 <-> FP64 conversion of flat coordinate / force arrays for the single-precision transfer calls
+// (sdm_set_positions_all_f32 / sdm_enqueue_results_f32): 12 B/element, HBM bound, a few microseconds.
+namespace {
+__global__ void __launch_bounds__(256) widen_kernel(size_t count, const float* __restrict__ src, double* __restrict__ dst) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (double)src[i];
+}
+__global__ void __launch_bounds__(256) narrow_kernel(size_t count, const double* __restrict__ src, float* __restrict__ dst) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+}  // namespace
+void launch_widen(size_t count, const float* src, double* dst, cudaStream_t s) {
+    if (count == 0) return;
+    widen_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 148 * 16), 256, 0, s>>>(count, src, dst);
+}
+void launch_narrow(size_t count, const double* src, float* dst, cudaStream_t s) {
+    if (count == 0) return;
+    narrow_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 148 * 16), 256, 0, s>>>(count, src, dst);
 }
 
 void launch_kinetic_energy(int n, int R, const double* vel, const double* mass, double* ke, cudaStream_t s) {

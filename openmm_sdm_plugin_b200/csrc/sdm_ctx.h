@@ -23,6 +23,7 @@ struct sdm_ctx {
     sdm::EvalBuffers B{};
     std::vector<void*> allocs;          // every cudaMalloc of this ctx (freed in sdm_destroy)
     double* d_pos = nullptr;
+    float* d_stage32 = nullptr;         // [R][n][3] staging of the single-precision transfer calls
     double* d_fb = nullptr;
     double* d_disp = nullptr;
     int* d_group = nullptr;

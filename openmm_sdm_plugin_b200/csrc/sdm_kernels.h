@@ -109,6 +109,8 @@ void launch_md_update(int n, int R, double* pos, double* vel, const double* forc
                       double vscale, double fscale, double noisescale, double dt, const double* noise,
                       unsigned long long seed, unsigned long long step, const MdConstraints* C,
                       double* xprime, unsigned long long* ctl, int* flags, cudaStream_t s);
+void launch_widen(size_t count, const float* src, double* dst, cudaStream_t s);    // dst = (double)src
+void launch_narrow(size_t count, const double* src, float* dst, cudaStream_t s);   // dst = (float)src
 void launch_kinetic_energy(int n, int R, const double* vel, const double* mass, double* ke, cudaStream_t s);
 
 }  // namespace sdm

@@ -254,3 +254,34 @@ def test_column_layout_with_overfull_columns():
             assert np.array_equal(ctx.pairs(0), want)
     finally:
         del os.environ["SDMB200_LAYOUT"]
+
+
+def test_single_precision_transfers():
+    """sdm_set_positions_all_f32 / sdm_enqueue_results_f32: positions in and forces out cross PCIe as
+    float32 (the reference's OpenCL path holds them as float4); the device arithmetic is unchanged, so
+    the result is the FP64-transfer result of the float-rounded coordinates, narrowed."""
+    from openmm_sdm_plugin_b200.context import PinnedArray
+    case = S.cfg2()
+    n, R = case.system.n_atoms, 2
+    rng = np.random.default_rng(3)
+    x64 = np.stack([case.positions, case.positions + rng.normal(scale=0.003, size=(n, 3))])
+    x32 = PinnedArray((R, n, 3), np.float32)
+    f32 = PinnedArray((R, n, 3), np.float32)
+    x32.array[...] = x64
+    with SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=_lib.PAIR_CLUSTER) as ctx:
+        for r in range(R):
+            ctx.set_alchemical(r, case.alch)
+        ctx.set_positions_all(np.ascontiguousarray(x32.array.astype(np.float64)))   # the rounded coordinates, FP64 path
+        ctx.eval()
+        f64 = np.empty((R, n, 3))
+        sc64 = ctx.read_results(f64)
+        ctx.invalidate_list()
+        ctx.set_positions_all(x32.array)
+        ctx.eval()
+        ctx.enqueue_results(f32.array)
+        ctx.synchronize()
+        sc32 = ctx.collect_scalars()
+        for r in range(R):
+            assert sc32[r]["status"] == 0 and sc32[r]["n_pairs1"] == sc64[r]["n_pairs1"]
+            assert sc32[r]["u"] == sc64[r]["u"] and sc32[r]["E1"] == sc64[r]["E1"]
+        assert np.array_equal(f32.array, f64.astype(np.float32))
