@@ -280,6 +280,81 @@ def md_leg(case, R, args, device, stream, flush, states, rank, skin=None, nstlis
                     "(counted in steps_repeated_stale_list, its time is inside ms_per_step)"}
 
 
+def cfg3_leg(case, args, world, rank, device, stream, rounds=6, steps_per_round=10, n_windows=22):
+    """BASELINE.json configs[2]: the explicit-solvent fixture as a 22-window lambda ladder under replica
+    exchange, the windows dealt over the ranks ((3,3,3,3,3,3,2,2) on 8 GPUs).  Every replica runs
+    constrained Langevin dynamics on its GPU (sdm_md_step); every `steps_per_round` steps the ranks
+    all-gather (u_sc, state) -- the path's only collective, 16 bytes per replica -- run the same
+    Metropolis sweep and APPLY the new assignment (sdm_set_alchemical).  A fixed-size job: strong
+    scaling.  Device time between two events on the launching stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from openmm_sdm_plugin_b200 import exchange as X, system as S
+    from openmm_sdm_plugin_b200.context import SDMContext
+    counts = X.split_replicas(n_windows, world)
+    Rl, first = counts[rank], int(sum(counts[:rank]))
+    states = S.atm_lambda_schedule(n_windows)
+    n = case.system.n_atoms
+    kT = 1.380658e-23 * 6.0221367e23 / 1000.0 * 300.0
+    rng = np.random.default_rng(500 + rank)
+    with SDMContext(case.system, case.displacement, n_replicas=Rl, pair_mode=args.pair_mode, device=device,
+                    skin=args.md_skin, nstlist=args.md_nstlist) as c:
+        c.set_stream(stream.cuda_stream)
+        c.md_init(case.masses, 300.0, 0.1, 0.001, seed=4321 + rank)
+        c.md_set_constraints(case.constraint_pairs, case.constraint_dist, 1e-5)
+        state_of = np.arange(first, first + Rl)
+        for r in range(Rl):
+            c.set_alchemical(r, states[state_of[r]])
+            c.set_positions(r, case.positions)
+            c.md_set_velocities(r, rng.normal(size=(n, 3)) * np.sqrt(kT / case.masses)[:, None])
+        c.md_step(2 * steps_per_round)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stats, moved, same = {}, 0, True
+        e0.record(stream)
+        for k in range(rounds):
+            c.md_step(steps_per_round)
+            u_local = [c.scalars(r)["u_sc"] for r in range(Rl)]
+            if world > 1:
+                u_all, s_all = X.all_gather_replica_info(u_local, state_of, counts=counts)
+            else:
+                u_all, s_all = np.asarray(u_local), state_of.copy()
+            new_all = X.exchange_round(u_all, s_all, states, 300.0, seed=2024, round_index=k, stats=stats)
+            new_local = new_all[first:first + Rl]
+            for r in range(Rl):
+                if new_local[r] != state_of[r]:
+                    c.set_alchemical(r, states[int(new_local[r])])
+                    moved += 1
+            state_of = new_local.copy()
+            if world > 1:   # every rank must have reached the same assignment without a second collective
+                h = torch.tensor([float((new_all * (np.arange(n_windows) + 1)).sum())], dtype=torch.float64, device="cuda")
+                lo, hi = h.clone(), h.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                same = same and bool(lo.item() == hi.item())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        ok = all(c.scalars(r)["status"] == 0 for r in range(Rl))
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+    nsteps = rounds * steps_per_round
+    return {"workload": "cfg3: 22-window lambda ladder under replica exchange", "replicas_per_rank": counts,
+            "value": n_windows * nsteps / (ms * 1e-3), "unit": "replica-steps/s (whole job)", "scaling": "strong",
+            "ms_per_step": ms / nsteps, "ns_per_day_per_replica": nsteps / (ms * 1e-3) * 0.001 * 1e-3 * 86400,
+            "exchange_every_steps": steps_per_round, "exchange_rounds": rounds,
+            "swap_acceptance": stats.get("accepted", 0) / max(stats.get("proposed", 0), 1),
+            "state_changes_applied_on_rank0": moved, "same_assignment_on_all_ranks": bool(same), "status_ok": bool(ok),
+            "skin_nm": args.md_skin, "nstlist": args.md_nstlist,
+            "note": "constrained dynamics per replica (real masses, 1 fs), (u_sc, state) all-gather + Metropolis sweep + "
+                    "sdm_set_alchemical every %d steps; the ranks with the larger share set the pace" % steps_per_round}
+
+
 def main():
     # NCCL prints its version banner to stdout under NCCL_DEBUG=VERSION: keep stdout to the one JSON line
     ap = argparse.ArgumentParser()
@@ -301,6 +376,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-elementwise", action="store_true")
     ap.add_argument("--no-md-loop", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--md-skin", type=float, default=0.2, help="pair-list skin of the dynamics legs (nm): real motion wants a wider one")
+    ap.add_argument("--md-nstlist", type=int, default=40, help="upper limit of the list lifetime in the dynamics legs")
     ap.add_argument("--no-single-lambda", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
@@ -639,9 +717,18 @@ def main():
                                  "note": "one resident replica, positions in HBM, list rebuilds included, no L2 flush"}
     if rank == 0 and not args.no_md_loop and case.masses is not None:
         try:
-            line["md_loop"] = md_leg(case, R, args, local, stream, flush, states, rank)
+            line["md_loop"] = md_leg(case, R, args, local, stream, flush, states, rank, skin=args.md_skin,
+                                     nstlist=args.md_nstlist)
         except Exception as ex:   # an extra, never the reason for a missing bench line
             line["md_loop"] = {"error": str(ex)[:200]}
+    if not args.no_cfg3 and args.workload == "cfg2" and case.constraint_pairs is not None:
+        try:   # every rank takes part (the ladder is dealt over the ranks)
+            res = cfg3_leg(case, args, world, rank, local, stream)
+            if rank == 0:
+                line["cfg3"] = res
+        except Exception as ex:
+            if rank == 0:
+                line["cfg3"] = {"error": str(ex)[:200]}
     if rank == 0 and not args.no_elementwise:
         # the bandwidth-bound kernels of the path against the measured HBM copy bandwidth
         line["roofline_elementwise"] = elementwise_hbm(pk["hbm_gbs"])

@@ -44,9 +44,10 @@ def reduced_energy_matrix(u_sc, states, temperature):
     return beta * np.stack([bias_energy(s, u) for s in states], axis=1)
 
 
-def exchange_round(u_sc, state_of_replica, states, temperature, seed, round_index, n_sweeps=None):
+def exchange_round(u_sc, state_of_replica, states, temperature, seed, round_index, n_sweeps=None, stats=None):
     """New state index per replica after one round of Metropolis pair swaps.  Deterministic in
-    (inputs, seed, round_index): every rank computes the same answer."""
+    (inputs, seed, round_index): every rank computes the same answer.  stats (a dict) receives the
+    numbers of proposed and accepted swaps."""
     state_of = np.array(state_of_replica, dtype=np.int64, copy=True)
     n = len(state_of)
     if sorted(state_of.tolist()) != sorted(set(state_of.tolist())):
@@ -54,6 +55,7 @@ def exchange_round(u_sc, state_of_replica, states, temperature, seed, round_inde
     M = reduced_energy_matrix(u_sc, states, temperature)
     rng = np.random.Generator(np.random.Philox(key=[int(seed) & (2**64 - 1), int(round_index)]))
     n_sweeps = n * n if n_sweeps is None else n_sweeps
+    proposed = accepted = 0
     for _ in range(n_sweeps):
         i, j = rng.integers(0, n, size=2)
         if i == j:
@@ -61,29 +63,54 @@ def exchange_round(u_sc, state_of_replica, states, temperature, seed, round_inde
         si, sj = state_of[i], state_of[j]
         # swap the states of replicas i and j: delta = [W_sj(u_i) + W_si(u_j)] - [W_si(u_i) + W_sj(u_j)]
         delta = (M[i, sj] + M[j, si]) - (M[i, si] + M[j, sj])
+        proposed += 1
         if delta <= 0.0 or rng.random() < np.exp(-delta):
             state_of[i], state_of[j] = sj, si
+            accepted += 1
+    if stats is not None:
+        stats["proposed"] = stats.get("proposed", 0) + proposed
+        stats["accepted"] = stats.get("accepted", 0) + accepted
     return state_of
 
 
-def all_gather_replica_info(u_sc_local, state_local, group=None):
+def split_replicas(n_replicas: int, world: int):
+    """Replicas per rank when n_replicas lambda-windows are dealt over `world` GPUs as evenly as
+    possible, larger shares first: 22 over 8 -> (3, 3, 3, 3, 3, 3, 2, 2) (BASELINE.json configs[2])."""
+    base, extra = divmod(int(n_replicas), int(world))
+    return [base + (1 if r < extra else 0) for r in range(world)]
+
+
+def all_gather_replica_info(u_sc_local, state_local, group=None, counts=None):
     """The collective: (u_sc, state index) of every replica of every rank, in rank order.
-    Tensors live on the current CUDA device under NCCL and on the CPU under gloo."""
+    Tensors live on the current CUDA device under NCCL and on the CPU under gloo.  counts = replicas
+    per rank when the ranks hold different numbers (every rank then sends max(counts) rows, the
+    padding rows are dropped on arrival)."""
     import torch
     import torch.distributed as dist
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    t = torch.tensor(np.stack([np.asarray(u_sc_local, np.float64),
-                               np.asarray(state_local, np.float64)], axis=1), dtype=torch.float64, device=dev)
     world = dist.get_world_size(group)
-    out = torch.empty((world * t.shape[0], 2), dtype=torch.float64, device=dev)   # rank-major concatenation
+    rows = len(u_sc_local) if counts is None else max(counts)
+    mine = np.zeros((rows, 2))
+    mine[:len(u_sc_local), 0] = np.asarray(u_sc_local, np.float64)
+    mine[:len(u_sc_local), 1] = np.asarray(state_local, np.float64)
+    t = torch.tensor(mine, dtype=torch.float64, device=dev)
+    out = torch.empty((world * rows, 2), dtype=torch.float64, device=dev)   # rank-major concatenation
     dist.all_gather_into_tensor(out, t, group=group)
-    out = out.cpu().numpy().reshape(-1, 2)
+    out = out.cpu().numpy().reshape(world, rows, 2)
+    if counts is not None:
+        out = np.concatenate([out[r, :counts[r]] for r in range(world)], axis=0)
+    else:
+        out = out.reshape(-1, 2)
     return out[:, 0].copy(), out[:, 1].astype(np.int64)
 
 
-def replica_exchange_step(u_sc_local, state_local, states, temperature, seed, round_index, rank, group=None):
+def replica_exchange_step(u_sc_local, state_local, states, temperature, seed, round_index, rank, group=None,
+                          counts=None):
     """One exchange round for this rank's replicas; returns their new state indices."""
-    u_all, s_all = all_gather_replica_info(u_sc_local, state_local, group)
+    u_all, s_all = all_gather_replica_info(u_sc_local, state_local, group, counts)
     new_all = exchange_round(u_all, s_all, states, temperature, seed, round_index)
-    r_local = len(u_sc_local)
-    return new_all[rank * r_local:(rank + 1) * r_local]
+    if counts is None:
+        r_local = len(u_sc_local)
+        return new_all[rank * r_local:(rank + 1) * r_local]
+    first = int(sum(counts[:rank]))
+    return new_all[first:first + counts[rank]]

@@ -73,3 +73,38 @@ def test_two_ranks_agree_over_gloo():
     expected = X.exchange_round(u0, s0, S.atm_lambda_schedule(6), 300.0, 11, 0).tolist()
     assert n0 + n1 == expected                               # each rank took its own slice
     assert sorted(n0 + n1) == list(range(6))
+
+
+def test_split_of_22_windows_over_8_gpus():
+    assert X.split_replicas(22, 8) == [3, 3, 3, 3, 3, 3, 2, 2]        # BASELINE.json configs[2]
+    assert X.split_replicas(22, 1) == [22] and X.split_replicas(22, 4) == [6, 6, 5, 5]
+    assert sum(X.split_replicas(22, 3)) == 22
+
+
+def _ragged_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    counts = X.split_replicas(5, world)                      # 3 + 2: ranks hold different numbers of replicas
+    states = S.atm_lambda_schedule(5)
+    first = sum(counts[:rank])
+    rng = np.random.default_rng(200 + rank)
+    u_local = rng.normal(0.0, 50.0, size=counts[rank])
+    s_local = np.arange(first, first + counts[rank])
+    u_all, s_all = X.all_gather_replica_info(u_local, s_local, counts=counts)
+    new_local = X.replica_exchange_step(u_local, s_local, states, 300.0, seed=5, round_index=2, rank=rank, counts=counts)
+    ret[rank] = (u_all.tolist(), s_all.tolist(), new_local.tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_with_unequal_replica_counts_over_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ragged_worker, args=(2, port, ret), nprocs=2, join=True)
+    (u0, s0, n0), (u1, s1, n1) = ret[0], ret[1]
+    assert u0 == u1 and s0 == s1 == list(range(5)) and len(n0) == 3 and len(n1) == 2
+    expected = X.exchange_round(u0, s0, S.atm_lambda_schedule(5), 300.0, 5, 2).tolist()
+    assert n0 + n1 == expected and sorted(n0 + n1) == list(range(5))
