@@ -355,6 +355,62 @@ def cfg3_leg(case, args, world, rank, device, stream, rounds=6, steps_per_round=
                     "sdm_set_alchemical every %d steps; the ranks with the larger share set the pace" % steps_per_round}
 
 
+def sweep_leg(args, device, stream, peak_tflops, quick=False):
+    """The other configurations of BASELINE.json next to the headline workload, each measured the same
+    way (resident evaluations, CUDA events on the launching stream, list rebuilds included, pair
+    kernel bracketed on its own): cfg1 (230 atoms, all-pairs kernel) at growing replica batches, cfg4
+    (synthetic 50 k atoms x 16 replicas), cfg5 (5 k .. 500 k atoms at 1 and 8 replicas)."""
+    import torch
+    from openmm_sdm_plugin_b200 import system as S
+    from openmm_sdm_plugin_b200.context import SDMContext
+    plan = [("cfg1", r) for r in (16, 128, 512)] + [("synthetic:50000", 16)]
+    sizes = (5000, 20000, 100000) if quick else (5000, 10000, 20000, 50000, 100000, 200000, 500000)
+    plan += [("synthetic:%d" % n, r) for n in sizes for r in (1, 8)]
+    out = []
+    for wl, R in plan:
+        try:
+            case, name = load_case(wl)
+            n = case.system.n_atoms
+            rng = np.random.default_rng(9)
+            with SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=args.pair_mode, device=device,
+                            skin=args.skin, nstlist=args.nstlist) as c:
+                c.set_stream(stream.cuda_stream)
+                for r in range(R):
+                    c.set_alchemical(r, case.alch)
+                    c.set_positions(r, case.positions + (rng.normal(scale=0.002, size=(n, 3)) if r else 0.0))
+                for _ in range(3):
+                    c.eval()
+                torch.cuda.synchronize()
+                k = 20 if n * R < 2_000_000 else 10
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(k):
+                    c.eval()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / k
+                c.set_timing(True)
+                pk = []
+                for _ in range(3):
+                    c.eval()
+                    pk.append(c.last_timing()[0])
+                torch.cuda.synchronize()
+                c.set_timing(False)
+                sc = c.read_results(None)
+                mode = int(c.info("pair_mode"))
+            pairs = sum(x["n_pairs1"] + x["n_moved2"] for x in sc)
+            flop = FLOP_PER_PAIR[int(case.system.method)] * pairs
+            pm = float(np.median(pk))
+            out.append({"workload": wl, "n_atoms": n, "replicas": R, "pair_mode": {1: "allpairs", 2: "cluster"}[mode],
+                        "evals_per_s": R / (ms * 1e-3), "ms_per_step": ms, "pair_kernel_ms": pm,
+                        "roofline_frac": flop / (pm * 1e-3) / 1e12 / peak_tflops,
+                        "roofline_frac_step": flop / (ms * 1e-3) / 1e12 / peak_tflops,
+                        "status_ok": all(x["status"] == 0 for x in sc)})
+        except Exception as ex:
+            out.append({"workload": wl, "replicas": R, "error": str(ex)[:160]})
+    return out
+
+
 def main():
     # NCCL prints its version banner to stdout under NCCL_DEBUG=VERSION: keep stdout to the one JSON line
     ap = argparse.ArgumentParser()
@@ -377,6 +433,8 @@ def main():
     ap.add_argument("--no-elementwise", action="store_true")
     ap.add_argument("--no-md-loop", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the cfg1 / cfg4 / cfg5 legs")
+    ap.add_argument("--sweep-quick", action="store_true")
     ap.add_argument("--md-skin", type=float, default=0.2, help="pair-list skin of the dynamics legs (nm): real motion wants a wider one")
     ap.add_argument("--md-nstlist", type=int, default=40, help="upper limit of the list lifetime in the dynamics legs")
     ap.add_argument("--no-single-lambda", action="store_true")
@@ -641,19 +699,21 @@ def main():
     achieved = flop / (pair_ms_avg * 1e-3) / 1e12
     peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     mode = int(ctx.info("pair_mode"))
+    fma_measured = ctx.info("fp32_fma_tflops_measured")   # sustained packed-FMA rate of THIS device, timed in this run
     # DRAM traffic of the dominant kernel comes from the committed ncu capture of this very
     # configuration (profiles/): a number measured under a profiler is never timed here
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_pair_kernel_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_pair_kernel_traffic.json")))
         if tr["workload"] == args.workload and tr["replicas_per_gpu"] == R and mode == 2:
             traffic = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "fp32_simt", "bound_note": "neither hbm nor tensor: the pair kernel is bound by the FP32 SIMT pipe (SURVEY.md 8d)", "kernel": "pair_cluster_kernel" if mode == 2 else "allpairs_kernel",
+    roofline = {"bound": "fp32_simt", "bound_note": "neither hbm nor tensor: the pair kernel is bound by the FP32 SIMT pipe (SURVEY.md 8d)", "kernel": "pair_row_kernel" if mode == 2 else "allpairs_kernel",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json)" % pk["source"],
+                "peak_fma_measured_in_this_run": fma_measured, "frac_of_measured_fma_peak": achieved / fma_measured if fma_measured else None,
                 "algorithmic_pairs_per_launch": algo_pairs, "flop_per_pair": FLOP_PER_PAIR[int(case.system.method)],
                 "kernel_ms": pair_ms_avg, "kernel_share_of_step": pair_ms_avg * args.steps / t_ms}
 
@@ -711,10 +771,37 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             ms1 = e0.elapsed_time(e1) / ns
-            assert c1.scalars(0)["status"] == 0
+            sc1 = c1.scalars(0)
+            assert sc1["status"] == 0
+            # the evaluations between two list builds alone (the latency a one-Context adapter sees on
+            # most steps), and the pair kernel alone
+            c1.invalidate_list()
+            c1.eval()
+            torch.cuda.synchronize()
+            nb = max(args.nstlist - 2, 1)
+            e0.record(stream)
+            for _ in range(nb):
+                c1.eval()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms1_nobuild = e0.elapsed_time(e1) / nb
+            c1.set_timing(True)
+            pk1 = []
+            for _ in range(5):
+                c1.eval()
+                pk1.append(c1.last_timing()[0])
+            torch.cuda.synchronize()
+            c1.set_timing(False)
+        flop1 = FLOP_PER_PAIR[int(case.system.method)] * (sc1["n_pairs1"] + sc1["n_moved2"])
         line["single_lambda"] = {"value": 1e3 / ms1, "unit": "evals/s", "ms_per_step": ms1, "replicas": 1,
+                                 "ms_per_step_between_list_builds": ms1_nobuild,
+                                 "pair_kernel_ms": float(np.median(pk1)),
+                                 "roofline_frac_pair_kernel": flop1 / (float(np.median(pk1)) * 1e-3) / 1e12 / peak,
+                                 "roofline_frac_step": flop1 / (ms1 * 1e-3) / 1e12 / peak,
                                  "ns_per_day_upper_bound": 1e3 / ms1 * 1e-6 * 86400,
-                                 "note": "one resident replica, positions in HBM, list rebuilds included, no L2 flush"}
+                                 "note": "BASELINE.json configs[1] as worded: ONE resident replica, positions in HBM, list rebuilds "
+                                         "(every nstlist evaluations) included in ms_per_step, no L2 flush; latency bound: the "
+                                         "critical path is refresh -> pair kernel (one unit per resident warp) -> scalars -> mix"}
     if rank == 0 and not args.no_md_loop and case.masses is not None:
         try:
             line["md_loop"] = md_leg(case, R, args, local, stream, flush, states, rank, skin=args.md_skin,
@@ -729,6 +816,8 @@ def main():
         except Exception as ex:
             if rank == 0:
                 line["cfg3"] = {"error": str(ex)[:200]}
+    if rank == 0 and world == 1 and not args.no_sweep and args.workload == "cfg2":
+        line["sweep"] = sweep_leg(args, local, stream, peak, quick=args.sweep_quick)
     if rank == 0 and not args.no_elementwise:
         # the bandwidth-bound kernels of the path against the measured HBM copy bandwidth
         line["roofline_elementwise"] = elementwise_hbm(pk["hbm_gbs"])

@@ -941,6 +941,7 @@ int sdm_get_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "list_age") *value = c->list_valid ? (double)c->list_age : 0.0;   // evaluations since the list was built
     else if (k == "e_dispersion") *value = c->T.e_disp;
     else if (k == "num_sms") *value = c->num_sms;
+    else if (k == "fp32_fma_tflops_measured") *value = sdm::measure_fp32_fma_tflops(c->num_sms, c->stream);   // ~1 ms of FMAs
     else if (sdm_ctx_pairlist_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
     else return fail(SDM_ERR_INVALID, "unknown info key: " + k);
     return SDM_OK;

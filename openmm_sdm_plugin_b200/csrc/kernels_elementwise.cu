@@ -221,6 +221,48 @@ void launch_narrow(size_t count, const double* src, float* dst, cudaStream_t s) 
     narrow_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 148 * 16), 256, 0, s>>>(count, src, dst);
 }
 
+// Sustained FP32 FMA rate of the device this library runs on: the denominator of the pair kernel's
+// roofline, measured instead of derived from the clock.  Eight independent packed FMA chains per
+// thread (fma.rn.f32x2, the instruction the pair kernel is made of), 8 x 256 threads per SM.
+namespace {
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float* sink) {
+    unsigned long long p[8];
+    const unsigned long long m = ((unsigned long long)__float_as_uint(0.999f) << 32) | __float_as_uint(0.999f);
+    const unsigned long long a = ((unsigned long long)__float_as_uint(seed) << 32) | __float_as_uint(seed);
+#pragma unroll
+    for (int c = 0; c < 8; c++) p[c] = a + c;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[c]) : "l"(m), "l"(a));
+    }
+    unsigned long long x = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) x ^= p[c];
+    if (x == 0x1234567ull) sink[0] = 1.f;
+}
+}  // namespace
+double measure_fp32_fma_tflops(int num_sms, cudaStream_t s) {
+    float* sink = nullptr;
+    if (cudaMalloc(&sink, sizeof(float)) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 40000, blocks = num_sms * 8;
+    fma_peak_kernel<<<blocks, 256, 0, s>>>(2000, 1.0f, sink);   // warm-up (clocks)
+    cudaEventRecord(e0, s);
+    fma_peak_kernel<<<blocks, 256, 0, s>>>(iters, 1.0f, sink);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (!(ms > 0.f)) return 0.0;
+    const double flop = (double)blocks * 256 * 8 * 2 * 2 * (double)iters;   // 8 chains x 2 halves x (mul + add)
+    return flop / (ms * 1e-3) / 1e12;
+}
+
 void launch_kinetic_energy(int n, int R, const double* vel, const double* mass, double* ke, cudaStream_t s) {
     if (R <= 0) return;
     kinetic_energy_kernel<<<R, 256, 0, s>>>(n, vel, mass, ke);

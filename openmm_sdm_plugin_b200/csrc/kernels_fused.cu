@@ -780,11 +780,13 @@ exceptions_kernel(Topology T, const double* __restrict__ pos_all, long long* __r
 // runs SoftCoreF + bias + bookkeeping on the device -- no host round trip (the reference pays
 // three D->H energy reads per step).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div) {
-    // all seven sums in ONE pass: independent loads in flight together, one barrier, fixed order
-    __shared__ double s_d[4][8];
-    __shared__ long long s_l[3][8];
+    // all seven sums in ONE pass: independent loads in flight together, one barrier, fixed order.
+    // 1024 threads: the per-unit partials of a replica (a few thousand) are two or three loads per
+    // thread instead of a chain of ten -- this kernel sits on the critical path of every evaluation
+    __shared__ double s_d[4][32];
+    __shared__ long long s_l[3][32];
     const int r = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p0 = B.part_off[r], np_ = B.part_off[r + 1] - p0;
@@ -813,7 +815,7 @@ scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div) {
     double ep = 0.0, ee = 0.0, ue = 0.0, ul = 0.0;
     long long c = 0, m1 = 0, m2 = 0;
     if (threadIdx.x == 0)
-        for (int w = 0; w < 8; w++) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
             ep += s_d[0][w]; ee += s_d[1][w]; ue += s_d[2][w]; ul += s_d[3][w];
             c += s_l[0][w]; m1 += s_l[1][w]; m2 += s_l[2][w];
         }
@@ -929,7 +931,7 @@ void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) 
 
 void launch_scalars(const Topology& T, const EvalBuffers& B, double e_scale, int c_div,
                     cudaStream_t s) {
-    scalars_kernel<<<B.R, 256, 0, s>>>(T, B, e_scale, c_div);
+    scalars_kernel<<<B.R, 1024, 0, s>>>(T, B, e_scale, c_div);
 }
 
 void launch_mix(const Topology& T, const EvalBuffers& B, int zero_acc, cudaStream_t s) {

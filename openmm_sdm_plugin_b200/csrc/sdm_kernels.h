@@ -111,6 +111,7 @@ void launch_md_update(int n, int R, double* pos, double* vel, const double* forc
                       double* xprime, unsigned long long* ctl, int* flags, cudaStream_t s);
 void launch_widen(size_t count, const float* src, double* dst, cudaStream_t s);    // dst = (double)src
 void launch_narrow(size_t count, const double* src, float* dst, cudaStream_t s);   // dst = (float)src
+double measure_fp32_fma_tflops(int num_sms, cudaStream_t s);   // sustained packed-FMA rate (TFLOP/s), synchronises
 void launch_kinetic_energy(int n, int R, const double* vel, const double* mass, double* ke, cudaStream_t s);
 
 }  // namespace sdm

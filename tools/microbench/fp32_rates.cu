@@ -72,10 +72,17 @@ void run(const char* name, double instr_per_chain_step, float* out, long long* c
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    long long h[4096]; cudaMemcpy(h, cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
-    double avg = 0; for (int i = 0; i < grid; i++) avg += h[i]; avg /= grid;
+    // rate from the kernel's own duration (CUDA events) and the SM clock the device reports: the
+    // whole grid is resident at once (blocks_per_sm <= 8 blocks of 256 threads), so
+    // warp-instructions per SM / (ms * clock) is the sustained issue rate per SM.  (Per-block clock64
+    // deltas, used before, under-count the time of blocks that share a scheduler: rates above the
+    // 4/clk/SM issue limit came out of that.)
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const double clocks = (double)ms * 1e-3 * (double)khz * 1e3;
     const double warp_instr = (double)IT * CH * instr_per_chain_step * 8.0 * blocks_per_sm;  // per SM
-    printf("%-28s blocks/SM=%d  cycles=%9.0f  warp-instr/clk/SM=%6.3f  (%.3f ms)\n", name, blocks_per_sm, avg, warp_instr / avg, ms);
+    printf("%-28s blocks/SM=%d  warp-instr/clk/SM=%6.3f  (%.3f ms at %.3f GHz)\n", name, blocks_per_sm, warp_instr / clocks, ms,
+           khz * 1e-6);
 }
 
 int main() {
