@@ -1,9 +1,9 @@
-// nblist_core.h -- cluster-pair list construction, written once as per-item bodies that compile
-// both for the device (thin __global__ wrappers in pairlist.cu) and for the host (the CPU
-// checker tests/hostcheck builds from this same header with g++ to validate pair coverage
-// against the oracle without a GPU).  No reference code corresponds to this: the reference
-// delegates neighbour lists to OpenMM; the layout below is designed
-// for the sm_100a pair kernel in kernels_cluster.cu.
+// nblist_core.h -- pair list construction, written once as per-item bodies that compile both
+// for the device (thin __global__ wrappers in pairlist.cu) and for the host (the CPU checker
+// tests/hostcheck builds from this same header with g++ to validate pair coverage against the
+// oracle without a GPU).  No reference code corresponds to this: the reference delegates
+// neighbour lists to OpenMM; the layout below is designed for the
+// sm_100a pair kernel in kernels_rows.cu.
 //
 // Layout
 //   * replicas live in disjoint cell ranges of ONE global index space: global cell
@@ -19,14 +19,13 @@
 //     clusters, so padding exists only at the top of a column (0.8 % dummy slots instead of 6.3 %
 //     on the 20 k-atom fixture) and the imasks are denser: 9 % fewer tiles, 15 % fewer entries,
 //     35.5 % instead of 31.8 % useful pairs per tile than with geometric 3-D cells of ~52 atoms.
-//   * an i-supercluster (sci) is a run of <= 8 clusters of one cell; its list holds j-cluster
-//     entries {cj | shift<<26, imask | mask_index<<8}; imask bit ci says cluster ci of the sci
-//     interacts with j-cluster cj (an 8 x 8 "tile").  Every unordered cluster pair is owned by
-//     exactly one side (the lower cluster index) and the diagonal uses a triangle mask, so each
-//     atom pair is evaluated once.
-//   * exclusion masks: 16 words per masked entry; the pair kernel's lane (tj, ti) = (lane>>2,
-//     lane&3) evaluates i-atoms ti and ti+4 of a cluster against j-atom tj, so word 2*ci+h holds
-//     the pairs of i-atoms 4h..4h+3: bit (ja*4 + (ia&3)) == bit `lane`.
+//   * an i-supercluster (sci) is a run of <= 8 clusters of one cell; the search gives it j-cluster
+//     entries {cj | shift<<26, imask}; imask bit ci says cluster ci of the sci has an atom within
+//     rlist of an atom of j-cluster cj.  Every unordered cluster pair is owned by exactly one side
+//     (the lower cluster index) and a cluster against itself keeps the triangle j > i, so each atom
+//     pair is evaluated once.
+//   * the entries are an intermediate: the pair kernel walks per-atom j ROWS derived from them
+//     (stage 5 below), with exclusions and the triangle folded into per-entry allow words.
 #pragma once
 
 #include <stdint.h>
@@ -45,7 +44,6 @@ namespace nbl {
 constexpr int kClusterSize = 8;      // atoms per i-cluster
 constexpr int kJGroup = 8;           // atoms per j-group (a whole cluster)
 constexpr int kMaxCi = 8;            // clusters per supercluster
-constexpr int kMaskWords = 2 * kMaxCi;  // words per exclusion-mask set
 constexpr int kCoordBits = 16;       // in-cell coordinate resolution of the sort key
 constexpr int kSubBits = kCoordBits + 2;  // sort key = cell << 18 | kd bucket (2 bits) << 16 | coordinate
 constexpr int kMaxSpan = 6;          // search stencil is at most kMaxSpan cells per dimension
@@ -488,36 +486,6 @@ SDM_HD void entry_hits(const SearchView& V, const SciDesc& sd, uint32_t w0, uint
     }
 }
 
-// ---- stage 4: exclusion masks -------------------------------------------------------------------
-// Resolve an excluded atom pair (slots sa, sb) to (i-slot, j-slot) under the ownership rule.
-SDM_HD void exclusion_roles(int sa, int sb, int* si, int* sj) {
-    const int A = sa / kClusterSize, B = sb / kClusterSize;
-    if (A == B) {
-        *si = sa < sb ? sa : sb;   // triangle keeps j-slot > i-slot
-        *sj = sa < sb ? sb : sa;
-    } else if (owner_is_i(A, B)) {
-        *si = sa; *sj = sb;
-    } else {
-        *si = sb; *sj = sa;
-    }
-}
-
-// Mask word and bit of the atom pair (i-slot si, j-slot sj) inside the mask set of its entry.
-SDM_HD int mask_word(int ci, int si) { return 2 * ci + ((si % kClusterSize) >> 2); }
-SDM_HD uint32_t mask_bit(int si, int sj) {
-    return 1u << ((sj % kJGroup) * 4 + ((si % kClusterSize) & 3));
-}
-
-// Triangle mask word of cluster-against-itself for the i-atom half h (i-atoms 4h..4h+3): keeps
-// the pairs with j index > i index.
-SDM_HD uint32_t triangle_mask(int h) {
-    uint32_t m = 0;
-    for (int tj = 0; tj < kJGroup; tj++)
-        for (int ti = 0; ti < 4; ti++)
-            if (tj > 4 * h + ti) m |= 1u << (tj * 4 + ti);
-    return m;
-}
-
 // ---- stage 5: per-atom j rows -------------------------------------------------------------------
 // The pair kernel does not walk the cluster-pair entries themselves: every i-group (G = 1 or 2
 // consecutive clusters of a supercluster, 8*G atoms) gets a ROW of individual j-atoms -- the atoms
@@ -527,6 +495,39 @@ SDM_HD uint32_t triangle_mask(int h) {
 // 50 % (G = 1) on the 20 k-atom fixture.  Row entries with an exclusion / triangle mask come first
 // and carry an allow word (bit a = i-atom a of the group may interact with this j-atom).
 constexpr int kRowChunkSteps = 32;   // warp steps (32 j-atoms each) per work unit, at most 32
+
+// What the row construction needs to know about a j-cluster, gathered once per list build: the slot
+// range its atoms' excluded partners fall into (lo > hi: none) -- an i-group outside that range has
+// no exclusion with the cluster, which is the case for all but a handful of (entry, group) cells --
+// and which of its atoms carry no Lennard-Jones term.
+struct ClusterInfo {
+    int excl_lo, excl_hi;
+    uint32_t nolj;      // bit tj: epsilon of atom tj is zero (or the slot is a dummy)
+    uint32_t pad;
+};
+
+// par2: [nslot][2] floats (sigma/2, 2*sqrt(eps))
+SDM_HD ClusterInfo cluster_info(int c, const int* atom, const float* par2, const int* excl_start, const int* excl_idx,
+                                const int* slot_of, int n) {
+    ClusterInfo ci;
+    ci.excl_lo = 0x7fffffff;
+    ci.excl_hi = -1;
+    ci.nolj = 0u;
+    ci.pad = 0u;
+    for (int tj = 0; tj < kJGroup; tj++) {
+        const int s = c * kJGroup + tj;
+        if (par2[2 * (size_t)s + 1] == 0.f) ci.nolj |= 1u << tj;
+        const int ga = atom[s];
+        if (ga < 0) continue;
+        const int r = ga / n, a = ga - r * n;
+        for (int k = excl_start[a]; k < excl_start[a + 1]; k++) {
+            const int sp = slot_of[r * n + excl_idx[k]];
+            if (sp < ci.excl_lo) ci.excl_lo = sp;
+            if (sp > ci.excl_hi) ci.excl_hi = sp;
+        }
+    }
+    return ci;
+}
 
 // bit t of the result = any of bits 4t..4t+3 of a warp ballot over lanes (tj, ti) = (lane>>2, lane&3)
 SDM_HD uint32_t compress_nibbles(uint32_t b) {
@@ -550,22 +551,40 @@ SDM_HD uint32_t row_hits(uint32_t jh_lo, uint32_t jh_hi, uint32_t imask, int g, 
     return h;
 }
 
-// Allow word of j-atom tj for i-group g: bit (8*q + ia) = i-atom ia of the group's q-th cluster may
-// interact with it.  maskset = the entry's 16 exclusion words (nullptr: none).  A cluster of the
-// group that is not in imask is switched off when the entry has a mask set or its j-cluster lies
-// in the same supercluster (ownership / triangle); otherwise it stays on -- its atoms are further
-// than rlist from the whole j-cluster, and an all-ones word keeps the entry on the unmasked path.
-SDM_HD uint32_t row_allow(const uint32_t* maskset, uint32_t imask, bool same_sci, int g, int G, int tj) {
+// Allow word of the j-atom tj of an entry (j-cluster B under image `code`) for i-group g of the
+// supercluster sd: bit (8*q + ia) = i-atom ia of the group's q-th cluster may interact with it.
+//   * a cluster against itself under the zero shift keeps the triangle j index > i index;
+//   * a cluster of the group that is not in imask is switched off when B lies in the same
+//     supercluster (the other cluster owns that pair); elsewhere it stays on -- its atoms are further
+//     than rlist from the whole j-cluster, and an all-ones word keeps the entry on the unmasked path;
+//   * every excluded partner of the j-atom (excl_start / excl_idx: the System's exclusions as a CSR
+//     over atoms, both directions) that sits in the group is switched off.
+// atom[slot] = replica*n + atom, slot_of = its inverse.
+// walk_excl = false skips the exclusion walk: the caller knows that no excluded partner of any atom
+// of j-cluster B has its slot inside the i-group (ClusterInfo below).
+SDM_HD uint32_t row_allow(const SciDesc& sd, uint32_t imask, int B, uint32_t code, int g, int G, int tj,
+                          const int* excl_start, const int* excl_idx, const int* slot_of, const int* atom, int n,
+                          bool walk_excl = true) {
+    const bool same_sci = B >= sd.c0 && B < sd.c0 + sd.nci;
     uint32_t allow = 0;
     for (int q = 0; q < G; q++) {
         const int ci = g * G + q;
         uint32_t bits = 0xffu;
         if (!((imask >> ci) & 1u)) {
-            if (maskset || same_sci) bits = 0u;
-        } else if (maskset) {
-            bits = ((maskset[2 * ci] >> (4 * tj)) & 0xfu) | (((maskset[2 * ci + 1] >> (4 * tj)) & 0xfu) << 4);
+            if (same_sci) bits = 0u;
+        } else if (code == kShiftZero && B == sd.c0 + ci) {
+            bits = (1u << tj) - 1u;
         }
         allow |= bits << (8 * q);
+    }
+    if (!walk_excl) return allow;
+    const int ga = atom[B * kJGroup + tj];
+    if (ga < 0) return 0u;
+    const int r = ga / n, a = ga - r * n;
+    const int first = (sd.c0 + g * G) * kClusterSize;
+    for (int k = excl_start[a]; k < excl_start[a + 1]; k++) {
+        const int rel = slot_of[r * n + excl_idx[k]] - first;
+        if (rel >= 0 && rel < G * kClusterSize) allow &= ~(1u << rel);
     }
     return allow;
 }

@@ -1,5 +1,6 @@
-// pairlist.cu -- builds the cluster-pair list on the device (per-item bodies from
-// nblist_core.h, CUB for the sort and the scans) and drives the cluster pair kernel.
+// pairlist.cu -- builds the pair list on the device (per-item bodies from nblist_core.h, CUB for
+// the sorts and the scans): cell-sorted 8-atom clusters, cluster-pair entries from the search and
+// the exact prune, and from those the per-atom j rows the pair kernel (kernels_rows.cu) walks.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -19,17 +20,14 @@ using nbl::BBox;
 using nbl::Grid;
 using nbl::SciDesc;
 
-constexpr int kChunk = 32;  // j-group entries per work unit (one per lane; shorter units measured slower at every size)
-
 struct PairList {
     Grid G{};
     int ncells = 0;          // R * ncell
     int cell_cap = 0;        // allocated cells per replica
     int nslot_cap = 0, ncl_cap = 0, nsci_cap = 0;
-    size_t entries_cap = 0, masks_cap = 0, units_cap = 0, items_cap = 0;
-    int chunk = kChunk;
+    size_t entries_cap = 0, items_cap = 0;
     // sizes of the current list (host copies)
-    int nslot = 0, ncl = 0, nsci = 0, nentries = 0, nmasks = 0, nunits = 0, scan_max = 0;
+    int nslot = 0, ncl = 0, nsci = 0, nentries = 0, scan_max = 0;
 
     uint64_t *keys = nullptr, *keys_sorted = nullptr;
     int *vals = nullptr, *vals_sorted = nullptr;
@@ -39,23 +37,24 @@ struct PairList {
     float2* par = nullptr;
     int *atom = nullptr, *img = nullptr, *slot_of = nullptr;
     BBox *cl_box = nullptr, *sci_box = nullptr, *cell_box = nullptr;
+    nbl::ClusterInfo* cl_info = nullptr;   // [ncl] exclusion-partner slot range and LJ-free atoms of every cluster
     int use_columns = 1;        // column layout (default) or geometric 3-D cells (SDMB200_LAYOUT=cells)
     SciDesc* sci = nullptr;
     int* cl_sci = nullptr;
     int *item_count = nullptr, *item_off = nullptr;
     uint2* entries = nullptr;
-    int *entry_flag = nullptr, *entry_midx = nullptr, *entry_sci = nullptr;
+    int* entry_sci = nullptr;
     // raw (box-pruned) entries of the search, before the exact prune + compaction
     uint2* raw_entries = nullptr;
-    int *raw_flag = nullptr, *raw_sci = nullptr, *raw_c0nci = nullptr, *raw_keep = nullptr, *raw_pos = nullptr;
+    int *raw_sci = nullptr, *raw_c0nci = nullptr, *raw_keep = nullptr, *raw_pos = nullptr;
     size_t raw_cap = 0;
     int nraw = 0;
-    // per-atom j rows (nblist_core.h stage 5): the list the product kernel walks
-    int use_rows = 1;           // 0: the cluster kernel walks the entries (SDMB200_PAIR_KERNEL=cluster)
+    // per-atom j rows (nblist_core.h stage 5): the list the pair kernel walks
     int row_group = 1;          // clusters per i-group (SDMB200_ROW_GROUP = 1 | 2)
     int row_chunk = nbl::kRowChunkSteps;   // warp steps per unit (SDMB200_ROW_CHUNK)
     uint2 *raw_jhit = nullptr, *entry_jhit = nullptr;   // per (cluster of the sci, j-atom) hit bits of an entry
-    int *row_cnt = nullptr, *row_scan = nullptr;        // [2 * (8 / G) * nentries + 1] masked / unmasked counts
+    int* row_cnt = nullptr;     // [nentries][8 / G][3] cell counts, then within-segment offsets (entry-major)
+    int *seg_total = nullptr, *seg_off = nullptr;       // [nsci * (8 / G) * 3 + 1] row segments
     size_t row_cnt_cap = 0;
     uint32_t* jent = nullptr;
     uint16_t* jallow = nullptr;
@@ -69,17 +68,12 @@ struct PairList {
     int njent = 0, nrunits = 0;
     int dummy_slot = 0;
     int* sci_off = nullptr;     // [nsci+1] first (compacted) entry of every sci
-    uint32_t* masks = nullptr;
-    int *sci_nunits = nullptr, *sci_unit_off = nullptr;
-    Unit* units = nullptr;
     int* part_off = nullptr;    // [R+1]
     int* unit_counter = nullptr; // work counter of the persistent pair kernel
     unsigned int* max_disp2 = nullptr;   // largest squared displacement since the build (float bits)
     double* epart = nullptr;
     long long* cpart = nullptr;
     double* minmax = nullptr;   // [6] non-periodic extent reduction
-    const int* excl_pairs = nullptr;  // [2*n_excl_unique] a<b
-    int n_excl = 0;
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
     int* h_counts = nullptr;    // pinned [8]
@@ -282,13 +276,11 @@ struct CountEmit {
 };
 struct FillEmit {
     uint2* out;
-    int* flag;
     int* esci;
     int* c0nci;      // first cluster | cluster count << 27 of the owning supercluster (for the prune pass)
     int base, isci, sd_c0nci;
-    __device__ void operator()(int k, uint32_t w0, uint32_t imask, bool diag) const {
+    __device__ void operator()(int k, uint32_t w0, uint32_t imask, bool) const {
         out[base + k] = make_uint2(w0, imask);
-        flag[base + k] = diag ? 1 : 0;
         esci[base + k] = isci;
         c0nci[base + k] = sd_c0nci;
     }
@@ -301,14 +293,14 @@ __global__ void search_count_kernel(nbl::SearchView V, int nsci, int noff, int* 
 }
 
 __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
-                                   const int* __restrict__ item_off, uint2* entries, int* flag,
-                                   int* esci, int* c0nci, int cap) {
+                                   const int* __restrict__ item_off, uint2* entries, int* esci, int* c0nci,
+                                   int cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsci * noff) return;
     const int base = item_off[t];
     if (base >= cap) return;
     const SciDesc sd = V.sci[t / noff];
-    nbl::search_any(V, t / noff, t % noff, FillEmit{entries, flag, esci, c0nci, base, t / noff, sd.c0 | (sd.nci << 27)});
+    nbl::search_any(V, t / noff, t % noff, FillEmit{entries, esci, c0nci, base, t / noff, sd.c0 | (sd.nci << 27)});
 }
 
 // Exact pruning, one warp per raw entry: imask bit ci survives only if some real atom pair of
@@ -316,8 +308,7 @@ __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
 // nbl::prune_imask.  Lane (tj, ti) = (lane>>2, lane&3) tests j-atom tj against i-atoms ti, ti+4.
 __global__ void __launch_bounds__(128)
 prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ raw_c0nci,
-             int* __restrict__ raw_flag, const float4* __restrict__ posq, int* __restrict__ keep,
-             uint2* __restrict__ jhit) {
+             const float4* __restrict__ posq, int* __restrict__ keep, uint2* __restrict__ jhit) {
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (e >= nraw) return;
@@ -331,8 +322,8 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
     xj.x += (float)nbl::shift_x(code) * G.boxf[0];
     xj.y += (float)nbl::shift_y(code) * G.boxf[1];
     xj.z += (float)nbl::shift_z(code) * G.boxf[2];
-    uint32_t todo = ent.y & 0xffu, out = 0u;
-    uint32_t jh_lo = 0u, jh_hi = 0u;   // per cluster of the sci: which j-atoms have an i-atom within rlist
+    uint32_t todo = ent.y & 0xffu;
+    uint32_t mine = 0u;   // bit ci: one of this lane's two atom pairs with cluster ci is inside rlist
     while (todo) {
         const int ci = __ffs(todo) - 1;
         todo &= todo - 1u;
@@ -345,26 +336,30 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
             dx = b.x - xj.x; dy = b.y - xj.y; dz = b.z - xj.z;
             hit = hit || (b.x < 0.5f * nbl::kFar && dx * dx + dy * dy + dz * dz < G.rlist2);
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-        if (bal) {
-            out |= 1u << ci;
-            const uint32_t h8 = nbl::compress_nibbles(bal);
-            if (ci < 4) jh_lo |= h8 << (8 * ci);
-            else jh_hi |= h8 << (8 * (ci - 4));
-        }
+        mine |= (hit ? 1u : 0u) << ci;
     }
+    // OR over the four ti lanes of a j-atom: the clusters that reach j-atom tj; then every j-atom
+    // drops its bits into the per-cluster hit bytes (bit tj of byte ci) and the warp ORs them together
+    mine |= __shfl_xor_sync(0xffffffffu, mine, 1);
+    mine |= __shfl_xor_sync(0xffffffffu, mine, 2);
+    uint32_t jh_lo = 0u, jh_hi = 0u;   // per cluster of the sci: which j-atoms have an i-atom within rlist
+#pragma unroll
+    for (int ci = 0; ci < 4; ci++) {
+        jh_lo |= ((mine >> ci) & 1u) << (8 * ci + tj);
+        jh_hi |= ((mine >> (ci + 4)) & 1u) << (8 * ci + tj);
+    }
+    jh_lo = __reduce_or_sync(0xffffffffu, jh_lo);
+    jh_hi = __reduce_or_sync(0xffffffffu, jh_hi);
+    const uint32_t out = __reduce_or_sync(0xffffffffu, mine);
     if (lane == 0) {
         jhit[e] = make_uint2(jh_lo, jh_hi);
         raw[e].y = out;
         keep[e] = out != 0u;
-        // the diagonal flag needs the self tile, which always survives while the cluster has atoms
-        if (raw_flag[e] && !((out >> (B - c0)) & 1u)) raw_flag[e] = 0;
     }
 }
 
-__global__ void compact_kernel(int nraw, const uint2* __restrict__ raw, const int* __restrict__ raw_flag,
-                               const int* __restrict__ raw_sci, const int* __restrict__ keep,
-                               const int* __restrict__ pos, uint2* entries, int* entry_flag,
+__global__ void compact_kernel(int nraw, const uint2* __restrict__ raw, const int* __restrict__ raw_sci,
+                               const int* __restrict__ keep, const int* __restrict__ pos, uint2* entries,
                                int* entry_sci, int cap, const uint2* __restrict__ raw_jhit, uint2* entry_jhit) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nraw || !keep[e]) return;
@@ -372,7 +367,6 @@ __global__ void compact_kernel(int nraw, const uint2* __restrict__ raw, const in
     if (k >= cap) return;
     entries[k] = raw[e];
     entry_jhit[k] = raw_jhit[e];
-    entry_flag[k] = raw_flag[e];
     entry_sci[k] = raw_sci[e];
 }
 
@@ -384,178 +378,159 @@ __global__ void sci_off_kernel(int nsci, int noff, int nraw, const int* __restri
     sci_off[s] = pos[first];   // pos has nraw+1 elements (exclusive scan incl. the total)
 }
 
-// Exclusions.  pass 0 flags the entries that need a mask set, pass 1 clears the pair's bit.
-// (One thread per excluded pair; a warp-per-pair scan of the entries was measured slower.)
-__global__ void exclusion_kernel(Grid G, int n_excl, const int* __restrict__ excl_pairs,
-                                 const int* __restrict__ slot_of, const int* __restrict__ cl_sci,
-                                 const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
-                                 const uint2* __restrict__ entries, int* entry_flag,
-                                 uint32_t* masks, int pass) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G.R * n_excl) return;
-    const int r = t / n_excl, k = t - r * n_excl;
-    const int sa = slot_of[r * G.n + excl_pairs[2 * k]], sb = slot_of[r * G.n + excl_pairs[2 * k + 1]];
-    int si, sj;
-    nbl::exclusion_roles(sa, sb, &si, &sj);
-    const int isci = cl_sci[si / nbl::kClusterSize];
-    const int ci = si / nbl::kClusterSize - sci[isci].c0;
-    const uint32_t cj = (uint32_t)(sj / nbl::kJGroup);
-    const uint32_t bit = nbl::mask_bit(si, sj);
-    const int e0 = sci_off[isci], e1 = sci_off[isci + 1];
-    for (int e = e0; e < e1; e++) {
-        const uint2 ent = entries[e];
-        if ((ent.x & 0x3ffffffu) != cj) continue;
-        if (pass == 0) {
-            entry_flag[e] = 1;
-        } else {
-            const uint32_t midx = ent.y >> 8;
-            atomicAnd(masks + (size_t)midx * nbl::kMaskWords + nbl::mask_word(ci, si), ~bit);
-        }
-    }
-}
-
-// Assign mask-set indices (1-based; 0 = all ones) and initialise the sets.
-__global__ void mask_init_kernel(int nentries, const int* __restrict__ entry_flag,
-                                 const int* __restrict__ entry_midx, uint2* entries, uint32_t* masks,
-                                 const SciDesc* __restrict__ sci, const int* __restrict__ entry_sci) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nentries || !entry_flag[e]) return;
-    const uint32_t midx = (uint32_t)entry_midx[e] + 1u;
-    uint2 ent = entries[e];
-    ent.y = (ent.y & 0xffu) | (midx << 8);
-    entries[e] = ent;
-    const int cj = (int)(ent.x & 0x3ffffffu);
-    const uint32_t code = ent.x >> 26;
-    const SciDesc sd = sci[entry_sci[e]];
-    for (int w = 0; w < nbl::kMaskWords; w++) {
-        uint32_t m = 0xffffffffu;
-        if (code == nbl::kShiftZero && cj == sd.c0 + (w >> 1)) m = nbl::triangle_mask(w & 1);
-        masks[(size_t)midx * nbl::kMaskWords + w] = m;
-    }
-}
-
 // ---- per-atom j rows (nblist_core.h stage 5) -----------------------------------------------------
-// The counts of all (entry, i-group) cells of a supercluster are laid out [group][masked | unmasked]
-// [entry of the sci], so ONE exclusive scan over the whole array yields, in order, every row's
-// masked entries followed by its unmasked ones, rows in cluster order.
-struct RowCell {
-    size_t base;       // index of (group 0, masked, entry 0 of the sci) in the count array
-    int len, k;        // entries of the sci, this entry's rank among them
-    uint32_t imask;
-    const uint32_t* maskset;
-    bool same_sci;
-    uint2 jh;
+// One thread per (entry, i-group) cell counts / writes the cell's row entries of the three classes
+// 0 = carries an allow word, 1 = plain, 2 = plain and the j-atom has no Lennard-Jones term
+// (epsilon == 0).  A row (supercluster s, group g) is laid out [class 0 | class 1 | class 2], each
+// class in entry order, rows in cluster order: the cell counts (entry-major, coalesced) are turned
+// into within-row-segment offsets by a scan along the entries of each supercluster
+// (rows_scan_kernel, one block per supercluster), and one small global scan over the segment totals
+// (nsci * groups * 3 values) places the segments.
+struct RowsIn {
+    int nentries, G, n;
+    const uint2* entries;
+    const uint2* jhit;
+    const int* entry_sci;
+    const SciDesc* sci;
+    const int* sci_off;
+    const nbl::ClusterInfo* cl_info;
+    const int *excl_start, *excl_idx, *slot_of, *atom;
 };
 
-__device__ __forceinline__ RowCell row_cell(int e, int ng, const uint2* __restrict__ entries,
-                                            const uint2* __restrict__ jhit, const int* __restrict__ entry_sci,
-                                            const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
-                                            const uint32_t* __restrict__ masks, uint2* ent_out) {
-    RowCell c;
-    const int s = entry_sci[e];
-    const int e0 = sci_off[s];
-    const uint2 ent = entries[e];
-    const SciDesc sd = sci[s];
+__global__ void cluster_info_kernel(int ncl, int n, const int* __restrict__ atom, const float2* __restrict__ par,
+                                    const int* __restrict__ excl_start, const int* __restrict__ excl_idx,
+                                    const int* __restrict__ slot_of, nbl::ClusterInfo* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncl) return;
+    out[c] = nbl::cluster_info(c, atom, reinterpret_cast<const float*>(par), excl_start, excl_idx, slot_of, n);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+rows_kernel(RowsIn in, int* __restrict__ cnt, const int* __restrict__ seg_off, uint32_t* __restrict__ jent,
+            uint16_t* __restrict__ jallow, int cap) {
+    const int ng = nbl::kMaxCi / in.G;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)in.nentries * ng) return;
+    const int e = (int)(t / ng), g = (int)(t - (long long)e * ng);
+    const uint32_t full = in.G == 2 ? 0xffffu : 0xffu;
+    const int s = in.entry_sci[e];
+    const uint2 ent = in.entries[e];
+    const uint2 jh = in.jhit[e];
+    const SciDesc sd = in.sci[s];
+    const uint32_t imask = ent.y & 0xffu, code = ent.x >> 26;
     const int B = (int)(ent.x & 0x3ffffffu);
-    c.base = (size_t)e0 * 2 * ng;
-    c.len = sci_off[s + 1] - e0;
-    c.k = e - e0;
-    c.imask = ent.y & 0xffu;
-    c.maskset = (ent.y >> 8) ? masks + (size_t)(ent.y >> 8) * nbl::kMaskWords : nullptr;
-    c.same_sci = B >= sd.c0 && B < sd.c0 + sd.nci;
-    c.jh = jhit[e];
-    *ent_out = ent;
-    return c;
-}
-
-__global__ void rows_count_kernel(int nentries, int G, const uint2* __restrict__ entries,
-                                  const uint2* __restrict__ jhit, const int* __restrict__ entry_sci,
-                                  const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
-                                  const uint32_t* __restrict__ masks, int* __restrict__ cnt) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nentries) return;
-    const int ng = nbl::kMaxCi / G;
-    const uint32_t full = G == 2 ? 0xffffu : 0xffu;
-    uint2 ent;
-    const RowCell c = row_cell(e, ng, entries, jhit, entry_sci, sci, sci_off, masks, &ent);
-    for (int g = 0; g < ng; g++) {
-        int cm = 0, cu = 0;
-        uint32_t hits = nbl::row_hits(c.jh.x, c.jh.y, c.imask, g, G);
-        while (hits) {
-            const int tj = __ffs(hits) - 1;
-            hits &= hits - 1u;
-            const uint32_t allow = nbl::row_allow(c.maskset, c.imask, c.same_sci, g, G, tj);
-            if (allow == 0u) continue;
-            if (allow == full) cu++; else cm++;
-        }
-        cnt[c.base + (size_t)g * 2 * c.len + c.k] = cm;
-        cnt[c.base + (size_t)g * 2 * c.len + c.len + c.k] = cu;
+    const size_t cell = 3 * (size_t)t;   // (e * ng + g) * 3
+    const nbl::ClusterInfo info = in.cl_info[B];
+    const int first = (sd.c0 + g * in.G) * nbl::kClusterSize;
+    const bool walk = info.excl_hi >= first && info.excl_lo < first + in.G * nbl::kClusterSize;
+    int p0 = 0, p1 = 0, p2 = 0;   // scalars, not an array: a dynamically indexed array would live in local memory
+    if (FILL) {   // offset of the row segment + offset of this cell inside it
+        const int* so = seg_off + 3 * ((size_t)s * ng + g);
+        p0 = so[0] + cnt[cell]; p1 = so[1] + cnt[cell + 1]; p2 = so[2] + cnt[cell + 2];
     }
-}
-
-__global__ void rows_fill_kernel(int nentries, int G, const uint2* __restrict__ entries,
-                                 const uint2* __restrict__ jhit, const int* __restrict__ entry_sci,
-                                 const SciDesc* __restrict__ sci, const int* __restrict__ sci_off,
-                                 const uint32_t* __restrict__ masks, const int* __restrict__ scan,
-                                 uint32_t* __restrict__ jent, uint16_t* __restrict__ jallow, int cap) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nentries) return;
-    const int ng = nbl::kMaxCi / G;
-    const uint32_t full = G == 2 ? 0xffffu : 0xffu;
-    uint2 ent;
-    const RowCell c = row_cell(e, ng, entries, jhit, entry_sci, sci, sci_off, masks, &ent);
-    const uint32_t jbase = (ent.x & 0x3ffffffu) * nbl::kJGroup;
-    const uint32_t code = ent.x & ~0x3ffffffu;
-    for (int g = 0; g < ng; g++) {
-        int pm = scan[c.base + (size_t)g * 2 * c.len + c.k];
-        int pu = scan[c.base + (size_t)g * 2 * c.len + c.len + c.k];
-        uint32_t hits = nbl::row_hits(c.jh.x, c.jh.y, c.imask, g, G);
+    uint32_t hits = nbl::row_hits(jh.x, jh.y, imask, g, in.G);
+    // Nearly every cell is plain: no excluded partner of the j-cluster sits in the i-group and the
+    // j-cluster is not one of the supercluster's own (no triangle, no ownership split) -- all its
+    // hits carry the all-ones allow word and the counts are two popcounts.
+    const bool special = walk || (B >= sd.c0 && B < sd.c0 + sd.nci);
+    if (!special) {
+        if (!FILL) {
+            p1 = __popc(hits & ~info.nolj);
+            p2 = __popc(hits & info.nolj);
+        } else {
+            while (hits) {
+                const int tj = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                const int p = ((info.nolj >> tj) & 1u) ? p2++ : p1++;
+                if (p < cap) jent[p] = (uint32_t)(B * nbl::kJGroup + tj) | (code << 26);   // plain: no allow word is read
+            }
+        }
+    } else {
         while (hits) {
             const int tj = __ffs(hits) - 1;
             hits &= hits - 1u;
-            const uint32_t allow = nbl::row_allow(c.maskset, c.imask, c.same_sci, g, G, tj);
+            const uint32_t allow = nbl::row_allow(sd, imask, B, code, g, in.G, tj, in.excl_start, in.excl_idx, in.slot_of,
+                                                  in.atom, in.n, walk);
             if (allow == 0u) continue;
-            const int pos = allow == full ? pu++ : pm++;
-            if (pos < cap) {
-                jent[pos] = (jbase + (uint32_t)tj) | code;
-                jallow[pos] = (uint16_t)allow;
+            const bool masked = allow != full, nolj = ((info.nolj >> tj) & 1u) != 0u;
+            const int p = masked ? p0 : nolj ? p2 : p1;
+            p0 += masked ? 1 : 0;
+            p2 += (!masked && nolj) ? 1 : 0;
+            p1 += (!masked && !nolj) ? 1 : 0;
+            if (FILL && p < cap) {
+                jent[p] = (uint32_t)(B * nbl::kJGroup + tj) | (code << 26);
+                jallow[p] = (uint16_t)allow;
             }
         }
     }
+    if (!FILL) { cnt[cell] = p0; cnt[cell + 1] = p1; cnt[cell + 2] = p2; }
 }
 
-// row (s, g): [begin, mend) masked, [mend, end) unmasked entries; units of <= chunk steps
-__device__ __forceinline__ void row_bounds(int s, int g, int ng, const int* __restrict__ sci_off,
-                                           const int* __restrict__ scan, int* begin, int* mend, int* end) {
+// Exclusive scan of the cell counts along the entries of one supercluster, separately for each of its
+// 3 * groups row segments (columns of the entry-major count array), in place; the column totals go to
+// seg_total.  One block per supercluster, one warp per column at a time, 32 entries per shuffle scan.
+__global__ void __launch_bounds__(256)
+rows_scan_kernel(int ng, const int* __restrict__ sci_off, int* __restrict__ cnt, int* __restrict__ seg_total) {
+    const int s = blockIdx.x;
     const int e0 = sci_off[s], len = sci_off[s + 1] - e0;
-    const size_t b = (size_t)e0 * 2 * ng + (size_t)g * 2 * len;
-    *begin = scan[b];
-    *mend = scan[b + len];
-    *end = scan[b + 2 * (size_t)len];
+    const int ncol = 3 * ng, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int col = warp; col < ncol; col += 8) {
+        const int g = col / 3, cls = col - 3 * g;
+        int carry = 0;
+        for (int k0 = 0; k0 < len; k0 += 32) {
+            const int k = k0 + lane;
+            int* p = cnt + ((size_t)(e0 + k) * ng + g) * 3 + cls;
+            const int v = k < len ? *p : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (k < len) *p = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) seg_total[(size_t)s * ncol + col] = carry;
+    }
 }
 
-__global__ void rows_units_count_kernel(int nsci, int ng, int chunk, const int* __restrict__ sci_off,
-                                        const int* __restrict__ scan, int* __restrict__ row_nunits) {
+// row (s, g): [begin, mend) masked, [mend, lend) plain, [lend, end) plain without LJ (seg_off: the
+// exclusive scan of the segment totals, one more element than segments); units of <= chunk steps
+__device__ __forceinline__ void row_bounds(int s, int g, int ng, const int* __restrict__ seg_off, int* begin,
+                                           int* mend, int* lend, int* end) {
+    const int* so = seg_off + 3 * ((size_t)s * ng + g);
+    *begin = so[0];
+    *mend = so[1];
+    *lend = so[2];
+    *end = so[3];
+}
+
+__global__ void rows_units_count_kernel(int nsci, int ng, int chunk, const int* __restrict__ seg_off,
+                                        int* __restrict__ row_nunits) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsci * ng) return;
-    int b, m, e;
-    row_bounds(t / ng, t % ng, ng, sci_off, scan, &b, &m, &e);
+    int b, m, l, e;
+    row_bounds(t / ng, t % ng, ng, seg_off, &b, &m, &l, &e);
     row_nunits[t] = (e - b + 32 * chunk - 1) / (32 * chunk);
 }
 
 __global__ void rows_units_fill_kernel(int nsci, int ng, int G, int chunk, const SciDesc* __restrict__ sci,
-                                       const int* __restrict__ sci_off, const int* __restrict__ scan,
-                                       const int* __restrict__ row_unit_off, RowUnit* __restrict__ units, int cap) {
+                                       const int* __restrict__ seg_off, const int* __restrict__ row_unit_off,
+                                       RowUnit* __restrict__ units, int cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsci * ng) return;
     const int s = t / ng, g = t % ng;
-    int b, m, e;
-    row_bounds(s, g, ng, sci_off, scan, &b, &m, &e);
+    int b, m, l, e;
+    row_bounds(s, g, ng, seg_off, &b, &m, &l, &e);
     const SciDesc sd = sci[s];
     const int ncl = min(G, sd.nci - g * G);
     int u = row_unit_off[t];
-    for (int x = b; x < e; x += 32 * chunk, u++)
-        if (u < cap) units[u] = RowUnit{(sd.c0 + g * G) | (ncl << 28), x, min(x + 32 * chunk, e), max(x, min(m, x + 32 * chunk))};
+    for (int x = b; x < e; x += 32 * chunk, u++) {
+        const int xe = min(x + 32 * chunk, e);
+        const int mlen = max(x, min(m, xe)) - x, llen = max(x, min(l, xe)) - x;   // <= 1024 each
+        if (u < cap) units[u] = RowUnit{(sd.c0 + g * G) | (ncl << 28), x, xe, mlen | (llen << 16)};
+    }
 }
 
 // sort key of a unit: longer units first; the radix sort is stable, so units of equal length keep
@@ -580,31 +555,6 @@ __global__ void dummy_slot_kernel(int slot, float4* posq, float4* posq_build, fl
     par[slot] = make_float2(0.f, 0.f);
     atom[slot] = -1;
     img[slot] = 512 | (512 << 10) | (512 << 20);
-}
-
-__global__ void sci_units_count_kernel(int nsci, const int* __restrict__ sci_off, int chunk, int* sci_nunits) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nsci) return;
-    const int len = sci_off[s + 1] - sci_off[s];
-    sci_nunits[s] = (len + chunk - 1) / chunk;
-}
-
-__global__ void units_fill_kernel(int nsci, const int* __restrict__ sci_off, int chunk,
-                                  const int* __restrict__ sci_unit_off, Unit* units) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nsci) return;
-    const int e0 = sci_off[s], e1 = sci_off[s + 1];
-    int u = sci_unit_off[s];
-    for (int e = e0; e < e1; e += chunk, u++) units[u] = Unit{s, e, min(e + chunk, e1), 0};
-}
-
-__global__ void part_off_kernel(Grid G, const int* __restrict__ cell_sci,
-                                const int* __restrict__ sci_unit_off, int nsci, int nunits, int* part_off) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > G.R) return;
-    if (r == G.R) { part_off[r] = nunits; return; }
-    const int s = cell_sci[r * G.ncell];
-    part_off[r] = s < nsci ? sci_unit_off[s] : nunits;
 }
 
 __global__ void minmax_kernel(int total, const double* __restrict__ pos, double* out) {
@@ -646,39 +596,32 @@ int setup_grid(sdm_ctx* c, PairList* pl, const double lo[3], const double ext[3]
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// per-atom j rows from the final entries + exclusion masks (nblist_core.h stage 5)
+// per-atom j rows from the pruned entries and the System's exclusions (nblist_core.h stage 5)
 // ---------------------------------------------------------------------------------------------
 static int build_rows(sdm_ctx* c) {
     PairList* pl = c->pl;
     cudaStream_t s = c->stream;
     const int G = pl->row_group, ng = nbl::kMaxCi / G;
-    const size_t ncnt = (size_t)pl->nentries * 2 * ng;
-    const int nrows = pl->nsci * ng;
-    if (ncnt + 1 > (size_t)0x7fffffff) return sdm_fail(SDM_ERR_CAPACITY, "pair list too large for the row scan");
+    const size_t ncnt = (size_t)pl->nentries * 3 * ng;
+    const int nrows = pl->nsci * ng, nseg = 3 * nrows;
     if (ncnt + 1 > pl->row_cnt_cap) {
         pl->row_cnt_cap = (size_t)(ncnt * 1.25) + 1024;
         if (int rc = pl_realloc(pl, &pl->row_cnt, pl->row_cnt_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->row_scan, pl->row_cnt_cap)) return rc;
     }
-    {
-        size_t need = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, need, pl->row_cnt, pl->row_scan, (int)(ncnt + 1), s);
-        if (need > pl->cub_tmp_bytes) {
-            if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
-            pl->cub_tmp_bytes = need;
-        }
-    }
+    cluster_info_kernel<<<blocks(pl->ncl), 256, 0, s>>>(pl->ncl, c->n, pl->atom, pl->par, c->T.excl_start, c->T.excl_idx,
+                                                       pl->slot_of, pl->cl_info);
+    const RowsIn in{pl->nentries, G, c->n, pl->entries, pl->entry_jhit, pl->entry_sci, pl->sci, pl->sci_off, pl->cl_info,
+                    c->T.excl_start, c->T.excl_idx, pl->slot_of, pl->atom};
     if (pl->nentries > 0)
-        rows_count_kernel<<<blocks(pl->nentries, 128), 128, 0, s>>>(pl->nentries, G, pl->entries, pl->entry_jhit,
-                                                                   pl->entry_sci, pl->sci, pl->sci_off, pl->masks,
-                                                                   pl->row_cnt);
-    PL_CUDA(cudaMemsetAsync(pl->row_cnt + ncnt, 0, sizeof(int), s));
-    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->row_cnt, pl->row_scan, (int)(ncnt + 1), s));
-    rows_units_count_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, pl->row_chunk, pl->sci_off, pl->row_scan,
-                                                         pl->row_nunits);
+        rows_kernel<false><<<blocks((long long)pl->nentries * ng, 128), 128, 0, s>>>(in, pl->row_cnt, nullptr, nullptr,
+                                                                                    nullptr, 0);
+    if (pl->nsci > 0) rows_scan_kernel<<<pl->nsci, 256, 0, s>>>(ng, pl->sci_off, pl->row_cnt, pl->seg_total);
+    PL_CUDA(cudaMemsetAsync(pl->seg_total + nseg, 0, sizeof(int), s));
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->seg_total, pl->seg_off, nseg + 1, s));
+    rows_units_count_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, pl->row_chunk, pl->seg_off, pl->row_nunits);
     PL_CUDA(cudaMemsetAsync(pl->row_nunits + nrows, 0, sizeof(int), s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->row_nunits, pl->row_unit_off, nrows + 1, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[6], pl->row_scan + ncnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[6], pl->seg_off + nseg, sizeof(int), cudaMemcpyDeviceToHost, s));
     PL_CUDA(cudaMemcpyAsync(&pl->h_counts[7], pl->row_unit_off + nrows, sizeof(int), cudaMemcpyDeviceToHost, s));
     PL_CUDA(cudaStreamSynchronize(s));
     pl->njent = pl->h_counts[6];
@@ -699,11 +642,10 @@ static int build_rows(sdm_ctx* c) {
         if (int rc = pl_realloc(pl, &pl->ru_order, pl->runits_cap)) return rc;
     }
     if (pl->nentries > 0)
-        rows_fill_kernel<<<blocks(pl->nentries, 128), 128, 0, s>>>(pl->nentries, G, pl->entries, pl->entry_jhit,
-                                                                  pl->entry_sci, pl->sci, pl->sci_off, pl->masks,
-                                                                  pl->row_scan, pl->jent, pl->jallow, (int)pl->jent_cap);
-    rows_units_fill_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, G, pl->row_chunk, pl->sci, pl->sci_off,
-                                                        pl->row_scan, pl->row_unit_off, pl->runits, (int)pl->runits_cap);
+        rows_kernel<true><<<blocks((long long)pl->nentries * ng, 128), 128, 0, s>>>(in, pl->row_cnt, pl->seg_off, pl->jent,
+                                                                                   pl->jallow, (int)pl->jent_cap);
+    rows_units_fill_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, G, pl->row_chunk, pl->sci, pl->seg_off,
+                                                        pl->row_unit_off, pl->runits, (int)pl->runits_cap);
     rows_part_off_kernel<<<blocks(c->R + 1), 256, 0, s>>>(pl->G, ng, pl->cell_sci, pl->row_unit_off, pl->nsci, pl->part_off);
     if (pl->row_lpt && pl->nrunits > 0) {
         rows_unit_key_kernel<<<blocks(pl->nrunits), 256, 0, s>>>(pl->nrunits, pl->runits, pl->ru_key, pl->ru_val);
@@ -838,7 +780,6 @@ static int build_list(sdm_ctx* c) {
     if ((size_t)pl->nraw > pl->raw_cap) {
         pl->raw_cap = (size_t)(pl->nraw * 1.25) + 1024;
         if (int rc = pl_realloc(pl, &pl->raw_entries, pl->raw_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->raw_flag, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_sci, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_c0nci, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_jhit, pl->raw_cap)) return rc;
@@ -847,11 +788,11 @@ static int build_list(sdm_ctx* c) {
     }
     const int nraw = pl->nraw;
     search_fill_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_off, pl->raw_entries,
-                                                          pl->raw_flag, pl->raw_sci, pl->raw_c0nci, (int)pl->raw_cap);
+                                                          pl->raw_sci, pl->raw_c0nci, (int)pl->raw_cap);
     // exact prune (one warp per raw entry), then order-preserving compaction
     if (nraw > 0)
         prune_kernel<<<blocks((long long)nraw * 32, 128), 128, 0, s>>>(G, nraw, pl->raw_entries, pl->raw_c0nci,
-                                                                      pl->raw_flag, pl->posq, pl->raw_keep, pl->raw_jhit);
+                                                                      pl->posq, pl->raw_keep, pl->raw_jhit);
     PL_CUDA(cudaMemsetAsync(pl->raw_keep + nraw, 0, sizeof(int), s));
     if (int rc = ensure_cub((size_t)nraw + 1)) return rc;
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->raw_keep, pl->raw_pos, nraw + 1, s));
@@ -861,64 +802,19 @@ static int build_list(sdm_ctx* c) {
     if ((size_t)pl->nentries > pl->entries_cap) {
         pl->entries_cap = (size_t)(pl->nentries * 1.25) + 1024;
         if (int rc = pl_realloc(pl, &pl->entries, pl->entries_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->entry_flag, pl->entries_cap + 1)) return rc;
-        if (int rc = pl_realloc(pl, &pl->entry_midx, pl->entries_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_sci, pl->entries_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_jhit, pl->entries_cap + 1)) return rc;
     }
     if (nraw > 0)
-        compact_kernel<<<blocks(nraw), 256, 0, s>>>(nraw, pl->raw_entries, pl->raw_flag, pl->raw_sci, pl->raw_keep,
-                                                   pl->raw_pos, pl->entries, pl->entry_flag, pl->entry_sci,
+        compact_kernel<<<blocks(nraw), 256, 0, s>>>(nraw, pl->raw_entries, pl->raw_sci, pl->raw_keep,
+                                                   pl->raw_pos, pl->entries, pl->entry_sci,
                                                    (int)pl->entries_cap, pl->raw_jhit, pl->entry_jhit);
     sci_off_kernel<<<blocks(pl->nsci + 1), 256, 0, s>>>(pl->nsci, noff, nraw, pl->item_off, pl->raw_pos, pl->sci_off);
     c->launches += 7;
 
-    // exclusion masks
-    if (pl->n_excl > 0)
-        exclusion_kernel<<<blocks((long long)R * pl->n_excl), 256, 0, s>>>(
-            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->sci_off, pl->entries,
-            pl->entry_flag, pl->masks, 0);
-    PL_CUDA(cudaMemsetAsync(pl->entry_flag + pl->nentries, 0, sizeof(int), s));
-    if (int rc = ensure_cub((size_t)pl->nentries + 1)) return rc;
-    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->entry_flag, pl->entry_midx, pl->nentries + 1, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[3], pl->entry_midx + pl->nentries, sizeof(int), cudaMemcpyDeviceToHost, s));
-    // units of the cluster kernel (only when it is selected; the row kernel has its own below)
-    pl->h_counts[4] = 0;
-    if (!pl->use_rows) {
-        if (const char* e = getenv("SDMB200_CHUNK")) pl->chunk = std::min(kChunk, std::max(1, atoi(e)));   // development knob
-        sci_units_count_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_nunits);
-        PL_CUDA(cudaMemsetAsync(pl->sci_nunits + pl->nsci, 0, sizeof(int), s));
-        PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->sci_nunits, pl->sci_unit_off, pl->nsci + 1, s));
-        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[4], pl->sci_unit_off + pl->nsci, sizeof(int), cudaMemcpyDeviceToHost, s));
-    }
-    PL_CUDA(cudaStreamSynchronize(s));
-    pl->nmasks = pl->h_counts[3];
-    pl->nunits = pl->h_counts[4];
-    if ((size_t)pl->nmasks + 1 > pl->masks_cap) {
-        pl->masks_cap = (size_t)(pl->nmasks * 1.25) + 256;
-        if (int rc = pl_realloc(pl, &pl->masks, pl->masks_cap * nbl::kMaskWords)) return rc;
-    }
-    if (!pl->use_rows && (size_t)pl->nunits > pl->units_cap) {
-        pl->units_cap = (size_t)(pl->nunits * 1.25) + 256;
-        if (int rc = pl_realloc(pl, &pl->units, pl->units_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->epart, pl->units_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->cpart, pl->units_cap)) return rc;
-    }
-    // mask set 0 = all ones
-    PL_CUDA(cudaMemsetAsync(pl->masks, 0xff, sizeof(uint32_t) * nbl::kMaskWords, s));
-    if (pl->nentries > 0)
-        mask_init_kernel<<<blocks(pl->nentries), 256, 0, s>>>(pl->nentries, pl->entry_flag, pl->entry_midx,
-                                                             pl->entries, pl->masks, pl->sci, pl->entry_sci);
-    if (pl->n_excl > 0)
-        exclusion_kernel<<<blocks((long long)R * pl->n_excl), 256, 0, s>>>(
-            G, pl->n_excl, pl->excl_pairs, pl->slot_of, pl->cl_sci, pl->sci, pl->sci_off, pl->entries,
-            pl->entry_flag, pl->masks, 1);
-    if (pl->use_rows) {
-        if (int rc = build_rows(c)) return rc;
-    } else {
-        units_fill_kernel<<<blocks(pl->nsci), 256, 0, s>>>(pl->nsci, pl->sci_off, pl->chunk, pl->sci_unit_off, pl->units);
-        part_off_kernel<<<blocks(R + 1), 256, 0, s>>>(G, pl->cell_sci, pl->sci_unit_off, pl->nsci, pl->nunits, pl->part_off);
-    }
+    // the rows the pair kernel walks: individual j-atoms per i-group, exclusions and triangle as
+    // allow words, Lennard-Jones-free j-atoms last
+    if (int rc = build_rows(c)) return rc;
     PL_CUDA(cudaMemcpyAsync(pl->posq_build, pl->posq, sizeof(float4) * (size_t)pl->nslot, cudaMemcpyDeviceToDevice, s));
     c->launches += 7;
     PL_CUDA(cudaGetLastError());
@@ -972,7 +868,6 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     pl->nslot_cap = (pl->nslot_cap + 7) / 8 * 8;
     pl->ncl_cap = pl->nslot_cap / 8;
     pl->nsci_cap = pl->ncl_cap / 8 + ncells_cap + 1;
-    pl->chunk = kChunk;
 
 #define A(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
     A(pl_alloc(pl, &pl->keys, total));
@@ -992,12 +887,11 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->img, pl->nslot_cap));
     A(pl_alloc(pl, &pl->slot_of, total));
     A(pl_alloc(pl, &pl->cl_box, pl->ncl_cap));
+    A(pl_alloc(pl, &pl->cl_info, pl->ncl_cap));
     A(pl_alloc(pl, &pl->cell_box, ncells_cap + 1));
     A(pl_alloc(pl, &pl->sci_box, pl->nsci_cap));
     A(pl_alloc(pl, &pl->sci, pl->nsci_cap));
     A(pl_alloc(pl, &pl->cl_sci, pl->ncl_cap));
-    A(pl_alloc(pl, &pl->sci_nunits, pl->nsci_cap + 1));
-    A(pl_alloc(pl, &pl->sci_unit_off, pl->nsci_cap + 1));
     A(pl_alloc(pl, &pl->part_off, R + 1));
     A(pl_alloc(pl, &pl->unit_counter, 1));
     A(pl_alloc(pl, &pl->max_disp2, 1));
@@ -1008,12 +902,9 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     // initial guesses; grown on demand at build time
     pl->entries_cap = (size_t)total * 8 + 1024;
     A(pl_alloc(pl, &pl->entries, pl->entries_cap));
-    A(pl_alloc(pl, &pl->entry_flag, pl->entries_cap + 1));
-    A(pl_alloc(pl, &pl->entry_midx, pl->entries_cap + 1));
     A(pl_alloc(pl, &pl->entry_sci, pl->entries_cap + 1));
     pl->raw_cap = pl->entries_cap * 2;
     A(pl_alloc(pl, &pl->raw_entries, pl->raw_cap));
-    A(pl_alloc(pl, &pl->raw_flag, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_sci, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_c0nci, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_jhit, pl->raw_cap));
@@ -1021,18 +912,14 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->raw_keep, pl->raw_cap + 1));
     A(pl_alloc(pl, &pl->raw_pos, pl->raw_cap + 1));
     A(pl_alloc(pl, &pl->sci_off, pl->nsci_cap + 2));
-    pl->masks_cap = (size_t)total / 2 + 256;
-    A(pl_alloc(pl, &pl->masks, pl->masks_cap * nbl::kMaskWords));
-    if (const char* e = getenv("SDMB200_PAIR_KERNEL")) pl->use_rows = std::string(e) != "cluster";   // development knob
     if (const char* e = getenv("SDMB200_ROW_GROUP")) pl->row_group = atoi(e) == 2 ? 2 : 1;            // development knob
     if (const char* e = getenv("SDMB200_ROW_CHUNK")) pl->row_chunk = std::min(nbl::kRowChunkSteps, std::max(1, atoi(e)));
-    pl->units_cap = pl->entries_cap / 8 + 256;
-    A(pl_alloc(pl, &pl->units, pl->units_cap));
-    if (pl->use_rows) {
+    {
         const int ng = nbl::kMaxCi / pl->row_group;
-        pl->row_cnt_cap = pl->entries_cap * 2 * ng + 1;
+        pl->row_cnt_cap = pl->entries_cap * 3 * ng + 1;
         A(pl_alloc(pl, &pl->row_cnt, pl->row_cnt_cap));
-        A(pl_alloc(pl, &pl->row_scan, pl->row_cnt_cap));
+        A(pl_alloc(pl, &pl->seg_total, (size_t)pl->nsci_cap * ng * 3 + 1));
+        A(pl_alloc(pl, &pl->seg_off, (size_t)pl->nsci_cap * ng * 3 + 1));
         A(pl_alloc(pl, &pl->row_nunits, (size_t)pl->nsci_cap * ng + 1));
         A(pl_alloc(pl, &pl->row_unit_off, (size_t)pl->nsci_cap * ng + 1));
         // ~50 row entries per atom at 100 atoms/nm^3 and rlist 1.06 nm; grown on demand
@@ -1050,21 +937,6 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
         if (const char* e = getenv("SDMB200_ROW_LPT")) pl->row_lpt = atoi(e) != 0;   // development knob
         pl->dummy_slot = pl->nslot_cap - 1;   // never a real slot: nslot <= nslot_cap - 8
         dummy_slot_kernel<<<1, 1, 0, c->stream>>>(pl->dummy_slot, pl->posq, pl->posq_build, pl->par, pl->atom, pl->img);
-    } else {
-        A(pl_alloc(pl, &pl->epart, pl->units_cap));
-        A(pl_alloc(pl, &pl->cpart, pl->units_cap));
-    }
-    {
-        // unique exclusion pairs a<b from the CSR the ctx already holds
-        std::vector<int> ex;
-        for (int i = 0; i < n; i++)
-            for (int k = c->h_excl_start[i]; k < c->h_excl_start[i + 1]; k++)
-                if (c->h_excl_idx[k] > i) { ex.push_back(i); ex.push_back(c->h_excl_idx[k]); }
-        pl->n_excl = (int)ex.size() / 2;
-        int* d = nullptr;
-        A(pl_alloc(pl, &d, ex.size()));
-        if (!ex.empty()) PL_CUDA(cudaMemcpy(d, ex.data(), ex.size() * sizeof(int), cudaMemcpyHostToDevice));
-        pl->excl_pairs = d;
     }
     {
         size_t a = 0, b = 0;
@@ -1105,11 +977,6 @@ static PairListView make_view(const sdm_ctx* c) {
     V.posq = pl->posq;
     V.par = pl->par;
     V.atom = pl->atom;
-    V.sci = pl->sci;
-    V.entries = pl->entries;
-    V.masks = pl->masks;
-    V.units = pl->units;
-    V.nunits = pl->nunits;
     V.nslot_cap = pl->nslot_cap;
     V.jent = pl->jent;
     V.jallow = pl->jallow;
@@ -1160,9 +1027,8 @@ int sdm_ctx_pairlist_launch(sdm_ctx* c) {
     cudaStream_t s = c->stream;
     // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
-    (pl->use_rows ? launch_pair_rows : launch_pair_cluster)(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart,
-                                                            pl->cpart, c->opt.exact_cutoff, pl->unit_counter,
-                                                            c->num_sms, nullptr, s);
+    launch_pair_rows(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
+                     pl->unit_counter, c->num_sms, nullptr, s);
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[2], s));
     c->launches++;
     PL_CUDA(cudaGetLastError());
@@ -1175,9 +1041,8 @@ int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs,
     // the debug build of the hot kernel itself: same list, same code, plus the pair records.  It adds
     // its forces to the accumulators a second time; they are cleared before the next evaluation.
     const PairEmit em{d_counter, d_pairs, cap, replica};
-    (pl->use_rows ? launch_pair_rows : launch_pair_cluster)(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart,
-                                                            pl->cpart, c->opt.exact_cutoff, pl->unit_counter,
-                                                            c->num_sms, &em, c->stream);
+    launch_pair_rows(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
+                     pl->unit_counter, c->num_sms, &em, c->stream);
     PL_CUDA(cudaStreamSynchronize(c->stream));
     return SDM_OK;
 }
@@ -1193,10 +1058,9 @@ int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "n_sci") *value = pl->nsci;
     else if (k == "n_entries") *value = pl->nentries;
     else if (k == "n_raw_entries") *value = pl->nraw;
-    else if (k == "n_masks") *value = pl->nmasks;
-    else if (k == "n_units") *value = pl->use_rows ? pl->nrunits : pl->nunits;
+    else if (k == "n_units") *value = pl->nrunits;
     else if (k == "n_row_entries") *value = pl->njent;
-    else if (k == "row_group") *value = pl->use_rows ? pl->row_group : 0;
+    else if (k == "row_group") *value = pl->row_group;
     else if (k == "n_cells") *value = pl->G.ncell;
     else if (k == "cell_span") *value = pl->G.span;
     else if (k == "layout_columns") *value = pl->G.columns;

@@ -1,5 +1,5 @@
-// pairlist.h -- device-resident cluster-pair list of a context and the launchers that build
-// and consume it (internal).
+// pairlist.h -- what the pair kernel reads of a context's device-resident pair list, and the
+// launchers of the kernels that consume it (internal).
 #pragma once
 
 #include "nblist_core.h"
@@ -7,19 +7,14 @@
 
 namespace sdm {
 
-struct Unit {
-    int sci;      // supercluster
-    int begin;    // first entry (global index into entries)
-    int end;      // one past the last entry
-    int pad;
-};
-
 // Work unit of the row kernel: an i-group and a chunk (<= 32 warp steps) of its row of j-atoms.
 struct RowUnit {
     int c0n;      // first cluster of the i-group | clusters in it (1..2) << 28
     int begin;    // first row entry (global index into jent)
     int end;      // one past the last
-    int mend;     // entries [begin, mend) carry an allow word (exclusions / triangle)
+    int seg;      // (mend - begin) | (lend - begin) << 16: entries [begin, mend) carry an allow word
+                  // (exclusions / triangle), entries [lend, end) are j-atoms WITHOUT a Lennard-Jones
+                  // term (epsilon == 0: water hydrogens) -- their steps skip a third of the arithmetic
 };
 
 // Everything the pair kernel reads.
@@ -28,13 +23,8 @@ struct PairListView {
     const float4* posq;          // [nslot] sorted, wrapped (+ image) positions, .w = q*sqrt(K)
     const float2* par;           // [nslot] (sigma/2, 2*sqrt(eps)); (0,0) for dummies
     const int* atom;             // [nslot] replica*n + atom, or -1 for a dummy slot
-    const nbl::SciDesc* sci;     // [nsci]
-    const uint2* entries;        // {cj | shift<<26, imask | mask_index<<8}
-    const uint32_t* masks;       // [(nmasks+1)*16]; set 0 = all ones
-    const Unit* units;           // [nunits]
-    int nunits;
     int nslot_cap;               // accumulator plane stride
-    // per-atom j rows (the product kernel)
+    // per-atom j rows (nblist_core.h stage 5)
     const uint32_t* jent;        // row entries: j slot | shift << 26
     const uint16_t* jallow;      // allow word per row entry (read for the masked prefix of a row only)
     const RowUnit* runits;       // [nrunits]
@@ -53,10 +43,6 @@ struct PairEmit {
     int cap;
     int replica;
 };
-void launch_pair_cluster(const Topology& T, const PairListView& V, const double* pos_all,
-                         long long* f1acc, double* epart, long long* cpart, int exact,
-                         int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s);
-// The row kernel: same contract, walks V.runits / V.jent.
 void launch_pair_rows(const Topology& T, const PairListView& V, const double* pos_all,
                       long long* f1acc, double* epart, long long* cpart, int exact,
                       int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s);

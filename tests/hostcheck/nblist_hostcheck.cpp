@@ -37,8 +37,8 @@ extern "C" {
 
 // pos: [R][n][3] doubles.  excl: unique pairs a<b.  Returns the number of covered pairs of
 // replica `replica` (sorted (i<j) System indices written to out_pairs up to max_pairs), or <0.
-// stats[0..7]: nslot, nsci, nentries, nmasks, nunits, evaluated lane-pairs (all replicas),
-// ncell, span.
+// stats[0..9]: nslot, nsci, nentries, -, row units, evaluated lane-pairs (all replicas), ncell, span,
+// row entries, row entries that carry an allow word.
 long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const double* box,
                           double rc, double skin, int n_excl, const int* excl, int chunk,
                           int replica, int* out_pairs, long long max_pairs, double* stats) {
@@ -193,19 +193,18 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
         item_off[t + 1] = item_off[t] + search_any(V, (int)(t / noff), (int)(t % noff), [](int, uint32_t, uint32_t, bool) {});
     const int nraw = item_off[nitems];
     std::vector<uint32_t> rx(nraw), ry(nraw);
-    std::vector<int> rflag(nraw, 0), rsci(nraw);
+    std::vector<int> rsci(nraw);
     for (long long t = 0; t < nitems; t++) {
         int base = item_off[t];
         search_any(V, (int)(t / noff), (int)(t % noff), [&](int k, uint32_t w0, uint32_t imask, bool diag) {
             rx[base + k] = w0;
             ry[base + k] = imask;
-            rflag[base + k] = diag ? 1 : 0;
             rsci[base + k] = (int)(t / noff);
         });
     }
     // exact prune + order-preserving compaction (prune_kernel / compact_kernel / sci_off_kernel)
     std::vector<uint32_t> ex, ey;
-    std::vector<int> flag, esci, sci_off(nsci + 1, 0);
+    std::vector<int> esci, sci_off(nsci + 1, 0);
     {
         int next_sci = 0;
         for (int e = 0; e < nraw; e++) {
@@ -216,106 +215,24 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
             const int B = (int)(rx[e] & 0x3ffffffu);
             ex.push_back(rx[e]);
             ey.push_back(m);
-            flag.push_back(rflag[e] && ((m >> (B - sd.c0)) & 1u) ? 1 : 0);
             esci.push_back(rsci[e]);
         }
         while (next_sci <= nsci) sci_off[next_sci++] = (int)ex.size();
     }
     const int nentries = (int)ex.size();
-    flag.push_back(0);
-    // exclusions pass 0
-    auto for_excl = [&](int pass, std::vector<uint32_t>* masks) {
-        for (int r = 0; r < R; r++)
-            for (int k = 0; k < n_excl; k++) {
-                int sa = slot_of[r * n + excl[2 * k]], sb = slot_of[r * n + excl[2 * k + 1]];
-                int si, sj;
-                exclusion_roles(sa, sb, &si, &sj);
-                int isci = cl_sci[si / kClusterSize];
-                int ci = si / kClusterSize - sci[isci].c0;
-                uint32_t cj = (uint32_t)(sj / kJGroup);
-                uint32_t bit = mask_bit(si, sj);
-                for (int e = sci_off[isci]; e < sci_off[isci + 1]; e++) {
-                    if ((ex[e] & 0x3ffffffu) != cj) continue;
-                    if (pass == 0) flag[e] = 1;
-                    else (*masks)[(size_t)(ey[e] >> 8) * kMaskWords + mask_word(ci, si)] &= ~bit;
-                }
-            }
-    };
-    for_excl(0, nullptr);
-    int nmasks = 0;
-    std::vector<int> midx(nentries, 0);
-    for (int e = 0; e < nentries; e++) if (flag[e]) midx[e] = nmasks++;
-    std::vector<uint32_t> masks((size_t)(nmasks + 1) * kMaskWords, 0xffffffffu);
-    for (int e = 0; e < nentries; e++) {
-        if (!flag[e]) continue;
-        uint32_t m = (uint32_t)midx[e] + 1u;
-        ey[e] = (ey[e] & 0xffu) | (m << 8);
-        int cj = (int)(ex[e] & 0x3ffffffu);
-        uint32_t code = ex[e] >> 26;
-        const SciDesc sd = sci[esci[e]];
-        for (int w = 0; w < kMaskWords; w++) {
-            uint32_t v = 0xffffffffu;
-            if (code == kShiftZero && cj == sd.c0 + (w >> 1)) v = triangle_mask(w & 1);
-            masks[(size_t)m * kMaskWords + w] = v;
+    // the System's exclusions as the CSR over atoms (both directions) the device path walks
+    // (Topology::excl_start / excl_idx)
+    std::vector<int> excl_start(n + 1, 0), excl_idx;
+    {
+        std::vector<std::vector<int>> nb(n);
+        for (int k = 0; k < n_excl; k++) { nb[excl[2 * k]].push_back(excl[2 * k + 1]); nb[excl[2 * k + 1]].push_back(excl[2 * k]); }
+        for (int a = 0; a < n; a++) {
+            std::sort(nb[a].begin(), nb[a].end());
+            excl_start[a + 1] = excl_start[a] + (int)nb[a].size();
+            excl_idx.insert(excl_idx.end(), nb[a].begin(), nb[a].end());
         }
     }
-    for_excl(1, &masks);
     int nunits = 0;
-    for (int s = 0; s < nsci; s++) {
-        int len = sci_off[s + 1] - sci_off[s];
-        nunits += (len + chunk - 1) / chunk;
-    }
-
-    if (getenv("SDM_HOSTCHECK_STATS")) {
-        // pairing statistics: consecutive unmasked entries of a unit taken two at a time
-        long both = 0, one = 0, single_tiles = 0, masked_tiles = 0, npairs = 0, nsingle = 0, nmasked = 0;
-        for (int s = 0; s < nsci; s++)
-            for (int b = sci_off[s]; b < sci_off[s + 1]; b += chunk) {
-                const int e1 = std::min(b + chunk, sci_off[s + 1]);
-                std::vector<uint32_t> um;
-                for (int e = b; e < e1; e++) {
-                    if (ey[e] >> 8) { nmasked++; masked_tiles += __builtin_popcount(ey[e] & 0xffu); }
-                    else um.push_back(ey[e] & 0xffu);
-                }
-                size_t k = 0;
-                for (; k + 1 < um.size(); k += 2) {
-                    npairs++;
-                    both += __builtin_popcount(um[k] & um[k + 1]);
-                    one += __builtin_popcount(um[k] ^ um[k + 1]);
-                }
-                if (k < um.size()) { nsingle++; single_tiles += __builtin_popcount(um[k]); }
-            }
-        {
-            // all entries of a unit (masked too), ordered by imask value, then paired; and a greedy
-            // minimum-Hamming-distance pairing for comparison
-            long tiles = 0, un_sorted = 0, un_plain = 0, un_greedy = 0, steps = 0;
-            for (int s = 0; s < nsci; s++)
-                for (int b = sci_off[s]; b < sci_off[s + 1]; b += chunk) {
-                    const int e1 = std::min(b + chunk, sci_off[s + 1]);
-                    std::vector<uint32_t> m;
-                    for (int e = b; e < e1; e++) { m.push_back(ey[e] & 0xffu); tiles += __builtin_popcount(ey[e] & 0xffu); }
-                    steps += ((long)m.size() + 1) / 2;
-                    for (size_t k = 0; k < m.size(); k += 2) un_plain += __builtin_popcount(m[k] | (k + 1 < m.size() ? m[k + 1] : 0u));
-                    std::vector<uint32_t> q = m;
-                    std::sort(q.begin(), q.end());
-                    for (size_t k = 0; k < q.size(); k += 2) un_sorted += __builtin_popcount(q[k] | (k + 1 < q.size() ? q[k + 1] : 0u));
-                    std::vector<char> used(m.size(), 0);
-                    for (size_t a = 0; a < m.size(); a++) {
-                        if (used[a]) continue;
-                        used[a] = 1;
-                        int best = -1, bd = 99;
-                        for (size_t c = a + 1; c < m.size(); c++)
-                            if (!used[c] && __builtin_popcount(m[a] ^ m[c]) < bd) { bd = __builtin_popcount(m[a] ^ m[c]); best = (int)c; }
-                        if (best >= 0) { used[best] = 1; un_greedy += __builtin_popcount(m[a] | m[best]); }
-                        else un_greedy += __builtin_popcount(m[a]);
-                    }
-                }
-            fprintf(stderr, "union pairing: tiles %ld steps %ld | 2*union plain %ld sorted %ld greedy %ld\n", tiles, steps,
-                    2 * un_plain, 2 * un_sorted, 2 * un_greedy);
-        }
-        fprintf(stderr, "pairing: pairs %ld both %ld one %ld | singles %ld tiles %ld | masked %ld tiles %ld | units %d\n",
-                npairs, both, one, nsingle, single_tiles, nmasked, masked_tiles, nunits);
-    }
 
     // traversal exactly like the row kernel (kernels_cluster.cu, pair_row_kernel): every i-group
     // (G consecutive clusters of a supercluster) walks its row of individual j-atoms -- the atoms
@@ -327,24 +244,25 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     std::vector<std::pair<int, int>> found;
     const double rc2 = rc * rc;
     double lane_pairs = 0, row_entries = 0, row_masked = 0;
+    std::vector<long> row_len((size_t)nsci * ng, 0);
     for (int s = 0; s < nsci; s++) {
         const SciDesc sd = sci[s];
         for (int e = sci_off[s]; e < sci_off[s + 1]; e++) {
             const int cj = (int)(ex[e] & 0x3ffffffu);
-            const uint32_t imask = ey[e] & 0xffu, m = ey[e] >> 8;
+            const uint32_t imask = ey[e] & 0xffu;
             const uint32_t code = ex[e] >> 26;
             const int sh[3] = {shift_x(code), shift_y(code), shift_z(code)};
             uint32_t jh_lo, jh_hi;
             entry_hits(V, sd, ex[e], imask, &jh_lo, &jh_hi);
-            const uint32_t* maskset = m ? &masks[(size_t)m * kMaskWords] : nullptr;
-            const bool same_sci = cj >= sd.c0 && cj < sd.c0 + sd.nci;
             for (int g = 0; g < ng; g++) {
                 const uint32_t hits = row_hits(jh_lo, jh_hi, imask, g, Grow);
                 for (int tj = 0; tj < kJGroup; tj++) {
                     if (!((hits >> tj) & 1u)) continue;
-                    const uint32_t allow = row_allow(maskset, imask, same_sci, g, Grow, tj);
+                    const uint32_t allow = row_allow(sd, imask, cj, code, g, Grow, tj, excl_start.data(), excl_idx.data(),
+                                                     slot_of.data(), atom.data(), n);
                     if (!allow) continue;
                     row_entries += 1;
+                    row_len[(size_t)s * ng + g] += 1;
                     if (allow != (Grow == 2 ? 0xffffu : 0xffu)) row_masked += 1;
                     lane_pairs += 8 * Grow;
                     if (sd.replica != replica) continue;
@@ -370,11 +288,12 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
             }
         }
     }
+    for (long len : row_len) nunits += (int)((len + 32L * chunk - 1) / (32L * chunk));   // rows_units_count_kernel
     std::sort(found.begin(), found.end());
     long long m = std::min<long long>((long long)found.size(), max_pairs);
     for (long long k = 0; k < m; k++) { out_pairs[2 * k] = found[k].first; out_pairs[2 * k + 1] = found[k].second; }
     if (stats) {
-        stats[0] = nslot; stats[1] = nsci; stats[2] = nentries; stats[3] = nmasks;
+        stats[0] = nslot; stats[1] = nsci; stats[2] = nentries; stats[3] = 0;
         stats[4] = nunits; stats[5] = lane_pairs; stats[6] = G.ncell; stats[7] = G.span;
         stats[8] = row_entries; stats[9] = row_masked;
     }
