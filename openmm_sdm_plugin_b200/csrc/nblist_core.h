@@ -496,24 +496,32 @@ SDM_HD void entry_hits(const SearchView& V, const SciDesc& sd, uint32_t w0, uint
 // and carry an allow word (bit a = i-atom a of the group may interact with this j-atom).
 constexpr int kRowChunkSteps = 32;   // warp steps (32 j-atoms each) per work unit, at most 32
 
-// What the row construction needs to know about a j-cluster, gathered once per list build: the slot
-// range its atoms' excluded partners fall into (lo > hi: none) -- an i-group outside that range has
-// no exclusion with the cluster, which is the case for all but a handful of (entry, group) cells --
-// and which of its atoms carry no Lennard-Jones term.
+// What the row construction needs to know about a j-cluster, gathered once per list build: which of
+// its atoms carry no Lennard-Jones term, and its EXCLUSION TILES -- the (few) clusters that hold an
+// excluded partner of one of its atoms, each with the 8 x 8 bit matrix of the excluded pairs.  With
+// this record in registers the allow word of a row entry needs no further memory access (walking
+// the exclusion CSR per j-atom -- four dependent loads per partner -- stalled whole warps of the row
+// kernels).  npart < 0: more partner clusters than the record holds (0.6 % of the clusters of the
+// 20 k-atom fixture: spatially sorted atoms split most molecules over clusters, the mean is five
+// partner clusters), the CSR is walked instead.  The matrices live in a separate array
+// (ClusterTiles): only the few cells that have a tile on their i-group read one.
+constexpr int kMaxPartners = 10;
 struct ClusterInfo {
-    int excl_lo, excl_hi;
-    uint32_t nolj;      // bit tj: epsilon of atom tj is zero (or the slot is a dummy)
-    uint32_t pad;
+    uint32_t nolj;                  // bit tj: epsilon of atom tj is zero (or the slot is a dummy)
+    int npart;
+    int part[kMaxPartners];         // partner clusters (global cluster index)
+};
+struct ClusterTiles {
+    uint64_t mask[kMaxPartners];    // bit (8*tj + ia): atom tj of this cluster is excluded with atom ia of part[k]
 };
 
 // par2: [nslot][2] floats (sigma/2, 2*sqrt(eps))
 SDM_HD ClusterInfo cluster_info(int c, const int* atom, const float* par2, const int* excl_start, const int* excl_idx,
-                                const int* slot_of, int n) {
+                                const int* slot_of, int n, ClusterTiles* tiles) {
     ClusterInfo ci;
-    ci.excl_lo = 0x7fffffff;
-    ci.excl_hi = -1;
     ci.nolj = 0u;
-    ci.pad = 0u;
+    ci.npart = 0;
+    for (int k = 0; k < kMaxPartners; k++) { ci.part[k] = -1; tiles->mask[k] = 0ull; }
     for (int tj = 0; tj < kJGroup; tj++) {
         const int s = c * kJGroup + tj;
         if (par2[2 * (size_t)s + 1] == 0.f) ci.nolj |= 1u << tj;
@@ -522,8 +530,14 @@ SDM_HD ClusterInfo cluster_info(int c, const int* atom, const float* par2, const
         const int r = ga / n, a = ga - r * n;
         for (int k = excl_start[a]; k < excl_start[a + 1]; k++) {
             const int sp = slot_of[r * n + excl_idx[k]];
-            if (sp < ci.excl_lo) ci.excl_lo = sp;
-            if (sp > ci.excl_hi) ci.excl_hi = sp;
+            const int A = sp / kClusterSize;
+            int w = 0;
+            while (w < ci.npart && ci.part[w] != A) w++;
+            if (w == ci.npart) {
+                if (ci.npart < 0 || ci.npart == kMaxPartners) { ci.npart = -1; continue; }
+                ci.part[ci.npart++] = A;
+            }
+            if (ci.npart >= 0) tiles->mask[w] |= 1ull << (8 * tj + sp % kClusterSize);
         }
     }
     return ci;
@@ -560,11 +574,8 @@ SDM_HD uint32_t row_hits(uint32_t jh_lo, uint32_t jh_hi, uint32_t imask, int g, 
 //   * every excluded partner of the j-atom (excl_start / excl_idx: the System's exclusions as a CSR
 //     over atoms, both directions) that sits in the group is switched off.
 // atom[slot] = replica*n + atom, slot_of = its inverse.
-// walk_excl = false skips the exclusion walk: the caller knows that no excluded partner of any atom
-// of j-cluster B has its slot inside the i-group (ClusterInfo below).
-SDM_HD uint32_t row_allow(const SciDesc& sd, uint32_t imask, int B, uint32_t code, int g, int G, int tj,
-                          const int* excl_start, const int* excl_idx, const int* slot_of, const int* atom, int n,
-                          bool walk_excl = true) {
+// The part of an allow word that does not depend on exclusions: triangle and ownership.
+SDM_HD uint32_t row_allow_base(const SciDesc& sd, uint32_t imask, int B, uint32_t code, int g, int G, int tj) {
     const bool same_sci = B >= sd.c0 && B < sd.c0 + sd.nci;
     uint32_t allow = 0;
     for (int q = 0; q < G; q++) {
@@ -577,7 +588,50 @@ SDM_HD uint32_t row_allow(const SciDesc& sd, uint32_t imask, int B, uint32_t cod
         }
         allow |= bits << (8 * q);
     }
-    if (!walk_excl) return allow;
+    return allow;
+}
+
+// Exclusions from the j-cluster's exclusion tiles (info.npart >= 0), in two steps so that the tile
+// search runs once per (entry, i-group) cell and not once per j-atom: ex[q] = the 8 x 8 exclusion
+// matrix (bit 8*tj + ia) between the j-cluster and the group's q-th cluster, zero when there is none.
+// Fixed trip counts and constant indices: the record stays in registers.
+SDM_HD bool row_excl_tiles(const SciDesc& sd, int g, int G, const ClusterInfo& info, const ClusterTiles* tiles,
+                           uint64_t ex[2]) {
+    ex[0] = ex[1] = 0ull;
+    bool any = false;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 0; k < kMaxPartners; k++) {
+        const int q = info.part[k] - (sd.c0 + g * G);
+        if (k < info.npart && q >= 0 && q < G) {
+            if (q == 0) ex[0] |= tiles->mask[k]; else ex[1] |= tiles->mask[k];
+            any = true;
+        }
+    }
+    return any;
+}
+
+SDM_HD uint32_t row_allow(const SciDesc& sd, uint32_t imask, int B, uint32_t code, int g, int G, int tj,
+                          const uint64_t ex[2]) {
+    uint32_t allow = row_allow_base(sd, imask, B, code, g, G, tj);
+    allow &= ~(uint32_t)((ex[0] >> (8 * tj)) & 0xffull);
+    if (G == 2) allow &= ~((uint32_t)((ex[1] >> (8 * tj)) & 0xffull) << 8);
+    return allow;
+}
+
+SDM_HD uint32_t row_allow(const SciDesc& sd, uint32_t imask, int B, uint32_t code, int g, int G, int tj,
+                          const ClusterInfo& info, const ClusterTiles* tiles) {
+    uint64_t ex[2];
+    row_excl_tiles(sd, g, G, info, tiles, ex);
+    return row_allow(sd, imask, B, code, g, G, tj, ex);
+}
+
+// Exclusions by walking the System's exclusion CSR for the j-atom (clusters whose partners do not
+// fit the record, and the reference the host checker can compare the tiles with).
+SDM_HD uint32_t row_allow(const SciDesc& sd, uint32_t imask, int B, uint32_t code, int g, int G, int tj,
+                          const int* excl_start, const int* excl_idx, const int* slot_of, const int* atom, int n) {
+    uint32_t allow = row_allow_base(sd, imask, B, code, g, G, tj);
     const int ga = atom[B * kJGroup + tj];
     if (ga < 0) return 0u;
     const int r = ga / n, a = ga - r * n;

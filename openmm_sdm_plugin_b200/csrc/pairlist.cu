@@ -37,7 +37,8 @@ struct PairList {
     float2* par = nullptr;
     int *atom = nullptr, *img = nullptr, *slot_of = nullptr;
     BBox *cl_box = nullptr, *sci_box = nullptr, *cell_box = nullptr;
-    nbl::ClusterInfo* cl_info = nullptr;   // [ncl] exclusion-partner slot range and LJ-free atoms of every cluster
+    nbl::ClusterInfo* cl_info = nullptr;   // [ncl] partner clusters and LJ-free atoms of every cluster
+    nbl::ClusterTiles* cl_tiles = nullptr; // [ncl] its exclusion tiles
     int use_columns = 1;        // column layout (default) or geometric 3-D cells (SDMB200_LAYOUT=cells)
     SciDesc* sci = nullptr;
     int* cl_sci = nullptr;
@@ -53,9 +54,7 @@ struct PairList {
     int row_group = 1;          // clusters per i-group (SDMB200_ROW_GROUP = 1 | 2)
     int row_chunk = nbl::kRowChunkSteps;   // warp steps per unit (SDMB200_ROW_CHUNK)
     uint2 *raw_jhit = nullptr, *entry_jhit = nullptr;   // per (cluster of the sci, j-atom) hit bits of an entry
-    int* row_cnt = nullptr;     // [nentries][8 / G][3] cell counts, then within-segment offsets (entry-major)
     int *seg_total = nullptr, *seg_off = nullptr;       // [nsci * (8 / G) * 3 + 1] row segments
-    size_t row_cnt_cap = 0;
     uint32_t* jent = nullptr;
     uint16_t* jallow = nullptr;
     size_t jent_cap = 0;
@@ -379,119 +378,195 @@ __global__ void sci_off_kernel(int nsci, int noff, int nraw, const int* __restri
 }
 
 // ---- per-atom j rows (nblist_core.h stage 5) -----------------------------------------------------
-// One thread per (entry, i-group) cell counts / writes the cell's row entries of the three classes
-// 0 = carries an allow word, 1 = plain, 2 = plain and the j-atom has no Lennard-Jones term
-// (epsilon == 0).  A row (supercluster s, group g) is laid out [class 0 | class 1 | class 2], each
-// class in entry order, rows in cluster order: the cell counts (entry-major, coalesced) are turned
-// into within-row-segment offsets by a scan along the entries of each supercluster
-// (rows_scan_kernel, one block per supercluster), and one small global scan over the segment totals
-// (nsci * groups * 3 values) places the segments.
+// A row (supercluster s, i-group g) is laid out [class 0 | class 1 | class 2] -- 0 = entries that
+// carry an allow word, 1 = plain, 2 = plain and the j-atom has no Lennard-Jones term (epsilon == 0)
+// -- each class in entry order, rows in cluster order.  One block per supercluster, one warp per
+// i-group, one lane per entry of a 32-entry chunk: the first pass (FILL = false) only sums the three
+// class counts of every row (seg_total); one small global scan over those nsci * groups * 3 totals
+// places the segments (seg_off); the second pass repeats the walk, turns the lanes' counts into
+// positions with one packed warp scan per chunk and writes the row entries -- consecutive lanes write
+// consecutive pieces of the same three segments.  Nothing per (entry, group) cell ever goes to memory.
 struct RowsIn {
-    int nentries, G, n;
+    int G, n;
     const uint2* entries;
     const uint2* jhit;
-    const int* entry_sci;
     const SciDesc* sci;
     const int* sci_off;
     const nbl::ClusterInfo* cl_info;
+    const nbl::ClusterTiles* cl_tiles;
     const int *excl_start, *excl_idx, *slot_of, *atom;
 };
 
-__global__ void cluster_info_kernel(int ncl, int n, const int* __restrict__ atom, const float2* __restrict__ par,
-                                    const int* __restrict__ excl_start, const int* __restrict__ excl_idx,
-                                    const int* __restrict__ slot_of, nbl::ClusterInfo* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncl) return;
-    out[c] = nbl::cluster_info(c, atom, reinterpret_cast<const float*>(par), excl_start, excl_idx, slot_of, n);
+// nbl::cluster_info with one lane per atom (32 clusters per block): every lane walks the exclusions of
+// its own atom -- the dependent loads of the eight atoms of a cluster overlap -- and the lanes of a
+// cluster then take turns to enter their partners into the cluster's record in shared memory, in
+// atom order, so the record is the one the scalar routine builds.
+__global__ void __launch_bounds__(256)
+cluster_info_kernel(int ncl, int n, const int* __restrict__ atom, const float2* __restrict__ par,
+                    const int* __restrict__ excl_start, const int* __restrict__ excl_idx,
+                    const int* __restrict__ slot_of, nbl::ClusterInfo* __restrict__ out,
+                    nbl::ClusterTiles* __restrict__ tiles) {
+    __shared__ nbl::ClusterInfo s_info[32];
+    __shared__ nbl::ClusterTiles s_tiles[32];
+    const int lc = threadIdx.x >> 3, tj = threadIdx.x & 7;
+    const int c = blockIdx.x * 32 + lc;
+    if (tj == 0) {
+        s_info[lc].nolj = 0u;
+        s_info[lc].npart = 0;
+        for (int k = 0; k < nbl::kMaxPartners; k++) { s_info[lc].part[k] = -1; s_tiles[lc].mask[k] = 0ull; }
+    }
+    __syncwarp();
+    const bool live = c < ncl;
+    const int slot = c * nbl::kJGroup + tj;
+    const int ga = live ? atom[slot] : -1;
+    if (live && par[slot].y == 0.f) atomicOr(&s_info[lc].nolj, 1u << tj);
+    int k0 = 0, k1 = 0, r = 0;
+    if (ga >= 0) {
+        r = ga / n;
+        const int a = ga - r * n;
+        k0 = excl_start[a];
+        k1 = excl_start[a + 1];
+    }
+    // the partner slots of this lane's atom, fetched before the turns (all lanes' loads in flight
+    // together); an atom with more than kPre exclusions fetches the rest during its turn
+    constexpr int kPre = 12;
+    int pre[kPre];
+#pragma unroll
+    for (int k = 0; k < kPre; k++) pre[k] = k0 + k < k1 ? slot_of[r * n + excl_idx[k0 + k]] : -1;
+    for (int turn = 0; turn < nbl::kJGroup; turn++) {
+        if (turn == tj) {
+            nbl::ClusterInfo& ci = s_info[lc];
+#pragma unroll
+            for (int kk = 0; kk < kPre + 1; kk++) {
+              const int kend = kk < kPre ? k0 + kk + 1 : k1;
+              for (int k = k0 + kk; k < kend && k < k1; k++) {
+                const int sp = kk < kPre ? pre[kk] : slot_of[r * n + excl_idx[k]];
+                const int A = sp / nbl::kClusterSize;
+                int w = 0;
+                while (w < ci.npart && ci.part[w] != A) w++;
+                if (w == ci.npart) {
+                    if (ci.npart < 0 || ci.npart == nbl::kMaxPartners) { ci.npart = -1; continue; }
+                    ci.part[ci.npart++] = A;
+                }
+                if (ci.npart >= 0) s_tiles[lc].mask[w] |= 1ull << (8 * tj + sp % nbl::kClusterSize);
+              }
+            }
+        }
+        __syncwarp();
+    }
+    if (live && tj == 0) {
+        out[c] = s_info[lc];
+        tiles[c] = s_tiles[lc];
+    }
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(128)
-rows_kernel(RowsIn in, int* __restrict__ cnt, const int* __restrict__ seg_off, uint32_t* __restrict__ jent,
+__global__ void __launch_bounds__(256)
+rows_kernel(RowsIn in, int* __restrict__ seg_total, const int* __restrict__ seg_off, uint32_t* __restrict__ jent,
             uint16_t* __restrict__ jallow, int cap) {
     const int ng = nbl::kMaxCi / in.G;
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= (long long)in.nentries * ng) return;
-    const int e = (int)(t / ng), g = (int)(t - (long long)e * ng);
+    const int s = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;   // blockDim.x = 32 * ng
     const uint32_t full = in.G == 2 ? 0xffffu : 0xffu;
-    const int s = in.entry_sci[e];
-    const uint2 ent = in.entries[e];
-    const uint2 jh = in.jhit[e];
     const SciDesc sd = in.sci[s];
-    const uint32_t imask = ent.y & 0xffu, code = ent.x >> 26;
-    const int B = (int)(ent.x & 0x3ffffffu);
-    const size_t cell = 3 * (size_t)t;   // (e * ng + g) * 3
-    const nbl::ClusterInfo info = in.cl_info[B];
-    const int first = (sd.c0 + g * in.G) * nbl::kClusterSize;
-    const bool walk = info.excl_hi >= first && info.excl_lo < first + in.G * nbl::kClusterSize;
-    int p0 = 0, p1 = 0, p2 = 0;   // scalars, not an array: a dynamically indexed array would live in local memory
-    if (FILL) {   // offset of the row segment + offset of this cell inside it
+    const int e0 = in.sci_off[s], e1 = in.sci_off[s + 1];
+    int base0 = 0, base1 = 0, base2 = 0;   // FILL: next free position of the row's three segments
+    if (FILL) {
         const int* so = seg_off + 3 * ((size_t)s * ng + g);
-        p0 = so[0] + cnt[cell]; p1 = so[1] + cnt[cell + 1]; p2 = so[2] + cnt[cell + 2];
+        base0 = so[0]; base1 = so[1]; base2 = so[2];
     }
-    uint32_t hits = nbl::row_hits(jh.x, jh.y, imask, g, in.G);
-    // Nearly every cell is plain: no excluded partner of the j-cluster sits in the i-group and the
-    // j-cluster is not one of the supercluster's own (no triangle, no ownership split) -- all its
-    // hits carry the all-ones allow word and the counts are two popcounts.
-    const bool special = walk || (B >= sd.c0 && B < sd.c0 + sd.nci);
-    if (!special) {
-        if (!FILL) {
-            p1 = __popc(hits & ~info.nolj);
-            p2 = __popc(hits & info.nolj);
+    int t0 = 0, t1 = 0, t2 = 0;            // !FILL: this lane's share of the segment totals
+    for (int c0 = e0; c0 < e1; c0 += 32) {
+        const int e = c0 + lane;
+        uint32_t hits = 0u, code = 0u;
+        int B = 0;
+        bool special = false;
+        nbl::ClusterInfo info;
+        info.nolj = 0u;
+        info.npart = 0;
+        uint32_t imask = 0u;
+        uint64_t ex[2] = {0ull, 0ull};
+        if (e < e1) {
+            const uint2 ent = in.entries[e];
+            const uint2 jh = in.jhit[e];
+            imask = ent.y & 0xffu;
+            code = ent.x >> 26;
+            B = (int)(ent.x & 0x3ffffffu);
+            info = in.cl_info[B];
+            hits = nbl::row_hits(jh.x, jh.y, imask, g, in.G);
+            // special cells: an exclusion tile of the j-cluster falls on a cluster of this i-group, the
+            // j-cluster is the group's own cluster (triangle) or -- groups of two -- one of the
+            // supercluster's (ownership split); its exclusions did not fit the record (CSR walk)
+            const bool own = in.G == 1 ? (B == sd.c0 + g && code == nbl::kShiftZero) : (B >= sd.c0 && B < sd.c0 + sd.nci);
+            special = nbl::row_excl_tiles(sd, g, in.G, info, in.cl_tiles + B, ex) || own || info.npart < 0;
+        }
+        // class counts of this lane's cell; nearly every cell is plain: two popcounts
+        int n0 = 0, n1 = 0, n2 = 0;
+        uint32_t keep = hits;              // special cells: the hits whose allow word is not empty
+        if (!special) {
+            n1 = __popc(hits & ~info.nolj);
+            n2 = __popc(hits & info.nolj);
         } else {
-            while (hits) {
-                const int tj = __ffs(hits) - 1;
-                hits &= hits - 1u;
-                const int p = ((info.nolj >> tj) & 1u) ? p2++ : p1++;
-                if (p < cap) jent[p] = (uint32_t)(B * nbl::kJGroup + tj) | (code << 26);   // plain: no allow word is read
+            uint32_t h = hits;
+            while (h) {
+                const int tj = __ffs(h) - 1;
+                h &= h - 1u;
+                const uint32_t allow = info.npart >= 0
+                                           ? nbl::row_allow(sd, imask, B, code, g, in.G, tj, ex)
+                                           : nbl::row_allow(sd, imask, B, code, g, in.G, tj, in.excl_start, in.excl_idx,
+                                                            in.slot_of, in.atom, in.n);
+                if (allow == 0u) { keep &= ~(1u << tj); continue; }
+                if (allow != full) n0++;
+                else if ((info.nolj >> tj) & 1u) n2++;
+                else n1++;
             }
         }
-    } else {
-        while (hits) {
-            const int tj = __ffs(hits) - 1;
-            hits &= hits - 1u;
-            const uint32_t allow = nbl::row_allow(sd, imask, B, code, g, in.G, tj, in.excl_start, in.excl_idx, in.slot_of,
-                                                  in.atom, in.n, walk);
-            if (allow == 0u) continue;
-            const bool masked = allow != full, nolj = ((info.nolj >> tj) & 1u) != 0u;
+        if (!FILL) {
+            t0 += n0; t1 += n1; t2 += n2;
+            continue;
+        }
+        // positions: exclusive warp scan of the three counts in one packed word (each sum <= 32 * 8)
+        const uint32_t packed = (uint32_t)n0 | ((uint32_t)n1 << 10) | ((uint32_t)n2 << 20);
+        uint32_t x = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, x, 31);
+        x -= packed;
+        int p0 = base0 + (int)(x & 0x3ffu), p1 = base1 + (int)((x >> 10) & 0x3ffu), p2 = base2 + (int)(x >> 20);
+        base0 += (int)(tot & 0x3ffu); base1 += (int)((tot >> 10) & 0x3ffu); base2 += (int)(tot >> 20);
+        while (keep) {
+            const int tj = __ffs(keep) - 1;
+            keep &= keep - 1u;
+            const bool nolj = ((info.nolj >> tj) & 1u) != 0u;
+            uint32_t allow = full;
+            if (special)
+                allow = info.npart >= 0 ? nbl::row_allow(sd, imask, B, code, g, in.G, tj, ex)
+                                        : nbl::row_allow(sd, imask, B, code, g, in.G, tj, in.excl_start, in.excl_idx,
+                                                         in.slot_of, in.atom, in.n);
+            const bool masked = allow != full;
             const int p = masked ? p0 : nolj ? p2 : p1;
             p0 += masked ? 1 : 0;
             p2 += (!masked && nolj) ? 1 : 0;
             p1 += (!masked && !nolj) ? 1 : 0;
-            if (FILL && p < cap) {
+            if (p < cap) {
                 jent[p] = (uint32_t)(B * nbl::kJGroup + tj) | (code << 26);
-                jallow[p] = (uint16_t)allow;
+                if (masked) jallow[p] = (uint16_t)allow;   // plain entries: no allow word is read
             }
         }
     }
-    if (!FILL) { cnt[cell] = p0; cnt[cell + 1] = p1; cnt[cell + 2] = p2; }
-}
-
-// Exclusive scan of the cell counts along the entries of one supercluster, separately for each of its
-// 3 * groups row segments (columns of the entry-major count array), in place; the column totals go to
-// seg_total.  One block per supercluster, one warp per column at a time, 32 entries per shuffle scan.
-__global__ void __launch_bounds__(256)
-rows_scan_kernel(int ng, const int* __restrict__ sci_off, int* __restrict__ cnt, int* __restrict__ seg_total) {
-    const int s = blockIdx.x;
-    const int e0 = sci_off[s], len = sci_off[s + 1] - e0;
-    const int ncol = 3 * ng, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int col = warp; col < ncol; col += 8) {
-        const int g = col / 3, cls = col - 3 * g;
-        int carry = 0;
-        for (int k0 = 0; k0 < len; k0 += 32) {
-            const int k = k0 + lane;
-            int* p = cnt + ((size_t)(e0 + k) * ng + g) * 3 + cls;
-            const int v = k < len ? *p : 0;
-            int x = v;
+    if (!FILL) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            if (k < len) *p = carry + x - v;
-            carry += __shfl_sync(0xffffffffu, x, 31);
+        for (int o = 16; o > 0; o >>= 1) {
+            t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
         }
-        if (lane == 0) seg_total[(size_t)s * ncol + col] = carry;
+        if (lane == 0) {
+            int* out = seg_total + 3 * ((size_t)s * ng + g);
+            out[0] = t0; out[1] = t1; out[2] = t2;
+        }
     }
 }
 
@@ -602,20 +677,12 @@ static int build_rows(sdm_ctx* c) {
     PairList* pl = c->pl;
     cudaStream_t s = c->stream;
     const int G = pl->row_group, ng = nbl::kMaxCi / G;
-    const size_t ncnt = (size_t)pl->nentries * 3 * ng;
     const int nrows = pl->nsci * ng, nseg = 3 * nrows;
-    if (ncnt + 1 > pl->row_cnt_cap) {
-        pl->row_cnt_cap = (size_t)(ncnt * 1.25) + 1024;
-        if (int rc = pl_realloc(pl, &pl->row_cnt, pl->row_cnt_cap)) return rc;
-    }
-    cluster_info_kernel<<<blocks(pl->ncl), 256, 0, s>>>(pl->ncl, c->n, pl->atom, pl->par, c->T.excl_start, c->T.excl_idx,
-                                                       pl->slot_of, pl->cl_info);
-    const RowsIn in{pl->nentries, G, c->n, pl->entries, pl->entry_jhit, pl->entry_sci, pl->sci, pl->sci_off, pl->cl_info,
+    cluster_info_kernel<<<blocks(pl->ncl, 32), 256, 0, s>>>(pl->ncl, c->n, pl->atom, pl->par, c->T.excl_start, c->T.excl_idx,
+                                                       pl->slot_of, pl->cl_info, pl->cl_tiles);
+    const RowsIn in{G, c->n, pl->entries, pl->entry_jhit, pl->sci, pl->sci_off, pl->cl_info, pl->cl_tiles,
                     c->T.excl_start, c->T.excl_idx, pl->slot_of, pl->atom};
-    if (pl->nentries > 0)
-        rows_kernel<false><<<blocks((long long)pl->nentries * ng, 128), 128, 0, s>>>(in, pl->row_cnt, nullptr, nullptr,
-                                                                                    nullptr, 0);
-    if (pl->nsci > 0) rows_scan_kernel<<<pl->nsci, 256, 0, s>>>(ng, pl->sci_off, pl->row_cnt, pl->seg_total);
+    if (pl->nsci > 0) rows_kernel<false><<<pl->nsci, 32 * ng, 0, s>>>(in, pl->seg_total, nullptr, nullptr, nullptr, 0);
     PL_CUDA(cudaMemsetAsync(pl->seg_total + nseg, 0, sizeof(int), s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->seg_total, pl->seg_off, nseg + 1, s));
     rows_units_count_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, pl->row_chunk, pl->seg_off, pl->row_nunits);
@@ -641,9 +708,8 @@ static int build_rows(sdm_ctx* c) {
         if (int rc = pl_realloc(pl, &pl->ru_val, pl->runits_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->ru_order, pl->runits_cap)) return rc;
     }
-    if (pl->nentries > 0)
-        rows_kernel<true><<<blocks((long long)pl->nentries * ng, 128), 128, 0, s>>>(in, pl->row_cnt, pl->seg_off, pl->jent,
-                                                                                   pl->jallow, (int)pl->jent_cap);
+    if (pl->nsci > 0)
+        rows_kernel<true><<<pl->nsci, 32 * ng, 0, s>>>(in, nullptr, pl->seg_off, pl->jent, pl->jallow, (int)pl->jent_cap);
     rows_units_fill_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, G, pl->row_chunk, pl->sci, pl->seg_off,
                                                         pl->row_unit_off, pl->runits, (int)pl->runits_cap);
     rows_part_off_kernel<<<blocks(c->R + 1), 256, 0, s>>>(pl->G, ng, pl->cell_sci, pl->row_unit_off, pl->nsci, pl->part_off);
@@ -888,6 +954,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->slot_of, total));
     A(pl_alloc(pl, &pl->cl_box, pl->ncl_cap));
     A(pl_alloc(pl, &pl->cl_info, pl->ncl_cap));
+    A(pl_alloc(pl, &pl->cl_tiles, pl->ncl_cap));
     A(pl_alloc(pl, &pl->cell_box, ncells_cap + 1));
     A(pl_alloc(pl, &pl->sci_box, pl->nsci_cap));
     A(pl_alloc(pl, &pl->sci, pl->nsci_cap));
@@ -916,8 +983,6 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     if (const char* e = getenv("SDMB200_ROW_CHUNK")) pl->row_chunk = std::min(nbl::kRowChunkSteps, std::max(1, atoi(e)));
     {
         const int ng = nbl::kMaxCi / pl->row_group;
-        pl->row_cnt_cap = pl->entries_cap * 3 * ng + 1;
-        A(pl_alloc(pl, &pl->row_cnt, pl->row_cnt_cap));
         A(pl_alloc(pl, &pl->seg_total, (size_t)pl->nsci_cap * ng * 3 + 1));
         A(pl_alloc(pl, &pl->seg_off, (size_t)pl->nsci_cap * ng * 3 + 1));
         A(pl_alloc(pl, &pl->row_nunits, (size_t)pl->nsci_cap * ng + 1));

@@ -240,6 +240,8 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
     // lane evaluates its j-atom against the allowed i-atoms of the group.
     int Grow = 1;
     if (const char* e = getenv("SDMB200_ROW_GROUP")) Grow = atoi(e) == 2 ? 2 : 1;
+    const bool use_walk = getenv("SDM_HOSTCHECK_WALK") != nullptr;
+    std::vector<float> par2(2 * (size_t)nslot, 1.0f);   // the checker carries no LJ parameters: every atom has a term
     const int ng = kMaxCi / Grow;
     std::vector<std::pair<int, int>> found;
     const double rc2 = rc * rc;
@@ -254,12 +256,18 @@ long long hostcheck_pairs(int n, int R, const double* pos, int periodic, const d
             const int sh[3] = {shift_x(code), shift_y(code), shift_z(code)};
             uint32_t jh_lo, jh_hi;
             entry_hits(V, sd, ex[e], imask, &jh_lo, &jh_hi);
+            // the j-cluster's exclusion tiles (cluster_info_kernel), or the CSR walk when SDM_HOSTCHECK_WALK is set
+            ClusterTiles tiles;
+            const ClusterInfo info = cluster_info(cj, atom.data(), par2.data(), excl_start.data(), excl_idx.data(),
+                                                  slot_of.data(), n, &tiles);
             for (int g = 0; g < ng; g++) {
                 const uint32_t hits = row_hits(jh_lo, jh_hi, imask, g, Grow);
                 for (int tj = 0; tj < kJGroup; tj++) {
                     if (!((hits >> tj) & 1u)) continue;
-                    const uint32_t allow = row_allow(sd, imask, cj, code, g, Grow, tj, excl_start.data(), excl_idx.data(),
-                                                     slot_of.data(), atom.data(), n);
+                    const uint32_t allow = (use_walk || info.npart < 0)
+                                               ? row_allow(sd, imask, cj, code, g, Grow, tj, excl_start.data(),
+                                                           excl_idx.data(), slot_of.data(), atom.data(), n)
+                                               : row_allow(sd, imask, cj, code, g, Grow, tj, info, &tiles);
                     if (!allow) continue;
                     row_entries += 1;
                     row_len[(size_t)s * ng + g] += 1;
