@@ -217,7 +217,7 @@ __device__ __forceinline__ void red_fixed_nonzero(long long* p, const float f, c
 }
 
 #ifndef SDM_ROW_MINB
-#define SDM_ROW_MINB 20
+#define SDM_ROW_MINB 24
 #endif
 #ifndef SDM_ROW_JPREFETCH
 #define SDM_ROW_JPREFETCH 1   // 1: j-atom data one step ahead (row entries two ahead); 0: entries one ahead only
