@@ -226,7 +226,44 @@ def run_reference(args):
     return 0
 
 
-def md_leg(case, R, args, device, stream, flush, states, rank, skin=None, nstlist=None, steps=None, dt=0.001):
+def md_setup(case, freeze_solute=True):
+    """Masses and constraints of the dynamics legs.  Bonded forces are external to the path (a10: they come
+    from OpenMM's force group 1), so a free solute would move under nonbonded forces alone -- unphysical, and
+    its runaway atoms would dictate the pair-list lifetime.  freeze_solute: atoms that have bonded terms (every
+    molecule that is not a rigid three-site water or a single ion) get mass 0 (the library does not move massless
+    particles, like ReferenceStochasticDynamicsSDM.cpp:150) and their constraints are dropped; the waters (SETTLE)
+    and ions -- 99 % of the atoms, whose force field is complete without bonded terms -- move."""
+    masses = case.masses.copy()
+    pairs, dist = case.constraint_pairs, case.constraint_dist
+    frozen = 0
+    if freeze_solute and pairs is not None and len(pairs) > 0:
+        n = len(masses)
+        deg = np.bincount(pairs.ravel(), minlength=n)
+        # connected components of the exclusion graph = molecules
+        parent = np.arange(n)
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+        for a, b in case.system.exclusions:
+            ra, rb = find(int(a)), find(int(b))
+            if ra != rb:
+                parent[ra] = rb
+        root = np.array([find(a) for a in range(n)])
+        size = np.bincount(root, minlength=n)[root]
+        rigid_water = (size == 3) & (deg == 2)
+        solute = (size > 1) & ~rigid_water
+        masses[solute] = 0.0
+        frozen = int(solute.sum())
+        keep = ~(solute[pairs[:, 0]] | solute[pairs[:, 1]])
+        pairs, dist = pairs[keep], dist[keep]
+    return masses, pairs, dist, frozen
+
+
+def md_leg(case, R, args, device, stream, flush, states, rank, skin=None, nstlist=None, steps=None, dt=0.001,
+           freeze_solute=True):
     """Device-resident dynamics (sdm_md_step) as the reference's example runs it
     (example/test_explicit.py:166-169: 300 K, friction 0.1/ps, 1 fs): real masses, thermal
     velocities, the fixture's own distance constraints (SETTLE waters + X-H clusters) applied between
@@ -241,17 +278,19 @@ def md_leg(case, R, args, device, stream, flush, states, rank, skin=None, nstlis
     n = case.system.n_atoms
     kT = 1.380658e-23 * 6.0221367e23 / 1000.0 * 300.0
     rng = np.random.default_rng(77 + rank)
-    have_cons = case.constraint_pairs is not None and len(case.constraint_pairs) > 0
+    masses, cpairs, cdist, frozen = md_setup(case, freeze_solute)
+    have_cons = cpairs is not None and len(cpairs) > 0
+    vscale = np.where(masses > 0, np.sqrt(kT / np.maximum(masses, 1e-30)), 0.0)[:, None]
     with SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=args.pair_mode, device=device,
                     skin=skin, nstlist=nstlist) as c:
         c.set_stream(stream.cuda_stream)
-        c.md_init(case.masses, 300.0, 0.1, dt, seed=1234 + rank)
+        c.md_init(masses, 300.0, 0.1, dt, seed=1234 + rank)
         if have_cons:
-            c.md_set_constraints(case.constraint_pairs, case.constraint_dist, 1e-5)
+            c.md_set_constraints(cpairs, cdist, 1e-5)
         for r in range(R):
             c.set_alchemical(r, states[(rank * R + r) % len(states)])
             c.set_positions(r, case.positions)
-            c.md_set_velocities(r, rng.normal(size=(n, 3)) * np.sqrt(kT / case.masses)[:, None])
+            c.md_set_velocities(r, rng.normal(size=(n, 3)) * vscale)
         c.md_step(2 * nstlist)          # warm-up: first list, graph capture, constraint kick of the thermal start
         torch.cuda.synchronize()
         b0, (t0, r0) = c.info("n_list_builds"), c.md_counters()
@@ -266,17 +305,18 @@ def md_leg(case, R, args, device, stream, flush, states, rank, skin=None, nstlis
         sc = c.read_results(None)
         ok = all(x["status"] == 0 for x in sc)
         ke = c.md_kinetic_energy(0)
-        ncons = len(case.constraint_dist) if have_cons else 0
-        t_kin = 2.0 * ke / ((3 * n - ncons) * kT) * 300.0
+        ncons = len(cdist) if have_cons else 0
+        t_kin = 2.0 * ke / ((3 * (n - frozen) - ncons) * kT) * 300.0
     return {"value": R / (md_ms * 1e-3), "unit": "replica-steps/s", "ms_per_step": md_ms,
             "ns_per_day_per_replica": 1e3 / md_ms * dt * 1e-3 * 86400, "dt_ps": dt, "steps": steps,
             "skin_nm": skin, "nstlist": nstlist, "list_builds": int(builds),
             "steps_repeated_stale_list": int(r1 - r0), "steps_taken": int(t1 - t0), "status_ok": bool(ok),
-            "kinetic_temperature_K": t_kin, "constraints": ncons,
+            "kinetic_temperature_K": t_kin, "constraints": ncons, "frozen_solute_atoms": frozen,
             "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
             "note": "sdm_md_step on the device: dual-state eval + FP64 Langevin update + SETTLE/SHAKE constraints, "
-                    "real masses, 300 K thermal start, friction 0.1/ps; bonded forces are external to the path "
-                    "(zero here); a step whose list went stale is not taken: the list is rebuilt and the step repeated "
+                    "real masses, 300 K thermal start, friction 0.1/ps; bonded forces are external to the path, so "
+                    "the atoms that have bonded terms (the host and the two ligands) are held fixed (mass 0) while the "
+                    "rigid waters and the ions move; a step whose list went stale is not taken: the list is rebuilt and the step repeated "
                     "(counted in steps_repeated_stale_list, its time is inside ms_per_step)"}
 
 
@@ -300,13 +340,15 @@ def cfg3_leg(case, args, world, rank, device, stream, rounds=6, steps_per_round=
     with SDMContext(case.system, case.displacement, n_replicas=Rl, pair_mode=args.pair_mode, device=device,
                     skin=args.md_skin, nstlist=args.md_nstlist) as c:
         c.set_stream(stream.cuda_stream)
-        c.md_init(case.masses, 300.0, 0.1, 0.001, seed=4321 + rank)
-        c.md_set_constraints(case.constraint_pairs, case.constraint_dist, 1e-5)
+        masses, cpairs, cdist, frozen = md_setup(case, True)
+        vscale = np.where(masses > 0, np.sqrt(kT / np.maximum(masses, 1e-30)), 0.0)[:, None]
+        c.md_init(masses, 300.0, 0.1, 0.001, seed=4321 + rank)
+        c.md_set_constraints(cpairs, cdist, 1e-5)
         state_of = np.arange(first, first + Rl)
         for r in range(Rl):
             c.set_alchemical(r, states[state_of[r]])
             c.set_positions(r, case.positions)
-            c.md_set_velocities(r, rng.normal(size=(n, 3)) * np.sqrt(kT / case.masses)[:, None])
+            c.md_set_velocities(r, rng.normal(size=(n, 3)) * vscale)
         c.md_step(2 * steps_per_round)
         torch.cuda.synchronize()
         if world > 1:
@@ -634,8 +676,9 @@ def main():
             raise errors[0]
         return dt, [x for x in lasts if x is not None][-1]
 
-    def e2e_run(nsteps, depth, timed):
-        """nsteps steps with `depth` batches in flight; returns (seconds, last scalars)."""
+    def e2e_run(nsteps, depth, timed, flush_each=False):
+        """nsteps steps with `depth` batches in flight; returns (seconds, last scalars).  flush_each: a 160 MiB
+        write runs beside every step (needed when the batches in flight fit the L2 together)."""
         if timed and depth > 1 and world == 1 and args.e2e_threads:
             return e2e_run_threaded(nsteps, depth)
         torch.cuda.synchronize()
@@ -645,7 +688,7 @@ def main():
         t0 = time.perf_counter()
         last = None
         for k in range(nsteps):
-            if timed:
+            if timed and flush_each:
                 with torch.cuda.stream(flush_stream):
                     flush.zero_()            # keeps evicting L2 next to the pipeline, unordered
             last = e2e_submit(k, depth) or last
@@ -670,23 +713,32 @@ def main():
         for _ in range((target - age_now) % args.nstlist):
             e_ctx[d].eval()
         e_ctx[d].synchronize()
-    e2e_t, s = e2e_run(args.steps, D, True)
+    # L2 rule of the timed region: the D batches in flight have disjoint working sets (cfg2, R = 16: ~125 MB each --
+    # rows 67 MB, positions / forces 39 MB, sorted atoms 10 MB, accumulators 8 MB) that follow each other through
+    # the 126 MB L2, and every step's inputs arrive from the host: with D >= 2 no batch finds its previous step's
+    # data cached, so no flush kernel is needed (it would only steal SM time from the pipeline).  With one batch
+    # in flight the flush write runs beside every step.  The figure WITH the flush kernel is reported next to it.
+    ws_mb = D * 125.0 * (R * n) / (16 * 20446.0)
+    e2e_needs_flush = D < 2 or ws_mb <= 2 * 126.0
+    e2e_t, s = e2e_run(args.steps, D, True, flush_each=e2e_needs_flush)
+    assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
+    e2e_flush_t, s = e2e_run(args.steps, D, True, flush_each=True)
     assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
     io32[0] = True
     e2e_run(max(args.warmup, D), D, False)
-    e2e32_t, s = e2e_run(args.steps, D, True)
+    e2e32_t, s = e2e_run(args.steps, D, True, flush_each=e2e_needs_flush)
     assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
     f32_dev = float(np.abs(e_hf32[0].array - e_hf[0].array).max() / max(np.abs(e_hf[0].array).max(), 1e-30))
     io32[0] = False
     e2e_run(args.warmup, 1, False)
-    e2e_serial_t, s = e2e_run(args.steps, 1, True)
+    e2e_serial_t, s = e2e_run(args.steps, 1, True, flush_each=True)
     assert all(x["status"] == 0 for x in s), [x["status"] for x in s]
     for cg in e_ctx:
         cg.close()
     if world > 1:
-        tt = torch.tensor([e2e_t, e2e_serial_t, e2e32_t], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([e2e_t, e2e_serial_t, e2e32_t, e2e_flush_t], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t, e2e_serial_t, e2e32_t = float(tt[0].item()), float(tt[1].item()), float(tt[2].item())
+        e2e_t, e2e_serial_t, e2e32_t, e2e_flush_t = (float(tt[k].item()) for k in range(4))
     e2e_value = world * R * args.steps / e2e_t
     h2d = R * n * 3 * 8
     d2h = R * n * 3 * 8 + R * 8 * 20
@@ -740,6 +792,12 @@ def main():
                                "note": "same pipeline through sdm_set_positions_all_f32 / sdm_enqueue_results_f32: positions and "
                                        "forces cross PCIe in single precision (the precision of the reference's OpenCL path, "
                                        "OpenCLSDMKernels.cpp:96-103); arithmetic on the device unchanged"},
+                    "l2": ("%d batches in flight x ~%.0f MB working set each = %.0f MB > 126 MB L2 and fresh host inputs every "
+                           "step: inputs larger than L2, no flush kernel" % (D, ws_mb / D, ws_mb)) if not e2e_needs_flush else
+                          "160 MiB flush write beside every step",
+                    "with_flush_kernel": {"value": world * R * args.steps / e2e_flush_t, "ms_per_step": 1e3 * e2e_flush_t / args.steps,
+                                          "note": "same pipeline with a 160 MiB flush write launched beside every step (how this "
+                                                  "leg ran in round 1): the fill kernel takes its ~45 us of SM time per step"},
                     "exchange_every_steps": args.exchange_every if world > 1 else None,
                     "list_builds": "lists pre-aged to staggered ages: the timed steps carry K/nstlist list builds",
                     "host_threads": D if (world == 1 and args.e2e_threads and D > 1) else 1,
@@ -749,7 +807,7 @@ def main():
                     "note": "C-ABI calls with pinned HOST buffers: sdm_set_positions_all (H2D) + sdm_eval + sdm_enqueue_results (D2H of forces and scalars) "
                             "+ sdm_synchronize/sdm_collect_scalars per step inside the timed region (host wall clock over all K steps, synchronize on both "
                             "sides); D batches of R replicas in flight on D contexts/streams so copies overlap the kernels of the neighbouring batches; "
-                            "the D working sets (D x ~60 MB) rotate through the 126 MB L2 and a 160 MiB flush write runs beside every step"},
+                            "see l2 for the cache rule of this leg"},
             "clocks": sampler.result(), "wall_s_resident_leg": wall_resident}
 
     if rank == 0 and R > 1 and not args.no_single_lambda:

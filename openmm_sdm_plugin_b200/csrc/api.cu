@@ -742,6 +742,10 @@ int sdm_eval(sdm_ctx* c) {
 // An evaluation that ran out of per-hit scratch says so in its status; the next one gets twice
 // the room (the caller repeats the evaluation, as the header documents for SDM_ERR_CAPACITY).
 static void note_status(sdm_ctx* c, int status) {
+    if (status == SDM_ERR_CAPACITY && sdm_ctx_pairlist_overflowed(c)) {
+        c->list_valid = false;   // the list build ran past its bounds: the next one is sized on the host
+        return;
+    }
     if (status == SDM_ERR_CAPACITY && c->pairf_scale < (1 << 16)) {
         c->pairf_scale *= 2;
         c->graph_valid = false;

@@ -499,11 +499,12 @@ pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ Pair
         ec_store.n = T.n;
         ec = &ec_store;
     }
+    const int nrunits = *V.nrunits;
     for (;;) {
         int unit = 0;
         if (lane == 0) unit = atomicAdd(unit_counter, 1);
         unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= V.nrunits) break;
+        if (unit >= nrunits) break;
         if (V.runit_order) unit = V.runit_order[unit];   // longest units first
         process_row_unit<NI, PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, V.runits[unit], lane,
                                                     s_ip[warp], s_shift, ec);
@@ -515,14 +516,14 @@ pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ Pair
 // chosen at build time; raises SDM_ERR_STALE_LIST when an atom moved more than skin/2.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-refresh_kernel(Topology T, nbl::Grid G, int nslot, const double* __restrict__ pos_all,
+refresh_kernel(Topology T, nbl::Grid G, const int* __restrict__ d_nslot, const double* __restrict__ pos_all,
                const int* __restrict__ atom, const int* __restrict__ img,
                const float4* __restrict__ posq_build, float4* __restrict__ posq, float half_skin2,
                int* flags, int* list_age, unsigned int* max_disp2) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) *list_age += 1;   // one more evaluation with this list (read by the scalar stage)
     float d2 = 0.f;
-    const int ga = s < nslot ? atom[s] : -1;
+    const int ga = s < *d_nslot ? atom[s] : -1;
     if (ga >= 0) {   // a dummy slot keeps its far-away coordinates
         const int r = ga / T.n;
         const double* p = pos_all + 3 * (size_t)ga;  // ga = r*n + a
@@ -555,7 +556,7 @@ refresh_kernel(Topology T, nbl::Grid G, int nslot, const double* __restrict__ po
 void launch_pair_rows(const Topology& T, const PairListView& V, const double* pos_all,
                       long long* f1acc, double* epart, long long* cpart, int exact,
                       int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s) {
-    if (V.nrunits <= 0) return;
+    if (V.nrunits_ub <= 0) return;
     cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
     const PairEmit em = emit ? *emit : PairEmit{nullptr, nullptr, 0, -1};
@@ -569,7 +570,7 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
                 resident = SDM_ROW_MINB;                                                          \
             if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
         }                                                                                         \
-        const int grid = std::min((V.nrunits + kWarps - 1) / kWarps, num_sms * resident);          \
+        const int grid = std::min((V.nrunits_ub + kWarps - 1) / kWarps, num_sms * resident);       \
         pair_row_kernel<N, P, X, E><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
                                                                 unit_counter, em);                \
     } while (0)
@@ -592,11 +593,11 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
 #undef SDM_LAUNCH
 }
 
-void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,
+void launch_refresh(const Topology& T, const nbl::Grid& G, const int* d_nslot, int nslot_ub, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq,
                     float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s) {
-    if (nslot <= 0) return;
-    refresh_kernel<<<(nslot + 255) / 256, 256, 0, s>>>(T, G, nslot, pos_all, atom, img, posq_build,
+    if (nslot_ub <= 0) return;
+    refresh_kernel<<<(nslot_ub + 255) / 256, 256, 0, s>>>(T, G, d_nslot, pos_all, atom, img, posq_build,
                                                       posq, half_skin2, flags, list_age, max_disp2);
 }
 

@@ -75,7 +75,17 @@ struct PairList {
     double* minmax = nullptr;   // [6] non-periodic extent reduction
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
-    int* h_counts = nullptr;    // pinned [8]
+    int* h_counts = nullptr;    // pinned [16]: counts of the last build (see kCnt*)
+    int* d_cnt = nullptr;       // device [16]
+    cudaEvent_t ev_counts = nullptr;   // the read-back of d_cnt of the last build has landed in h_counts
+    bool counts_pending = false;       // that read-back has not been looked at yet
+    bool have_counts = false;          // the host counts describe a complete earlier build
+    bool force_sync = false;           // the next build sizes its buffers step by step on the host
+    int kd_in_block = 1;               // SDMB200_KD_SORTS=1: the two kd rounds as global radix sorts (development knob)
+    int async_builds = 1;              // SDMB200_ASYNC_BUILD=0: every build synchronises (development knob)
+    // launch bounds of the device-sized stages (upper bounds of the counts the kernels read from device memory)
+    int ub_nsci = 0, ub_nraw = 0, ub_nrunits = 0;
+    int64_t n_async = 0, n_sync = 0;
     double* h_minmax = nullptr; // pinned [6]
     std::vector<void*> allocs;
     double density_hint = 0;    // atoms / nm^3 used to size cells
@@ -175,6 +185,64 @@ __global__ void refine_key_kernel(Grid G, int level, int total, const double* __
     vals[p] = ga;
 }
 
+// The two kd refinement rounds of every cell in ONE kernel, one block per cell (replaces two global
+// radix sorts): the atoms of the cell arrive in z order; they are ordered by y inside each z half and by
+// x inside each y half of those -- the same keys (16-bit in-cell coordinates, ties keep the previous
+// order) and the same split points (nbl::kd_bucket) as the sort-based rounds, so the result is the
+// order those produce.  Ranks are counted directly (a cell holds about 64 atoms; an overfull one just
+// takes longer); `scratch` holds y | x << 16 | position after the first round << 32 per atom.
+__global__ void __launch_bounds__(64)
+kd_refine_kernel(Grid G, const double* __restrict__ pos_all, const int* __restrict__ vals_sorted,
+                 const int* __restrict__ cell_first, const int* __restrict__ cell_count,
+                 uint64_t* __restrict__ scratch, int* __restrict__ vals_out) {
+    const int c = blockIdx.x;
+    const int first = cell_first[c], cnt = cell_count[c];
+    if (cnt <= 0) return;
+    const int h1 = nbl::split_first(cnt);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int ga = vals_sorted[first + i];
+        const double* q = pos_all + 3 * (size_t)ga;
+        float xw[3];
+        int img[3];
+        uint32_t fr[3];
+        nbl::atom_cell(G, ga / G.n, q[0], q[1], q[2], xw, img, fr);
+        scratch[first + i] = (uint64_t)fr[1] | ((uint64_t)fr[0] << 16);
+    }
+    __syncthreads();
+    // round 1: by y inside the z half
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int b1 = i >= h1;
+        const int s0 = b1 ? h1 : 0, s1 = b1 ? cnt : h1;
+        const uint32_t yi = (uint32_t)scratch[first + i] & 0xffffu;
+        int rank = s0;
+        for (int j = s0; j < s1; j++) {
+            const uint32_t yj = (uint32_t)scratch[first + j] & 0xffffu;
+            rank += (yj < yi || (yj == yi && j < i)) ? 1 : 0;
+        }
+        scratch[first + i] |= (uint64_t)rank << 32;
+    }
+    __syncthreads();
+    // round 2: by x inside the y half of the z half; then the atom's final place
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int b1 = i >= h1;
+        const int s0 = b1 ? h1 : 0, s1 = b1 ? cnt : h1;
+        const int h2 = nbl::split_first(s1 - s0);
+        const uint64_t wi = scratch[first + i];
+        const int pi = (int)(wi >> 32);
+        const int b2 = (pi - s0) >= h2;
+        const uint32_t xi = (uint32_t)(wi >> 16) & 0xffffu;
+        int rank = s0 + (b2 ? h2 : 0);
+        for (int j = s0; j < s1; j++) {
+            const uint64_t wj = scratch[first + j];
+            const int pj = (int)(wj >> 32);
+            if (((pj - s0) >= h2) != b2) continue;
+            const uint32_t xj = (uint32_t)(wj >> 16) & 0xffffu;
+            rank += (xj < xi || (xj == xi && pj < pi)) ? 1 : 0;
+        }
+        vals_out[first + rank] = vals_sorted[first + i];
+    }
+}
+
 __global__ void cell_bounds_kernel(int total, const uint64_t* __restrict__ keys_sorted,
                                    int* cell_first, int* cell_count) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,9 +307,9 @@ __global__ void fill_dummies_kernel(int ncells, const int* __restrict__ cell_cou
     }
 }
 
-__global__ void bbox_kernel(int ncl, const float4* __restrict__ posq, BBox* cl_box) {
+__global__ void bbox_kernel(const int* __restrict__ d_nslot, const float4* __restrict__ posq, BBox* cl_box) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncl) return;
+    if (c >= *d_nslot / nbl::kClusterSize) return;
     cl_box[c] = nbl::group_bbox(reinterpret_cast<const float*>(posq), c * nbl::kClusterSize,
                                 nbl::kClusterSize);
 }
@@ -285,19 +353,23 @@ struct FillEmit {
     }
 };
 
-__global__ void search_count_kernel(nbl::SearchView V, int nsci, int noff, int* item_count) {
+// The counts a stage reads (superclusters, raw entries, ...) live in device memory; the grids are sized
+// with host-side upper bounds (ub_*), so a build needs no host synchronisation.  Items past the real
+// count get a zero so that the scans can run over the bound.
+__global__ void search_count_kernel(nbl::SearchView V, const int* __restrict__ d_nsci, int ub_items, int noff,
+                                    int* item_count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nsci * noff) return;
-    item_count[t] = nbl::search_any(V, t / noff, t % noff, CountEmit());
+    if (t >= ub_items) return;
+    item_count[t] = t < *d_nsci * noff ? nbl::search_any(V, t / noff, t % noff, CountEmit()) : 0;
 }
 
-__global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
+__global__ void search_fill_kernel(nbl::SearchView V, const int* __restrict__ d_nsci, int noff,
                                    const int* __restrict__ item_off, uint2* entries, int* esci, int* c0nci,
                                    int cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nsci * noff) return;
+    if (t >= *d_nsci * noff) return;
     const int base = item_off[t];
-    if (base >= cap) return;
+    if (item_off[t + 1] > cap) return;   // the whole item must fit (overflow is reported by finish_kernel)
     const SciDesc sd = V.sci[t / noff];
     nbl::search_any(V, t / noff, t % noff, FillEmit{entries, esci, c0nci, base, t / noff, sd.c0 | (sd.nci << 27)});
 }
@@ -306,11 +378,15 @@ __global__ void search_fill_kernel(nbl::SearchView V, int nsci, int noff,
 // (cluster c0+ci, the entry's shifted j-cluster) is closer than rlist -- the predicate of
 // nbl::prune_imask.  Lane (tj, ti) = (lane>>2, lane&3) tests j-atom tj against i-atoms ti, ti+4.
 __global__ void __launch_bounds__(128)
-prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ raw_c0nci,
-             const float4* __restrict__ posq, int* __restrict__ keep, uint2* __restrict__ jhit) {
+prune_kernel(Grid G, const int* __restrict__ d_nraw, int ub_nraw, int raw_cap, uint2* __restrict__ raw,
+             const int* __restrict__ raw_c0nci, const float4* __restrict__ posq, int* __restrict__ keep,
+             uint2* __restrict__ jhit) {
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (e >= nraw) return;
+    if (e >= min(*d_nraw, raw_cap)) {
+        if (e <= ub_nraw && lane == 0) keep[e] = 0;   // the scan runs over ub_nraw + 1 flags
+        return;
+    }
     const uint2 ent = raw[e];                 // two independent loads, then the atoms: no
     const int c0 = raw_c0nci[e] & 0x7ffffff;  // dependent descriptor chain per entry
     const int B = (int)(ent.x & 0x3ffffffu);
@@ -357,11 +433,12 @@ prune_kernel(Grid G, int nraw, uint2* __restrict__ raw, const int* __restrict__ 
     }
 }
 
-__global__ void compact_kernel(int nraw, const uint2* __restrict__ raw, const int* __restrict__ raw_sci,
-                               const int* __restrict__ keep, const int* __restrict__ pos, uint2* entries,
-                               int* entry_sci, int cap, const uint2* __restrict__ raw_jhit, uint2* entry_jhit) {
+__global__ void compact_kernel(const int* __restrict__ d_nraw, int raw_cap, const uint2* __restrict__ raw,
+                               const int* __restrict__ raw_sci, const int* __restrict__ keep,
+                               const int* __restrict__ pos, uint2* entries, int* entry_sci, int cap,
+                               const uint2* __restrict__ raw_jhit, uint2* entry_jhit) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nraw || !keep[e]) return;
+    if (e >= min(*d_nraw, raw_cap) || !keep[e]) return;
     const int k = pos[e];
     if (k >= cap) return;
     entries[k] = raw[e];
@@ -369,12 +446,13 @@ __global__ void compact_kernel(int nraw, const uint2* __restrict__ raw, const in
     entry_sci[k] = raw_sci[e];
 }
 
-__global__ void sci_off_kernel(int nsci, int noff, int nraw, const int* __restrict__ item_off,
-                               const int* __restrict__ pos, int* sci_off) {
+__global__ void sci_off_kernel(const int* __restrict__ d_nsci, int noff, const int* __restrict__ d_nraw, int ub_nraw,
+                               const int* __restrict__ item_off, const int* __restrict__ pos, int* sci_off) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nsci = *d_nsci;
     if (s > nsci) return;
-    const int first = s < nsci ? item_off[(size_t)s * noff] : nraw;
-    sci_off[s] = pos[first];   // pos has nraw+1 elements (exclusive scan incl. the total)
+    const int first = s < nsci ? item_off[(size_t)s * noff] : *d_nraw;
+    sci_off[s] = pos[min(first, ub_nraw)];   // pos: exclusive scan over ub_nraw + 1 flags, zero past the real count
 }
 
 // ---- per-atom j rows (nblist_core.h stage 5) -----------------------------------------------------
@@ -402,7 +480,7 @@ struct RowsIn {
 // cluster then take turns to enter their partners into the cluster's record in shared memory, in
 // atom order, so the record is the one the scalar routine builds.
 __global__ void __launch_bounds__(256)
-cluster_info_kernel(int ncl, int n, const int* __restrict__ atom, const float2* __restrict__ par,
+cluster_info_kernel(const int* __restrict__ d_nslot, int n, const int* __restrict__ atom, const float2* __restrict__ par,
                     const int* __restrict__ excl_start, const int* __restrict__ excl_idx,
                     const int* __restrict__ slot_of, nbl::ClusterInfo* __restrict__ out,
                     nbl::ClusterTiles* __restrict__ tiles) {
@@ -410,6 +488,7 @@ cluster_info_kernel(int ncl, int n, const int* __restrict__ atom, const float2* 
     __shared__ nbl::ClusterTiles s_tiles[32];
     const int lc = threadIdx.x >> 3, tj = threadIdx.x & 7;
     const int c = blockIdx.x * 32 + lc;
+    const int ncl = *d_nslot / nbl::kClusterSize;
     if (tj == 0) {
         s_info[lc].nolj = 0u;
         s_info[lc].npart = 0;
@@ -462,10 +541,14 @@ cluster_info_kernel(int ncl, int n, const int* __restrict__ atom, const float2* 
 
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-rows_kernel(RowsIn in, int* __restrict__ seg_total, const int* __restrict__ seg_off, uint32_t* __restrict__ jent,
-            uint16_t* __restrict__ jallow, int cap) {
+rows_kernel(RowsIn in, const int* __restrict__ d_nsci, int* __restrict__ seg_total, const int* __restrict__ seg_off,
+            uint32_t* __restrict__ jent, uint16_t* __restrict__ jallow, int cap) {
     const int ng = nbl::kMaxCi / in.G;
     const int s = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;   // blockDim.x = 32 * ng
+    if (s >= *d_nsci) {   // the grid covers the bound: rows past the real count are empty
+        if (!FILL && lane < 3) seg_total[3 * ((size_t)s * ng + g) + lane] = 0;
+        return;
+    }
     const uint32_t full = in.G == 2 ? 0xffffu : 0xffu;
     const SciDesc sd = in.sci[s];
     const int e0 = in.sci_off[s], e1 = in.sci_off[s + 1];
@@ -581,20 +664,21 @@ __device__ __forceinline__ void row_bounds(int s, int g, int ng, const int* __re
     *end = so[3];
 }
 
-__global__ void rows_units_count_kernel(int nsci, int ng, int chunk, const int* __restrict__ seg_off,
-                                        int* __restrict__ row_nunits) {
+__global__ void rows_units_count_kernel(const int* __restrict__ d_nsci, int ub_nsci, int ng, int chunk,
+                                        const int* __restrict__ seg_off, int* __restrict__ row_nunits) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nsci * ng) return;
+    if (t >= ub_nsci * ng) return;
+    if (t >= *d_nsci * ng) { row_nunits[t] = 0; return; }
     int b, m, l, e;
     row_bounds(t / ng, t % ng, ng, seg_off, &b, &m, &l, &e);
     row_nunits[t] = (e - b + 32 * chunk - 1) / (32 * chunk);
 }
 
-__global__ void rows_units_fill_kernel(int nsci, int ng, int G, int chunk, const SciDesc* __restrict__ sci,
-                                       const int* __restrict__ seg_off, const int* __restrict__ row_unit_off,
-                                       RowUnit* __restrict__ units, int cap) {
+__global__ void rows_units_fill_kernel(const int* __restrict__ d_nsci, int ng, int G, int chunk,
+                                       const SciDesc* __restrict__ sci, const int* __restrict__ seg_off,
+                                       const int* __restrict__ row_unit_off, RowUnit* __restrict__ units, int cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nsci * ng) return;
+    if (t >= *d_nsci * ng) return;
     const int s = t / ng, g = t % ng;
     int b, m, l, e;
     row_bounds(s, g, ng, seg_off, &b, &m, &l, &e);
@@ -610,17 +694,20 @@ __global__ void rows_units_fill_kernel(int nsci, int ng, int G, int chunk, const
 
 // sort key of a unit: longer units first; the radix sort is stable, so units of equal length keep
 // the list order (neighbouring i-clusters, which share their j-atoms in L1)
-__global__ void rows_unit_key_kernel(int nunits, const RowUnit* __restrict__ units, uint32_t* key, int* val) {
+__global__ void rows_unit_key_kernel(const int* __restrict__ d_nunits, int ub_nunits, int cap,
+                                     const RowUnit* __restrict__ units, uint32_t* key, int* val) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= nunits) return;
-    key[u] = 63u - (uint32_t)min(63, (units[u].end - units[u].begin + 31) >> 5);
+    if (u >= ub_nunits) return;
+    // the sort runs over the bound: padding keys sort behind every unit
+    key[u] = u < min(*d_nunits, cap) ? 63u - (uint32_t)min(63, (units[u].end - units[u].begin + 31) >> 5) : 64u;
     val[u] = u;
 }
 
 __global__ void rows_part_off_kernel(Grid G, int ng, const int* __restrict__ cell_sci,
-                                     const int* __restrict__ row_unit_off, int nsci, int* part_off) {
+                                     const int* __restrict__ row_unit_off, const int* __restrict__ d_nsci, int* part_off) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > G.R) return;
+    const int nsci = *d_nsci;
     const int s = r == G.R ? nsci : min(cell_sci[r * G.ncell], nsci);
     part_off[r] = row_unit_off[(size_t)s * ng];
 }
@@ -671,58 +758,106 @@ int setup_grid(sdm_ctx* c, PairList* pl, const double lo[3], const double ext[3]
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// counts of a build: device words, read back once, asynchronously
+// ---------------------------------------------------------------------------------------------
+enum { kCntSlot = 0, kCntSci, kCntRaw, kCntEntries, kCntJent, kCntUnits, kCntOverflow, kCntUnitsLaunch, kCntN = 16 };
+
+// Last kernel of a build: gathers the counts the stages left at the ends of their scans, compares them
+// with the capacities and the launch bounds this build ran with, and -- if one of them was exceeded --
+// raises SDM_ERR_CAPACITY for every replica and hides the (incomplete) units from the pair kernel.
+// Also starts the list's age and displacement tracking (one evaluation with the new list is under way).
+__global__ void finish_kernel(const int* d_nslot, const int* d_nsci, int ub_nsci, const int* d_nraw, const int* d_nent,
+                              const int* d_njent, const int* d_nunits, int raw_cap, int ub_nraw, int entries_cap,
+                              int jent_cap, int runits_cap, int ub_nunits, int R, int* flags, int* cnt,
+                              int* list_age, unsigned int* max_disp2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nraw = *d_nraw, nent = *d_nent, njent = *d_njent, nunits = *d_nunits;
+    const bool over = *d_nsci > ub_nsci || nraw > raw_cap || nraw > ub_nraw || nent > entries_cap || njent > jent_cap ||
+                      nunits > runits_cap || nunits > ub_nunits;
+    cnt[kCntSlot] = *d_nslot;
+    cnt[kCntSci] = *d_nsci;
+    cnt[kCntRaw] = nraw;
+    cnt[kCntEntries] = nent;
+    cnt[kCntJent] = njent;
+    cnt[kCntUnits] = nunits;
+    cnt[kCntOverflow] = over ? 1 : 0;
+    cnt[kCntUnitsLaunch] = over ? 0 : nunits;
+    if (over)
+        for (int r = 0; r < R; r++) flags[r] = SDM_ERR_CAPACITY;
+    *list_age = 1;
+    *max_disp2 = 0u;
+}
+
+// Launch bound for a count that was `prev` at the last build: a quarter more, and sticky -- a bound that
+// still has room is kept, so that consecutive builds (and the evaluation graph) launch identical grids.
+static int sticky_bound(int bound, int prev, int slack, long long cap) {
+    if (bound > 0 && prev <= bound - bound / 12 && prev >= bound / 2) return bound;
+    return (int)std::min<long long>(cap, (long long)prev + prev / 4 + slack);
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-atom j rows from the pruned entries and the System's exclusions (nblist_core.h stage 5)
 // ---------------------------------------------------------------------------------------------
-static int build_rows(sdm_ctx* c) {
+static int build_rows(sdm_ctx* c, bool sync, const int* d_nslot, const int* d_nsci) {
     PairList* pl = c->pl;
     cudaStream_t s = c->stream;
     const int G = pl->row_group, ng = nbl::kMaxCi / G;
-    const int nrows = pl->nsci * ng, nseg = 3 * nrows;
-    cluster_info_kernel<<<blocks(pl->ncl, 32), 256, 0, s>>>(pl->ncl, c->n, pl->atom, pl->par, c->T.excl_start, c->T.excl_idx,
-                                                       pl->slot_of, pl->cl_info, pl->cl_tiles);
+    const int ub_nsci = pl->ub_nsci;
+    const int nrows = ub_nsci * ng, nseg = 3 * nrows;
+    cluster_info_kernel<<<blocks(pl->ncl_cap, 32), 256, 0, s>>>(d_nslot, c->n, pl->atom, pl->par, c->T.excl_start,
+                                                               c->T.excl_idx, pl->slot_of, pl->cl_info, pl->cl_tiles);
     const RowsIn in{G, c->n, pl->entries, pl->entry_jhit, pl->sci, pl->sci_off, pl->cl_info, pl->cl_tiles,
                     c->T.excl_start, c->T.excl_idx, pl->slot_of, pl->atom};
-    if (pl->nsci > 0) rows_kernel<false><<<pl->nsci, 32 * ng, 0, s>>>(in, pl->seg_total, nullptr, nullptr, nullptr, 0);
+    if (ub_nsci > 0) rows_kernel<false><<<ub_nsci, 32 * ng, 0, s>>>(in, d_nsci, pl->seg_total, nullptr, nullptr, nullptr, 0);
     PL_CUDA(cudaMemsetAsync(pl->seg_total + nseg, 0, sizeof(int), s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->seg_total, pl->seg_off, nseg + 1, s));
-    rows_units_count_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, pl->row_chunk, pl->seg_off, pl->row_nunits);
+    rows_units_count_kernel<<<blocks(nrows), 256, 0, s>>>(d_nsci, ub_nsci, ng, pl->row_chunk, pl->seg_off, pl->row_nunits);
     PL_CUDA(cudaMemsetAsync(pl->row_nunits + nrows, 0, sizeof(int), s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->row_nunits, pl->row_unit_off, nrows + 1, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[6], pl->seg_off + nseg, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[7], pl->row_unit_off + nrows, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PL_CUDA(cudaStreamSynchronize(s));
-    pl->njent = pl->h_counts[6];
-    pl->nrunits = pl->h_counts[7];
-    if ((size_t)pl->njent > pl->jent_cap) {
-        pl->jent_cap = (size_t)(pl->njent * 1.25) + 4096;
-        if (int rc = pl_realloc(pl, &pl->jent, pl->jent_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->jallow, pl->jent_cap)) return rc;
+    const int* d_njent = pl->seg_off + nseg;
+    const int* d_nunits = pl->row_unit_off + nrows;
+    if (sync) {
+        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[kCntJent], d_njent, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[kCntUnits], d_nunits, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        pl->njent = pl->h_counts[kCntJent];
+        pl->nrunits = pl->h_counts[kCntUnits];
+        if ((size_t)pl->njent > pl->jent_cap) {
+            pl->jent_cap = (size_t)(pl->njent * 1.25) + 4096;
+            if (int rc = pl_realloc(pl, &pl->jent, pl->jent_cap)) return rc;
+            if (int rc = pl_realloc(pl, &pl->jallow, pl->jent_cap)) return rc;
+        }
+        pl->ub_nrunits = sticky_bound(pl->ub_nrunits, pl->nrunits, 256, 1ll << 30);
+        if ((size_t)pl->ub_nrunits > pl->runits_cap) {
+            pl->runits_cap = (size_t)pl->ub_nrunits;
+            if (int rc = pl_realloc(pl, &pl->runits, pl->runits_cap)) return rc;
+            if (int rc = pl_realloc(pl, &pl->epart, pl->runits_cap)) return rc;
+            if (int rc = pl_realloc(pl, &pl->cpart, pl->runits_cap)) return rc;
+            if (int rc = pl_realloc(pl, &pl->ru_key, pl->runits_cap)) return rc;
+            if (int rc = pl_realloc(pl, &pl->ru_key_sorted, pl->runits_cap)) return rc;
+            if (int rc = pl_realloc(pl, &pl->ru_val, pl->runits_cap)) return rc;
+            if (int rc = pl_realloc(pl, &pl->ru_order, pl->runits_cap)) return rc;
+        }
     }
-    if ((size_t)pl->nrunits > pl->runits_cap) {
-        pl->runits_cap = (size_t)(pl->nrunits * 1.25) + 256;
-        if (int rc = pl_realloc(pl, &pl->runits, pl->runits_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->epart, pl->runits_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->cpart, pl->runits_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->ru_key, pl->runits_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->ru_key_sorted, pl->runits_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->ru_val, pl->runits_cap)) return rc;
-        if (int rc = pl_realloc(pl, &pl->ru_order, pl->runits_cap)) return rc;
-    }
-    if (pl->nsci > 0)
-        rows_kernel<true><<<pl->nsci, 32 * ng, 0, s>>>(in, nullptr, pl->seg_off, pl->jent, pl->jallow, (int)pl->jent_cap);
-    rows_units_fill_kernel<<<blocks(nrows), 256, 0, s>>>(pl->nsci, ng, G, pl->row_chunk, pl->sci, pl->seg_off,
+    if (!sync) pl->ub_nrunits = sticky_bound(pl->ub_nrunits, pl->nrunits, 256, (long long)pl->runits_cap);   // previous build's count
+    const int ub_nunits = (int)std::min<size_t>(pl->ub_nrunits, pl->runits_cap);
+    if (ub_nsci > 0)
+        rows_kernel<true><<<ub_nsci, 32 * ng, 0, s>>>(in, d_nsci, nullptr, pl->seg_off, pl->jent, pl->jallow, (int)pl->jent_cap);
+    rows_units_fill_kernel<<<blocks(nrows), 256, 0, s>>>(d_nsci, ng, G, pl->row_chunk, pl->sci, pl->seg_off,
                                                         pl->row_unit_off, pl->runits, (int)pl->runits_cap);
-    rows_part_off_kernel<<<blocks(c->R + 1), 256, 0, s>>>(pl->G, ng, pl->cell_sci, pl->row_unit_off, pl->nsci, pl->part_off);
-    if (pl->row_lpt && pl->nrunits > 0) {
-        rows_unit_key_kernel<<<blocks(pl->nrunits), 256, 0, s>>>(pl->nrunits, pl->runits, pl->ru_key, pl->ru_val);
+    rows_part_off_kernel<<<blocks(c->R + 1), 256, 0, s>>>(pl->G, ng, pl->cell_sci, pl->row_unit_off, d_nsci, pl->part_off);
+    if (pl->row_lpt && ub_nunits > 0) {
+        rows_unit_key_kernel<<<blocks(ub_nunits), 256, 0, s>>>(d_nunits, ub_nunits, (int)pl->runits_cap, pl->runits,
+                                                              pl->ru_key, pl->ru_val);
         size_t need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, pl->ru_key, pl->ru_key_sorted, pl->ru_val, pl->ru_order, pl->nrunits, 0, 6, s);
+        cub::DeviceRadixSort::SortPairs(nullptr, need, pl->ru_key, pl->ru_key_sorted, pl->ru_val, pl->ru_order, ub_nunits, 0, 7, s);
         if (need > pl->cub_tmp_bytes) {
+            if (!sync) return sdm_fail(SDM_ERR_CUDA, "internal: sort scratch too small for an asynchronous build");
             if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
             pl->cub_tmp_bytes = need;
         }
         PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->ru_key, pl->ru_key_sorted, pl->ru_val,
-                                                pl->ru_order, pl->nrunits, 0, 6, s));
+                                                pl->ru_order, ub_nunits, 0, 7, s));
         c->launches += 2;
     }
     c->launches += 7;
@@ -732,10 +867,43 @@ static int build_rows(sdm_ctx* c) {
 // ---------------------------------------------------------------------------------------------
 // build
 // ---------------------------------------------------------------------------------------------
+// Two ways through the same kernels.  sync: the host reads every count as soon as it exists and grows
+// the buffers that are too small (first build, non-periodic systems, after an overflow).  Otherwise the
+// whole build is enqueued without a single host synchronisation: the kernels read their counts from
+// device memory, the grids are sized with bounds derived from the previous build, finish_kernel checks
+// the bounds and capacities on the device (SDM_ERR_CAPACITY for every replica -> the caller repeats the
+// evaluation, which then builds synchronously), and the counts come back with one asynchronous copy
+// that the NEXT build looks at.
+static int read_back_counts(sdm_ctx* c) {
+    PairList* pl = c->pl;
+    if (!pl->counts_pending) return SDM_OK;
+    PL_CUDA(cudaEventSynchronize(pl->ev_counts));
+    pl->counts_pending = false;
+    const int* h = pl->h_counts;
+    pl->nslot = h[kCntSlot];
+    pl->ncl = pl->nslot / nbl::kClusterSize;
+    pl->nsci = h[kCntSci];
+    pl->nraw = h[kCntRaw];
+    pl->nentries = h[kCntEntries];
+    pl->njent = h[kCntJent];
+    pl->nrunits = h[kCntUnits];
+    pl->have_counts = h[kCntOverflow] == 0;
+    if (h[kCntOverflow]) pl->force_sync = true;
+    return SDM_OK;
+}
+
 static int build_list(sdm_ctx* c) {
     PairList* pl = c->pl;
     cudaStream_t s = c->stream;
     const int n = c->n, R = c->R, total = n * R;
+
+    if (int rc = read_back_counts(c)) return rc;
+    const bool sync = !pl->async_builds || pl->force_sync || !pl->have_counts || c->T.method != SDM_CUTOFF_PERIODIC;
+    pl->force_sync = false;
+    (sync ? pl->n_sync : pl->n_async)++;
+    // what the captured evaluation sequence depends on
+    const void* const view0[] = {pl->jent, pl->jallow, pl->runits, pl->ru_order, pl->epart, pl->cpart};
+    const int ub_units0 = pl->ub_nrunits;
 
     if (c->T.method != SDM_CUTOFF_PERIODIC) {
         minmax_kernel<<<1, 256, 0, s>>>(total, c->d_pos, pl->minmax);
@@ -779,35 +947,48 @@ static int build_list(sdm_ctx* c) {
     cell_sizes_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_first, pl->cell_count,
                                                     pl->cell_pcount, pl->cell_nsci);
     // kd refinement inside every cell: by y within the z halves, by x within the y halves
-    for (int level = 1; level <= 2; level++) {
-        refine_key_kernel<<<blocks(total), 256, 0, s>>>(G, level, total, c->d_pos, pl->keys_sorted, pl->vals_sorted,
-                                                       pl->cell_first, pl->cell_count, pl->keys, pl->vals);
-        PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->keys, pl->keys_sorted,
-                                                pl->vals, pl->vals_sorted, total, 0, key_end, s));
+    const int* vals_final = pl->vals_sorted;
+    if (pl->kd_in_block) {
+        kd_refine_kernel<<<ncells, 64, 0, s>>>(G, c->d_pos, pl->vals_sorted, pl->cell_first, pl->cell_count, pl->keys, pl->vals);
+        vals_final = pl->vals;   // the atoms only moved inside their cells: keys_sorted still names the cell
+        c->launches += 1;
+    } else {
+        for (int level = 1; level <= 2; level++) {
+            refine_key_kernel<<<blocks(total), 256, 0, s>>>(G, level, total, c->d_pos, pl->keys_sorted, pl->vals_sorted,
+                                                           pl->cell_first, pl->cell_count, pl->keys, pl->vals);
+            PL_CUDA(cub::DeviceRadixSort::SortPairs(pl->cub_tmp, pl->cub_tmp_bytes, pl->keys, pl->keys_sorted,
+                                                    pl->vals, pl->vals_sorted, total, 0, key_end, s));
+        }
+        c->launches += 4;
     }
-    c->launches += 4;
     // exclusive scans over ncells+1 elements (the extra zero element yields the totals)
     PL_CUDA(cudaMemsetAsync(pl->cell_pcount + ncells, 0, sizeof(int), s));
     PL_CUDA(cudaMemsetAsync(pl->cell_nsci + ncells, 0, sizeof(int), s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->cell_pcount, pl->cell_slot, ncells + 1, s));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->cell_nsci, pl->cell_sci, ncells + 1, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[0], pl->cell_slot + ncells, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[1], pl->cell_sci + ncells, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PL_CUDA(cudaStreamSynchronize(s));
-    pl->nslot = pl->h_counts[0];
-    pl->nsci = pl->h_counts[1];
+    // slots and superclusters cannot exceed their capacities (n atoms + < 8 padding slots per cell)
+    const int* d_nslot = pl->cell_slot + ncells;
+    const int* d_nsci = pl->cell_sci + ncells;
+    if (sync) {
+        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[kCntSlot], d_nslot, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[kCntSci], d_nsci, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        pl->nslot = pl->h_counts[kCntSlot];
+        pl->nsci = pl->h_counts[kCntSci];
+        pl->ncl = pl->nslot / nbl::kClusterSize;
+        if (pl->nslot > pl->nslot_cap || pl->nsci > pl->nsci_cap)
+            return sdm_fail(SDM_ERR_CAPACITY, "internal: slot capacity exceeded");
+    }
+    pl->ub_nsci = sticky_bound(pl->ub_nsci, pl->nsci, 16, pl->nsci_cap);   // asynchronous build: nsci of the previous one
     // a replica holds n atoms and at most 7 padding slots per cell
-    pl->scan_max = std::min(pl->nslot, n + 7 * G.ncell);
-    pl->ncl = pl->nslot / nbl::kClusterSize;
-    if (pl->nslot > pl->nslot_cap || pl->nsci > pl->nsci_cap)
-        return sdm_fail(SDM_ERR_CAPACITY, "internal: slot capacity exceeded");
+    pl->scan_max = std::min(pl->nslot_cap, n + 7 * G.ncell);
 
-    fill_slots_kernel<<<blocks(total), 256, 0, s>>>(G, c->T, total, c->d_pos, pl->keys_sorted, pl->vals_sorted,
+    fill_slots_kernel<<<blocks(total), 256, 0, s>>>(G, c->T, total, c->d_pos, pl->keys_sorted, vals_final,
                                                    pl->cell_first, pl->cell_slot, pl->posq, pl->par,
                                                    pl->atom, pl->img, pl->slot_of);
     fill_dummies_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_count, pl->cell_slot, pl->posq,
                                                       pl->par, pl->atom, pl->img);
-    bbox_kernel<<<blocks(pl->ncl), 256, 0, s>>>(pl->ncl, pl->posq, pl->cl_box);
+    bbox_kernel<<<blocks(pl->ncl_cap), 256, 0, s>>>(d_nslot, pl->posq, pl->cl_box);
     sci_kernel<<<blocks(ncells), 256, 0, s>>>(G, ncells, pl->cell_slot, pl->cell_sci, pl->cl_box, pl->sci,
                                              pl->sci_box, pl->cl_sci);
     if (G.columns) cell_box_kernel<<<blocks(ncells), 256, 0, s>>>(ncells, pl->cell_slot, pl->cl_box, pl->cell_box);
@@ -821,18 +1002,20 @@ static int build_list(sdm_ctx* c) {
     V.cell_slot = pl->cell_slot;
     V.cell_box = pl->cell_box;
     V.posq4 = reinterpret_cast<const float*>(pl->posq);
-    const long long nitems = (long long)pl->nsci * noff;
+    const long long nitems = (long long)pl->ub_nsci * noff;
     if ((size_t)nitems + 1 > pl->items_cap) {
+        if (!sync) return sdm_fail(SDM_ERR_CUDA, "internal: item capacity changed under an asynchronous build");
         pl->items_cap = (size_t)nitems + 1;
         if (int rc = pl_realloc(pl, &pl->item_count, pl->items_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->item_off, pl->items_cap)) return rc;
     }
-    search_count_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_count);
+    search_count_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, d_nsci, (int)nitems, noff, pl->item_count);
     PL_CUDA(cudaMemsetAsync(pl->item_count + nitems, 0, sizeof(int), s));
     auto ensure_cub = [&](size_t count) -> int {
         size_t need = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, need, pl->item_count, pl->item_off, (int)count, s);
         if (need > pl->cub_tmp_bytes) {
+            if (!sync) return sdm_fail(SDM_ERR_CUDA, "internal: scan scratch too small for an asynchronous build");
             if (int rc = pl_realloc(pl, (char**)&pl->cub_tmp, need)) return rc;
             pl->cub_tmp_bytes = need;
         }
@@ -840,62 +1023,67 @@ static int build_list(sdm_ctx* c) {
     };
     if (int rc = ensure_cub((size_t)nitems + 1)) return rc;
     PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->item_count, pl->item_off, (int)nitems + 1, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[2], pl->item_off + nitems, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PL_CUDA(cudaStreamSynchronize(s));
-    pl->nraw = pl->h_counts[2];
-    if ((size_t)pl->nraw > pl->raw_cap) {
-        pl->raw_cap = (size_t)(pl->nraw * 1.25) + 1024;
+    const int* d_nraw = pl->item_off + nitems;
+    if (sync) {
+        PL_CUDA(cudaMemcpyAsync(&pl->h_counts[kCntRaw], d_nraw, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        pl->nraw = pl->h_counts[kCntRaw];
+    }
+    pl->ub_nraw = sticky_bound(pl->ub_nraw, pl->nraw, 1024, 1ll << 30);
+    if (sync && (size_t)pl->ub_nraw + 1 > pl->raw_cap) {
+        // the pruned entries are a subset of the raw ones: one capacity for both
+        pl->raw_cap = (size_t)pl->ub_nraw + 1;
         if (int rc = pl_realloc(pl, &pl->raw_entries, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_sci, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_c0nci, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_jhit, pl->raw_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_keep, pl->raw_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->raw_pos, pl->raw_cap + 1)) return rc;
-    }
-    const int nraw = pl->nraw;
-    search_fill_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, pl->nsci, noff, pl->item_off, pl->raw_entries,
-                                                          pl->raw_sci, pl->raw_c0nci, (int)pl->raw_cap);
-    // exact prune (one warp per raw entry), then order-preserving compaction
-    if (nraw > 0)
-        prune_kernel<<<blocks((long long)nraw * 32, 128), 128, 0, s>>>(G, nraw, pl->raw_entries, pl->raw_c0nci,
-                                                                      pl->posq, pl->raw_keep, pl->raw_jhit);
-    PL_CUDA(cudaMemsetAsync(pl->raw_keep + nraw, 0, sizeof(int), s));
-    if (int rc = ensure_cub((size_t)nraw + 1)) return rc;
-    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->raw_keep, pl->raw_pos, nraw + 1, s));
-    PL_CUDA(cudaMemcpyAsync(&pl->h_counts[5], pl->raw_pos + nraw, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PL_CUDA(cudaStreamSynchronize(s));
-    pl->nentries = pl->h_counts[5];
-    if ((size_t)pl->nentries > pl->entries_cap) {
-        pl->entries_cap = (size_t)(pl->nentries * 1.25) + 1024;
+        pl->entries_cap = pl->raw_cap;
         if (int rc = pl_realloc(pl, &pl->entries, pl->entries_cap)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_sci, pl->entries_cap + 1)) return rc;
         if (int rc = pl_realloc(pl, &pl->entry_jhit, pl->entries_cap + 1)) return rc;
     }
-    if (nraw > 0)
-        compact_kernel<<<blocks(nraw), 256, 0, s>>>(nraw, pl->raw_entries, pl->raw_sci, pl->raw_keep,
-                                                   pl->raw_pos, pl->entries, pl->entry_sci,
-                                                   (int)pl->entries_cap, pl->raw_jhit, pl->entry_jhit);
-    sci_off_kernel<<<blocks(pl->nsci + 1), 256, 0, s>>>(pl->nsci, noff, nraw, pl->item_off, pl->raw_pos, pl->sci_off);
+    const int ub_nraw = (int)std::min<size_t>(pl->ub_nraw, pl->raw_cap - 1);
+    search_fill_kernel<<<blocks(nitems, 128), 128, 0, s>>>(V, d_nsci, noff, pl->item_off, pl->raw_entries,
+                                                          pl->raw_sci, pl->raw_c0nci, (int)pl->raw_cap);
+    // exact prune (one warp per raw entry), then order-preserving compaction
+    prune_kernel<<<blocks(((long long)ub_nraw + 1) * 32, 128), 128, 0, s>>>(G, d_nraw, ub_nraw, (int)pl->raw_cap,
+                                                                          pl->raw_entries, pl->raw_c0nci, pl->posq,
+                                                                          pl->raw_keep, pl->raw_jhit);
+    if (int rc = ensure_cub((size_t)ub_nraw + 1)) return rc;
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(pl->cub_tmp, pl->cub_tmp_bytes, pl->raw_keep, pl->raw_pos, ub_nraw + 1, s));
+    const int* d_nent = pl->raw_pos + ub_nraw;
+    compact_kernel<<<blocks(ub_nraw), 256, 0, s>>>(d_nraw, (int)pl->raw_cap, pl->raw_entries, pl->raw_sci, pl->raw_keep,
+                                                  pl->raw_pos, pl->entries, pl->entry_sci, (int)pl->entries_cap,
+                                                  pl->raw_jhit, pl->entry_jhit);
+    sci_off_kernel<<<blocks(pl->ub_nsci + 1), 256, 0, s>>>(d_nsci, noff, d_nraw, ub_nraw, pl->item_off, pl->raw_pos, pl->sci_off);
     c->launches += 7;
 
     // the rows the pair kernel walks: individual j-atoms per i-group, exclusions and triangle as
     // allow words, Lennard-Jones-free j-atoms last
-    if (int rc = build_rows(c)) return rc;
-    PL_CUDA(cudaMemcpyAsync(pl->posq_build, pl->posq, sizeof(float4) * (size_t)pl->nslot, cudaMemcpyDeviceToDevice, s));
-    c->launches += 7;
-    PL_CUDA(cudaGetLastError());
-
+    if (int rc = build_rows(c, sync, d_nslot, d_nsci)) return rc;
+    PL_CUDA(cudaMemcpyAsync(pl->posq_build, pl->posq, sizeof(float4) * (size_t)pl->nslot_cap, cudaMemcpyDeviceToDevice, s));
     // the fixed-point accumulators are indexed by slot: start from zero for the new layout
     PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
-    {
-        static const int one = 1;   // this evaluation is the first one with the new list
-        PL_CUDA(cudaMemcpyAsync(c->d_list_age, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    const int G_ = pl->row_group, ng = nbl::kMaxCi / G_;
+    finish_kernel<<<1, 32, 0, s>>>(d_nslot, d_nsci, pl->ub_nsci, d_nraw, d_nent, pl->seg_off + 3 * pl->ub_nsci * ng,
+                                  pl->row_unit_off + pl->ub_nsci * ng, (int)pl->raw_cap, ub_nraw, (int)pl->entries_cap,
+                                  (int)std::min<size_t>(pl->jent_cap, 0x7fffffff), (int)pl->runits_cap,
+                                  (int)std::min<size_t>(pl->ub_nrunits, pl->runits_cap), R, c->B.flags, pl->d_cnt,
+                                  c->d_list_age, pl->max_disp2);
+    PL_CUDA(cudaMemcpyAsync(pl->h_counts, pl->d_cnt, kCntN * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaEventRecord(pl->ev_counts, s));
+    pl->counts_pending = true;
+    c->launches += 8;
+    PL_CUDA(cudaGetLastError());
+    {   // buffers or the pair kernel's grid bound moved: the evaluation graph is captured again
+        const void* const view1[] = {pl->jent, pl->jallow, pl->runits, pl->ru_order, pl->epart, pl->cpart};
+        if (memcmp(view0, view1, sizeof(view0)) != 0 || ub_units0 != pl->ub_nrunits) c->graph_valid = false;
     }
-    PL_CUDA(cudaMemsetAsync(pl->max_disp2, 0, sizeof(unsigned int), s));
     c->list_valid = true;
     c->list_age = 0;
     c->n_builds++;
-    c->graph_valid = false;   // list arrays may have moved
     return SDM_OK;
 }
 
@@ -967,10 +1155,11 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->item_count, pl->items_cap));
     A(pl_alloc(pl, &pl->item_off, pl->items_cap));
     // initial guesses; grown on demand at build time
-    pl->entries_cap = (size_t)total * 8 + 1024;
+    // the pruned entries are a subset of the raw ones: one capacity for both
+    pl->entries_cap = (size_t)total * 12 + 1024;
     A(pl_alloc(pl, &pl->entries, pl->entries_cap));
     A(pl_alloc(pl, &pl->entry_sci, pl->entries_cap + 1));
-    pl->raw_cap = pl->entries_cap * 2;
+    pl->raw_cap = pl->entries_cap;
     A(pl_alloc(pl, &pl->raw_entries, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_sci, pl->raw_cap));
     A(pl_alloc(pl, &pl->raw_c0nci, pl->raw_cap));
@@ -1010,7 +1199,12 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
         pl->cub_tmp_bytes = std::max(a, b) + 256;
         A(pl_alloc(pl, (char**)&pl->cub_tmp, pl->cub_tmp_bytes));
     }
-    PL_CUDA(cudaMallocHost((void**)&pl->h_counts, 8 * sizeof(int)));
+    PL_CUDA(cudaMallocHost((void**)&pl->h_counts, kCntN * sizeof(int)));
+    memset(pl->h_counts, 0, kCntN * sizeof(int));
+    A(pl_alloc(pl, &pl->d_cnt, kCntN));
+    PL_CUDA(cudaEventCreateWithFlags(&pl->ev_counts, cudaEventDisableTiming));
+    if (const char* e = getenv("SDMB200_KD_SORTS")) pl->kd_in_block = atoi(e) == 0;
+    if (const char* e = getenv("SDMB200_ASYNC_BUILD")) pl->async_builds = atoi(e) != 0;   // development knob
     PL_CUDA(cudaMallocHost((void**)&pl->h_minmax, 6 * sizeof(double)));
     // the accumulators live in the global slot space for this path
     {
@@ -1030,6 +1224,7 @@ void sdm_ctx_free_pairlist(sdm_ctx* c) {
     if (!c->pl) return;
     for (void* p : c->pl->allocs) cudaFree(p);
     if (c->pl->h_counts) cudaFreeHost(c->pl->h_counts);
+    if (c->pl->ev_counts) cudaEventDestroy(c->pl->ev_counts);
     if (c->pl->h_minmax) cudaFreeHost(c->pl->h_minmax);
     delete c->pl;
     c->pl = nullptr;
@@ -1047,7 +1242,8 @@ static PairListView make_view(const sdm_ctx* c) {
     V.jallow = pl->jallow;
     V.runits = pl->runits;
     V.runit_order = pl->row_lpt ? pl->ru_order : nullptr;
-    V.nrunits = pl->nrunits;
+    V.nrunits = pl->d_cnt + kCntUnitsLaunch;
+    V.nrunits_ub = (int)std::min<size_t>(pl->ub_nrunits, pl->runits_cap);
     V.row_group = pl->row_group;
     V.dummy_slot = pl->dummy_slot;
     return V;
@@ -1066,7 +1262,7 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
         if (int rc = build_list(c)) return rc;
     } else {
         const float hs = 0.5f * (float)c->opt.skin;
-        launch_refresh(c->T, pl->G, pl->nslot, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq,
+        launch_refresh(c->T, pl->G, pl->d_cnt + kCntSlot, pl->nslot_cap, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq,
                        hs * hs, c->B.flags, c->d_list_age, pl->max_disp2, s);
         c->launches++;
         // fresh state-1 accumulators (one 8 MB memset is cheaper than scattered stores in the mix kernel)
@@ -1112,10 +1308,19 @@ int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs,
     return SDM_OK;
 }
 
+// After the host has seen SDM_ERR_CAPACITY: was it the last list build that ran out of room (its bounds
+// or buffers)?  Then the next build sizes itself step by step on the host.
+bool sdm_ctx_pairlist_overflowed(sdm_ctx* c) {
+    if (!c->pl) return false;
+    if (read_back_counts(c)) return false;
+    return c->pl->force_sync;
+}
+
 unsigned int* sdm_ctx_pairlist_max_disp_ptr(sdm_ctx* c) { return c->pl ? c->pl->max_disp2 : nullptr; }
 
 int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     if (!c->pl) return SDM_ERR_INVALID;
+    if (int rc = read_back_counts(c)) return rc;
     const PairList* pl = c->pl;
     std::string k(key);
     if (k == "n_slots") *value = pl->nslot;
@@ -1131,6 +1336,8 @@ int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "layout_columns") *value = pl->G.columns;
     else if (k == "chunk_cells_per_column") *value = pl->G.kz;
     else if (k == "rlist") *value = pl->G.rlist;
+    else if (k == "n_async_builds") *value = (double)pl->n_async;
+    else if (k == "n_sync_builds") *value = (double)pl->n_sync;
     else return SDM_ERR_INVALID;
     return SDM_OK;
 }

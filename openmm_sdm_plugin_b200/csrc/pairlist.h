@@ -29,7 +29,8 @@ struct PairListView {
     const uint16_t* jallow;      // allow word per row entry (read for the masked prefix of a row only)
     const RowUnit* runits;       // [nrunits]
     const int* runit_order;      // [nrunits] the order in which the warps draw the units (longest first), or nullptr
-    int nrunits;
+    const int* nrunits;          // device word: units of the current list (0 when its build overflowed)
+    int nrunits_ub;              // host-side upper bound (grid sizing)
     int row_group;               // clusters per i-group (1 or 2)
     int dummy_slot;              // a slot that holds a far-away dummy atom (padding lanes)
 };
@@ -50,7 +51,7 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
 // Per-eval refresh of the sorted positions from the current double positions (same periodic
 // image as at build time) + staleness check against the build-time positions; max_disp2 (may be
 // null) receives the largest squared displacement since the build, as float bits.
-void launch_refresh(const Topology& T, const nbl::Grid& G, int nslot, const double* pos_all,
+void launch_refresh(const Topology& T, const nbl::Grid& G, const int* d_nslot, int nslot_ub, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq,
                     float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s);
 

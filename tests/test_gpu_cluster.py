@@ -172,3 +172,76 @@ def test_auto_mode_picks_cluster_for_large_and_allpairs_for_small(cfg2):
         assert ctx.info("pair_mode") == CL
     with SDMContext(S.cfg1().system, None) as ctx:
         assert ctx.info("pair_mode") == _lib.PAIR_ALLPAIRS
+
+
+def _drift_run(case, env_async, monkeypatch, n_evals=9, nstlist=3):
+    """Forces / scalars of n_evals evaluations under drifting positions, list rebuilt every nstlist."""
+    monkeypatch.setenv("SDMB200_ASYNC_BUILD", env_async)
+    rng = np.random.default_rng(77)
+    out = []
+    with SDMContext(case.system, case.displacement, pair_mode=CL, nstlist=nstlist, skin=0.08) as ctx:
+        ctx.set_alchemical(0, case.alch)
+        pos = case.positions.copy()
+        for _ in range(n_evals):
+            ctx.set_positions(0, pos)
+            ctx.eval()
+            sc = ctx.scalars(0)
+            assert sc["status"] == 0, sc
+            out.append((ctx.forces(0).copy(), sc["E1"], sc["u"], sc["n_pairs1"]))
+            pos = pos + rng.normal(scale=0.002, size=pos.shape)
+        counts = (ctx.info("n_list_builds"), ctx.info("n_async_builds"), ctx.info("n_sync_builds"))
+    return out, counts, pos
+
+
+def test_asynchronous_list_builds_match_synchronous_ones(cfg2, monkeypatch):
+    """Builds after the first are enqueued without host synchronisation (counts stay on the device, grids
+    sized with bounds from the previous build): same bits as builds that size every stage on the host."""
+    case, _ = cfg2
+    a, ca, _ = _drift_run(case, "1", monkeypatch)
+    b, cb, _ = _drift_run(case, "0", monkeypatch)
+    assert ca == (3, 2, 1) and cb == (3, 0, 3), (ca, cb)
+    for (fa, e1a, ua, na), (fb, e1b, ub, nb) in zip(a, b):
+        assert na == nb and e1a == e1b and ua == ub
+        assert np.array_equal(fa, fb)
+
+
+def test_asynchronous_build_that_outgrows_its_bounds_is_reported_and_repaired(monkeypatch):
+    """A frame much denser than the one the bounds came from: the build notices on the device, every replica
+    reports SDM_ERR_CAPACITY, and the repeated evaluation (sized on the host) is correct."""
+    monkeypatch.setenv("SDMB200_ASYNC_BUILD", "1")
+    case = S.synthetic_case(6000, 30, seed=11, protein_atoms=300, displacement=(0.0, 0.0, 1.5))
+    dense = case.positions.copy()
+    L = case.system.box
+    dense[:, 0] = dense[:, 0] % L[0] * 0.5            # everything squeezed into half of the box
+    with SDMContext(case.system, case.displacement, pair_mode=CL, nstlist=1, skin=0.08) as ctx:
+        ctx.set_alchemical(0, case.alch)
+        ctx.set_positions(0, case.positions)
+        ctx.eval()
+        assert ctx.scalars(0)["status"] == 0
+        ctx.eval()                                     # an asynchronous build with the first frame's counts
+        assert ctx.scalars(0)["status"] == 0 and ctx.info("n_async_builds") == 1
+        ctx.set_positions(0, dense)
+        ctx.eval()
+        first = ctx.scalars(0)["status"]
+        tries = 0
+        while ctx.scalars(0)["status"] == _lib.SDM_ERR_CAPACITY and tries < 4:
+            ctx.eval()
+            tries += 1
+        sc = ctx.scalars(0)
+        assert sc["status"] == 0
+        assert first == _lib.SDM_ERR_CAPACITY, "the scenario did not outgrow the bounds"
+        ref = oracle_eval(case, dense)
+        assert sc["n_pairs1"] == ref["n_pairs1"]   # (energies of a squeezed box overflow FP32: not compared)
+
+
+def test_in_block_kd_refinement_gives_the_order_of_the_sort_based_rounds(cfg2, monkeypatch):
+    """The two kd refinement rounds of the list build run as one kernel (ranks counted inside each cell);
+    the development knob SDMB200_KD_SORTS=1 runs them as two global radix sorts: same slots, same bits."""
+    case, _ = cfg2
+    monkeypatch.setenv("SDMB200_KD_SORTS", "0")
+    a, _, _ = _drift_run(case, "1", monkeypatch, n_evals=4, nstlist=2)
+    monkeypatch.setenv("SDMB200_KD_SORTS", "1")
+    b, _, _ = _drift_run(case, "1", monkeypatch, n_evals=4, nstlist=2)
+    for (fa, e1a, ua, na), (fb, e1b, ub, nb) in zip(a, b):
+        assert na == nb and e1a == e1b and ua == ub
+        assert np.array_equal(fa, fb)

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--replicas", type=int, default=16)
 ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--dt", type=float, default=0.001)
+ap.add_argument("--free-solute", action="store_true", help="let the solute move under nonbonded forces alone (no bonded terms)")
 ap.add_argument("--grid", default="0.06:20,0.08:20,0.10:20,0.10:40,0.12:40,0.14:40,0.16:80")
 a = ap.parse_args()
 case, _ = bench.load_case("cfg2")
@@ -26,6 +27,7 @@ flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 states = S.atm_lambda_schedule(22)
 for item in a.grid.split(","):
     skin, nst = item.split(":")
-    r = bench.md_leg(case, a.replicas, args, 0, stream, flush, states, 0, skin=float(skin), nstlist=int(nst), steps=a.steps, dt=a.dt)
+    r = bench.md_leg(case, a.replicas, args, 0, stream, flush, states, 0, skin=float(skin), nstlist=int(nst), steps=a.steps, dt=a.dt,
+                      freeze_solute=not a.free_solute)
     print(json.dumps({k: r[k] for k in ("skin_nm", "nstlist", "dt_ps", "ms_per_step", "ns_per_day_per_replica", "list_builds",
-                                        "steps_repeated_stale_list", "kinetic_temperature_K", "status_ok")}))
+                                        "steps_repeated_stale_list", "kinetic_temperature_K", "frozen_solute_atoms", "status_ok")}))
