@@ -47,6 +47,15 @@
 namespace sdm {
 namespace {
 
+#ifndef SDM_ROW_ROTATE_LATE
+#define SDM_ROW_ROTATE_LATE 1
+#endif
+#ifndef SDM_ROW_LDG256
+#define SDM_ROW_LDG256 1      // the 32-byte j record with one 256-bit load (sm_100: LDG.E.256)
+#endif
+#ifndef SDM_ROW_SHIFT_VOTE
+#define SDM_ROW_SHIFT_VOTE 1
+#endif
 #ifndef SDM_PAIR_WARPS
 #define SDM_PAIR_WARPS 1
 #endif
@@ -93,6 +102,20 @@ __device__ __forceinline__ f2 sel2_or_zero(const f2 v, const bool c_lo, const bo
         " setp.ne.s32 q, %3, 0;\n selp.f32 a, a, 0f00000000, p;\n selp.f32 b, b, 0f00000000, q;\n"
         " mov.b64 %0, {a, b};\n}" : "=l"(r) : "l"(v), "r"((int)c_lo), "r"((int)c_hi));
     return r;
+}
+
+// The 32-byte record of a slot (position + charge, sigma/2, 2*sqrt(eps)): two 128-bit loads from one sector.
+__device__ __forceinline__ void load_jrec(const float4* __restrict__ jrec, const uint32_t slot, float4& xj, float2& pj) {
+    const float4* r = jrec + 2 * (size_t)slot;
+#if SDM_ROW_LDG256
+    float u0, u1;   // padding words of the record
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(xj.x), "=f"(xj.y), "=f"(xj.z), "=f"(xj.w), "=f"(pj.x), "=f"(pj.y), "=f"(u0), "=f"(u1) : "l"(r));
+#else
+    xj = r[0];
+    const float4 p = r[1];
+    pj = make_float2(p.x, p.y);
+#endif
 }
 
 struct PairConsts {
@@ -310,15 +333,18 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
         float4 q = make_float4(-nbl::kFar, -nbl::kFar, -nbl::kFar, 0.f);
         float2 pr = make_float2(0.f, 0.f);
         if (lane < ni) {
-            const float4 g = V.posq[ibase + lane];
-            if (g.x < 0.5f * nbl::kFar) { q = g; pr = V.par[ibase + lane]; }
+            float4 g;
+            float2 gp;
+            load_jrec(V.jrec, (uint32_t)(ibase + lane), g, gp);
+            if (g.x < 0.5f * nbl::kFar) { q = g; pr = gp; }
         }
         float* dst = reinterpret_cast<float*>(s_ip + (lane >> 1)) + (lane & 1);
         dst[0] = q.x; dst[2] = q.y; dst[4] = q.z; dst[6] = q.w; dst[8] = pr.x; dst[10] = pr.y;
     }
 #if SDM_ROW_JPREFETCH
-    float4 xj1 = V.posq[ent1 & 0x3ffffffu];
-    float2 pj1 = V.par[ent1 & 0x3ffffffu];
+    float4 xj1;
+    float2 pj1;
+    load_jrec(V.jrec, ent1 & 0x3ffffffu, xj1, pj1);
 #endif
     __syncwarp();
 
@@ -337,18 +363,33 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
         const float2 pj = pj1;
         ent1 = ent2;
         ent2 = idx + 64 < u.end ? V.jent[idx + 64] : dummy_ent;
-        xj1 = V.posq[ent1 & 0x3ffffffu];
-        pj1 = V.par[ent1 & 0x3ffffffu];
+#if SDM_ROW_ROTATE_LATE
+        // the next step's record lands in its own registers and is handed over at the END of this step
+        // (volatile moves after the REDs): left to itself the compiler copies the landing registers into
+        // the loop-carried ones right after issuing the load and waits for it there -- no prefetch at all
+        float4 xjn;
+        float2 pjn;
+        load_jrec(V.jrec, ent1 & 0x3ffffffu, xjn, pjn);
 #else
-        float4 xj = V.posq[ent & 0x3ffffffu];
-        const float2 pj = V.par[ent & 0x3ffffffu];
+        load_jrec(V.jrec, ent1 & 0x3ffffffu, xj1, pj1);
+#endif
+#else
+        float4 xj;
+        float2 pj;
+        load_jrec(V.jrec, ent & 0x3ffffffu, xj, pj);
         ent1 = ent2;
         ent2 = idx + 64 < u.end ? V.jent[idx + 64] : dummy_ent;
 #endif
         const int jslot = (int)(ent & 0x3ffffffu);
         if (PERIODIC) {
-            const float4 sh = s_shift[ent >> 26];
-            xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
+#if SDM_ROW_SHIFT_VOTE
+            // most steps hold central-image atoms only: one vote instead of the table look-up
+            if (__any_sync(0xffffffffu, (ent >> 26) != nbl::kShiftZero))
+#endif
+            {
+                const float4 sh = s_shift[ent >> 26];
+                xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
+            }
         }
         Acc2 fj{0ull, 0ull, 0ull};
         float tmin = 3.0e38f;
@@ -379,6 +420,11 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
         red_fixed_nonzero(fjp, lo(fj.x) + hi(fj.x), -kFix);
         red_fixed_nonzero(fjp + plane, lo(fj.y) + hi(fj.y), -kFix);
         red_fixed_nonzero(fjp + 2 * plane, lo(fj.z) + hi(fj.z), -kFix);
+#if SDM_ROW_JPREFETCH && SDM_ROW_ROTATE_LATE
+        asm volatile("mov.b32 %0, %6;\n mov.b32 %1, %7;\n mov.b32 %2, %8;\n mov.b32 %3, %9;\n mov.b32 %4, %10;\n mov.b32 %5, %11;"
+                     : "=f"(xj1.x), "=f"(xj1.y), "=f"(xj1.z), "=f"(xj1.w), "=f"(pj1.x), "=f"(pj1.y)
+                     : "f"(xjn.x), "f"(xjn.y), "f"(xjn.z), "f"(xjn.w), "f"(pjn.x), "f"(pjn.y));
+#endif
     }
 
     // i forces: v[3*a + d] of atom a, summed over the lanes
@@ -447,13 +493,15 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
             const int id = u.begin + 32 * k + lane;
             const uint32_t fe = V.jent[id];
             const int js = (int)(fe & 0x3ffffffu);
-            float4 xj = V.posq[js];
+            float4 xj;
+            float2 pjf;
+            load_jrec(V.jrec, (uint32_t)js, xj, pjf);
             if (PERIODIC) {
                 const float4 sh = s_shift[fe >> 26];
                 xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
             }
             const uint32_t allow = id < mend ? (uint32_t)V.jallow[id] : 0xffffu;
-            fix_band_row<NI, EMIT>(T, V, pos_all, f1acc, s_ip, ibase, js, xj, V.par[js], allow, &en_fix, &cnt_fix, ec);
+            fix_band_row<NI, EMIT>(T, V, pos_all, f1acc, s_ip, ibase, js, xj, pjf, allow, &en_fix, &cnt_fix, ec);
         }
         en1 += en_fix;
         cnt += cnt_fix;
@@ -518,8 +566,8 @@ pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ Pair
 __global__ void __launch_bounds__(256)
 refresh_kernel(Topology T, nbl::Grid G, const int* __restrict__ d_nslot, const double* __restrict__ pos_all,
                const int* __restrict__ atom, const int* __restrict__ img,
-               const float4* __restrict__ posq_build, float4* __restrict__ posq, float half_skin2,
-               int* flags, int* list_age, unsigned int* max_disp2) {
+               const float4* __restrict__ posq_build, float4* __restrict__ posq, float4* __restrict__ jrec,
+               float half_skin2, int* flags, int* list_age, unsigned int* max_disp2) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) *list_age += 1;   // one more evaluation with this list (read by the scalar stage)
     float d2 = 0.f;
@@ -541,6 +589,7 @@ refresh_kernel(Topology T, nbl::Grid G, const int* __restrict__ d_nslot, const d
         d2 = dx * dx + dy * dy + dz * dz;
         if (d2 > half_skin2) atomicExch(flags + r, SDM_ERR_STALE_LIST);
         posq[s] = make_float4(fx, fy, fz, b.w);
+        jrec[2 * (size_t)s] = make_float4(fx, fy, fz, b.w);
     }
     // largest squared displacement since the list was built, over all replicas: the host plans the
     // next rebuild from its growth (non-negative floats order like their bit patterns)
@@ -594,11 +643,11 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
 }
 
 void launch_refresh(const Topology& T, const nbl::Grid& G, const int* d_nslot, int nslot_ub, const double* pos_all,
-                    const int* atom, const int* img, const float4* posq_build, float4* posq,
+                    const int* atom, const int* img, const float4* posq_build, float4* posq, float4* jrec,
                     float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s) {
     if (nslot_ub <= 0) return;
     refresh_kernel<<<(nslot_ub + 255) / 256, 256, 0, s>>>(T, G, d_nslot, pos_all, atom, img, posq_build,
-                                                      posq, half_skin2, flags, list_age, max_disp2);
+                                                      posq, jrec, half_skin2, flags, list_age, max_disp2);
 }
 
 }  // namespace sdm

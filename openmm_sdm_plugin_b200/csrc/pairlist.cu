@@ -34,6 +34,7 @@ struct PairList {
     int *cell_first = nullptr, *cell_count = nullptr, *cell_pcount = nullptr, *cell_nsci = nullptr;
     int *cell_slot = nullptr, *cell_sci = nullptr;
     float4 *posq = nullptr, *posq_build = nullptr;
+    float4* jrec = nullptr;     // [nslot][2] (posq, par) side by side: the pair kernel's gather record
     float2* par = nullptr;
     int *atom = nullptr, *img = nullptr, *slot_of = nullptr;
     BBox *cl_box = nullptr, *sci_box = nullptr, *cell_box = nullptr;
@@ -712,6 +713,19 @@ __global__ void rows_part_off_kernel(Grid G, int ng, const int* __restrict__ cel
     part_off[r] = row_unit_off[(size_t)s * ng];
 }
 
+// End of a build: the build-time positions the refresh kernel measures displacements against, and the
+// 32-byte gather records of the pair kernel.
+__global__ void snapshot_kernel(int nslot_cap, const float4* __restrict__ posq, const float2* __restrict__ par,
+                                float4* __restrict__ posq_build, float4* __restrict__ jrec) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslot_cap) return;
+    const float4 p = posq[s];
+    const float2 q = par[s];
+    posq_build[s] = p;
+    jrec[2 * (size_t)s] = p;
+    jrec[2 * (size_t)s + 1] = make_float4(q.x, q.y, 0.f, 0.f);
+}
+
 __global__ void dummy_slot_kernel(int slot, float4* posq, float4* posq_build, float2* par, int* atom, int* img) {
     posq[slot] = posq_build[slot] = make_float4(nbl::kFar, nbl::kFar, nbl::kFar, 0.f);
     par[slot] = make_float2(0.f, 0.f);
@@ -1063,7 +1077,7 @@ static int build_list(sdm_ctx* c) {
     // the rows the pair kernel walks: individual j-atoms per i-group, exclusions and triangle as
     // allow words, Lennard-Jones-free j-atoms last
     if (int rc = build_rows(c, sync, d_nslot, d_nsci)) return rc;
-    PL_CUDA(cudaMemcpyAsync(pl->posq_build, pl->posq, sizeof(float4) * (size_t)pl->nslot_cap, cudaMemcpyDeviceToDevice, s));
+    snapshot_kernel<<<blocks(pl->nslot_cap), 256, 0, s>>>(pl->nslot_cap, pl->posq, pl->par, pl->posq_build, pl->jrec);
     // the fixed-point accumulators are indexed by slot: start from zero for the new layout
     PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
     const int G_ = pl->row_group, ng = nbl::kMaxCi / G_;
@@ -1137,6 +1151,7 @@ int sdm_ctx_init_pairlist(sdm_ctx* c) {
     A(pl_alloc(pl, &pl->posq, pl->nslot_cap));
     A(pl_alloc(pl, &pl->posq_build, pl->nslot_cap));
     A(pl_alloc(pl, &pl->par, pl->nslot_cap));
+    A(pl_alloc(pl, &pl->jrec, 2 * (size_t)pl->nslot_cap));
     A(pl_alloc(pl, &pl->atom, pl->nslot_cap));
     A(pl_alloc(pl, &pl->img, pl->nslot_cap));
     A(pl_alloc(pl, &pl->slot_of, total));
@@ -1236,6 +1251,7 @@ static PairListView make_view(const sdm_ctx* c) {
     V.G = pl->G;
     V.posq = pl->posq;
     V.par = pl->par;
+    V.jrec = pl->jrec;
     V.atom = pl->atom;
     V.nslot_cap = pl->nslot_cap;
     V.jent = pl->jent;
@@ -1262,7 +1278,7 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
         if (int rc = build_list(c)) return rc;
     } else {
         const float hs = 0.5f * (float)c->opt.skin;
-        launch_refresh(c->T, pl->G, pl->d_cnt + kCntSlot, pl->nslot_cap, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq,
+        launch_refresh(c->T, pl->G, pl->d_cnt + kCntSlot, pl->nslot_cap, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq, pl->jrec,
                        hs * hs, c->B.flags, c->d_list_age, pl->max_disp2, s);
         c->launches++;
         // fresh state-1 accumulators (one 8 MB memset is cheaper than scattered stores in the mix kernel)

@@ -22,6 +22,8 @@ struct PairListView {
     nbl::Grid G;
     const float4* posq;          // [nslot] sorted, wrapped (+ image) positions, .w = q*sqrt(K)
     const float2* par;           // [nslot] (sigma/2, 2*sqrt(eps)); (0,0) for dummies
+    const float4* jrec;          // [nslot][2] the same two records side by side (32 bytes = one sector per atom):
+                                 // what the pair kernel gathers, one address and one sector per j-atom
     const int* atom;             // [nslot] replica*n + atom, or -1 for a dummy slot
     int nslot_cap;               // accumulator plane stride
     // per-atom j rows (nblist_core.h stage 5)
@@ -52,7 +54,7 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
 // image as at build time) + staleness check against the build-time positions; max_disp2 (may be
 // null) receives the largest squared displacement since the build, as float bits.
 void launch_refresh(const Topology& T, const nbl::Grid& G, const int* d_nslot, int nslot_ub, const double* pos_all,
-                    const int* atom, const int* img, const float4* posq_build, float4* posq,
+                    const int* atom, const int* img, const float4* posq_build, float4* posq, float4* jrec,
                     float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s);
 
 }  // namespace sdm
