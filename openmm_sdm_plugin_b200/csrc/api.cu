@@ -715,7 +715,8 @@ int sdm_eval(sdm_ctx* c) {
                 enqueue_position_only(c, s);
             }
         }
-        if (!rc) rc = enqueue_tail(c, 1.0, 1, 0);   // the accumulators are cleared by a memset before the pair pass
+        // the accumulators are cleared by a memset before the pair pass, or (small batches) by the mix kernel
+        if (!rc) rc = enqueue_tail(c, 1.0, 1, sdm_ctx_mix_clears_accumulators(c) ? 1 : 0);
         if (capturing) {
             cudaGraph_t g = nullptr;
             cudaError_t e = cudaStreamEndCapture(s, &g);

@@ -856,6 +856,7 @@ mix_kernel(Topology T, EvalBuffers B, int zero_acc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (i == 0) B.flags[r] = 0;  // already copied into sc.status by the scalar stage
+    if (i == 0 && r == 0 && B.work_counter) *B.work_counter = 0;
     const double sp = B.state[r].sc.sp;
     const int slot = B.slot_of ? B.slot_of[(size_t)r * n + i] : i;
     long long* acc = B.f1acc + (size_t)r * B.acc_rstride;

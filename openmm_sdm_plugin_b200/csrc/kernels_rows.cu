@@ -606,7 +606,9 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
                       long long* f1acc, double* epart, long long* cpart, int exact,
                       int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s) {
     if (V.nrunits_ub <= 0) return;
-    cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
+    // the counter is zero when an evaluation starts (the mix kernel of the previous one put it back);
+    // the debug launch stands outside that cycle
+    if (emit) cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
     const PairEmit em = emit ? *emit : PairEmit{nullptr, nullptr, 0, -1};
 #define SDM_LAUNCH(N, P, X, E)                                                                    \

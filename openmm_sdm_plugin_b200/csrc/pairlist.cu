@@ -1281,14 +1281,17 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
         launch_refresh(c->T, pl->G, pl->d_cnt + kCntSlot, pl->nslot_cap, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq, pl->jrec,
                        hs * hs, c->B.flags, c->d_list_age, pl->max_disp2, s);
         c->launches++;
-        // fresh state-1 accumulators (one 8 MB memset is cheaper than scattered stores in the mix kernel)
-        PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
+        // fresh state-1 accumulators: one memset (8 MB at 16 x 20 k atoms: cheaper than scattered stores in the
+        // mix kernel); small batches let the mix kernel clear what it reads and save the launch
+        if (!sdm_ctx_mix_clears_accumulators(c))
+            PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
     }
     c->list_age++;
     // partial-sum buffers of this path
     c->B.epart = pl->epart;
     c->B.cpart = pl->cpart;
     c->B.part_off = pl->part_off;
+    c->B.work_counter = pl->unit_counter;
     // the displaced-atom kernels scan the cell-sorted slots (spatial locality per warp)
     c->B.scan_posq = pl->posq;
     c->B.scan_atom = pl->atom;
@@ -1320,6 +1323,8 @@ int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs,
     const PairEmit em{d_counter, d_pairs, cap, replica};
     launch_pair_rows(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
                      pl->unit_counter, c->num_sms, &em, c->stream);
+    PL_CUDA(cudaMemsetAsync(pl->unit_counter, 0, sizeof(int), c->stream));
+    PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, c->stream));
     PL_CUDA(cudaStreamSynchronize(c->stream));
     return SDM_OK;
 }

@@ -97,5 +97,6 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c);  // (re)build the list if due, else re
 int sdm_ctx_pairlist_launch(sdm_ctx* c);   // the pair kernel
 int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs, int cap);
 int sdm_ctx_pairlist_info(sdm_ctx* c, const char* key, double* value);
+inline bool sdm_ctx_mix_clears_accumulators(const sdm_ctx* c) { return (long long)c->R * c->n <= 65536; }
 bool sdm_ctx_pairlist_overflowed(sdm_ctx* c);   // the last list build ran out of room (call after the host has seen SDM_ERR_CAPACITY)
 unsigned int* sdm_ctx_pairlist_max_disp_ptr(sdm_ctx* c);   // device word: largest squared displacement since the build (float bits)

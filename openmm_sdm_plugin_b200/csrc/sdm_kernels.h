@@ -8,6 +8,8 @@ namespace sdm {
 // Device buffers of one context that the per-eval kernels touch.  R = replicas, n = atoms.
 struct EvalBuffers {
     int R;
+    int* work_counter;      // cluster path: unit counter of the persistent pair kernel, set back to zero by the
+                            // mix kernel (the last kernel of an evaluation) for the next one; nullptr otherwise
     const double* pos;      // [R][3n]   positions, System order, nm
     const double* fb;       // [R][3n]   bonded/restraint forces (zero when absent)
     float4* posq;           // [R][n]    (x,y,z wrapped into the box, q*sqrt(K)) float
