@@ -47,8 +47,12 @@ typedef enum {
                                   sdm_scalars.status of later evaluations until the host has read it
                                   (sdm_get_scalars / sdm_read_results / sdm_enqueue_results), so a
                                   pipelined sequence of sdm_eval calls cannot lose it              */
-    SDM_ERR_CAPACITY = -7,     /* internal scratch capacity exceeded: reported in sdm_scalars.status,
-                                  the context grows the scratch, repeat the evaluation            */
+    SDM_ERR_CAPACITY = -7,     /* internal capacity exceeded -- the per-hit scratch of the displaced-atom
+                                  kernels, or a pair-list build (enqueued without host synchronisation,
+                                  sized with bounds from the previous build) that outgrew its bounds:
+                                  reported in sdm_scalars.status of every affected replica (sticky like
+                                  STALE_LIST); the context grows what was too small / sizes the next build
+                                  on the host; repeat the evaluation                              */
     SDM_ERR_CONSTRAINT = -8    /* a constraint cluster did not converge (sdm_md_step)              */
 } sdm_status;
 
