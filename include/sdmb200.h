@@ -311,6 +311,35 @@ int sdm_md_set_noise(sdm_ctx* ctx, const double* xi_all);
 /* 0.5 * sum m v^2 of one replica (ReferenceSDMKernels.cpp:105-137 without constraints). */
 int sdm_md_kinetic_energy(sdm_ctx* ctx, int replica, double* ke);
 
+/* ---- restraint forces of SDMUtils (the SDMUtils part) -------------------------------
+ * What python/SDMUtils.py builds as OpenMM Custom*Forces in force group 1, evaluated on the device for every
+ * replica inside sdm_eval(): the energy enters sdm_scalars.pot_energy like Eb, the forces are added to the
+ * hybrid force like Fb (F1 stays the nonbonded state-1 force).  Units: kJ/mol, nm, radians.  Terms are kept
+ * until sdm_clear_restraints(); index arrays are copied. */
+typedef struct sdm_centroid_restraint {     /* SDMUtils.addRestraintForce, python/SDMUtils.py:32-162 */
+    int32_t n_lig_cm, n_rcpt_cm;
+    const int32_t* lig_cm_atoms;            /* g1: ligand atoms of the centroid          (:102) */
+    const int32_t* rcpt_cm_atoms;           /* g2: receptor atoms of the centroid        (:103) */
+    const double* lig_cm_weights;           /* NULL = equal weights; OpenMM's default is the particle masses */
+    const double* rcpt_cm_weights;
+    double kfcm, tolcm, offset[3];          /* (kfcm/2) step(d12-tolcm) (d12-tolcm)^2, d12 = |g1 - offset - g2| (:61,:68) */
+    int32_t do_angles;                      /* 0: the distance term only                 (:55-59) */
+    int32_t rcpt_ref[3], lig_ref[3];        /* g3..g5, g6..g8                            (:122-128) */
+    double kfcd[3], a[3], b[3];             /* angle(g3,g6,g7), dihedral(g4,g3,g6,g7), dihedral(g3,g6,g7,g8):
+                                               force constants and flat-bottom windows [a, b] (:63-83, :137-149) */
+} sdm_centroid_restraint;
+typedef struct sdm_alignment_restraint {    /* SDMUtils.addAlignmentForce, python/SDMUtils.py:166-258 */
+    int32_t liga_ref[3], ligb_ref[3];
+    double kfdispl, ktheta, kpsi, offset[3];
+} sdm_alignment_restraint;
+int sdm_add_centroid_restraint(sdm_ctx* ctx, const sdm_centroid_restraint* r);
+int sdm_add_alignment_restraint(sdm_ctx* ctx, const sdm_alignment_restraint* r);
+int sdm_clear_restraints(sdm_ctx* ctx);
+/* The global parameter "SDMRestraintControlParameter" (SDMUtils.py:7,97): scales the centroid restraints. */
+int sdm_set_restraint_control(sdm_ctx* ctx, double value);
+/* Restraint energy of the last evaluation of one replica (already inside pot_energy); synchronises. */
+int sdm_get_restraint_energy(sdm_ctx* ctx, int replica, double* energy);
+
 /* Scalar half of execute() (ReferenceSDMKernels.cpp:205-302): from E1, E2, Eb and the
  * integrator state compute u_sc, fp, ebias, bfp, sp, PotEnergy, BindE and update the
  * non-equilibrium state in *alch.  O(1) host arithmetic, exactly as the reference does it on

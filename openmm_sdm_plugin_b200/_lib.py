@@ -51,6 +51,20 @@ class SdmAlch(C.Structure):
                 ("b_u0", C.c_double), ("b_w0", C.c_double)]
 
 
+class SdmCentroidRestraint(C.Structure):
+    _fields_ = [("n_lig_cm", C.c_int32), ("n_rcpt_cm", C.c_int32),
+                ("lig_cm_atoms", C.POINTER(C.c_int32)), ("rcpt_cm_atoms", C.POINTER(C.c_int32)),
+                ("lig_cm_weights", C.POINTER(C.c_double)), ("rcpt_cm_weights", C.POINTER(C.c_double)),
+                ("kfcm", C.c_double), ("tolcm", C.c_double), ("offset", C.c_double * 3),
+                ("do_angles", C.c_int32), ("rcpt_ref", C.c_int32 * 3), ("lig_ref", C.c_int32 * 3),
+                ("kfcd", C.c_double * 3), ("a", C.c_double * 3), ("b", C.c_double * 3)]
+
+
+class SdmAlignmentRestraint(C.Structure):
+    _fields_ = [("liga_ref", C.c_int32 * 3), ("ligb_ref", C.c_int32 * 3),
+                ("kfdispl", C.c_double), ("ktheta", C.c_double), ("kpsi", C.c_double), ("offset", C.c_double * 3)]
+
+
 class SdmScalars(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("E1", "E2", "Eb", "u", "u_sc", "fp", "ebias", "bfp", "sp", "pot_energy",
@@ -115,6 +129,11 @@ SYMBOLS = {
     "sdm_md_update": (_I, [_VP, _VP]),
     "sdm_md_set_noise": (_I, [_VP, _VP]),
     "sdm_md_kinetic_energy": (_I, [_VP, _I, C.POINTER(_D)]),
+    "sdm_add_centroid_restraint": (_I, [_VP, C.POINTER(SdmCentroidRestraint)]),
+    "sdm_add_alignment_restraint": (_I, [_VP, C.POINTER(SdmAlignmentRestraint)]),
+    "sdm_clear_restraints": (_I, [_VP]),
+    "sdm_set_restraint_control": (_I, [_VP, _D]),
+    "sdm_get_restraint_energy": (_I, [_VP, _I, C.POINTER(_D)]),
 }
 
 _LIB = None

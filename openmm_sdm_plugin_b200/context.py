@@ -295,6 +295,54 @@ class SDMContext:
         _lib.check(self._L.sdm_md_kinetic_energy(self._h, replica, C.byref(v)))
         return v.value
 
+    # ---- restraint forces of SDMUtils (python/SDMUtils.py:32-258); kJ/mol, nm, radians ------------------
+    def add_centroid_restraint(self, lig_cm_atoms, rcpt_cm_atoms, kfcm, tolcm, offset=(0.0, 0.0, 0.0),
+                               lig_cm_weights=None, rcpt_cm_weights=None, lig_ref=None, rcpt_ref=None,
+                               kfcd=(0.0, 0.0, 0.0), a=(0.0, 0.0, 0.0), b=(0.0, 0.0, 0.0)):
+        la = np.ascontiguousarray(lig_cm_atoms, dtype=np.int32)
+        ra = np.ascontiguousarray(rcpt_cm_atoms, dtype=np.int32)
+        lw = None if lig_cm_weights is None else np.ascontiguousarray(lig_cm_weights, dtype=np.float64)
+        rw = None if rcpt_cm_weights is None else np.ascontiguousarray(rcpt_cm_weights, dtype=np.float64)
+        r = _lib.SdmCentroidRestraint()
+        r.n_lig_cm, r.n_rcpt_cm = len(la), len(ra)
+        r.lig_cm_atoms = la.ctypes.data_as(C.POINTER(C.c_int32))
+        r.rcpt_cm_atoms = ra.ctypes.data_as(C.POINTER(C.c_int32))
+        r.lig_cm_weights = lw.ctypes.data_as(C.POINTER(C.c_double)) if lw is not None else None
+        r.rcpt_cm_weights = rw.ctypes.data_as(C.POINTER(C.c_double)) if rw is not None else None
+        r.kfcm, r.tolcm = float(kfcm), float(tolcm)
+        r.offset = (C.c_double * 3)(*[float(x) for x in offset])
+        r.do_angles = 1 if (lig_ref is not None and rcpt_ref is not None) else 0
+        if r.do_angles:
+            if len(lig_ref) != 3 or len(rcpt_ref) != 3:
+                raise ValueError("Invalid lists of reference atoms")
+            r.lig_ref = (C.c_int32 * 3)(*[int(x) for x in lig_ref])
+            r.rcpt_ref = (C.c_int32 * 3)(*[int(x) for x in rcpt_ref])
+            r.kfcd = (C.c_double * 3)(*[float(x) for x in kfcd])
+            r.a = (C.c_double * 3)(*[float(x) for x in a])
+            r.b = (C.c_double * 3)(*[float(x) for x in b])
+        _lib.check(self._L.sdm_add_centroid_restraint(self._h, C.byref(r)))
+
+    def add_alignment_restraint(self, liga_ref, ligb_ref, kfdispl, ktheta, kpsi, offset=(0.0, 0.0, 0.0)):
+        if len(liga_ref) != 3 or len(ligb_ref) != 3:
+            raise ValueError("Invalid lists of reference atoms")
+        r = _lib.SdmAlignmentRestraint()
+        r.liga_ref = (C.c_int32 * 3)(*[int(x) for x in liga_ref])
+        r.ligb_ref = (C.c_int32 * 3)(*[int(x) for x in ligb_ref])
+        r.kfdispl, r.ktheta, r.kpsi = float(kfdispl), float(ktheta), float(kpsi)
+        r.offset = (C.c_double * 3)(*[float(x) for x in offset])
+        _lib.check(self._L.sdm_add_alignment_restraint(self._h, C.byref(r)))
+
+    def clear_restraints(self):
+        _lib.check(self._L.sdm_clear_restraints(self._h))
+
+    def set_restraint_control(self, value: float):
+        _lib.check(self._L.sdm_set_restraint_control(self._h, float(value)))
+
+    def restraint_energy(self, replica: int = 0) -> float:
+        v = C.c_double()
+        _lib.check(self._L.sdm_get_restraint_energy(self._h, replica, C.byref(v)))
+        return v.value
+
     def info(self, key: str) -> float:
         v = C.c_double()
         _lib.check(self._L.sdm_get_info(self._h, key.encode(), C.byref(v)))

@@ -232,6 +232,7 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     c->device = dev;
     c->opt = opt;
     c->n = s->n_atoms;
+    c->RT.control = 1.0;   // SDMRestraintControlParameter (SDMUtils.py:97)
     c->R = s->n_replicas;
     c->num_sms = prop.multiProcessorCount;
     const int n = c->n, R = c->R;
@@ -580,6 +581,131 @@ static int enqueue_tail(sdm_ctx* c, double e_scale, int c_div, int zero_acc) {
     sdm::launch_scalars(c->T, c->B, e_scale, c_div, s);
     sdm::launch_mix(c->T, c->B, zero_acc, s);
     c->launches += 2;
+    if (c->RT.n_terms > 0) {   // SDMUtils restraints: energy into pot_energy, forces onto the hybrid force
+        sdm::launch_restraints(c->RT, c->n, c->R, c->d_pos, c->B.F, c->B.state, c->d_erest, s);
+        c->launches += 1;
+    }
+    return SDM_OK;
+}
+
+// Device copy of the restraint tables (rebuilt whenever a term was added or removed; never inside a capture).
+static int upload_restraints(sdm_ctx* c) {
+    if (!c->rt_dirty) return SDM_OK;
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    auto drop = [&](const void* p) {
+        if (!p) return;
+        c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void*)p), c->allocs.end());
+        cudaFree((void*)p);
+    };
+    drop(c->RT.terms); drop(c->RT.atoms); drop(c->RT.weights);
+    c->RT.terms = nullptr; c->RT.atoms = nullptr; c->RT.weights = nullptr;
+    c->RT.n_terms = (int)c->h_rterms.size();
+    if (c->RT.n_terms > 0) {
+        void *t = nullptr, *a = nullptr, *w = nullptr;
+        SDM_CUDA(cudaMalloc(&t, sizeof(sdm::RestraintTerm) * c->h_rterms.size()));
+        SDM_CUDA(cudaMalloc(&a, sizeof(int) * std::max<size_t>(c->h_ratoms.size(), 1)));
+        SDM_CUDA(cudaMalloc(&w, sizeof(double) * std::max<size_t>(c->h_rweights.size(), 1)));
+        c->allocs.push_back(t); c->allocs.push_back(a); c->allocs.push_back(w);
+        SDM_CUDA(cudaMemcpy(t, c->h_rterms.data(), sizeof(sdm::RestraintTerm) * c->h_rterms.size(), cudaMemcpyHostToDevice));
+        SDM_CUDA(cudaMemcpy(a, c->h_ratoms.data(), sizeof(int) * c->h_ratoms.size(), cudaMemcpyHostToDevice));
+        SDM_CUDA(cudaMemcpy(w, c->h_rweights.data(), sizeof(double) * c->h_rweights.size(), cudaMemcpyHostToDevice));
+        c->RT.terms = (const sdm::RestraintTerm*)t;
+        c->RT.atoms = (const int*)a;
+        c->RT.weights = (const double*)w;
+        if (!c->d_erest) {
+            void* e = nullptr;
+            SDM_CUDA(cudaMalloc(&e, sizeof(double) * (size_t)c->R));
+            SDM_CUDA(cudaMemset(e, 0, sizeof(double) * (size_t)c->R));
+            c->allocs.push_back(e);
+            c->d_erest = (double*)e;
+        }
+    }
+    c->rt_dirty = false;
+    c->graph_valid = false;   // one launch more or less per evaluation
+    return SDM_OK;
+}
+
+// One group of a restraint term: its atoms with normalised weights (NULL weights = equal).
+static int push_group(sdm_ctx* c, sdm::RestraintTerm& t, int k, int count, const int32_t* atoms, const double* weights) {
+    if (count <= 0 || !atoms) return fail(SDM_ERR_INVALID, "restraint: empty atom group");
+    double sum = 0.0;
+    for (int i = 0; i < count; i++) {
+        if (atoms[i] < 0 || atoms[i] >= c->n) return fail(SDM_ERR_INVALID, "restraint: atom index out of range");
+        const double w = weights ? weights[i] : 1.0;
+        if (!(w >= 0.0)) return fail(SDM_ERR_INVALID, "restraint: negative weight");
+        sum += w;
+    }
+    if (!(sum > 0.0)) return fail(SDM_ERR_INVALID, "restraint: weights of a group sum to zero");
+    t.grp_begin[k] = (int)c->h_ratoms.size();
+    for (int i = 0; i < count; i++) {
+        c->h_ratoms.push_back(atoms[i]);
+        c->h_rweights.push_back((weights ? weights[i] : 1.0) / sum);
+    }
+    t.grp_begin[k + 1] = (int)c->h_ratoms.size();
+    return SDM_OK;
+}
+
+int sdm_add_centroid_restraint(sdm_ctx* c, const sdm_centroid_restraint* r) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c || !r) return fail(SDM_ERR_INVALID, "null argument");
+    sdm::RestraintTerm t{};
+    t.kind = 0;
+    t.npoints = r->do_angles ? 8 : 2;
+    const size_t keep_a = c->h_ratoms.size();
+    int rc = push_group(c, t, 0, r->n_lig_cm, r->lig_cm_atoms, r->lig_cm_weights);
+    if (!rc) rc = push_group(c, t, 1, r->n_rcpt_cm, r->rcpt_cm_atoms, r->rcpt_cm_weights);
+    for (int k = 0; k < 3 && !rc && r->do_angles; k++) rc = push_group(c, t, 2 + k, 1, &r->rcpt_ref[k], nullptr);
+    for (int k = 0; k < 3 && !rc && r->do_angles; k++) rc = push_group(c, t, 5 + k, 1, &r->lig_ref[k], nullptr);
+    if (rc) { c->h_ratoms.resize(keep_a); c->h_rweights.resize(keep_a); return rc; }
+    t.p[0] = r->kfcm; t.p[1] = r->tolcm; t.p[2] = r->offset[0]; t.p[3] = r->offset[1]; t.p[4] = r->offset[2];
+    for (int k = 0; k < 3; k++) { t.p[5 + 3 * k] = r->kfcd[k]; t.p[6 + 3 * k] = r->a[k]; t.p[7 + 3 * k] = r->b[k]; }
+    c->h_rterms.push_back(t);
+    c->rt_dirty = true;
+    return SDM_OK;
+}
+
+int sdm_add_alignment_restraint(sdm_ctx* c, const sdm_alignment_restraint* r) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c || !r) return fail(SDM_ERR_INVALID, "null argument");
+    sdm::RestraintTerm t{};
+    t.kind = 1;
+    t.npoints = 6;
+    const size_t keep_a = c->h_ratoms.size();
+    int rc = SDM_OK;
+    for (int k = 0; k < 3 && !rc; k++) rc = push_group(c, t, k, 1, &r->ligb_ref[k], nullptr);
+    for (int k = 0; k < 3 && !rc; k++) rc = push_group(c, t, 3 + k, 1, &r->liga_ref[k], nullptr);
+    if (rc) { c->h_ratoms.resize(keep_a); c->h_rweights.resize(keep_a); return rc; }
+    t.p[0] = r->kfdispl; t.p[1] = r->ktheta; t.p[2] = r->kpsi;
+    t.p[3] = r->offset[0]; t.p[4] = r->offset[1]; t.p[5] = r->offset[2];
+    c->h_rterms.push_back(t);
+    c->rt_dirty = true;
+    return SDM_OK;
+}
+
+int sdm_clear_restraints(sdm_ctx* c) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    c->h_rterms.clear(); c->h_ratoms.clear(); c->h_rweights.clear();
+    c->rt_dirty = true;
+    return SDM_OK;
+}
+
+int sdm_set_restraint_control(sdm_ctx* c, double value) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    c->RT.control = value;
+    c->graph_valid = false;   // a launch parameter of the captured sequence
+    return SDM_OK;
+}
+
+int sdm_get_restraint_energy(sdm_ctx* c, int replica, double* energy) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c || !energy) return fail(SDM_ERR_INVALID, "null argument");
+    if (replica < 0 || replica >= c->R) return fail(SDM_ERR_INVALID, "replica out of range");
+    *energy = 0.0;
+    if (!c->d_erest || c->h_rterms.empty()) return SDM_OK;
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    SDM_CUDA(cudaMemcpy(energy, c->d_erest + replica, sizeof(double), cudaMemcpyDeviceToHost));
     return SDM_OK;
 }
 
@@ -651,6 +777,7 @@ static int ensure_hitbits(sdm_ctx* c) {
 int sdm_eval(sdm_ctx* c) {
     SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (int rc = upload_restraints(c)) return rc;
     cudaStream_t s = c->stream;
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;

@@ -80,6 +80,14 @@ struct sdm_ctx {
     double md_dt = 0, md_vscale = 0, md_fscale = 0, md_noisescale = 0;
     unsigned long long md_seed = 0, md_steps = 0;
 
+    // restraint forces of SDMUtils (sdm_add_centroid_restraint / sdm_add_alignment_restraint)
+    std::vector<sdm::RestraintTerm> h_rterms;
+    std::vector<int> h_ratoms;
+    std::vector<double> h_rweights;
+    sdm::RestraintTables RT{};
+    bool rt_dirty = false;              // host tables changed since the last upload
+    double* d_erest = nullptr;          // [R] restraint energy of the last evaluation
+
     int64_t launches = 0;
     int64_t n_evals = 0;
     bool timing = false, timing_valid = false;

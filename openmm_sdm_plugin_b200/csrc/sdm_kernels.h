@@ -78,6 +78,25 @@ void launch_scalars(const Topology& T, const EvalBuffers& B, double e_scale, int
                     cudaStream_t s);
 void launch_mix(const Topology& T, const EvalBuffers& B, int zero_acc, cudaStream_t s);
 
+// ---- restraint forces of SDMUtils (kernels_restraints.cu) --------------------------------------
+constexpr int kRestraintPoints = 8;   // points (centroids / single atoms) a term can name
+struct RestraintTerm {
+    int kind;                               // 0: addRestraintForce (centroid bond), 1: addAlignmentForce
+    int npoints;                            // 2 or 8 (kind 0), 6 (kind 1)
+    int grp_begin[kRestraintPoints + 1];    // atoms / weights of point k: [grp_begin[k], grp_begin[k+1])
+    double p[16];                           // parameters, see kernels_restraints.cu
+};
+struct RestraintTables {
+    int n_terms;
+    const RestraintTerm* terms;             // device
+    const int* atoms;                       // device: group members (System indices)
+    const double* weights;                  // device: normalised weights (sum 1 per group)
+    double control;                         // SDMRestraintControlParameter (scales kind 0)
+};
+struct ReplicaState;
+void launch_restraints(const RestraintTables& RT, int n, int R, const double* pos_all, double* F_all,
+                       ReplicaState* state, double* erest, cudaStream_t s);
+
 // ---- literal kernel-interface operations (float4 device buffers) ------------------------------
 void launch_make_state2(int n, float4* posq, const float4* displ, cudaStream_t s);
 void launch_save_state1(int n, const float4* posq, const float4* force, float4* save_f,

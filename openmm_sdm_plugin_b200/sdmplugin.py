@@ -27,12 +27,31 @@ class OpenMMException(Exception):
     """Stands in for OpenMM::OpenMMException (the reference throws it from C++)."""
 
 
+def _md_units(x):
+    """A plain number (or list of numbers) in OpenMM's unit system -- kJ/mol, nm, radians.  The reference's
+    scripts pass simtk.unit quantities; those are converted when simtk.unit is importable."""
+    if hasattr(x, "value_in_unit_system"):
+        from simtk.unit import md_unit_system   # only reached with simtk quantities in hand
+        x = x.value_in_unit_system(md_unit_system)
+    if isinstance(x, (list, tuple)):
+        return [float(v) for v in x]
+    try:
+        return float(x)
+    except TypeError:
+        return [float(v) for v in x]
+
+
 class SDMUtils(object):
-    """Method constants exactly as python/SDMUtils.py:9-15 names them."""
+    """python/SDMUtils.py: the method constants (:9-15) and the two restraint builders.  The reference adds
+    OpenMM Custom*Forces (force group 1) to the System; here the same terms are recorded on the system
+    description (``system.sdm_restraints``) and evaluated on the device by every context bound to it
+    (LangevinIntegratorSDM.bind -> sdm_add_centroid_restraint / sdm_add_alignment_restraint).  Numbers are in
+    kJ/mol, nm and radians (what the reference divides its quantities down to, SDMUtils.py:130-149)."""
 
     def __init__(self, system=None):
         self.system = system
         self.RestraintControlParameterName = "SDMRestraintControlParameter"
+        self.force = None
         self.LinearMethod = 0
         self.QuadraticMethod = 1
         self.ILogisticMethod = 2
@@ -42,6 +61,60 @@ class SDMUtils(object):
 
     def getControlParameterName(self):
         return self.RestraintControlParameterName
+
+    def _restraints(self):
+        if self.system is None:
+            raise OpenMMException("SDMUtils was created without a system")
+        if not hasattr(self.system, "sdm_restraints"):
+            self.system.sdm_restraints = []
+        return self.system.sdm_restraints
+
+    def addRestraintForce(self, lig_cm_particles=None, rcpt_cm_particles=None, kfcm=0.0, tolcm=0.0,
+                          lig_ref_particles=None, rcpt_ref_particles=None, angle_center=0.0, kfangle=0.0,
+                          angletol=10.0 * 3.14159265358979323846 / 180.0, dihedral1center=0.0, kfdihedral1=0.0,
+                          dihedral1tol=10.0 * 3.14159265358979323846 / 180.0, dihedral2center=0.0, kfdihedral2=0.0,
+                          dihedral2tol=10.0 * 3.14159265358979323846 / 180.0, offset=(0.0, 0.0, 0.0),
+                          lig_cm_weights=None, rcpt_cm_weights=None):
+        """SDMUtils.py:32-162.  Centroid weights: OpenMM's CustomCentroidBondForce weighs by mass; pass the
+        masses of the group atoms as lig_cm_weights / rcpt_cm_weights (None = equal weights)."""
+        if not (lig_cm_particles and rcpt_cm_particles):
+            return                                             # :49-53
+        spec = {"kind": "centroid", "lig_cm_atoms": [int(i) for i in lig_cm_particles],
+                "rcpt_cm_atoms": [int(i) for i in rcpt_cm_particles],
+                "lig_cm_weights": lig_cm_weights, "rcpt_cm_weights": rcpt_cm_weights,
+                "kfcm": _md_units(kfcm), "tolcm": _md_units(tolcm), "offset": _md_units(offset)}
+        if lig_ref_particles and rcpt_ref_particles:
+            if not (len(lig_ref_particles) == 3 and len(rcpt_ref_particles) == 3):
+                raise ValueError("Invalid lists of reference atoms")      # :57-58
+            c = [_md_units(angle_center), _md_units(dihedral1center), _md_units(dihedral2center)]
+            t = [_md_units(angletol), _md_units(dihedral1tol), _md_units(dihedral2tol)]
+            spec.update(lig_ref=[int(i) for i in lig_ref_particles], rcpt_ref=[int(i) for i in rcpt_ref_particles],
+                        kfcd=[_md_units(kfangle), _md_units(kfdihedral1), _md_units(kfdihedral2)],
+                        a=[c[k] - t[k] for k in range(3)], b=[c[k] + t[k] for k in range(3)])   # :137-149
+        self._restraints().append(spec)
+        self.force = spec
+
+    def addAlignmentForce(self, liga_ref_particles=None, ligb_ref_particles=None, kfdispl=0.0, ktheta=0.0, kpsi=0.0,
+                          offset=(0.0, 0.0, 0.0)):
+        """SDMUtils.py:166-258."""
+        if not (liga_ref_particles and ligb_ref_particles) or \
+                not (len(liga_ref_particles) == 3 and len(ligb_ref_particles) == 3):
+            raise ValueError("Invalid lists of reference atoms")          # :173-175
+        self._restraints().append({"kind": "alignment", "liga_ref": [int(i) for i in liga_ref_particles],
+                                   "ligb_ref": [int(i) for i in ligb_ref_particles], "kfdispl": _md_units(kfdispl),
+                                   "ktheta": _md_units(ktheta), "kpsi": _md_units(kpsi), "offset": _md_units(offset)})
+
+
+def apply_restraints(ctx, system):
+    """Hand the restraint terms recorded on `system` by SDMUtils to a context."""
+    for s in getattr(system, "sdm_restraints", []):
+        if s["kind"] == "centroid":
+            ctx.add_centroid_restraint(s["lig_cm_atoms"], s["rcpt_cm_atoms"], s["kfcm"], s["tolcm"], s["offset"],
+                                       s.get("lig_cm_weights"), s.get("rcpt_cm_weights"), s.get("lig_ref"),
+                                       s.get("rcpt_ref"), s.get("kfcd", (0, 0, 0)), s.get("a", (0, 0, 0)),
+                                       s.get("b", (0, 0, 0)))
+        else:
+            ctx.add_alignment_restraint(s["liga_ref"], s["ligb_ref"], s["kfdispl"], s["ktheta"], s["kpsi"], s["offset"])
 
 
 class LangevinIntegratorSDM(object):
@@ -156,6 +229,7 @@ class LangevinIntegratorSDM(object):
         if system.n_atoms != self._n:
             raise OpenMMException("nParticles (%d) does not match the system (%d)" % (self._n, system.n_atoms))
         self._ctx = SDMContext(system, self._displ, n_replicas=1, device=device, **ctx_options)
+        apply_restraints(self._ctx, system)     # what SDMUtils recorded on the system (force group 1 in the reference)
         self._displ_dirty = False
         return self
 
