@@ -784,6 +784,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_t / args.steps, "batches_in_flight": D,
                     "pcie_gb_s_per_rank": (h2d + d2h) * args.steps / e2e_t / 1e9,
+                    "host_gb_s_all_ranks": world * (h2d + d2h) * args.steps / e2e_t / 1e9,
                     "f32_io": {"value": world * R * args.steps / e2e32_t, "unit": "evals/s",
                                "ms_per_step": 1e3 * e2e32_t / args.steps,
                                "h2d_bytes_per_step": R * n * 3 * 4, "d2h_bytes_per_step": R * n * 3 * 4 + R * 8 * 20,
