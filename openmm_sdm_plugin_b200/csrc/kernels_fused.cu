@@ -639,6 +639,61 @@ ligand_probe_list_kernel(const __grid_constant__ Topology T, const __grid_consta
     probe_finish(T, B, P, A, pos, m, r, s_red, s_redl);
 }
 
+// All-pairs path, small systems (a few hundred atoms, hundreds of replicas): ONE WARP per (displaced atom,
+// replica) instead of a block -- lane = scan index of the current bitmap word, hit index = running prefix +
+// popcount below the lane: no block barriers, no search for the n-th set bit, eight rows per block.  Same
+// outputs and layouts as ligand_probe_kernel (sums in a different, still fixed, order).
+constexpr int kProbeWarpRows = 8;
+__global__ void __launch_bounds__(32 * kProbeWarpRows)
+ligand_probe_warp_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B) {
+    const int lane = threadIdx.x & 31;
+    const int rowi = blockIdx.x * kProbeWarpRows + (threadIdx.x >> 5);
+    if (rowi >= B.R * T.n_lig) return;
+    const int r = rowi / T.n_lig, m = rowi - r * T.n_lig, n = T.n;
+    const double* pos = B.pos + (size_t)r * 3 * n;
+    const ProbeAtom P = load_probe_atom(T, pos, m);
+    int begin, end;
+    scan_range(T, B, r, &begin, &end);
+    const size_t row = (size_t)rowi;
+    const uint32_t* bits = B.hitbits + (size_t)r * B.scan_words * T.n_lig + m;
+    int* pre_out = B.hitpre + (size_t)r * B.scan_words * T.n_lig + m;
+    const size_t wstride = (size_t)T.n_lig;
+    double* pf_out = B.pairf + row * (size_t)B.pairf_cap * 3;
+    const int nwords = min(B.scan_words, (end - begin + 31) / 32);
+    ProbeAcc A{0, 0, 0, 0, 0, 0};
+    int pre = 0;
+    for (int w = 0; w < nwords; w++) {
+        const uint32_t v = bits[(size_t)w * wstride];
+        if (lane == 0) pre_out[(size_t)w * wstride] = pre;
+        if ((v >> lane) & 1u) {
+            const int idx = begin + w * 32 + lane;
+            int k = idx - begin;
+            if (B.scan_atom) k = B.scan_atom[idx] - r * n;
+            double px, py, pz;
+            probe_pair(T, pos, P, k, (P.flags & 1) != 0, A, px, py, pz);
+            const int hg = pre + __popc(v & ((1u << lane) - 1u));
+            if (hg < B.pairf_cap) {
+                pf_out[3 * (size_t)hg] = -px; pf_out[3 * (size_t)hg + 1] = -py; pf_out[3 * (size_t)hg + 2] = -pz;
+            }
+        }
+        pre += __popc(v);
+    }
+    if (pre > B.pairf_cap && lane == 0) atomicExch(B.flags + r, SDM_ERR_CAPACITY);
+    for (int mm = lane; mm < T.n_lig; mm += 32) {
+        double px, py, pz;
+        probe_pair(T, pos, P, T.lig_idx[mm], true, A, px, py, pz);
+    }
+    const double sx = warp_sum(A.fx), sy = warp_sum(A.fy), sz = warp_sum(A.fz), su = warp_sum(A.u);
+    const long long sc1 = warp_sum_ll(A.c1), sc2 = warp_sum_ll(A.c2);
+    if (lane == 0) {
+        double* dF = B.dF + (size_t)r * 3 * n;
+        dF[3 * P.i] = sx; dF[3 * P.i + 1] = sy; dF[3 * P.i + 2] = sz;
+        B.upart[row] = su;
+        B.mcnt[row * 2] = sc1;
+        B.mcnt[row * 2 + 1] = sc2;
+    }
+}
+
 // ---- gather kernel -------------------------------------------------------------------------------
 // One thread per scan index (a NON-displaced atom j): dF_j = sum over the displaced atoms m (in
 // index order: fixed summation order) of the force the probe kernel stored for the pair, found
@@ -897,6 +952,11 @@ void launch_allpairs(const Topology& T, const EvalBuffers& B, int exact, int* em
 
 void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
     if (T.n_lig == 0) return;
+    if (B.scan_words <= 64) {   // small systems: one warp per (displaced atom, replica)
+        const int rows = T.n_lig * B.R;
+        ligand_probe_warp_kernel<<<(rows + kProbeWarpRows - 1) / kProbeWarpRows, 32 * kProbeWarpRows, 0, s>>>(T, B);
+        return;
+    }
     dim3 grid(T.n_lig, B.R);
     ligand_probe_kernel<<<grid, kProbeThreads, 0, s>>>(T, B);
 }
