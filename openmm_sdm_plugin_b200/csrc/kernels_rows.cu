@@ -567,9 +567,17 @@ __global__ void __launch_bounds__(256)
 refresh_kernel(Topology T, nbl::Grid G, const int* __restrict__ d_nslot, const double* __restrict__ pos_all,
                const int* __restrict__ atom, const int* __restrict__ img,
                const float4* __restrict__ posq_build, float4* __restrict__ posq, float4* __restrict__ jrec,
-               float half_skin2, int* flags, int* list_age, unsigned int* max_disp2) {
+               float half_skin2, int* flags, int* list_age, unsigned int* max_disp2,
+               long long* __restrict__ acc, int nslot_cap) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) *list_age += 1;   // one more evaluation with this list (read by the scalar stage)
+    // fresh state-1 accumulators for the pair pass that follows (replaces an 8 MB memset node; acc == nullptr
+    // when the mix kernel of the previous evaluation has cleared them already)
+    if (acc && s < nslot_cap) {
+        acc[s] = 0;
+        acc[(size_t)nslot_cap + s] = 0;
+        acc[2 * (size_t)nslot_cap + s] = 0;
+    }
     float d2 = 0.f;
     const int ga = s < *d_nslot ? atom[s] : -1;
     if (ga >= 0) {   // a dummy slot keeps its far-away coordinates
@@ -646,10 +654,12 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
 
 void launch_refresh(const Topology& T, const nbl::Grid& G, const int* d_nslot, int nslot_ub, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq, float4* jrec,
-                    float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s) {
+                    float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, long long* acc_to_clear,
+                    cudaStream_t s) {
     if (nslot_ub <= 0) return;
     refresh_kernel<<<(nslot_ub + 255) / 256, 256, 0, s>>>(T, G, d_nslot, pos_all, atom, img, posq_build,
-                                                      posq, jrec, half_skin2, flags, list_age, max_disp2);
+                                                      posq, jrec, half_skin2, flags, list_age, max_disp2,
+                                                      acc_to_clear, nslot_ub);
 }
 
 }  // namespace sdm

@@ -1279,12 +1279,12 @@ int sdm_ctx_pairlist_prepare(sdm_ctx* c) {
     } else {
         const float hs = 0.5f * (float)c->opt.skin;
         launch_refresh(c->T, pl->G, pl->d_cnt + kCntSlot, pl->nslot_cap, c->d_pos, pl->atom, pl->img, pl->posq_build, pl->posq, pl->jrec,
-                       hs * hs, c->B.flags, c->d_list_age, pl->max_disp2, s);
+                       hs * hs, c->B.flags, c->d_list_age, pl->max_disp2,
+                       // fresh state-1 accumulators: cleared slot by slot by this kernel (coalesced; cheaper than
+                       // scattered stores in the mix kernel at 16 x 20 k atoms); small batches let the mix kernel
+                       // clear what it reads
+                       sdm_ctx_mix_clears_accumulators(c) ? nullptr : c->B.f1acc, s);
         c->launches++;
-        // fresh state-1 accumulators: one memset (8 MB at 16 x 20 k atoms: cheaper than scattered stores in the
-        // mix kernel); small batches let the mix kernel clear what it reads and save the launch
-        if (!sdm_ctx_mix_clears_accumulators(c))
-            PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, s));
     }
     c->list_age++;
     // partial-sum buffers of this path

@@ -55,6 +55,7 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
 // null) receives the largest squared displacement since the build, as float bits.
 void launch_refresh(const Topology& T, const nbl::Grid& G, const int* d_nslot, int nslot_ub, const double* pos_all,
                     const int* atom, const int* img, const float4* posq_build, float4* posq, float4* jrec,
-                    float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, cudaStream_t s);
+                    float half_skin2, int* flags, int* list_age, unsigned int* max_disp2, long long* acc_to_clear,
+                    cudaStream_t s);
 
 }  // namespace sdm
