@@ -27,13 +27,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_PAIR = {2: 61.0, 1: 46.0, 0: 46.0}   # periodic / non-periodic
+# periodic / non-periodic.  Ewald / PME direct space (3, 4) has no figure there: the
+# reaction-field term (rinv + krf r^2 - crf and its derivative) is replaced by erfc(alpha r)/r and its
+# derivative -- the exponential, a reciprocal and the five-term polynomial of Abramowitz & Stegun 7.1.26:
+# 61 + 20 by our count.
+FLOP_PER_PAIR = {2: 61.0, 1: 46.0, 0: 46.0, 3: 81.0, 4: 81.0}
 
 
 def load_case(workload: str):
     from openmm_sdm_plugin_b200 import system as S
     if workload == "cfg2":
         return S.cfg2(), "cfg2: TEMOA-G1/G4 explicit solvent (20446 atoms, CutoffPeriodic RF, rc=1.0 nm, 38 displaced atoms)"
+    if workload == "cfg2:pme":
+        c = S.cfg2()
+        c.system.method = S.PME
+        return c, "cfg2 as example/test_explicit.py:64 ships it: nonbondedMethod=PME, DIRECT SPACE only (erfc pair terms + " \
+                  "erf correction of the excluded pairs; the reciprocal part enters through sdm_set_external_dual)"
     if workload == "cfg1":
         return S.cfg1(), "cfg1: OA-G6/G3 (230 atoms, CutoffNonPeriodic 15 nm, 38 displaced atoms)"
     if workload.startswith("synthetic:"):
@@ -405,7 +414,7 @@ def sweep_leg(args, device, stream, peak_tflops, quick=False):
     import torch
     from openmm_sdm_plugin_b200 import system as S
     from openmm_sdm_plugin_b200.context import SDMContext
-    plan = [("cfg1", r) for r in (16, 128, 512)] + [("synthetic:50000", 16)]
+    plan = [("cfg1", r) for r in (16, 128, 512)] + [("cfg2:pme", 16), ("synthetic:50000", 16)]
     sizes = (5000, 20000, 100000) if quick else (5000, 10000, 20000, 50000, 100000, 200000, 500000)
     plan += [("synthetic:%d" % n, r) for n in sizes for r in (1, 8)]
     out = []

@@ -61,6 +61,14 @@ typedef enum {
 #define SDM_NOCUTOFF 0
 #define SDM_CUTOFF_NONPERIODIC 1
 #define SDM_CUTOFF_PERIODIC 2
+/* NonbondedForce::Ewald / ::PME (what example/test_explicit.py:64 asks for): the DIRECT-SPACE part of the Ewald sum --
+ * erfc(alpha r)/r pair terms inside the cutoff, the erf(alpha r)/r correction of the excluded pairs, 1-4
+ * exceptions and the dispersion correction: OpenMM's calculateEwaldIxn with includeDirect only.  The
+ * reciprocal-space part (and the self energy OpenMM books with it) is NOT computed here; it enters through
+ * sdm_set_external_dual() -- with OpenMM in the loop: NonbondedForce::setReciprocalSpaceForceGroup and one
+ * evaluation of that group per state.  Both values select the same direct-space arithmetic. */
+#define SDM_EWALD 3
+#define SDM_PME 4
 
 /* LangevinIntegratorSDM.h:120-122 and :143-145 */
 #define SDM_BIAS_LINEAR 0
@@ -87,7 +95,7 @@ typedef enum {
  * sdm_set_displacement() to change it later (the reference needs Context::reinitialize). */
 typedef struct {
     int32_t n_atoms;
-    int32_t method;                 /* SDM_NOCUTOFF / SDM_CUTOFF_NONPERIODIC / SDM_CUTOFF_PERIODIC */
+    int32_t method;                 /* SDM_NOCUTOFF / SDM_CUTOFF_NONPERIODIC / SDM_CUTOFF_PERIODIC / SDM_EWALD / SDM_PME */
     double cutoff;                  /* nm */
     double eps_rf;                  /* reaction-field dielectric, 78.3 is NonbondedForce's default */
     double box[3];                  /* orthorhombic box edges (nm); ignored unless periodic */
@@ -102,6 +110,9 @@ typedef struct {
     const int32_t* exceptions;      /* [2*n_exceptions] */
     const double* exception_params; /* [3*n_exceptions] chargeProd (e^2), sigma (nm), epsilon (kJ/mol) */
     const double* displacement;     /* [3*n_atoms] nm; NULL = all zero */
+    double ewald_alpha;             /* SDM_EWALD / SDM_PME: splitting parameter (1/nm); 0 = OpenMM's rule
+                                       sqrt(-log(2 tol)) / cutoff (NonbondedForceImpl::calcPMEParameters) */
+    double ewald_tolerance;         /* tol of that rule; 0 = NonbondedForce's default 5e-4 */
 } sdm_system;
 
 typedef struct {
@@ -310,6 +321,14 @@ int sdm_md_update(sdm_ctx* ctx, const double* forces_all);
 int sdm_md_set_noise(sdm_ctx* ctx, const double* xi_all);
 /* 0.5 * sum m v^2 of one replica (ReferenceSDMKernels.cpp:105-137 without constraints). */
 int sdm_md_kinetic_energy(sdm_ctx* ctx, int replica, double* ke);
+
+/* Contributions of BOTH states that are computed outside this library, per replica: energies E1_ext, E2_ext
+ * (kJ/mol) and forces F1_ext, F2_ext ([3*n_atoms], kJ/mol/nm, System order) of a term that cannot be reduced
+ * to moved pairs -- the reciprocal-space part of PME (global in the charge density), a GB model.  They enter
+ * like the nonbonded terms themselves: E1 += E1_ext, u += E2_ext - E1_ext, F1 += F1_ext, F2 - F1 += F2_ext -
+ * F1_ext, and stay in force until replaced; NULL force pointers remove them.  (Row N4 of SURVEY.md 8f.) */
+int sdm_set_external_dual(sdm_ctx* ctx, int replica, const double* f1_ext, const double* f2_ext,
+                          double e1_ext, double e2_ext);
 
 /* ---- restraint forces of SDMUtils (the SDMUtils part) -------------------------------
  * What python/SDMUtils.py builds as OpenMM Custom*Forces in force group 1, evaluated on the device for every

@@ -28,7 +28,8 @@ class SdmSystem(C.Structure):
                 ("n_exceptions", C.c_int32), ("n_replicas", C.c_int32),
                 ("charge", C.c_void_p), ("sigma", C.c_void_p), ("epsilon", C.c_void_p),
                 ("exclusions", C.c_void_p), ("exceptions", C.c_void_p),
-                ("exception_params", C.c_void_p), ("displacement", C.c_void_p)]
+                ("exception_params", C.c_void_p), ("displacement", C.c_void_p),
+                ("ewald_alpha", C.c_double), ("ewald_tolerance", C.c_double)]
 
 
 class SdmOptions(C.Structure):
@@ -129,6 +130,7 @@ SYMBOLS = {
     "sdm_md_update": (_I, [_VP, _VP]),
     "sdm_md_set_noise": (_I, [_VP, _VP]),
     "sdm_md_kinetic_energy": (_I, [_VP, _I, C.POINTER(_D)]),
+    "sdm_set_external_dual": (_I, [_VP, _I, _VP, _VP, _D, _D]),
     "sdm_add_centroid_restraint": (_I, [_VP, C.POINTER(SdmCentroidRestraint)]),
     "sdm_add_alignment_restraint": (_I, [_VP, C.POINTER(SdmAlignmentRestraint)]),
     "sdm_clear_restraints": (_I, [_VP]),

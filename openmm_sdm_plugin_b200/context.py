@@ -84,6 +84,8 @@ class SDMContext:
         s.n_exclusions = len(keep[3])
         s.n_exceptions = len(keep[4])
         s.n_replicas = self.R
+        s.ewald_alpha = float(getattr(system, "ewald_alpha", 0.0))
+        s.ewald_tolerance = float(getattr(system, "ewald_tolerance", 0.0))
         (s.charge, s.sigma, s.epsilon, s.exclusions, s.exceptions, s.exception_params,
          s.displacement) = [_ptr(a) for a in keep]
         o = _lib.SdmOptions()
@@ -294,6 +296,18 @@ class SDMContext:
         v = C.c_double()
         _lib.check(self._L.sdm_md_kinetic_energy(self._h, replica, C.byref(v)))
         return v.value
+
+    def set_external_dual(self, replica: int, f1_ext=None, f2_ext=None, e1_ext: float = 0.0, e2_ext: float = 0.0):
+        """Energies and forces of both states computed outside the library (reciprocal-space PME, GB ...):
+        E1 += e1, u += e2 - e1, F1 += f1, F2 - F1 += f2 - f1.  None removes them."""
+        if f1_ext is None:
+            _lib.check(self._L.sdm_set_external_dual(self._h, replica, None, None, 0.0, 0.0))
+            return
+        a = np.ascontiguousarray(f1_ext, dtype=np.float64)
+        b = np.ascontiguousarray(f2_ext, dtype=np.float64)
+        if a.shape != (self.n, 3) or b.shape != (self.n, 3):
+            raise ValueError("external forces must be [n_atoms, 3]")
+        _lib.check(self._L.sdm_set_external_dual(self._h, replica, _ptr(a), _ptr(b), float(e1_ext), float(e2_ext)))
 
     # ---- restraint forces of SDMUtils (python/SDMUtils.py:32-258); kJ/mol, nm, radians ------------------
     def add_centroid_restraint(self, lig_cm_atoms, rcpt_cm_atoms, kfcm, tolcm, offset=(0.0, 0.0, 0.0),

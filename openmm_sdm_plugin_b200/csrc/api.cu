@@ -194,9 +194,14 @@ void sdm_default_alch(sdm_alch* a) {
     a->step_size = 0.001;
 }
 
-int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
-    if (!s || !out) return fail(SDM_ERR_INVALID, "null argument");
+int sdm_create(const sdm_system* s_in, const sdm_options* opt_in, sdm_ctx** out) {
+    if (!s_in || !out) return fail(SDM_ERR_INVALID, "null argument");
     *out = nullptr;
+    // SDM_EWALD / SDM_PME: a periodic cutoff system whose Coulomb term is the direct-space Ewald one
+    sdm_system sys_ = *s_in;
+    const bool ewald = sys_.method == SDM_EWALD || sys_.method == SDM_PME;
+    if (ewald) sys_.method = SDM_CUTOFF_PERIODIC;
+    const sdm_system* s = &sys_;
     if (s->n_atoms <= 0) return fail(SDM_ERR_INVALID, "n_atoms must be positive");
     if (s->n_replicas < 1) return fail(SDM_ERR_INVALID, "n_replicas must be >= 1");
     if (!s->charge || !s->sigma || !s->epsilon) return fail(SDM_ERR_INVALID, "null parameter array");
@@ -271,6 +276,14 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
         T.inv_boxf[d] = (float)T.inv_box[d];
     }
     if (s->method == SDM_CUTOFF_PERIODIC) cmax = std::max({T.box[0], T.box[1], T.box[2]});
+    if (ewald) {
+        // NonbondedForceImpl::calcPMEParameters / calcEwaldParameters: alpha = sqrt(-log(2 tol)) / cutoff
+        const double tol = s->ewald_tolerance > 0 ? s->ewald_tolerance : 5e-4;
+        T.ewald = 1;
+        T.alpha = s->ewald_alpha > 0 ? s->ewald_alpha : std::sqrt(-std::log(2.0 * tol)) / T.rc;
+        T.alphaf = (float)T.alpha;
+        T.krf = T.crf = 0.0;
+    }
     T.rc2f = (float)T.rc2;
     T.krff = (float)T.krf;
     T.crff = (float)T.crf;
@@ -312,6 +325,15 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
         }
         TRY(dev_upload(c, &T.excl_start, start));
         TRY(dev_upload(c, &T.excl_idx, idx));
+        if (ewald) {   // the unique excluded pairs (i < j): each gets the erf(alpha r)/r correction once
+            std::vector<int> pairs;
+            for (int i = 0; i < n; i++)
+                for (int j : rows[i])
+                    if (j > i) { pairs.push_back(i); pairs.push_back(j); }
+            T.n_excl_pairs = (int)(pairs.size() / 2);
+            if (pairs.empty()) pairs.assign(2, 0);
+            TRY(dev_upload(c, &T.excl_pairs, pairs));
+        }
         c->h_excl_start = start;
         c->h_excl_idx = idx;
     }
@@ -338,7 +360,7 @@ int sdm_create(const sdm_system* s, const sdm_options* opt_in, sdm_ctx** out) {
     std::memset(&B, 0, sizeof(B));
     B.R = R;
     B.n_epart_allpairs = sdm::allpairs_num_blocks(n);
-    B.n_excpart = sdm::exceptions_num_blocks(s->n_exceptions);
+    B.n_excpart = sdm::exceptions_num_blocks(s->n_exceptions + (T.ewald ? T.n_excl_pairs : 0));
     B.nslot = n;
     B.acc_rstride = 3 * (size_t)n;
     B.slot_of = nullptr;
@@ -642,6 +664,42 @@ static int push_group(sdm_ctx* c, sdm::RestraintTerm& t, int k, int count, const
         c->h_rweights.push_back((weights ? weights[i] : 1.0) / sum);
     }
     t.grp_begin[k + 1] = (int)c->h_ratoms.size();
+    return SDM_OK;
+}
+
+int sdm_set_external_dual(sdm_ctx* c, int replica, const double* f1_ext, const double* f2_ext, double e1_ext,
+                          double e2_ext) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (replica < 0 || replica >= c->R) return fail(SDM_ERR_INVALID, "replica out of range");
+    if ((f1_ext == nullptr) != (f2_ext == nullptr)) return fail(SDM_ERR_INVALID, "give both force arrays or neither");
+    const size_t n3 = 3 * (size_t)c->n;
+    if (!c->d_ext_f1) {
+        if (!f1_ext) return SDM_OK;   // nothing to remove
+        void *a = nullptr, *b = nullptr, *e = nullptr, *on = nullptr;
+        SDM_CUDA(cudaMalloc(&a, sizeof(double) * n3 * c->R));
+        SDM_CUDA(cudaMalloc(&b, sizeof(double) * n3 * c->R));
+        SDM_CUDA(cudaMalloc(&e, sizeof(double) * 2 * c->R));
+        SDM_CUDA(cudaMalloc(&on, sizeof(int) * c->R));
+        SDM_CUDA(cudaMemset(a, 0, sizeof(double) * n3 * c->R));
+        SDM_CUDA(cudaMemset(b, 0, sizeof(double) * n3 * c->R));
+        SDM_CUDA(cudaMemset(e, 0, sizeof(double) * 2 * c->R));
+        SDM_CUDA(cudaMemset(on, 0, sizeof(int) * c->R));
+        c->allocs.push_back(a); c->allocs.push_back(b); c->allocs.push_back(e); c->allocs.push_back(on);
+        c->d_ext_f1 = (double*)a; c->d_ext_f2 = (double*)b; c->d_ext_e = (double*)e; c->d_ext_on = (int*)on;
+        c->B.ext_f1 = c->d_ext_f1; c->B.ext_f2 = c->d_ext_f2; c->B.ext_e = c->d_ext_e; c->B.ext_on = c->d_ext_on;
+        c->graph_valid = false;   // kernel arguments of the captured sequence changed
+    }
+    // staged through the stream (pageable host memory: the copies return when the data has been taken)
+    const double e[2] = {f1_ext ? e1_ext : 0.0, f1_ext ? e2_ext : 0.0};
+    const int on = f1_ext ? 1 : 0;
+    if (f1_ext) {
+        SDM_CUDA(cudaMemcpyAsync(c->d_ext_f1 + n3 * replica, f1_ext, sizeof(double) * n3, cudaMemcpyHostToDevice, c->stream));
+        SDM_CUDA(cudaMemcpyAsync(c->d_ext_f2 + n3 * replica, f2_ext, sizeof(double) * n3, cudaMemcpyHostToDevice, c->stream));
+    }
+    SDM_CUDA(cudaMemcpyAsync(c->d_ext_e + 2 * replica, e, sizeof(e), cudaMemcpyHostToDevice, c->stream));
+    SDM_CUDA(cudaMemcpyAsync(c->d_ext_on + replica, &on, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
     return SDM_OK;
 }
 

@@ -147,7 +147,14 @@ allpairs_kernel(Topology T, const float4* __restrict__ posq_all, const double* _
                 const float qq = pi.w * pj.w;
                 float dEdR = eps * (12.f * sr6 - 6.f) * sr6;
                 float e = eps * (sr6 - 1.f) * sr6;
-                if (METHOD != SDM_NOCUTOFF) {
+                if (METHOD == SDM_CUTOFF_PERIODIC && T.ewald) {   // direct-space Ewald (A&S 7.1.26 erfc, like the row kernel)
+                    const float ar = T.alphaf * (r2 * rinv);
+                    const float expo = __expf(-ar * ar);
+                    const float t = 1.f / (1.f + 0.3275911f * ar);
+                    const float ec = ((((1.061405429f * t - 1.453152027f) * t + 1.421413741f) * t - 0.284496736f) * t + 0.254829592f) * t * expo;
+                    dEdR += qq * rinv * (ec + 1.1283791670955126f * ar * expo);
+                    e += qq * rinv * ec;
+                } else if (METHOD != SDM_NOCUTOFF) {
                     dEdR += qq * (rinv - 2.f * T.krff * r2);
                     e += qq * (rinv + T.krff * r2 - T.crff);
                 } else {
@@ -396,14 +403,14 @@ __device__ __forceinline__ void probe_pair(const Topology& T, const double* __re
     const int wc = (gk != 0) ? 1 : 2;
     if (in1) {
         double e;
-        double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+        double fs = pair_term_f64(g1.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e, T.ewald ? T.alpha : 0.0);
         px -= fs * g1.dx; py -= fs * g1.dy; pz -= fs * g1.dz;
         A.u -= w * e;
         A.c1 += wc;
     }
     if (in2) {
         double e;
-        double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e);
+        double fs = pair_term_f64(g2.r2, sig, eps, qq, cutoff, T.krf, T.crf, &e, T.ewald ? T.alpha : 0.0);
         px += fs * g2.dx; py += fs * g2.dy; pz += fs * g2.dz;
         A.u += w * e;
         A.c2 += wc;
@@ -778,6 +785,21 @@ __device__ __forceinline__ double exc_term(double dx, double dy, double dz, doub
     return dEdR;
 }
 
+// -qq*erf(alpha r)/r of an excluded pair (energy returned, *fs: F_a += fs*d, F_b -= fs*d); for r -> 0 the
+// limit -qq*2*alpha/sqrt(pi) without a force, as OpenMM does when erf(alpha r) <= 1e-6.
+__device__ __forceinline__ double ewald_exclusion_term(double r2, double qq, double alpha, double* fs) {
+    const double r = sqrt(r2);
+    const double alphaR = alpha * r;
+    const double ef = erf(alphaR);
+    if (ef > 1e-6) {
+        const double inverseR = 1.0 / r;
+        *fs = -qq * inverseR * inverseR * inverseR * (ef - alphaR * exp(-alphaR * alphaR) * 1.1283791670955126);
+        return -qq * inverseR * ef;
+    }
+    *fs = 0.0;
+    return -alpha * 1.1283791670955126 * qq;
+}
+
 __global__ void __launch_bounds__(128)
 exceptions_kernel(Topology T, const double* __restrict__ pos_all, long long* __restrict__ f1acc,
                   size_t acc_rstride, int nslot, const int* __restrict__ slot_of, double* __restrict__ dF_all,
@@ -820,6 +842,41 @@ exceptions_kernel(Topology T, const double* __restrict__ pos_all, long long* __r
                 atomicAdd(dF + 3 * b + 2, -(fs2 * dz2 - fs * dz));
                 du = e2 - e1;
             }
+        }
+    }
+    // Direct-space Ewald: the excluded pairs were implicitly included in the reciprocal-space sum, their
+    // erf(alpha r)/r part is taken out here (OpenMM 7.3 ReferenceLJCoulombIxn::calculateEwaldIxn, "subtract
+    // off the exclusions"): items n_exceptions .. n_exceptions + n_excl_pairs - 1 of this kernel.
+    const int kx = k - T.n_exceptions;
+    if (T.ewald && kx >= 0 && kx < T.n_excl_pairs) {
+        const int a = T.excl_pairs[2 * kx], b = T.excl_pairs[2 * kx + 1];
+        const double qq = SDM_K_COULOMB * T.q[a] * T.q[b];
+        const PairGeom g = geom(T, pos[3 * a], pos[3 * a + 1], pos[3 * a + 2], pos[3 * b], pos[3 * b + 1], pos[3 * b + 2]);
+        double fs;
+        e1 = ewald_exclusion_term(g.r2, qq, T.alpha, &fs);
+        long long* acc = f1acc + (size_t)r * acc_rstride;
+        const int sa = slot_of ? slot_of[(size_t)r * n + a] : a;
+        const int sb = slot_of ? slot_of[(size_t)r * n + b] : b;
+        atomic_add_fixed(acc + sa, to_fixed(fs * g.dx));
+        atomic_add_fixed(acc + nslot + sa, to_fixed(fs * g.dy));
+        atomic_add_fixed(acc + 2 * nslot + sa, to_fixed(fs * g.dz));
+        atomic_add_fixed(acc + sb, to_fixed(-fs * g.dx));
+        atomic_add_fixed(acc + nslot + sb, to_fixed(-fs * g.dy));
+        atomic_add_fixed(acc + 2 * nslot + sb, to_fixed(-fs * g.dz));
+        if (T.group[a] != T.group[b]) {   // an excluded pair with different displacements: state 2 differs
+            const PairGeom g2 = geom(T, pos[3 * a] + T.disp[3 * a], pos[3 * a + 1] + T.disp[3 * a + 1],
+                                     pos[3 * a + 2] + T.disp[3 * a + 2], pos[3 * b] + T.disp[3 * b],
+                                     pos[3 * b + 1] + T.disp[3 * b + 1], pos[3 * b + 2] + T.disp[3 * b + 2]);
+            double fs2;
+            const double e2 = ewald_exclusion_term(g2.r2, qq, T.alpha, &fs2);
+            double* dF = dF_all + (size_t)r * 3 * n;
+            atomicAdd(dF + 3 * a, fs2 * g2.dx - fs * g.dx);
+            atomicAdd(dF + 3 * a + 1, fs2 * g2.dy - fs * g.dy);
+            atomicAdd(dF + 3 * a + 2, fs2 * g2.dz - fs * g.dz);
+            atomicAdd(dF + 3 * b, -(fs2 * g2.dx - fs * g.dx));
+            atomicAdd(dF + 3 * b + 1, -(fs2 * g2.dy - fs * g.dy));
+            atomicAdd(dF + 3 * b + 2, -(fs2 * g2.dz - fs * g.dz));
+            du = e2 - e1;
         }
     }
     double se = block_sum(e1, s_red);
@@ -890,6 +947,10 @@ scalars_kernel(Topology T, EvalBuffers B, double e_scale, int c_div) {
         sc->E1_disp = T.e_disp;
         sc->E1 = sc->E1_pair + sc->E1_exc + sc->E1_disp;
         sc->u = ul + ue;
+        if (B.ext_e) {   // contributions computed outside the library (sdm_set_external_dual)
+            sc->E1 += B.ext_e[2 * r];
+            sc->u += B.ext_e[2 * r + 1] - B.ext_e[2 * r];
+        }
         sc->E2 = sc->E1 + sc->u;
         sc->n_pairs1 = c / c_div;
         sc->n_moved1 = m1 / 2;
@@ -918,8 +979,14 @@ mix_kernel(Topology T, EvalBuffers B, int zero_acc) {
     const size_t o = (size_t)r * 3 * n + 3 * (size_t)i;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const double f1 = (double)acc[(size_t)c * B.nslot + slot] * SDM_INV_FORCE_SCALE;
-        const double f = f1 + sp * B.dF[o + c] + B.fb[o + c];
+        double f1 = (double)acc[(size_t)c * B.nslot + slot] * SDM_INV_FORCE_SCALE;
+        double d = B.dF[o + c];
+        if (B.ext_f1 && B.ext_on[r]) {   // external dual-state term: F1 += F1_ext, F2 - F1 += F2_ext - F1_ext
+            f1 += B.ext_f1[o + c];
+            d += B.ext_f2[o + c] - B.ext_f1[o + c];
+            B.dF[o + c] = d;   // F2 - F1 as sdm_get_forces reports it (rewritten by the next evaluation)
+        }
+        const double f = f1 + sp * d + B.fb[o + c];
         B.F1[o + c] = f1;
         B.F[o + c] = f;
         if (zero_acc) acc[(size_t)c * B.nslot + slot] = 0;
@@ -986,7 +1053,7 @@ void launch_ligand_probe_list(const Topology& T, const EvalBuffers& B, cudaStrea
 }
 
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
-    dim3 grid(exceptions_num_blocks(T.n_exceptions), B.R);
+    dim3 grid(exceptions_num_blocks(T.n_exceptions + (T.ewald ? T.n_excl_pairs : 0)), B.R);
     exceptions_kernel<<<grid, 128, 0, s>>>(T, B.pos, B.f1acc, B.acc_rstride, B.nslot, B.slot_of, B.dF, B.eexc_part, B.uexc_part, B.n_excpart);
 }
 

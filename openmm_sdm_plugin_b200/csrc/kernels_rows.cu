@@ -120,7 +120,41 @@ __device__ __forceinline__ void load_jrec(const float4* __restrict__ jrec, const
 
 struct PairConsts {
     float rc2, krf, crf, band;
+    float alpha;   // Ewald splitting parameter (EWALD instantiations)
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// erfc(x) for x >= 0 by Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7; the polynomial OpenMM's GPU platforms
+// use for the direct-space Ewald term): returns erfc, and exp(-x^2) through `expo`.
+constexpr float kErfcP = 0.3275911f, kErfcA1 = 0.254829592f, kErfcA2 = -0.284496736f, kErfcA3 = 1.421413741f,
+                kErfcA4 = -1.453152027f, kErfcA5 = 1.061405429f, kLog2e = 1.4426950408889634f,
+                kTwoOverSqrtPi = 1.1283791670955126f;
+__device__ __forceinline__ float erfc_approx(const float x, float& expo) {
+    expo = ex2_approx(-kLog2e * x * x);
+    const float t = rcp_approx(fmaf(kErfcP, x, 1.f));
+    return ((((kErfcA5 * t + kErfcA4) * t + kErfcA3) * t + kErfcA2) * t + kErfcA1) * t * expo;
+}
+__device__ __forceinline__ f2 erfc_approx2(const f2 x, f2& expo) {
+    const f2 a = mul2(mul2(x, x), bc(-kLog2e));
+    expo = pk(ex2_approx(lo(a)), ex2_approx(hi(a)));
+    const f2 d = fma2(x, bc(kErfcP), bc(1.f));
+    const f2 t = pk(rcp_approx(lo(d)), rcp_approx(hi(d)));
+    f2 p = fma2(bc(kErfcA5), t, bc(kErfcA4));
+    p = fma2(p, t, bc(kErfcA3));
+    p = fma2(p, t, bc(kErfcA2));
+    p = fma2(p, t, bc(kErfcA1));
+    return mul2(mul2(p, t), expo);
+}
 
 // Debug build of the hot kernel (template flag EMIT): every pair the kernel ACCEPTS -- in the tile
 // loop and in the band fix-up -- is also recorded with its System indices, so
@@ -153,9 +187,17 @@ __device__ __forceinline__ float pair_term_f32(const float r2, const float qi, c
     const float sr6 = sr2 * sr2 * sr2;
     const float elj = (ei * pj.y) * sr6;
     const float qq = qi * qj;
-    const float kr2 = K.krf * r2;
     const float a = elj * sr6;
     const float e_lj = a - elj;
+    if (K.alpha > 0.f) {   // direct-space Ewald (EWALD instantiations set alpha)
+        float expo;
+        const float ar = K.alpha * (r2 * rinv);
+        const float ec = erfc_approx(ar, expo);
+        const float qr = qq * rinv;
+        e = fmaf(qr, ec, e_lj);
+        return fmaf(a + e_lj, 6.f, qr * fmaf(ar * expo, kTwoOverSqrtPi, ec)) * rinv2;
+    }
+    const float kr2 = K.krf * r2;
     const float dEdR = fmaf(a + e_lj, 6.f, qq * fmaf(-2.f, kr2, rinv));
     e = fmaf(qq, (rinv + kr2) - K.crf, e_lj);
     return dEdR * rinv2;
@@ -166,7 +208,7 @@ __device__ __forceinline__ float pair_term_f32(const float r2, const float qi, c
 //   e_lj = elj*(sr6 - 1) = a - elj,   elj*(12*sr6 - 6) = 6*(a + e_lj)   with a = elj*sr6
 // LJ = false: the j-atom has no Lennard-Jones term (epsilon_j == 0: elj, a and e_lj are exactly
 // zero), so the eleven packed instructions that would compute them are left out -- same bits out.
-template <bool MASKED, bool EXACT, bool EMIT, int HI_OFF, bool LJ = true>
+template <bool MASKED, bool EXACT, bool EMIT, int HI_OFF, bool LJ = true, bool EWALD = false>
 __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const float4 xj,
                                           const float2 pj, const bool allow_lo, const bool allow_hi,
                                           const PairConsts& K, Acc2& fi, Acc2& fj, f2& en, int& cnt,
@@ -191,7 +233,21 @@ __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const fl
     const f2 rinv = pk(rsqrt_approx(lo(r2)), rsqrt_approx(hi(r2)));
     const f2 rinv2 = mul2(rinv, rinv);
     const f2 qq = mul2(a1.y, bc(xj.w));
-    const f2 kr2 = mul2(r2, bc(K.krf));
+    // Coulomb part: (ce, cd) = energy and dE/dr*r per unit charge product -- reaction field
+    // (rinv + krf r^2 - crf, rinv - 2 krf r^2) or direct-space Ewald (erfc(alpha r)/r,
+    // (erfc(alpha r) + 2 alpha r exp(-alpha^2 r^2)/sqrt(pi))/r)
+    f2 ce, cd;
+    if (EWALD) {
+        f2 expo;
+        const f2 ar = mul2(mul2(r2, rinv), bc(K.alpha));
+        const f2 ec = erfc_approx2(ar, expo);
+        ce = mul2(rinv, ec);
+        cd = mul2(rinv, fma2(mul2(ar, expo), bc(kTwoOverSqrtPi), ec));
+    } else {
+        const f2 kr2 = mul2(r2, bc(K.krf));
+        ce = sub2(add2(rinv, kr2), bc(K.crf));
+        cd = fma2(kr2, bc(-2.f), rinv);
+    }
     f2 dEdR, e;
     if (LJ) {
         const f2 sig = add2(a2.x, bc(pj.x));
@@ -200,11 +256,11 @@ __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const fl
         const f2 elj = mul2(mul2(a2.y, bc(pj.y)), sr6);
         const f2 a = mul2(elj, sr6);
         const f2 e_lj = sub2(a, elj);
-        dEdR = fma2(add2(a, e_lj), bc(6.f), mul2(qq, fma2(kr2, bc(-2.f), rinv)));
-        e = fma2(qq, sub2(add2(rinv, kr2), bc(K.crf)), e_lj);
+        dEdR = fma2(add2(a, e_lj), bc(6.f), mul2(qq, cd));
+        e = fma2(qq, ce, e_lj);
     } else {
-        dEdR = mul2(qq, fma2(kr2, bc(-2.f), rinv));
-        e = mul2(qq, sub2(add2(rinv, kr2), bc(K.crf)));
+        dEdR = mul2(qq, cd);
+        e = mul2(qq, ce);
     }
     const f2 fsr = mul2(dEdR, rinv2);
 #if SDM_PAIR_SEL2
@@ -250,14 +306,14 @@ __device__ __forceinline__ void red_fixed_nonzero(long long* p, const float f, c
 // re-decided with the FP64 in-cutoff test of the oracle; where that differs from the FP32 decision
 // of the hot loop the pair's force / energy / count is added or taken back (forces straight to the
 // fixed-point accumulators of both atoms).  Out of line so that the hot loop stays small.
-template <int NI, bool EMIT>
+template <int NI, bool EMIT, bool EWALD>
 __device__ __noinline__ void fix_band_row(const Topology& T, const PairListView& V,
                                           const double* __restrict__ pos_all,
                                           long long* __restrict__ f1acc, const IPair* s_ip, int ibase,
                                           int jslot, float4 xj, float2 pj, uint32_t allow, float* en,
                                           int* cnt, const EmitCtx* ec) {
     const size_t plane = (size_t)V.nslot_cap;
-    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band, EWALD ? T.alphaf : 0.f};
     const int aj = V.atom[jslot];
     if (aj < 0) return;
     for (int a = 0; a < NI; a++) {
@@ -306,7 +362,7 @@ __device__ __forceinline__ void row_halve(float (&v)[N], const int lane) {
     }
 }
 
-template <int NI, bool PERIODIC, bool EXACT, bool EMIT>
+template <int NI, bool PERIODIC, bool EXACT, bool EMIT, bool EWALD>
 __device__ __forceinline__ void process_row_unit(const Topology& T, const PairListView& V,
                                                  const double* __restrict__ pos_all,
                                                  long long* __restrict__ f1acc, double* __restrict__ epart,
@@ -316,7 +372,7 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
     constexpr int NP = NI / 2;
     const int ibase = (u.c0n & 0xfffffff) * nbl::kClusterSize;
     const int ni = (u.c0n >> 28) * nbl::kClusterSize;
-    const PairConsts K{T.rc2f, T.krff, T.crff, T.band};
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band, EWALD ? T.alphaf : 0.f};
     const uint32_t dummy_ent = (uint32_t)V.dummy_slot | (nbl::kShiftZero << 26);
 
     // row entries two steps ahead, j-atom data one step ahead
@@ -397,18 +453,18 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
             const uint32_t allow = idx < mend ? (uint32_t)V.jallow[idx] : 0xffffu;
 #pragma unroll
             for (int p = 0; p < NP; p++)
-                tile_step<true, EXACT, EMIT, 1>(s_ip + p, xj, pj, ((allow >> (2 * p)) & 1u) != 0u,
+                tile_step<true, EXACT, EMIT, 1, true, EWALD>(s_ip + p, xj, pj, ((allow >> (2 * p)) & 1u) != 0u,
                                                 ((allow >> (2 * p + 1)) & 1u) != 0u, K, fi[p], fj, en, cnt,
                                                 tmin, ec, ibase + 2 * p, jslot);
         } else if (k < lsteps) {
 #pragma unroll
             for (int p = 0; p < NP; p++)
-                tile_step<false, EXACT, EMIT, 1>(s_ip + p, xj, pj, true, true, K, fi[p], fj, en, cnt, tmin, ec,
+                tile_step<false, EXACT, EMIT, 1, true, EWALD>(s_ip + p, xj, pj, true, true, K, fi[p], fj, en, cnt, tmin, ec,
                                                  ibase + 2 * p, jslot);
         } else {   // the tail of the row: j-atoms without a Lennard-Jones term (water hydrogens)
 #pragma unroll
             for (int p = 0; p < NP; p++)
-                tile_step<false, EXACT, EMIT, 1, false>(s_ip + p, xj, pj, true, true, K, fi[p], fj, en, cnt, tmin,
+                tile_step<false, EXACT, EMIT, 1, false, EWALD>(s_ip + p, xj, pj, true, true, K, fi[p], fj, en, cnt, tmin,
                                                         ec, ibase + 2 * p, jslot);
         }
         if (EXACT) fixmask |= (tmin < K.band ? 1u : 0u) << k;
@@ -501,7 +557,7 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
                 xj.x += sh.x; xj.y += sh.y; xj.z += sh.z;
             }
             const uint32_t allow = id < mend ? (uint32_t)V.jallow[id] : 0xffffu;
-            fix_band_row<NI, EMIT>(T, V, pos_all, f1acc, s_ip, ibase, js, xj, pjf, allow, &en_fix, &cnt_fix, ec);
+            fix_band_row<NI, EMIT, EWALD>(T, V, pos_all, f1acc, s_ip, ibase, js, xj, pjf, allow, &en_fix, &cnt_fix, ec);
         }
         en1 += en_fix;
         cnt += cnt_fix;
@@ -523,7 +579,7 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
     __syncwarp();   // the staging area is reused by the next unit of this warp
 }
 
-template <int NI, bool PERIODIC, bool EXACT, bool EMIT>
+template <int NI, bool PERIODIC, bool EXACT, bool EMIT, bool EWALD = false>
 __global__ void __launch_bounds__(kWarps * 32, NI == 16 ? 16 : SDM_ROW_MINB)
 pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
                 const double* __restrict__ pos_all, long long* __restrict__ f1acc,
@@ -554,7 +610,7 @@ pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ Pair
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= nrunits) break;
         if (V.runit_order) unit = V.runit_order[unit];   // longest units first
-        process_row_unit<NI, PERIODIC, EXACT, EMIT>(T, V, pos_all, f1acc, epart, cpart, unit, V.runits[unit], lane,
+        process_row_unit<NI, PERIODIC, EXACT, EMIT, EWALD>(T, V, pos_all, f1acc, epart, cpart, unit, V.runits[unit], lane,
                                                     s_ip[warp], s_shift, ec);
     }
 }
@@ -619,34 +675,38 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
     if (emit) cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
     const PairEmit em = emit ? *emit : PairEmit{nullptr, nullptr, 0, -1};
-#define SDM_LAUNCH(N, P, X, E)                                                                    \
+#define SDM_LAUNCH(N, P, X, E, W)                                                                 \
     do {                                                                                          \
         static int resident = 0; /* blocks per SM the hardware keeps resident (register limited) */ \
         if (!resident) {                                                                          \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_row_kernel<N, P, X, E>, \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_row_kernel<N, P, X, E, W>, \
                                                               kWarps * 32, 0) != cudaSuccess ||    \
                 resident < 1)                                                                     \
                 resident = SDM_ROW_MINB;                                                          \
             if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
         }                                                                                         \
         const int grid = std::min((V.nrunits_ub + kWarps - 1) / kWarps, num_sms * resident);       \
-        pair_row_kernel<N, P, X, E><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
-                                                                unit_counter, em);                \
+        pair_row_kernel<N, P, X, E, W><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
+                                                                   unit_counter, em);             \
     } while (0)
-#define SDM_LAUNCH_N(P, X, E)                                                                     \
+#define SDM_LAUNCH_N(P, X, E, W)                                                                  \
     do {                                                                                          \
-        if (V.row_group == 2) SDM_LAUNCH(16, P, X, E);                                            \
-        else SDM_LAUNCH(8, P, X, E);                                                              \
+        if (V.row_group == 2) SDM_LAUNCH(16, P, X, E, W);                                         \
+        else SDM_LAUNCH(8, P, X, E, W);                                                           \
     } while (0)
-    if (emit) {   // debug build of the same kernel: records the accepted pairs
-        if (exact) { if (periodic) SDM_LAUNCH_N(true, true, true); else SDM_LAUNCH_N(false, true, true); }
-        else { if (periodic) SDM_LAUNCH_N(true, false, true); else SDM_LAUNCH_N(false, false, true); }
+    if (T.ewald) {   // direct-space Ewald / PME: periodic by definition
+        if (emit) { if (exact) SDM_LAUNCH_N(true, true, true, true); else SDM_LAUNCH_N(true, false, true, true); }
+        else if (exact) SDM_LAUNCH_N(true, true, false, true);
+        else SDM_LAUNCH_N(true, false, false, true);
+    } else if (emit) {   // debug build of the same kernel: records the accepted pairs
+        if (exact) { if (periodic) SDM_LAUNCH_N(true, true, true, false); else SDM_LAUNCH_N(false, true, true, false); }
+        else { if (periodic) SDM_LAUNCH_N(true, false, true, false); else SDM_LAUNCH_N(false, false, true, false); }
     } else if (exact) {
-        if (periodic) SDM_LAUNCH_N(true, true, false);
-        else SDM_LAUNCH_N(false, true, false);
+        if (periodic) SDM_LAUNCH_N(true, true, false, false);
+        else SDM_LAUNCH_N(false, true, false, false);
     } else {
-        if (periodic) SDM_LAUNCH_N(true, false, false);
-        else SDM_LAUNCH_N(false, false, false);
+        if (periodic) SDM_LAUNCH_N(true, false, false, false);
+        else SDM_LAUNCH_N(false, false, false, false);
     }
 #undef SDM_LAUNCH_N
 #undef SDM_LAUNCH

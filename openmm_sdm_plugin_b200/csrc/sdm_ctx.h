@@ -80,6 +80,10 @@ struct sdm_ctx {
     double md_dt = 0, md_vscale = 0, md_fscale = 0, md_noisescale = 0;
     unsigned long long md_seed = 0, md_steps = 0;
 
+    // external dual-state contributions (sdm_set_external_dual): reciprocal-space PME, GB, ...
+    double *d_ext_f1 = nullptr, *d_ext_f2 = nullptr, *d_ext_e = nullptr;
+    int* d_ext_on = nullptr;
+
     // restraint forces of SDMUtils (sdm_add_centroid_restraint / sdm_add_alignment_restraint)
     std::vector<sdm::RestraintTerm> h_rterms;
     std::vector<int> h_ratoms;

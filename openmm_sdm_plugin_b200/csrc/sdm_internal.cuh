@@ -25,6 +25,11 @@ struct Topology {
     float rc2f, krff, crff, band;      // band: |r2-rc2| below which the FP64 re-test runs
     float boxf[3], inv_boxf[3];
     double e_disp;                      // dispersion correction energy (coefficient / volume)
+    int ewald;                          // 1: SDM_EWALD / SDM_PME -- direct-space Ewald Coulomb instead of the reaction field
+    double alpha;                       // Ewald splitting parameter (1/nm)
+    float alphaf;
+    int n_excl_pairs;                   // excluded pairs (i < j) that get the erf(alpha r)/r correction
+    const int* excl_pairs;              // [2*n_excl_pairs]
     const double* q;       // [n] charge
     const double* hsig;    // [n] sigma/2
     const double* heps;    // [n] 2*sqrt(eps)
@@ -139,15 +144,23 @@ __host__ __device__ inline void execute_scalars(sdm_alch* al, sdm_scalars* sc) {
 // ReferenceLJCoulombIxn::calculateOneIxn.  d = x_i - x_j.
 // Returns dEdR/r^2-scaled factor so that F_i += fs*d, F_j -= fs*d; *e is the pair energy.
 // ---------------------------------------------------------------------------------------------
+// alpha > 0: direct-space Ewald Coulomb (OpenMM 7.3 ReferenceLJCoulombIxn::calculateEwaldIxn, the
+// "SHORT-RANGE ENERGY AND FORCES" loop): qq*erfc(alpha r)/r, dE/dr*r = qq*(erfc(alpha r) + 2 alpha r
+// exp(-alpha^2 r^2)/sqrt(pi))/r.
 __device__ __forceinline__ double pair_term_f64(double r2, double sig, double eps, double qq,
-                                                bool cutoff, double krf, double crf, double* e) {
+                                                bool cutoff, double krf, double crf, double* e, double alpha = 0.0) {
     double inverseR = rsqrt(r2);  // within 2 ulp of 1/sqrt(r2) and three times cheaper
     double sig2 = inverseR * sig;
     sig2 *= sig2;
     double sig6 = sig2 * sig2 * sig2;
     double dEdR = eps * (12.0 * sig6 - 6.0) * sig6;
     double en = eps * (sig6 - 1.0) * sig6;
-    if (cutoff) {
+    if (alpha > 0.0) {
+        const double alphaR = alpha * r2 * inverseR;
+        const double ec = erfc(alphaR);
+        dEdR += qq * inverseR * (ec + alphaR * exp(-alphaR * alphaR) * 1.1283791670955126);   // 2/sqrt(pi)
+        en += qq * inverseR * ec;
+    } else if (cutoff) {
         dEdR += qq * (inverseR - 2.0 * krf * r2);
         en += qq * (inverseR + krf * r2 - crf);
     } else {

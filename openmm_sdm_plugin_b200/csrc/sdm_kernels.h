@@ -8,6 +8,10 @@ namespace sdm {
 // Device buffers of one context that the per-eval kernels touch.  R = replicas, n = atoms.
 struct EvalBuffers {
     int R;
+    const double* ext_f1;   // [R][3n] external state-1 forces (sdm_set_external_dual) or nullptr
+    const double* ext_f2;   // [R][3n] external state-2 forces
+    const double* ext_e;    // [R][2]  external (E1, E2); zero for a replica without the term
+    const int* ext_on;      // [R]     1: the replica has external forces
     int* work_counter;      // cluster path: unit counter of the persistent pair kernel, set back to zero by the
                             // mix kernel (the last kernel of an evaluation) for the next one; nullptr otherwise
     const double* pos;      // [R][3n]   positions, System order, nm

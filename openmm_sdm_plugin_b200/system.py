@@ -16,6 +16,8 @@ import numpy as np
 NOCUTOFF = 0
 CUTOFF_NONPERIODIC = 1
 CUTOFF_PERIODIC = 2
+EWALD = 3             # NonbondedForce::Ewald / ::PME: the direct-space part (include/sdmb200.h)
+PME = 4
 
 # LangevinIntegratorSDM.h:120-122,143-145 / SDMUtils.py:9-15
 LINEAR, QUADRATIC, ILOGISTIC = 0, 1, 2
@@ -39,6 +41,15 @@ class NonbondedSystem:
     eps_rf: float = 78.3          # NonbondedForce default reaction-field dielectric
     box: np.ndarray = field(default_factory=lambda: np.zeros(3))
     use_dispersion_correction: bool = True
+    ewald_alpha: float = 0.0      # EWALD / PME: 0 = OpenMM's rule sqrt(-log(2 tol)) / cutoff
+    ewald_tolerance: float = 5e-4
+
+    def ewald_alpha_effective(self) -> float:
+        """The splitting parameter the library and the oracle use (NonbondedForceImpl::calcPMEParameters)."""
+        if self.method not in (EWALD, PME):
+            return 0.0
+        tol = self.ewald_tolerance if self.ewald_tolerance > 0 else 5e-4
+        return float(self.ewald_alpha) if self.ewald_alpha > 0 else float(np.sqrt(-np.log(2.0 * tol)) / self.cutoff)
 
     def __post_init__(self):
         self.charge = np.ascontiguousarray(self.charge, dtype=np.float64)

@@ -23,7 +23,7 @@ class OrcSystem(C.Structure):
                 ("n_exceptions", C.c_int32), ("pad_", C.c_int32),
                 ("charge", C.c_void_p), ("sigma", C.c_void_p), ("epsilon", C.c_void_p),
                 ("exclusions", C.c_void_p), ("exceptions", C.c_void_p),
-                ("exception_params", C.c_void_p)]
+                ("exception_params", C.c_void_p), ("ewald_alpha", C.c_double)]
 
 
 class OrcAlch(C.Structure):
@@ -102,7 +102,11 @@ class _Sys:
                      np.ascontiguousarray(s.exception_params, np.float64)]
         c = OrcSystem()
         c.n_atoms = s.n_atoms
-        c.method = int(s.method)
+        # NonbondedForce::Ewald (3) / ::PME (4): a periodic cutoff system whose Coulomb term is the direct-space
+        # Ewald one (sdm_oracle.c: ewald_alpha > 0)
+        ewald = int(s.method) in (3, 4)
+        c.method = 2 if ewald else int(s.method)
+        c.ewald_alpha = float(s.ewald_alpha_effective()) if ewald else 0.0
         c.cutoff = float(s.cutoff)
         c.eps_rf = float(s.eps_rf)
         for d in range(3):

@@ -384,6 +384,13 @@ static int build_neighbor_list(const orc_system* sys, const double* pos, const e
  *   exceptions  -- OpenMM 7.3 ReferenceLJCoulomb14::calculateBondIxn (no cutoff, no RF,
  *                  plain delta).
  *   dispersion  -- + coefficient / volume for CutoffPeriodic.
+ *   Ewald / PME -- sys->ewald_alpha > 0: the direct-space part of OpenMM 7.3
+ *                  ReferenceLJCoulombIxn::calculateEwaldIxn: Coulomb term qq*erfc(alpha r)/r in
+ *                  the pair loop, then "subtract off the exclusions": -qq*erf(alpha r)/r for every
+ *                  excluded pair (minimum image), -qq*2*alpha/sqrt(pi) without a force where
+ *                  erf(alpha r) <= 1e-6.  Reciprocal space and self energy (includeReciprocal)
+ *                  are NOT part of this function; tests/test_oracle.py adds them in numpy to
+ *                  check the split.
  * Call sites in the reference: LangevinIntegratorSDM.cpp:160,168
  * (context->calcForcesAndEnergy(true, true, 4)).
  * ---------------------------------------------------------------------------------- */
@@ -410,6 +417,7 @@ int orc_nonbonded(const orc_system* sys, const double* pos, double* forces,
         return rc;
     }
 
+    const double ewald_alpha = periodic ? sys->ewald_alpha : 0.0;
     double krf = 0, crf = 0;
     if (cutoff) {
         double rcut = sys->cutoff, es = sys->eps_rf;
@@ -455,16 +463,19 @@ int orc_nonbonded(const orc_system* sys, const double* pos, double* forces,
             double eps = heps[ii] * heps[jj];
             double qq = ORC_ONE_4PI_EPS0 * sys->charge[ii] * sys->charge[jj];
             double dEdR = eps * (12.0 * sig6 - 6.0) * sig6;
-            if (cutoff)
-                dEdR += qq * (inverseR - 2.0 * krf * r2);
-            else
-                dEdR += qq * inverseR;
-            dEdR *= inverseR * inverseR;
             double e = eps * (sig6 - 1.0) * sig6;
-            if (cutoff)
+            if (ewald_alpha > 0) {
+                double alphaR = ewald_alpha * r;
+                dEdR += qq * inverseR * (erfc(alphaR) + 2.0 * alphaR * exp(-alphaR * alphaR) / ORC_SQRT_PI);
+                e += qq * inverseR * erfc(alphaR);
+            } else if (cutoff) {
+                dEdR += qq * (inverseR - 2.0 * krf * r2);
                 e += qq * (inverseR + krf * r2 - crf);
-            else
+            } else {
+                dEdR += qq * inverseR;
                 e += qq * inverseR;
+            }
+            dEdR *= inverseR * inverseR;
             for (int k = 0; k < 3; k++) {
                 double fk = dEdR * d[k];
                 f[3 * ii + k] += fk;
@@ -510,6 +521,41 @@ int orc_nonbonded(const orc_system* sys, const double* pos, double* forces,
             forces[3 * b + c] -= fk;
         }
         eexc += eps4 * (sig6 - 1.0) * sig6 + ORC_ONE_4PI_EPS0 * qq * inverseR;
+    }
+
+    /* Ewald: take the erf part of the excluded pairs out again (booked with the exceptions) */
+    if (ewald_alpha > 0 && sys->n_exclusions > 0) {
+        /* every unordered pair once, whatever the input lists: sorted (min, max) keys */
+        int32_t* key = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)sys->n_exclusions);
+        for (int k = 0; k < sys->n_exclusions; k++) {
+            int a = sys->exclusions[2 * k], b = sys->exclusions[2 * k + 1];
+            key[2 * k] = a < b ? a : b;
+            key[2 * k + 1] = a < b ? b : a;
+        }
+        qsort(key, (size_t)sys->n_exclusions, 2 * sizeof(int32_t), cmp_pair);
+        for (int k = 0; k < sys->n_exclusions; k++) {
+            int a = key[2 * k], b = key[2 * k + 1];
+            if (a == b) continue;
+            if (k > 0 && key[2 * k - 2] == a && key[2 * k - 1] == b) continue;
+            double d[3];
+            for (int c = 0; c < 3; c++) d[c] = min_image(pos[3 * a + c] - pos[3 * b + c], sys->box[c]);
+            double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            double alphaR = ewald_alpha * r;
+            double qq = ORC_ONE_4PI_EPS0 * sys->charge[a] * sys->charge[b];
+            if (erf(alphaR) > 1e-6) {
+                double inverseR = 1.0 / r;
+                double dEdR = qq * inverseR * inverseR * inverseR;
+                dEdR = dEdR * (erf(alphaR) - 2.0 * alphaR * exp(-alphaR * alphaR) / ORC_SQRT_PI);
+                for (int c = 0; c < 3; c++) {
+                    forces[3 * a + c] -= dEdR * d[c];
+                    forces[3 * b + c] += dEdR * d[c];
+                }
+                eexc -= qq * inverseR * erf(alphaR);
+            } else {
+                eexc -= ewald_alpha * 2.0 / ORC_SQRT_PI * qq;
+            }
+        }
+        free(key);
     }
 
     double edisp = 0;

@@ -39,6 +39,7 @@ extern "C" {
 #define ORC_CUTOFF_PERIODIC 2
 
 #define ORC_ONE_4PI_EPS0 138.935456
+#define ORC_SQRT_PI 1.7724538509055160273
 
 /* Flat description of what reaches OpenMM's NonbondedForce for force group 2
  * (example/desmonddmsfile75.py:772-850). */
@@ -58,6 +59,9 @@ typedef struct {
     const int32_t* exclusions;   /* [2*n_exclusions] */
     const int32_t* exceptions;   /* [2*n_exceptions] */
     const double* exception_params; /* [3*n_exceptions] chargeProd, sigma, epsilon */
+    double ewald_alpha;          /* > 0 (with ORC_CUTOFF_PERIODIC): NonbondedForce::Ewald / ::PME, DIRECT-SPACE part
+                                    only -- erfc(alpha r)/r pair terms and the erf(alpha r)/r correction of the
+                                    excluded pairs (ReferenceLJCoulombIxn::calculateEwaldIxn, includeDirect) */
 } orc_system;
 
 /* Alchemical / soft-core state held by LangevinIntegratorSDM

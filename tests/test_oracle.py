@@ -222,3 +222,109 @@ def test_u_only_depends_on_moved_pairs():
     assert e2 - e1 == pytest.approx(r["u"], abs=1e-9)
     same = lambda p: (c.displacement[p[:, 0]] == c.displacement[p[:, 1]]).all(axis=1)
     assert (~same(p1)).sum() == 7656 and (moved[p1[:, 0]] | moved[p1[:, 1]]).sum() >= 7656
+
+
+# ---- NonbondedForce::Ewald / ::PME, direct-space part (sdm_oracle.c: ewald_alpha > 0) ----------------------
+def ewald_direct_numpy(system, pos, alpha):
+    """Pair sum qq*erfc(alpha r)/r inside the cutoff + LJ, minus qq*erf(alpha r)/r of the excluded pairs
+    (minimum image) -- ReferenceLJCoulombIxn::calculateEwaldIxn with includeDirect only."""
+    from scipy.special import erf, erfc
+    n = system.n_atoms
+    d = pos[:, None, :] - pos[None, :, :]
+    d -= np.floor(d / system.box + 0.5) * system.box
+    r2 = (d ** 2).sum(-1)
+    iu = np.triu(np.ones((n, n), bool), 1)
+    ex = np.zeros((n, n), bool)
+    for a, b in system.exclusions:
+        ex[min(a, b), max(a, b)] = True
+    inc = iu & ~ex & (r2 <= system.cutoff ** 2)
+    i, j = np.nonzero(inc)
+    r = np.sqrt(r2[i, j])
+    sig = 0.5 * (system.sigma[i] + system.sigma[j])
+    eps = np.sqrt(system.epsilon[i] * system.epsilon[j])
+    qq = K * system.charge[i] * system.charge[j]
+    s6 = (sig / r) ** 6
+    e_pair = (4 * eps * (s6 * s6 - s6) + qq * erfc(alpha * r) / r).sum()
+    dedr = 4 * eps * (12 * s6 * s6 - 6 * s6) + qq * (erfc(alpha * r) + 2 * alpha * r * np.exp(-(alpha * r) ** 2) / np.sqrt(np.pi)) / r
+    f = np.zeros((n, 3))
+    fv = (dedr / r ** 2)[:, None] * d[i, j]
+    np.add.at(f, i, fv)
+    np.add.at(f, j, -fv)
+    i, j = np.nonzero(ex)
+    r = np.sqrt(r2[i, j])
+    qq = K * system.charge[i] * system.charge[j]
+    e_excl = -(qq * erf(alpha * r) / r).sum()
+    dedr = qq * (erf(alpha * r) - 2 * alpha * r * np.exp(-(alpha * r) ** 2) / np.sqrt(np.pi)) / r
+    fv = (dedr / r ** 2)[:, None] * d[i, j]
+    np.add.at(f, i, -fv)
+    np.add.at(f, j, fv)
+    return e_pair, e_excl, f
+
+
+def ewald_reciprocal_numpy(q, pos, box, alpha, kmax):
+    """Reciprocal-space Ewald energy + self energy by the plain structure-factor sum (what OpenMM books under
+    includeReciprocal): (2 pi / V) K sum_k exp(-k^2 / 4 alpha^2) / k^2 |S(k)|^2 - K alpha / sqrt(pi) sum q^2."""
+    V = box.prod()
+    e = 0.0
+    n = [np.arange(-kmax, kmax + 1)] * 3
+    kx, ky, kz = np.meshgrid(*n, indexing="ij")
+    kv = 2 * np.pi * np.stack([kx.ravel() / box[0], ky.ravel() / box[1], kz.ravel() / box[2]], 1)
+    k2 = (kv ** 2).sum(1)
+    keep = k2 > 0
+    kv, k2 = kv[keep], k2[keep]
+    phase = pos @ kv.T
+    sre, sim = (q[:, None] * np.cos(phase)).sum(0), (q[:, None] * np.sin(phase)).sum(0)
+    e = 2 * np.pi / V * K * (np.exp(-k2 / (4 * alpha ** 2)) / k2 * (sre ** 2 + sim ** 2)).sum()
+    return e - K * alpha / np.sqrt(np.pi) * (q ** 2).sum()
+
+
+def small_ewald_case(n_mol=40, seed=4):
+    """Neutral box of rigid three-site molecules (intramolecular exclusions) small enough for numpy."""
+    rng = np.random.default_rng(seed)
+    box = np.array([2.3, 2.5, 2.4])
+    centres = rng.uniform(0, 1, (n_mol, 3)) * box
+    pos = np.concatenate([centres[:, None, :] + rng.normal(scale=0.06, size=(n_mol, 3, 3))], 0).reshape(-1, 3)
+    q = np.tile([-0.834, 0.417, 0.417], n_mol)
+    sig = np.tile([0.315, 0.1, 0.1], n_mol)
+    eps = np.tile([0.636, 0.0, 0.0], n_mol)
+    excl = np.array([[3 * m + a, 3 * m + b] for m in range(n_mol) for a, b in ((0, 1), (0, 2), (1, 2))], np.int32)
+    sysd = S.NonbondedSystem(q, sig, eps, excl, np.zeros((0, 2), np.int32), np.zeros((0, 3)), method=S.PME,
+                             cutoff=1.0, box=box, use_dispersion_correction=False)
+    return sysd, pos
+
+
+def test_ewald_direct_space_matches_numpy():
+    sysd, pos = small_ewald_case()
+    alpha = sysd.ewald_alpha_effective()
+    assert abs(alpha - np.sqrt(-np.log(2 * 5e-4)) / 1.0) < 1e-15          # OpenMM's rule
+    out = O.nonbonded(sysd, pos)
+    e_pair, e_excl, f = ewald_direct_numpy(sysd, pos, alpha)
+    assert abs(out["E_pair"] - e_pair) <= 1e-10 * abs(e_pair)
+    assert abs(out["E_exc"] - e_excl) <= 1e-10 * abs(e_excl)
+    assert np.abs(out["forces"] - f).max() <= 1e-9 * np.abs(f).max()
+
+
+def test_ewald_split_is_independent_of_alpha():
+    """Direct space (oracle) + reciprocal space and self energy (independent numpy structure-factor sum) is the
+    Coulomb energy of the periodic system, whatever the splitting parameter: the erfc pair term and the erf
+    correction of the excluded pairs are the right counterpart of the reciprocal sum."""
+    sysd, pos = small_ewald_case(n_mol=24, seed=7)
+    sysd.epsilon[:] = 0.0                                  # Coulomb only
+    tot = []
+    for alpha in (4.6, 5.4):                               # erfc(alpha * rc) < 1e-10: the cutoff truncates nothing
+        sysd.ewald_alpha = alpha
+        out = O.nonbonded(sysd, pos)
+        rec = ewald_reciprocal_numpy(sysd.charge, pos, sysd.box, alpha, kmax=22)
+        tot.append(out["E_pair"] + out["E_exc"] + rec)
+    assert abs(tot[0] - tot[1]) <= 1e-7 * abs(tot[0]), tot
+
+
+def test_ewald_dual_state_eval_runs_through_the_reference_sequence():
+    """orc_sdm_eval with method = PME: u = E2 - E1 from two full direct-space evaluations."""
+    sysd, pos = small_ewald_case()
+    disp = np.zeros_like(pos)
+    disp[:6] = (0.4, 0.0, 0.0)
+    res = O.sdm_eval(sysd, S.AlchemicalState(lambdac=0.5), disp, pos)
+    e1 = O.nonbonded(sysd, pos)["E"]
+    e2 = O.nonbonded(sysd, pos + disp)["E"]
+    assert abs(res["E1"] - e1) <= 1e-12 * abs(e1) and abs(res["u"] - (e2 - e1)) <= 1e-9 * max(1.0, abs(e2 - e1))
