@@ -29,7 +29,7 @@ import sqlite3
 
 import numpy as np
 
-from .system import (CUTOFF_NONPERIODIC, CUTOFF_PERIODIC, KCAL, NOCUTOFF, NonbondedSystem)
+from .system import (CUTOFF_NONPERIODIC, CUTOFF_PERIODIC, EWALD, KCAL, NOCUTOFF, PME, NonbondedSystem)
 
 ANGSTROM = 0.1  # nm
 
@@ -128,11 +128,12 @@ class DesmondDMSFile(object):
         return np.array([cell[0][0], cell[1][1], cell[2][2]], dtype=np.float64) * ANGSTROM
 
     def createSystem(self, nonbondedMethod=NOCUTOFF, nonbondedCutoff=1.0, reactionFieldDielectric=78.3,
-                     useDispersionCorrection=True) -> NonbondedSystem:
+                     useDispersionCorrection=True, ewaldErrorTolerance=0.0005) -> NonbondedSystem:
         """The force-group-2 content of the reference's createSystem: the NonbondedForce
         particles, exclusions and 1-4 exceptions (desmonddmsfile75.py:772-850), with the cutoff
-        method/distance of :418-426 and the box of :393-396."""
-        if nonbondedMethod not in (NOCUTOFF, CUTOFF_NONPERIODIC, CUTOFF_PERIODIC):
+        method/distance of :418-426 (Ewald and PME included: direct space here, system.py) and the
+        box of :393-396; ewaldErrorTolerance as :426."""
+        if nonbondedMethod not in (NOCUTOFF, CUTOFF_NONPERIODIC, CUTOFF_PERIODIC, EWALD, PME):
             raise ValueError("Illegal value for nonbondedMethod")
         charge, sigma, epsilon, excl, exc_pairs, exc_params = [], [], [], [], [], []
         for conn, tables, off in zip(self._conn, self._tables, self._offset[:-1]):
@@ -164,7 +165,7 @@ class DesmondDMSFile(object):
             if (min(a, b), max(a, b)) not in es:
                 raise ValueError("1-4 pair (%d, %d) is not in the exclusion table" % (a, b))
         box = self.getBox()
-        if nonbondedMethod == CUTOFF_PERIODIC and not np.all(box > 0):
+        if nonbondedMethod in (CUTOFF_PERIODIC, EWALD, PME) and not np.all(box > 0):
             raise ValueError("a periodic cutoff needs a global_cell table")
         return NonbondedSystem(np.array(charge), np.array(sigma), np.array(epsilon),
                                np.array(excl, dtype=np.int32).reshape(-1, 2),
@@ -172,7 +173,8 @@ class DesmondDMSFile(object):
                                np.array(exc_params, dtype=np.float64).reshape(-1, 3),
                                method=int(nonbondedMethod), cutoff=float(nonbondedCutoff),
                                eps_rf=float(reactionFieldDielectric), box=box,
-                               use_dispersion_correction=bool(useDispersionCorrection))
+                               use_dispersion_correction=bool(useDispersionCorrection),
+                               ewald_tolerance=float(ewaldErrorTolerance))
 
     # ---- write-back ---------------------------------------------------------------------------
     def _write_vec3(self, columns, values, scale):

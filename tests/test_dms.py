@@ -54,6 +54,8 @@ def test_read_synthetic(tmp_path):
         assert np.array_equal(d.getResidueIds(), [0, 0, 0, 1, 1, 1])
         assert np.allclose(d.getBox(), [3.0, 3.1, 3.2])
         sysd = d.createSystem(nonbondedMethod=S.CUTOFF_PERIODIC, nonbondedCutoff=0.9)
+        pme = d.createSystem(nonbondedMethod=S.PME, nonbondedCutoff=0.9, ewaldErrorTolerance=1e-4)   # test_explicit.py:64
+    assert pme.method == S.PME and abs(pme.ewald_alpha_effective() - np.sqrt(-np.log(2e-4)) / 0.9) < 1e-14
     assert sysd.method == S.CUTOFF_PERIODIC and sysd.cutoff == 0.9 and sysd.eps_rf == 78.3
     assert np.allclose(sysd.charge, 0.1 * (np.arange(6) - 2))
     assert np.allclose(sysd.sigma, [0.34, 0.25] * 3)
