@@ -330,6 +330,13 @@ int sdm_md_kinetic_energy(sdm_ctx* ctx, int replica, double* ke);
 int sdm_set_external_dual(sdm_ctx* ctx, int replica, const double* f1_ext, const double* f2_ext,
                           double e1_ext, double e2_ext);
 
+/* The reciprocal-space part of PME on the device (SDM_PME / SDM_EWALD contexts): smooth particle-mesh Ewald with
+ * B-splines of order 5 (OpenMM 7.3 ReferencePME), both states of every replica per evaluation, plus the self
+ * energy -- it then fills the external slots itself (sdm_set_external_dual is refused).  grid: [3] mesh sizes,
+ * or NULL for OpenMM's rule ceil(2 alpha L / (3 tol^(1/5))) rounded up to a size with factors 2, 3, 5, 7
+ * (sdm_get_info "pme_grid_x/y/z").  Needs cuFFT (libcufft.so.11) at run time; SDM_ERR_CUDA if it is absent. */
+int sdm_enable_reciprocal_pme(sdm_ctx* ctx, const int32_t* grid);
+
 /* ---- restraint forces of SDMUtils (the SDMUtils part) -------------------------------
  * What python/SDMUtils.py builds as OpenMM Custom*Forces in force group 1, evaluated on the device for every
  * replica inside sdm_eval(): the energy enters sdm_scalars.pot_energy like Eb, the forces are added to the

@@ -130,6 +130,7 @@ SYMBOLS = {
     "sdm_md_update": (_I, [_VP, _VP]),
     "sdm_md_set_noise": (_I, [_VP, _VP]),
     "sdm_md_kinetic_energy": (_I, [_VP, _I, C.POINTER(_D)]),
+    "sdm_enable_reciprocal_pme": (_I, [_VP, _VP]),
     "sdm_set_external_dual": (_I, [_VP, _I, _VP, _VP, _D, _D]),
     "sdm_add_centroid_restraint": (_I, [_VP, C.POINTER(SdmCentroidRestraint)]),
     "sdm_add_alignment_restraint": (_I, [_VP, C.POINTER(SdmAlignmentRestraint)]),

@@ -297,6 +297,12 @@ class SDMContext:
         _lib.check(self._L.sdm_md_kinetic_energy(self._h, replica, C.byref(v)))
         return v.value
 
+    def enable_reciprocal_pme(self, grid=None):
+        """Reciprocal-space PME of both states on the device (SDM_PME / SDM_EWALD systems); grid = [3] mesh sizes or
+        None for OpenMM's rule."""
+        g = None if grid is None else np.ascontiguousarray(grid, dtype=np.int32)
+        _lib.check(self._L.sdm_enable_reciprocal_pme(self._h, _ptr(g)))
+
     def set_external_dual(self, replica: int, f1_ext=None, f2_ext=None, e1_ext: float = 0.0, e2_ext: float = 0.0):
         """Energies and forces of both states computed outside the library (reciprocal-space PME, GB ...):
         E1 += e1, u += e2 - e1, F1 += f1, F2 - F1 += f2 - f1.  None removes them."""

@@ -283,6 +283,7 @@ int sdm_create(const sdm_system* s_in, const sdm_options* opt_in, sdm_ctx** out)
         T.alpha = s->ewald_alpha > 0 ? s->ewald_alpha : std::sqrt(-std::log(2.0 * tol)) / T.rc;
         T.alphaf = (float)T.alpha;
         T.krf = T.crf = 0.0;
+        c->ewald_tol = tol;
     }
     T.rc2f = (float)T.rc2;
     T.krff = (float)T.krf;
@@ -301,6 +302,7 @@ int sdm_create(const sdm_system* s_in, const sdm_options* opt_in, sdm_ctx** out)
         heps[i] = 2.0 * std::sqrt(s->epsilon[i]);
         parf[i] = make_float4((float)(q[i] * sqrtK), (float)hsig[i], (float)heps[i], 0.f);
     }
+    c->h_charge = q;
     TRY(dev_upload(c, &T.q, q));
     TRY(dev_upload(c, &T.hsig, hsig));
     TRY(dev_upload(c, &T.heps, heps));
@@ -429,6 +431,7 @@ void sdm_destroy(sdm_ctx* c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     sdm_ctx_free_pairlist(c);
+    sdm_ctx_free_pme(c);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -595,6 +598,7 @@ static void enqueue_position_only(sdm_ctx* c, cudaStream_t s) {
     sdm::launch_ligand_gather(T, B, s);   // per-atom gather of the displaced-atom pair forces
     sdm::launch_exceptions(T, B, s);      // after the probe kernel: adds to dF of displaced 1-4 pairs
     c->launches += 2;
+    sdm_ctx_pme_enqueue(c, s);            // reciprocal-space PME of both states (when switched on)
 }
 
 // The kernels that need both: scalar stage (soft-core, bias, bookkeeping) and the hybrid force.
@@ -667,29 +671,46 @@ static int push_group(sdm_ctx* c, sdm::RestraintTerm& t, int k, int count, const
     return SDM_OK;
 }
 
+// Device buffers of the external dual-state terms ([R][3n] forces of both states, [R][2] energies, [R] flags).
+static int ensure_ext_buffers(sdm_ctx* c) {
+    if (c->d_ext_f1) return SDM_OK;
+    const size_t n3 = 3 * (size_t)c->n;
+    void *a = nullptr, *b = nullptr, *e = nullptr, *on = nullptr;
+    SDM_CUDA(cudaMalloc(&a, sizeof(double) * n3 * c->R));
+    SDM_CUDA(cudaMalloc(&b, sizeof(double) * n3 * c->R));
+    SDM_CUDA(cudaMalloc(&e, sizeof(double) * 2 * c->R));
+    SDM_CUDA(cudaMalloc(&on, sizeof(int) * c->R));
+    SDM_CUDA(cudaMemset(a, 0, sizeof(double) * n3 * c->R));
+    SDM_CUDA(cudaMemset(b, 0, sizeof(double) * n3 * c->R));
+    SDM_CUDA(cudaMemset(e, 0, sizeof(double) * 2 * c->R));
+    SDM_CUDA(cudaMemset(on, 0, sizeof(int) * c->R));
+    c->allocs.push_back(a); c->allocs.push_back(b); c->allocs.push_back(e); c->allocs.push_back(on);
+    c->d_ext_f1 = (double*)a; c->d_ext_f2 = (double*)b; c->d_ext_e = (double*)e; c->d_ext_on = (int*)on;
+    c->B.ext_f1 = c->d_ext_f1; c->B.ext_f2 = c->d_ext_f2; c->B.ext_e = c->d_ext_e; c->B.ext_on = c->d_ext_on;
+    c->graph_valid = false;   // kernel arguments of the captured sequence changed
+    return SDM_OK;
+}
+
+int sdm_enable_reciprocal_pme(sdm_ctx* c, const int32_t* grid) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    if (int rc = ensure_ext_buffers(c)) return rc;
+    if (int rc = sdm_ctx_init_pme(c, grid)) return rc;
+    c->graph_valid = false;
+    return SDM_OK;
+}
+
 int sdm_set_external_dual(sdm_ctx* c, int replica, const double* f1_ext, const double* f2_ext, double e1_ext,
                           double e2_ext) {
     SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     if (replica < 0 || replica >= c->R) return fail(SDM_ERR_INVALID, "replica out of range");
     if ((f1_ext == nullptr) != (f2_ext == nullptr)) return fail(SDM_ERR_INVALID, "give both force arrays or neither");
+    if (c->pme) return fail(SDM_ERR_INVALID, "the external slots are filled by the library's reciprocal-space PME");
     const size_t n3 = 3 * (size_t)c->n;
-    if (!c->d_ext_f1) {
-        if (!f1_ext) return SDM_OK;   // nothing to remove
-        void *a = nullptr, *b = nullptr, *e = nullptr, *on = nullptr;
-        SDM_CUDA(cudaMalloc(&a, sizeof(double) * n3 * c->R));
-        SDM_CUDA(cudaMalloc(&b, sizeof(double) * n3 * c->R));
-        SDM_CUDA(cudaMalloc(&e, sizeof(double) * 2 * c->R));
-        SDM_CUDA(cudaMalloc(&on, sizeof(int) * c->R));
-        SDM_CUDA(cudaMemset(a, 0, sizeof(double) * n3 * c->R));
-        SDM_CUDA(cudaMemset(b, 0, sizeof(double) * n3 * c->R));
-        SDM_CUDA(cudaMemset(e, 0, sizeof(double) * 2 * c->R));
-        SDM_CUDA(cudaMemset(on, 0, sizeof(int) * c->R));
-        c->allocs.push_back(a); c->allocs.push_back(b); c->allocs.push_back(e); c->allocs.push_back(on);
-        c->d_ext_f1 = (double*)a; c->d_ext_f2 = (double*)b; c->d_ext_e = (double*)e; c->d_ext_on = (int*)on;
-        c->B.ext_f1 = c->d_ext_f1; c->B.ext_f2 = c->d_ext_f2; c->B.ext_e = c->d_ext_e; c->B.ext_on = c->d_ext_on;
-        c->graph_valid = false;   // kernel arguments of the captured sequence changed
-    }
+    if (!c->d_ext_f1 && !f1_ext) return SDM_OK;   // nothing to remove
+    if (int rc = ensure_ext_buffers(c)) return rc;
     // staged through the stream (pageable host memory: the copies return when the data has been taken)
     const double e[2] = {f1_ext ? e1_ext : 0.0, f1_ext ? e2_ext : 0.0};
     const int on = f1_ext ? 1 : 0;
@@ -1132,6 +1153,8 @@ int sdm_get_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "e_dispersion") *value = c->T.e_disp;
     else if (k == "num_sms") *value = c->num_sms;
     else if (k == "fp32_fma_tflops_measured") *value = sdm::measure_fp32_fma_tflops(c->num_sms, c->stream);   // ~1 ms of FMAs
+    else if (k == "ewald_alpha") *value = c->T.ewald ? c->T.alpha : 0.0;
+    else if (c->pme && sdm_ctx_pme_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
     else if (sdm_ctx_pairlist_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
     else return fail(SDM_ERR_INVALID, "unknown info key: " + k);
     return SDM_OK;

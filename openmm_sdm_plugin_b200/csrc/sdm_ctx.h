@@ -6,7 +6,7 @@
 
 #include "sdm_kernels.h"
 
-namespace sdm { struct PairList; }
+namespace sdm { struct PairList; struct PmeState; }
 
 struct sdm_ctx {
     int device = 0;
@@ -80,6 +80,11 @@ struct sdm_ctx {
     double md_dt = 0, md_vscale = 0, md_fscale = 0, md_noisescale = 0;
     unsigned long long md_seed = 0, md_steps = 0;
 
+    // reciprocal-space PME on the device (kernels_pme.cu; sdm_enable_reciprocal_pme): fills the external slots
+    sdm::PmeState* pme = nullptr;
+    std::vector<double> h_charge;       // host copy of the charges (self energy)
+    double ewald_tol = 0;
+
     // external dual-state contributions (sdm_set_external_dual): reciprocal-space PME, GB, ...
     double *d_ext_f1 = nullptr, *d_ext_f2 = nullptr, *d_ext_e = nullptr;
     int* d_ext_on = nullptr;
@@ -100,6 +105,12 @@ struct sdm_ctx {
 
 // api.cu
 int sdm_fail(int code, const char* msg);
+
+// kernels_pme.cu -- reciprocal-space PME
+int sdm_ctx_init_pme(sdm_ctx* c, const int32_t* grid);   // grid: [3] or nullptr (OpenMM's rule)
+void sdm_ctx_free_pme(sdm_ctx* c);
+int sdm_ctx_pme_enqueue(sdm_ctx* c, cudaStream_t s);      // no-op without sdm_ctx_init_pme
+int sdm_ctx_pme_info(sdm_ctx* c, const char* key, double* value);
 
 // pairlist.cu -- cluster-pair list path (SDM_PAIR_CLUSTER)
 int sdm_ctx_init_pairlist(sdm_ctx* c);

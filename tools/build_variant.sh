@@ -8,5 +8,5 @@ NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 $NVCC -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC -Xptxas -v "$@" -c kernels_rows.cu -o /tmp/kc_$NAME.o 2> /tmp/kc_$NAME.log
 grep -A3 "pair_row_kernelILi8ELb1ELb1ELb0" /tmp/kc_$NAME.log | grep -E "registers|spill" | head -8
-$NVCC $ARCH -shared -cudart static -o ../libsdmb200_$NAME.so api.o kernels_fused.o kernels_elementwise.o kernels_md.o kernels_restraints.o pairlist.o /tmp/kc_$NAME.o
+$NVCC $ARCH -shared -cudart static -o ../libsdmb200_$NAME.so api.o kernels_fused.o kernels_elementwise.o kernels_md.o kernels_restraints.o kernels_pme.o pairlist.o /tmp/kc_$NAME.o
 echo built libsdmb200_$NAME.so
