@@ -38,11 +38,14 @@ def load_case(workload: str):
     from openmm_sdm_plugin_b200 import system as S
     if workload == "cfg2":
         return S.cfg2(), "cfg2: TEMOA-G1/G4 explicit solvent (20446 atoms, CutoffPeriodic RF, rc=1.0 nm, 38 displaced atoms)"
-    if workload == "cfg2:pme":
+    if workload in ("cfg2:pme", "cfg2:pme+reciprocal"):
         c = S.cfg2()
         c.system.method = S.PME
-        return c, "cfg2 as example/test_explicit.py:64 ships it: nonbondedMethod=PME, DIRECT SPACE only (erfc pair terms + " \
-                  "erf correction of the excluded pairs; the reciprocal part enters through sdm_set_external_dual)"
+        if workload.endswith("+reciprocal"):
+            return c, "cfg2 as example/test_explicit.py:64 ships it: nonbondedMethod=PME complete -- direct space + " \
+                      "reciprocal space (mesh 48x54x48, order 5, both states, cuFFT) on the device"
+        return c, "cfg2 with nonbondedMethod=PME, DIRECT SPACE only (erfc pair terms + erf correction of the excluded " \
+                  "pairs; the reciprocal part enters through sdm_set_external_dual)"
     if workload == "cfg1":
         return S.cfg1(), "cfg1: OA-G6/G3 (230 atoms, CutoffNonPeriodic 15 nm, 38 displaced atoms)"
     if workload.startswith("synthetic:"):
@@ -414,7 +417,8 @@ def sweep_leg(args, device, stream, peak_tflops, quick=False):
     import torch
     from openmm_sdm_plugin_b200 import system as S
     from openmm_sdm_plugin_b200.context import SDMContext
-    plan = [("cfg1", r) for r in (16, 128, 512)] + [("cfg2:pme", 16), ("synthetic:50000", 16)]
+    plan = [("cfg1", r) for r in (16, 128, 512)] + [("cfg2:pme", 16), ("cfg2:pme+reciprocal", 16), ("cfg2:pme+reciprocal", 1),
+                                                      ("synthetic:50000", 16)]
     sizes = (5000, 20000, 100000) if quick else (5000, 10000, 20000, 50000, 100000, 200000, 500000)
     plan += [("synthetic:%d" % n, r) for n in sizes for r in (1, 8)]
     out = []
@@ -426,6 +430,8 @@ def sweep_leg(args, device, stream, peak_tflops, quick=False):
             with SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=args.pair_mode, device=device,
                             skin=args.skin, nstlist=args.nstlist) as c:
                 c.set_stream(stream.cuda_stream)
+                if wl.endswith("+reciprocal"):
+                    c.enable_reciprocal_pme()
                 for r in range(R):
                     c.set_alchemical(r, case.alch)
                     c.set_positions(r, case.positions + (rng.normal(scale=0.002, size=(n, 3)) if r else 0.0))
