@@ -230,6 +230,8 @@ class LangevinIntegratorSDM(object):
             raise OpenMMException("nParticles (%d) does not match the system (%d)" % (self._n, system.n_atoms))
         self._ctx = SDMContext(system, self._displ, n_replicas=1, device=device, **ctx_options)
         apply_restraints(self._ctx, system)     # what SDMUtils recorded on the system (force group 1 in the reference)
+        if int(system.method) in (3, 4):        # NonbondedForce::Ewald / ::PME: the reference gets the complete sum
+            self._ctx.enable_reciprocal_pme()   # from OpenMM; here direct space + reciprocal space on the device
         self._displ_dirty = False
         return self
 

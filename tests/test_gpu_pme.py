@@ -97,3 +97,31 @@ def test_reciprocal_pme_needs_an_ewald_system():
     with SDMContext(case.system, case.displacement) as ctx:
         with pytest.raises(_lib.SDMError):
             ctx.enable_reciprocal_pme()
+
+
+def test_plugin_surface_with_a_pme_system_and_device_dynamics():
+    """The integrator mirror bound to a PME system evaluates the complete sum (bind switches the reciprocal part on),
+    and the device MD loop runs on it."""
+    from openmm_sdm_plugin_b200.sdmplugin import LangevinIntegratorSDM
+    sysd, pos = small_ewald_case(n_mol=40, seed=4)
+    n = sysd.n_atoms
+    integ = LangevinIntegratorSDM(300.0, 1.0, 0.0005, n)
+    for i in range(6):
+        integ.setDisplacement(i, 0.4, -0.2, 0.1)
+    integ.setLambda1(0.3); integ.setLambda2(0.3)
+    integ.bind(sysd, pair_mode=_lib.PAIR_ALLPAIRS)
+    try:
+        integ.evaluate(pos)
+        ctx = integ._ctx
+        grid = [int(ctx.info("pme_grid_" + a)) for a in "xyz"]
+        disp = np.zeros_like(pos); disp[:6] = (0.4, -0.2, 0.1)
+        ref = full_pme_reference(S.SDMCase("s", sysd, pos, disp, S.AlchemicalState()), grid)
+        sc = ctx.scalars(0)
+        assert abs(sc["E1"] - ref["E1"]) <= E_RTOL * abs(ref["E1"]) and abs(sc["u"] - ref["u"]) <= 1e-6 * max(1.0, abs(ref["u"]))
+        masses = np.tile([15.999, 1.008, 1.008], n // 3)
+        integ.setState(pos, np.zeros_like(pos), masses)
+        integ.step(5)
+        assert np.isfinite(integ.getPositions()).all() and np.abs(integ.getPositions() - pos).max() > 0.0
+        assert ctx.scalars(0)["status"] == 0
+    finally:
+        integ.cleanup()
