@@ -21,10 +21,10 @@ namespace SDMB200 {
 class B200NonbondedForce : public OpenMM::Force {
 public:
     // values of OpenMM::NonbondedForce::NonbondedMethod that the path supports
-    enum NonbondedMethod { NoCutoff = 0, CutoffNonPeriodic = 1, CutoffPeriodic = 2 };
+    enum NonbondedMethod { NoCutoff = 0, CutoffNonPeriodic = 1, CutoffPeriodic = 2, Ewald = 3, PME = 4 };
     struct Exception { int p1, p2; double chargeProd, sigma, epsilon; };
 
-    B200NonbondedForce() : method(NoCutoff), cutoff(1.0), rfDielectric(78.3), dispersion(true) {
+    B200NonbondedForce() : method(NoCutoff), cutoff(1.0), rfDielectric(78.3), ewaldTol(5e-4), dispersion(true) {
         box[0] = box[1] = box[2] = 0.0;
         setForceGroup(2);
     }
@@ -49,12 +49,14 @@ public:
     void setCutoffDistance(double d) { cutoff = d; }
     double getReactionFieldDielectric() const { return rfDielectric; }
     void setReactionFieldDielectric(double d) { rfDielectric = d; }
+    double getEwaldErrorTolerance() const { return ewaldTol; }
+    void setEwaldErrorTolerance(double t) { ewaldTol = t; }
     bool getUseDispersionCorrection() const { return dispersion; }
     void setUseDispersionCorrection(bool b) { dispersion = b; }
     // orthorhombic box edges (nm); System::getDefaultPeriodicBoxVectors in a full OpenMM
     void setPeriodicBox(double a, double b, double c) { box[0] = a; box[1] = b; box[2] = c; }
     const double* getPeriodicBox() const { return box; }
-    bool usesPeriodicBoundaryConditions() const { return method == CutoffPeriodic; }
+    bool usesPeriodicBoundaryConditions() const { return method == CutoffPeriodic || method == Ewald || method == PME; }
 
 #ifndef SDMB200_OPENMM_STUB
 protected:
@@ -66,7 +68,7 @@ private:
     std::vector<double> charge, sigma, epsilon;
     std::vector<Exception> exceptions;
     NonbondedMethod method;
-    double cutoff, rfDielectric, box[3];
+    double cutoff, rfDielectric, ewaldTol, box[3];
     bool dispersion;
 };
 

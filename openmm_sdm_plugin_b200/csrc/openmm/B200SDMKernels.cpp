@@ -149,9 +149,14 @@ void B200IntegrateLangevinStepSDMKernel::initialize(const System& system, const 
         s.charge = q.data(); s.sigma = sig.data(); s.epsilon = eps.data();
         s.exclusions = excl.data(); s.exceptions = exc.data(); s.exception_params = excp.data();
         s.displacement = displ.data();
+        s.ewald_tolerance = nb->getEwaldErrorTolerance();   // Ewald / PME: alpha by OpenMM's rule
         sdm_options opt;
         sdm_default_options(&opt);
         check(sdm_create(&s, &opt, &ctx), "sdm_create");
+        // NonbondedForce::Ewald / ::PME: the complete sum, like OpenMM's own NonbondedForce kernel -- direct space
+        // in the pair kernels, reciprocal space (smooth PME, both states) on the device as well
+        if (s.method == SDM_EWALD || s.method == SDM_PME)
+            check(sdm_enable_reciprocal_pme(ctx, nullptr), "sdm_enable_reciprocal_pme");
     } else {
         // ---- level B: OpenMM evaluates force group 2; the plugin's own kernels run on the device -----
         const size_t bytes = sizeof(float) * 4 * (size_t)n;
