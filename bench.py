@@ -275,7 +275,7 @@ def md_setup(case, freeze_solute=True):
 
 
 def md_leg(case, R, args, device, stream, flush, states, rank, skin=None, nstlist=None, steps=None, dt=0.001,
-           freeze_solute=True):
+           freeze_solute=True, reciprocal_pme=False):
     """Device-resident dynamics (sdm_md_step) as the reference's example runs it
     (example/test_explicit.py:166-169: 300 K, friction 0.1/ps, 1 fs): real masses, thermal
     velocities, the fixture's own distance constraints (SETTLE waters + X-H clusters) applied between
@@ -296,6 +296,8 @@ def md_leg(case, R, args, device, stream, flush, states, rank, skin=None, nstlis
     with SDMContext(case.system, case.displacement, n_replicas=R, pair_mode=args.pair_mode, device=device,
                     skin=skin, nstlist=nstlist) as c:
         c.set_stream(stream.cuda_stream)
+        if reciprocal_pme:
+            c.enable_reciprocal_pme()
         c.md_init(masses, 300.0, 0.1, dt, seed=1234 + rank)
         if have_cons:
             c.md_set_constraints(cpairs, cdist, 1e-5)
@@ -882,6 +884,17 @@ def main():
                                      nstlist=args.md_nstlist)
         except Exception as ex:   # an extra, never the reason for a missing bench line
             line["md_loop"] = {"error": str(ex)[:200]}
+        if args.workload == "cfg2":
+            # the same dynamics with the electrostatics example/test_explicit.py:64 ships: nonbondedMethod=PME,
+            # direct + reciprocal space of both states on the device
+            try:
+                pme_case, _ = load_case("cfg2:pme+reciprocal")
+                line["md_loop_pme"] = md_leg(pme_case, R, args, local, stream, flush, states, rank, skin=args.md_skin,
+                                             nstlist=args.md_nstlist, reciprocal_pme=True)
+                line["md_loop_pme"]["note"] = "md_loop with nonbondedMethod=PME complete (mesh 48x54x48, order 5): " + \
+                    line["md_loop_pme"]["note"]
+            except Exception as ex:
+                line["md_loop_pme"] = {"error": str(ex)[:200]}
     if not args.no_cfg3 and args.workload == "cfg2" and case.constraint_pairs is not None:
         try:   # every rank takes part (the ladder is dealt over the ranks)
             res = cfg3_leg(case, args, world, rank, local, stream)
