@@ -47,6 +47,12 @@
 namespace sdm {
 namespace {
 
+#ifndef SDM_ROW_MADWIDE
+#define SDM_ROW_MADWIDE 1   // gather / accumulator addresses as one mad.wide.u32
+#endif
+#ifndef SDM_ROW_RED1
+#define SDM_ROW_RED1 1      // one non-zero test for the three j-force REDs of a step
+#endif
 #ifndef SDM_ROW_ROTATE_LATE
 #define SDM_ROW_ROTATE_LATE 1
 #endif
@@ -106,7 +112,12 @@ __device__ __forceinline__ f2 sel2_or_zero(const f2 v, const bool c_lo, const bo
 
 // The 32-byte record of a slot (position + charge, sigma/2, 2*sqrt(eps)): two 128-bit loads from one sector.
 __device__ __forceinline__ void load_jrec(const float4* __restrict__ jrec, const uint32_t slot, float4& xj, float2& pj) {
+#if SDM_ROW_MADWIDE
+    const float4* r;   // base + slot * 32 as ONE multiply-add (the compiler's rendering takes a shift, a mask and a 64-bit add)
+    asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(r) : "r"(slot), "l"(jrec));
+#else
     const float4* r = jrec + 2 * (size_t)slot;
+#endif
 #if SDM_ROW_LDG256
     float u0, u1;   // padding words of the record
     asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -472,10 +483,27 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
         // a j-atom of the row that has no partner inside the cutoff (one in six: the list reaches to
         // rc + skin) and the padding lanes stay silent; ptxas renders each predicated RED as a short
         // branch region that also skips the 64-bit conversion
+#if SDM_ROW_MADWIDE
+        long long* fjp;
+        asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(fjp) : "r"((uint32_t)jslot), "l"(f1acc));
+#else
         long long* fjp = f1acc + jslot;
+#endif
+#if SDM_ROW_RED1
+        {   // one test for the three components: a j-atom out of reach of all eight i-atoms has an exactly zero force
+            const float fx = lo(fj.x) + hi(fj.x), fy = lo(fj.y) + hi(fj.y), fz = lo(fj.z) + hi(fj.z);
+            if (fx != 0.f || fy != 0.f || fz != 0.f) {
+                const long long vx = __float2ll_rn(fx * -kFix), vy = __float2ll_rn(fy * -kFix), vz = __float2ll_rn(fz * -kFix);
+                asm volatile("red.global.add.u64 [%0], %1;" :: "l"(fjp), "l"(vx) : "memory");
+                asm volatile("red.global.add.u64 [%0], %1;" :: "l"(fjp + plane), "l"(vy) : "memory");
+                asm volatile("red.global.add.u64 [%0], %1;" :: "l"(fjp + 2 * plane), "l"(vz) : "memory");
+            }
+        }
+#else
         red_fixed_nonzero(fjp, lo(fj.x) + hi(fj.x), -kFix);
         red_fixed_nonzero(fjp + plane, lo(fj.y) + hi(fj.y), -kFix);
         red_fixed_nonzero(fjp + 2 * plane, lo(fj.z) + hi(fj.z), -kFix);
+#endif
 #if SDM_ROW_JPREFETCH && SDM_ROW_ROTATE_LATE
         asm volatile("mov.b32 %0, %6;\n mov.b32 %1, %7;\n mov.b32 %2, %8;\n mov.b32 %3, %9;\n mov.b32 %4, %10;\n mov.b32 %5, %11;"
                      : "=f"(xj1.x), "=f"(xj1.y), "=f"(xj1.z), "=f"(xj1.w), "=f"(pj1.x), "=f"(pj1.y)
