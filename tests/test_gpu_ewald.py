@@ -107,3 +107,31 @@ def test_external_dual_state_terms_enter_like_nonbonded_ones():
         ctx.set_external_dual(1)                                                        # remove
         ctx.eval()
         assert ctx.scalars(1)["E1"] == base[1][0]["E1"] and np.array_equal(ctx.forces(1, _lib.FORCE_STATE1), base[1][1])
+
+
+def test_excluded_pair_with_different_displacements_under_ewald():
+    """A molecule displaced only in part: its excluded pairs change their erf(alpha r)/r correction between the
+    states (the branch of the exceptions kernel that feeds dF and u), with and without the reciprocal part."""
+    from test_oracle import small_ewald_case
+    from oracle import pme as P
+    sysd, pos = small_ewald_case(n_mol=40, seed=4)
+    disp = np.zeros_like(pos)
+    disp[0] = (0.05, 0.02, -0.03)            # atoms 0 and 1 of the first molecule move, atom 2 stays
+    disp[1] = (0.05, 0.02, -0.03)
+    disp[6:9] = (0.3, 0.1, 0.0)              # a whole molecule with another displacement vector
+    case = S.SDMCase("partial", sysd, pos, disp, S.AlchemicalState(lambdac=0.5))
+    ref = oracle_eval(case)
+    with run_case(case, _lib.PAIR_ALLPAIRS) as ctx:
+        check_against_oracle(ctx, case, ref)
+        grid = [24, 27, 25]
+        ctx.enable_reciprocal_pme(grid)
+        ctx.eval()
+        alpha = sysd.ewald_alpha_effective()
+        e1r, f1r = P.reciprocal(sysd.charge, pos, sysd.box, alpha, grid)
+        e2r, f2r = P.reciprocal(sysd.charge, pos + disp, sysd.box, alpha, grid)
+        sc = ctx.scalars(0)
+        assert abs(sc["E1"] - (ref["E1"] + e1r)) <= 1e-5 * abs(ref["E1"] + e1r)
+        assert abs(sc["u"] - (ref["u"] + e2r - e1r)) <= 1e-6 * max(1.0, abs(ref["u"] + e2r - e1r))
+        df = ctx.forces(0, _lib.FORCE_DELTA)
+        dref = (ref["f2"] + f2r) - (ref["f1"] + f1r)
+        assert np.abs(df - dref).max() <= 1e-7 * np.abs(ref["f1"]).max() + 1e-9 * np.abs(dref).max()
