@@ -61,12 +61,13 @@ typedef enum {
 #define SDM_NOCUTOFF 0
 #define SDM_CUTOFF_NONPERIODIC 1
 #define SDM_CUTOFF_PERIODIC 2
-/* NonbondedForce::Ewald / ::PME (what example/test_explicit.py:64 asks for): the DIRECT-SPACE part of the Ewald sum --
- * erfc(alpha r)/r pair terms inside the cutoff, the erf(alpha r)/r correction of the excluded pairs, 1-4
- * exceptions and the dispersion correction: OpenMM's calculateEwaldIxn with includeDirect only.  The
- * reciprocal-space part (and the self energy OpenMM books with it) is NOT computed here; it enters through
+/* NonbondedForce::Ewald / ::PME (what example/test_explicit.py:64 asks for).  A context created with one of them
+ * computes the DIRECT-SPACE part of the Ewald sum -- erfc(alpha r)/r pair terms inside the cutoff, the
+ * erf(alpha r)/r correction of the excluded pairs, 1-4 exceptions and the dispersion correction: OpenMM's
+ * calculateEwaldIxn with includeDirect.  The reciprocal-space part (and the self energy OpenMM books with it) is
+ * added by sdm_enable_reciprocal_pme() (smooth PME on the device, both states) or handed in through
  * sdm_set_external_dual() -- with OpenMM in the loop: NonbondedForce::setReciprocalSpaceForceGroup and one
- * evaluation of that group per state.  Both values select the same direct-space arithmetic. */
+ * evaluation of that group per state.  Both values select the same arithmetic. */
 #define SDM_EWALD 3
 #define SDM_PME 4
 
