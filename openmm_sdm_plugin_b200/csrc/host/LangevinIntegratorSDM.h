@@ -131,6 +131,13 @@ public:
         system.displacement = flat.data();
         system.n_replicas = 1;
         if (sdm_create(&system, options, &ctx) != SDM_OK) throw SDMException(sdm_last_error());
+        // NonbondedForce::Ewald / ::PME: the reference gets the complete sum from OpenMM -- direct space is in the
+        // pair kernels, the reciprocal part of both states is switched on here
+        if ((system.method == SDM_EWALD || system.method == SDM_PME) && sdm_enable_reciprocal_pme(ctx, nullptr) != SDM_OK) {
+            const std::string msg = sdm_last_error();
+            cleanup();
+            throw SDMException(msg);
+        }
         displDirty = false;
     }
     void cleanup() {
