@@ -338,6 +338,21 @@ int sdm_set_external_dual(sdm_ctx* ctx, int replica, const double* f1_ext, const
  * (sdm_get_info "pme_grid_x/y/z").  Needs cuFFT (libcufft.so.11) at run time; SDM_ERR_CUDA if it is absent. */
 int sdm_enable_reciprocal_pme(sdm_ctx* ctx, const int32_t* grid);
 
+/* The HCT generalized-Born model with the ACE surface-area term on the device: what the reference's DMS reader adds
+ * for implicitSolvent=HCT (example/desmonddmsfile75.py:454-465: GBSAHCTForce(SA='ACE') in the nonbonded force group,
+ * so LangevinIntegratorSDM::step, openmmapi/src/LangevinIntegratorSDM.cpp:160-170, evaluates it in both states).
+ * Expressions of OpenMM 7.3's app/internal/customgbforces.py under CustomGBForce's NoCutoff / no-exclusion rules;
+ * Born radii are global in the coordinates, so both states of every replica get the full model per evaluation
+ * (FP64), and the library fills the external slots itself (sdm_set_external_dual is refused).  Arrays of n_atoms:
+ * charge (NULL: the NonbondedForce charges of sdm_system), offset_radius = "or" (nm, radius - 0.009),
+ * scaled_radius = "sr" (nm, scale * or) -- the per-particle parameters as the CustomGBForce holds them.
+ * solute/solvent dielectric: 1.0 / 78.5 are GBSAHCTForce's defaults.  sa_ace != 0 adds
+ * 28.3919551 (radius + 0.14)^2 (radius/B)^6.  Refused (SDM_ERR_INVALID) for periodic methods. */
+int sdm_enable_hct_gb(sdm_ctx* ctx, const double* charge, const double* offset_radius, const double* scaled_radius,
+                      double solute_dielectric, double solvent_dielectric, int sa_ace);
+/* Born radii B_i of state 1 or 2 (x or x + d) of one replica in the last evaluation; synchronises. */
+int sdm_get_born_radii(sdm_ctx* ctx, int replica, int state, double* radii);
+
 /* ---- restraint forces of SDMUtils (the SDMUtils part) -------------------------------
  * What python/SDMUtils.py builds as OpenMM Custom*Forces in force group 1, evaluated on the device for every
  * replica inside sdm_eval(): the energy enters sdm_scalars.pot_energy like Eb, the forces are added to the

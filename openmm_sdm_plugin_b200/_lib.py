@@ -132,6 +132,8 @@ SYMBOLS = {
     "sdm_md_kinetic_energy": (_I, [_VP, _I, C.POINTER(_D)]),
     "sdm_enable_reciprocal_pme": (_I, [_VP, _VP]),
     "sdm_set_external_dual": (_I, [_VP, _I, _VP, _VP, _D, _D]),
+    "sdm_enable_hct_gb": (_I, [_VP, _VP, _VP, _VP, _D, _D, _I]),
+    "sdm_get_born_radii": (_I, [_VP, _I, _I, _VP]),
     "sdm_add_centroid_restraint": (_I, [_VP, C.POINTER(SdmCentroidRestraint)]),
     "sdm_add_alignment_restraint": (_I, [_VP, C.POINTER(SdmAlignmentRestraint)]),
     "sdm_clear_restraints": (_I, [_VP]),

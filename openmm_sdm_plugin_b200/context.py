@@ -303,6 +303,25 @@ class SDMContext:
         g = None if grid is None else np.ascontiguousarray(grid, dtype=np.int32)
         _lib.check(self._L.sdm_enable_reciprocal_pme(self._h, _ptr(g)))
 
+    def enable_hct_gb(self, offset_radius, scaled_radius, charge=None, solute_dielectric=1.0,
+                      solvent_dielectric=78.5, sa_ace=True):
+        """HCT generalized Born (+ ACE surface area) of both states on the device: GBSAHCTForce(SA='ACE') of
+        example/desmonddmsfile75.py:460.  offset_radius / scaled_radius: the CustomGBForce parameters "or" and "sr"
+        (nm); charge None = the NonbondedForce charges."""
+        o = np.ascontiguousarray(offset_radius, dtype=np.float64)
+        sr = np.ascontiguousarray(scaled_radius, dtype=np.float64)
+        q = None if charge is None else np.ascontiguousarray(charge, dtype=np.float64)
+        if o.shape != (self.n,) or sr.shape != (self.n,) or (q is not None and q.shape != (self.n,)):
+            raise ValueError("GB parameter arrays must be [n_atoms]")
+        _lib.check(self._L.sdm_enable_hct_gb(self._h, _ptr(q), _ptr(o), _ptr(sr), float(solute_dielectric),
+                                             float(solvent_dielectric), 1 if sa_ace else 0))
+
+    def born_radii(self, replica: int, state: int = 1):
+        """Born radii (nm) of state 1 (x) or 2 (x + d) in the last evaluation."""
+        out = np.empty(self.n, np.float64)
+        _lib.check(self._L.sdm_get_born_radii(self._h, replica, state, _ptr(out)))
+        return out
+
     def set_external_dual(self, replica: int, f1_ext=None, f2_ext=None, e1_ext: float = 0.0, e2_ext: float = 0.0):
         """Energies and forces of both states computed outside the library (reciprocal-space PME, GB ...):
         E1 += e1, u += e2 - e1, F1 += f1, F2 - F1 += f2 - f1.  None removes them."""

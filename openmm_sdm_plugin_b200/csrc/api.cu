@@ -432,6 +432,7 @@ void sdm_destroy(sdm_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     sdm_ctx_free_pairlist(c);
     sdm_ctx_free_pme(c);
+    sdm_ctx_free_gb(c);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -599,6 +600,7 @@ static void enqueue_position_only(sdm_ctx* c, cudaStream_t s) {
     sdm::launch_exceptions(T, B, s);      // after the probe kernel: adds to dF of displaced 1-4 pairs
     c->launches += 2;
     sdm_ctx_pme_enqueue(c, s);            // reciprocal-space PME of both states (when switched on)
+    sdm_ctx_gb_enqueue(c, s);             // HCT-GB + ACE of both states (when switched on)
 }
 
 // The kernels that need both: scalar stage (soft-core, bias, bookkeeping) and the hybrid force.
@@ -701,6 +703,31 @@ int sdm_enable_reciprocal_pme(sdm_ctx* c, const int32_t* grid) {
     return SDM_OK;
 }
 
+int sdm_enable_hct_gb(sdm_ctx* c, const double* charge, const double* offset_radius, const double* scaled_radius,
+                      double solute_dielectric, double solvent_dielectric, int sa_ace) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c) return fail(SDM_ERR_INVALID, "null context");
+    if (!offset_radius || !scaled_radius) return fail(SDM_ERR_INVALID, "null radius array");
+    if (c->T.method == SDM_CUTOFF_PERIODIC || c->T.ewald)
+        return fail(SDM_ERR_INVALID, "HCT-GB is evaluated without a cutoff on plain distances: not with a periodic method");
+    if (c->pme) return fail(SDM_ERR_INVALID, "the external slots are filled by the library's reciprocal-space PME");
+    if (!(solute_dielectric > 0.0) || !(solvent_dielectric > 0.0)) return fail(SDM_ERR_INVALID, "dielectric constants must be positive");
+    for (int a = 0; a < c->n; a++)
+        if (!(offset_radius[a] > 0.0) || !(scaled_radius[a] >= 0.0)) return fail(SDM_ERR_INVALID, "offset radii must be positive, scaled radii non-negative");
+    SDM_CUDA(cudaStreamSynchronize(c->stream));
+    if (int rc = ensure_ext_buffers(c)) return rc;
+    if (int rc = sdm_ctx_init_gb(c, charge, offset_radius, scaled_radius, solute_dielectric, solvent_dielectric, sa_ace)) return rc;
+    c->graph_valid = false;
+    return SDM_OK;
+}
+
+int sdm_get_born_radii(sdm_ctx* c, int replica, int state, double* radii) {
+    SDM_ON_CTX_DEVICE(c);
+    if (!c || !radii) return fail(SDM_ERR_INVALID, "null argument");
+    if (replica < 0 || replica >= c->R || state < 1 || state > 2) return fail(SDM_ERR_INVALID, "replica or state out of range");
+    return sdm_ctx_gb_born_radii(c, replica, state - 1, radii, c->stream);
+}
+
 int sdm_set_external_dual(sdm_ctx* c, int replica, const double* f1_ext, const double* f2_ext, double e1_ext,
                           double e2_ext) {
     SDM_ON_CTX_DEVICE(c);
@@ -708,6 +735,7 @@ int sdm_set_external_dual(sdm_ctx* c, int replica, const double* f1_ext, const d
     if (replica < 0 || replica >= c->R) return fail(SDM_ERR_INVALID, "replica out of range");
     if ((f1_ext == nullptr) != (f2_ext == nullptr)) return fail(SDM_ERR_INVALID, "give both force arrays or neither");
     if (c->pme) return fail(SDM_ERR_INVALID, "the external slots are filled by the library's reciprocal-space PME");
+    if (c->gb) return fail(SDM_ERR_INVALID, "the external slots are filled by the library's HCT-GB model");
     const size_t n3 = 3 * (size_t)c->n;
     if (!c->d_ext_f1 && !f1_ext) return SDM_OK;   // nothing to remove
     if (int rc = ensure_ext_buffers(c)) return rc;
@@ -1155,6 +1183,7 @@ int sdm_get_info(sdm_ctx* c, const char* key, double* value) {
     else if (k == "fp32_fma_tflops_measured") *value = sdm::measure_fp32_fma_tflops(c->num_sms, c->stream);   // ~1 ms of FMAs
     else if (k == "ewald_alpha") *value = c->T.ewald ? c->T.alpha : 0.0;
     else if (c->pme && sdm_ctx_pme_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
+    else if (c->gb && sdm_ctx_gb_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
     else if (sdm_ctx_pairlist_info(c, k.c_str(), value) == SDM_OK) return SDM_OK;
     else return fail(SDM_ERR_INVALID, "unknown info key: " + k);
     return SDM_OK;

@@ -6,7 +6,7 @@
 
 #include "sdm_kernels.h"
 
-namespace sdm { struct PairList; struct PmeState; }
+namespace sdm { struct PairList; struct PmeState; struct GbState; }
 
 struct sdm_ctx {
     int device = 0;
@@ -85,6 +85,9 @@ struct sdm_ctx {
     std::vector<double> h_charge;       // host copy of the charges (self energy)
     double ewald_tol = 0;
 
+    // HCT generalized Born + ACE on the device (kernels_gb.cu; sdm_enable_hct_gb): fills the external slots
+    sdm::GbState* gb = nullptr;
+
     // external dual-state contributions (sdm_set_external_dual): reciprocal-space PME, GB, ...
     double *d_ext_f1 = nullptr, *d_ext_f2 = nullptr, *d_ext_e = nullptr;
     int* d_ext_on = nullptr;
@@ -111,6 +114,14 @@ int sdm_ctx_init_pme(sdm_ctx* c, const int32_t* grid);   // grid: [3] or nullptr
 void sdm_ctx_free_pme(sdm_ctx* c);
 int sdm_ctx_pme_enqueue(sdm_ctx* c, cudaStream_t s);      // no-op without sdm_ctx_init_pme
 int sdm_ctx_pme_info(sdm_ctx* c, const char* key, double* value);
+
+// kernels_gb.cu -- HCT generalized Born + ACE surface area
+int sdm_ctx_init_gb(sdm_ctx* c, const double* charge, const double* offset_radius, const double* scaled_radius,
+                    double solute_dielectric, double solvent_dielectric, int sa_ace);
+void sdm_ctx_free_gb(sdm_ctx* c);
+int sdm_ctx_gb_enqueue(sdm_ctx* c, cudaStream_t s);       // no-op without sdm_ctx_init_gb
+int sdm_ctx_gb_info(sdm_ctx* c, const char* key, double* value);
+int sdm_ctx_gb_born_radii(sdm_ctx* c, int replica, int state, double* out, cudaStream_t s);
 
 // pairlist.cu -- cluster-pair list path (SDM_PAIR_CLUSTER)
 int sdm_ctx_init_pairlist(sdm_ctx* c);

@@ -29,7 +29,8 @@ import sqlite3
 
 import numpy as np
 
-from .system import (CUTOFF_NONPERIODIC, CUTOFF_PERIODIC, EWALD, KCAL, NOCUTOFF, PME, NonbondedSystem)
+from .system import (CUTOFF_NONPERIODIC, CUTOFF_PERIODIC, EWALD, HCT, KCAL, NOCUTOFF, PME, GBSAHCTForce,
+                     NonbondedSystem)
 
 ANGSTROM = 0.1  # nm
 
@@ -127,14 +128,44 @@ class DesmondDMSFile(object):
             return np.zeros(3)
         return np.array([cell[0][0], cell[1][1], cell[2][2]], dtype=np.float64) * ANGSTROM
 
+    def _get_gb_params(self):
+        """(charge, radius, screened_radius) rows of the `hct` tables as desmonddmsfile75.py:290-313 hands them
+        to GBSAHCTForce.addParticle: radius in nm minus 0.009, screened_radius times that.  (finalize() subtracts
+        the offset again -- the reference does both, so both are done here.)  None when a file has no table."""
+        out = []
+        for conn, tables in zip(self._conn, self._tables):
+            if "hct" not in tables:
+                return None
+            for charge, radius, screened_radius in conn.execute("SELECT charge,radius,screened_radius FROM hct ORDER BY id"):
+                radius_n = radius * ANGSTROM - 0.009
+                out.append((charge, radius_n, screened_radius * radius_n))
+        return out
+
     def createSystem(self, nonbondedMethod=NOCUTOFF, nonbondedCutoff=1.0, reactionFieldDielectric=78.3,
-                     useDispersionCorrection=True, ewaldErrorTolerance=0.0005) -> NonbondedSystem:
+                     useDispersionCorrection=True, ewaldErrorTolerance=0.0005, implicitSolvent=None) -> NonbondedSystem:
         """The force-group-2 content of the reference's createSystem: the NonbondedForce
         particles, exclusions and 1-4 exceptions (desmonddmsfile75.py:772-850), with the cutoff
         method/distance of :418-426 (Ewald and PME included: direct space here, system.py) and the
-        box of :393-396; ewaldErrorTolerance as :426."""
+        box of :393-396; ewaldErrorTolerance as :426; implicitSolvent=HCT adds GBSAHCTForce(SA='ACE') from the
+        `hct` table and sets the reaction-field dielectric to 1 (:441-467).  The AGBNP / GVolSA models are external
+        plugins the reference only loads if present (:469-526): not built."""
         if nonbondedMethod not in (NOCUTOFF, CUTOFF_NONPERIODIC, CUTOFF_PERIODIC, EWALD, PME):
             raise ValueError("Illegal value for nonbondedMethod")
+        gb = None
+        if implicitSolvent is not None:
+            if implicitSolvent in ("AGBNP", "GVolSA", "AGBNP3"):
+                raise NotImplementedError("%s is not supported in this version" % implicitSolvent)
+            if implicitSolvent != HCT:
+                raise ValueError("Illegal implicit solvent method")
+            reactionFieldDielectric = 1.0          # nb.setReactionFieldDielectric(1.0), :451
+            gb_parms = self._get_gb_params()
+            if not gb_parms:
+                raise IOError("No HCT parameters found in DMS file")
+            gb = GBSAHCTForce(SA="ACE")
+            for p in gb_parms:
+                gb.addParticle(list(p))
+            gb.finalize()
+            gb.setForceGroup(self._nonbonded_force_group)
         charge, sigma, epsilon, excl, exc_pairs, exc_params = [], [], [], [], [], []
         for conn, tables, off in zip(self._conn, self._tables, self._offset[:-1]):
             q = """SELECT charge, sigma, epsilon FROM particle INNER JOIN nonbonded_param
@@ -174,7 +205,7 @@ class DesmondDMSFile(object):
                                method=int(nonbondedMethod), cutoff=float(nonbondedCutoff),
                                eps_rf=float(reactionFieldDielectric), box=box,
                                use_dispersion_correction=bool(useDispersionCorrection),
-                               ewald_tolerance=float(ewaldErrorTolerance))
+                               ewald_tolerance=float(ewaldErrorTolerance), gb=gb)
 
     # ---- write-back ---------------------------------------------------------------------------
     def _write_vec3(self, columns, values, scale):

@@ -20,7 +20,7 @@ import copy
 import numpy as np
 
 from . import _lib
-from .system import AlchemicalState, NonbondedSystem
+from .system import AlchemicalState, NonbondedSystem, apply_implicit_solvent
 
 
 class OpenMMException(Exception):
@@ -232,6 +232,7 @@ class LangevinIntegratorSDM(object):
         apply_restraints(self._ctx, system)     # what SDMUtils recorded on the system (force group 1 in the reference)
         if int(system.method) in (3, 4):        # NonbondedForce::Ewald / ::PME: the reference gets the complete sum
             self._ctx.enable_reciprocal_pme()   # from OpenMM; here direct space + reciprocal space on the device
+        apply_implicit_solvent(self._ctx, system)   # GBSAHCTForce in the nonbonded force group: both states
         self._displ_dirty = False
         return self
 

@@ -28,6 +28,72 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
                           "tests", "golden")
 
 
+HCT = "HCT"     # stands in for simtk.openmm.app.amberprmtopfile.HCT (desmonddmsfile75.py:40)
+
+
+class GBSAHCTForce:
+    """Host-side mirror of OpenMM 7.2/7.3 app/internal/customgbforces.py GBSAHCTForce as the reference's reader
+    uses it (example/desmonddmsfile75.py:460-465): addParticle([charge, radius, scale]) records, finalize()
+    turns every record into the CustomGBForce per-particle parameters charge, or = radius - OFFSET,
+    sr = scale * or (CustomAmberGBForceBase._addParticles).  The energy expressions are evaluated on the device
+    by csrc/kernels_gb.cu (sdm_enable_hct_gb).  Only the options the reference uses exist: no cutoff, kappa = 0,
+    SA None or 'ACE'.  OpenMM is not available in this image: restated, parity unpinned."""
+    OFFSET = 0.009
+
+    def __init__(self, solventDielectric=78.5, soluteDielectric=1, SA=None, cutoff=None, kappa=0.0):
+        if cutoff is not None or kappa != 0.0:
+            raise ValueError("only cutoff=None, kappa=0 (what desmonddmsfile75.py:460 asks for) is built")
+        if SA not in (None, "ACE"):
+            raise ValueError("Unknown surface area method: " + str(SA))
+        self.solventDielectric, self.soluteDielectric, self.SA = float(solventDielectric), float(soluteDielectric), SA
+        self.parameters = []
+        self._particles = None
+        self.force_group = 0
+
+    def addParticle(self, params):
+        self.parameters.append(list(params))
+
+    def setParticleParameters(self, idx, params):
+        self.parameters[idx] = list(params)
+
+    def finalize(self):
+        out = []
+        for charge, radius, scale in self.parameters:
+            offset_radius = float(radius) - self.OFFSET
+            out.append((float(charge), offset_radius, float(scale) * offset_radius))
+        self._particles = np.array(out, dtype=np.float64).reshape(-1, 3)
+
+    def setForceGroup(self, group):
+        self.force_group = int(group)
+
+    def getNumParticles(self):
+        return len(self.parameters)
+
+    def getParticleParameters(self, idx):
+        """(charge, or, sr) of a finalized force."""
+        if self._particles is None:
+            raise ValueError("finalize() has not been called")
+        return tuple(self._particles[idx])
+
+    def device_parameters(self):
+        """charge, or, sr arrays for sdm_enable_hct_gb."""
+        if self._particles is None:
+            raise ValueError("GBSAHCTForce.finalize() has not been called")
+        return self._particles[:, 0].copy(), self._particles[:, 1].copy(), self._particles[:, 2].copy()
+
+
+def apply_implicit_solvent(ctx, system):
+    """Switch the system's GB force (if any) on in a context: both states, every replica."""
+    gb = getattr(system, "gb", None)
+    if gb is None:
+        return
+    if gb.getNumParticles() != system.n_atoms:
+        raise ValueError("GBSAHCTForce has %d particles, the system %d" % (gb.getNumParticles(), system.n_atoms))
+    q, o, sr = gb.device_parameters()
+    ctx.enable_hct_gb(o, sr, charge=q, solute_dielectric=gb.soluteDielectric,
+                      solvent_dielectric=gb.solventDielectric, sa_ace=gb.SA == "ACE")
+
+
 @dataclass
 class NonbondedSystem:
     charge: np.ndarray            # [n] e
@@ -43,6 +109,7 @@ class NonbondedSystem:
     use_dispersion_correction: bool = True
     ewald_alpha: float = 0.0      # EWALD / PME: 0 = OpenMM's rule sqrt(-log(2 tol)) / cutoff
     ewald_tolerance: float = 5e-4
+    gb: object = None             # GBSAHCTForce (finalized) or None: implicit solvent in the nonbonded force group
 
     def ewald_alpha_effective(self) -> float:
         """The splitting parameter the library and the oracle use (NonbondedForceImpl::calcPMEParameters)."""
@@ -63,6 +130,13 @@ class NonbondedSystem:
     @property
     def n_atoms(self) -> int:
         return int(self.charge.shape[0])
+
+    def addForce(self, force):
+        """sys.addForce(gb) of desmonddmsfile75.py:464 -- the one extra force of the nonbonded group."""
+        if not isinstance(force, GBSAHCTForce):
+            raise TypeError("only a GBSAHCTForce can be added to the nonbonded force group")
+        self.gb = force
+        return 0
 
 
 @dataclass
