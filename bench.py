@@ -48,6 +48,17 @@ def load_case(workload: str):
                   "pairs; the reciprocal part enters through sdm_set_external_dual)"
     if workload == "cfg1":
         return S.cfg1(), "cfg1: OA-G6/G3 (230 atoms, CutoffNonPeriodic 15 nm, 38 displaced atoms)"
+    if workload == "cfg1:hct_gb":
+        c = S.cfg1()
+        c.system.eps_rf = 1.0       # desmonddmsfile75.py:451
+        rng = np.random.default_rng(1)        # the fixture has no hct table: synthetic radii 0.12-0.20 nm, scale 0.72-0.88
+        gb = S.GBSAHCTForce(SA="ACE")
+        for a in range(c.system.n_atoms):
+            gb.addParticle([c.system.charge[a], rng.uniform(0.12, 0.20), rng.uniform(0.72, 0.88)])
+        gb.finalize()
+        c.system.addForce(gb)
+        return c, "cfg1 with implicitSolvent=HCT (GBSAHCTForce(SA='ACE'), desmonddmsfile75.py:454-465; synthetic GB radii): " \
+                  "pair path + HCT-GB of both states on the device"
     if workload.startswith("synthetic:"):
         n = int(workload.split(":")[1])
         return S.synthetic_case(n_atoms=n, ligand_atoms=60, seed=1234), \
@@ -419,7 +430,7 @@ def sweep_leg(args, device, stream, peak_tflops, quick=False):
     import torch
     from openmm_sdm_plugin_b200 import system as S
     from openmm_sdm_plugin_b200.context import SDMContext
-    plan = [("cfg1", r) for r in (16, 128, 512)] + [("cfg2:pme", 16), ("cfg2:pme+reciprocal", 16), ("cfg2:pme+reciprocal", 1),
+    plan = [("cfg1", r) for r in (16, 128, 512)] + [("cfg1:hct_gb", 16), ("cfg1:hct_gb", 128), ("cfg2:pme", 16), ("cfg2:pme+reciprocal", 16), ("cfg2:pme+reciprocal", 1),
                                                       ("synthetic:50000", 16)]
     sizes = (5000, 20000, 100000) if quick else (5000, 10000, 20000, 50000, 100000, 200000, 500000)
     plan += [("synthetic:%d" % n, r) for n in sizes for r in (1, 8)]
@@ -434,6 +445,7 @@ def sweep_leg(args, device, stream, peak_tflops, quick=False):
                 c.set_stream(stream.cuda_stream)
                 if wl.endswith("+reciprocal"):
                     c.enable_reciprocal_pme()
+                S.apply_implicit_solvent(c, case.system)
                 for r in range(R):
                     c.set_alchemical(r, case.alch)
                     c.set_positions(r, case.positions + (rng.normal(scale=0.002, size=(n, 3)) if r else 0.0))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SDM_ABI_VERSION 1
+#define SDM_ABI_VERSION 2
 
 typedef enum {
     SDM_OK = 0,
@@ -70,6 +70,14 @@ typedef enum {
  * evaluation of that group per state.  Both values select the same arithmetic. */
 #define SDM_EWALD 3
 #define SDM_PME 4
+
+/* Lennard-Jones combining rule (sdm_system.lj_combining).  Lorentz-Berthelot is NonbondedForce's; the geometric
+ * rule is what createSystem(OPLS=True) of the reference's reader builds in the nonbonded force group: NonbondedForce
+ * with every epsilon zeroed plus CustomNonbondedForce("4 eps12 ((s12/r)^12 - (s12/r)^6); s12 = sqrt(s1 s2);
+ * eps12 = sqrt(eps1 eps2)") with the same exclusions and cutoff, no long-range correction
+ * (example/desmonddmsfile75.py:780-810, :427-438).  1-4 exceptions keep their own sigma / epsilon either way. */
+#define SDM_LJ_LORENTZ_BERTHELOT 0
+#define SDM_LJ_GEOMETRIC 1
 
 /* LangevinIntegratorSDM.h:120-122 and :143-145 */
 #define SDM_BIAS_LINEAR 0
@@ -114,6 +122,9 @@ typedef struct {
     double ewald_alpha;             /* SDM_EWALD / SDM_PME: splitting parameter (1/nm); 0 = OpenMM's rule
                                        sqrt(-log(2 tol)) / cutoff (NonbondedForceImpl::calcPMEParameters) */
     double ewald_tolerance;         /* tol of that rule; 0 = NonbondedForce's default 5e-4 */
+    int32_t lj_combining;           /* SDM_LJ_LORENTZ_BERTHELOT (0, default) / SDM_LJ_GEOMETRIC; the geometric rule
+                                       needs use_dispersion_correction = 0 with a periodic method */
+    int32_t reserved_;
 } sdm_system;
 
 typedef struct {

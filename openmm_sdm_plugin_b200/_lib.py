@@ -29,7 +29,8 @@ class SdmSystem(C.Structure):
                 ("charge", C.c_void_p), ("sigma", C.c_void_p), ("epsilon", C.c_void_p),
                 ("exclusions", C.c_void_p), ("exceptions", C.c_void_p),
                 ("exception_params", C.c_void_p), ("displacement", C.c_void_p),
-                ("ewald_alpha", C.c_double), ("ewald_tolerance", C.c_double)]
+                ("ewald_alpha", C.c_double), ("ewald_tolerance", C.c_double),
+                ("lj_combining", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class SdmOptions(C.Structure):
@@ -176,7 +177,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if L.sdm_abi_version() != 1:
+        if L.sdm_abi_version() != 2:
             raise ImportError("libsdmb200.so ABI version mismatch")
         _LIB = L
     return _LIB

@@ -86,6 +86,7 @@ class SDMContext:
         s.n_replicas = self.R
         s.ewald_alpha = float(getattr(system, "ewald_alpha", 0.0))
         s.ewald_tolerance = float(getattr(system, "ewald_tolerance", 0.0))
+        s.lj_combining = 1 if getattr(system, "lj_geometric", False) else 0
         (s.charge, s.sigma, s.epsilon, s.exclusions, s.exceptions, s.exception_params,
          s.displacement) = [_ptr(a) for a in keep]
         o = _lib.SdmOptions()

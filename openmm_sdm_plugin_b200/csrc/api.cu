@@ -208,6 +208,10 @@ int sdm_create(const sdm_system* s_in, const sdm_options* opt_in, sdm_ctx** out)
     if (s->method < SDM_NOCUTOFF || s->method > SDM_CUTOFF_PERIODIC)
         return fail(SDM_ERR_INVALID, "unknown nonbonded method");
     if (s->method != SDM_NOCUTOFF && !(s->cutoff > 0)) return fail(SDM_ERR_INVALID, "cutoff must be positive");
+    if (s->lj_combining != SDM_LJ_LORENTZ_BERTHELOT && s->lj_combining != SDM_LJ_GEOMETRIC)
+        return fail(SDM_ERR_INVALID, "unknown Lennard-Jones combining rule");
+    if (s->lj_combining == SDM_LJ_GEOMETRIC && s->use_dispersion_correction && s->method >= SDM_CUTOFF_PERIODIC)
+        return fail(SDM_ERR_INVALID, "no dispersion correction with the geometric rule (the reference switches it off: desmonddmsfile75.py:428,438)");
     if (s->method == SDM_CUTOFF_PERIODIC)
         for (int d = 0; d < 3; d++)
             if (!(s->box[d] > 0) || 2 * s->cutoff > s->box[d])
@@ -291,14 +295,16 @@ int sdm_create(const sdm_system* s_in, const sdm_options* opt_in, sdm_ctx** out)
     T.band = (float)(64.0 * FLT_EPSILON * T.rc * std::max(cmax, T.rc));
     if (s->method == SDM_CUTOFF_PERIODIC && s->use_dispersion_correction)
         T.e_disp = dispersion_coefficient(s) / (s->box[0] * s->box[1] * s->box[2]);
+    T.lj_geom = s->lj_combining == SDM_LJ_GEOMETRIC ? 1 : 0;
 
-    // per-atom parameters as the Reference kernel stores them: sigma/2, 2*sqrt(eps)
+    // per-atom parameters as the Reference kernel stores them: sigma/2, 2*sqrt(eps); with the geometric rule
+    // sigma itself (sigma_ij^2 = sigma_i sigma_j)
     std::vector<double> q(n), hsig(n), heps(n);
     std::vector<float4> parf(n);
     const double sqrtK = std::sqrt(SDM_K_COULOMB);
     for (int i = 0; i < n; i++) {
         q[i] = s->charge[i];
-        hsig[i] = 0.5 * s->sigma[i];
+        hsig[i] = T.lj_geom ? s->sigma[i] : 0.5 * s->sigma[i];
         heps[i] = 2.0 * std::sqrt(s->epsilon[i]);
         parf[i] = make_float4((float)(q[i] * sqrtK), (float)hsig[i], (float)heps[i], 0.f);
     }

@@ -141,7 +141,7 @@ allpairs_kernel(Topology T, const float4* __restrict__ posq_all, const double* _
                 const float rinv = rsqrtf(r2);
                 const float rinv2 = rinv * rinv;
                 const float sig = pari.y + parj.x;
-                const float sr2 = sig * sig * rinv2;
+                const float sr2 = (T.lj_geom ? pari.y * parj.x : sig * sig) * rinv2;   // geometric rule: sigma_i sigma_j
                 const float sr6 = sr2 * sr2 * sr2;
                 const float eps = pari.z * parj.y;
                 const float qq = pi.w * pj.w;
@@ -397,7 +397,7 @@ __device__ __forceinline__ void probe_pair(const Topology& T, const double* __re
     const bool in2 = !cutoff || g2.r2 <= T.rc2;
     if (!(in1 || in2)) return;
     if (check_excl && is_excluded(T, P.i, k)) return;
-    const double sig = P.hsig + T.hsig[k], eps = P.heps * T.heps[k];
+    const double sig = T.lj_geom ? sqrt(P.hsig * T.hsig[k]) : P.hsig + T.hsig[k], eps = P.heps * T.heps[k];
     const double qq = SDM_K_COULOMB * P.q * T.q[k];
     const double w = (gk != 0) ? 0.5 : 1.0;
     const int wc = (gk != 0) ? 1 : 2;

@@ -132,6 +132,7 @@ __device__ __forceinline__ void load_jrec(const float4* __restrict__ jrec, const
 struct PairConsts {
     float rc2, krf, crf, band;
     float alpha;   // Ewald splitting parameter (EWALD instantiations)
+    int geom;      // 1: sigma_ij^2 = sigma_i sigma_j (SDM_LJ_GEOMETRIC; GEOM instantiations)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -194,7 +195,7 @@ __device__ __forceinline__ float pair_term_f32(const float r2, const float qi, c
     const float rinv = rsqrt_approx(r2);
     const float rinv2 = rinv * rinv;
     const float sig = si + pj.x;
-    const float sr2 = (sig * sig) * rinv2;
+    const float sr2 = (K.geom ? si * pj.x : sig * sig) * rinv2;   // geometric rule: the parameter is sigma itself
     const float sr6 = sr2 * sr2 * sr2;
     const float elj = (ei * pj.y) * sr6;
     const float qq = qi * qj;
@@ -219,7 +220,7 @@ __device__ __forceinline__ float pair_term_f32(const float r2, const float qi, c
 //   e_lj = elj*(sr6 - 1) = a - elj,   elj*(12*sr6 - 6) = 6*(a + e_lj)   with a = elj*sr6
 // LJ = false: the j-atom has no Lennard-Jones term (epsilon_j == 0: elj, a and e_lj are exactly
 // zero), so the eleven packed instructions that would compute them are left out -- same bits out.
-template <bool MASKED, bool EXACT, bool EMIT, int HI_OFF, bool LJ = true, bool EWALD = false>
+template <bool MASKED, bool EXACT, bool EMIT, int HI_OFF, bool LJ = true, bool EWALD = false, bool GEOM = false>
 __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const float4 xj,
                                           const float2 pj, const bool allow_lo, const bool allow_hi,
                                           const PairConsts& K, Acc2& fi, Acc2& fj, f2& en, int& cnt,
@@ -261,8 +262,10 @@ __device__ __forceinline__ void tile_step(const IPair* __restrict__ ip, const fl
     }
     f2 dEdR, e;
     if (LJ) {
+        // Lorentz-Berthelot: the parameters are sigma/2 and sigma_ij their sum; geometric rule (the OPLS
+        // CustomNonbondedForce of desmonddmsfile75.py:781): the parameters are sigma and sigma_ij^2 their product
         const f2 sig = add2(a2.x, bc(pj.x));
-        const f2 sr2 = mul2(mul2(sig, sig), rinv2);
+        const f2 sr2 = mul2(GEOM ? mul2(a2.x, bc(pj.x)) : mul2(sig, sig), rinv2);
         const f2 sr6 = mul2(mul2(sr2, sr2), sr2);
         const f2 elj = mul2(mul2(a2.y, bc(pj.y)), sr6);
         const f2 a = mul2(elj, sr6);
@@ -324,7 +327,7 @@ __device__ __noinline__ void fix_band_row(const Topology& T, const PairListView&
                                           int jslot, float4 xj, float2 pj, uint32_t allow, float* en,
                                           int* cnt, const EmitCtx* ec) {
     const size_t plane = (size_t)V.nslot_cap;
-    const PairConsts K{T.rc2f, T.krff, T.crff, T.band, EWALD ? T.alphaf : 0.f};
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band, EWALD ? T.alphaf : 0.f, T.lj_geom};
     const int aj = V.atom[jslot];
     if (aj < 0) return;
     for (int a = 0; a < NI; a++) {
@@ -373,7 +376,7 @@ __device__ __forceinline__ void row_halve(float (&v)[N], const int lane) {
     }
 }
 
-template <int NI, bool PERIODIC, bool EXACT, bool EMIT, bool EWALD>
+template <int NI, bool PERIODIC, bool EXACT, bool EMIT, bool EWALD, bool GEOM>
 __device__ __forceinline__ void process_row_unit(const Topology& T, const PairListView& V,
                                                  const double* __restrict__ pos_all,
                                                  long long* __restrict__ f1acc, double* __restrict__ epart,
@@ -383,7 +386,7 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
     constexpr int NP = NI / 2;
     const int ibase = (u.c0n & 0xfffffff) * nbl::kClusterSize;
     const int ni = (u.c0n >> 28) * nbl::kClusterSize;
-    const PairConsts K{T.rc2f, T.krff, T.crff, T.band, EWALD ? T.alphaf : 0.f};
+    const PairConsts K{T.rc2f, T.krff, T.crff, T.band, EWALD ? T.alphaf : 0.f, T.lj_geom};
     const uint32_t dummy_ent = (uint32_t)V.dummy_slot | (nbl::kShiftZero << 26);
 
     // row entries two steps ahead, j-atom data one step ahead
@@ -464,13 +467,13 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
             const uint32_t allow = idx < mend ? (uint32_t)V.jallow[idx] : 0xffffu;
 #pragma unroll
             for (int p = 0; p < NP; p++)
-                tile_step<true, EXACT, EMIT, 1, true, EWALD>(s_ip + p, xj, pj, ((allow >> (2 * p)) & 1u) != 0u,
+                tile_step<true, EXACT, EMIT, 1, true, EWALD, GEOM>(s_ip + p, xj, pj, ((allow >> (2 * p)) & 1u) != 0u,
                                                 ((allow >> (2 * p + 1)) & 1u) != 0u, K, fi[p], fj, en, cnt,
                                                 tmin, ec, ibase + 2 * p, jslot);
         } else if (k < lsteps) {
 #pragma unroll
             for (int p = 0; p < NP; p++)
-                tile_step<false, EXACT, EMIT, 1, true, EWALD>(s_ip + p, xj, pj, true, true, K, fi[p], fj, en, cnt, tmin, ec,
+                tile_step<false, EXACT, EMIT, 1, true, EWALD, GEOM>(s_ip + p, xj, pj, true, true, K, fi[p], fj, en, cnt, tmin, ec,
                                                  ibase + 2 * p, jslot);
         } else {   // the tail of the row: j-atoms without a Lennard-Jones term (water hydrogens)
 #pragma unroll
@@ -607,7 +610,7 @@ __device__ __forceinline__ void process_row_unit(const Topology& T, const PairLi
     __syncwarp();   // the staging area is reused by the next unit of this warp
 }
 
-template <int NI, bool PERIODIC, bool EXACT, bool EMIT, bool EWALD = false>
+template <int NI, bool PERIODIC, bool EXACT, bool EMIT, bool EWALD = false, bool GEOM = false>
 __global__ void __launch_bounds__(kWarps * 32, NI == 16 ? 16 : SDM_ROW_MINB)
 pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ PairListView V,
                 const double* __restrict__ pos_all, long long* __restrict__ f1acc,
@@ -638,7 +641,7 @@ pair_row_kernel(const __grid_constant__ Topology T, const __grid_constant__ Pair
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= nrunits) break;
         if (V.runit_order) unit = V.runit_order[unit];   // longest units first
-        process_row_unit<NI, PERIODIC, EXACT, EMIT, EWALD>(T, V, pos_all, f1acc, epart, cpart, unit, V.runits[unit], lane,
+        process_row_unit<NI, PERIODIC, EXACT, EMIT, EWALD, GEOM>(T, V, pos_all, f1acc, epart, cpart, unit, V.runits[unit], lane,
                                                     s_ip[warp], s_shift, ec);
     }
 }
@@ -703,24 +706,32 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
     if (emit) cudaMemsetAsync(unit_counter, 0, sizeof(int), s);
     const bool periodic = T.method == SDM_CUTOFF_PERIODIC;
     const PairEmit em = emit ? *emit : PairEmit{nullptr, nullptr, 0, -1};
-#define SDM_LAUNCH(N, P, X, E, W)                                                                 \
+#define SDM_LAUNCH(N, P, X, E, W, G)                                                               \
     do {                                                                                          \
         static int resident = 0; /* blocks per SM the hardware keeps resident (register limited) */ \
         if (!resident) {                                                                          \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_row_kernel<N, P, X, E, W>, \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pair_row_kernel<N, P, X, E, W, G>, \
                                                               kWarps * 32, 0) != cudaSuccess ||    \
                 resident < 1)                                                                     \
                 resident = SDM_ROW_MINB;                                                          \
             if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
         }                                                                                         \
         const int grid = std::min((V.nrunits_ub + kWarps - 1) / kWarps, num_sms * resident);       \
-        pair_row_kernel<N, P, X, E, W><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
+        pair_row_kernel<N, P, X, E, W, G><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
                                                                    unit_counter, em);             \
+    } while (0)
+    // geometric combining rule: its own instantiations of the production kernel; the debug build (pair records
+    // only, forces discarded) has none
+    const bool geom = T.lj_geom != 0 && !emit;
+#define SDM_LAUNCH_G(N, P, X, E, W)                                                               \
+    do {                                                                                          \
+        if (!E && geom) SDM_LAUNCH(N, P, X, false, W, true);                                      \
+        else SDM_LAUNCH(N, P, X, E, W, false);                                                    \
     } while (0)
 #define SDM_LAUNCH_N(P, X, E, W)                                                                  \
     do {                                                                                          \
-        if (V.row_group == 2) SDM_LAUNCH(16, P, X, E, W);                                         \
-        else SDM_LAUNCH(8, P, X, E, W);                                                           \
+        if (V.row_group == 2) SDM_LAUNCH_G(16, P, X, E, W);                                       \
+        else SDM_LAUNCH_G(8, P, X, E, W);                                                         \
     } while (0)
     if (T.ewald) {   // direct-space Ewald / PME: periodic by definition
         if (emit) { if (exact) SDM_LAUNCH_N(true, true, true, true); else SDM_LAUNCH_N(true, false, true, true); }
@@ -737,6 +748,7 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
         else SDM_LAUNCH_N(false, false, false, false);
     }
 #undef SDM_LAUNCH_N
+#undef SDM_LAUNCH_G
 #undef SDM_LAUNCH
 }
 

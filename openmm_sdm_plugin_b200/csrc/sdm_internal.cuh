@@ -31,9 +31,10 @@ struct Topology {
     int n_excl_pairs;                   // excluded pairs (i < j) that get the erf(alpha r)/r correction
     const int* excl_pairs;              // [2*n_excl_pairs]
     const double* q;       // [n] charge
-    const double* hsig;    // [n] sigma/2
+    int lj_geom;           // 1: SDM_LJ_GEOMETRIC -- sigma_ij = sqrt(sigma_i sigma_j); hsig / parf.y then hold sigma itself
+    const double* hsig;    // [n] sigma/2 (Lorentz-Berthelot) or sigma (geometric rule)
     const double* heps;    // [n] 2*sqrt(eps)
-    const float4* parf;    // [n] (q*sqrt(K), sigma/2, 2*sqrt(eps), 0) float
+    const float4* parf;    // [n] (q*sqrt(K), sigma/2 or sigma, 2*sqrt(eps), 0) float
     const double* disp;    // [3n] displacement map
     const int* group;      // [n] id of the displacement vector (0 = not displaced)
     const int* lig_idx;    // [n_lig] displaced atoms, ascending

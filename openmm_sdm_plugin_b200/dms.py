@@ -142,15 +142,21 @@ class DesmondDMSFile(object):
         return out
 
     def createSystem(self, nonbondedMethod=NOCUTOFF, nonbondedCutoff=1.0, reactionFieldDielectric=78.3,
-                     useDispersionCorrection=True, ewaldErrorTolerance=0.0005, implicitSolvent=None) -> NonbondedSystem:
+                     useDispersionCorrection=True, ewaldErrorTolerance=0.0005, implicitSolvent=None,
+                     OPLS=False) -> NonbondedSystem:
         """The force-group-2 content of the reference's createSystem: the NonbondedForce
         particles, exclusions and 1-4 exceptions (desmonddmsfile75.py:772-850), with the cutoff
         method/distance of :418-426 (Ewald and PME included: direct space here, system.py) and the
         box of :393-396; ewaldErrorTolerance as :426; implicitSolvent=HCT adds GBSAHCTForce(SA='ACE') from the
         `hct` table and sets the reaction-field dielectric to 1 (:441-467).  The AGBNP / GVolSA models are external
-        plugins the reference only loads if present (:469-526): not built."""
+        plugins the reference only loads if present (:469-526): not built.  OPLS=True forces the geometric combining
+        rule: the reference zeroes every NonbondedForce epsilon and adds a CustomNonbondedForce with
+        sigma12 = sqrt(s1 s2), eps12 = sqrt(e1 e2) on the same exclusions and cutoff, and switches both long-range
+        corrections off (:780-810, :427-438) -- here one flag of the pair kernels (system.lj_geometric)."""
         if nonbondedMethod not in (NOCUTOFF, CUTOFF_NONPERIODIC, CUTOFF_PERIODIC, EWALD, PME):
             raise ValueError("Illegal value for nonbondedMethod")
+        if OPLS:
+            useDispersionCorrection = False        # nb.setUseDispersionCorrection(False), cnb.setUseLongRangeCorrection(False)
         gb = None
         if implicitSolvent is not None:
             if implicitSolvent in ("AGBNP", "GVolSA", "AGBNP3"):
@@ -205,7 +211,7 @@ class DesmondDMSFile(object):
                                method=int(nonbondedMethod), cutoff=float(nonbondedCutoff),
                                eps_rf=float(reactionFieldDielectric), box=box,
                                use_dispersion_correction=bool(useDispersionCorrection),
-                               ewald_tolerance=float(ewaldErrorTolerance), gb=gb)
+                               ewald_tolerance=float(ewaldErrorTolerance), gb=gb, lj_geometric=bool(OPLS))
 
     # ---- write-back ---------------------------------------------------------------------------
     def _write_vec3(self, columns, values, scale):

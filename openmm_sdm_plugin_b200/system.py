@@ -110,6 +110,8 @@ class NonbondedSystem:
     ewald_alpha: float = 0.0      # EWALD / PME: 0 = OpenMM's rule sqrt(-log(2 tol)) / cutoff
     ewald_tolerance: float = 5e-4
     gb: object = None             # GBSAHCTForce (finalized) or None: implicit solvent in the nonbonded force group
+    lj_geometric: bool = False    # createSystem(OPLS=True): Lennard-Jones through the CustomNonbondedForce with
+                                  # sigma12 = sqrt(s1 s2), eps12 = sqrt(e1 e2) (desmonddmsfile75.py:780-810)
 
     def ewald_alpha_effective(self) -> float:
         """The splitting parameter the library and the oracle use (NonbondedForceImpl::calcPMEParameters)."""

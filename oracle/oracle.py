@@ -23,7 +23,8 @@ class OrcSystem(C.Structure):
                 ("n_exceptions", C.c_int32), ("pad_", C.c_int32),
                 ("charge", C.c_void_p), ("sigma", C.c_void_p), ("epsilon", C.c_void_p),
                 ("exclusions", C.c_void_p), ("exceptions", C.c_void_p),
-                ("exception_params", C.c_void_p), ("ewald_alpha", C.c_double)]
+                ("exception_params", C.c_void_p), ("ewald_alpha", C.c_double),
+                ("lj_geometric", C.c_int32), ("pad2_", C.c_int32)]
 
 
 class OrcAlch(C.Structure):
@@ -107,6 +108,7 @@ class _Sys:
         ewald = int(s.method) in (3, 4)
         c.method = 2 if ewald else int(s.method)
         c.ewald_alpha = float(s.ewald_alpha_effective()) if ewald else 0.0
+        c.lj_geometric = int(bool(getattr(s, "lj_geometric", False)))
         c.cutoff = float(s.cutoff)
         c.eps_rf = float(s.eps_rf)
         for d in range(3):

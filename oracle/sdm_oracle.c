@@ -464,6 +464,14 @@ int orc_nonbonded(const orc_system* sys, const double* pos, double* forces,
             double qq = ORC_ONE_4PI_EPS0 * sys->charge[ii] * sys->charge[jj];
             double dEdR = eps * (12.0 * sig6 - 6.0) * sig6;
             double e = eps * (sig6 - 1.0) * sig6;
+            if (sys->lj_geometric) {
+                /* the CustomNonbondedForce expression of desmonddmsfile75.py:781 and its -r dE/dr */
+                double sigma12 = sqrt(sys->sigma[ii] * sys->sigma[jj]);
+                double epsilon12 = sqrt(sys->epsilon[ii] * sys->epsilon[jj]);
+                double x6 = pow(sigma12 / r, 6.0), x12 = pow(sigma12 / r, 12.0);
+                e = 4.0 * epsilon12 * (x12 - x6);
+                dEdR = 4.0 * epsilon12 * (12.0 * x12 - 6.0 * x6);
+            }
             if (ewald_alpha > 0) {
                 double alphaR = ewald_alpha * r;
                 dEdR += qq * inverseR * (erfc(alphaR) + 2.0 * alphaR * exp(-alphaR * alphaR) / ORC_SQRT_PI);

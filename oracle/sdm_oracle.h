@@ -62,6 +62,13 @@ typedef struct {
     double ewald_alpha;          /* > 0 (with ORC_CUTOFF_PERIODIC): NonbondedForce::Ewald / ::PME, DIRECT-SPACE part
                                     only -- erfc(alpha r)/r pair terms and the erf(alpha r)/r correction of the
                                     excluded pairs (ReferenceLJCoulombIxn::calculateEwaldIxn, includeDirect) */
+    int32_t lj_geometric;        /* 1: the force group as createSystem(OPLS=True) builds it
+                                    (example/desmonddmsfile75.py:780-810): NonbondedForce keeps the charges (every
+                                    epsilon 0) and a CustomNonbondedForce adds 4 eps12 ((s12/r)^12 - (s12/r)^6),
+                                    s12 = sqrt(s1 s2), eps12 = sqrt(eps1 eps2), same exclusions and cutoff, no
+                                    long-range correction.  (ReferenceCustomNonbondedIxn drops r >= cutoff where
+                                    NonbondedForce drops r > cutoff: the sets differ only at r == cutoff exactly.) */
+    int32_t pad2_;
 } orc_system;
 
 /* Alchemical / soft-core state held by LangevinIntegratorSDM

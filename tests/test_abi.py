@@ -30,13 +30,13 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(_lib.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(L, name), name
-    assert _lib.lib().sdm_abi_version() == 1
+    assert _lib.lib().sdm_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
     assert C.sizeof(_lib.SdmAlch) == 2 * 4 + 11 * 8 + 2 * 4 + 4 * 8 + 8 * 8
     assert C.sizeof(_lib.SdmScalars) == 14 * 8 + 3 * 8 + 2 * 4
-    assert C.sizeof(_lib.SdmSystem) == 2 * 4 + 2 * 8 + 3 * 8 + 4 * 4 + 7 * 8 + 2 * 8
+    assert C.sizeof(_lib.SdmSystem) == 2 * 4 + 2 * 8 + 3 * 8 + 4 * 4 + 7 * 8 + 2 * 8 + 2 * 4
     assert C.sizeof(_lib.SdmOptions) == 2 * 4 + 8 + 2 * 4 + 8 * 4
 
 

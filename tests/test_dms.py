@@ -133,3 +133,16 @@ def test_shipped_fixtures_match_golden(dms, npz, tmp_path):
         assert np.array_equal(d.getBox(), z["box"])
     for k in ("charge", "sigma", "epsilon", "exclusions", "exception_pairs", "exception_params"):
         assert np.array_equal(getattr(sysd, k), z[k]), k
+
+
+def test_opls_option_selects_the_geometric_rule(tmp_path):
+    """createSystem(OPLS=True): desmonddmsfile75.py:780-810 and :427-438."""
+    p = str(tmp_path / "a.dms")
+    make_dms(p)
+    with DesmondDMSFile(p) as d:
+        lb = d.createSystem(nonbondedMethod=S.CUTOFF_PERIODIC, nonbondedCutoff=0.9)
+        geo = d.createSystem(nonbondedMethod=S.CUTOFF_PERIODIC, nonbondedCutoff=0.9, OPLS=True)
+    assert not lb.lj_geometric and lb.use_dispersion_correction
+    assert geo.lj_geometric and not geo.use_dispersion_correction
+    assert np.array_equal(lb.sigma, geo.sigma) and np.array_equal(lb.epsilon, geo.epsilon)
+    assert np.array_equal(lb.exclusions, geo.exclusions) and np.array_equal(lb.exception_params, geo.exception_params)

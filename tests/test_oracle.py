@@ -328,3 +328,40 @@ def test_ewald_dual_state_eval_runs_through_the_reference_sequence():
     e1 = O.nonbonded(sysd, pos)["E"]
     e2 = O.nonbonded(sysd, pos + disp)["E"]
     assert abs(res["E1"] - e1) <= 1e-12 * abs(e1) and abs(res["u"] - (e2 - e1)) <= 1e-9 * max(1.0, abs(e2 - e1))
+
+
+def test_geometric_combining_rule_against_the_literal_expression():
+    """createSystem(OPLS=True), desmonddmsfile75.py:780-810: NonbondedForce keeps the charges, the Lennard-Jones part is
+    the CustomNonbondedForce expression 4 eps12 ((s12/r)^12 - (s12/r)^6) with geometric means; no cutoff here, so the
+    total is a plain double loop."""
+    import copy
+    case = S.cfg1()
+    sysd = copy.copy(case.system)
+    sysd.method = S.NOCUTOFF
+    sysd.lj_geometric = True
+    sysd.exception_pairs = np.zeros((0, 2), np.int32)
+    sysd.exception_params = np.zeros((0, 3))
+    pos = case.positions
+    out = O.nonbonded(sysd, pos)
+    n = sysd.n_atoms
+    excl = {(min(a, b), max(a, b)) for a, b in sysd.exclusions.tolist()}
+    e = 0.0
+    f = np.zeros_like(pos)
+    for i in range(n):
+        for j in range(i + 1, n):
+            if (i, j) in excl:
+                continue
+            d = pos[i] - pos[j]
+            r = np.sqrt(d @ d)
+            s12 = np.sqrt(sysd.sigma[i] * sysd.sigma[j])
+            e12 = np.sqrt(sysd.epsilon[i] * sysd.epsilon[j])
+            x6 = (s12 / r) ** 6
+            qq = 138.935456 * sysd.charge[i] * sysd.charge[j]
+            e += 4 * e12 * (x6 * x6 - x6) + qq / r
+            dedr = -4 * e12 * (12 * x6 * x6 - 6 * x6) / r - qq / r ** 2
+            f[i] -= dedr * d / r
+            f[j] += dedr * d / r
+    assert out["E"] == pytest.approx(e, rel=1e-12)
+    assert np.abs(out["forces"] - f).max() <= 1e-10 * np.abs(f).max()
+    lb = O.nonbonded(case.system, pos)
+    assert abs(lb["E"] - out["E"]) > 1e-3                      # the rule matters on this fixture
