@@ -23,8 +23,14 @@ public:
     // values of OpenMM::NonbondedForce::NonbondedMethod that the path supports
     enum NonbondedMethod { NoCutoff = 0, CutoffNonPeriodic = 1, CutoffPeriodic = 2, Ewald = 3, PME = 4 };
     struct Exception { int p1, p2; double chargeProd, sigma, epsilon; };
+    // Lorentz-Berthelot is NonbondedForce's rule; Geometric stands for the NonbondedForce (epsilons zeroed) +
+    // CustomNonbondedForce pair that createSystem(OPLS=True) builds (example/desmonddmsfile75.py:780-810)
+    enum CombiningRule { LorentzBerthelot = 0, Geometric = 1 };
+    // GBSAHCTForce(SA='ACE') of desmonddmsfile75.py:460 as its CustomGBForce holds it: charge, or, sr per particle
+    struct GBParticle { double charge, offsetRadius, scaledRadius; };
 
-    B200NonbondedForce() : method(NoCutoff), cutoff(1.0), rfDielectric(78.3), ewaldTol(5e-4), dispersion(true) {
+    B200NonbondedForce() : method(NoCutoff), cutoff(1.0), rfDielectric(78.3), ewaldTol(5e-4), dispersion(true),
+                           rule(LorentzBerthelot), gbSolute(1.0), gbSolvent(78.5), gbAce(true) {
         box[0] = box[1] = box[2] = 0.0;
         setForceGroup(2);
     }
@@ -53,6 +59,19 @@ public:
     void setEwaldErrorTolerance(double t) { ewaldTol = t; }
     bool getUseDispersionCorrection() const { return dispersion; }
     void setUseDispersionCorrection(bool b) { dispersion = b; }
+    CombiningRule getCombiningRule() const { return rule; }
+    void setCombiningRule(CombiningRule r) { rule = r; }
+    int getNumGBParticles() const { return (int)gb.size(); }
+    int addGBParticle(double q, double offsetRadius, double scaledRadius) {
+        gb.push_back(GBParticle{q, offsetRadius, scaledRadius});
+        return (int)gb.size() - 1;
+    }
+    const GBParticle& getGBParticle(int i) const { return gb[i]; }
+    void setGBDielectrics(double solute, double solvent) { gbSolute = solute; gbSolvent = solvent; }
+    double getGBSoluteDielectric() const { return gbSolute; }
+    double getGBSolventDielectric() const { return gbSolvent; }
+    void setGBSurfaceAreaACE(bool on) { gbAce = on; }
+    bool getGBSurfaceAreaACE() const { return gbAce; }
     // orthorhombic box edges (nm); System::getDefaultPeriodicBoxVectors in a full OpenMM
     void setPeriodicBox(double a, double b, double c) { box[0] = a; box[1] = b; box[2] = c; }
     const double* getPeriodicBox() const { return box; }
@@ -70,6 +89,10 @@ private:
     NonbondedMethod method;
     double cutoff, rfDielectric, ewaldTol, box[3];
     bool dispersion;
+    CombiningRule rule;
+    std::vector<GBParticle> gb;
+    double gbSolute, gbSolvent;
+    bool gbAce;
 };
 
 }  // namespace SDMB200

@@ -150,6 +150,7 @@ void B200IntegrateLangevinStepSDMKernel::initialize(const System& system, const 
         s.exclusions = excl.data(); s.exceptions = exc.data(); s.exception_params = excp.data();
         s.displacement = displ.data();
         s.ewald_tolerance = nb->getEwaldErrorTolerance();   // Ewald / PME: alpha by OpenMM's rule
+        s.lj_combining = nb->getCombiningRule() == B200NonbondedForce::Geometric ? SDM_LJ_GEOMETRIC : SDM_LJ_LORENTZ_BERTHELOT;
         sdm_options opt;
         sdm_default_options(&opt);
         check(sdm_create(&s, &opt, &ctx), "sdm_create");
@@ -157,6 +158,17 @@ void B200IntegrateLangevinStepSDMKernel::initialize(const System& system, const 
         // in the pair kernels, reciprocal space (smooth PME, both states) on the device as well
         if (s.method == SDM_EWALD || s.method == SDM_PME)
             check(sdm_enable_reciprocal_pme(ctx, nullptr), "sdm_enable_reciprocal_pme");
+        // implicit solvent in the nonbonded group (GBSAHCTForce): both states on the device as well
+        if (nb->getNumGBParticles() > 0) {
+            if (nb->getNumGBParticles() != n) throw OpenMMException("B200NonbondedForce: one GB particle per particle");
+            std::vector<double> gq(n), go(n), gs(n);
+            for (int i = 0; i < n; i++) {
+                const B200NonbondedForce::GBParticle& g = nb->getGBParticle(i);
+                gq[i] = g.charge; go[i] = g.offsetRadius; gs[i] = g.scaledRadius;
+            }
+            check(sdm_enable_hct_gb(ctx, gq.data(), go.data(), gs.data(), nb->getGBSoluteDielectric(),
+                                    nb->getGBSolventDielectric(), nb->getGBSurfaceAreaACE() ? 1 : 0), "sdm_enable_hct_gb");
+        }
     } else {
         // ---- level B: OpenMM evaluates force group 2; the plugin's own kernels run on the device -----
         const size_t bytes = sizeof(float) * 4 * (size_t)n;

@@ -75,6 +75,9 @@ struct sdmb200_nonbonded {
     const double *charge, *sigma, *epsilon;       // [n]
     const int* exception_pairs;                   // [2*n_exceptions] every addException pair
     const double* exception_params;               // [3*n_exceptions] chargeProd, sigma, epsilon
+    int lj_geometric, gb_ace;                     // createSystem(OPLS=True); GBSAHCTForce SA='ACE'
+    const double *gb_charge, *gb_or, *gb_sr;      // [n] GBSAHCTForce parameters, or NULL: no implicit solvent
+    double gb_solute, gb_solvent;
 };
 
 const char* sdmb200_adapter_last_error() { return g_error.c_str(); }
@@ -112,6 +115,12 @@ int sdmb200_adapter_run(int level, int n, const double* masses, double* position
             f->setReactionFieldDielectric(nb->eps_rf);
             f->setUseDispersionCorrection(nb->use_dispersion_correction != 0);
             f->setPeriodicBox(nb->box[0], nb->box[1], nb->box[2]);
+            if (nb->lj_geometric) f->setCombiningRule(SDMB200::B200NonbondedForce::Geometric);
+            if (nb->gb_or) {
+                for (int i = 0; i < n; i++) f->addGBParticle(nb->gb_charge[i], nb->gb_or[i], nb->gb_sr[i]);
+                f->setGBDielectrics(nb->gb_solute, nb->gb_solvent);
+                f->setGBSurfaceAreaACE(nb->gb_ace != 0);
+            }
             system.addForce(f);               // force group 2, evaluates to nothing on the OpenMM side
         } else {
             system.addForce(new Force(2));    // OpenMM's own NonbondedForce (the callback)

@@ -148,7 +148,10 @@ class B200Nonbonded(C.Structure):
     _fields_ = [("method", C.c_int), ("n_exceptions", C.c_int), ("use_dispersion_correction", C.c_int), ("pad_", C.c_int),
                 ("cutoff", C.c_double), ("eps_rf", C.c_double), ("box", C.c_double * 3),
                 ("charge", C.c_void_p), ("sigma", C.c_void_p), ("epsilon", C.c_void_p),
-                ("exception_pairs", C.c_void_p), ("exception_params", C.c_void_p)]
+                ("exception_pairs", C.c_void_p), ("exception_params", C.c_void_p),
+                ("lj_geometric", C.c_int), ("gb_ace", C.c_int),
+                ("gb_charge", C.c_void_p), ("gb_or", C.c_void_p), ("gb_sr", C.c_void_p),
+                ("gb_solute", C.c_double), ("gb_solvent", C.c_double)]
 
 
 def b200_adapter_available() -> bool:
@@ -206,6 +209,12 @@ def run_b200(level, system, masses, positions, velocities, displacement, params:
         nb.box[k] = float(system.box[k])
     nb.charge, nb.sigma, nb.epsilon = q.ctypes.data, sg.ctypes.data, ep.ctypes.data
     nb.exception_pairs, nb.exception_params = ex_pairs.ctypes.data, ex_par.ctypes.data
+    nb.lj_geometric = int(bool(getattr(system, "lj_geometric", False)))
+    gb = getattr(system, "gb", None)
+    if gb is not None:                      # GBSAHCTForce of the nonbonded group (system.py)
+        gq, go, gs = [np.ascontiguousarray(a, np.float64) for a in gb.device_parameters()]
+        nb.gb_charge, nb.gb_or, nb.gb_sr = gq.ctypes.data, go.ctypes.data, gs.ctypes.data
+        nb.gb_solute, nb.gb_solvent, nb.gb_ace = gb.soluteDielectric, gb.solventDielectric, int(gb.SA == "ACE")
     cp = np.ascontiguousarray(constraint_pairs if constraint_pairs is not None else np.zeros((0, 2)), np.int32)
     cd = np.ascontiguousarray(constraint_dist if constraint_dist is not None else np.zeros(0), np.float64)
     err = []

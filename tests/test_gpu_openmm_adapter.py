@@ -107,3 +107,45 @@ def test_non_equilibrium_schedule_is_written_back_to_the_integrator():
     for k in ("lambdac", "lambda1", "lambda2", "u0", "w0coeff"):
         assert got[k] == pytest.approx(ref[k], rel=1e-12, abs=1e-15), k
     assert got["work_value"] == pytest.approx(ref["work_value"], rel=1e-5, abs=1e-7)
+
+
+def test_fused_level_with_the_opls_rule_and_hct_gb_in_the_nonbonded_group():
+    """createSystem(OPLS=True, implicitSolvent=HCT): the B200NonbondedForce carries the combining rule and the
+    GBSAHCTForce parameters; the reference arm gets both from the oracles playing OpenMM's force group 2."""
+    import copy
+    from oracle import gb as G
+    case, vel, xi, fb, _ = _setup(41)
+    n = case.system.n_atoms
+    sysd = copy.copy(case.system)
+    sysd.lj_geometric, sysd.use_dispersion_correction, sysd.eps_rf = True, False, 1.0
+    rng = np.random.default_rng(3)
+    gb = S.GBSAHCTForce(SA="ACE")
+    for a in range(n):
+        gb.addParticle([sysd.charge[a], rng.uniform(0.12, 0.2), rng.uniform(0.72, 0.88)])
+    gb.finalize()
+    sysd.addForce(gb)
+    q, o, sr = gb.device_parameters()
+
+    def group2(pos):
+        r = O.nonbonded(sysd, pos, nthreads=1)
+        e, f, _ = G.hct(pos, q, o, sr)
+        return r["E"] + e, r["forces"] + f
+
+    def ref_force(groups, pos):
+        return group2(pos) if groups == 4 else (12.5, fb)
+
+    def b200_force(groups, pos):
+        return (0.0, np.zeros_like(pos)) if groups == 4 else (12.5, fb)
+
+    p = R.params_from_alch(case.alch, temperature=T, friction=GAMMA)
+    ref = R.run(case.masses, case.positions, vel, case.displacement, p, ref_force, steps=STEPS, noise=xi.ravel())
+    got = R.run_b200(0, sysd, case.masses, case.positions, vel, case.displacement, p, b200_force,
+                     steps=STEPS, noise=xi.ravel())
+    plain = R.run_b200(0, case.system, case.masses, case.positions, vel, case.displacement, p, b200_force,
+                       steps=1, noise=xi.ravel())
+    assert abs(plain["traj"][0, 1] - got["traj"][0, 1]) > 1.0        # the two additions are visible in PotEnergy
+    assert np.allclose(got["traj"][:, 0], ref["traj"][:, 0], rtol=1e-5, atol=1e-5)
+    assert np.allclose(got["traj"][:, 1], ref["traj"][:, 1], rtol=1e-5, atol=0)
+    rms = np.sqrt((ref["hybrid_force"] ** 2).sum(1).mean())
+    assert np.sqrt(((got["hybrid_force"] - ref["hybrid_force"]) ** 2).sum(1).mean()) <= 1e-4 * rms
+    assert np.abs(got["positions"] - ref["positions"]).max() < 1e-8
