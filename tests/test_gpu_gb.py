@@ -172,3 +172,56 @@ def test_plugin_surface_binds_the_gb_force_of_the_system():
     u1, e1, _ = run(sysd)
     ref = gb_reference(case, q, o, sr)
     assert (u1 - u0) == pytest.approx(ref["e2"] - ref["e1"], rel=1e-9, abs=1e-9 * abs(ref["e1"]))
+
+
+def test_device_dynamics_with_hct_gb_follow_the_reference_integrator():
+    """integrator.step(n) with the GB force in the nonbonded group: two steps of the 230-atom fixture with the
+    reference's noise against the reference's own integrator + kernels (oracle/_ref) whose force-group-2 callback is
+    the nonbonded oracle plus the GB oracle."""
+    import copy
+    from oracle import oracle as O
+    from oracle import reference as R
+    if not R.available():
+        pytest.skip("oracle/_ref is built only where /root/reference exists")
+    case = S.cfg1()
+    n = case.system.n_atoms
+    rng = np.random.default_rng(23)
+    sysd = copy.copy(case.system)
+    sysd.eps_rf = 1.0
+    gb = S.GBSAHCTForce(SA="ACE")
+    for a in range(n):
+        gb.addParticle([sysd.charge[a], rng.uniform(0.12, 0.2), rng.uniform(0.72, 0.88)])
+    gb.finalize()
+    sysd.addForce(gb)
+    q, o, sr = gb.device_parameters()
+    vel = rng.normal(scale=0.3, size=(n, 3))
+    xi = rng.normal(size=(2, n, 3))
+
+    def force_fn(groups, pos):
+        if groups == 4:
+            r = O.nonbonded(sysd, pos, nthreads=1)
+            e, f, _ = G.hct(pos, q, o, sr)
+            return r["E"] + e, r["forces"] + f
+        return 0.0, np.zeros_like(pos)
+    ref = R.run(case.masses, case.positions, vel, case.displacement,
+                R.params_from_alch(case.alch, temperature=300.0, friction=0.5), force_fn, steps=2, noise=xi.ravel())
+    integ = sdmplugin.LangevinIntegratorSDM(300.0, 0.5, case.alch.step_size, n)
+    integ.setBiasMethod(case.alch.bias_method)
+    integ.setSoftCoreMethod(case.alch.softcore_method)
+    integ.setLambda1(case.alch.lambda1); integ.setLambda2(case.alch.lambda2); integ.setAlpha(case.alch.alpha)
+    integ.setU0(case.alch.u0); integ.setW0coeff(case.alch.w0coeff)
+    integ.setUmax(case.alch.umax); integ.setUbcore(case.alch.ubcore); integ.setAcore(case.alch.acore)
+    for i in np.nonzero(np.abs(case.displacement).sum(1))[0]:
+        integ.setDisplacement(int(i), *case.displacement[i])
+    integ.bind(sysd)
+    try:
+        integ.setState(case.positions, vel, case.masses)
+        integ.step(0)
+        for k in range(2):
+            integ._ctx.md_set_noise(xi[k][None])
+            integ.step(1)
+        assert np.abs(integ.getPositions() - ref["positions"]).max() < 1e-8
+        assert integ.getBindE() == pytest.approx(ref["bind_e"], abs=1e-6)
+        assert integ.getPotEnergy() == pytest.approx(ref["pot_energy"], rel=1e-5)
+    finally:
+        integ.cleanup()

@@ -18,10 +18,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--replicas", type=int, default=1)
 ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--nstlist", type=int, default=20)
+ap.add_argument("--skin", type=float, default=-1.0)
 a = ap.parse_args()
 case = S.cfg2()
 stream = torch.cuda.current_stream()
-with SDMContext(case.system, case.displacement, n_replicas=a.replicas, nstlist=a.nstlist) as c:
+with SDMContext(case.system, case.displacement, n_replicas=a.replicas, nstlist=a.nstlist, skin=a.skin) as c:
     c.set_stream(stream.cuda_stream)
     for r in range(a.replicas):
         c.set_alchemical(r, case.alch)
@@ -51,6 +52,7 @@ with SDMContext(case.system, case.displacement, n_replicas=a.replicas, nstlist=a
     torch.cuda.synchronize()
     pair = c.last_timing()[0]
     assert c.scalars(0)["status"] == 0
+    print("skin %.2f nstlist %d " % (a.skin, a.nstlist), end="")
     print("replicas %d  ms/eval %.4f (%.0f evals/s/replica-batch)  between builds %.4f  pair kernel %.4f  units %d  env %s" % (
         a.replicas, ms, 1e3 / ms, ms_nobuild, pair, int(c.info("n_units")),
         {k: v for k, v in os.environ.items() if k.startswith("SDMB200_")}))
