@@ -37,7 +37,7 @@ struct GbState {
     int sa_ace = 1;
     double* par = nullptr;         // [n][4] charge, or, sr, ACE prefactor 28.39 (rad+0.14)^2 rad^6 (0 without SA)
     double* xs = nullptr;          // [2R][n][4] positions of system g = 2 r + state, .w = charge
-    double* born = nullptr;        // [2R][n] B
+    double* born = nullptr;        // [2R][n][2] B and 1/B
     double* dEdI = nullptr;        // [2R][n] dE/dI
     double* eatom = nullptr;       // [2R][n] energy booked on the atom
 };
@@ -52,19 +52,23 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// H(r; or_i, sr_j) of the computed value I and its derivative with respect to r
-__device__ __forceinline__ void hct_term(const double r, const double o, const double s, double* h, double* dh) {
+// H(r; or_i, sr_j) of the computed value I and its derivative with respect to r; ir = 1/r.  One division: 1/L and
+// 1/U come from the reciprocal of their product.
+__device__ __forceinline__ void hct_term(const double r, const double ir, const double o, const double s, double* h,
+                                         double* dh) {
     if (r + s - o < 0.0) { *h = 0.0; *dh = 0.0; return; }
     const double U = r + s, D = fabs(r - s);
     const bool lo = o >= D;                         // L = max(or, D)
     const double L = lo ? o : D;
     const double dL = lo ? 0.0 : (r >= s ? 1.0 : -1.0);
-    const double iL = 1.0 / L, iU = 1.0 / U, ir = 1.0 / r;
+    const double iLU = 1.0 / (L * U);
+    const double iL = iLU * U, iU = iLU * L;
     const double iL2 = iL * iL, iU2 = iU * iU;
     const double lg = log(L * iU);
-    const double a = r - s * s * ir;
+    const double s2ir = s * s * ir;
+    const double a = r - s2ir;
     *h = 0.5 * (iL - iU + 0.25 * a * (iU2 - iL2) + 0.5 * lg * ir);
-    *dh = 0.5 * (-dL * iL2 + iU2 + 0.25 * (1.0 + s * s * ir * ir) * (iU2 - iL2) +
+    *dh = 0.5 * (-dL * iL2 + iU2 + 0.25 * (1.0 + s2ir * ir) * (iU2 - iL2) +
                  0.5 * a * (dL * iL2 * iL - iU2 * iU) + 0.5 * ((dL * iL - iU) * ir - lg * ir * ir));
 }
 
@@ -91,13 +95,17 @@ gb_born_kernel(int n, const double* __restrict__ par, const double* __restrict__
     for (int j = lane; j < n; j += 32) {
         if (j == i) continue;
         const double dx = xi - X[4 * j], dy = yi - X[4 * j + 1], dz = zi - X[4 * j + 2];
-        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        const double ir = rsqrt(r2), r = r2 * ir;
         double h, dh;
-        hct_term(r, oi, par[4 * j + 2], &h, &dh);
+        hct_term(r, ir, oi, par[4 * j + 2], &h, &dh);
         I += h;
     }
     I = warp_sum(I);
-    if (lane == 0) born[(size_t)g * n + i] = 1.0 / (1.0 / oi - I);
+    if (lane == 0) {
+        const double ib = 1.0 / oi - I;
+        reinterpret_cast<double2*>(born)[(size_t)g * n + i] = make_double2(1.0 / ib, ib);
+    }
 }
 
 // Pair term at fixed Born radii: energy, force on i, dE/dB_i -> dE/dI_i; single-particle terms of atom i.
@@ -108,15 +116,17 @@ gb_pair_kernel(int n, double kp, const double* __restrict__ par, const double* _
     const int i = blockIdx.x * kGbWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31, g = blockIdx.y;
     if (i >= n) return;
     const double* X = xs + (size_t)g * n * 4;
-    const double* Bv = born + (size_t)g * n;
-    const double xi = X[4 * i], yi = X[4 * i + 1], zi = X[4 * i + 2], qi = X[4 * i + 3], Bi = Bv[i];
+    const double2* Bv = reinterpret_cast<const double2*>(born) + (size_t)g * n;   // (B, 1/B)
+    const double xi = X[4 * i], yi = X[4 * i + 1], zi = X[4 * i + 2], qi = X[4 * i + 3], Bi = Bv[i].x;
+    const double qiB = 0.25 * Bv[i].y;
     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0, dB = 0.0;
     for (int j = lane; j < n; j += 32) {
         if (j == i) continue;
         const double dx = xi - X[4 * j], dy = yi - X[4 * j + 1], dz = zi - X[4 * j + 2];
         const double r2 = dx * dx + dy * dy + dz * dz;
-        const double Bj = Bv[j], bb = Bi * Bj;
-        const double w = r2 / (4.0 * bb);
+        const double2 bj = Bv[j];
+        const double Bj = bj.x, bb = Bi * Bj;
+        const double w = r2 * (qiB * bj.y);                   // r^2 / (4 B_i B_j)
         const double ex = exp(-w);
         const double f2 = r2 + bb * ex;
         const double inv_f = rsqrt(f2);
@@ -153,11 +163,12 @@ gb_chain_kernel(int n, const double* __restrict__ par, const double* __restrict_
     for (int j = lane; j < n; j += 32) {
         if (j == i) continue;
         const double dx = xi - X[4 * j], dy = yi - X[4 * j + 1], dz = zi - X[4 * j + 2];
-        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        const double ir = rsqrt(r2), r = r2 * ir;
         double h, dh_ij, dh_ji;
-        hct_term(r, oi, par[4 * j + 2], &h, &dh_ij);
-        hct_term(r, par[4 * j + 1], si, &h, &dh_ji);
-        const double fr = -(gi * dh_ij + G[j] * dh_ji) / r;
+        hct_term(r, ir, oi, par[4 * j + 2], &h, &dh_ij);
+        hct_term(r, ir, par[4 * j + 1], si, &h, &dh_ji);
+        const double fr = -(gi * dh_ij + G[j] * dh_ji) * ir;
         fx += fr * dx; fy += fr * dy; fz += fr * dz;
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
@@ -218,7 +229,7 @@ int sdm_ctx_init_gb(sdm_ctx* c, const double* charge, const double* offset_radiu
     GB_CUDA(cudaMalloc(&G->par, sizeof(double) * par.size()));
     GB_CUDA(cudaMemcpy(G->par, par.data(), sizeof(double) * par.size(), cudaMemcpyHostToDevice));
     GB_CUDA(cudaMalloc(&G->xs, sizeof(double) * 4 * sys));
-    GB_CUDA(cudaMalloc(&G->born, sizeof(double) * sys));
+    GB_CUDA(cudaMalloc(&G->born, sizeof(double) * 2 * sys));
     GB_CUDA(cudaMalloc(&G->dEdI, sizeof(double) * sys));
     GB_CUDA(cudaMalloc(&G->eatom, sizeof(double) * sys));
     return SDM_OK;
@@ -253,8 +264,8 @@ int sdm_ctx_gb_info(sdm_ctx* c, const char* key, double* value) {
 int sdm_ctx_gb_born_radii(sdm_ctx* c, int replica, int state, double* out, cudaStream_t s) {
     GbState* G = c->gb;
     if (!G) return sdm_fail(SDM_ERR_INVALID, "HCT-GB is not switched on");
-    GB_CUDA(cudaMemcpyAsync(out, G->born + (size_t)(2 * replica + state) * G->n, sizeof(double) * G->n,
-                            cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaMemcpy2DAsync(out, sizeof(double), G->born + 2 * (size_t)(2 * replica + state) * G->n, 2 * sizeof(double),
+                              sizeof(double), G->n, cudaMemcpyDeviceToHost, s));
     GB_CUDA(cudaStreamSynchronize(s));
     return SDM_OK;
 }
