@@ -7,3 +7,5 @@ run() { echo "### compute-sanitizer $*" | tee -a $OUT; timeout 1500 compute-sani
 run --tool memcheck python -m pytest tests/test_gpu_cluster.py tests/test_gpu_restraints.py -q -x -m gpu
 run --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge.py tests/test_gpu_md.py tests/test_gpu_reference_golden.py -q -x -m gpu -k "not 100k"
 run --tool racecheck python -m pytest tests/test_gpu_restraints.py tests/test_gpu_parity.py -q -x -m gpu -k "cfg1 or restraint_energy"
+run --tool memcheck python -m pytest tests/test_gpu_gb.py tests/test_gpu_opls.py tests/test_gpu_ewald.py tests/test_gpu_pme.py -q -x -m gpu
+run --tool racecheck python -m pytest tests/test_gpu_gb.py -q -x -m gpu -k "cfg1_host_guest or own_charges"
