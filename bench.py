@@ -604,6 +604,15 @@ def main():
         resident_step()
         pair_ms.append(ctx.last_timing()[0])
     torch.cuda.synchronize()
+    # diagnostic: the same kernel with every resident block it can have (the production launch leaves room on each SM
+    # for the displaced-atom kernels that run beside it)
+    ctx.set_timing(2)
+    pair_full_ms = []
+    for k in range(max(5, args.steps // 4)):
+        flush.zero_()
+        resident_step()
+        pair_full_ms.append(ctx.last_timing()[0])
+    torch.cuda.synchronize()
     ctx.set_timing(False)
     sampler.stop_flag = True
     if world > 1:
@@ -796,7 +805,12 @@ def main():
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json)" % pk["source"],
                 "peak_fma_measured_in_this_run": fma_measured, "frac_of_measured_fma_peak": achieved / fma_measured if fma_measured else None,
                 "algorithmic_pairs_per_launch": algo_pairs, "flop_per_pair": FLOP_PER_PAIR[int(case.system.method)],
-                "kernel_ms": pair_ms_avg, "kernel_share_of_step": pair_ms_avg * args.steps / t_ms}
+                "kernel_ms": pair_ms_avg, "kernel_share_of_step": pair_ms_avg * args.steps / t_ms,
+                "kernel_launch": "as in production: for this batch 20 of the 24 possible resident blocks per SM, the rest of the "
+                                 "register file is left to the FP64 displaced-atom kernels that run beside it; timed here with "
+                                 "those kernels behind it (events on the launching stream)",
+                "kernel_ms_full_residency": float(np.mean(pair_full_ms)),
+                "frac_full_residency": achieved * pair_ms_avg / float(np.mean(pair_full_ms)) / peak}
 
     line = {"metric": "SDM dual-state force evals/s", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -254,7 +254,10 @@ int sdm_get_pairs(sdm_ctx* ctx, int replica, int32_t* pairs, int64_t max_pairs, 
 /* Launch statistics since creation (own kernels only) and device time of the last eval. */
 int sdm_get_launch_count(sdm_ctx* ctx, int64_t* n_launches);
 /* Device time (ms) spent in the pair kernel during the last sdm_eval() that had timing
- * enabled; enable with sdm_set_timing(ctx, 1) (adds two cudaEventRecord per eval). */
+ * enabled; enable with sdm_set_timing(ctx, 1) (adds two cudaEventRecord per eval; the displaced-atom kernels then
+ * follow the pair kernel instead of running beside it).  The kernel is launched as in production -- for large
+ * batches with room left on every SM for the displaced-atom kernels; sdm_set_timing(ctx, 2) times it with every
+ * resident block it can have instead (a diagnostic: that launch is not what an evaluation runs). */
 int sdm_set_timing(sdm_ctx* ctx, int enabled);
 int sdm_get_last_timing(sdm_ctx* ctx, float* pair_ms, float* total_ms);
 /* Algorithmic work of the last eval, summed over replicas: in-cutoff pairs evaluated. */

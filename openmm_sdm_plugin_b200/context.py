@@ -228,7 +228,8 @@ class SDMContext:
         _lib.check(self._L.sdm_get_launch_count(self._h, C.byref(n)))
         return n.value
 
-    def set_timing(self, enabled: bool):
+    def set_timing(self, enabled):
+        """True / 1: time the pair kernel as launched in production; 2: with every resident block it can have."""
         _lib.check(self._L.sdm_set_timing(self._h, int(enabled)))
 
     def last_timing(self):

@@ -595,7 +595,7 @@ static void enqueue_position_only(sdm_ctx* c, cudaStream_t s) {
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;
     if (T.n_lig > 0 && c->pair_mode == SDM_PAIR_CLUSTER) {
-        sdm::launch_ligand_probe_list(T, B, s);   // candidates were laid down at the list build
+        sdm::launch_ligand_probe_list(T, B, c->num_sms, s);   // candidates were laid down at the list build
         c->launches += 1;
     } else if (T.n_lig > 0) {
         sdm::launch_ligand_filter(T, B, s);
@@ -1155,6 +1155,7 @@ int sdm_set_timing(sdm_ctx* c, int enabled) {
     SDM_ON_CTX_DEVICE(c);
     if (!c) return fail(SDM_ERR_INVALID, "null context");
     c->timing = enabled != 0;
+    c->timing_full_residency = enabled == 2;
     c->timing_valid = false;
     c->graph_valid = false;
     return SDM_OK;

@@ -6,6 +6,9 @@
 // Reference behaviour restated (never copied): LangevinIntegratorSDM.cpp:153-183 (sequence),
 // ReferenceSDMKernels.cpp:161-199 (state copies), :202-318 (execute), OpenMM 7.3 Reference
 // NonbondedForce arithmetic.
+#include <algorithm>
+#include <cstdlib>
+
 #include "sdm_kernels.h"
 
 namespace sdm {
@@ -646,6 +649,68 @@ ligand_probe_list_kernel(const __grid_constant__ Topology T, const __grid_consta
     probe_finish(T, B, P, A, pos, m, r, s_red, s_redl);
 }
 
+// The same work sized to run BESIDE the persistent pair kernel.  One 512-thread block of the kernel above holds
+// 50 k registers: while it is resident the pair kernel gets a quarter of that SM, so at 16 replicas (608 rows, four
+// waves) the displaced-atom kernels cost the evaluation their whole duration (measured: 44 us of 280).  Here a few
+// small blocks (three per SM, 64 threads = 4.6 k registers each) walk the rows with a grid stride and the pair kernel leaves
+// them the room (launch_pair_rows' reserve): both run at the same time, the FP64 latency chains of these rows in the
+// shadow of the FP32 pipe.
+// Summation order, independent of the block size (a replica must give the same bits in every batch size): hits in
+// chunks of 32 consecutive candidates -- lane = hit % 32, butterfly per chunk -- then the other displaced atoms as
+// further chunks; thread 0 adds the chunk sums in chunk order.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+ligand_probe_rows_kernel(const __grid_constant__ Topology T, const __grid_constant__ EvalBuffers B, const int rows,
+                         const int max_chunks) {
+    extern __shared__ double s_chunk[];                 // [max_chunks][4] sums, then [max_chunks][2] counts
+    long long* s_cnt = reinterpret_cast<long long*>(s_chunk + 4 * (size_t)max_chunks);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n = T.n;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int r = row / T.n_lig, m = row - r * T.n_lig;
+        const double* pos = B.pos + (size_t)r * 3 * n;
+        const ProbeAtom P = load_probe_atom(T, pos, m);
+        const int* cand = B.cand + (size_t)row * (size_t)B.pairf_cap;
+        double* pf_out = B.pairf + (size_t)row * (size_t)B.pairf_cap * 3;
+        const int total = B.cand_count[row];
+        if (total > B.pairf_cap && threadIdx.x == 0) atomicExch(B.flags + r, SDM_ERR_CAPACITY);
+        const int cnt = min(total, B.pairf_cap);
+        const int nch1 = (cnt + 31) >> 5, nch = min(nch1 + ((T.n_lig + 31) >> 5), max_chunks);
+        for (int ch = warp; ch < nch; ch += THREADS / 32) {
+            ProbeAcc A{0, 0, 0, 0, 0, 0};
+            double px, py, pz;
+            if (ch < nch1) {
+                const int h = ch * 32 + lane;
+                if (h < cnt) {
+                    probe_pair(T, pos, P, cand[h], (P.flags & 1) != 0, A, px, py, pz);
+                    pf_out[3 * (size_t)h] = -px; pf_out[3 * (size_t)h + 1] = -py; pf_out[3 * (size_t)h + 2] = -pz;
+                }
+            } else {
+                const int mm = (ch - nch1) * 32 + lane;
+                if (mm < T.n_lig) probe_pair(T, pos, P, T.lig_idx[mm], true, A, px, py, pz);
+            }
+            const double sx = warp_sum(A.fx), sy = warp_sum(A.fy), sz = warp_sum(A.fz), su = warp_sum(A.u);
+            const long long sc1 = warp_sum_ll(A.c1), sc2 = warp_sum_ll(A.c2);
+            if (lane == 0) {
+                s_chunk[4 * ch] = sx; s_chunk[4 * ch + 1] = sy; s_chunk[4 * ch + 2] = sz; s_chunk[4 * ch + 3] = su;
+                s_cnt[2 * ch] = sc1; s_cnt[2 * ch + 1] = sc2;
+            }
+        }
+        __syncthreads();
+        // one thread per quantity, chunks in order
+        if (threadIdx.x < 4) {
+            double v = 0.0;
+            for (int ch = 0; ch < nch; ch++) v += s_chunk[4 * ch + threadIdx.x];
+            if (threadIdx.x < 3) B.dF[(size_t)r * 3 * n + 3 * P.i + threadIdx.x] = v;
+            else B.upart[row] = v;
+        } else if (threadIdx.x < 6) {
+            long long v = 0;
+            for (int ch = 0; ch < nch; ch++) v += s_cnt[2 * ch + (threadIdx.x - 4)];
+            B.mcnt[(size_t)row * 2 + (threadIdx.x - 4)] = v;
+        }
+        __syncthreads();
+    }
+}
+
 // All-pairs path, small systems (a few hundred atoms, hundreds of replicas): ONE WARP per (displaced atom,
 // replica) instead of a block -- lane = scan index of the current bitmap word, hit index = running prefix +
 // popcount below the lane: no block barriers, no search for the n-th set bit, eight rows per block.  Same
@@ -1046,10 +1111,36 @@ void launch_ligand_compact(const Topology& T, const EvalBuffers& B, cudaStream_t
     ligand_compact_kernel<<<grid, kCompactThreads, 0, s>>>(T, B);
 }
 
-void launch_ligand_probe_list(const Topology& T, const EvalBuffers& B, cudaStream_t s) {
+int ligand_rows_beside_pair_kernel(const Topology& T, const EvalBuffers& B, int num_sms) {
+    static const int force = getenv("SDMB200_SIDE_SMALL") ? atoi(getenv("SDMB200_SIDE_SMALL")) : -1;   // development knob
+    if (force >= 0) return force;
+    // enough rows to occupy the small blocks, and a pair pass long enough to hide them (at low occupancy the rows
+    // take about three times as long as in the one-block-per-row kernel)
+    return (T.n_lig * B.R >= 2 * num_sms && T.n >= 200 * T.n_lig) ? 1 : 0;
+}
+
+void launch_ligand_probe_list(const Topology& T, const EvalBuffers& B, int num_sms, cudaStream_t s) {
     if (T.n_lig <= 0) return;
-    dim3 grid(T.n_lig, B.R);
-    ligand_probe_list_kernel<<<grid, kProbeThreads, 0, s>>>(T, B);
+    const int rows = T.n_lig * B.R;
+    const int max_chunks = (B.pairf_cap + 31) / 32 + (T.n_lig + 31) / 32;
+    const size_t smem = (size_t)max_chunks * (4 * sizeof(double) + 2 * sizeof(long long));
+    if (smem > 200 * 1024) {   // absurd capacities: the one-block-per-row kernel has no such table
+        dim3 grid(T.n_lig, B.R);
+        ligand_probe_list_kernel<<<grid, kProbeThreads, 0, s>>>(T, B);
+        return;
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(ligand_probe_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(ligand_probe_rows_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    if (ligand_rows_beside_pair_kernel(T, B, num_sms)) {
+        static const int per_sm = getenv("SDMB200_SIDE_BLOCKS") ? std::max(1, atoi(getenv("SDMB200_SIDE_BLOCKS"))) : 3;
+        ligand_probe_rows_kernel<64><<<std::min(rows, num_sms * per_sm), 64, smem, s>>>(T, B, rows, max_chunks);
+    } else {
+        ligand_probe_rows_kernel<512><<<rows, 512, smem, s>>>(T, B, rows, max_chunks);
+    }
 }
 
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s) {

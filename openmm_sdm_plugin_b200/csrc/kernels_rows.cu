@@ -699,7 +699,7 @@ refresh_kernel(Topology T, nbl::Grid G, const int* __restrict__ d_nslot, const d
 
 void launch_pair_rows(const Topology& T, const PairListView& V, const double* pos_all,
                       long long* f1acc, double* epart, long long* cpart, int exact,
-                      int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s) {
+                      int* unit_counter, int num_sms, const PairEmit* emit, int reserve, cudaStream_t s) {
     if (V.nrunits_ub <= 0) return;
     // the counter is zero when an evaluation starts (the mix kernel of the previous one put it back);
     // the debug launch stands outside that cycle
@@ -716,7 +716,7 @@ void launch_pair_rows(const Topology& T, const PairListView& V, const double* po
                 resident = SDM_ROW_MINB;                                                          \
             if (const char* e_ = getenv("SDMB200_PAIR_RESIDENT")) resident = std::max(1, atoi(e_)); \
         }                                                                                         \
-        const int grid = std::min((V.nrunits_ub + kWarps - 1) / kWarps, num_sms * resident);       \
+        const int grid = std::min((V.nrunits_ub + kWarps - 1) / kWarps, num_sms * std::max(1, resident - reserve));       \
         pair_row_kernel<N, P, X, E, W, G><<<grid, kWarps * 32, 0, s>>>(T, V, pos_all, f1acc, epart, cpart, \
                                                                    unit_counter, em);             \
     } while (0)

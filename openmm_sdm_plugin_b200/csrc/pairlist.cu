@@ -1307,8 +1307,15 @@ int sdm_ctx_pairlist_launch(sdm_ctx* c) {
     cudaStream_t s = c->stream;
     // ev[1]..ev[2] bracket the pair kernel alone (list build and refresh are outside)
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[1], s));
+    // large batches: the displaced-atom rows run beside this kernel in small blocks; leave them the registers of
+    // four resident blocks per SM: 20 x 2 560 + 3 x 4 608 registers fit one SM, so every pair block is resident from
+    // the start and the space the row blocks free goes to the gather and exceptions kernels that follow them, not to
+    // late pair blocks (with a smaller reserve those take it and the side chain ends up behind the pair kernel).
+    // The same grid when the pair kernel is timed alone: what is measured is what runs.
+    static const int reserve_blocks = getenv("SDMB200_PAIR_RESERVE") ? atoi(getenv("SDMB200_PAIR_RESERVE")) : 4;
+    const int reserve = (sdm::ligand_rows_beside_pair_kernel(c->T, c->B, c->num_sms) && !c->timing_full_residency) ? reserve_blocks : 0;
     launch_pair_rows(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
-                     pl->unit_counter, c->num_sms, nullptr, s);
+                     pl->unit_counter, c->num_sms, nullptr, reserve, s);
     if (c->timing) PL_CUDA(cudaEventRecord(c->ev[2], s));
     c->launches++;
     PL_CUDA(cudaGetLastError());
@@ -1322,7 +1329,7 @@ int sdm_ctx_pairlist_emit(sdm_ctx* c, int replica, int* d_counter, int* d_pairs,
     // its forces to the accumulators a second time; they are cleared before the next evaluation.
     const PairEmit em{d_counter, d_pairs, cap, replica};
     launch_pair_rows(c->T, make_view(c), c->d_pos, c->B.f1acc, pl->epart, pl->cpart, c->opt.exact_cutoff,
-                     pl->unit_counter, c->num_sms, &em, c->stream);
+                     pl->unit_counter, c->num_sms, &em, 0, c->stream);
     PL_CUDA(cudaMemsetAsync(pl->unit_counter, 0, sizeof(int), c->stream));
     PL_CUDA(cudaMemsetAsync(c->B.f1acc, 0, sizeof(long long) * 3 * (size_t)pl->nslot_cap, c->stream));
     PL_CUDA(cudaStreamSynchronize(c->stream));

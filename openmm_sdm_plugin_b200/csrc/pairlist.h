@@ -48,7 +48,7 @@ struct PairEmit {
 };
 void launch_pair_rows(const Topology& T, const PairListView& V, const double* pos_all,
                       long long* f1acc, double* epart, long long* cpart, int exact,
-                      int* unit_counter, int num_sms, const PairEmit* emit, cudaStream_t s);
+                      int* unit_counter, int num_sms, const PairEmit* emit, int reserve, cudaStream_t s);
 
 // Per-eval refresh of the sorted positions from the current double positions (same periodic
 // image as at build time) + staleness check against the build-time positions; max_disp2 (may be

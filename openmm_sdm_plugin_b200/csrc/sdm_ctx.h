@@ -103,6 +103,7 @@ struct sdm_ctx {
     int64_t launches = 0;
     int64_t n_evals = 0;
     bool timing = false, timing_valid = false;
+    bool timing_full_residency = false;  // sdm_set_timing(ctx, 2): the pair kernel timed with every resident block it can have
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -73,7 +73,9 @@ void launch_ligand_probe(const Topology& T, const EvalBuffers& B, cudaStream_t s
 void launch_ligand_filter(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 void launch_ligand_gather(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 void launch_ligand_compact(const Topology& T, const EvalBuffers& B, cudaStream_t s);      // list build: bitmap -> candidates
-void launch_ligand_probe_list(const Topology& T, const EvalBuffers& B, cudaStream_t s);   // per eval, from the candidates
+void launch_ligand_probe_list(const Topology& T, const EvalBuffers& B, int num_sms, cudaStream_t s);   // per eval, from the candidates
+// 1: the displaced-atom rows run in small blocks beside the pair kernel, which leaves them room (large batches)
+int ligand_rows_beside_pair_kernel(const Topology& T, const EvalBuffers& B, int num_sms);
 void launch_exceptions(const Topology& T, const EvalBuffers& B, cudaStream_t s);
 int exceptions_num_blocks(int n_exceptions);
 // e_scale / c_div: 0.5 / 2 when every pair was visited from both sides (all-pairs), 1 / 1 for a
