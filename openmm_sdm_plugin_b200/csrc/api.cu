@@ -946,9 +946,27 @@ int sdm_eval(sdm_ctx* c) {
                 cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0);
                 // side work first: its (small) grids are dispatched ahead of the persistent pair
                 // kernel, whose blocks then fill every slot that is or becomes free
+                static const bool side_timing = getenv("SDMB200_SIDE_TIMING") != nullptr;   // development knob (no graph)
+                static cudaEvent_t sev[4] = {nullptr, nullptr, nullptr, nullptr};
+                if (side_timing && !capturing) {
+                    if (!sev[0]) for (auto& e : sev) cudaEventCreate(&e);
+                    else {
+                        float side_ms = 0.f, pair_ms = 0.f, lag = 0.f;
+                        cudaEventSynchronize(sev[1]); cudaEventSynchronize(sev[3]);
+                        cudaEventElapsedTime(&side_ms, sev[0], sev[1]);
+                        cudaEventElapsedTime(&pair_ms, sev[2], sev[3]);
+                        cudaEventElapsedTime(&lag, sev[3], sev[1]);
+                        fprintf(stderr, "side chain %.1f us  pair kernel %.1f us  side ends %.1f us after the pair kernel\n",
+                                1e3 * side_ms, 1e3 * pair_ms, 1e3 * lag);
+                    }
+                    cudaEventRecord(sev[0], c->side_stream);
+                }
                 enqueue_position_only(c, c->side_stream);
+                if (side_timing && !capturing) cudaEventRecord(sev[1], c->side_stream);
                 cudaEventRecord(c->ev_join, c->side_stream);
+                if (side_timing && !capturing) cudaEventRecord(sev[2], s);
                 rc = sdm_ctx_pairlist_launch(c);
+                if (side_timing && !capturing) cudaEventRecord(sev[3], s);
                 cudaStreamWaitEvent(s, c->ev_join, 0);
             } else {
                 rc = sdm_ctx_pairlist_launch(c);  // records ev[1], ev[2] around the pair kernel when timing
