@@ -384,7 +384,7 @@ def cfg3_leg(case, args, world, rank, device, stream, rounds=6, steps_per_round=
         e0.record(stream)
         for k in range(rounds):
             c.md_step(steps_per_round)
-            u_local = [c.scalars(r)["u_sc"] for r in range(Rl)]
+            u_local = [x["u_sc"] for x in c.read_results(None)]   # one read-back for all replicas of the rank
             if world > 1:
                 u_all, s_all = X.all_gather_replica_info(u_local, state_of, counts=counts)
             else:

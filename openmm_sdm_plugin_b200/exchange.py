@@ -14,6 +14,8 @@ AlchemicalState of the ladder they run) is permuted.  One round =
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 from .system import ILOGISTIC, LINEAR, QUADRATIC, AlchemicalState
@@ -52,21 +54,27 @@ def exchange_round(u_sc, state_of_replica, states, temperature, seed, round_inde
     n = len(state_of)
     if sorted(state_of.tolist()) != sorted(set(state_of.tolist())):
         raise ValueError("two replicas hold the same state")
-    M = reduced_energy_matrix(u_sc, states, temperature)
+    M = reduced_energy_matrix(u_sc, states, temperature).tolist()
     rng = np.random.Generator(np.random.Philox(key=[int(seed) & (2**64 - 1), int(round_index)]))
     n_sweeps = n * n if n_sweeps is None else n_sweeps
+    # all random numbers of the round up front (one pair and one uniform per proposal, used or not), then a plain
+    # Python loop over lists: the sweep is sequential by nature but costs ~0.4 us per proposal this way instead of
+    # ~10 us with one generator call per proposal -- it sits between two dynamics segments on every rank
+    pairs = rng.integers(0, n, size=(n_sweeps, 2)).tolist()
+    unif = rng.random(n_sweeps).tolist()
+    st = state_of.tolist()
     proposed = accepted = 0
-    for _ in range(n_sweeps):
-        i, j = rng.integers(0, n, size=2)
+    for (i, j), x in zip(pairs, unif):
         if i == j:
             continue
-        si, sj = state_of[i], state_of[j]
+        si, sj = st[i], st[j]
         # swap the states of replicas i and j: delta = [W_sj(u_i) + W_si(u_j)] - [W_si(u_i) + W_sj(u_j)]
-        delta = (M[i, sj] + M[j, si]) - (M[i, si] + M[j, sj])
+        delta = (M[i][sj] + M[j][si]) - (M[i][si] + M[j][sj])
         proposed += 1
-        if delta <= 0.0 or rng.random() < np.exp(-delta):
-            state_of[i], state_of[j] = sj, si
+        if delta <= 0.0 or (delta < 745.0 and x < math.exp(-delta)):
+            st[i], st[j] = sj, si
             accepted += 1
+    state_of = np.array(st, dtype=np.int64)
     if stats is not None:
         stats["proposed"] = stats.get("proposed", 0) + proposed
         stats["accepted"] = stats.get("accepted", 0) + accepted
