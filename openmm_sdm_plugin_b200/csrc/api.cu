@@ -919,6 +919,7 @@ int sdm_eval(sdm_ctx* c) {
             return SDM_OK;
         }
         if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[0], s));
+        B.side_concurrent = s != nullptr ? 1 : 0;   // (timing mode keeps the production launch of the pair kernel)
         bool capturing = false;
         int64_t launches0 = c->launches;
         if (graphable) {
