@@ -594,6 +594,21 @@ int sdm_invalidate_list(sdm_ctx* c) {
 static void enqueue_position_only(sdm_ctx* c, cudaStream_t s) {
     const sdm::Topology& T = c->T;
     sdm::EvalBuffers& B = c->B;
+    // development knob (with SDMB200_SIDE_TIMING, outside graph capture): where the side chain spends its time
+    static const bool stage_timing = getenv("SDMB200_SIDE_TIMING") != nullptr;
+    static cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (stage_timing) cudaStreamIsCapturing(s, &cap);
+    const bool stages = stage_timing && cap == cudaStreamCaptureStatusNone;
+    if (stages) {
+        if (!pev[0]) for (auto& e : pev) cudaEventCreate(&e);
+        else if (cudaEventSynchronize(pev[3]) == cudaSuccess) {
+            float a = 0.f, b = 0.f, d = 0.f;
+            cudaEventElapsedTime(&a, pev[0], pev[1]); cudaEventElapsedTime(&b, pev[1], pev[2]); cudaEventElapsedTime(&d, pev[2], pev[3]);
+            fprintf(stderr, "  rows %.1f us  gather %.1f us  exceptions %.1f us\n", 1e3 * a, 1e3 * b, 1e3 * d);
+        }
+        cudaEventRecord(pev[0], s);
+    }
     if (T.n_lig > 0 && c->pair_mode == SDM_PAIR_CLUSTER) {
         sdm::launch_ligand_probe_list(T, B, c->num_sms, s);   // candidates were laid down at the list build
         c->launches += 1;
@@ -602,8 +617,11 @@ static void enqueue_position_only(sdm_ctx* c, cudaStream_t s) {
         sdm::launch_ligand_probe(T, B, s);
         c->launches += 2;
     }
+    if (stages) cudaEventRecord(pev[1], s);
     sdm::launch_ligand_gather(T, B, s);   // per-atom gather of the displaced-atom pair forces
+    if (stages) cudaEventRecord(pev[2], s);
     sdm::launch_exceptions(T, B, s);      // after the probe kernel: adds to dF of displaced 1-4 pairs
+    if (stages) cudaEventRecord(pev[3], s);
     c->launches += 2;
     sdm_ctx_pme_enqueue(c, s);            // reciprocal-space PME of both states (when switched on)
     sdm_ctx_gb_enqueue(c, s);             // HCT-GB + ACE of both states (when switched on)
@@ -919,7 +937,6 @@ int sdm_eval(sdm_ctx* c) {
             return SDM_OK;
         }
         if (c->timing) SDM_CUDA(cudaEventRecord(c->ev[0], s));
-        B.side_concurrent = s != nullptr ? 1 : 0;   // (timing mode keeps the production launch of the pair kernel)
         bool capturing = false;
         int64_t launches0 = c->launches;
         if (graphable) {
