@@ -1114,7 +1114,6 @@ void launch_ligand_compact(const Topology& T, const EvalBuffers& B, cudaStream_t
 int ligand_rows_beside_pair_kernel(const Topology& T, const EvalBuffers& B, int num_sms) {
     static const int force = getenv("SDMB200_SIDE_SMALL") ? atoi(getenv("SDMB200_SIDE_SMALL")) : -1;   // development knob
     if (force >= 0) return force;
-    if (!B.side_concurrent) return 0;   // legacy default stream: no side stream, the kernels follow one another
     // enough rows to occupy the small blocks, and a pair pass long enough to hide them (at low occupancy the rows
     // take about three times as long as in the one-block-per-row kernel)
     return (T.n_lig * B.R >= 2 * num_sms && T.n >= 200 * T.n_lig) ? 1 : 0;

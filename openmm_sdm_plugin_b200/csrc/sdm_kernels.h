@@ -59,7 +59,6 @@ struct EvalBuffers {
     int* cand;               // [R][n_lig][pairf_cap] resting atom (System index) of hit h
     int* cand_count;         // [R][n_lig] hits of the row (may exceed pairf_cap: overflow)
     int* list_age;           // device: evals since the cluster-pair list was built (0: no list)
-    int side_concurrent;     // 1: the position-only kernels run on the side stream beside the pair kernel (set per evaluation)
 };
 
 // ---- fused path, v0 (all-pairs tiles, System order) ------------------------------------------
