@@ -140,6 +140,16 @@ public:
         }
         displDirty = false;
     }
+    // The GBSAHCTForce the reference's reader adds to the nonbonded force group for implicitSolvent=HCT
+    // (example/desmonddmsfile75.py:454-465): evaluated in both states from now on.  Per-particle parameters as the
+    // CustomGBForce holds them (charge may be null: the NonbondedForce charges; or = radius - 0.009, sr = scale * or).
+    void addImplicitSolventHCT(const double* charge, const double* offsetRadius, const double* scaledRadius,
+                               double soluteDielectric = 1.0, double solventDielectric = 78.5, bool surfaceAreaACE = true) {
+        if (!ctx) throw SDMException("the integrator is not bound to a context: call bind(system) first");
+        if (sdm_enable_hct_gb(ctx, charge, offsetRadius, scaledRadius, soluteDielectric, solventDielectric,
+                              surfaceAreaACE ? 1 : 0) != SDM_OK)
+            throw SDMException(sdm_last_error());
+    }
     void cleanup() {
         if (ctx) sdm_destroy(ctx);
         ctx = nullptr;

@@ -40,6 +40,9 @@ int main() {
     threw = false;
     try { g.step(1); } catch (const SDMPlugin::SDMException&) { threw = true; }
     CHECK(threw);
+    threw = false;   // implicit solvent needs a bound context as well
+    try { g.addImplicitSolventHCT(nullptr, x.data(), x.data()); } catch (const SDMPlugin::SDMException&) { threw = true; }
+    CHECK(threw);
     if (sdm_device_count() == 0) {
         // no CPU fallback: binding must fail loudly
         std::vector<double> q(4, 0.1), sg(4, 0.3), ep(4, 0.5);
@@ -64,6 +67,17 @@ int main() {
         std::vector<double> force(3 * n);
         h.evaluate(pos.data(), nullptr, 0.0, force.data());
         const double pe0 = h.getPotEnergy();
+        {   // implicit solvent on a second integrator: the GB energy of both states enters PotEnergy / BindE
+            SDMPlugin::LangevinIntegratorSDM gb(300.0, 1.0, 0.001, n);
+            gb.setDisplacement(3, 1.0, 0.0, 0.0);
+            gb.bind(s);
+            std::vector<double> orad = {0.15, 0.16, 0.11, 0.14}, srad = {0.12, 0.13, 0.09, 0.11}, fgb(3 * n);
+            gb.addImplicitSolventHCT(nullptr, orad.data(), srad.data());
+            gb.evaluate(pos.data(), nullptr, 0.0, fgb.data());
+            CHECK(std::isfinite(gb.getPotEnergy()) && std::fabs(gb.getPotEnergy() - pe0) > 1.0);
+            CHECK(std::fabs(gb.getBindE() - h.getBindE()) > 1e-6);
+            gb.cleanup();
+        }
         threw = false;
         try { h.step(1); } catch (const SDMPlugin::SDMException&) { threw = true; }   // no masses yet
         CHECK(threw);
