@@ -9,3 +9,8 @@ run --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_edg
 run --tool racecheck python -m pytest tests/test_gpu_restraints.py tests/test_gpu_parity.py -q -x -m gpu -k "cfg1 or restraint_energy"
 run --tool memcheck python -m pytest tests/test_gpu_gb.py tests/test_gpu_opls.py tests/test_gpu_ewald.py tests/test_gpu_pme.py -q -x -m gpu
 run --tool racecheck python -m pytest tests/test_gpu_gb.py -q -x -m gpu -k "cfg1_host_guest or own_charges"
+# the displaced-atom rows kernels (block-per-row with 512 threads and the small persistent blocks): memcheck over the cluster
+# tests with the small-block launch forced on, racecheck over the tiny cluster-path case in both launches
+SDMB200_SIDE_SMALL=1 run --tool memcheck python -m pytest tests/test_gpu_cluster.py -q -x -m gpu
+SDMB200_SIDE_SMALL=1 run --tool racecheck python -m pytest tests/test_gpu_edge.py -q -x -m gpu -k "tiny_ragged or three_displacement_groups"
+run --tool racecheck python -m pytest tests/test_gpu_edge.py -q -x -m gpu -k "tiny_ragged"
