@@ -364,7 +364,9 @@ int sdm_enable_reciprocal_pme(sdm_ctx* ctx, const int32_t* grid);
  * 28.3919551 (radius + 0.14)^2 (radius/B)^6.  Refused (SDM_ERR_INVALID) for periodic methods. */
 int sdm_enable_hct_gb(sdm_ctx* ctx, const double* charge, const double* offset_radius, const double* scaled_radius,
                       double solute_dielectric, double solvent_dielectric, int sa_ace);
-/* Born radii B_i of state 1 or 2 (x or x + d) of one replica in the last evaluation; synchronises. */
+/* Born radii B_i of state 1 or 2 (x or x + d) of one replica in the last evaluation (zeros before the first one);
+ * synchronises.  HCT has no guard against 1/or - I <= 0 for deeply buried atoms (neither has OpenMM's expression): such
+ * a configuration gives a negative or infinite radius and non-finite energies, which show up in sdm_scalars as they are. */
 int sdm_get_born_radii(sdm_ctx* ctx, int replica, int state, double* radii);
 
 /* ---- restraint forces of SDMUtils (the SDMUtils part) -------------------------------

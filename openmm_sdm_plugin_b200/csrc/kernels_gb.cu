@@ -230,6 +230,7 @@ int sdm_ctx_init_gb(sdm_ctx* c, const double* charge, const double* offset_radiu
     GB_CUDA(cudaMemcpy(G->par, par.data(), sizeof(double) * par.size(), cudaMemcpyHostToDevice));
     GB_CUDA(cudaMalloc(&G->xs, sizeof(double) * 4 * sys));
     GB_CUDA(cudaMalloc(&G->born, sizeof(double) * 2 * sys));
+    GB_CUDA(cudaMemset(G->born, 0, sizeof(double) * 2 * sys));   // sdm_get_born_radii before the first evaluation: zeros
     GB_CUDA(cudaMalloc(&G->dEdI, sizeof(double) * sys));
     GB_CUDA(cudaMalloc(&G->eatom, sizeof(double) * sys));
     return SDM_OK;
