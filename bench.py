@@ -12,6 +12,13 @@ buffers (H2D of positions and D2H of forces + scalars inside the timed region).
 Multi-GPU: one process per GPU (torchrun), replicas sharded by rank, no data-path collective
 (weak scaling: R replicas per GPU); the only collective is the (u_sc, state) all-gather that a
 replica-exchange round needs, exercised once per step outside the kernel timing.
+
+Other keys of the line (rank 0): `roofline` (pair kernel as an evaluation launches it, timed with CUDA events in this
+run; `*_full_residency` = the same kernel with every resident block it can have, a diagnostic), `single_lambda`
+(BASELINE.json configs[1]: one resident replica -- static evaluations with the headline list parameters and with
+parameters sized for one replica, and the replica alone in the device MD loop), `md_loop` / `md_loop_pme` (constrained
+dynamics on the device, measured ns/day), `cfg3` (22 windows under replica exchange, dealt over the ranks), `sweep`
+(cfg1, cfg1 + HCT-GB, cfg2 with PME, cfg4, cfg5 sizes), `roofline_elementwise`, `cpu_baseline`.
 """
 from __future__ import annotations
 
